@@ -1,0 +1,238 @@
+/* rcb200.h — C ABI of librcb200.so: the B200-native (sm_100a) ESN hot path of
+ * SciML/ReservoirComputing.jl v0.12.35.
+ *
+ * The reference is 100 % Julia and has no FFI for this path; its extension points
+ * are multiple-dispatch hooks.  Each entry point below names the reference function it replaces
+ * (paths relative to the reference tree).  Julia reaches these with `ccall` (see INTEGRATION.md,
+ * reservoircomputing.jl_b200/julia/RCB200.jl); the in-tree tests and bench reach them with ctypes.
+ *
+ * Conventions
+ *  - every function returns an rcb_status (0 = ok, <0 = error class); nothing throws across the
+ *    boundary; `rcb_last_error()` returns the thread-local message of the last failure.  Error
+ *    classes map 1:1 onto the exception types the reference raises for the same condition
+ *    (ArgumentError / DimensionMismatch), so a shim can re-raise them.
+ *  - all matrices are COLUMN-MAJOR (Julia layout), features x time: element (f,t) of an F x T
+ *    matrix is p[f + ld*t].  Batched arrays put the sequence index slowest: element (f,t,b) of an
+ *    F x T x B array is p[f + F*(t + T*b)], i.e. one reference-layout F x T matrix per sequence.
+ *  - data pointers may be HOST pointers (pageable or pinned) or DEVICE pointers of the context's
+ *    GPU; the library classifies each pointer with cudaPointerGetAttributes and stages host data
+ *    through its own pinned buffers.  Weight/descriptor pointers are host pointers.
+ *  - there is NO CPU fallback: every compute entry point fails with RCB_ERR_CUDA when no sm_100
+ *    device is usable.
+ *  - a handle is bound to one context (one GPU, one stream); calls on one handle are serialised
+ *    by the caller (the reference is single-threaded); distinct contexts may be driven from
+ *    distinct host threads / processes (one process per GPU under torch.distributed).
+ */
+#ifndef RCB200_H
+#define RCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCB_VERSION 100 /* 0.1.0 */
+#define RCB_API __attribute__((visibility("default")))
+
+typedef enum {
+  RCB_OK = 0,
+  RCB_ERR_ARGUMENT = -1,    /* Julia ArgumentError   */
+  RCB_ERR_DIMENSION = -2,   /* Julia DimensionMismatch */
+  RCB_ERR_CUDA = -3,        /* CUDA runtime / no usable device */
+  RCB_ERR_NUMERIC = -4,     /* solver failure (train.jl:194-196) or non-finite values (inits_components.jl:99-111) */
+  RCB_ERR_UNSUPPORTED = -5, /* configuration outside the hot-path scope */
+  RCB_ERR_ALLOC = -6
+} rcb_status;
+
+typedef enum { RCB_F32 = 0, RCB_F64 = 1 } rcb_dtype;
+
+/* activation ids: src/layers/esn_cell.jl:129 (tanh_fast default), src/models/esn.jl:95 (tanh) */
+typedef enum {
+  RCB_ACT_IDENTITY = 0,
+  RCB_ACT_TANH = 1,
+  RCB_ACT_TANH_FAST = 2, /* NNlib.tanh_fast: evaluated as accurate tanh (parity unpinned upstream) */
+  RCB_ACT_SIGMOID = 3,
+  RCB_ACT_RELU = 4
+} rcb_activation;
+
+/* state modifiers: src/states.jl:73-88 (Pad), :205-217 (NLAT1), :277-289 (NLAT2), :349-361 (NLAT3),
+ * :404-421 (PartialSquare), :466-473 (ExtendedSquare) */
+typedef enum {
+  RCB_MOD_NLAT1 = 1,
+  RCB_MOD_NLAT2 = 2,
+  RCB_MOD_NLAT3 = 3,
+  RCB_MOD_PAD = 4,            /* param = padding value */
+  RCB_MOD_PARTIAL_SQUARE = 5, /* param = eta */
+  RCB_MOD_EXTENDED_SQUARE = 6
+} rcb_modifier;
+
+#define RCB_MAX_MODIFIERS 8
+#define RCB_MAX_LAYERS 8
+
+/* One ESNCell + its state_modifiers (src/layers/esn_cell.jl:114-148, src/models/esn.jl:93-106,
+ * src/models/esn_deep.jl:102-147). */
+typedef struct {
+  int32_t res_dims;       /* N_l */
+  int32_t activation;     /* rcb_activation */
+  int32_t use_bias;       /* esn_cell.jl:129 */
+  int32_t leak_is_vector; /* 0: scalar leak_scalar; 1: per-neuron vector set by rcb_esn_set_leak_vector */
+  double leak_scalar;     /* leak_coefficient, esn_cell.jl:131 */
+  int32_t n_modifiers;
+  int32_t modifier_kind[RCB_MAX_MODIFIERS];
+  double modifier_param[RCB_MAX_MODIFIERS];
+} rcb_layer_desc;
+
+/* ESN (n_layers == 1) / DeepESN (n_layers > 1) + LinearReadout (src/layers/basic.jl:129-182). */
+typedef struct {
+  int32_t n_layers;
+  int32_t in_dims;
+  int32_t out_dims;
+  int32_t readout_activation; /* rcb_activation, default identity */
+  int32_t readout_use_bias;
+  int32_t data_dtype;         /* rcb_dtype of input data == eltype of collected states (reservoircomputer.jl:123) */
+} rcb_esn_desc;
+
+typedef struct rcb_ctx rcb_ctx;
+typedef struct rcb_esn rcb_esn;
+
+/* ---- library / context -------------------------------------------------------------------- */
+RCB_API int32_t rcb_version(void);
+RCB_API const char* rcb_last_error(void);
+RCB_API int32_t rcb_device_count(int32_t* count);
+/* One context = one GPU + one stream.  `cuda_stream` NULL -> the library creates its own stream;
+ * otherwise a cudaStream_t of the same process (e.g. torch.cuda.current_stream().cuda_stream). */
+RCB_API int32_t rcb_ctx_create(int32_t device, void* cuda_stream, rcb_ctx** out);
+RCB_API int32_t rcb_ctx_destroy(rcb_ctx* ctx);
+RCB_API int32_t rcb_ctx_synchronize(rcb_ctx* ctx);
+/* number of kernel launches of this library issued on the context since creation (bench: gpu_launches) */
+RCB_API int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches);
+/* device time [ms] between the first and last kernel of the most recent data-path call, measured
+ * with CUDA events on the context's stream (bench: roofline.achieved) */
+RCB_API int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms);
+#define RCB_TIMER_RECURRENCE 0 /* K1 / K4 */
+#define RCB_TIMER_GRAM 1       /* K2 */
+#define RCB_TIMER_SOLVE 2      /* K3 */
+
+/* ---- model handle: replaces ESN / DeepESN + LuxCore.setup parameter hand-off ------------------
+ * src/models/esn.jl:93-106, src/models/esn_deep.jl:102-147, src/reservoircomputer.jl:51-63 */
+RCB_API int32_t rcb_esn_create(rcb_ctx* ctx, const rcb_esn_desc* desc, const rcb_layer_desc* layers, rcb_esn** out);
+RCB_API int32_t rcb_esn_destroy(rcb_esn* esn);
+/* F = feature dims of the last layer after its modifiers (Pad: +1, ExtendedSquare: x2) */
+RCB_API int32_t rcb_esn_feature_dims(const rcb_esn* esn, int32_t* F);
+/* sum over layers of N_l: rows of the packed hidden-state ("carry") array */
+RCB_API int32_t rcb_esn_carry_dims(const rcb_esn* esn, int32_t* sumN);
+
+/* ps.reservoir.{reservoir_matrix,input_matrix,bias} (src/layers/esn_cell.jl:150-159).
+ * Dense hand-off: what rand_sparse returns by default (a dense Matrix with zeros,
+ * src/inits/inits_reservoir.jl:55-67).  W is N x N, W_in is N x d_in_l (d_in_l = in_dims for layer 0,
+ * N_{l-1}-after-modifiers for deeper layers), bias is N or NULL. */
+RCB_API int32_t rcb_esn_set_weights_dense(rcb_esn* esn, int32_t layer, const float* W, int64_t ldw,
+                                  const float* W_in, int64_t ldwin, const float* bias);
+/* CSC hand-off: SparseMatrixCSC{Float32,Int64} fields as Julia stores them (1-based colptr/rowval),
+ * what return_sparse=true yields (ext/RCSparseArraysExt.jl:5-7). */
+RCB_API int32_t rcb_esn_set_weights_csc(rcb_esn* esn, int32_t layer, const int64_t* colptr, const int64_t* rowval,
+                                const float* nzval, const float* W_in, int64_t ldwin, const float* bias);
+RCB_API int32_t rcb_esn_set_leak_vector(rcb_esn* esn, int32_t layer, const float* leak);
+/* Canonical CSR the kernels were built from (0-based, columns ascending) — for the bit-exact
+ * sparsity-pattern parity check. */
+RCB_API int32_t rcb_esn_csr_nnz(const rcb_esn* esn, int32_t layer, int64_t* nnz);
+RCB_API int32_t rcb_esn_export_csr(const rcb_esn* esn, int32_t layer, int64_t* rowptr, int32_t* colind, float* vals);
+/* Host-only format conversion (no GPU needed): the same dense / CSC -> canonical CSR routine the
+ * handle uses.  Call once with rowptr = colind = vals = NULL to get *nnz, then again with arrays of
+ * n+1 / nnz / nnz entries.  Entries with W[i,j] == 0 are dropped for the dense form (what
+ * SparseArrays.sparse keeps); stored entries of a CSC are kept as they are.  NaN/Inf ->
+ * RCB_ERR_NUMERIC (check_inf_nan, src/inits/inits_components.jl:99-111). */
+RCB_API int32_t rcb_csr_from_dense(const float* W, int64_t ldw, int32_t n, int64_t* nnz, int64_t* rowptr,
+                                   int32_t* colind, float* vals);
+RCB_API int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n,
+                                 int64_t* nnz, int64_t* rowptr, int32_t* colind, float* vals);
+/* Ensemble members (BASELINE config 5): sequence b of a batched call uses W*w_scale[b] and
+ * leak[b] instead of the layer's own (layer 0 only).  NULL clears. */
+RCB_API int32_t rcb_esn_set_member_params(rcb_esn* esn, int64_t B, const float* w_scale, const float* leak);
+
+/* ps.readout.{weight,bias}: addreadout! (src/reservoircomputer.jl:137-144).  W is out_dims x F
+ * (column-major, ld = out_dims), always handed over in Float64 (the default ridge eltype,
+ * src/train.jl:126-129); bias is out_dims or NULL.  n_members > 1: one readout per sequence. */
+RCB_API int32_t rcb_esn_set_readout(rcb_esn* esn, const double* W, const double* bias, int64_t n_members);
+
+/* ---- K1: collectstates -------------------------------------------------------------------------
+ * Replaces __collectstates (src/reservoircomputer.jl:113-133) and collectstates(::DeepESN)
+ * (src/models/esn_deep.jl:261-291), i.e. T steps of ESNCell (src/layers/esn_cell.jl:175-184) +
+ * __apply_seq of the state modifiers (src/reservoircomputer.jl:72-79), for B independent sequences.
+ *   u          d_in x T x B   input data (dtype = desc.data_dtype)
+ *   h0         sumN x B       initial hidden states per layer, stacked (NULL -> zeros).  The
+ *                             reference draws this from init_state on the first call
+ *                             (esn_cell.jl:169-173); here it is an explicit input.
+ *   states_out F x T x B      collected (modified) states, or NULL to skip materialisation
+ *   hT_out     sumN x B       final carries (un-modified h_T) — copied back into st.…carry by the shim
+ * Errors: T < 1 -> RCB_ERR_ARGUMENT (reservoircomputer.jl:65-70). */
+RCB_API int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, const void* h0,
+                    void* states_out, void* hT_out);
+
+/* ---- K2+K3: ridge readout fit ------------------------------------------------------------------
+ * Replaces __fit_readout(::RidgeRegression, states, targets) (src/train.jl:100-198): the
+ * least-squares solution of [Z'; sqrt(λ) I] W' = [Y'; 0], computed as the FP64 Cholesky solve of
+ * (Z Z' + λ I) W' = Z Y' (the Gram form the reference's own tests use as cross-check,
+ * test/test_train_ridge.jl:18-27).
+ *   states  F x S (ld = ld_states), targets d_out x S (ld = ld_targets), dtype each RCB_F32/RCB_F64
+ *   W_out   d_out x F Float64 (ld = d_out)
+ *   gram_mode: RCB_GRAM_AUTO / RCB_GRAM_FP64 (exact products, FP64 accumulate) /
+ *              RCB_GRAM_TENSOR (tcgen05 3xTF32, FP32 accumulate in TMEM, FP64 flush)
+ * Errors (train.jl:113-134): S_states != S_targets -> RCB_ERR_DIMENSION (caller checks and passes
+ * both counts); S < 1 -> RCB_ERR_ARGUMENT; λ < 0 -> RCB_ERR_ARGUMENT; not positive definite ->
+ * RCB_ERR_NUMERIC (train.jl:194-196). */
+#define RCB_GRAM_AUTO 0
+#define RCB_GRAM_FP64 1
+#define RCB_GRAM_TENSOR 2
+RCB_API int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S_states,
+                        int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out,
+                        int64_t S_targets, int64_t ld_targets, double lambda, int32_t gram_mode,
+                        double* W_out);
+
+/* Streaming Gram accumulator (partial Grams per GPU, summed by the caller's all-reduce — SURVEY §8e):
+ *   GC is a DEVICE or HOST buffer of F x (F + d_out) Float64: [G | C] with G = Σ z z', C = Σ z y'. */
+RCB_API int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S,
+                            int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out,
+                            int64_t ld_targets, int32_t gram_mode, int32_t zero_first, double* GC);
+/* Solve (G + λ I) W' = C from a packed [G | C]; only the lower triangle of G is read. */
+RCB_API int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
+
+/* ---- train: collect -> washout -> ridge -> addreadout! ------------------------------------------
+ * Replaces train (src/train.jl:232-251) with __apply_washout (:36-47).  Pooled readout over the B
+ * sequences.  targets: d_out x T x B (dtype = targets_dtype).  W_out: d_out x F Float64 (also
+ * installed in the handle, like addreadout!).  states_out (post-washout layout is the caller's
+ * business: the full F x T x B array is returned) and hT_out may be NULL.
+ * Errors: washout < 0 or washout >= T -> RCB_ERR_ARGUMENT (train.jl:37-43). */
+RCB_API int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                  int64_t washout, double lambda, int32_t gram_mode, const void* h0, double* W_out,
+                  void* states_out, void* hT_out);
+/* Same, but stops before the solve and leaves the packed partial [G | C] (F x (F+d_out) Float64) in
+ * GC (host or device) so that ranks can all-reduce it (one process per GPU) and call rcb_ridge_solve. */
+RCB_API int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
+                          int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* GC,
+                          void* hT_out);
+
+/* ---- K4: predict --------------------------------------------------------------------------------
+ * Teacher-forced: replaces __predict(reservoir, rc, data::AbstractMatrix, ps, st)
+ * (src/predict.jl:163-177): y_t = readout(modifiers(cell(u_t))).  u: d_in x T x B.
+ * y_out: out_dims x T x B Float64 (W_out is Float64 after the default train, so the reference's
+ * outputs are Float64).  h: sumN x B carried in and out (NULL -> zeros, not written back). */
+RCB_API int32_t rcb_predict_teacher(rcb_esn* esn, const void* u, int64_t T, int64_t B, void* h_inout, double* y_out);
+/* Autoregressive: replaces __autoregressive_predict (src/predict.jl:74-88): y_1 = model(u0),
+ * y_{t+1} = model(y_t).  u0: in_dims x B (dtype = desc.data_dtype).  compute_dtype RCB_F64 follows
+ * the reference's silent promotion to Float64 (Float64 W_out feeds back, esn_cell.jl:176); RCB_F32
+ * keeps the recurrence in Float32 (readout accumulated in Float64).
+ * Errors: steps < 1 -> RCB_ERR_ARGUMENT (predict.jl:75); out_dims != in_dims -> RCB_ERR_DIMENSION
+ * (predict.jl:62-72). */
+RCB_API int32_t rcb_predict_autoregressive(rcb_esn* esn, const void* u0, int64_t steps, int64_t B, int32_t compute_dtype,
+                                   void* h_inout, double* y_out);
+
+/* ---- standalone modifier pass (matrix form of src/states.jl, __apply_tomatrix :1-15) ----------- */
+RCB_API int32_t rcb_apply_modifiers(rcb_ctx* ctx, int32_t n_modifiers, const int32_t* kinds, const double* params,
+                            const void* x, int32_t dtype, int64_t n, int64_t cols, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCB200_H */

@@ -1,0 +1,864 @@
+// C-ABI of librcb200.so (declared in include/rcb200.h): contexts, model handles, and the host
+// orchestration of collect / fit_readout / train / predict.  Everything numeric runs in the
+// CUDA kernels of recurrence.cu, dense_kernels.cu, gram_tensor.cu and solve.cu; there is no CPU
+// compute path in this library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "rcb_internal.h"
+
+namespace rcb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      RCB_CUDA(cudaFree(ctx->scratch[slot]));
+      ctx->scratch[slot] = nullptr;
+      ctx->scratch_bytes[slot] = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->scratch[slot];
+  return RCB_OK;
+}
+
+int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->pinned_bytes < bytes) {
+    if (ctx->pinned) {
+      RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      RCB_CUDA(cudaFreeHost(ctx->pinned));
+      ctx->pinned = nullptr;
+      ctx->pinned_bytes = 0;
+    }
+    cudaError_t e = cudaMallocHost(&ctx->pinned, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RCB_ERR_ALLOC, "cudaMallocHost of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->pinned_bytes = bytes;
+  }
+  *out = ctx->pinned;
+  return RCB_OK;
+}
+
+int32_t to_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return RCB_OK;
+  RCB_CUDA(cudaMemcpyAsync(dst, src, bytes, is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  return RCB_OK;
+}
+
+int32_t from_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return RCB_OK;
+  RCB_CUDA(cudaMemcpyAsync(dst, src, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  return RCB_OK;
+}
+
+// Timers: a pool of event pairs per phase, summed on query, reset at the start of each data-path call.
+struct TimerPool {
+  std::vector<cudaEvent_t> beg, end;
+  int used = 0;
+};
+static TimerPool* pools(rcb_ctx* ctx) { return reinterpret_cast<TimerPool*>(ctx->timer_pools); }
+
+void timer_begin(rcb_ctx* ctx, int which) {
+  TimerPool& p = pools(ctx)[which];
+  if (p.used == (int)p.beg.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    p.beg.push_back(a);
+    p.end.push_back(b);
+  }
+  cudaEventRecord(p.beg[p.used], ctx->stream);
+}
+void timer_end(rcb_ctx* ctx, int which) {
+  TimerPool& p = pools(ctx)[which];
+  cudaEventRecord(p.end[p.used], ctx->stream);
+  p.used++;
+}
+static void timers_reset(rcb_ctx* ctx) {
+  for (int i = 0; i < 3; ++i) pools(ctx)[i].used = 0;
+}
+
+// resolve a host-or-device input into a device pointer (copying host data into a scratch slot)
+static int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, const void** dev) {
+  if (!p) { *dev = nullptr; return RCB_OK; }
+  if (is_device_ptr(p)) { *dev = p; return RCB_OK; }
+  void* d = nullptr;
+  RCB_TRY(ctx_scratch(ctx, slot, bytes, &d));
+  RCB_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *dev = d;
+  return RCB_OK;
+}
+
+static void free_layer(Layer& L) {
+  cudaFree(L.sell.perm); cudaFree(L.sell.blk_off); cudaFree(L.sell.blk_w2); cudaFree(L.sell.vals); cudaFree(L.sell.cols);
+  cudaFree(L.d_Win); cudaFree(L.d_bias); cudaFree(L.d_leak);
+  L.sell = DevSell{};
+  L.d_Win = L.d_bias = L.d_leak = nullptr;
+}
+
+template <typename V>
+static int32_t upload(const std::vector<V>& h, V** d) {
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(V);
+  cudaError_t e = cudaMalloc((void**)d, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RCB_ERR_ALLOC, "cudaMalloc of %zu bytes failed", bytes); }
+  if (!h.empty()) RCB_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+  return RCB_OK;
+}
+
+static int esn_nthreads(const rcb_esn* e) {
+  int nmax = 32;
+  for (const Layer& L : e->layers) nmax = std::max(nmax, L.n);
+  int nt = (nmax + 31) / 32 * 32;
+  return nt > 1024 ? 1024 : nt;
+}
+
+static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, int64_t ldwin, const float* bias) {
+  Layer& L = esn->layers[(size_t)layer];
+  if (!W_in) return fail(RCB_ERR_ARGUMENT, "input_matrix pointer is NULL");
+  if (ldwin < L.n) return fail(RCB_ERR_DIMENSION, "input_matrix leading dimension %lld < res_dims=%d", (long long)ldwin, L.n);
+  if (L.desc.use_bias && !bias) return fail(RCB_ERR_ARGUMENT, "layer %d has use_bias=true but bias is NULL", layer);
+  RCB_CUDA(cudaSetDevice(esn->ctx->device));
+  free_layer(L);
+  HostSell hs;
+  RCB_TRY(sell_from_csr(L.csr, esn_nthreads(esn), &hs));
+  L.sell.n = hs.n; L.sell.nthreads = hs.nthreads; L.sell.R = hs.R; L.sell.nwarps = hs.nwarps;
+  L.sell.total_pairs = (int64_t)hs.vals.size() / 32;
+  RCB_TRY(upload(hs.perm, &L.sell.perm));
+  RCB_TRY(upload(hs.blk_off, &L.sell.blk_off));
+  RCB_TRY(upload(hs.blk_w2, &L.sell.blk_w2));
+  RCB_TRY(upload(hs.vals, &L.sell.vals));
+  RCB_TRY(upload(hs.cols, &L.sell.cols));
+  const int npos = hs.R * hs.nthreads;
+  std::vector<float> winp((size_t)npos * L.d_in, 0.f);
+  for (int d = 0; d < L.d_in; ++d)
+    for (int p = 0; p < npos; ++p) {
+      const uint16_t r = hs.perm[(size_t)p];
+      if (r != 0xFFFF) {
+        const float v = W_in[(size_t)d * ldwin + r];
+        if (v != v || v - v != 0.f) return fail(RCB_ERR_NUMERIC, "input_matrix contains invalid values (NaN/Inf)");
+        winp[(size_t)d * npos + p] = v;
+      }
+    }
+  RCB_TRY(upload(winp, &L.d_Win));
+  if (L.desc.use_bias) {
+    std::vector<float> b(bias, bias + L.n);
+    RCB_TRY(upload(b, &L.d_bias));
+  }
+  L.weights_set = true;
+  return RCB_OK;
+}
+
+static int32_t check_layer(const rcb_esn* esn, int32_t layer) {
+  if (!esn) return fail(RCB_ERR_ARGUMENT, "esn handle is NULL");
+  if (layer < 0 || layer >= (int32_t)esn->layers.size())
+    return fail(RCB_ERR_ARGUMENT, "layer index %d out of range 0:%d", layer, (int)esn->layers.size() - 1);
+  return RCB_OK;
+}
+
+static int32_t check_ready(const rcb_esn* esn) {
+  if (!esn) return fail(RCB_ERR_ARGUMENT, "esn handle is NULL");
+  for (size_t l = 0; l < esn->layers.size(); ++l) {
+    if (!esn->layers[l].weights_set) return fail(RCB_ERR_ARGUMENT, "weights of layer %d have not been set", (int)l);
+    if (esn->layers[l].desc.leak_is_vector && !esn->layers[l].d_leak)
+      return fail(RCB_ERR_ARGUMENT, "layer %d declares a vector leak_coefficient but rcb_esn_set_leak_vector was not called", (int)l);
+  }
+  return RCB_OK;
+}
+
+// One pass of all layers over `Bc` sequences x `Tc` steps (device pointers).  `states` receives the
+// last layer's modified states (F x Tc x Bc) or is nullptr.  h: packed sumN x Bc carry, in/out.
+static int32_t collect_device(rcb_esn* esn, const void* u_dev, int64_t Tc, int64_t Bc, const void* h0_dev, void* states,
+                              void* hT_dev, int64_t member_off) {
+  rcb_ctx* ctx = esn->ctx;
+  const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4;
+  const int nl = (int)esn->layers.size();
+  const void* zin = nullptr;  // modified states of the previous layer
+  int c_off = 0;
+  for (int l = 0; l < nl; ++l) {
+    Layer& L = esn->layers[(size_t)l];
+    const bool last = l == nl - 1;
+    const bool fus = chain_is_fusable(L.chain);
+    CollectArgs a;
+    a.layer = &L; a.dtype = esn->desc.data_dtype; a.T = Tc; a.B = Bc;
+    a.h_stride = esn->sumN; a.h_off = c_off;
+    a.h0 = h0_dev; a.hT = hT_dev;
+    if (l == 0) {
+      a.u = u_dev;
+      if (esn->member_count) {
+        a.member_scale = esn->d_member_scale + member_off;
+        a.member_leak = esn->d_member_leak + member_off;
+      }
+    } else {
+      if (esn->desc.data_dtype != RCB_F32)
+        return fail(RCB_ERR_UNSUPPORTED, "DeepESN collectstates is implemented for Float32 data");
+      const int npos = L.sell.R * L.sell.nthreads;
+      void* P = nullptr;
+      RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)npos * Tc * Bc * sizeof(float), &P));
+      RCB_TRY(launch_input_projection(ctx, L.d_Win, npos, L.d_in, (const float*)zin, Tc * Bc, (float*)P));
+      a.pre_in = P;
+    }
+    void* zout = nullptr;
+    if (last) {
+      zout = states;
+    } else {
+      // ping-pong the inter-layer state buffers between two scratch slots
+      RCB_TRY(ctx_scratch(ctx, (l & 1) ? SCR_Y : SCR_TMP2, (size_t)L.feat * Tc * Bc * esz, &zout));
+    }
+    if (fus || !zout) {
+      a.states = zout;
+      RCB_TRY(launch_collect(ctx, a));
+    } else {
+      void* raw = nullptr;
+      RCB_TRY(ctx_scratch(ctx, SCR_RAW, (size_t)L.n * Tc * Bc * esz, &raw));
+      a.states = raw; a.raw_states = true;
+      RCB_TRY(launch_collect(ctx, a));
+      RCB_TRY(launch_modifiers(ctx, L.chain, raw, esn->desc.data_dtype, L.n, Tc * Bc, zout));
+    }
+    zin = zout;
+    c_off += L.n;
+  }
+  return RCB_OK;
+}
+
+}  // namespace rcb
+
+using namespace rcb;
+
+extern "C" {
+
+int32_t rcb_version(void) { return RCB_VERSION; }
+const char* rcb_last_error(void) { return g_err; }
+
+int32_t rcb_device_count(int32_t* count) {
+  if (!count) return fail(RCB_ERR_ARGUMENT, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return fail(RCB_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_create(int32_t device, void* cuda_stream, rcb_ctx** out) {
+  if (!out) return fail(RCB_ERR_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(RCB_ERR_CUDA, "no usable CUDA device (%s); librcb200 has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(RCB_ERR_ARGUMENT, "device %d out of range 0:%d", device, n - 1);
+  RCB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RCB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RCB_ERR_CUDA, "device %d (%s) is sm_%d%d; librcb200 is built for sm_100a (B200) only", device, prop.name, prop.major, prop.minor);
+  rcb_ctx* ctx = new (std::nothrow) rcb_ctx();
+  if (!ctx) return fail(RCB_ERR_ALLOC, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cuda_stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    RCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  ctx->timer_pools = new TimerPool[3];
+  *out = ctx;
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_destroy(rcb_ctx* ctx) {
+  if (!ctx) return RCB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  TimerPool* p = pools(ctx);
+  for (int i = 0; i < 3; ++i)
+    for (size_t k = 0; k < p[i].beg.size(); ++k) { cudaEventDestroy(p[i].beg[k]); cudaEventDestroy(p[i].end[k]); }
+  delete[] p;
+  for (int i = 0; i < SCR_COUNT; ++i) cudaFree(ctx->scratch[i]);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_synchronize(rcb_ctx* ctx) {
+  if (!ctx) return fail(RCB_ERR_ARGUMENT, "ctx is NULL");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches) {
+  if (!ctx || !launches) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *launches = ctx->launches;
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms) {
+  if (!ctx || !ms) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (which < 0 || which > 2) return fail(RCB_ERR_ARGUMENT, "unknown timer %d", which);
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  TimerPool& p = pools(ctx)[which];
+  float total = 0.f;
+  for (int i = 0; i < p.used; ++i) {
+    RCB_CUDA(cudaEventSynchronize(p.end[i]));
+    float t = 0.f;
+    RCB_CUDA(cudaEventElapsedTime(&t, p.beg[i], p.end[i]));
+    total += t;
+  }
+  *ms = total;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_create(rcb_ctx* ctx, const rcb_esn_desc* desc, const rcb_layer_desc* layers, rcb_esn** out) {
+  if (!ctx || !desc || !layers || !out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (desc->n_layers < 1 || desc->n_layers > RCB_MAX_LAYERS)
+    return fail(RCB_ERR_ARGUMENT, "n_layers must be in 1:%d, got %d", RCB_MAX_LAYERS, desc->n_layers);
+  if (desc->in_dims < 1 || desc->out_dims < 1) return fail(RCB_ERR_ARGUMENT, "in_dims and out_dims must be ≥ 1");
+  if (desc->data_dtype != RCB_F32 && desc->data_dtype != RCB_F64) return fail(RCB_ERR_ARGUMENT, "unknown data_dtype %d", desc->data_dtype);
+  rcb_esn* e = new (std::nothrow) rcb_esn();
+  if (!e) return fail(RCB_ERR_ALLOC, "out of host memory");
+  e->ctx = ctx;
+  e->desc = *desc;
+  int prev = desc->in_dims;
+  for (int l = 0; l < desc->n_layers; ++l) {
+    const rcb_layer_desc& d = layers[l];
+    if (d.res_dims < 1) { delete e; return fail(RCB_ERR_ARGUMENT, "res_dims of layer %d must be ≥ 1", l); }
+    if (d.n_modifiers < 0 || d.n_modifiers > RCB_MAX_MODIFIERS) { delete e; return fail(RCB_ERR_ARGUMENT, "layer %d: n_modifiers out of range", l); }
+    Layer L;
+    L.desc = d;
+    L.n = d.res_dims;
+    L.d_in = prev;
+    L.chain.n = d.n_modifiers;
+    for (int i = 0; i < d.n_modifiers; ++i) {
+      if (d.modifier_kind[i] < RCB_MOD_NLAT1 || d.modifier_kind[i] > RCB_MOD_EXTENDED_SQUARE) {
+        delete e;
+        return fail(RCB_ERR_ARGUMENT, "layer %d: unknown state modifier id %d", l, d.modifier_kind[i]);
+      }
+      L.chain.kind[i] = d.modifier_kind[i];
+      L.chain.param[i] = d.modifier_param[i];
+    }
+    L.feat = (int32_t)chain_feature_dims(L.n, L.chain);
+    prev = L.feat;
+    e->sumN += L.n;
+    e->layers.push_back(L);
+  }
+  e->feat = prev;
+  *out = e;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_destroy(rcb_esn* esn) {
+  if (!esn) return RCB_OK;
+  cudaSetDevice(esn->ctx->device);
+  cudaStreamSynchronize(esn->ctx->stream);
+  for (Layer& L : esn->layers) free_layer(L);
+  cudaFree(esn->d_Wout); cudaFree(esn->d_bout); cudaFree(esn->d_member_scale); cudaFree(esn->d_member_leak);
+  delete esn;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_feature_dims(const rcb_esn* esn, int32_t* F) {
+  if (!esn || !F) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *F = esn->feat;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_carry_dims(const rcb_esn* esn, int32_t* sumN) {
+  if (!esn || !sumN) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *sumN = esn->sumN;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_set_weights_dense(rcb_esn* esn, int32_t layer, const float* W, int64_t ldw, const float* W_in,
+                                  int64_t ldwin, const float* bias) {
+  RCB_TRY(check_layer(esn, layer));
+  Layer& L = esn->layers[(size_t)layer];
+  RCB_TRY(csr_from_dense(W, ldw, L.n, &L.csr));
+  return install_weights(esn, layer, W_in, ldwin, bias);
+}
+
+int32_t rcb_esn_set_weights_csc(rcb_esn* esn, int32_t layer, const int64_t* colptr, const int64_t* rowval,
+                                const float* nzval, const float* W_in, int64_t ldwin, const float* bias) {
+  RCB_TRY(check_layer(esn, layer));
+  Layer& L = esn->layers[(size_t)layer];
+  RCB_TRY(csr_from_csc(colptr, rowval, nzval, L.n, &L.csr));
+  return install_weights(esn, layer, W_in, ldwin, bias);
+}
+
+int32_t rcb_esn_set_leak_vector(rcb_esn* esn, int32_t layer, const float* leak) {
+  RCB_TRY(check_layer(esn, layer));
+  if (!leak) return fail(RCB_ERR_ARGUMENT, "leak pointer is NULL");
+  Layer& L = esn->layers[(size_t)layer];
+  if (!L.desc.leak_is_vector) return fail(RCB_ERR_DIMENSION, "layer %d was created with a scalar leak_coefficient", layer);
+  RCB_CUDA(cudaSetDevice(esn->ctx->device));
+  cudaFree(L.d_leak);
+  L.d_leak = nullptr;
+  std::vector<float> v(leak, leak + L.n);
+  return upload(v, &L.d_leak);
+}
+
+int32_t rcb_esn_csr_nnz(const rcb_esn* esn, int32_t layer, int64_t* nnz) {
+  RCB_TRY(check_layer(esn, layer));
+  if (!nnz) return fail(RCB_ERR_ARGUMENT, "nnz is NULL");
+  const Layer& L = esn->layers[(size_t)layer];
+  *nnz = L.csr.rowptr.empty() ? 0 : L.csr.rowptr.back();
+  return RCB_OK;
+}
+
+int32_t rcb_esn_export_csr(const rcb_esn* esn, int32_t layer, int64_t* rowptr, int32_t* colind, float* vals) {
+  RCB_TRY(check_layer(esn, layer));
+  const Layer& L = esn->layers[(size_t)layer];
+  if (L.csr.rowptr.empty()) return fail(RCB_ERR_ARGUMENT, "weights of layer %d have not been set", layer);
+  if (rowptr) memcpy(rowptr, L.csr.rowptr.data(), L.csr.rowptr.size() * sizeof(int64_t));
+  if (colind) memcpy(colind, L.csr.colind.data(), L.csr.colind.size() * sizeof(int32_t));
+  if (vals) memcpy(vals, L.csr.vals.data(), L.csr.vals.size() * sizeof(float));
+  return RCB_OK;
+}
+
+static int32_t csr_out(const HostCsr& c, int64_t* nnz, int64_t* rowptr, int32_t* colind, float* vals) {
+  if (nnz) *nnz = c.rowptr.back();
+  if (rowptr) memcpy(rowptr, c.rowptr.data(), c.rowptr.size() * sizeof(int64_t));
+  if (colind) memcpy(colind, c.colind.data(), c.colind.size() * sizeof(int32_t));
+  if (vals) memcpy(vals, c.vals.data(), c.vals.size() * sizeof(float));
+  return RCB_OK;
+}
+
+int32_t rcb_csr_from_dense(const float* W, int64_t ldw, int32_t n, int64_t* nnz, int64_t* rowptr, int32_t* colind,
+                           float* vals) {
+  if (n < 1) return fail(RCB_ERR_ARGUMENT, "n must be ≥ 1");
+  HostCsr c;
+  RCB_TRY(csr_from_dense(W, ldw, n, &c));
+  return csr_out(c, nnz, rowptr, colind, vals);
+}
+
+int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n, int64_t* nnz,
+                         int64_t* rowptr, int32_t* colind, float* vals) {
+  if (n < 1) return fail(RCB_ERR_ARGUMENT, "n must be ≥ 1");
+  HostCsr c;
+  RCB_TRY(csr_from_csc(colptr, rowval, nzval, n, &c));
+  return csr_out(c, nnz, rowptr, colind, vals);
+}
+
+int32_t rcb_esn_set_member_params(rcb_esn* esn, int64_t B, const float* w_scale, const float* leak) {
+  if (!esn) return fail(RCB_ERR_ARGUMENT, "esn handle is NULL");
+  RCB_CUDA(cudaSetDevice(esn->ctx->device));
+  cudaFree(esn->d_member_scale); cudaFree(esn->d_member_leak);
+  esn->d_member_scale = esn->d_member_leak = nullptr;
+  esn->member_count = 0;
+  if (!w_scale && !leak) return RCB_OK;
+  if (B < 1 || !w_scale || !leak) return fail(RCB_ERR_ARGUMENT, "member params need B ≥ 1 and both w_scale and leak");
+  std::vector<float> s(w_scale, w_scale + B), l(leak, leak + B);
+  RCB_TRY(upload(s, &esn->d_member_scale));
+  RCB_TRY(upload(l, &esn->d_member_leak));
+  esn->member_count = B;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_set_readout(rcb_esn* esn, const double* W, const double* bias, int64_t n_members) {
+  if (!esn || !W) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (n_members < 1) return fail(RCB_ERR_ARGUMENT, "n_members must be ≥ 1");
+  if (esn->desc.readout_use_bias && !bias) return fail(RCB_ERR_ARGUMENT, "readout has use_bias=true but bias is NULL");
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(esn->d_Wout); cudaFree(esn->d_bout);
+  esn->d_Wout = esn->d_bout = nullptr;
+  const size_t wn = (size_t)n_members * esn->desc.out_dims * esn->feat;
+  RCB_CUDA(cudaMalloc((void**)&esn->d_Wout, wn * sizeof(double)));
+  RCB_CUDA(cudaMemcpy(esn->d_Wout, W, wn * sizeof(double), is_device_ptr(W) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  if (esn->desc.readout_use_bias) {
+    const size_t bn = (size_t)n_members * esn->desc.out_dims;
+    RCB_CUDA(cudaMalloc((void**)&esn->d_bout, bn * sizeof(double)));
+    RCB_CUDA(cudaMemcpy(esn->d_bout, bias, bn * sizeof(double), is_device_ptr(bias) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  }
+  esn->readout_members = n_members;
+  return RCB_OK;
+}
+
+int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, const void* h0, void* states_out, void* hT_out) {
+  RCB_TRY(check_ready(esn));
+  if (!u) return fail(RCB_ERR_ARGUMENT, "data pointer is NULL");
+  if (T < 1) return fail(RCB_ERR_ARGUMENT, "collectstates data must have at least one column, got %lld.", (long long)T);
+  if (B < 1) return fail(RCB_ERR_ARGUMENT, "batch must have at least one sequence, got %lld.", (long long)B);
+  if (esn->member_count && esn->member_count != B)
+    return fail(RCB_ERR_DIMENSION, "member params were set for %lld sequences, got B=%lld", (long long)esn->member_count, (long long)B);
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4;
+  const void* u_dev = nullptr;
+  const void* h0_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)esn->desc.in_dims * T * B * esz, &u_dev));
+  RCB_TRY(stage_in(ctx, SCR_H, h0, (size_t)esn->sumN * B * esz, &h0_dev));
+  void* st_dev = nullptr;
+  const size_t st_bytes = (size_t)esn->feat * T * B * esz;
+  if (states_out) {
+    if (is_device_ptr(states_out)) st_dev = states_out;
+    else RCB_TRY(ctx_scratch(ctx, SCR_STATES, st_bytes, &st_dev));
+  }
+  void* hT_dev = nullptr;
+  const size_t h_bytes = (size_t)esn->sumN * B * esz;
+  if (hT_out) {
+    if (is_device_ptr(hT_out)) hT_dev = hT_out;
+    else RCB_TRY(ctx_scratch(ctx, SCR_TGT, h_bytes, &hT_dev));
+  }
+  RCB_TRY(collect_device(esn, u_dev, T, B, h0_dev, st_dev, hT_dev, 0));
+  if (states_out && st_dev != states_out) RCB_TRY(from_device(ctx, states_out, st_dev, st_bytes));
+  if (hT_out && hT_dev != hT_out) RCB_TRY(from_device(ctx, hT_out, hT_dev, h_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+// [G | C] += over the sample set; GC device, F x (F + d_out), lower triangle of G only.
+static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt,
+                           int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq, int32_t gram_mode,
+                           double* GC) {
+  (void)gram_mode;
+  timer_begin(ctx, RCB_TIMER_GRAM);
+  GramArgs g;
+  g.A = Z; g.a_dtype = zdt; g.M = F; g.lda = ldz; g.Bm = Z; g.b_dtype = zdt; g.Nc = F; g.ldb = ldz;
+  g.T = T; g.washout = washout; g.nseq = nseq; g.out = GC; g.ldo = F; g.lower_only = true;
+  int32_t st = launch_gram_fp64(ctx, g);
+  if (st == RCB_OK) {
+    GramArgs c;
+    c.A = Z; c.a_dtype = zdt; c.M = F; c.lda = ldz; c.Bm = Y; c.b_dtype = ydt; c.Nc = d_out; c.ldb = ldy;
+    c.T = T; c.washout = washout; c.nseq = nseq; c.out = GC + (size_t)F * F; c.ldo = F; c.lower_only = false;
+    st = launch_gram_fp64(ctx, c);
+  }
+  timer_end(ctx, RCB_TIMER_GRAM);
+  return st;
+}
+
+static int32_t check_ridge_args(int64_t S_states, int64_t S_targets, double lambda) {
+  if (S_states != S_targets)
+    return fail(RCB_ERR_DIMENSION, "states has %lld samples, targets has %lld", (long long)S_states, (long long)S_targets);
+  if (S_states < 1) return fail(RCB_ERR_ARGUMENT, "ridge regression requires at least one training sample");
+  if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);
+  return RCB_OK;
+}
+
+int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S, int64_t ld_states,
+                            const void* targets, int32_t targets_dtype, int64_t d_out, int64_t ld_targets, int32_t gram_mode,
+                            int32_t zero_first, double* GC) {
+  if (!ctx || !states || !targets || !GC) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (F < 1 || d_out < 1) return fail(RCB_ERR_ARGUMENT, "F and d_out must be ≥ 1");
+  if (S < 1) return fail(RCB_ERR_ARGUMENT, "ridge regression requires at least one training sample");
+  if (ld_states < F || ld_targets < d_out) return fail(RCB_ERR_DIMENSION, "leading dimension smaller than the row count");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t zsz = states_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
+  const void* Z = nullptr;
+  const void* Y = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, states, (size_t)ld_states * S * zsz, &Z));
+  RCB_TRY(stage_in(ctx, SCR_TGT, targets, (size_t)ld_targets * S * ysz, &Y));
+  const size_t gc_bytes = (size_t)F * (F + d_out) * sizeof(double);
+  double* gc_dev = GC;
+  const bool gc_host = !is_device_ptr(GC);
+  if (gc_host) {
+    void* p = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_bytes, &p));
+    gc_dev = (double*)p;
+    if (!zero_first) RCB_CUDA(cudaMemcpyAsync(gc_dev, GC, gc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (zero_first) RCB_CUDA(cudaMemsetAsync(gc_dev, 0, gc_bytes, ctx->stream));
+  RCB_TRY(gram_device(ctx, Z, states_dtype, F, ld_states, Y, targets_dtype, d_out, ld_targets, S, 0, 1, gram_mode, gc_dev));
+  if (gc_host) RCB_TRY(from_device(ctx, GC, gc_dev, gc_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double lambda, double* W_out) {
+  if (!ctx || !GC || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t gc_bytes = (size_t)F * (F + d_out) * sizeof(double);
+  void* work = nullptr;  // the factorisation is in place: always work on a copy
+  RCB_TRY(ctx_scratch(ctx, SCR_TMP, gc_bytes, &work));
+  RCB_TRY(to_device(ctx, work, GC, gc_bytes));
+  void* w_dev = nullptr;
+  const size_t w_bytes = (size_t)d_out * F * sizeof(double);
+  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
+  RCB_TRY(launch_ridge_solve(ctx, (double*)work, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S_states,
+                        int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out, int64_t S_targets,
+                        int64_t ld_targets, double lambda, int32_t gram_mode, double* W_out) {
+  if (!ctx || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  RCB_TRY(check_ridge_args(S_states, S_targets, lambda));
+  if (!states || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  void* gc = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
+  RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
+                              gram_mode, 1, (double*)gc));
+  void* w_dev = nullptr;
+  const size_t w_bytes = (size_t)d_out * F * sizeof(double);
+  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
+  RCB_TRY(launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+// shared body of rcb_train / rcb_train_partial: collect in (sequence, time) chunks sized to a
+// device-memory budget, accumulating [G | C] chunk by chunk; states are never kept unless asked for.
+static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
+                                int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* gc_dev,
+                                void* states_out, void* hT_out) {
+  rcb_ctx* ctx = esn->ctx;
+  const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
+  const int64_t F = esn->feat, d_out = esn->desc.out_dims, d_in = esn->desc.in_dims, sumN = esn->sumN;
+  const void* u_dev = nullptr;
+  const void* y_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)d_in * T * B * esz, &u_dev));
+  RCB_TRY(stage_in(ctx, SCR_TGT, targets, (size_t)d_out * T * B * ysz, &y_dev));
+  // carry buffer (sumN x B), initialised from h0 or zeros
+  void* h_dev = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_H, (size_t)sumN * B * esz, &h_dev));
+  if (h0) RCB_TRY(to_device(ctx, h_dev, h0, (size_t)sumN * B * esz));
+  else RCB_CUDA(cudaMemsetAsync(h_dev, 0, (size_t)sumN * B * esz, ctx->stream));
+  RCB_CUDA(cudaMemsetAsync(gc_dev, 0, (size_t)F * (F + d_out) * sizeof(double), ctx->stream));
+  // chunking: budget for the state buffer (deep nets also hold inter-layer buffers of similar size)
+  size_t free_b = 0, total_b = 0;
+  RCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = free_b / (esn->layers.size() > 1 ? 6 : 2);
+  const size_t cap = (size_t)24 << 30;
+  if (budget > cap) budget = cap;
+  const bool multi = esn->layers.size() > 1;
+  int64_t Bc = B, Tc = T;
+  const size_t per_seq = (size_t)F * T * esz;
+  if (per_seq * (size_t)B > budget) {
+    Bc = (int64_t)(budget / per_seq);
+    if (Bc < 1) {
+      Bc = 1;
+      Tc = (int64_t)(budget / ((size_t)F * esz));
+      if (Tc < 1) return fail(RCB_ERR_ALLOC, "not enough device memory for one column of states");
+      if (multi) return fail(RCB_ERR_UNSUPPORTED, "time-chunked training is implemented for single-layer ESNs");
+    }
+  }
+  void* st_dev = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * Tc * Bc * esz, &st_dev));
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = std::min<int64_t>(Bc, B - b0);
+    for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+      const int64_t nt = std::min<int64_t>(Tc, T - t0);
+      const void* uc = (const char*)u_dev + ((size_t)b0 * T + t0) * d_in * esz;
+      void* hc = (char*)h_dev + (size_t)b0 * sumN * esz;
+      // either all T steps of nb sequences, or a time chunk of ONE sequence: contiguous inputs both ways
+      RCB_TRY(collect_device(esn, uc, nt, nb, hc, st_dev, hc, b0));
+      const int64_t wo = std::max<int64_t>(0, std::min<int64_t>(nt, washout - t0));
+      if (wo < nt) {
+        // targets of this chunk: d_out x nt per sequence inside the d_out x T x B array
+        const void* yc = (const char*)y_dev + ((size_t)b0 * T + t0) * d_out * ysz;
+        RCB_TRY(gram_device(ctx, st_dev, esn->desc.data_dtype, F, F, yc, targets_dtype, d_out, d_out, nt, wo, nb, gram_mode, gc_dev));
+      }
+      if (states_out) {
+        for (int64_t b = 0; b < nb; ++b) {
+          void* dst = (char*)states_out + ((size_t)(b0 + b) * T + t0) * F * esz;
+          const void* src = (const char*)st_dev + (size_t)b * nt * F * esz;
+          RCB_TRY(from_device(ctx, dst, src, (size_t)F * nt * esz));
+        }
+      }
+    }
+  }
+  if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
+  return RCB_OK;
+}
+
+static int32_t check_train_args(rcb_esn* esn, const void* u, const void* targets, int64_t T, int64_t B, int64_t washout) {
+  RCB_TRY(check_ready(esn));
+  if (!u || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (T < 1) return fail(RCB_ERR_ARGUMENT, "collectstates data must have at least one column, got %lld.", (long long)T);
+  if (B < 1) return fail(RCB_ERR_ARGUMENT, "batch must have at least one sequence, got %lld.", (long long)B);
+  if (washout < 0) return fail(RCB_ERR_ARGUMENT, "washout must be ≥ 0, got %lld", (long long)washout);
+  if (washout >= T) return fail(RCB_ERR_ARGUMENT, "washout=%lld is ≥ number of time steps=%lld", (long long)washout, (long long)T);
+  if (esn->member_count && esn->member_count != B)
+    return fail(RCB_ERR_DIMENSION, "member params were set for %lld sequences, got B=%lld", (long long)esn->member_count, (long long)B);
+  return RCB_OK;
+}
+
+int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                          int64_t washout, int32_t gram_mode, const void* h0, double* GC, void* hT_out) {
+  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  if (!GC) return fail(RCB_ERR_ARGUMENT, "GC is NULL");
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t gc_bytes = (size_t)esn->feat * (esn->feat + esn->desc.out_dims) * sizeof(double);
+  double* gc_dev = GC;
+  if (!is_device_ptr(GC)) {
+    void* p = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_bytes, &p));
+    gc_dev = (double*)p;
+  }
+  RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, gram_mode, h0, gc_dev, nullptr, hT_out));
+  if (gc_dev != GC) RCB_TRY(from_device(ctx, GC, gc_dev, gc_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                  int64_t washout, double lambda, int32_t gram_mode, const void* h0, double* W_out, void* states_out,
+                  void* hT_out) {
+  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);
+  if (!W_out) return fail(RCB_ERR_ARGUMENT, "W_out is NULL");
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const int64_t F = esn->feat, d_out = esn->desc.out_dims;
+  void* gc = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
+  RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, gram_mode, h0, (double*)gc, states_out, hT_out));
+  void* w_dev = nullptr;
+  const size_t w_bytes = (size_t)d_out * F * sizeof(double);
+  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
+  RCB_TRY(launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  // addreadout! (src/reservoircomputer.jl:137-144): install the fitted weight; a bias, if the readout
+  // has one, keeps whatever rcb_esn_set_readout installed before.
+  if (!esn->desc.readout_use_bias) RCB_TRY(rcb_esn_set_readout(esn, (const double*)w_dev, nullptr, 1));
+  return RCB_OK;
+}
+
+static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B, int32_t compute_dtype, bool autoreg,
+                              void* h_inout, double* y_out) {
+  RCB_TRY(check_ready(esn));
+  if (!u || !y_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (!esn->d_Wout) return fail(RCB_ERR_ARGUMENT, "the readout has not been trained or set (addreadout!)");
+  if (B < 1) return fail(RCB_ERR_ARGUMENT, "batch must have at least one sequence, got %lld.", (long long)B);
+  if (esn->readout_members > 1 && esn->readout_members != B)
+    return fail(RCB_ERR_DIMENSION, "%lld per-member readouts were set, got B=%lld", (long long)esn->readout_members, (long long)B);
+  if (esn->member_count && esn->member_count != B)
+    return fail(RCB_ERR_DIMENSION, "member params were set for %lld sequences, got B=%lld", (long long)esn->member_count, (long long)B);
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t dsz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, csz = compute_dtype == RCB_F64 ? 8 : 4;
+  const void* u_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)esn->desc.in_dims * (autoreg ? 1 : T) * B * dsz, &u_dev));
+  void* h_dev = nullptr;
+  const size_t h_bytes = (size_t)esn->sumN * B * csz;
+  if (h_inout) {
+    if (is_device_ptr(h_inout)) h_dev = h_inout;
+    else {
+      RCB_TRY(ctx_scratch(ctx, SCR_H, h_bytes, &h_dev));
+      RCB_CUDA(cudaMemcpyAsync(h_dev, h_inout, h_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  double* y_dev = y_out;
+  const size_t y_bytes = (size_t)esn->desc.out_dims * T * B * sizeof(double);
+  if (!is_device_ptr(y_out)) {
+    void* p = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_Y, y_bytes, &p));
+    y_dev = (double*)p;
+  }
+  PredictArgs a;
+  a.esn = esn; a.compute_dtype = compute_dtype; a.autoregressive = autoreg; a.u = u_dev; a.T = T; a.B = B; a.h = h_dev; a.y = y_dev;
+  RCB_TRY(launch_predict(ctx, a));
+  if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, y_bytes));
+  if (h_inout && h_dev != h_inout) RCB_TRY(from_device(ctx, h_inout, h_dev, h_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_predict_teacher(rcb_esn* esn, const void* u, int64_t T, int64_t B, void* h_inout, double* y_out) {
+  if (!esn) return fail(RCB_ERR_ARGUMENT, "esn handle is NULL");
+  if (T < 1) return fail(RCB_ERR_ARGUMENT, "predict data must have at least one column, got %lld.", (long long)T);
+  return predict_common(esn, u, T, B, esn->desc.data_dtype, false, h_inout, y_out);
+}
+
+int32_t rcb_predict_autoregressive(rcb_esn* esn, const void* u0, int64_t steps, int64_t B, int32_t compute_dtype,
+                                   void* h_inout, double* y_out) {
+  if (!esn) return fail(RCB_ERR_ARGUMENT, "esn handle is NULL");
+  if (steps < 1) return fail(RCB_ERR_ARGUMENT, "steps must be ≥ 1, got %lld", (long long)steps);
+  if (esn->desc.out_dims != esn->desc.in_dims)
+    return fail(RCB_ERR_DIMENSION,
+                "autoregressive predict requires each output to have length %d so it can be used as the next input; "
+                "step 1 produced length %d", esn->desc.in_dims, esn->desc.out_dims);
+  if (compute_dtype != RCB_F32 && compute_dtype != RCB_F64) return fail(RCB_ERR_ARGUMENT, "unknown compute_dtype %d", compute_dtype);
+  return predict_common(esn, u0, steps, B, compute_dtype, true, h_inout, y_out);
+}
+
+int32_t rcb_apply_modifiers(rcb_ctx* ctx, int32_t n_modifiers, const int32_t* kinds, const double* params, const void* x,
+                            int32_t dtype, int64_t n, int64_t cols, void* out) {
+  if (!ctx || !x || !out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (n_modifiers < 0 || n_modifiers > RCB_MAX_MODIFIERS) return fail(RCB_ERR_ARGUMENT, "n_modifiers out of range");
+  if (n < 1 || cols < 0) return fail(RCB_ERR_ARGUMENT, "bad dimensions");
+  ModChain c;
+  c.n = n_modifiers;
+  for (int i = 0; i < n_modifiers; ++i) {
+    if (kinds[i] < RCB_MOD_NLAT1 || kinds[i] > RCB_MOD_EXTENDED_SQUARE) return fail(RCB_ERR_ARGUMENT, "unknown state modifier id %d", kinds[i]);
+    c.kind[i] = kinds[i];
+    c.param[i] = params ? params[i] : 0.0;
+  }
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const int64_t fout = chain_feature_dims(n, c);
+  const void* x_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, x, (size_t)n * cols * esz, &x_dev));
+  void* o_dev = out;
+  if (!is_device_ptr(out)) RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)fout * cols * esz, &o_dev));
+  RCB_TRY(launch_modifiers(ctx, c, x_dev, dtype, n, cols, o_dev));
+  if (o_dev != out) RCB_TRY(from_device(ctx, out, o_dev, (size_t)fout * cols * esz));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+}  // extern "C"

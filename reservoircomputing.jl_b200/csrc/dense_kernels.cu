@@ -1,0 +1,251 @@
+// K2 (exact path): Gram / cross-moment accumulation with exact products and FP64 accumulation,
+// the dense input projection of deep layers, and the generic (un-fused) state-modifier pass.
+//
+//   G = Z Z', C = Z Y'   — the Gram form of the ridge system, test/test_train_ridge.jl:18-27; it
+//                          replaces building [Z'; sqrt(λ) I] (src/train.jl:108-138).
+//   washout              — src/train.jl:36-47: the first `washout` columns of every sequence are
+//                          skipped by index arithmetic, never copied.
+//   modifiers            — matrix form of src/states.jl (__apply_tomatrix, :1-15).
+#include <cuda_runtime.h>
+
+#include "rcb_internal.h"
+
+namespace rcb {
+
+// ---- out += A * B^T over a strided sample set, FP64 accumulate --------------------------------
+struct GramParams {
+  const void* A; long long M, lda;
+  const void* B; long long Nc, ldb;
+  long long T, washout, Te, Stot, chunk;
+  double* out; long long ldo;
+  int lower_only;
+};
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) gram_fp64_kernel(const GramParams g) {
+  constexpr int TILE = 64, KC = 16;
+  const long long i0 = (long long)blockIdx.y * TILE, j0 = (long long)blockIdx.x * TILE;
+  if (g.lower_only && j0 > i0) return;
+  __shared__ double As[KC][TILE];
+  __shared__ double Bs[KC][TILE];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const TA* A = reinterpret_cast<const TA*>(g.A);
+  const TB* B = reinterpret_cast<const TB*>(g.B);
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  const long long s_beg = (long long)blockIdx.z * g.chunk;
+  const long long s_end = s_beg + g.chunk < g.Stot ? s_beg + g.chunk : g.Stot;
+  const int li = tid & 63, ls = tid >> 6;  // 64 rows x 4 samples per pass
+  for (long long s0 = s_beg; s0 < s_end; s0 += KC) {
+#pragma unroll
+    for (int q = 0; q < KC / 4; ++q) {
+      const int ss = ls + 4 * q;
+      const long long s = s0 + ss;
+      double av = 0.0, bv = 0.0;
+      if (s < s_end) {
+        const long long col = (s / g.Te) * g.T + g.washout + (s % g.Te);
+        if (i0 + li < g.M) av = (double)A[(size_t)col * g.lda + i0 + li];
+        if (j0 + li < g.Nc) bv = (double)B[(size_t)col * g.ldb + j0 + li];
+      }
+      As[ss][li] = av;
+      Bs[ss][li] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ss = 0; ss < KC; ++ss) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = As[ss][ty + 16 * q]; b[q] = Bs[ss][tx + 16 * q]; }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const long long i = i0 + ty + 16 * x, j = j0 + tx + 16 * y;
+      if (i < g.M && j < g.Nc && !(g.lower_only && j > i)) atomicAdd(g.out + (size_t)j * g.ldo + i, acc[x][y]);
+    }
+}
+
+int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a) {
+  GramParams g{};
+  g.A = a.A; g.M = a.M; g.lda = a.lda; g.B = a.Bm; g.Nc = a.Nc; g.ldb = a.ldb;
+  g.T = a.T; g.washout = a.washout; g.Te = a.T - a.washout; g.Stot = g.Te * a.nseq;
+  g.out = a.out; g.ldo = a.ldo; g.lower_only = a.lower_only ? 1 : 0;
+  if (g.Stot <= 0) return RCB_OK;
+  const long long tm = (a.M + 63) / 64, tn = (a.Nc + 63) / 64;
+  const long long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  long long splits = (4LL * ctx->sm_count + tiles - 1) / tiles;
+  const long long max_splits = (g.Stot + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  g.chunk = ((g.Stot + splits - 1) / splits + 15) / 16 * 16;
+  splits = (g.Stot + g.chunk - 1) / g.chunk;
+  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+  const bool a64 = a.a_dtype == RCB_F64, b64 = a.b_dtype == RCB_F64;
+  if (!a64 && !b64) gram_fp64_kernel<float, float><<<grid, 256, 0, ctx->stream>>>(g);
+  else if (!a64 && b64) gram_fp64_kernel<float, double><<<grid, 256, 0, ctx->stream>>>(g);
+  else if (a64 && !b64) gram_fp64_kernel<double, float><<<grid, 256, 0, ctx->stream>>>(g);
+  else gram_fp64_kernel<double, double><<<grid, 256, 0, ctx->stream>>>(g);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// ---- P(npos x S) = Wp(npos x K) * Z(K x S), all column-major FP32 ------------------------------
+// The input projection of a deep layer for every time step at once: layer l+1 at step t consumes
+// the modified state of layer l at step t and nothing feeds back (src/models/esn_deep.jl:270-280),
+// so the DeepESN wavefront factors into L recurrence passes with a dense GEMM between them.
+__global__ void __launch_bounds__(256) input_projection_kernel(const float* __restrict__ Wp, long long N, long long K,
+                                                               const float* __restrict__ Z, long long S,
+                                                               float* __restrict__ P) {
+  constexpr int TILE = 64, KC = 16;
+  __shared__ float As[KC][TILE];
+  __shared__ float Bs[KC][TILE + 1];
+  const long long i0 = (long long)blockIdx.x * TILE, j0 = (long long)blockIdx.y * TILE;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (long long k0 = 0; k0 < K; k0 += KC) {
+    {
+      const int li = tid & 63, lk = tid >> 6;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long k = k0 + lk + 4 * q;
+        As[lk + 4 * q][li] = (k < K && i0 + li < N) ? Wp[(size_t)k * N + i0 + li] : 0.f;
+      }
+      const int lkk = tid & 15, lj = tid >> 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long j = j0 + lj + 16 * q, k = k0 + lkk;
+        Bs[lkk][lj + 16 * q] = (k < K && j < S) ? Z[(size_t)j * K + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; b[q] = Bs[kk][ty + 16 * q]; }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const long long i = i0 + tx + 16 * x, j = j0 + ty + 16 * y;
+      if (i < N && j < S) P[(size_t)j * N + i] = acc[x][y];
+    }
+}
+
+int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,
+                                float* P) {
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((S + 63) / 64));
+  if (grid.y > 65535) {
+    // split the sample range so grid.y stays within limits
+    const int64_t step = 65535LL * 64;
+    for (int64_t s0 = 0; s0 < S; s0 += step) {
+      const int64_t sc = S - s0 < step ? S - s0 : step;
+      dim3 g2((unsigned)((N + 63) / 64), (unsigned)((sc + 63) / 64));
+      input_projection_kernel<<<g2, 256, 0, ctx->stream>>>(Win, N, K, Z + (size_t)s0 * K, sc, P + (size_t)s0 * N);
+      ctx->launches++;
+    }
+  } else {
+    input_projection_kernel<<<grid, 256, 0, ctx->stream>>>(Win, N, K, Z, S, P);
+    ctx->launches++;
+  }
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// ---- generic modifier chain, one column per CTA iteration ---------------------------------------
+struct ModParams {
+  int n_mod;
+  int kind[RCB_MAX_MODIFIERS];
+  double param[RCB_MAX_MODIFIERS];
+  long long n, cols, fout, fmax;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) modifiers_kernel(const ModParams m, const T* __restrict__ x, T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_mod[];
+  T* buf0 = reinterpret_cast<T*>(smem_mod);
+  T* buf1 = buf0 + m.fmax;
+  for (long long c = blockIdx.x; c < m.cols; c += gridDim.x) {
+    for (long long i = threadIdx.x; i < m.n; i += blockDim.x) buf0[i] = x[(size_t)c * m.n + i];
+    __syncthreads();
+    T* a = buf0;
+    T* b = buf1;
+    long long len = m.n;
+    for (int q = 0; q < m.n_mod; ++q) {
+      const int kind = m.kind[q];
+      long long nlen = len;
+      if (kind == RCB_MOD_PAD) nlen = len + 1;
+      if (kind == RCB_MOD_EXTENDED_SQUARE) nlen = 2 * len;
+      const long long thr = kind == RCB_MOD_PARTIAL_SQUARE ? (long long)floor(m.param[q] * (double)len) : 0;
+      for (long long f = threadIdx.x; f < nlen; f += blockDim.x) {
+        T v;
+        switch (kind) {
+          case RCB_MOD_NLAT1: v = (f & 1) == 0 ? a[f] * a[f] : a[f]; break;
+          case RCB_MOD_NLAT2: v = ((f & 1) == 0 && f >= 2) ? a[f - 1] * a[f - 2] : a[f]; break;
+          case RCB_MOD_NLAT3: v = ((f & 1) == 0 && f >= 2 && f < len - 1) ? a[f - 1] * a[f + 1] : a[f]; break;
+          case RCB_MOD_PAD: v = f < len ? a[f] : (T)m.param[q]; break;
+          case RCB_MOD_PARTIAL_SQUARE: v = f < thr ? a[f] * a[f] : a[f]; break;
+          case RCB_MOD_EXTENDED_SQUARE: v = f < len ? a[f] : a[f - len] * a[f - len]; break;
+          default: v = a[f];
+        }
+        b[f] = v;
+      }
+      __syncthreads();
+      T* tmp = a; a = b; b = tmp;
+      len = nlen;
+    }
+    for (long long f = threadIdx.x; f < len; f += blockDim.x) out[(size_t)c * m.fout + f] = a[f];
+    __syncthreads();
+  }
+}
+
+int32_t launch_modifiers(rcb_ctx* ctx, const ModChain& c, const void* x, int32_t dtype, int64_t n, int64_t cols,
+                         void* out) {
+  ModParams m{};
+  m.n_mod = c.n;
+  long long len = n, fmax = n;
+  for (int i = 0; i < c.n; ++i) {
+    m.kind[i] = c.kind[i];
+    m.param[i] = c.param[i];
+    if (c.kind[i] == RCB_MOD_PAD) len += 1;
+    if (c.kind[i] == RCB_MOD_EXTENDED_SQUARE) len *= 2;
+    if (len > fmax) fmax = len;
+  }
+  m.n = n; m.cols = cols; m.fout = len; m.fmax = (fmax + 3) & ~3LL;
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const size_t smem = 2 * (size_t)m.fmax * esz;
+  if (smem > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "modifier chain output (%lld features) exceeds shared memory", fmax);
+  if (cols <= 0) return RCB_OK;
+  const int grid = (int)(cols < 8LL * ctx->sm_count ? cols : 8LL * ctx->sm_count);
+  if (dtype == RCB_F64) {
+    RCB_CUDA(cudaFuncSetAttribute(modifiers_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    modifiers_kernel<double><<<grid, 256, smem, ctx->stream>>>(m, (const double*)x, (double*)out);
+  } else {
+    RCB_CUDA(cudaFuncSetAttribute(modifiers_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    modifiers_kernel<float><<<grid, 256, smem, ctx->stream>>>(m, (const float*)x, (float*)out);
+  }
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+}  // namespace rcb

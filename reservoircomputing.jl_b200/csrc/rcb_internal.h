@@ -1,0 +1,191 @@
+// Internal declarations shared by the translation units of librcb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rcb200.h"
+
+namespace rcb {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int32_t fail(int32_t code, const char* fmt, ...);
+
+#define RCB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::rcb::fail(RCB_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), \
+                         __FILE__, __LINE__, #expr);                                            \
+  } while (0)
+
+#define RCB_TRY(expr)           \
+  do {                          \
+    int32_t _s = (expr);        \
+    if (_s != RCB_OK) return _s; \
+  } while (0)
+
+// ---- sparse formats (host) -------------------------------------------------------------------
+// Canonical CSR: rows ascending, columns ascending within a row, 0-based.
+struct HostCsr {
+  int32_t n = 0;
+  std::vector<int64_t> rowptr;
+  std::vector<int32_t> colind;
+  std::vector<float> vals;
+};
+// dense column-major N x N -> CSR of the entries with W[i,j] != 0 (what SparseArrays.sparse keeps)
+int32_t csr_from_dense(const float* W, int64_t ld, int32_t n, HostCsr* out);
+// Julia SparseMatrixCSC (1-based colptr/rowval, stored entries kept as they are) -> CSR
+int32_t csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n, HostCsr* out);
+
+// Sliced-ELL layout consumed by the recurrence kernels: rows sorted by descending length
+// ("position" p = sorted rank), thread `tid` of a CTA owns positions p = k*nthreads + tid
+// (k = 0..R-1, "slab" k).  One block per (slab, warp) holds width2 slot-PAIRS for its 32 rows,
+// slot-major, so lane l reads pair j at [(off + j)*32 + l]: fully coalesced 256 B (values) and
+// 128 B (two packed uint16 column indices).  Padding entries are (0.0f, column = own row).
+struct HostSell {
+  int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
+  std::vector<uint16_t> perm;     // [R*nthreads] position -> row (0xFFFF = no row)
+  std::vector<int32_t> blk_off;   // [R*nwarps] pair offset of block (k, w)
+  std::vector<int32_t> blk_w2;    // [R*nwarps] pairs in block (k, w)
+  std::vector<float2> vals;       // [total_pairs*32]
+  std::vector<uint32_t> cols;     // [total_pairs*32] lo16 = first column, hi16 = second
+  int64_t padded_nnz = 0;
+};
+int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out);
+
+// ---- device-side views -----------------------------------------------------------------------
+struct DevSell {
+  int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
+  uint16_t* perm = nullptr;
+  int32_t* blk_off = nullptr;
+  int32_t* blk_w2 = nullptr;
+  float2* vals = nullptr;
+  uint32_t* cols = nullptr;
+  int64_t total_pairs = 0;
+};
+
+struct ModChain {  // fused-epilogue description of a state_modifiers tuple
+  int32_t n = 0;
+  int32_t kind[RCB_MAX_MODIFIERS];
+  double param[RCB_MAX_MODIFIERS];
+};
+int64_t chain_feature_dims(int64_t n, const ModChain& c);
+// chains the recurrence epilogue evaluates in place: [], [X], [Pad], [X, Pad]
+bool chain_is_fusable(const ModChain& c);
+
+struct Layer {
+  rcb_layer_desc desc{};
+  int32_t n = 0;      // res dims
+  int32_t d_in = 0;   // input dims of this layer
+  int32_t feat = 0;   // feature dims after modifiers
+  ModChain chain;
+  HostCsr csr;
+  DevSell sell;
+  float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
+  float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
+  float* d_bias = nullptr;  // [n] by row
+  float* d_leak = nullptr;  // [n] by row (vector leak) or nullptr
+  bool weights_set = false;
+};
+
+}  // namespace rcb
+
+struct rcb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  void* timer_pools = nullptr;  // rcb::TimerPool[3]
+  // pinned staging + scratch, grown on demand
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* scratch[12] = {};
+  size_t scratch_bytes[12] = {};
+};
+
+struct rcb_esn {
+  rcb_ctx* ctx = nullptr;
+  rcb_esn_desc desc{};
+  std::vector<rcb::Layer> layers;
+  int32_t feat = 0;   // F of last layer
+  int32_t sumN = 0;
+  // readout
+  double* d_Wout = nullptr;  // [members][d_out x F]
+  double* d_bout = nullptr;  // [members][d_out] or nullptr
+  int64_t readout_members = 0;
+  // ensemble member params
+  float* d_member_scale = nullptr;
+  float* d_member_leak = nullptr;
+  int64_t member_count = 0;
+};
+
+namespace rcb {
+
+// scratch slots
+enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5, SCR_TMP2 = 6, SCR_TGT = 7,
+       SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_COUNT = 12 };
+int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out);
+int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out);
+bool is_device_ptr(const void* p);
+// copy host-or-device -> device buffer on the ctx stream
+int32_t to_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int32_t from_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+void timer_begin(rcb_ctx* ctx, int which);
+void timer_end(rcb_ctx* ctx, int which);
+
+// ---- kernel launchers (device pointers only) -------------------------------------------------
+struct CollectArgs {
+  const Layer* layer = nullptr;
+  int32_t dtype = RCB_F32;
+  const void* u = nullptr;        // d_in x T x B (small d_in) — or nullptr when pre_in is used
+  const void* pre_in = nullptr;   // N x T x B precomputed input projection (deep layers)
+  int64_t T = 0, B = 0;
+  const void* h0 = nullptr;       // packed carry (h_stride x B), this layer's rows start at h_off; or nullptr
+  void* states = nullptr;         // F x T x B or nullptr
+  void* hT = nullptr;             // packed carry out (same layout) or nullptr
+  int64_t h_stride = 0, h_off = 0;
+  const float* member_scale = nullptr;
+  const float* member_leak = nullptr;
+  bool raw_states = false;        // write un-modified states (N x T x B) — generic modifier fallback
+};
+int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a);
+
+struct PredictArgs {
+  const rcb_esn* esn = nullptr;
+  int32_t compute_dtype = RCB_F32;
+  bool autoregressive = false;
+  const void* u = nullptr;  // teacher: d_in x T x B (data dtype); autoregressive: d_in x B
+  int64_t T = 0, B = 0;
+  void* h = nullptr;        // sumN x B in compute dtype (in/out)
+  double* y = nullptr;      // d_out x T x B
+};
+int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a);
+
+int32_t launch_modifiers(rcb_ctx* ctx, const ModChain& c, const void* x, int32_t dtype, int64_t n, int64_t cols,
+                         void* out);
+
+// out(M x Nc, ld = ldo, Float64) += A(M x S) * B(Nc x S)^T over the sample set
+// {b*T + t : b < nseq, washout <= t < T}; lower_only: skip tiles strictly above the diagonal.
+struct GramArgs {
+  const void* A = nullptr; int32_t a_dtype = RCB_F32; int64_t M = 0, lda = 0;
+  const void* Bm = nullptr; int32_t b_dtype = RCB_F32; int64_t Nc = 0, ldb = 0;
+  int64_t T = 0, washout = 0, nseq = 1;
+  double* out = nullptr; int64_t ldo = 0;
+  bool lower_only = false;
+};
+int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a);
+
+// (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.
+int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
+
+// dense input projection P(N x S) = W_in(N x K) * Z(K x S), FP32 (deep layers)
+int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,
+                                float* P);
+
+}  // namespace rcb

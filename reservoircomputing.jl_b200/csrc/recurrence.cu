@@ -1,0 +1,616 @@
+// K1 (collectstates) and K4 (predict): persistent, sequence-partitioned ESN recurrence for sm_100a.
+//
+// Reference semantics (paths in SciML/ReservoirComputing.jl v0.12.35):
+//   step      src/layers/esn_cell.jl:175-184   h' = (1-a) .* h .+ a .* act(W_in*u .+ (W*h .+ b))
+//   modifiers src/states.jl:73-88,205-217,277-289,349-361,404-421,466-473 via __apply_seq
+//             (src/reservoircomputer.jl:72-79); the carry stays the UN-modified h.
+//   loop      src/reservoircomputer.jl:113-133 (collectstates), src/predict.jl:74-88,163-177.
+//
+// Design: sequences are independent, so each CTA owns NB sequences for all T steps
+// and keeps their state vectors in shared memory; there is no inter-CTA synchronisation at all.
+// The N x NB state tile is stored as component arrays ([N] float4 | [N] float2 | [N] float) so
+// that one gather of column c serves NB sequences with 1-3 vector LDS.  W is a sliced-ELL stream
+// (32-row slices sorted by length, slot-pair major, 16-bit column indices) read through the
+// read-only path every step: it is shared by all CTAs and stays L2-resident (295 KB at N=8192).
+// State is double-buffered in shared memory, which needs ONE __syncthreads per step.  The state
+// modifier and the streaming store of the F x T x B feature tensor are fused into the step.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "rcb_internal.h"
+
+namespace rcb {
+
+// ---- component-array state tile ----------------------------------------------------------------
+// NB values per neuron split into chunks of (16/sizeof(T)), 2, 1 values; chunk arrays are laid out
+// one after the other, each Npad entries long, so every access is a naturally aligned vector LDS/STS.
+template <typename T, int W> struct VecOf;
+template <> struct VecOf<float, 4> { using type = float4; };
+template <> struct VecOf<float, 2> { using type = float2; };
+template <> struct VecOf<float, 1> { using type = float; };
+template <> struct VecOf<double, 2> { using type = double2; };
+template <> struct VecOf<double, 1> { using type = double; };
+
+template <typename T, int REM>
+__host__ __device__ constexpr int chunk_width() {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  return REM >= VEC ? VEC : (REM >= 2 ? 2 : 1);
+}
+
+template <typename T, int NB, int DONE = 0>
+__device__ __forceinline__ void pack_load(const unsigned char* base, int npad, int idx, T* v) {
+  if constexpr (DONE < NB) {
+    constexpr int W = chunk_width<T, NB - DONE>();
+    using V = typename VecOf<T, W>::type;
+    const V x = *reinterpret_cast<const V*>(base + (size_t)DONE * sizeof(T) * npad + (size_t)idx * W * sizeof(T));
+    const T* xs = reinterpret_cast<const T*>(&x);
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[DONE + i] = xs[i];
+    pack_load<T, NB, DONE + W>(base, npad, idx, v);
+  }
+}
+
+template <typename T, int NB, int DONE = 0>
+__device__ __forceinline__ void pack_store(unsigned char* base, int npad, int idx, const T* v) {
+  if constexpr (DONE < NB) {
+    constexpr int W = chunk_width<T, NB - DONE>();
+    using V = typename VecOf<T, W>::type;
+    V x;
+    T* xs = reinterpret_cast<T*>(&x);
+#pragma unroll
+    for (int i = 0; i < W; ++i) xs[i] = v[DONE + i];
+    *reinterpret_cast<V*>(base + (size_t)DONE * sizeof(T) * npad + (size_t)idx * W * sizeof(T)) = x;
+    pack_store<T, NB, DONE + W>(base, npad, idx, v);
+  }
+}
+
+// ---- activation ------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T apply_act(int act, T x) {
+  switch (act) {
+    case RCB_ACT_TANH:
+    case RCB_ACT_TANH_FAST:
+      if constexpr (sizeof(T) == 4) return tanhf(x); else return tanh(x);
+    case RCB_ACT_SIGMOID:
+      if constexpr (sizeof(T) == 4) return 1.0f / (1.0f + expf(-x)); else return 1.0 / (1.0 + exp(-x));
+    case RCB_ACT_RELU:
+      return x > T(0) ? x : T(0);
+    default:
+      return x;
+  }
+}
+
+// ---- fused modifier epilogue -------------------------------------------------------------------
+struct FusedMod {
+  int kind;     // 0 = none, else rcb_modifier of the first (non-Pad) modifier
+  int thr;      // PartialSquare: floor(eta*N)
+  int has_pad;  // trailing Pad
+  int feat1;    // feature dims before the Pad
+  double pad;   // padding value
+};
+
+// feature f of (modifier chain applied to the state tile `s`), for the NB sequences of the tile.
+// Indices are 0-based here; the reference's are 1-based.
+template <typename T, int NB>
+__device__ __forceinline__ void feature_eval(const FusedMod& m, const unsigned char* s, int npad, int n, int f, T* out) {
+  if (m.has_pad && f == m.feat1) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) out[b] = (T)m.pad;  // T(pad.padding), states.jl:79-82
+    return;
+  }
+  T a[NB], c[NB];
+  switch (m.kind) {
+    case RCB_MOD_NLAT1:  // states.jl:205-213: 1-based odd idx squared
+      pack_load<T, NB>(s, npad, f, a);
+      if ((f & 1) == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b] * a[b];
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b];
+      }
+      break;
+    case RCB_MOD_NLAT2:  // states.jl:277-285: odd idx > 1: x[idx-1]*x[idx-2]
+      if ((f & 1) == 0 && f >= 2) {
+        pack_load<T, NB>(s, npad, f - 1, a);
+        pack_load<T, NB>(s, npad, f - 2, c);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b] * c[b];
+      } else {
+        pack_load<T, NB>(s, npad, f, out);
+      }
+      break;
+    case RCB_MOD_NLAT3:  // states.jl:349-357: odd 1 < idx < n: x[idx-1]*x[idx+1]
+      if ((f & 1) == 0 && f >= 2 && f < n - 1) {
+        pack_load<T, NB>(s, npad, f - 1, a);
+        pack_load<T, NB>(s, npad, f + 1, c);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b] * c[b];
+      } else {
+        pack_load<T, NB>(s, npad, f, out);
+      }
+      break;
+    case RCB_MOD_PARTIAL_SQUARE:  // states.jl:408-418
+      pack_load<T, NB>(s, npad, f, a);
+      if (f < m.thr) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b] * a[b];
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b];
+      }
+      break;
+    case RCB_MOD_EXTENDED_SQUARE:  // states.jl:466-469: vcat(x, x.^2)
+      if (f < n) {
+        pack_load<T, NB>(s, npad, f, out);
+      } else {
+        pack_load<T, NB>(s, npad, f - n, a);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) out[b] = a[b] * a[b];
+      }
+      break;
+    default:
+      pack_load<T, NB>(s, npad, f, out);
+  }
+}
+
+// ---- kernel parameters -------------------------------------------------------------------------
+struct RecParams {
+  int n, npad, d_in, feat;
+  int nthreads, R, nwarps, npos;
+  const uint16_t* perm;
+  const int32_t* blk_off;
+  const int32_t* blk_w2;
+  const float2* vals;
+  const uint32_t* cols;
+  const float* Win;    // [d_in][npos] (position order), nullptr when pre_in is used
+  const float* bias;   // [n] by row, or nullptr
+  const float* leakv;  // [n] by row, or nullptr
+  double leak;
+  int act;
+  FusedMod mod;
+  const void* u;       // d_in x T x B
+  const void* pre_in;  // npos x T x B (position order), precomputed W_in*z for deep layers
+  long long T, B;
+  const void* h0;
+  void* states;
+  void* hT;
+  long long h_stride, h_off;
+  const float* member_scale;
+  const float* member_leak;
+  int raw;  // write the un-modified state (feat == n)
+};
+
+template <typename T, int NB>
+__device__ __forceinline__ void row_update(const RecParams& p, const unsigned char* cur, unsigned char* nxt,
+                                           const T* ucur, int k, int tid, int warp, int lane, const int32_t* blk_s,
+                                           long long t, long long seq0, const T* mscale, const T* mleak) {
+  const int pos = k * p.nthreads + tid;
+  const unsigned r16 = __ldg(p.perm + pos);
+  const bool valid = r16 != 0xFFFFu;
+  const int r = valid ? (int)r16 : 0;
+  T acc[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) acc[b] = T(0);
+  const int blk = k * p.nwarps + warp;
+  const int off = blk_s[2 * blk], w2 = blk_s[2 * blk + 1];
+  const float2* vp = p.vals + (size_t)off * 32 + lane;
+  const uint32_t* cp = p.cols + (size_t)off * 32 + lane;
+#pragma unroll 4
+  for (int j = 0; j < w2; ++j) {
+    const float2 v = __ldg(vp + (size_t)j * 32);
+    const uint32_t c = __ldg(cp + (size_t)j * 32);
+    T x0[NB], x1[NB];
+    pack_load<T, NB>(cur, p.npad, (int)(c & 0xFFFFu), x0);
+    pack_load<T, NB>(cur, p.npad, (int)(c >> 16), x1);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      acc[b] = fma((T)v.x, x0[b], acc[b]);
+      acc[b] = fma((T)v.y, x1[b], acc[b]);
+    }
+  }
+  if (mscale) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] *= mscale[b];
+  }
+  if (p.bias) {  // bias belongs to the recurrent term: W*h .+ b (esn_cell.jl:179)
+    const T bv = (T)__ldg(p.bias + r);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc[b] += bv;
+  }
+  T win[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) win[b] = T(0);
+  if (p.pre_in) {
+    const T* pin = reinterpret_cast<const T*>(p.pre_in);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      long long seq = seq0 + b < p.B ? seq0 + b : p.B - 1;
+      win[b] = __ldg(pin + ((size_t)seq * p.T + t) * p.npos + pos);
+    }
+  } else {
+    for (int d = 0; d < p.d_in; ++d) {
+      const T w = (T)__ldg(p.Win + (size_t)d * p.npos + pos);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) win[b] = fma(w, ucur[d * NB + b], win[b]);
+    }
+  }
+  T hold[NB], hnew[NB];
+  pack_load<T, NB>(cur, p.npad, r, hold);
+  T lc = (T)p.leak;
+  if (p.leakv) lc = (T)__ldg(p.leakv + r);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const T l = mleak ? mleak[b] : lc;
+    const T cand = apply_act<T>(p.act, win[b] + acc[b]);
+    hnew[b] = (T(1) - l) * hold[b] + l * cand;  // esn_cell.jl:182
+  }
+  if (valid) pack_store<T, NB>(nxt, p.npad, r, hnew);
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(1024, 1) k1_collect_kernel(const RecParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t buf = (size_t)p.npad * NB * sizeof(T);
+  unsigned char* S[2] = {smem, smem + buf};
+  T* u_s = reinterpret_cast<T*>(smem + 2 * buf);                   // [2][d_in*NB]
+  T* m_s = u_s + 2 * (p.d_in > 0 ? p.d_in : 1) * NB;               // [2][NB] member scale, leak
+  int32_t* blk_s = reinterpret_cast<int32_t*>(m_s + 2 * NB);       // [R*nwarps][2]
+  const long long seq0 = (long long)blockIdx.x * NB;
+  const T* u_g = reinterpret_cast<const T*>(p.u);
+  const T* h0_g = reinterpret_cast<const T*>(p.h0);
+
+  for (int i = tid; i < p.npad; i += p.nthreads) {
+    T v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const long long seq = seq0 + b;
+      v[b] = (h0_g && seq < p.B && i < p.n) ? h0_g[(size_t)seq * p.h_stride + p.h_off + i] : T(0);
+    }
+    pack_store<T, NB>(S[0], p.npad, i, v);
+    pack_store<T, NB>(S[1], p.npad, i, v);
+  }
+  for (int i = tid; i < p.R * p.nwarps; i += p.nthreads) {
+    blk_s[2 * i] = p.blk_off[i];
+    blk_s[2 * i + 1] = p.blk_w2[i];
+  }
+  const int nu = p.pre_in ? 0 : p.d_in * NB;
+  long long useq = 0;
+  int ud = 0;
+  if (tid < nu) {
+    ud = tid / NB;
+    const int b = tid % NB;
+    useq = seq0 + b < p.B ? seq0 + b : p.B - 1;
+    u_s[tid] = u_g[((size_t)useq * p.T + 0) * p.d_in + ud];
+  }
+  if (tid < NB) {
+    const long long seq = seq0 + tid < p.B ? seq0 + tid : p.B - 1;
+    m_s[tid] = p.member_scale ? (T)p.member_scale[seq] : T(1);
+    m_s[NB + tid] = p.member_leak ? (T)p.member_leak[seq] : T(0);
+  }
+  __syncthreads();
+  const T* mscale = p.member_scale ? m_s : nullptr;
+  const T* mleak = p.member_leak ? m_s + NB : nullptr;
+  T* out_g = reinterpret_cast<T*>(p.states);
+  const int F = p.raw ? p.n : p.feat;
+  FusedMod mod = p.mod;
+  if (p.raw) { mod.kind = 0; mod.has_pad = 0; }
+
+  for (long long t = 0; t < p.T; ++t) {
+    const unsigned char* cur = S[t & 1];
+    unsigned char* nxt = S[(t + 1) & 1];
+    const T* ucur = u_s + (t & 1) * nu;
+    T u_next = T(0);
+    if (tid < nu && t + 1 < p.T) u_next = __ldg(u_g + ((size_t)useq * p.T + (t + 1)) * p.d_in + ud);
+    for (int k = 0; k < p.R; ++k) row_update<T, NB>(p, cur, nxt, ucur, k, tid, warp, lane, blk_s, t, seq0, mscale, mleak);
+    if (tid < nu) u_s[((t + 1) & 1) * nu + tid] = u_next;
+    __syncthreads();
+    if (out_g) {
+      // streaming store of column t of every sequence: features fastest => 128 B+ coalesced rows
+      if ((F & 3) == 0 && sizeof(T) == 4) {
+        for (int f4 = tid * 4; f4 < F; f4 += p.nthreads * 4) {
+          T z[4][NB];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) feature_eval<T, NB>(mod, nxt, p.npad, p.n, f4 + i, z[i]);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            if (seq0 + b < p.B) {
+              float4 o = make_float4((float)z[0][b], (float)z[1][b], (float)z[2][b], (float)z[3][b]);
+              __stcs(reinterpret_cast<float4*>(out_g + ((size_t)(seq0 + b) * p.T + t) * F + f4), o);
+            }
+          }
+        }
+      } else {
+        for (int f = tid; f < F; f += p.nthreads) {
+          T z[NB];
+          feature_eval<T, NB>(mod, nxt, p.npad, p.n, f, z);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (seq0 + b < p.B) out_g[((size_t)(seq0 + b) * p.T + t) * F + f] = z[b];
+        }
+      }
+    }
+  }
+  if (p.hT) {
+    T* hT_g = reinterpret_cast<T*>(p.hT);
+    const unsigned char* fin = S[p.T & 1];
+    for (int i = tid; i < p.n; i += p.nthreads) {
+      T v[NB];
+      pack_load<T, NB>(fin, p.npad, i, v);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        if (seq0 + b < p.B) hT_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] = v[b];
+    }
+  }
+}
+
+// ---- host launcher -----------------------------------------------------------------------------
+static FusedMod make_fused(const Layer& L) {
+  FusedMod m{};
+  m.kind = 0; m.thr = 0; m.has_pad = 0; m.pad = 0.0; m.feat1 = L.n;
+  const ModChain& c = L.chain;
+  int i = 0;
+  if (c.n > 0 && c.kind[0] != RCB_MOD_PAD) {
+    m.kind = c.kind[0];
+    if (m.kind == RCB_MOD_PARTIAL_SQUARE) m.thr = (int)floor(c.param[0] * (double)L.n);
+    if (m.kind == RCB_MOD_EXTENDED_SQUARE) m.feat1 = 2 * L.n;
+    i = 1;
+  }
+  if (i < c.n && c.kind[i] == RCB_MOD_PAD) { m.has_pad = 1; m.pad = c.param[i]; }
+  return m;
+}
+
+template <typename T, int NB>
+static int32_t launch_collect_nb(rcb_ctx* ctx, const RecParams& p, size_t smem, int grid) {
+  auto kern = k1_collect_kernel<T, NB>;
+  RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, p.nthreads, smem, ctx->stream>>>(p);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+static size_t collect_smem_bytes(int npad, int nb, int d_in, int R, int nwarps, size_t esz) {
+  return 2 * (size_t)npad * nb * esz + (2 * (size_t)(d_in > 0 ? d_in : 1) * nb + 2 * nb) * esz + (size_t)R * nwarps * 8 + 16;
+}
+
+int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
+  const Layer& L = *a.layer;
+  const DevSell& s = L.sell;
+  RecParams p{};
+  p.n = L.n; p.npad = (L.n + 3) & ~3; p.d_in = L.d_in; p.feat = L.feat;
+  p.nthreads = s.nthreads; p.R = s.R; p.nwarps = s.nwarps; p.npos = s.R * s.nthreads;
+  p.perm = s.perm; p.blk_off = s.blk_off; p.blk_w2 = s.blk_w2; p.vals = s.vals; p.cols = s.cols;
+  p.Win = L.d_Win; p.bias = L.desc.use_bias ? L.d_bias : nullptr; p.leakv = L.desc.leak_is_vector ? L.d_leak : nullptr;
+  p.leak = L.desc.leak_scalar; p.act = L.desc.activation;
+  p.mod = make_fused(L);
+  p.u = a.u; p.pre_in = a.pre_in; p.T = a.T; p.B = a.B; p.h0 = a.h0; p.states = a.states; p.hT = a.hT;
+  p.h_stride = a.h_stride > 0 ? a.h_stride : L.n; p.h_off = a.h_off;
+  p.member_scale = a.member_scale; p.member_leak = a.member_leak; p.raw = a.raw_states ? 1 : 0;
+  if (a.pre_in) p.d_in = 0;
+  const size_t esz = a.dtype == RCB_F64 ? 8 : 4;
+  const size_t cap = ctx->smem_optin;
+  // sequences per CTA: enough to cover B with one wave of CTAs, bounded by shared memory
+  int want = (int)((a.B + ctx->sm_count - 1) / ctx->sm_count);
+  static const int f32_nb[] = {1, 2, 3, 4, 7};
+  static const int f64_nb[] = {1, 2};
+  const int* cand = a.dtype == RCB_F64 ? f64_nb : f32_nb;
+  const int ncand = a.dtype == RCB_F64 ? 2 : 5;
+  int nb = 0;
+  for (int i = 0; i < ncand; ++i) {
+    if (collect_smem_bytes(p.npad, cand[i], p.d_in, p.R, p.nwarps, esz) > cap) break;
+    nb = cand[i];
+    if (cand[i] >= want) break;
+  }
+  if (nb == 0)
+    return fail(RCB_ERR_UNSUPPORTED, "reservoir size %d does not fit the shared-memory state tile (%zu B available)", L.n, cap);
+  const size_t smem = collect_smem_bytes(p.npad, nb, p.d_in, p.R, p.nwarps, esz);
+  const int grid = (int)((a.B + nb - 1) / nb);
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  int32_t st = RCB_OK;
+  if (a.dtype == RCB_F64) {
+    if (nb == 1) st = launch_collect_nb<double, 1>(ctx, p, smem, grid);
+    else st = launch_collect_nb<double, 2>(ctx, p, smem, grid);
+  } else {
+    switch (nb) {
+      case 1: st = launch_collect_nb<float, 1>(ctx, p, smem, grid); break;
+      case 2: st = launch_collect_nb<float, 2>(ctx, p, smem, grid); break;
+      case 3: st = launch_collect_nb<float, 3>(ctx, p, smem, grid); break;
+      case 4: st = launch_collect_nb<float, 4>(ctx, p, smem, grid); break;
+      default: st = launch_collect_nb<float, 7>(ctx, p, smem, grid); break;
+    }
+  }
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  return st;
+}
+
+// ================================================================================================
+// K4: predict — all layers + readout (+ feedback) in one persistent kernel, one CTA per sequence.
+//   model call  src/reservoircomputer.jl:90-94, src/models/esn_deep.jl:190-217
+//   readout     src/layers/basic.jl:171-182   y = psi(W_out*z (+ b))
+//   loops       src/predict.jl:74-88 (autoregressive), :163-177 (teacher-forced)
+// ================================================================================================
+struct PredLayer {
+  int n, npad, d_in, feat, R, npos;
+  const uint16_t* perm; const int32_t* blk_off; const int32_t* blk_w2; const float2* vals; const uint32_t* cols;
+  const float* Win; const float* bias; const float* leakv;
+  double leak; int act; FusedMod mod;
+  int h_off;   // element offset of this layer's state double-buffer in smem
+  int c_off;   // row offset of this layer in the packed carry array
+};
+struct PredParams {
+  int n_layers, nthreads, nwarps, in_dims, d_out, feat, sumN, zmax;
+  int autoregressive, ro_act;
+  PredLayer L[RCB_MAX_LAYERS];
+  const double* Wout; const double* bout; long long readout_members;
+  const float* member_scale; const float* member_leak;
+  const void* u; int u_is_f64;
+  long long T, B;
+  void* h;      // sumN x B (compute dtype) in/out, may be null
+  double* y;    // d_out x T x B
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long seq = blockIdx.x;
+  // smem: per layer 2 x npad state | z buffer (zmax) | input buffer (in_dims) | reduction (nwarps x d_out doubles)
+  T* base = reinterpret_cast<T*>(smem);
+  int total_h = 0;
+  for (int l = 0; l < p.n_layers; ++l) total_h += 2 * p.L[l].npad;
+  T* z_s = base + total_h;
+  T* in_s = z_s + p.zmax;
+  size_t red_off = (size_t)(total_h + p.zmax + ((p.in_dims + 3) & ~3)) * sizeof(T);
+  red_off = (red_off + 7) & ~(size_t)7;  // keep the double array 8-byte aligned
+  double* red_s = reinterpret_cast<double*>(smem + red_off);
+  double* y_s = red_s + (size_t)p.nwarps * p.d_out;  // [d_out]
+  T* h_g = reinterpret_cast<T*>(p.h);
+  for (int l = 0; l < p.n_layers; ++l) {
+    const PredLayer& L = p.L[l];
+    T* h0s = base + L.h_off;
+    for (int i = tid; i < L.npad; i += p.nthreads) {
+      T v = (h_g && i < L.n) ? h_g[(size_t)seq * p.sumN + L.c_off + i] : T(0);
+      h0s[i] = v;
+      h0s[L.npad + i] = v;
+    }
+  }
+  if (tid < p.in_dims) {
+    if (p.autoregressive)
+      in_s[tid] = p.u_is_f64 ? (T) reinterpret_cast<const double*>(p.u)[(size_t)seq * p.in_dims + tid]
+                             : (T) reinterpret_cast<const float*>(p.u)[(size_t)seq * p.in_dims + tid];
+  }
+  const double* Wout = p.Wout + (p.readout_members > 1 ? (size_t)seq * p.d_out * p.feat : 0);
+  const double* bout = p.bout ? p.bout + (p.readout_members > 1 ? (size_t)seq * p.d_out : 0) : nullptr;
+  const T mscale = p.member_scale ? (T)p.member_scale[seq] : T(1);
+  __syncthreads();
+
+  for (long long t = 0; t < p.T; ++t) {
+    if (!p.autoregressive) {
+      if (tid < p.in_dims) {
+        size_t idx = ((size_t)seq * p.T + t) * p.in_dims + tid;
+        in_s[tid] = p.u_is_f64 ? (T) reinterpret_cast<const double*>(p.u)[idx] : (T) reinterpret_cast<const float*>(p.u)[idx];
+      }
+      __syncthreads();
+    }
+    const T* xin = in_s;
+    for (int l = 0; l < p.n_layers; ++l) {
+      const PredLayer& L = p.L[l];
+      const T* cur = base + L.h_off + (t & 1) * L.npad;
+      T* nxt = base + L.h_off + ((t + 1) & 1) * L.npad;
+      for (int k = 0; k < L.R; ++k) {
+        const int pos = k * p.nthreads + tid;
+        const unsigned r16 = __ldg(L.perm + pos);
+        const bool valid = r16 != 0xFFFFu;
+        const int r = valid ? (int)r16 : 0;
+        T acc = T(0);
+        const int blk = k * p.nwarps + warp;
+        const int off = __ldg(L.blk_off + blk), w2 = __ldg(L.blk_w2 + blk);
+        const float2* vp = L.vals + (size_t)off * 32 + lane;
+        const uint32_t* cp = L.cols + (size_t)off * 32 + lane;
+        for (int j = 0; j < w2; ++j) {
+          const float2 v = __ldg(vp + (size_t)j * 32);
+          const uint32_t c = __ldg(cp + (size_t)j * 32);
+          acc = fma((T)v.x, cur[c & 0xFFFFu], acc);
+          acc = fma((T)v.y, cur[c >> 16], acc);
+        }
+        if (l == 0) acc *= mscale;
+        if (L.bias) acc += (T)__ldg(L.bias + r);
+        T win = T(0);
+        for (int d = 0; d < L.d_in; ++d) win = fma((T)__ldg(L.Win + (size_t)d * L.npos + pos), xin[d], win);
+        T lc = L.leakv ? (T)__ldg(L.leakv + r) : (T)L.leak;
+        if (l == 0 && p.member_leak) lc = (T)p.member_leak[seq];
+        const T cand = apply_act<T>(L.act, win + acc);
+        const T hn = (T(1) - lc) * cur[r] + lc * cand;
+        if (valid) nxt[r] = hn;
+      }
+      __syncthreads();
+      // modified state of this layer -> z buffer (input of the next layer / of the readout)
+      for (int f = tid; f < L.feat; f += p.nthreads) {
+        T zz[1];
+        feature_eval<T, 1>(L.mod, reinterpret_cast<const unsigned char*>(nxt), L.npad, L.n, f, zz);
+        z_s[f] = zz[0];
+      }
+      __syncthreads();
+      xin = z_s;
+    }
+    // readout: y = psi(W_out z + b), accumulated in Float64 (W_out is Float64, basic.jl:171-182)
+    for (int o = 0; o < p.d_out; ++o) {
+      double part = 0.0;
+      for (int f = tid; f < p.feat; f += p.nthreads) part = fma(__ldg(Wout + (size_t)f * p.d_out + o), (double)z_s[f], part);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sh);
+      if (lane == 0) red_s[(size_t)warp * p.d_out + o] = part;
+    }
+    __syncthreads();
+    if (tid < p.d_out) {
+      double ysum = 0.0;
+      for (int w = 0; w < p.nwarps; ++w) ysum += red_s[(size_t)w * p.d_out + tid];
+      if (bout) ysum += bout[tid];
+      ysum = apply_act<double>(p.ro_act, ysum);
+      p.y[((size_t)seq * p.T + t) * p.d_out + tid] = ysum;
+      y_s[tid] = ysum;
+    }
+    __syncthreads();
+    if (p.autoregressive && tid < p.in_dims) in_s[tid] = (T)y_s[tid];  // y becomes the next input (predict.jl:83)
+    __syncthreads();
+  }
+  if (h_g) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      const PredLayer& L = p.L[l];
+      const T* fin = base + L.h_off + (p.T & 1) * L.npad;
+      for (int i = tid; i < L.n; i += p.nthreads) h_g[(size_t)seq * p.sumN + L.c_off + i] = fin[i];
+    }
+  }
+}
+
+int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
+  const rcb_esn& E = *a.esn;
+  PredParams p{};
+  p.n_layers = (int)E.layers.size();
+  p.in_dims = E.desc.in_dims; p.d_out = E.desc.out_dims; p.feat = E.feat; p.sumN = E.sumN;
+  p.autoregressive = a.autoregressive ? 1 : 0; p.ro_act = E.desc.readout_activation;
+  int nthreads = 32, zmax = 4, h_off = 0, c_off = 0;
+  for (const Layer& L : E.layers) nthreads = nthreads > L.sell.nthreads ? nthreads : L.sell.nthreads;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const Layer& L = E.layers[l];
+    if (L.sell.nthreads != nthreads)
+      return fail(RCB_ERR_UNSUPPORTED, "predict needs all layers built for the same CTA width (layer %d: %d vs %d)", l, L.sell.nthreads, nthreads);
+    PredLayer& q = p.L[l];
+    q.n = L.n; q.npad = (L.n + 3) & ~3; q.d_in = L.d_in; q.feat = L.feat; q.R = L.sell.R; q.npos = L.sell.R * L.sell.nthreads;
+    q.perm = L.sell.perm; q.blk_off = L.sell.blk_off; q.blk_w2 = L.sell.blk_w2; q.vals = L.sell.vals; q.cols = L.sell.cols;
+    q.Win = L.d_Win; q.bias = L.desc.use_bias ? L.d_bias : nullptr; q.leakv = L.desc.leak_is_vector ? L.d_leak : nullptr;
+    q.leak = L.desc.leak_scalar; q.act = L.desc.activation; q.mod = make_fused(L);
+    q.h_off = h_off; q.c_off = c_off;
+    h_off += 2 * q.npad; c_off += L.n;
+    zmax = zmax > L.feat ? zmax : L.feat;
+    if (!chain_is_fusable(L.chain))
+      return fail(RCB_ERR_UNSUPPORTED, "predict supports modifier chains of the form [], [X], [Pad], [X, Pad] (layer %d)", l);
+  }
+  p.nthreads = nthreads; p.nwarps = nthreads / 32; p.zmax = (zmax + 3) & ~3;
+  p.Wout = E.d_Wout; p.bout = E.d_bout; p.readout_members = E.readout_members;
+  p.member_scale = E.member_count ? E.d_member_scale : nullptr;
+  p.member_leak = E.member_count ? E.d_member_leak : nullptr;
+  p.u = a.u; p.u_is_f64 = E.desc.data_dtype == RCB_F64; p.T = a.T; p.B = a.B; p.h = a.h; p.y = a.y;
+  const size_t esz = a.compute_dtype == RCB_F64 ? 8 : 4;
+  size_t smem = ((size_t)h_off + p.zmax + ((p.in_dims + 3) & ~3)) * esz;
+  smem = (smem + 7) & ~(size_t)7;
+  smem += ((size_t)p.nwarps * p.d_out + p.d_out) * sizeof(double) + 16;
+  if (smem > ctx->smem_optin)
+    return fail(RCB_ERR_UNSUPPORTED, "predict state (%zu B) does not fit shared memory (%zu B)", smem, ctx->smem_optin);
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  if (a.compute_dtype == RCB_F64) {
+    RCB_CUDA(cudaFuncSetAttribute(k4_predict_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k4_predict_kernel<double><<<(int)a.B, nthreads, smem, ctx->stream>>>(p);
+  } else {
+    RCB_CUDA(cudaFuncSetAttribute(k4_predict_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k4_predict_kernel<float><<<(int)a.B, nthreads, smem, ctx->stream>>>(p);
+  }
+  ctx->launches++;
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+}  // namespace rcb

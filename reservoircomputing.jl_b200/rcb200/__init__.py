@@ -1,0 +1,11 @@
+"""rcb200 — host-side mirror of ReservoirComputing.jl's ESN hot-path API over librcb200.so (B200, sm_100a).
+
+There is no CPU fallback: every call ends in a CUDA kernel of the in-tree library, and importing
+this package without the built library raises on first use."""
+from ._lib import (ArgumentError, CudaError, DimensionMismatch, NumericError, UnsupportedError, LIB_PATH,
+                   GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, lib)
+from .api import (NT, Device, DeepESN, ESN, ESNCell, ExtendedSquare, LinearReadout, NLAT1, NLAT2, NLAT3, Pad,
+                  PartialSquare, QRFactorization, QRSolver, RidgeRegression, StandardRidge, addreadout,
+                  apply_modifiers, collectstates, csr_from_matrix, default_device, device_count, export_csr, fit_readout, identity,
+                  predict, rand32, rand_sparse, randn32, relu, resetcarry, scaled_rand, setup, sigmoid, tanh,
+                  tanh_fast, train, zeros32)

@@ -1,0 +1,765 @@
+"""Host-side mirror of the reference's operator interface for the ESN hot path.
+
+Julia is not available in the build image, so the host side above the C-ABI is written in Python
+with the same names, argument meaning and error behaviour as the reference:
+
+    ESN / DeepESN / ESNCell / LinearReadout        src/models/esn.jl:93-106, esn_deep.jl:102-147,
+                                                   src/layers/esn_cell.jl:127-148, basic.jl:139-154
+    NLAT1/NLAT2/NLAT3/Pad/PartialSquare/ExtendedSquare   src/states.jl
+    setup(rng, model) -> (ps, st)                  LuxCore.setup; reservoircomputer.jl:51-63
+    collectstates(rc, data, ps, st)                src/reservoircomputer.jl:96-133
+    train(rc, X, Y, ps, st; objective, washout, return_states)   src/train.jl:232-251
+    predict(rc, steps|data, ps, st; initialdata)   src/predict.jl:55-60,90-103,118-129
+    fit_readout(objective, states, targets)        __fit_readout, src/train.jl:100-106
+    addreadout / resetcarry                        reservoircomputer.jl:137-144,207-232
+
+All numerics run in librcb200.so on the B200; this module only marshals arrays (column-major,
+features x time) and threads the functional ``ps`` / ``st`` values.  Extension over the reference:
+``data`` may be 3-D ``(d_in, T, B)`` for B independent sequences (the reference loops over them).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import ArgumentError, DimensionMismatch, check, lib, ptr
+
+
+# ---- tiny immutable NamedTuple stand-in ---------------------------------------------------------
+class NT:
+    """Immutable record with ``merge`` (Julia ``merge(nt, (; k = v))``)."""
+
+    def __init__(self, **kw):
+        object.__setattr__(self, "_d", dict(kw))
+
+    def __getattr__(self, k):
+        try:
+            return self._d[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        raise AttributeError("ps/st records are immutable; use merge()")
+
+    def merge(self, **kw):
+        d = dict(self._d)
+        d.update(kw)
+        return NT(**d)
+
+    def keys(self):
+        return self._d.keys()
+
+    def __contains__(self, k):
+        return k in self._d
+
+    def __repr__(self):
+        return "(" + ", ".join(f"{k} = {type(v).__name__ if isinstance(v, np.ndarray) else v!r}" for k, v in self._d.items()) + ")"
+
+    def __eq__(self, o):
+        if not isinstance(o, NT) or self._d.keys() != o._d.keys():
+            return False
+        for k in self._d:
+            a, b = self._d[k], o._d[k]
+            if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+                if not np.array_equal(a, b):
+                    return False
+            elif isinstance(a, np.random.Generator):
+                continue
+            elif a != b:
+                return False
+        return True
+
+
+# ---- activations / modifiers --------------------------------------------------------------------
+def identity(x):
+    return x
+
+
+def tanh(x):
+    return np.tanh(x)
+
+
+def tanh_fast(x):
+    return np.tanh(x)
+
+
+def sigmoid(x):
+    return 1 / (1 + np.exp(-x))
+
+
+def relu(x):
+    return np.maximum(x, 0)
+
+
+_ACT_IDS = {identity: L.ACT_IDENTITY, tanh: L.ACT_TANH, np.tanh: L.ACT_TANH, tanh_fast: L.ACT_TANH_FAST,
+            sigmoid: L.ACT_SIGMOID, relu: L.ACT_RELU}
+
+
+def _act_id(f) -> int:
+    if f in _ACT_IDS:
+        return _ACT_IDS[f]
+    raise L.UnsupportedError(f"activation {f!r} is not implemented by the B200 recurrence "
+                             "(identity, tanh, tanh_fast, sigmoid, relu)")
+
+
+class _Modifier:
+    kind = 0
+    param = 0.0
+
+    def __call__(self, x):  # modifiers are stateless functions in the reference
+        x = np.asarray(x)
+        vec = x.ndim == 1
+        X = np.asfortranarray(x.reshape(x.shape[0], -1))
+        out = apply_modifiers((self,), X)
+        return out[:, 0] if vec else out
+
+    def __repr__(self):
+        return type(self).__name__
+
+
+class _NLAT1(_Modifier):
+    kind = L.MOD_NLAT1
+
+
+class _NLAT2(_Modifier):
+    kind = L.MOD_NLAT2
+
+
+class _NLAT3(_Modifier):
+    kind = L.MOD_NLAT3
+
+
+class _ExtendedSquare(_Modifier):
+    kind = L.MOD_EXTENDED_SQUARE
+
+
+NLAT1, NLAT2, NLAT3, ExtendedSquare = _NLAT1(), _NLAT2(), _NLAT3(), _ExtendedSquare()
+
+
+class Pad(_Modifier):  # src/states.jl:73-77
+    kind = L.MOD_PAD
+
+    def __init__(self, padding=1.0):
+        self.param = float(padding)
+
+    def __repr__(self):
+        return f"Pad({self.param})"
+
+
+class PartialSquare(_Modifier):  # src/states.jl:404-406
+    kind = L.MOD_PARTIAL_SQUARE
+
+    def __init__(self, eta):
+        self.param = float(eta)
+
+
+def _as_mods(m) -> tuple:
+    if m is None:
+        return ()
+    if isinstance(m, (tuple, list)):
+        return tuple(m)
+    return (m,)
+
+
+def _feature_dims(n: int, mods: Sequence[_Modifier]) -> int:
+    for m in mods:
+        if m.kind == L.MOD_PAD:
+            n += 1
+        elif m.kind == L.MOD_EXTENDED_SQUARE:
+            n *= 2
+    return n
+
+
+# ---- device context -----------------------------------------------------------------------------
+class Device:
+    """One GPU + one stream (rcb_ctx).  ``stream`` may be a raw cudaStream_t (e.g. torch's)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        h = C.c_void_p()
+        check(lib().rcb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def synchronize(self):
+        check(lib().rcb_ctx_synchronize(self.handle))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        check(lib().rcb_ctx_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+    def kernel_ms(self, which: int) -> float:
+        ms = C.c_float()
+        check(lib().rcb_ctx_last_kernel_ms(self.handle, which, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self.handle:
+            lib().rcb_ctx_destroy(self.handle)
+            self.handle = None
+
+
+_default = {}
+
+
+def default_device(device: Optional[int] = None) -> Device:
+    import os
+
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default:
+        _default[device] = Device(device)
+    return _default[device]
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    check(lib().rcb_device_count(C.byref(n)))
+    return n.value
+
+
+# ---- initializers (host-side producers) ------------------------------------
+class _Init:
+    """Curried initializer: ``rand_sparse(radius=1.2, sparsity=6/300)`` returns a callable
+    ``(rng, *dims) -> array`` (src/initializer_utils.jl:39-73).  Values come from NumPy streams:
+    parity with Julia's RNG streams is unpinned upstream."""
+
+    def __init__(self, fn, **kw):
+        self.fn, self.kw = fn, kw
+
+    def __call__(self, *args, **kw):
+        if args and isinstance(args[0], np.random.Generator):
+            k = dict(self.kw)
+            k.update(kw)
+            return self.fn(*args, **k)
+        k = dict(self.kw)
+        k.update(kw)
+        return _Init(self.fn, **k)
+
+
+def _spectral_radius(W) -> float:
+    import scipy.sparse as sp
+
+    n = W.shape[0]
+    if n <= 1500:  # dense eigvals, src/inits/inits_components.jl:127
+        Wd = W.toarray() if sp.issparse(W) else np.asarray(W)
+        return float(np.max(np.abs(np.linalg.eigvals(Wd.astype(np.float64)))))
+    import scipy.sparse.linalg as spla  # sparse Arnoldi above that: setup only
+
+    v0 = np.random.default_rng(0).standard_normal(n)
+    vals = spla.eigs(sp.csr_matrix(W).astype(np.float64), k=6, which="LM", v0=v0, return_eigenvectors=False,
+                     tol=1e-10, maxiter=20000)
+    return float(np.max(np.abs(vals)))
+
+
+def _rand_sparse(rng, *dims, radius=1.0, sparsity=0.1, std=1.0, return_sparse=False):
+    """src/inits/inits_reservoir.jl:55-67: sparse_init(sparsity = 1 - s) then scale_radius!."""
+    import scipy.sparse as sp
+
+    n, m = dims
+    if n != m:
+        raise DimensionMismatch(f"reservoir matrix must be square, got {dims}")
+    k = n - int(math.ceil((1.0 - float(sparsity)) * n))
+    rows = np.argsort(rng.random((n, n)), axis=0)[:k, :] if n <= 2048 else np.stack(
+        [rng.choice(n, size=k, replace=False) for _ in range(n)], axis=1)
+    rows = np.sort(rows, axis=0)
+    vals = (rng.standard_normal((k, n)) * std).astype(np.float32)
+    W = sp.csc_matrix((vals.T.ravel(), rows.T.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    rho = _spectral_radius(W)
+    W = (W * (np.float32(radius) / np.float32(rho))).astype(np.float32).tocsc()
+    if not np.all(np.isfinite(W.data)):
+        raise ArgumentError("Created matrix contains invalid values (NaN/Inf)")
+    return W if return_sparse else np.asfortranarray(W.toarray().astype(np.float32))
+
+
+def _scaled_rand(rng, *dims, scaling=0.1):
+    """src/inits/inits_input.jl:80-88 + apply_scale! (inits_components.jl:1-4)."""
+    x = rng.random(dims, dtype=np.float32)
+    return np.asfortranarray((x - np.float32(0.5)) * (np.float32(2) * np.float32(scaling)))
+
+
+rand_sparse = _Init(_rand_sparse)
+scaled_rand = _Init(_scaled_rand)
+randn32 = _Init(lambda rng, *dims: rng.standard_normal(dims).astype(np.float32))
+rand32 = _Init(lambda rng, *dims: rng.random(dims, dtype=np.float32))
+zeros32 = _Init(lambda rng, *dims: np.zeros(dims, np.float32))
+
+
+# ---- layers / models ------------------------------------------------------------------------------
+class ESNCell:
+    """src/layers/esn_cell.jl:114-148."""
+
+    def __init__(self, in_dims, out_dims, activation=tanh_fast, *, use_bias=False, init_bias=zeros32,
+                 init_reservoir=rand_sparse, init_input=scaled_rand, init_state=randn32, leak_coefficient=1.0):
+        if isinstance(leak_coefficient, (list, tuple, np.ndarray)):
+            leak_coefficient = np.asarray(leak_coefficient)
+            if leak_coefficient.shape[0] != out_dims:
+                raise DimensionMismatch(f"leak_coefficient must have length out_dims={out_dims}, got {leak_coefficient.shape[0]}.")
+        self.in_dims, self.out_dims, self.activation = int(in_dims), int(out_dims), activation
+        self.use_bias, self.init_bias, self.init_reservoir = bool(use_bias), init_bias, init_reservoir
+        self.init_input, self.init_state, self.leak_coefficient = init_input, init_state, leak_coefficient
+
+    def initialparameters(self, rng):  # esn_cell.jl:150-159 — draw order: input, reservoir, bias
+        ps = dict(input_matrix=self.init_input(rng, self.out_dims, self.in_dims),
+                  reservoir_matrix=self.init_reservoir(rng, self.out_dims, self.out_dims))
+        if self.use_bias:
+            ps["bias"] = self.init_bias(rng, self.out_dims)
+        return NT(**ps)
+
+    def initialstates(self, rng):  # esn_cell.jl:161-163, lux_layers.jl:207-210
+        rng.random()
+        return NT(cell=NT(rng=copy.deepcopy(rng)), carry=None)
+
+
+class LinearReadout:
+    """src/layers/basic.jl:129-154."""
+
+    def __init__(self, in_dims, out_dims, activation=identity, *, init_weight=rand32, init_bias=rand32, use_bias=False):
+        self.in_dims, self.out_dims, self.activation = int(in_dims), int(out_dims), activation
+        self.init_weight, self.init_bias, self.use_bias = init_weight, init_bias, bool(use_bias)
+
+    def initialparameters(self, rng):  # basic.jl:156-164
+        ps = dict(weight=self.init_weight(rng, self.out_dims, self.in_dims))
+        if self.use_bias:
+            ps["bias"] = self.init_bias(rng, self.out_dims)
+        return NT(**ps)
+
+
+class ESN:
+    """ESN(in_dims, res_dims, out_dims, activation=tanh; readout_activation, state_modifiers, cell kwargs...)
+    src/models/esn.jl:93-106."""
+
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, readout_activation=identity,
+                 state_modifiers=(), **cell_kw):
+        self.reservoir = ESNCell(in_dims, res_dims, activation, **cell_kw)
+        self.state_modifiers = _as_mods(state_modifiers)
+        self.readout = LinearReadout(res_dims, out_dims, readout_activation)
+        self._cache = {}
+
+    @property
+    def cells(self):
+        return (self.reservoir,)
+
+    @property
+    def layer_modifiers(self):
+        return (self.state_modifiers,)
+
+
+class DeepESN:
+    """DeepESN(in_dims, res_dims::Vector, out_dims, activation=tanh; ...) src/models/esn_deep.jl:102-154.
+    Per-layer kwargs broadcast like __asvec (src/models/esn_generics.jl:51-79)."""
+
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, depth=2, leak_coefficient=1.0,
+                 init_reservoir=rand_sparse, init_input=scaled_rand, init_bias=zeros32, init_state=randn32,
+                 use_bias=False, state_modifiers=(), readout_activation=identity):
+        if isinstance(res_dims, int):
+            res_dims = [res_dims] * depth
+        n = len(res_dims)
+
+        def asvec(x, allow_seq=True):
+            if allow_seq and isinstance(x, (tuple, list)):
+                if len(x) == n:
+                    return list(x)
+                if len(x) == 1:
+                    return [x[0]] * n
+                if len(x) == 0:
+                    return [None] * n
+                raise DimensionMismatch(f"Expected length {n} or 1, got {len(x)}")
+            return [x] * n
+
+        acts, leaks, ires, iinp = asvec(activation), asvec(leak_coefficient), asvec(init_reservoir), asvec(init_input)
+        ibias, istate, ub, mods = asvec(init_bias), asvec(init_state), asvec(use_bias), asvec(state_modifiers)
+        cells, lmods, prev = [], [], int(in_dims)
+        for i in range(n):
+            cells.append(ESNCell(prev, res_dims[i], acts[i], use_bias=ub[i], init_bias=ibias[i], init_reservoir=ires[i],
+                                 init_input=iinp[i], init_state=istate[i], leak_coefficient=leaks[i]))
+            lm = _as_mods(mods[i])
+            lmods.append(lm)
+            prev = _feature_dims(res_dims[i], lm)  # the next cell's in_dims is declared as res_dims[i] upstream
+            if prev != res_dims[i] and i + 1 < n:
+                raise DimensionMismatch("size-changing modifiers between DeepESN layers change the next layer's input size")
+        self._cells, self._mods = tuple(cells), tuple(lmods)
+        self.readout = LinearReadout(res_dims[-1], out_dims, readout_activation)
+        self._cache = {}
+
+    @property
+    def cells(self):
+        return self._cells
+
+    @property
+    def layer_modifiers(self):
+        return self._mods
+
+
+def _is_deep(rc) -> bool:
+    return isinstance(rc, DeepESN)
+
+
+def setup(rng: np.random.Generator, rc):
+    """LuxCore.setup(rng, model) -> (ps, st).  src/reservoircomputer.jl:51-63, esn_deep.jl:156-188."""
+    if _is_deep(rc):
+        ps_cells = tuple(c.initialparameters(rng) for c in rc.cells)
+        ps = NT(cells=ps_cells, state_modifiers=tuple(() for _ in rc.cells), readout=rc.readout.initialparameters(rng))
+        st = NT(cells=tuple(c.initialstates(rng) for c in rc.cells), state_modifiers=tuple(() for _ in rc.cells), readout=NT())
+    else:
+        ps = NT(reservoir=rc.reservoir.initialparameters(rng), state_modifiers=tuple(NT() for _ in rc.state_modifiers),
+                readout=rc.readout.initialparameters(rng))
+        st = NT(reservoir=rc.reservoir.initialstates(rng), state_modifiers=tuple(NT() for _ in rc.state_modifiers), readout=NT())
+    return ps, st
+
+
+def _cell_ps(rc, ps):
+    return ps.cells if _is_deep(rc) else (ps.reservoir,)
+
+
+def _cell_st(rc, st):
+    return st.cells if _is_deep(rc) else (st.reservoir,)
+
+
+def _with_cell_st(rc, st, new):
+    return st.merge(cells=tuple(new)) if _is_deep(rc) else st.merge(reservoir=new[0])
+
+
+# ---- device handle --------------------------------------------------------------------------------
+class _Handle:
+    def __init__(self, rc, ps, dtype, dev: Device):
+        import scipy.sparse as sp
+
+        cells, lmods = rc.cells, rc.layer_modifiers
+        nl = len(cells)
+        if nl > L.MAX_LAYERS:
+            raise L.UnsupportedError(f"at most {L.MAX_LAYERS} layers")
+        layers = (L.LayerDesc * nl)()
+        for i, c in enumerate(cells):
+            d = layers[i]
+            d.res_dims, d.activation, d.use_bias = c.out_dims, _act_id(c.activation), int(c.use_bias)
+            vec = isinstance(c.leak_coefficient, np.ndarray)
+            d.leak_is_vector = int(vec)
+            d.leak_scalar = 0.0 if vec else float(c.leak_coefficient)
+            if len(lmods[i]) > L.MAX_MODIFIERS:
+                raise L.UnsupportedError(f"at most {L.MAX_MODIFIERS} state modifiers per layer")
+            d.n_modifiers = len(lmods[i])
+            for j, m in enumerate(lmods[i]):
+                if not isinstance(m, _Modifier):
+                    raise L.UnsupportedError(f"state modifier {m!r} has no B200 implementation")
+                d.modifier_kind[j], d.modifier_param[j] = m.kind, float(m.param)
+        desc = L.EsnDesc(nl, cells[0].in_dims, rc.readout.out_dims, _act_id(rc.readout.activation),
+                         int(rc.readout.use_bias), L.dtype_id(dtype))
+        h = C.c_void_p()
+        check(lib().rcb_esn_create(dev.handle, C.byref(desc), layers, C.byref(h)))
+        self.handle, self.dev, self.keep = h, dev, []
+        for i, (c, p) in enumerate(zip(cells, _cell_ps(rc, ps))):
+            Win = np.asfortranarray(p.input_matrix, dtype=np.float32)
+            bias = np.ascontiguousarray(p.bias, dtype=np.float32) if c.use_bias else None
+            W = p.reservoir_matrix
+            if sp.issparse(W):  # SparseMatrixCSC hand-off (ext/RCSparseArraysExt.jl:5-7): 1-based Int64
+                Wc = sp.csc_matrix(W)
+                colptr = (Wc.indptr.astype(np.int64) + 1)
+                rowval = (Wc.indices.astype(np.int64) + 1)
+                nz = np.ascontiguousarray(Wc.data, dtype=np.float32)
+                check(lib().rcb_esn_set_weights_csc(h, i, ptr(colptr), ptr(rowval), ptr(nz), ptr(Win), Win.shape[0], ptr(bias)))
+            else:
+                Wd = np.asfortranarray(W, dtype=np.float32)
+                check(lib().rcb_esn_set_weights_dense(h, i, ptr(Wd), Wd.shape[0], ptr(Win), Win.shape[0], ptr(bias)))
+            if isinstance(c.leak_coefficient, np.ndarray):
+                lv = np.ascontiguousarray(c.leak_coefficient, dtype=np.float32)
+                check(lib().rcb_esn_set_leak_vector(h, i, ptr(lv)))
+        F, sN = C.c_int32(), C.c_int32()
+        check(lib().rcb_esn_feature_dims(h, C.byref(F)))
+        check(lib().rcb_esn_carry_dims(h, C.byref(sN)))
+        self.F, self.sumN = F.value, sN.value
+        self.readout_key = None
+
+    def set_readout(self, ps_ro, use_bias):
+        key = (id(ps_ro.weight), id(ps_ro.bias) if use_bias else None)
+        if key == self.readout_key:
+            return
+        W = np.asfortranarray(ps_ro.weight, dtype=np.float64)
+        if W.shape[1] != self.F:
+            raise DimensionMismatch(f"readout weight has {W.shape[1]} columns but the model produces {self.F} features")
+        b = np.ascontiguousarray(ps_ro.bias, dtype=np.float64) if use_bias else None
+        check(lib().rcb_esn_set_readout(self.handle, ptr(W), ptr(b), 1))
+        self.readout_key = key
+        self.keep = [ps_ro.weight, ps_ro.bias if use_bias else None]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().rcb_esn_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def _handle(rc, ps, dtype, dev: Optional[Device] = None) -> _Handle:
+    dev = dev or default_device()
+    cps = _cell_ps(rc, ps)
+    key = (np.dtype(dtype).str, dev.device) + tuple(id(getattr(p, k)) for p in cps for k in ("input_matrix", "reservoir_matrix"))
+    ent = rc._cache.get(key)
+    if ent is None:
+        ent = (_Handle(rc, ps, dtype, dev), cps)  # keep ps alive so ids are not recycled
+        rc._cache.clear()
+        rc._cache[key] = ent
+    return ent[0]
+
+
+def _initial_carry(rc, st, dtype, B):
+    """h0 for every layer: the stored carry, or a fresh init_state draw from the replicated rng
+    (src/layers/esn_cell.jl:169-173, src/layers/lux_layers.jl:35-46,212-216).  Returns
+    (packed (sumN, B) array, new per-layer cell states with advanced rngs)."""
+    parts, new_st = [], []
+    for c, s in zip(rc.cells, _cell_st(rc, st)):
+        if s.carry is None:
+            rng = copy.deepcopy(s.cell.rng)
+            h = np.asarray(c.init_state(rng, c.out_dims, B), dtype=dtype).reshape(c.out_dims, B)
+            new_st.append(s.merge(cell=NT(rng=rng)))
+        else:
+            h = np.asarray(s.carry[0], dtype=dtype).reshape(c.out_dims, -1)
+            if h.shape[1] != B:
+                raise DimensionMismatch(f"carry holds {h.shape[1]} sequences, data has {B}")
+            new_st.append(s)
+        parts.append(h)
+    return np.asfortranarray(np.concatenate(parts, axis=0)), new_st
+
+
+def _store_carry(rc, st, cell_sts, hT, vector: bool):
+    out, off = [], 0
+    for c, s in zip(rc.cells, cell_sts):
+        h = hT[off:off + c.out_dims]
+        off += c.out_dims
+        out.append(s.merge(carry=(np.ascontiguousarray(h[:, 0]) if vector else np.asfortranarray(h),)))
+    return _with_cell_st(rc, st, out)
+
+
+def _as3d(data):
+    data = np.asarray(data)
+    if data.ndim == 1:
+        data = data[:, None]
+    vec = data.ndim == 2
+    d3 = data[:, :, None] if vec else data
+    return np.asfortranarray(d3), vec
+
+
+# ---- collectstates / train / predict ---------------------------------------------------------------
+def collectstates(rc, data, ps, st, device: Optional[Device] = None):
+    """states (F, T[, B]) with eltype(data), and the new st (final carry stored).
+    src/reservoircomputer.jl:96-133, src/models/esn_deep.jl:261-291."""
+    d3, vec = _as3d(data)
+    if d3.shape[1] < 1:
+        raise ArgumentError(f"collectstates data must have at least one column, got {d3.shape[1]}.")
+    dtype = d3.dtype
+    h = _handle(rc, ps, dtype, device)
+    _, T, B = d3.shape
+    h0, cell_sts = _initial_carry(rc, st, dtype, B)
+    states = np.empty((h.F, T, B), dtype=dtype, order="F")
+    hT = np.empty((h.sumN, B), dtype=dtype, order="F")
+    check(lib().rcb_collect(h.handle, ptr(d3), T, B, ptr(h0), ptr(states), ptr(hT)))
+    st2 = _store_carry(rc, st, cell_sts, hT, vec)
+    return (states[:, :, 0] if vec else states), st2
+
+
+class RidgeRegression:
+    """src/train.jl:24-34.  ``RidgeRegression(np.float32, lam)`` keeps a Float32 λ."""
+
+    def __init__(self, *args):
+        if len(args) == 0:
+            self.reg, self.reg_dtype = 0.0, np.dtype(np.float64)
+        elif len(args) == 1:
+            self.reg = args[0]
+            self.reg_dtype = np.dtype(type(args[0])) if isinstance(args[0], np.floating) else np.dtype(np.float64)
+        else:
+            self.reg_dtype = np.dtype(args[0])
+            self.reg = self.reg_dtype.type(args[1])
+
+
+StandardRidge = RidgeRegression  # src/deprecated.jl:4
+
+
+class QRFactorization:  # solver facades (src/train.jl:85-98); both map onto the FP64 Cholesky kernel
+    pass
+
+
+class QRSolver:
+    pass
+
+
+def _promote(objective, *arrays):
+    T = objective.reg_dtype
+    for a in arrays:
+        T = np.promote_types(T, a.dtype)
+    if not np.issubdtype(T, np.floating):
+        T = np.dtype(np.float64)
+    return T
+
+
+def _check_solver(solver):
+    if solver is None or isinstance(solver, (QRFactorization, QRSolver)):
+        return
+    raise ArgumentError(f"solver {type(solver).__name__} is not supported. Pass QRFactorization(), QRSolver(), "
+                        "or a documented LinearSolve.jl algorithm instead.")
+
+
+def fit_readout(objective: RidgeRegression, states, targets, solver=None, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+    """__fit_readout(::RidgeRegression, states (F, S), targets (d_out, S)) -> W (d_out, F).
+    src/train.jl:100-198."""
+    _check_solver(solver)
+    Z, Y = np.asarray(states), np.asarray(targets)
+    if Z.dtype not in (np.float32, np.float64):
+        Z = Z.astype(np.float64)
+    if Y.dtype not in (np.float32, np.float64):
+        Y = Y.astype(np.float64)
+    Z, Y = np.asfortranarray(Z), np.asfortranarray(Y)
+    dev = device or default_device()
+    F, d_out = Z.shape[0], Y.shape[0]
+    W = np.empty((d_out, F), dtype=np.float64, order="F")
+    check(lib().rcb_fit_readout(dev.handle, ptr(Z), L.dtype_id(Z.dtype), F, Z.shape[1], max(F, 1), ptr(Y), L.dtype_id(Y.dtype),
+                                d_out, Y.shape[1], max(d_out, 1), float(objective.reg), gram_mode, ptr(W)))
+    return W.astype(_promote(objective, Z, Y))
+
+
+def addreadout(rc, output_matrix, ps, st):
+    """addreadout!(rc, W, ps, st): functional update of ps.readout.weight (reservoircomputer.jl:137-144)."""
+    return ps.merge(readout=ps.readout.merge(weight=output_matrix)), st
+
+
+def train(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, solver=None, washout: int = 0,
+          return_states: bool = False, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+    """train(rc, X, Y, ps, st; objective = RidgeRegression(0.0), solver, washout, return_states)
+    -> (ps, st) or ((ps, st), states_wo).  src/train.jl:232-251."""
+    objective = objective or RidgeRegression(0.0)
+    _check_solver(solver)
+    d3, vec = _as3d(train_data)
+    y3, _ = _as3d(target_data)
+    if y3.dtype not in (np.float32, np.float64):
+        y3 = np.asfortranarray(y3.astype(np.float64))
+    dtype = d3.dtype
+    _, T, B = d3.shape
+    if T < 1:
+        raise ArgumentError(f"collectstates data must have at least one column, got {T}.")
+    if washout < 0:
+        raise ArgumentError(f"washout must be ≥ 0, got {washout}")
+    if washout >= T:
+        raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
+    if y3.shape[1] != T or y3.shape[2] != B:
+        raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
+    h = _handle(rc, ps, dtype, device)
+    h0, cell_sts = _initial_carry(rc, st, dtype, B)
+    d_out = y3.shape[0]
+    if d_out != rc.readout.out_dims:
+        # the declared readout size is ignored by train (basic.jl:121-124); the kernel handle is sized by out_dims
+        raise DimensionMismatch(f"targets have {d_out} rows but the readout was declared with out_dims={rc.readout.out_dims}")
+    W = np.empty((d_out, h.F), dtype=np.float64, order="F")
+    hT = np.empty((h.sumN, B), dtype=dtype, order="F")
+    states = np.empty((h.F, T, B), dtype=dtype, order="F") if return_states else None
+    check(lib().rcb_train(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B, int(washout), float(objective.reg), gram_mode,
+                          ptr(h0), ptr(W), ptr(states), ptr(hT)))
+    W = W.astype(_promote(objective, d3, y3))
+    ps2, st2 = addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
+    if return_states:
+        sw = states[:, washout:, :]
+        return (ps2, st2), (sw[:, :, 0] if vec else sw)
+    return ps2, st2
+
+
+def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Device] = None):
+    """predict(rc, steps::Integer, ps, st; initialdata) — autoregressive (src/predict.jl:55-60,74-88);
+    predict(rc, data::AbstractMatrix, ps, st) — teacher-forced (:90-103,163-177).
+    Returns (outputs (d_out, T[, B]), st)."""
+    Wro = np.asarray(ps.readout.weight)
+    if isinstance(steps_or_data, (int, np.integer)):
+        steps = int(steps_or_data)
+        if initialdata is None:
+            raise ArgumentError("autoregressive predict needs initialdata")
+        if steps < 1:
+            raise ArgumentError(f"steps must be ≥ 1, got {steps}")
+        u0 = np.asarray(initialdata)
+        vec = u0.ndim == 1
+        u0 = np.asfortranarray(u0.reshape(u0.shape[0], -1))
+        data_dtype = u0.dtype if u0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+        u0 = u0.astype(data_dtype)
+        B = u0.shape[1]
+        # Float64 W_out (default train) feeds Float64 outputs back: the loop runs in Float64 (esn_cell.jl:176)
+        out_dtype = np.promote_types(Wro.dtype, data_dtype)
+        h = _handle(rc, ps, data_dtype, device)
+        h.set_readout(ps.readout, rc.readout.use_bias)
+        h0, cell_sts = _initial_carry(rc, st, out_dtype, B)
+        Y = np.empty((rc.readout.out_dims, steps, B), dtype=np.float64, order="F")
+        check(lib().rcb_predict_autoregressive(h.handle, ptr(u0), steps, B, L.dtype_id(out_dtype), ptr(h0), ptr(Y)))
+        st2 = _store_carry(rc, st, cell_sts, h0, vec)
+        Y = Y.astype(out_dtype)
+        return (Y[:, :, 0] if vec else Y), st2
+    d3, vec = _as3d(steps_or_data)
+    if d3.shape[1] < 1:
+        raise ArgumentError(f"predict data must have at least one column, got {d3.shape[1]}.")
+    dtype = d3.dtype
+    _, T, B = d3.shape
+    h = _handle(rc, ps, dtype, device)
+    h.set_readout(ps.readout, rc.readout.use_bias)
+    h0, cell_sts = _initial_carry(rc, st, dtype, B)
+    Y = np.empty((rc.readout.out_dims, T, B), dtype=np.float64, order="F")
+    check(lib().rcb_predict_teacher(h.handle, ptr(d3), T, B, ptr(h0), ptr(Y)))
+    st2 = _store_carry(rc, st, cell_sts, h0, vec)
+    Y = Y.astype(np.promote_types(Wro.dtype, dtype))
+    return (Y[:, :, 0] if vec else Y), st2
+
+
+def resetcarry(rng, rc, st, init_carry=None):
+    """resetcarry!(rng, rc, st; init_carry) — src/reservoircomputer.jl:207-232, esn_deep.jl:219-259."""
+    new = []
+    for i, (c, s) in enumerate(zip(rc.cells, _cell_st(rc, st))):
+        f = init_carry[i] if isinstance(init_carry, (tuple, list)) else init_carry
+        new.append(s.merge(carry=None if f is None else (np.asarray(f(rng, c.out_dims)),)))
+    return _with_cell_st(rc, st, new)
+
+
+def apply_modifiers(mods, x, device: Optional[Device] = None):
+    """Matrix form of the state modifiers (src/states.jl:1-15): x (n, cols) -> (F, cols)."""
+    mods = _as_mods(mods)
+    X = np.asfortranarray(x)
+    if X.dtype not in (np.float32, np.float64):
+        X = np.asfortranarray(X.astype(np.float64))
+    n, cols = X.shape
+    out = np.empty((_feature_dims(n, mods), cols), dtype=X.dtype, order="F")
+    kinds = (C.c_int32 * max(len(mods), 1))(*[m.kind for m in mods])
+    params = (C.c_double * max(len(mods), 1))(*[float(m.param) for m in mods])
+    dev = device or default_device()
+    check(lib().rcb_apply_modifiers(dev.handle, len(mods), kinds, params, ptr(X), L.dtype_id(X.dtype), n, cols, ptr(out)))
+    return out
+
+
+def export_csr(rc, ps, layer: int = 0, device: Optional[Device] = None):
+    """Canonical CSR (rowptr int64, colind int32, vals float32) the kernels were built from."""
+    h = _handle(rc, ps, np.float32, device)
+    nnz = C.c_int64()
+    check(lib().rcb_esn_csr_nnz(h.handle, layer, C.byref(nnz)))
+    n = rc.cells[layer].out_dims
+    rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
+    check(lib().rcb_esn_export_csr(h.handle, layer, ptr(rowptr), ptr(colind), ptr(vals)))
+    return rowptr, colind, vals
+
+
+def csr_from_matrix(W):
+    """Host-only (no GPU): canonical CSR of a dense (N, N) float32 matrix or a scipy sparse matrix
+    handed over as Julia's SparseMatrixCSC — the routine the device handle itself uses."""
+    import scipy.sparse as sp
+
+    nnz = C.c_int64()
+    if sp.issparse(W):
+        Wc = sp.csc_matrix(W)
+        n = Wc.shape[0]
+        colptr, rowval = Wc.indptr.astype(np.int64) + 1, Wc.indices.astype(np.int64) + 1
+        nz = np.ascontiguousarray(Wc.data, dtype=np.float32)
+        check(lib().rcb_csr_from_csc(ptr(colptr), ptr(rowval), ptr(nz), n, C.byref(nnz), None, None, None))
+        rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
+        check(lib().rcb_csr_from_csc(ptr(colptr), ptr(rowval), ptr(nz), n, C.byref(nnz), ptr(rowptr), ptr(colind), ptr(vals)))
+        return rowptr, colind, vals
+    Wd = np.asfortranarray(W, dtype=np.float32)
+    n = Wd.shape[0]
+    check(lib().rcb_csr_from_dense(ptr(Wd), n, n, C.byref(nnz), None, None, None))
+    rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
+    check(lib().rcb_csr_from_dense(ptr(Wd), n, n, C.byref(nnz), ptr(rowptr), ptr(colind), ptr(vals)))
+    return rowptr, colind, vals

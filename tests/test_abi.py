@@ -1,0 +1,137 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports exactly the
+symbols include/rcb200.h declares; host-only entry points work; compute entry points fail loudly
+(never fall back) without a B200; the host mirror reproduces the reference's argument errors."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import esn_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "reservoircomputing.jl_b200")
+
+
+@pytest.fixture(scope="session")
+def built():
+    sys.path.insert(0, PKG)
+    import build as rcb_build
+
+    return rcb_build.build()
+
+
+@pytest.fixture(scope="session")
+def R(built):
+    import rcb200
+
+    return rcb200
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "rcb200.h")).read()
+    return sorted(set(re.findall(r"RCB_API\s+[\w\s\*]+?\b(rcb_\w+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported(built):
+    declared = _declared_symbols()
+    assert len(declared) >= 28
+    out = subprocess.check_output(["nm", "-D", "--defined-only", built], text=True)
+    exported = sorted(set(re.findall(r"\sT\s(rcb_\w+)", out)))
+    assert exported == declared, (set(declared) ^ set(exported))
+
+
+def test_ctypes_signatures_cover_header(R):
+    from rcb200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    assert R.lib().rcb_version() == 100
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "rcb200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, comments stripped
+    assert "torch" not in code and "at::" not in code and "Tensor" not in code
+    assert re.findall(r"#include\s+<([^>]+)>", code) == ["stdint.h"]
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.replace("cross-check oracle", ""), f"{f} references oracle/"
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(R):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(R.CudaError, match="no CPU fallback"):
+        R.Device(0)
+    esn = R.ESN(3, 20, 3)
+    ps, st = R.setup(np.random.default_rng(0), esn)
+    with pytest.raises(R.CudaError):
+        R.collectstates(esn, np.zeros((3, 4), np.float32), ps, st)
+    with pytest.raises(R.CudaError):
+        R.fit_readout(R.RidgeRegression(1e-3), np.ones((4, 20)), np.ones((2, 20)))
+
+
+# ---- host-only format conversion: index parity is bit-exact ---------------------------------------
+@pytest.mark.parametrize("n,k", [(300, 6), (1024, 6), (64, 1)])
+def test_csr_from_dense_bit_exact(R, n, k):
+    W = O.rand_sparse_like(np.random.default_rng(17), n, radius=0.9, sparsity=k / n)
+    rp, ci, v = R.csr_from_matrix(W)
+    rp0, ci0, v0 = O.dense_to_csr(W)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert v.tobytes() == v0.astype(np.float32).tobytes()
+    assert rp[-1] == n * k
+
+
+def test_csr_from_csc_matches_dense_path(R):
+    Wc = O.rand_sparse_like(np.random.default_rng(3), 200, radius=1.1, sparsity=0.05, as_csc=True)
+    a = R.csr_from_matrix(Wc)
+    b = R.csr_from_matrix(Wc.toarray())
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
+
+
+def test_csr_edge_cases(R):
+    Z = np.zeros((5, 5), np.float32)
+    rp, ci, v = R.csr_from_matrix(Z)  # empty pattern
+    assert rp.tolist() == [0] * 6 and ci.size == 0
+    D = np.full((3, 3), 2.0, np.float32)  # fully dense
+    rp, ci, v = R.csr_from_matrix(D)
+    assert rp.tolist() == [0, 3, 6, 9] and ci.tolist() == [0, 1, 2] * 3
+    Wn = np.zeros((3, 3), np.float32); Wn[1, 2] = np.nan
+    with pytest.raises(R.NumericError, match="invalid values"):
+        R.csr_from_matrix(Wn)
+    Wz = np.zeros((2, 2), np.float32); Wz[0, 1] = -0.0  # -0.0 is a structural zero (iszero)
+    assert R.csr_from_matrix(Wz)[0][-1] == 0
+
+
+# ---- host-mirror argument errors mirror the reference's ------------------------------------------
+def test_constructor_errors(R):
+    with pytest.raises(R.DimensionMismatch, match="leak_coefficient must have length out_dims=6"):
+        R.ESNCell(4, 6, leak_coefficient=np.ones(5))  # esn_cell.jl:135-142
+    with pytest.raises(R.DimensionMismatch):
+        R.DeepESN(3, [10, 10, 10], 3, leak_coefficient=(0.1, 0.2))  # esn_generics.jl:51-66
+
+
+def test_setup_structure_and_draw_order(R):
+    esn = R.ESN(3, 50, 2, init_reservoir=R.rand_sparse(radius=1.2, sparsity=6 / 50), state_modifiers=(R.NLAT2, R.Pad(1.0)))
+    ps1, st1 = R.setup(np.random.default_rng(5), esn)
+    ps2, st2 = R.setup(np.random.default_rng(5), esn)
+    assert ps1 == ps2  # same seed => same parameters (serialization_reproducibility_tests.jl:59-81)
+    assert ps1.reservoir.input_matrix.shape == (50, 3) and ps1.reservoir.reservoir_matrix.shape == (50, 50)
+    assert "bias" not in ps1.reservoir and ps1.readout.weight.shape == (2, 50)
+    assert st1.reservoir.carry is None and "rng" in st1.reservoir.cell
+    assert np.all((ps1.reservoir.reservoir_matrix != 0).sum(axis=0) == 6)
+    assert abs(O.spectral_radius(ps1.reservoir.reservoir_matrix) - 1.2) < 1e-4
+    deep = R.DeepESN(3, [20, 30], 2, state_modifiers=(R.NLAT2,))
+    psd, std = R.setup(np.random.default_rng(1), deep)
+    assert psd.cells[1].input_matrix.shape == (30, 20) and len(std.cells) == 2

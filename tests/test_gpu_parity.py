@@ -1,0 +1,413 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI, via the host mirror rcb200) against the
+CPU oracle on the same seeded inputs, against the reference's golden vectors, and — at full
+BASELINE sizes — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): teacher-forced states ≤ 1e-5 relative (FP32), readout weights
+≤ 1e-4 relative, sparsity pattern bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import esn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "reservoircomputing.jl_b200"))
+
+STATE_RTOL = 1e-5
+WEIGHT_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def R():
+    import build as rcb_build
+
+    rcb_build.build()
+    import rcb200
+
+    return rcb200
+
+
+def _mods_to_oracle(mods):
+    return tuple((m.kind, m.param) for m in mods)
+
+
+def _act_to_oracle(R, f):
+    return {R.identity: O.ACT_IDENTITY, R.tanh: O.ACT_TANH, R.tanh_fast: O.ACT_TANH_FAST, R.sigmoid: O.ACT_SIGMOID,
+            R.relu: O.ACT_RELU}[f]
+
+
+def oracle_layers(R, rc, ps):
+    import scipy.sparse as sp
+
+    cps = ps.cells if isinstance(rc, R.DeepESN) else (ps.reservoir,)
+    out = []
+    for c, p, m in zip(rc.cells, cps, rc.layer_modifiers):
+        W = p.reservoir_matrix
+        W = sp.csr_matrix(W) if (sp.issparse(W) or W.shape[0] > 1500) else np.asarray(W)
+        out.append(O.ESNCellParams(input_matrix=np.asarray(p.input_matrix), reservoir_matrix=W,
+                                   bias=np.asarray(p.bias) if c.use_bias else None, leak=c.leak_coefficient,
+                                   act=_act_to_oracle(R, c.activation), modifiers=_mods_to_oracle(m)))
+    return out
+
+
+def state_err(a, b):
+    """max_t ||a(:,t) - b(:,t)||_inf / max(||b(:,t)||_inf, 1e-30)   (SURVEY.md §8d parity metric)"""
+    num = np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)), axis=0)
+    den = np.maximum(np.max(np.abs(b.astype(np.float64)), axis=0), 1e-30)
+    return float(np.max(num / den))
+
+
+def fixed_h0(R, st, rc, hs):
+    """st with explicit carries (so that GPU and oracle start from the same hidden state)."""
+    return R.resetcarry(None, rc, st, init_carry=[(lambda rng, n, h=h: h) for h in hs])
+
+
+def const_init(M):
+    return lambda rng, *dims: np.asarray(M, dtype=np.float32).reshape(dims)
+
+
+# ---- golden vectors ------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+def test_modifier_goldens(R, T):  # test/states_tests.jl:9-26
+    x = np.arange(1, 10).astype(T)
+    cases = [(R.NLAT1, [1, 2, 9, 4, 25, 6, 49, 8, 81]), (R.NLAT2, [1, 2, 2, 4, 12, 6, 30, 8, 56]),
+             (R.NLAT3, [1, 2, 8, 4, 24, 6, 48, 8, 9]), (R.PartialSquare(0.6), [1, 4, 9, 16, 25, 6, 7, 8, 9]),
+             (R.ExtendedSquare, [1, 2, 3, 4, 5, 6, 7, 8, 9, 1, 4, 9, 16, 25, 36, 49, 64, 81]),
+             (R.Pad(10.0), [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])]
+    for mod, expected in cases:
+        out = mod(x)
+        assert out.dtype == T and np.array_equal(out, np.array(expected, T)), mod
+    x0 = np.arange(0, 10).astype(T)  # doctests src/states.jl:186,257,329
+    assert np.array_equal(R.NLAT2(x0), [0, 1, 0, 3, 6, 5, 20, 7, 42, 9])
+    m = np.arange(21, dtype=T).reshape(3, 7).T
+    assert np.array_equal(R.NLAT2(m), O.nlat2(m))  # matrix form: per column
+    chain = (R.NLAT1, R.NLAT2, R.Pad(3.0), R.ExtendedSquare)  # generic (un-fused) chain
+    assert np.array_equal(R.apply_modifiers(chain, np.asfortranarray(m)), O.apply_modifiers(_mods_to_oracle(chain), m))
+
+
+def test_collectstates_golden_linear_cell(R):  # test/Interface/generic_contracts_tests.jl:296-300
+    esn = R.ESN(2, 2, 2, R.identity, init_input=const_init(np.eye(2)), init_reservoir=const_init(np.eye(2)),
+                init_state=R.zeros32)
+    ps, st = R.setup(np.random.default_rng(0), esn)
+    states, st2 = R.collectstates(esn, np.array([[3, 4], [4, 5]], np.float32), ps, st)
+    assert states.dtype == np.float32
+    assert np.array_equal(states, np.array([[3, 7], [4, 9]], np.float32))
+    assert np.array_equal(st2.reservoir.carry[0], [7, 9])
+    states3, _ = R.collectstates(esn, np.array([[1], [1]], np.float32), ps, st2)  # carry continues
+    assert np.array_equal(states3[:, 0], [8, 10])
+
+
+def test_cell_analytic_cases(R):  # test/Layers/esncell_tests.jl:131-263
+    I3, Z3 = np.eye(3), np.zeros((3, 3))
+    x = np.array([[10], [20], [30]], np.float32)
+    kw = dict(init_state=R.zeros32)
+    e = R.ESN(3, 3, 3, R.identity, init_input=const_init(I3), init_reservoir=const_init(Z3), **kw)
+    ps, st = R.setup(np.random.default_rng(0), e)
+    assert np.allclose(R.collectstates(e, x, ps, st)[0][:, 0], x[:, 0])  # identity + leak 1
+    e0 = R.ESN(3, 3, 3, R.identity, init_input=const_init(I3), init_reservoir=const_init(I3), leak_coefficient=0.0, **kw)
+    ps, st = R.setup(np.random.default_rng(0), e0)
+    st = fixed_h0(R, st, e0, [np.array([4, 5, 6], np.float32)])
+    assert np.allclose(R.collectstates(e0, x, ps, st)[0][:, 0], [4, 5, 6])  # leak 0 keeps h0
+    eb = R.ESN(3, 3, 3, R.identity, init_input=const_init(I3), init_reservoir=const_init(Z3), use_bias=True,
+               init_bias=const_init(np.ones(3)), **kw)
+    ps, st = R.setup(np.random.default_rng(0), eb)
+    assert np.allclose(R.collectstates(eb, x, ps, st)[0][:, 0], x[:, 0] + 1)  # bias adds
+    # scalar vs vector leak (atol 1e-6), batch of 3
+    rng = np.random.default_rng(42)
+    xs = rng.random((4, 1, 3), dtype=np.float32)
+    h0 = rng.random((6, 3), dtype=np.float32)
+    outs = []
+    for leak in (0.3, np.full(6, 0.3, np.float32)):
+        ev = R.ESN(4, 6, 2, R.identity, init_input=const_init(np.eye(6, 4)), init_reservoir=const_init(np.eye(6)),
+                   leak_coefficient=leak, **kw)
+        ps, st = R.setup(np.random.default_rng(0), ev)
+        st = fixed_h0(R, st, ev, [h0])
+        outs.append(R.collectstates(ev, xs, ps, st)[0])
+    assert np.allclose(outs[0], outs[1], atol=1e-6)
+    assert np.allclose(outs[0][:, 0, :], 0.7 * h0 + 0.3 * (np.eye(6, 4) @ xs[:, 0, :] + h0), atol=1e-6)
+
+
+# ---- C1: README Lorenz ESN -----------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c1(R):
+    rng = np.random.default_rng(17)
+    esn = R.ESN(3, 300, 3, init_reservoir=R.rand_sparse(radius=1.2, sparsity=6 / 300), state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(5000 + 1250)
+    data = np.asfortranarray(series[:, :5000].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:5001].astype(np.float32))
+    test = np.asfortranarray(series[:, 5000:6250].astype(np.float32))
+    h0 = np.random.default_rng(1).standard_normal(300).astype(np.float32)
+    st = fixed_h0(R, st, esn, [h0])
+    return dict(esn=esn, ps=ps, st=st, data=data, target=target, test=test, h0=h0)
+
+
+def test_c1_csr_pattern_bit_exact(R, c1):
+    rp, ci, v = R.export_csr(c1["esn"], c1["ps"])
+    rp0, ci0, v0 = O.dense_to_csr(c1["ps"].reservoir.reservoir_matrix)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.tobytes()
+    assert rp[-1] == 1800
+
+
+def test_c1_states_parity(R, c1):
+    states, st2 = R.collectstates(c1["esn"], c1["data"], c1["ps"], c1["st"])
+    ref, hs = O.collectstates(oracle_layers(R, c1["esn"], c1["ps"]), c1["data"], [c1["h0"]])
+    assert states.shape == (300, 5000) and states.dtype == np.float32
+    assert state_err(states, ref) <= STATE_RTOL
+    assert np.max(np.abs(st2.reservoir.carry[0] - hs[0])) <= STATE_RTOL * np.max(np.abs(hs[0]))
+
+
+@pytest.mark.parametrize("lam", [1e-6, 1e-2])
+def test_c1_train_weights_parity(R, c1, lam):
+    (ps2, st2), sw = R.train(c1["esn"], c1["data"], c1["target"], c1["ps"], c1["st"],
+                             objective=R.RidgeRegression(lam), washout=100, return_states=True)
+    W = ps2.readout.weight
+    assert W.shape == (3, 300) and W.dtype == np.float64  # Float64 λ promotes (train.jl:126-129)
+    # solver parity on the SAME states (the reference's own test form, test_train_ridge.jl:93-141)
+    Wref = O.train_ridge_qr(sw, c1["target"][:, 100:], lam)
+    assert np.linalg.norm(W - Wref) / np.linalg.norm(Wref) <= WEIGHT_RTOL
+    # end to end against the oracle's own states
+    Wo, hs, so = O.train(oracle_layers(R, c1["esn"], c1["ps"]), c1["data"], c1["target"], [c1["h0"]], reg=lam, washout=100)
+    assert state_err(sw, so) <= STATE_RTOL
+    pred, pred_o = W @ so.astype(np.float64), Wo @ so.astype(np.float64)
+    assert np.linalg.norm(pred - pred_o) / np.linalg.norm(pred_o) <= WEIGHT_RTOL
+    if lam >= 1e-2:
+        assert np.linalg.norm(W - Wo) / np.linalg.norm(Wo) <= WEIGHT_RTOL
+
+
+def test_c1_predict_parity(R, c1):
+    lam = 1e-6
+    ps2, st2 = R.train(c1["esn"], c1["data"], c1["target"], c1["ps"], c1["st"], objective=R.RidgeRegression(lam))
+    layers = oracle_layers(R, c1["esn"], c1["ps"])
+    W = ps2.readout.weight
+    hT = st2.reservoir.carry[0]
+    # teacher-forced (src/predict.jl:163-177): Float32 state, Float64 readout
+    Y, st3 = R.predict(c1["esn"], c1["test"][:, :200], ps2, st2)
+    Yo, hso = O.predict_teacher(layers, W, c1["test"][:, :200], [hT])
+    assert Y.dtype == np.float64 and Y.shape == (3, 200)
+    assert state_err(Y, Yo) <= 1e-4
+    # autoregressive (src/predict.jl:74-88): Float64 loop after the first feedback; chaotic, so short horizon
+    Ya, st4 = R.predict(c1["esn"], 1250, ps2, st2, initialdata=c1["test"][:, 0])
+    Yao, _ = O.predict_autoregressive(layers, W, 60, c1["test"][:, 0], [hT])
+    assert Ya.shape == (3, 1250) and Ya.dtype == np.float64 and np.all(np.isfinite(Ya))
+    assert state_err(Ya[:, :60], Yao) <= 1e-3
+    assert st4.reservoir.carry[0].dtype == np.float64
+
+
+# ---- batched recurrence: every sequences-per-CTA variant ------------------------------------------
+@pytest.mark.parametrize("B", [1, 5, 150, 300, 500, 900])
+def test_batched_matches_oracle_and_single(R, B):
+    N, T, d = 96, 24, 3
+    rng = np.random.default_rng(100 + B)
+    esn = R.ESN(d, N, 2, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), state_modifiers=(R.NLAT2, R.Pad(1.0)),
+                leak_coefficient=0.5, use_bias=True, init_bias=R.randn32)
+    ps, st = R.setup(rng, esn)
+    data = np.asfortranarray(rng.standard_normal((d, T, B)).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    st = fixed_h0(R, st, esn, [h0])
+    states, st2 = R.collectstates(esn, data, ps, st)
+    assert states.shape == (N + 1, T, B)
+    layers = oracle_layers(R, esn, ps)
+    for b in sorted(set([0, B // 2, B - 1])):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL, b
+        assert np.allclose(st2.reservoir.carry[0][:, b], hs[0], rtol=1e-5, atol=1e-6)
+    # a sequence computed inside a batch is bit-identical to the same sequence computed alone
+    b = B - 1
+    st1 = fixed_h0(R, st, esn, [h0[:, b:b + 1]])
+    alone, _ = R.collectstates(esn, np.asfortranarray(data[:, :, b:b + 1]), ps, st1)
+    assert np.array_equal(alone[:, :, 0], states[:, :, b])
+
+
+@pytest.mark.parametrize("mods", ["none", "nlat1", "nlat3", "psq", "esq", "pad", "esq_pad", "nlat1_nlat2"])
+def test_modifier_chains_in_recurrence(R, mods):
+    chains = dict(none=(), nlat1=(R.NLAT1,), nlat3=(R.NLAT3,), psq=(R.PartialSquare(0.4),), esq=(R.ExtendedSquare,),
+                  pad=(R.Pad(2.5),), esq_pad=(R.ExtendedSquare, R.Pad(1.0)), nlat1_nlat2=(R.NLAT1, R.NLAT2))
+    N, T = 75, 17  # odd N: exercises the NLAT3 upper bound and the scalar store path
+    rng = np.random.default_rng(7)
+    esn = R.ESN(2, N, 2, init_reservoir=R.rand_sparse(radius=0.8, sparsity=0.1), state_modifiers=chains[mods])
+    ps, st = R.setup(rng, esn)
+    data = np.asfortranarray(rng.standard_normal((2, T)).astype(np.float32))
+    h0 = rng.standard_normal(N).astype(np.float32)
+    states, _ = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [h0]))
+    ref, _ = O.collectstates(oracle_layers(R, esn, ps), data, [h0])
+    assert states.shape == ref.shape
+    assert state_err(states, ref) <= STATE_RTOL
+
+
+def test_float64_data_and_sparse_handoff(R):
+    N, T = 128, 40
+    rng = np.random.default_rng(9)
+    esn = R.ESN(1, N, 1, init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.05, return_sparse=True), state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)  # SparseMatrixCSC hand-off (ext/RCSparseArraysExt.jl:5-7)
+    data = np.asfortranarray(O.mackey_glass_series(T)[:, :T])
+    assert data.dtype == np.float64
+    h0 = rng.standard_normal(N)
+    states, _ = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [h0]))
+    ref, _ = O.collectstates(oracle_layers(R, esn, ps), data, [h0])
+    assert states.dtype == np.float64  # eltype follows data (reservoircomputer.jl:123)
+    assert state_err(states, ref) <= 1e-12
+    rp, ci, v = R.export_csr(esn, ps)
+    rp0, ci0, v0 = O.dense_to_csr(ps.reservoir.reservoir_matrix.toarray())
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.tobytes()
+
+
+def test_random_initial_state_when_no_carry(R):  # esn_cell.jl:169-173: h0 ~ init_state from st's rng
+    esn = R.ESN(2, 40, 2)
+    ps, st = R.setup(np.random.default_rng(3), esn)
+    data = np.zeros((2, 3), np.float32)
+    s1, st1 = R.collectstates(esn, data, ps, st)
+    s2, _ = R.collectstates(esn, data, ps, st)
+    assert np.array_equal(s1, s2) and np.any(s1 != 0)  # deterministic given st; non-zero start
+    assert st1.reservoir.carry is not None
+    st_reset = R.resetcarry(None, esn, st1)
+    assert st_reset.reservoir.carry is None
+
+
+# ---- DeepESN --------------------------------------------------------------------------------------
+def test_deep_esn_parity(R):
+    rng = np.random.default_rng(21)
+    res = [64, 96, 80]
+    desn = R.DeepESN(3, res, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.1), leak_coefficient=(1.0, 0.8, 0.6),
+                     state_modifiers=(R.NLAT2, R.NLAT1, (R.NLAT2, R.Pad(1.0))))
+    ps, st = R.setup(rng, desn)
+    T, B = 50, 3
+    data = np.asfortranarray(rng.standard_normal((3, T, B)).astype(np.float32))
+    hs0 = [rng.standard_normal((n, B)).astype(np.float32) for n in res]
+    st = fixed_h0(R, st, desn, hs0)
+    states, st2 = R.collectstates(desn, data, ps, st)
+    assert states.shape == (81, T, B)
+    layers = oracle_layers(R, desn, ps)
+    for b in range(B):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h[:, b] for h in hs0])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
+        for l in range(3):
+            assert np.allclose(st2.cells[l].carry[0][:, b], hs[l], rtol=1e-5, atol=1e-6)
+    # train + autoregressive predict through all layers
+    tgt = np.asfortranarray(rng.standard_normal((3, T, B)).astype(np.float32))
+    ps2, st3 = R.train(desn, data, tgt, ps, st, objective=R.RidgeRegression(1e-3), washout=5)
+    Y, _ = R.predict(desn, 20, ps2, st3, initialdata=data[:, 0, :])
+    hT = [st3.cells[l].carry[0] for l in range(3)]
+    for b in range(B):
+        Yo, _ = O.predict_autoregressive(layers, ps2.readout.weight, 20, data[:, 0, b], [h[:, b] for h in hT])
+        assert state_err(Y[:, :, b], Yo) <= 1e-4
+
+
+# ---- ridge readout: the reference's known-answer tests (test/test_train_ridge.jl) -------------------
+def _random_ridge_problem(rng, T, F, S, D):
+    Z = rng.standard_normal((F, S)).astype(T)
+    tw = rng.standard_normal((D, F)).astype(T)
+    return Z, (tw @ Z + T(0.01) * rng.standard_normal((D, S)).astype(T)).astype(T), tw
+
+
+def test_ridge_closed_form(R):  # :64-91
+    Z = 2.0 * np.eye(4)
+    tw = np.array([[1.0, 0.0, -1.0, 0.5], [0.0, 2.0, 0.0, -0.5]])
+    W = R.fit_readout(R.RidgeRegression(0.25), Z, tw @ Z, solver=R.QRFactorization())
+    assert W.shape == (2, 4) and np.allclose(W, tw * (4.0 / 4.25), rtol=1e-10)
+
+
+@pytest.mark.parametrize("seed,F,S,D,lam", [(7, 5, 60, 2, 1e-2), (3, 8, 20, 3, 1e-4), (19, 4, 50, 2, 0.0),
+                                            (41, 7, 45, 5, 5e-3), (43, 6, 25, 3, 1e-8), (5, 200, 1000, 3, 1e-3)])
+def test_ridge_matches_qr_f64(R, seed, F, S, D, lam):  # :93-181,293-328
+    Z, Y, _ = _random_ridge_problem(np.random.default_rng(seed), np.float64, F, S, D)
+    W = R.fit_readout(R.RidgeRegression(lam), Z, Y)
+    assert W.dtype == np.float64
+    assert np.allclose(W, O.train_ridge_qr(Z, Y, lam), rtol=1e-9, atol=1e-12)
+    assert np.allclose(W, O.reference_ridge(Z, Y, lam), rtol=1e-9, atol=1e-12)
+
+
+def test_ridge_f32_and_promotion(R):  # :119-141, train.jl:126-129
+    Z, Y, _ = _random_ridge_problem(np.random.default_rng(11), np.float32, 4, 50, 2)
+    W = R.fit_readout(R.RidgeRegression(np.float32, 1e-3), Z, Y)
+    assert W.dtype == np.float32 and np.allclose(W, O.reference_ridge(Z, Y, 1e-3), rtol=1e-4)
+    assert R.fit_readout(R.RidgeRegression(1e-3), Z, Y).dtype == np.float64
+    Zi = np.array([[1, 2, 3, 4], [2, 1, 0, 1]]); Yi = np.array([[1.0, 2.0, 3.0, 4.0]])
+    assert np.allclose(R.fit_readout(R.RidgeRegression(1e-3), Zi, Yi), O.train_ridge_qr(Zi, Yi, 1e-3), rtol=1e-9)
+
+
+def test_ridge_error_paths(R):  # :220-291
+    with pytest.raises(R.DimensionMismatch, match="states has 10 samples, targets has 9"):
+        R.fit_readout(R.RidgeRegression(1e-3), np.zeros((5, 10)), np.zeros((2, 9)))
+    with pytest.raises(R.ArgumentError, match="at least one training sample"):
+        R.fit_readout(R.RidgeRegression(1e-3), np.zeros((4, 0)), np.zeros((2, 0)))
+    with pytest.raises(R.ArgumentError, match="must be ≥ 0"):
+        R.fit_readout(R.RidgeRegression(-1e-3), np.ones((4, 20)), np.ones((2, 20)))
+    with pytest.raises(R.ArgumentError, match="is not supported"):
+        R.fit_readout(R.RidgeRegression(1e-3), np.ones((4, 20)), np.ones((2, 20)), solver="not_a_solver")
+    with pytest.raises(R.ArgumentError, match="failed to solve"):  # singular Gram, λ = 0 (train.jl:194-196)
+        R.fit_readout(R.RidgeRegression(0.0), np.ones((4, 20)), np.ones((2, 20)))
+
+
+def test_train_and_predict_error_paths(R):
+    esn = R.ESN(2, 30, 2)
+    ps, st = R.setup(np.random.default_rng(0), esn)
+    X = np.zeros((2, 10), np.float32)
+    with pytest.raises(R.ArgumentError, match="at least one column"):
+        R.collectstates(esn, np.zeros((2, 0), np.float32), ps, st)
+    with pytest.raises(R.ArgumentError, match="washout must be ≥ 0"):
+        R.train(esn, X, X, ps, st, washout=-1)
+    with pytest.raises(R.ArgumentError, match="washout=10 is ≥ number of time steps=10"):
+        R.train(esn, X, X, ps, st, washout=10)
+    with pytest.raises(R.DimensionMismatch):
+        R.train(esn, X, X[:, :9], ps, st)
+    with pytest.raises(R.ArgumentError, match="steps must be ≥ 1"):
+        R.predict(esn, 0, ps, st, initialdata=np.zeros(2, np.float32))
+    e32 = R.ESN(2, 30, 3)
+    ps3, st3 = R.setup(np.random.default_rng(0), e32)
+    with pytest.raises(R.DimensionMismatch, match="autoregressive predict requires each output to have length 2"):
+        R.predict(e32, 5, ps3, st3, initialdata=np.zeros(2, np.float32))  # predict.jl:62-72
+
+
+def test_washout_and_autoregressive_identity(R):  # array_workflow_tests.jl:145-155, test_train_ridge.jl:330-342
+    e = R.ESN(2, 2, 2, R.identity, init_input=const_init(np.eye(2)), init_reservoir=const_init(np.zeros((2, 2))),
+              init_state=R.zeros32)
+    ps, st = R.setup(np.random.default_rng(0), e)
+    ps = R.addreadout(e, np.eye(2), ps, st)[0]
+    Y, _ = R.predict(e, 3, ps, st, initialdata=np.array([1.0, 2.0], np.float32))
+    assert np.array_equal(Y, [[1, 1, 1], [2, 2, 2]]) and Y.dtype == np.float64
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((2, 30)).astype(np.float32)
+    A = rng.standard_normal((2, 2)).astype(np.float32)
+    (ps2, _), sw = R.train(e, X, A @ X, ps, st, objective=R.RidgeRegression(1e-10), washout=4, return_states=True)
+    assert sw.shape == (2, 26) and np.array_equal(sw, X[:, 4:])
+    Yt, _ = R.predict(e, X, ps2, st)
+    assert np.allclose(Yt, A @ X, atol=1e-4)  # train then teacher-forced predict recovers linear targets
+
+
+# ---- full BASELINE sizes: size-independent properties ------------------------------------------------
+def test_c3_shape_properties(R):
+    """N=8192, many sequences: (i) spot-check sequences against the oracle, (ii) batch == alone,
+    (iii) with identity activation the recurrence is linear in (h0, u)."""
+    N, B, T = 8192, 300, 12
+    rng = np.random.default_rng(17)
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=True),
+                state_modifiers=R.NLAT2, leak_coefficient=0.5)
+    ps, st = R.setup(rng, esn)
+    lor = O.lorenz_series(T + B)
+    data = np.asfortranarray(np.stack([lor[:, b:b + T] for b in range(B)], axis=2).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    states, st2 = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [h0]))
+    assert states.shape == (N, T, B)
+    layers = oracle_layers(R, esn, ps)
+    for b in (0, 151, B - 1):
+        ref, _ = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
+    rp, ci, v = R.export_csr(esn, ps)
+    assert rp[-1] == 6 * N and np.array_equal(np.bincount(ci, minlength=N), np.full(N, 6))
+    lin = R.ESN(3, N, 3, R.identity, init_reservoir=const_init_sparse(ps.reservoir.reservoir_matrix),
+                init_input=const_init(ps.reservoir.input_matrix), leak_coefficient=0.5)
+    psl, stl = R.setup(np.random.default_rng(0), lin)
+    a, b2 = data[:, :, :2], data[:, :, 2:4]
+    sa, _ = R.collectstates(lin, np.asfortranarray(a), psl, fixed_h0(R, stl, lin, [h0[:, :2]]))
+    sb, _ = R.collectstates(lin, np.asfortranarray(b2), psl, fixed_h0(R, stl, lin, [h0[:, 2:4]]))
+    sab, _ = R.collectstates(lin, np.asfortranarray(a + 2 * b2), psl, fixed_h0(R, stl, lin, [h0[:, :2] + 2 * h0[:, 2:4]]))
+    assert np.max(np.abs(sab - (sa + 2 * sb))) <= 1e-4 * np.max(np.abs(sab))
+
+
+def const_init_sparse(M):
+    return lambda rng, *dims: M

@@ -233,3 +233,24 @@ def test_rand_sparse_like_structure():
     assert Win.dtype == np.float32 and np.all(np.abs(Win) <= 0.1)
     rp, ci, v = O.dense_to_csr(W)
     assert rp[-1] == 1800 and ci.dtype == np.int32
+
+
+# ---- the plain-C port (cpu_baseline) must agree with the pinned NumPy oracle --------------------
+@pytest.mark.parametrize("sparse_form", [True, False])
+def test_c_port_matches_numpy_oracle(sparse_form):
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(5)
+    n, T, B = 120, 30, 3
+    W = O.rand_sparse_like(rng, n, radius=0.9, sparsity=0.05, as_csc=sparse_form)
+    Win = O.scaled_rand_like(rng, n, 3)
+    u = np.asfortranarray(rng.standard_normal((3, T, B)).astype(np.float32))
+    h0 = rng.standard_normal((n, B)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    states, hT = c_oracle.collect(W, Win, u, h0=h0, bias=bias, leak=0.5, act=O.ACT_TANH, mod_kind=O.MOD_NLAT2, pad=1.0)
+    p = O.ESNCellParams(input_matrix=Win, reservoir_matrix=W, bias=bias, leak=np.float32(0.5), act=O.ACT_TANH,
+                        modifiers=((O.MOD_NLAT2, 0), (O.MOD_PAD, 1.0)))
+    for b in range(B):
+        ref, hs = O.collectstates([p], u[:, :, b], [h0[:, b]])
+        assert np.allclose(states[:, :, b], ref, rtol=1e-5, atol=1e-6)
+        assert np.allclose(hT[:, b], hs[0], rtol=1e-5, atol=1e-6)
