@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — ESN hot-path benchmark on B200 (contract: see the task prompt / DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (config.workload): BASELINE.json configs[2] "C3" — batched ESN N=8192, 1024 independent
+3-dim Lorenz-shaped sequences x 10 000 steps per GPU, rand_sparse 6 nnz/col radius 0.9, leak 0.5,
+NLAT2 — the configuration the north-star's HBM-roofline target is quoted on.  One "step" = one
+teacher-forced pass of the recurrence over that batch with the modified states streamed to HBM
+(materialised-state mode; 335 GB per pass, written through a time-chunked ring because the tensor
+does not fit 180 GB).  Metric: ESN neuron-steps/s = N*T*B / seconds.  Multi-GPU: sequences shard
+per GPU with no data-path collective (weak scaling: 1024 sequences per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "reservoircomputing.jl_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: N, d_in, B per GPU, T, nnz/col, radius, leak, modifier, time chunk
+    "c3": dict(N=8192, d_in=3, B=1024, T=10000, k=6, radius=0.9, leak=0.5, mod="NLAT2", chunk=250,
+               desc="C3: batched ESN N=8192, 1024 Lorenz-shaped 3-dim sequences x 10000 steps per GPU, NLAT2"),
+    "c3s": dict(N=8192, d_in=3, B=1024, T=1000, k=6, radius=0.9, leak=0.5, mod="NLAT2", chunk=250,
+                desc="C3 short (T=1000) — development only, not a bench line"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_weights(w, seed=17):
+    import scipy.sparse as sp
+    from rcb200.api import _rand_sparse, _scaled_rand
+
+    rng = np.random.default_rng(seed)
+    W = _rand_sparse(rng, w["N"], w["N"], radius=w["radius"], sparsity=w["k"] / w["N"], return_sparse=True)
+    Win = _scaled_rand(rng, w["N"], w["d_in"])
+    return sp.csc_matrix(W), Win
+
+
+def lorenz_batch(B, T, seed=42, dt=0.02, discard=300):
+    """B Lorenz-63 trajectories from perturbed initial conditions, RK4, vectorised over B.
+    Returns float32 (3, T, B) F-order: element (d, t, b)."""
+    rng = np.random.default_rng(seed)
+    v = np.array([1.0, 0.0, 0.0])[:, None] + 1e-3 * rng.standard_normal((3, B))
+    s, r, bb = 10.0, 28.0, 8.0 / 3.0
+
+    def f(x):
+        return np.stack([s * (x[1] - x[0]), x[0] * (r - x[2]) - x[1], x[0] * x[1] - bb * x[2]])
+
+    out = np.empty((3, T, B), dtype=np.float32, order="F")
+    for i in range(T + discard):
+        if i >= discard:
+            out[:, i - discard, :] = v
+        k1 = f(v); k2 = f(v + 0.5 * dt * k1); k3 = f(v + 0.5 * dt * k2); k4 = f(v + dt * k3)
+        v = v + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl" if os.environ.get("RCB_BENCH_BACKEND", "nccl") == "nccl" else "gloo")
+    return rank, world, local
+
+
+def cpu_sample(w, W, Win, seconds_target=12.0, threads=0):
+    """The oracle's plain-C port (sparse-faithful: CSC SpMV per step, sequences over all host cores) on a
+    bounded sample of the workload; returns (neuron-steps/s, cores, sample description)."""
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads() if threads <= 0 else threads
+    Bs = cores * 2
+    u = lorenz_batch(Bs, 64, seed=7)
+    t0 = time.perf_counter()
+    c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, want_states=True, nthreads=cores)
+    probe = time.perf_counter() - t0
+    Ts = int(max(64, min(w["T"], 64 * seconds_target / max(probe, 1e-4))))
+    u = lorenz_batch(Bs, Ts, seed=7)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, want_states=True, nthreads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    value = w["N"] * Ts * Bs / best
+    return value, cores, f"{Bs} sequences x {Ts} steps of the same N={w['N']} recurrence (CSC SpMV, states materialised), best of 2"
+
+
+def run_reference(args, w):
+    rank, world, local = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    W, Win = make_weights(w)
+    from oracle import c_oracle
+
+    cores = c_oracle.max_threads()
+    Bs = cores * 2
+    u = lorenz_batch(Bs, 64, seed=7)
+    t0 = time.perf_counter()
+    c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, nthreads=cores)
+    probe = time.perf_counter() - t0
+    total_budget = 120.0
+    per_step = total_budget / max(args.steps + args.warmup, 1)
+    Ts = int(max(32, min(w["T"], 64 * per_step / max(probe, 1e-4))))
+    u = lorenz_batch(Bs, Ts, seed=7)
+    for _ in range(args.warmup):
+        c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, nthreads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = w["N"] * Ts * Bs / dt
+    sample = f"{Bs} sequences x {Ts} steps per step (bounded sample of the workload; per-step cost is constant in T and B)"
+    line = {"impl": "reference", "metric": "ESN neuron-steps/s", "value": value, "unit": "neuron-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "note": "reference CPU path = line-faithful C port of esn_cell.jl:175-184 + "
+                       "SparseMatrixCSC mat-vec (Julia is not installed; see DESIGN.md)"},
+            "cpu_baseline": {"value": value, "unit": "neuron-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "neuron-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args, w):
+    import torch
+
+    import rcb200 as R
+    from rcb200 import _lib as L
+    from rcb200.api import _Handle
+
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    stream = torch.cuda.current_stream()
+    dev = R.Device(local, stream.cuda_stream)
+    N, d_in, B, T, Tc = w["N"], w["d_in"], w["B"], w["T"], w["chunk"]
+    W, Win = make_weights(w)
+    esn = R.ESN(d_in, N, d_in, init_reservoir=lambda rng, *d: W, init_input=lambda rng, *d: Win,
+                state_modifiers=getattr(R, w["mod"]), leak_coefficient=w["leak"])
+    ps, st = R.setup(np.random.default_rng(0), esn)
+    h = _Handle(esn, ps, np.float32, dev)
+    lib = R.lib()
+    nchunks = (T + Tc - 1) // Tc
+    # inputs: each rank draws its own sequences (seed by rank); one (d_in, Tc, B) F-order block per time chunk
+    u_host = lorenz_batch(B, T, seed=42 + rank)
+    u_chunks_host = [torch.from_numpy(np.ascontiguousarray(u_host[:, c * Tc:(c + 1) * Tc, :].transpose(2, 1, 0))).pin_memory()
+                     for c in range(nchunks)]  # memory order (b, t, d) == column-major (d, t, b)
+    u_chunks_dev = [x.cuda(non_blocking=True) for x in u_chunks_host]
+    h0 = torch.from_numpy(np.random.default_rng(1 + rank).standard_normal((B, N)).astype(np.float32)).cuda()
+    carry = torch.empty_like(h0)
+    ring = torch.empty((B, Tc, h.F), dtype=torch.float32, device="cuda")  # one chunk of states (b, t, f)
+    hT_host = torch.empty((B, N), dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def one_pass(u_chunks, host_io):
+        k1_ms = 0.0
+        carry.copy_(h0, non_blocking=True)
+        for c in range(nchunks):
+            tc = min(Tc, T - c * Tc)
+            src = u_chunks[c]
+            L.check(lib.rcb_collect(h.handle, L.ptr(src), tc, B, L.ptr(carry), L.ptr(ring), L.ptr(carry)))
+            k1_ms += dev.kernel_ms(L.TIMER_RECURRENCE)
+        if host_io:
+            hT_host.copy_(carry, non_blocking=True)
+            torch.cuda.synchronize()
+        return k1_ms
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(u_chunks, host_io, steps, warmup):
+        for _ in range(warmup):
+            one_pass(u_chunks, host_io)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = dev.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        k1_ms = 0.0
+        for _ in range(steps):
+            k1_ms += one_pass(u_chunks, host_io)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = dev.launch_count() - l0
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms, k1_ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, k1_ms = float(t[0]), float(t[1])
+        return ms / steps, k1_ms / steps, launches, clocks
+
+    ms_step, k1_ms_step, launches, clocks = timed(u_chunks_dev, False, args.steps, args.warmup)
+    units = float(N) * T * B * world
+    value = units / (ms_step * 1e-3)
+    # end to end through the C-ABI with HOST buffers: pinned inputs H2D every chunk, final carry D2H
+    e2e_ms, _, _, _ = timed(u_chunks_host, True, max(1, min(args.steps, 3)), 1)
+    e2e_value = units / (e2e_ms * 1e-3)
+    pk = peaks()
+    F = h.F
+    alg_bytes = 4.0 * F * T * B + 4.0 * d_in * T * B  # state stream out + inputs in, per GPU per pass
+    achieved = alg_bytes / (k1_ms_step * 1e-3) / 1e9
+    line = {"metric": "ESN neuron-steps/s", "value": value, "unit": "neuron-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "N": N, "B_per_gpu": B, "T": T, "nnz_per_col": w["k"], "modifier": w["mod"],
+                       "state_stream": f"materialised, {Tc}-step ring of {ring.numel() * 4 / 1e9:.1f} GB in HBM",
+                       "l2": "working set per chunk (8.6 GB) >> 126 MB L2; no flush needed", "parallelism": f"seq-shard x{world}"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "kernel": "k1_collect_kernel", "kernel_ms_per_step": k1_ms_step,
+                         "algorithmic_bytes_per_launch": alg_bytes / nchunks},
+            "e2e": {"value": e2e_value, "unit": "neuron-steps/s", "h2d_bytes_per_step": int(4 * d_in * T * B),
+                    "d2h_bytes_per_step": int(4 * N * B), "ms_per_step": e2e_ms,
+                    "call": "rcb_collect (collectstates) per time chunk, pinned host inputs, final carry read back"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            v, cores, sample = cpu_sample(w, W, Win)
+            line["cpu_baseline"] = {"value": v, "unit": "neuron-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()
