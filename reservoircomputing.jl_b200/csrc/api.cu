@@ -134,6 +134,8 @@ static int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, con
 static void free_layer(Layer& L) {
   cudaFree(L.sell.perm); cudaFree(L.sell.blk_off); cudaFree(L.sell.blk_w2); cudaFree(L.sell.vals); cudaFree(L.sell.cols);
   cudaFree(L.d_Win); cudaFree(L.d_bias); cudaFree(L.d_leak);
+  cudaFree(L.fast.stream); cudaFree(L.fast.warp_off); cudaFree(L.fast.wwords);
+  L.fast = DevFast{};
   L.sell = DevSell{};
   L.d_Win = L.d_bias = L.d_leak = nullptr;
 }
@@ -170,6 +172,14 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   RCB_TRY(upload(hs.blk_w2, &L.sell.blk_w2));
   RCB_TRY(upload(hs.vals, &L.sell.vals));
   RCB_TRY(upload(hs.cols, &L.sell.cols));
+  HostFast hf;
+  RCB_TRY(fast_from_csr(L.csr, hs, &hf));
+  if (hf.ok) {
+    RCB_TRY(upload(hf.stream, &L.fast.stream));
+    RCB_TRY(upload(hf.warp_off, &L.fast.warp_off));
+    RCB_TRY(upload(hf.wwords, &L.fast.wwords));
+    L.fast.ok = true;
+  }
   const int npos = hs.R * hs.nthreads;
   std::vector<float> winp((size_t)npos * L.d_in, 0.f);
   for (int d = 0; d < L.d_in; ++d)

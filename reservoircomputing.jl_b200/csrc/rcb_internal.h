@@ -68,6 +68,31 @@ struct DevSell {
   int64_t total_pairs = 0;
 };
 
+struct HostCsr;
+struct HostSell;
+// "Warp stream" layout of the fast recurrence kernel (recurrence_fast.cu): same sorted positions
+// as HostSell (position p = k*nthreads + tid), but each warp's R slabs are stored back to back in one
+// byte stream the warp walks once per time step:
+//   slab k of warp w = nq quads then (w2 & 1) tail pair, w2 = slot pairs of that 32-row block
+//     quad: float4 vals[32] (lane-major, 512 B) | uint2 cols[32] (4 x uint16, 256 B)
+//     tail: float2 vals[32] (256 B)             | uint32 cols[32] (2 x uint16, 128 B)
+// Column entries are BYTE offsets col*4 (<= 65532, so N <= 16383).  The R widths of a warp are packed
+// 4 bits each into one 64-bit word (R <= 16, w2 <= 15); nothing else is fetched per slab.
+struct HostFast {
+  bool ok = false;  // false: pattern does not fit the format (kernel falls back to the generic one)
+  int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
+  std::vector<unsigned char> stream;
+  std::vector<uint32_t> warp_off;   // [nwarps] byte offset of the warp's stream
+  std::vector<uint64_t> wwords;     // [nwarps] packed widths
+};
+struct DevFast {
+  bool ok = false;
+  unsigned char* stream = nullptr;
+  uint32_t* warp_off = nullptr;
+  uint64_t* wwords = nullptr;
+};
+int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out);
+
 struct ModChain {  // fused-epilogue description of a state_modifiers tuple
   int32_t n = 0;
   int32_t kind[RCB_MAX_MODIFIERS];
@@ -85,6 +110,7 @@ struct Layer {
   ModChain chain;
   HostCsr csr;
   DevSell sell;
+  DevFast fast;
   float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
   float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
   float* d_bias = nullptr;  // [n] by row

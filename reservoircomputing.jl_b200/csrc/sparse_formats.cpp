@@ -139,6 +139,64 @@ int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out) {
   return RCB_OK;
 }
 
+int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out) {
+  out->ok = false;
+  out->n = sell.n; out->nthreads = sell.nthreads; out->R = sell.R; out->nwarps = sell.nwarps;
+  if (sell.n > 16383 || sell.R > 16) return RCB_OK;  // byte offsets col*4 must fit 16 bits; 16 width nibbles
+  for (int32_t w2 : sell.blk_w2)
+    if (w2 > 15) return RCB_OK;
+  out->warp_off.assign((size_t)sell.nwarps, 0);
+  out->wwords.assign((size_t)sell.nwarps, 0);
+  size_t total = 0;
+  for (int32_t w = 0; w < sell.nwarps; ++w) {
+    out->warp_off[(size_t)w] = (uint32_t)total;
+    for (int32_t k = 0; k < sell.R; ++k) {
+      const int32_t w2 = sell.blk_w2[(size_t)(k * sell.nwarps + w)];
+      out->wwords[(size_t)w] |= (uint64_t)w2 << (4 * k);
+      total += (size_t)(w2 >> 1) * 768 + (size_t)(w2 & 1) * 384;
+    }
+  }
+  if (total > 0xFFFFFFFFull) return RCB_OK;
+  out->stream.assign(total + 16, 0);
+  for (int32_t w = 0; w < sell.nwarps; ++w) {
+    unsigned char* p = out->stream.data() + out->warp_off[(size_t)w];
+    for (int32_t k = 0; k < sell.R; ++k) {
+      const int32_t b = k * sell.nwarps + w;
+      const int32_t w2 = sell.blk_w2[(size_t)b];
+      const int64_t off = sell.blk_off[(size_t)b];
+      // slot pair j of lane l lives at sell.vals/cols[(off + j)*32 + l]; regroup into quads + tail
+      auto val = [&](int32_t j, int32_t l) { return sell.vals[(size_t)(off + j) * 32 + l]; };
+      auto col = [&](int32_t j, int32_t l) { return sell.cols[(size_t)(off + j) * 32 + l]; };
+      for (int32_t q = 0; q < (w2 >> 1); ++q) {
+        float* v = reinterpret_cast<float*>(p);
+        uint16_t* c = reinterpret_cast<uint16_t*>(p + 512);
+        for (int32_t l = 0; l < 32; ++l) {
+          const float2 a = val(2 * q, l), bb = val(2 * q + 1, l);
+          const uint32_t ca = col(2 * q, l), cb = col(2 * q + 1, l);
+          v[4 * l + 0] = a.x; v[4 * l + 1] = a.y; v[4 * l + 2] = bb.x; v[4 * l + 3] = bb.y;
+          c[4 * l + 0] = (uint16_t)((ca & 0xFFFFu) * 4); c[4 * l + 1] = (uint16_t)((ca >> 16) * 4);
+          c[4 * l + 2] = (uint16_t)((cb & 0xFFFFu) * 4); c[4 * l + 3] = (uint16_t)((cb >> 16) * 4);
+        }
+        p += 768;
+      }
+      if (w2 & 1) {
+        float* v = reinterpret_cast<float*>(p);
+        uint16_t* c = reinterpret_cast<uint16_t*>(p + 256);
+        for (int32_t l = 0; l < 32; ++l) {
+          const float2 a = val(w2 - 1, l);
+          const uint32_t ca = col(w2 - 1, l);
+          v[2 * l + 0] = a.x; v[2 * l + 1] = a.y;
+          c[2 * l + 0] = (uint16_t)((ca & 0xFFFFu) * 4); c[2 * l + 1] = (uint16_t)((ca >> 16) * 4);
+        }
+        p += 384;
+      }
+    }
+  }
+  (void)csr;
+  out->ok = true;
+  return RCB_OK;
+}
+
 int64_t chain_feature_dims(int64_t n, const ModChain& c) {
   for (int i = 0; i < c.n; ++i) {
     if (c.kind[i] == RCB_MOD_PAD) n += 1;
