@@ -288,7 +288,7 @@ def run_b200(args, w):
                        "l2": "working set per chunk (8.6 GB) >> 126 MB L2; no flush needed", "parallelism": f"seq-shard x{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                         "kernel": "k1_collect_kernel", "kernel_ms_per_step": k1_ms_step,
+                         "kernel": dev.last_kernel(), "kernel_ms_per_step": k1_ms_step,
                          "algorithmic_bytes_per_launch": alg_bytes / nchunks},
             "e2e": {"value": e2e_value, "unit": "neuron-steps/s", "h2d_bytes_per_step": int(4 * d_in * T * B),
                     "d2h_bytes_per_step": int(4 * N * B), "ms_per_step": e2e_ms,

@@ -110,6 +110,8 @@ RCB_API int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches);
 /* device time [ms] between the first and last kernel of the most recent data-path call, measured
  * with CUDA events on the context's stream (bench: roofline.achieved) */
 RCB_API int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms);
+/* name of the kernel variant the most recent recurrence call launched, e.g. "k1_fast<NB=7,tmem,din=3,simple>" */
+RCB_API int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len);
 #define RCB_TIMER_RECURRENCE 0 /* K1 / K4 */
 #define RCB_TIMER_GRAM 1       /* K2 */
 #define RCB_TIMER_SOLVE 2      /* K3 */
@@ -147,6 +149,13 @@ RCB_API int32_t rcb_csr_from_dense(const float* W, int64_t ldw, int32_t n, int64
                                    int32_t* colind, float* vals);
 RCB_API int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n,
                                  int64_t* nnz, int64_t* rowptr, int32_t* colind, float* vals);
+/* Host-only diagnostics of the kernel-side sliced-ELL layout built from a dense matrix (balanced != 0:
+ * the bank-conflict-free schedule).  stats[0] = nnz, [1] = padded nnz, [2]/[3] = simulated / ideal
+ * shared-memory wavefronts of the LDS.64 gathers of one pass over W, [4]/[5] = same for LDS.32,
+ * [6] = 1 when decoding the layout gives back exactly the input triples (bit-exact pattern + values),
+ * [7] = rows missing or duplicated in the row permutation (0 = bijection). */
+RCB_API int32_t rcb_sell_stats_from_dense(const float* W, int64_t ldw, int32_t n, int32_t nthreads, int32_t balanced,
+                                          int64_t* stats);
 /* Ensemble members (BASELINE config 5): sequence b of a batched call uses W*w_scale[b] and
  * leak[b] instead of the layer's own (layer 0 only).  NULL clears. */
 RCB_API int32_t rcb_esn_set_member_params(rcb_esn* esn, int64_t B, const float* w_scale, const float* leak);

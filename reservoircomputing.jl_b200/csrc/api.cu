@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -132,7 +133,7 @@ static int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, con
 }
 
 static void free_layer(Layer& L) {
-  cudaFree(L.sell.perm); cudaFree(L.sell.blk_off); cudaFree(L.sell.blk_w2); cudaFree(L.sell.vals); cudaFree(L.sell.cols);
+  cudaFree(L.sell.perm); cudaFree(L.sell.blk_off); cudaFree(L.sell.blk_w); cudaFree(L.sell.vals); cudaFree(L.sell.cols);
   cudaFree(L.d_Win); cudaFree(L.d_bias); cudaFree(L.d_leak);
   cudaFree(L.fast.stream); cudaFree(L.fast.warp_off); cudaFree(L.fast.wwords);
   L.fast = DevFast{};
@@ -164,12 +165,14 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   RCB_CUDA(cudaSetDevice(esn->ctx->device));
   free_layer(L);
   HostSell hs;
-  RCB_TRY(sell_from_csr(L.csr, esn_nthreads(esn), &hs));
+  const char* plain = getenv("RCB_SELL");  // testing hook: RCB_SELL=plain disables the conflict-free schedule
+  if (plain && !strcmp(plain, "plain")) RCB_TRY(sell_from_csr(L.csr, esn_nthreads(esn), &hs));
+  else RCB_TRY(sell_from_csr_balanced(L.csr, esn_nthreads(esn), &hs));
   L.sell.n = hs.n; L.sell.nthreads = hs.nthreads; L.sell.R = hs.R; L.sell.nwarps = hs.nwarps;
-  L.sell.total_pairs = (int64_t)hs.vals.size() / 32;
+  L.sell.total_slots = (int64_t)hs.vals.size() / 32;
   RCB_TRY(upload(hs.perm, &L.sell.perm));
   RCB_TRY(upload(hs.blk_off, &L.sell.blk_off));
-  RCB_TRY(upload(hs.blk_w2, &L.sell.blk_w2));
+  RCB_TRY(upload(hs.blk_w, &L.sell.blk_w));
   RCB_TRY(upload(hs.vals, &L.sell.vals));
   RCB_TRY(upload(hs.cols, &L.sell.cols));
   HostFast hf;
@@ -353,6 +356,12 @@ int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches) {
   return RCB_OK;
 }
 
+int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len) {
+  if (!ctx || !buf || len < 1) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  snprintf(buf, (size_t)len, "%s", ctx->last_kernel);
+  return RCB_OK;
+}
+
 int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms) {
   if (!ctx || !ms) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   if (which < 0 || which > 2) return fail(RCB_ERR_ARGUMENT, "unknown timer %d", which);
@@ -498,6 +507,29 @@ int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const flo
   HostCsr c;
   RCB_TRY(csr_from_csc(colptr, rowval, nzval, n, &c));
   return csr_out(c, nnz, rowptr, colind, vals);
+}
+
+int32_t rcb_sell_stats_from_dense(const float* W, int64_t ldw, int32_t n, int32_t nthreads, int32_t balanced, int64_t* stats) {
+  if (!stats) return fail(RCB_ERR_ARGUMENT, "stats is NULL");
+  if (n < 1 || nthreads < 32 || nthreads > 1024 || (nthreads & 31)) return fail(RCB_ERR_ARGUMENT, "bad n / nthreads");
+  HostCsr c, back;
+  RCB_TRY(csr_from_dense(W, ldw, n, &c));
+  HostSell s;
+  RCB_TRY(balanced ? sell_from_csr_balanced(c, nthreads, &s) : sell_from_csr(c, nthreads, &s));
+  RCB_TRY(csr_from_sell(s, &back));
+  stats[0] = c.rowptr.back();
+  stats[1] = s.padded_nnz;
+  sell_conflict_stats(s, &stats[2], &stats[3], &stats[4], &stats[5]);
+  stats[6] = (back.rowptr == c.rowptr && back.colind == c.colind &&
+              back.vals.size() == c.vals.size() && !memcmp(back.vals.data(), c.vals.data(), c.vals.size() * sizeof(float)))
+                 ? 1 : 0;
+  std::vector<char> seen((size_t)n, 0);  // every row exactly once
+  int64_t dup = 0;
+  for (uint16_t r : s.perm)
+    if (r != 0xFFFF) { dup += seen[r]; seen[r] = 1; }
+  for (char x : seen) dup += x ? 0 : 1;
+  stats[7] = dup;
+  return RCB_OK;
 }
 
 int32_t rcb_esn_set_member_params(rcb_esn* esn, int64_t B, const float* w_scale, const float* leak) {

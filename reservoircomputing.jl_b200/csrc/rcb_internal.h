@@ -43,29 +43,33 @@ int32_t csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* 
 
 // Sliced-ELL layout consumed by the recurrence kernels: rows sorted by descending length
 // ("position" p = sorted rank), thread `tid` of a CTA owns positions p = k*nthreads + tid
-// (k = 0..R-1, "slab" k).  One block per (slab, warp) holds width2 slot-PAIRS for its 32 rows,
-// slot-major, so lane l reads pair j at [(off + j)*32 + l]: fully coalesced 256 B (values) and
-// 128 B (two packed uint16 column indices).  Padding entries are (0.0f, column = own row).
+// (k = 0..R-1, "slab" k).  One block per (slab, warp) holds `width` slots for its 32 rows,
+// slot-major, so lane l reads slot j at [(off + j)*32 + l]: fully coalesced.  Padding entries are
+// (0.0f, some valid column).
 struct HostSell {
   int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
   std::vector<uint16_t> perm;     // [R*nthreads] position -> row (0xFFFF = no row)
-  std::vector<int32_t> blk_off;   // [R*nwarps] pair offset of block (k, w)
-  std::vector<int32_t> blk_w2;    // [R*nwarps] pairs in block (k, w)
-  std::vector<float2> vals;       // [total_pairs*32]
-  std::vector<uint32_t> cols;     // [total_pairs*32] lo16 = first column, hi16 = second
+  std::vector<int32_t> blk_off;   // [R*nwarps] slot offset of block (k, w)
+  std::vector<int32_t> blk_w;     // [R*nwarps] slots in block (k, w)
+  std::vector<float> vals;        // [total_slots*32]
+  std::vector<uint16_t> cols;     // [total_slots*32]
   int64_t padded_nnz = 0;
 };
 int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out);
+// same layout, rows grouped and slots ordered so that half-warp gathers are bank-conflict free
+int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* out);
+int32_t csr_from_sell(const HostSell& s, HostCsr* out);
+void sell_conflict_stats(const HostSell& s, int64_t* wf64, int64_t* ideal64, int64_t* wf32, int64_t* ideal32);
 
 // ---- device-side views -----------------------------------------------------------------------
 struct DevSell {
   int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
   uint16_t* perm = nullptr;
   int32_t* blk_off = nullptr;
-  int32_t* blk_w2 = nullptr;
-  float2* vals = nullptr;
-  uint32_t* cols = nullptr;
-  int64_t total_pairs = 0;
+  int32_t* blk_w = nullptr;
+  float* vals = nullptr;
+  uint16_t* cols = nullptr;
+  int64_t total_slots = 0;
 };
 
 struct HostCsr;
@@ -73,11 +77,12 @@ struct HostSell;
 // "Warp stream" layout of the fast recurrence kernel (recurrence_fast.cu): same sorted positions
 // as HostSell (position p = k*nthreads + tid), but each warp's R slabs are stored back to back in one
 // byte stream the warp walks once per time step:
-//   slab k of warp w = nq quads then (w2 & 1) tail pair, w2 = slot pairs of that 32-row block
-//     quad: float4 vals[32] (lane-major, 512 B) | uint2 cols[32] (4 x uint16, 256 B)
-//     tail: float2 vals[32] (256 B)             | uint32 cols[32] (2 x uint16, 128 B)
-// Column entries are BYTE offsets col*4 (<= 65532, so N <= 16383).  The R widths of a warp are packed
-// 4 bits each into one 64-bit word (R <= 16, w2 <= 15); nothing else is fetched per slab.
+//   slab k of warp w (width wd slots) = wd/4 quads, then a pair if wd & 2, then a single if wd & 1
+//     quad:   float4 vals[32] (lane-major, 512 B) | 4 x uint16 cols[32] (256 B)
+//     pair:   float2 vals[32] (256 B)             | 2 x uint16 cols[32] (128 B)
+//     single: float  vals[32] (128 B)             | uint16 cols[32] (64 B)
+// The R widths of a warp are packed 4 bits each into one 64-bit word (R <= 16, width <= 15); nothing else
+// is fetched per slab.
 struct HostFast {
   bool ok = false;  // false: pattern does not fit the format (kernel falls back to the generic one)
   int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;
@@ -127,6 +132,7 @@ struct rcb_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  char last_kernel[96] = "";  // variant name of the most recent recurrence launch
   void* timer_pools = nullptr;  // rcb::TimerPool[3]
   // pinned staging + scratch, grown on demand
   void* pinned = nullptr;

@@ -16,6 +16,7 @@
 // modifier and the streaming store of the F x T x B feature tensor are fused into the step.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 
 #include "rcb_internal.h"
 #include "recurrence_common.cuh"
@@ -34,21 +35,17 @@ __device__ __forceinline__ void row_update(const RecParams& p, const unsigned ch
 #pragma unroll
   for (int b = 0; b < NB; ++b) acc[b] = T(0);
   const int blk = k * p.nwarps + warp;
-  const int off = blk_s[2 * blk], w2 = blk_s[2 * blk + 1];
-  const float2* vp = p.vals + (size_t)off * 32 + lane;
-  const uint32_t* cp = p.cols + (size_t)off * 32 + lane;
+  const int off = blk_s[2 * blk], wd = blk_s[2 * blk + 1];
+  const float* vp = p.vals + (size_t)off * 32 + lane;
+  const uint16_t* cp = p.cols + (size_t)off * 32 + lane;
 #pragma unroll 4
-  for (int j = 0; j < w2; ++j) {
-    const float2 v = __ldg(vp + (size_t)j * 32);
-    const uint32_t c = __ldg(cp + (size_t)j * 32);
-    T x0[NB], x1[NB];
-    pack_load<T, NB>(cur, p.npad, (int)(c & 0xFFFFu), x0);
-    pack_load<T, NB>(cur, p.npad, (int)(c >> 16), x1);
+  for (int j = 0; j < wd; ++j) {
+    const float v = __ldg(vp + (size_t)j * 32);
+    const int c = (int)__ldg(cp + (size_t)j * 32);
+    T x0[NB];
+    pack_load<T, NB>(cur, p.npad, c, x0);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      acc[b] = fma((T)v.x, x0[b], acc[b]);
-      acc[b] = fma((T)v.y, x1[b], acc[b]);
-    }
+    for (int b = 0; b < NB; ++b) acc[b] = fma((T)v, x0[b], acc[b]);
   }
   if (mscale) {
 #pragma unroll
@@ -114,7 +111,7 @@ __global__ void __launch_bounds__(1024, 1) k1_collect_kernel(const RecParams p) 
   }
   for (int i = tid; i < p.R * p.nwarps; i += p.nthreads) {
     blk_s[2 * i] = p.blk_off[i];
-    blk_s[2 * i + 1] = p.blk_w2[i];
+    blk_s[2 * i + 1] = p.blk_w[i];
   }
   const int nu = p.pre_in ? 0 : p.d_in * NB;
   long long useq = 0;
@@ -207,6 +204,7 @@ static int32_t launch_collect_nb(rcb_ctx* ctx, const RecParams& p, size_t smem, 
   auto kern = k1_collect_kernel<T, NB>;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, p.nthreads, smem, ctx->stream>>>(p);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_generic<%s,NB=%d> grid=%d", sizeof(T) == 8 ? "f64" : "f32", NB, grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
@@ -222,7 +220,7 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
   RecParams p{};
   p.n = L.n; p.npad = (L.n + 3) & ~3; p.d_in = L.d_in; p.feat = L.feat;
   p.nthreads = s.nthreads; p.R = s.R; p.nwarps = s.nwarps; p.npos = s.R * s.nthreads;
-  p.perm = s.perm; p.blk_off = s.blk_off; p.blk_w2 = s.blk_w2; p.vals = s.vals; p.cols = s.cols;
+  p.perm = s.perm; p.blk_off = s.blk_off; p.blk_w = s.blk_w; p.vals = s.vals; p.cols = s.cols;
   p.Win = L.d_Win; p.bias = L.desc.use_bias ? L.d_bias : nullptr; p.leakv = L.desc.leak_is_vector ? L.d_leak : nullptr;
   p.leak = L.desc.leak_scalar; p.act = L.desc.activation;
   p.mod = make_fused(L);
@@ -279,7 +277,7 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
 // ================================================================================================
 struct PredLayer {
   int n, npad, d_in, feat, R, npos;
-  const uint16_t* perm; const int32_t* blk_off; const int32_t* blk_w2; const float2* vals; const uint32_t* cols;
+  const uint16_t* perm; const int32_t* blk_off; const int32_t* blk_w; const float* vals; const uint16_t* cols;
   const float* Win; const float* bias; const float* leakv;
   double leak; int act; FusedMod mod;
   int h_off;   // element offset of this layer's state double-buffer in smem
@@ -352,15 +350,10 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
         const int r = valid ? (int)r16 : 0;
         T acc = T(0);
         const int blk = k * p.nwarps + warp;
-        const int off = __ldg(L.blk_off + blk), w2 = __ldg(L.blk_w2 + blk);
-        const float2* vp = L.vals + (size_t)off * 32 + lane;
-        const uint32_t* cp = L.cols + (size_t)off * 32 + lane;
-        for (int j = 0; j < w2; ++j) {
-          const float2 v = __ldg(vp + (size_t)j * 32);
-          const uint32_t c = __ldg(cp + (size_t)j * 32);
-          acc = fma((T)v.x, cur[c & 0xFFFFu], acc);
-          acc = fma((T)v.y, cur[c >> 16], acc);
-        }
+        const int off = __ldg(L.blk_off + blk), wd = __ldg(L.blk_w + blk);
+        const float* vp = L.vals + (size_t)off * 32 + lane;
+        const uint16_t* cp = L.cols + (size_t)off * 32 + lane;
+        for (int j = 0; j < wd; ++j) acc = fma((T)__ldg(vp + (size_t)j * 32), cur[__ldg(cp + (size_t)j * 32)], acc);
         if (l == 0) acc *= mscale;
         if (L.bias) acc += (T)__ldg(L.bias + r);
         T win = T(0);
@@ -425,7 +418,7 @@ int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
       return fail(RCB_ERR_UNSUPPORTED, "predict needs all layers built for the same CTA width (layer %d: %d vs %d)", l, L.sell.nthreads, nthreads);
     PredLayer& q = p.L[l];
     q.n = L.n; q.npad = (L.n + 3) & ~3; q.d_in = L.d_in; q.feat = L.feat; q.R = L.sell.R; q.npos = L.sell.R * L.sell.nthreads;
-    q.perm = L.sell.perm; q.blk_off = L.sell.blk_off; q.blk_w2 = L.sell.blk_w2; q.vals = L.sell.vals; q.cols = L.sell.cols;
+    q.perm = L.sell.perm; q.blk_off = L.sell.blk_off; q.blk_w = L.sell.blk_w; q.vals = L.sell.vals; q.cols = L.sell.cols;
     q.Win = L.d_Win; q.bias = L.desc.use_bias ? L.d_bias : nullptr; q.leakv = L.desc.leak_is_vector ? L.d_leak : nullptr;
     q.leak = L.desc.leak_scalar; q.act = L.desc.activation; q.mod = make_fused(L);
     q.h_off = h_off; q.c_off = c_off;

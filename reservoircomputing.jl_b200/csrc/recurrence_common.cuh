@@ -147,9 +147,9 @@ struct RecParams {
   int nthreads, R, nwarps, npos;
   const uint16_t* perm;
   const int32_t* blk_off;
-  const int32_t* blk_w2;
-  const float2* vals;
-  const uint32_t* cols;
+  const int32_t* blk_w;
+  const float* vals;
+  const uint16_t* cols;
   const float* Win;    // [d_in][npos] (position order), nullptr when pre_in is used
   const float* bias;   // [n] by row, or nullptr
   const float* leakv;  // [n] by row, or nullptr

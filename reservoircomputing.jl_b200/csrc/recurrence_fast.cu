@@ -8,19 +8,23 @@
 //    (224 KB at N = 8192) then fills shared memory, which leaves no room for a second buffer — so the
 //    new state of a step is staged in TENSOR MEMORY: every thread parks its rows' results in its own
 //    TMEM lane with tcgen05.st (32x32b.x8: 8 columns per row-slab, 8 slabs x 8 warps per lane
-//    quadrant = all 512 columns), and after the CTA barrier moves them back with tcgen05.ld.  TMEM is
-//    otherwise idle in this kernel; used this way it is a second 256 KB register file.
-//    When two buffers do fit (smaller N or fewer sequences) the state is double-buffered in shared
-//    memory instead and a step costs a single barrier.
-//  * W is a per-warp byte stream (see HostFast) walked once per step with 128-bit loads; the R slab
-//    widths of a warp sit in one 64-bit register, so nothing but W itself is fetched per slab.
-//    Column entries are pre-scaled byte offsets.
-//  * The multiply-adds run as packed FP32 (fma.rn.f32x2 -> FFMA2) on sequence pairs, which the
-//    [float4 | float2 | float] component layout of the state tile provides for free.
+//    quadrant = all 512 columns), and after the CTA barrier moves them back with tcgen05.ld.  The
+//    8th column of a slab holds the row index, and the block doubles as the thread's copy of its old
+//    state for the leaky update, so neither costs a memory access.  TMEM is otherwise idle in this
+//    kernel; used this way it is a second 256 KB register file.  When two buffers do fit (smaller N or
+//    fewer sequences) the state is double-buffered in shared memory and a step costs one barrier.
+//  * The state tile is stored as sequence PAIRS (float2), gathered with LDS.64: a half-warp of 16 lanes
+//    reads 16 x 8 B = one wavefront when its 16 columns are distinct mod 16, which the host-side
+//    schedule guarantees (sell_from_csr_balanced).  Three pairs are interleaved with a 24-byte stride
+//    (3 is invertible mod 16, so the property carries over and the pair offsets are immediates).
+//  * W is a per-warp byte stream (HostFast) walked once per step with 128-bit loads; the slab widths of
+//    a warp sit in one 64-bit register.
+//  * Multiply-adds run as packed FP32 (fma.rn.f32x2 -> FFMA2 with a broadcast scalar operand).
 //  * tanh is evaluated as 1 - 2/(1 + 2^(2x log2 e)) with ex2.approx + rcp.approx and one Newton step on
 //    the reciprocal: absolute error ~1e-7 (the same as tanhf) at a quarter of its instruction count.
 //    tanh.approx.f32 (2^-11) would break the 1e-5 state tolerance.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -53,64 +57,109 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return copysignf(fmaf(-2.0f, r, 1.0f), x);
 }
 
-__device__ __forceinline__ float act_fast(int act, float x) {
-  if (act == RCB_ACT_TANH || act == RCB_ACT_TANH_FAST) return fast_tanh(x);
-  return apply_act<float>(act, x);
-}
-
 __device__ __forceinline__ float4 ldg128(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint2 ldg64u(const unsigned char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ float2 ldg64f(const unsigned char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ uint32_t ldg32u(const unsigned char* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ float ldg32f(const unsigned char* p) { return __ldg(reinterpret_cast<const float*>(p)); }
+__device__ __forceinline__ uint32_t ldg16u(const unsigned char* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
+
+// ---- state tile layout: NP = NB/2 sequence pairs (+ one single when NB is odd) ------------------------
+//   NP == 1 or 3: pairs interleaved, stride 8*NP bytes per neuron; NP == 2: two separate float2 arrays;
+//   the odd sequence lives in a float array after the pairs.
+template <int NB>
+struct Lay {
+  static constexpr int NP = NB / 2;
+  static constexpr bool HAS1 = (NB & 1) != 0;
+  static constexpr bool AOS = NP == 1 || NP == 3;
+  __device__ static __forceinline__ uint32_t pair_off(uint32_t npad, uint32_t c, int k) {
+    return AOS ? c * (8u * NP) + 8u * k : (uint32_t)k * 8u * npad + c * 8u;
+  }
+  __device__ static __forceinline__ uint32_t single_off(uint32_t npad, uint32_t c) { return (uint32_t)NP * 8u * npad + c * 4u; }
+  __device__ static __forceinline__ void load(const unsigned char* s, uint32_t npad, uint32_t c, float* v) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const float2 x = *reinterpret_cast<const float2*>(s + pair_off(npad, c, k));
+      v[2 * k] = x.x; v[2 * k + 1] = x.y;
+    }
+    if constexpr (HAS1) v[NB - 1] = *reinterpret_cast<const float*>(s + single_off(npad, c));
+  }
+  __device__ static __forceinline__ void store(unsigned char* s, uint32_t npad, uint32_t c, const float* v) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) *reinterpret_cast<float2*>(s + pair_off(npad, c, k)) = make_float2(v[2 * k], v[2 * k + 1]);
+    if constexpr (HAS1) *reinterpret_cast<float*>(s + single_off(npad, c)) = v[NB - 1];
+  }
+};
 
 template <int NB>
 struct Acc {
-  float2 p01, p23, p45;
-  float p6;
+  float2 p[NB / 2 > 0 ? NB / 2 : 1];
+  float s;
 };
 
-// one non-zero: acc[b] += v * state[col][b] for the NB sequences of the tile; `a` = col*4 (byte offset)
+// one non-zero: acc[b] += v * state[col][b] for the NB sequences of the tile
 template <int NB>
-__device__ __forceinline__ void gather1(Acc<NB>& A, const unsigned char* cur, uint32_t off2, uint32_t off1, float v, uint32_t a) {
-  constexpr bool HAS4 = NB >= 4, HAS2 = (NB & 2) != 0, HAS1 = (NB & 1) != 0;
+__device__ __forceinline__ void gather1(Acc<NB>& A, const unsigned char* cur, uint32_t npad, float v, uint32_t c) {
+  using L = Lay<NB>;
   const float2 vv = make_float2(v, v);
-  if constexpr (HAS4) {
-    const float4 x = *reinterpret_cast<const float4*>(cur + (a << 2));
-    A.p01 = ffma2(vv, make_float2(x.x, x.y), A.p01);
-    A.p23 = ffma2(vv, make_float2(x.z, x.w), A.p23);
-  }
-  if constexpr (HAS2) {
-    const float2 x = *reinterpret_cast<const float2*>(cur + off2 + (a << 1));
-    A.p45 = ffma2(vv, x, A.p45);
-  }
-  if constexpr (HAS1) {
-    const float x = *reinterpret_cast<const float*>(cur + off1 + a);
-    A.p6 = fmaf(v, x, A.p6);
-  }
+#pragma unroll
+  for (int k = 0; k < L::NP; ++k) A.p[k] = ffma2(vv, *reinterpret_cast<const float2*>(cur + L::pair_off(npad, c, k)), A.p[k]);
+  if constexpr (L::HAS1) A.s = fmaf(v, *reinterpret_cast<const float*>(cur + L::single_off(npad, c)), A.s);
 }
 
+// feature f of the fused modifier chain for the NB sequences (same semantics as feature_eval)
 template <int NB>
-__device__ __forceinline__ void acc_unpack(const Acc<NB>& A, float* s) {
-  constexpr bool HAS4 = NB >= 4, HAS2 = (NB & 2) != 0, HAS1 = (NB & 1) != 0;
-  int i = 0;
-  if constexpr (HAS4) { s[0] = A.p01.x; s[1] = A.p01.y; s[2] = A.p23.x; s[3] = A.p23.y; i = 4; }
-  if constexpr (HAS2) { s[i] = A.p45.x; s[i + 1] = A.p45.y; i += 2; }
-  if constexpr (HAS1) { s[i] = A.p6; }
+__device__ __forceinline__ void feature_lay(const FusedMod& m, const unsigned char* s, uint32_t npad, int n, int f, float* out) {
+  using L = Lay<NB>;
+  if (m.has_pad && f == m.feat1) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) out[b] = (float)m.pad;
+    return;
+  }
+  // every modifier is z = a * (second ? b : 1) with a = S[ia], b = S[ib]: branch-free per lane
+  int ia = f, ib = f;
+  bool two = false;
+  const bool even = (f & 1) == 0;
+  switch (m.kind) {
+    case RCB_MOD_NLAT1: two = even; break;                                                  // x[i]^2 on 1-based odd i
+    case RCB_MOD_NLAT2: two = even && f >= 2; ia = two ? f - 1 : f; ib = two ? f - 2 : f; break;  // x[i-1]*x[i-2]
+    case RCB_MOD_NLAT3: two = even && f >= 2 && f < n - 1; ia = two ? f - 1 : f; ib = two ? f + 1 : f; break;
+    case RCB_MOD_PARTIAL_SQUARE: two = f < m.thr; break;
+    case RCB_MOD_EXTENDED_SQUARE: two = f >= n; ia = ib = two ? f - n : f; break;
+    default: break;
+  }
+  float a[NB], b[NB];
+  L::load(s, npad, (uint32_t)ia, a);
+  L::load(s, npad, (uint32_t)ib, b);
+#pragma unroll
+  for (int q = 0; q < NB; ++q) out[q] = two ? a[q] * b[q] : a[q];
 }
 
-template <int NB, bool TMEM>
+#define TMEM_ST8(addr, o)                                                                                         \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(o[0]), \
+               "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])                           \
+               : "memory")
+#define TMEM_LD8(addr, o)                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"          \
+               : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) \
+               : "r"(addr)                                                                            \
+               : "memory")
+
+// NB sequences per CTA; TMEM: new state staged in tensor memory (single shared-memory tile);
+// DIN > 0: compile-time input width; SIMPLE: tanh activation, scalar leak, no bias / member parameters.
+template <int NB, bool TMEM, int DIN, bool SIMPLE>
 __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, const FastArgs fa) {
-  constexpr bool HAS4 = NB >= 4, HAS2 = (NB & 2) != 0;
+  using L = Lay<NB>;
+  static_assert(!TMEM || NB <= 7, "the 8th TMEM column of a slab holds the row index");
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int npad = p.npad;
+  const uint32_t npad = (uint32_t)p.npad;
   const size_t buf = (size_t)npad * NB * 4;
+  const int d_in = DIN > 0 ? DIN : p.d_in;
   unsigned char* S[2] = {smem, TMEM ? smem : smem + buf};
   float* u_s = reinterpret_cast<float*>(smem + (TMEM ? 1 : 2) * buf);  // [2][d_in][8]
-  float* m_s = u_s + 2 * p.d_in * 8;                                   // [2][8] member scale | leak
+  float* m_s = u_s + 2 * d_in * 8;                                     // [2][8] member scale | leak
   uint32_t* tm_s = reinterpret_cast<uint32_t*>(m_s + 16);
-  const uint32_t off2 = HAS4 ? (uint32_t)npad * 16u : 0u;
-  const uint32_t off1 = off2 + (HAS2 ? (uint32_t)npad * 8u : 0u);
   const long long seq0 = (long long)blockIdx.x * NB;
   const float* u_g = reinterpret_cast<const float*>(p.u);
   const float* h0_g = reinterpret_cast<const float*>(p.h0);
@@ -123,19 +172,19 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  for (int i = tid; i < npad; i += p.nthreads) {
+  for (int i = tid; i < (int)npad; i += p.nthreads) {
     float v[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const long long seq = seq0 + b;
       v[b] = (h0_g && seq < p.B && i < p.n) ? h0_g[(size_t)seq * p.h_stride + p.h_off + i] : 0.0f;
     }
-    pack_store<float, NB>(S[0], npad, i, v);
-    if constexpr (!TMEM) pack_store<float, NB>(S[1], npad, i, v);
+    L::store(S[0], npad, (uint32_t)i, v);
+    if constexpr (!TMEM) L::store(S[1], npad, (uint32_t)i, v);
   }
-  for (int i = tid; i < 2 * p.d_in * 8 + 16; i += p.nthreads) u_s[i] = 0.0f;
+  for (int i = tid; i < 2 * d_in * 8 + 16; i += p.nthreads) u_s[i] = 0.0f;
   __syncthreads();
-  const int nu = p.d_in * NB;
+  const int nu = d_in * NB;
   long long useq = 0;
   int ud = 0, ub = 0;
   if (tid < nu) {
@@ -155,129 +204,153 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tmem_base = *tm_s;
     ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64u;
+    // park (h0 of my rows | row index) in my TMEM lane: slab k -> columns 8k .. 8k+7
+    for (int k = 0; k < p.R; ++k) {
+      const unsigned r16 = __ldg(p.perm + k * p.nthreads + tid);
+      float hv[NB];
+      L::load(S[0], npad, r16 != 0xFFFFu ? r16 : 0u, hv);
+      uint32_t o[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) o[b] = b < NB ? __float_as_uint(hv[b]) : 0u;
+      o[7] = r16;
+      TMEM_ST8(ta + (uint32_t)k * 8u, o);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   const unsigned char* wbase = fa.stream + fa.warp_off[warp];
-  const unsigned long long wword = fa.wwords[warp];
-  const bool use_mscale = p.member_scale != nullptr, use_mleak = p.member_leak != nullptr;
+  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab
+  const bool use_mscale = !SIMPLE && p.member_scale != nullptr, use_mleak = !SIMPLE && p.member_leak != nullptr;
   float* out_g = reinterpret_cast<float*>(p.states);
   const int F = p.raw ? p.n : p.feat;
   FusedMod mod = p.mod;
   if (p.raw) { mod.kind = 0; mod.has_pad = 0; }
   const float lc_scalar = (float)p.leak;
+  const bool is_tanh = SIMPLE || p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST;
 
   for (long long t = 0; t < p.T; ++t) {
     const unsigned char* cur = S[TMEM ? 0 : (t & 1)];
     unsigned char* nxt = S[TMEM ? 0 : ((t + 1) & 1)];
-    const float* ucur = u_s + (t & 1) * p.d_in * 8;
+    const float* ucur = u_s + (t & 1) * d_in * 8;
     float u_next = 0.0f;
     if (tid < nu && t + 1 < p.T) u_next = __ldg(u_g + ((size_t)useq * p.T + (t + 1)) * p.d_in + ud);
     const unsigned char* wp = wbase;
     for (int k = 0; k < p.R; ++k) {
-      const int w2 = (int)((wword >> (4 * k)) & 15ull);
+      const int wd = (int)(((k < 8 ? wword0 : wword1) >> (8 * (k & 7))) & 255ull);
       const int pos = k * p.nthreads + tid;
-      const unsigned r16 = __ldg(p.perm + pos);
-      const bool valid = r16 != 0xFFFFu;
-      const int r = valid ? (int)r16 : 0;
+      uint32_t o[8];
+      unsigned r16;
+      if constexpr (TMEM) {
+        TMEM_LD8(ta + (uint32_t)k * 8u, o);  // my old state of these rows + the row index (waited on below)
+      } else {
+        r16 = __ldg(p.perm + pos);
+      }
       Acc<NB> A;
-      A.p01 = A.p23 = A.p45 = make_float2(0.f, 0.f);
-      A.p6 = 0.f;
-      for (int q = 0; q < (w2 >> 1); ++q) {
+#pragma unroll
+      for (int q = 0; q < (NB / 2 > 0 ? NB / 2 : 1); ++q) A.p[q] = make_float2(0.f, 0.f);
+      A.s = 0.f;
+      for (int q = 0; q < (wd >> 2); ++q) {
         const float4 v = ldg128(wp + lane * 16);
         const uint2 c = ldg64u(wp + 512 + lane * 8);
         wp += 768;
-        gather1<NB>(A, cur, off2, off1, v.x, c.x & 0xFFFFu);
-        gather1<NB>(A, cur, off2, off1, v.y, c.x >> 16);
-        gather1<NB>(A, cur, off2, off1, v.z, c.y & 0xFFFFu);
-        gather1<NB>(A, cur, off2, off1, v.w, c.y >> 16);
+        gather1<NB>(A, cur, npad, v.x, c.x & 0xFFFFu);
+        gather1<NB>(A, cur, npad, v.y, c.x >> 16);
+        gather1<NB>(A, cur, npad, v.z, c.y & 0xFFFFu);
+        gather1<NB>(A, cur, npad, v.w, c.y >> 16);
       }
-      if (w2 & 1) {
+      if (wd & 2) {
         const float2 v = ldg64f(wp + lane * 8);
         const uint32_t c = ldg32u(wp + 256 + lane * 4);
         wp += 384;
-        gather1<NB>(A, cur, off2, off1, v.x, c & 0xFFFFu);
-        gather1<NB>(A, cur, off2, off1, v.y, c >> 16);
+        gather1<NB>(A, cur, npad, v.x, c & 0xFFFFu);
+        gather1<NB>(A, cur, npad, v.y, c >> 16);
+      }
+      if (wd & 1) {
+        const float v = ldg32f(wp + lane * 4);
+        const uint32_t c = ldg16u(wp + 128 + lane * 2);
+        wp += 192;
+        gather1<NB>(A, cur, npad, v, c);
       }
       float s[NB];
-      acc_unpack<NB>(A, s);
-      if (use_mscale) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) s[b] *= m_s[b];
-      }
-      if (p.bias) {  // bias belongs to the recurrent term: W*h .+ b (esn_cell.jl:179)
-        const float bv = __ldg(p.bias + r);
+      for (int q = 0; q < L::NP; ++q) { s[2 * q] = A.p[q].x; s[2 * q + 1] = A.p[q].y; }
+      if constexpr (L::HAS1) s[NB - 1] = A.s;
+      float hold[NB];
+      if constexpr (TMEM) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        r16 = o[7];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) s[b] += bv;
+        for (int b = 0; b < NB; ++b) hold[b] = __uint_as_float(o[b]);
       }
-      for (int d = 0; d < p.d_in; ++d) {  // W_in*u (generics.jl:91-96), u broadcast from shared memory
-        const float w = __ldg(p.Win + (size_t)d * p.npos + pos);
-        const float4 ua = *reinterpret_cast<const float4*>(ucur + d * 8);
-        const float4 ubv = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
-        const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ubv.x, ubv.y, ubv.z, ubv.w};
+      const bool valid = r16 != 0xFFFFu;
+      const uint32_t r = valid ? r16 : 0u;
+      if constexpr (!TMEM) L::load(cur, npad, r, hold);
+      if constexpr (!SIMPLE) {
+        if (use_mscale) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) s[b] = fmaf(w, uu[b], s[b]);
+          for (int b = 0; b < NB; ++b) s[b] *= m_s[b];
+        }
+        if (p.bias) {  // bias belongs to the recurrent term: W*h .+ b (esn_cell.jl:179)
+          const float bv = __ldg(p.bias + r);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) s[b] += bv;
+        }
       }
-      float hold[NB], hnew[NB];
-      pack_load<float, NB>(cur, npad, r, hold);
-      const float lc = p.leakv ? __ldg(p.leakv + r) : lc_scalar;
+#pragma unroll
+      for (int d = 0; d < (DIN > 0 ? DIN : 8); ++d) {  // W_in*u (generics.jl:91-96), u broadcast from shared memory
+        if (d < d_in) {
+          const float w = __ldg(p.Win + (size_t)d * p.npos + pos);
+          const float4 ua = *reinterpret_cast<const float4*>(ucur + d * 8);
+          const float4 ubv = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
+          const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ubv.x, ubv.y, ubv.z, ubv.w};
+#pragma unroll
+          for (int b = 0; b < NB; ++b) s[b] = fmaf(w, uu[b], s[b]);
+        }
+      }
+      float lc = lc_scalar;
+      if constexpr (!SIMPLE) {
+        if (p.leakv) lc = __ldg(p.leakv + r);
+      }
+      float hnew[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         const float l = use_mleak ? m_s[8 + b] : lc;
-        const float cand = act_fast(p.act, s[b]);
+        const float cand = is_tanh ? fast_tanh(s[b]) : apply_act<float>(p.act, s[b]);
         hnew[b] = fmaf(l, cand, (1.0f - l) * hold[b]);  // (1-a)*h + a*cand, esn_cell.jl:182
       }
       if constexpr (TMEM) {
-        uint32_t o[8];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) o[b] = b < NB ? __float_as_uint(hnew[b]) : 0u;
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(ta + (uint32_t)k * 8u),
-                     "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
-                     : "memory");
+        for (int b = 0; b < NB; ++b) o[b] = __float_as_uint(hnew[b]);
+        o[7] = r16;
+        TMEM_ST8(ta + (uint32_t)k * 8u, o);
       } else {
-        if (valid) pack_store<float, NB>(nxt, npad, r, hnew);
+        if (valid) L::store(nxt, npad, r, hnew);
       }
     }
-    if (tid < nu) u_s[((t + 1) & 1) * p.d_in * 8 + ud * 8 + ub] = u_next;
+    if (tid < nu) u_s[((t + 1) & 1) * d_in * 8 + ud * 8 + ub] = u_next;
     if constexpr (TMEM) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       __syncthreads();  // every gather of this step is done: the tile may be overwritten
       for (int k = 0; k < p.R; ++k) {
         uint32_t o[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
-                     : "r"(ta + (uint32_t)k * 8u)
-                     : "memory");
+        TMEM_LD8(ta + (uint32_t)k * 8u, o);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const unsigned r16 = __ldg(p.perm + k * p.nthreads + tid);
-        if (r16 != 0xFFFFu) {
+        if (o[7] != 0xFFFFu) {
           float hn[NB];
 #pragma unroll
           for (int b = 0; b < NB; ++b) hn[b] = __uint_as_float(o[b]);
-          pack_store<float, NB>(nxt, npad, (int)r16, hn);
+          L::store(nxt, npad, o[7], hn);
         }
       }
     }
     __syncthreads();
     if (out_g) {
-      if ((F & 3) == 0) {
-        for (int f4 = tid * 4; f4 < F; f4 += p.nthreads * 4) {
-          float z[4][NB];
+      // one feature per lane: conflict-free tile reads, 128 B coalesced streaming stores per sequence
+      for (int f = tid; f < F; f += p.nthreads) {
+        float z[NB];
+        feature_lay<NB>(mod, nxt, npad, p.n, f, z);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) feature_eval<float, NB>(mod, nxt, npad, p.n, f4 + i, z[i]);
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            if (seq0 + b < p.B)
-              __stcs(reinterpret_cast<float4*>(out_g + ((size_t)(seq0 + b) * p.T + t) * F + f4),
-                     make_float4(z[0][b], z[1][b], z[2][b], z[3][b]));
-          }
-        }
-      } else {
-        for (int f = tid; f < F; f += p.nthreads) {
-          float z[NB];
-          feature_eval<float, NB>(mod, nxt, npad, p.n, f, z);
-#pragma unroll
-          for (int b = 0; b < NB; ++b)
-            if (seq0 + b < p.B) out_g[((size_t)(seq0 + b) * p.T + t) * F + f] = z[b];
-        }
+        for (int b = 0; b < NB; ++b)
+          if (seq0 + b < p.B) __stcs(out_g + ((size_t)(seq0 + b) * p.T + t) * F + f, z[b]);
       }
     }
   }
@@ -286,7 +359,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     const unsigned char* fin = S[TMEM ? 0 : (p.T & 1)];
     for (int i = tid; i < p.n; i += p.nthreads) {
       float v[NB];
-      pack_load<float, NB>(fin, npad, i, v);
+      L::load(fin, npad, (uint32_t)i, v);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
         if (seq0 + b < p.B) hT_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] = v[b];
@@ -303,14 +376,25 @@ size_t fast_smem_bytes(int npad, int nb, int d_in, bool tmem) {
   return (tmem ? 1 : 2) * (size_t)npad * nb * 4 + (size_t)(2 * d_in * 8 + 16) * 4 + 16;
 }
 
-template <int NB, bool TMEM>
-static int32_t launch_fast_nb(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
-  auto kern = k1_fast_kernel<NB, TMEM>;
+template <int NB, bool TMEM, int DIN, bool SIMPLE>
+static int32_t launch_fast_one(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
+  auto kern = k1_fast_kernel<NB, TMEM, DIN, SIMPLE>;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, p.nthreads, smem, ctx->stream>>>(p, fa);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast<NB=%d,%s,din=%d,%s> grid=%d", NB, TMEM ? "tmem" : "smem2", DIN,
+           SIMPLE ? "simple" : "generic", grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
+}
+
+template <int NB, bool TMEM>
+static int32_t launch_fast_nb(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
+  const bool simple = (p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) && !p.bias && !p.leakv && !p.member_scale &&
+                      !p.member_leak;
+  if (simple && p.d_in == 3) return launch_fast_one<NB, TMEM, 3, true>(ctx, p, fa, smem, grid);
+  if (simple && p.d_in == 1) return launch_fast_one<NB, TMEM, 1, true>(ctx, p, fa, smem, grid);
+  return launch_fast_one<NB, TMEM, 0, false>(ctx, p, fa, smem, grid);
 }
 
 template <bool TMEM>
@@ -326,8 +410,8 @@ static int32_t launch_fast_stage(rcb_ctx* ctx, const RecParams& p, const FastArg
   }
 }
 
-// Picks (NB, staging) and launches; returns RCB_ERR_UNSUPPORTED (without setting an error) when the
-// fast path does not apply so that the caller can fall back to the generic kernel.
+// Picks (NB, staging) and launches; *launched stays false when the fast path does not apply so that
+// the caller can fall back to the generic kernel.
 int32_t launch_collect_fast(rcb_ctx* ctx, const RecParams& p, const DevFast& f, bool* launched) {
   *launched = false;
   if (!f.ok || p.pre_in || p.d_in > 8 || p.d_in < 1) return RCB_OK;

@@ -2,8 +2,8 @@
 // Replaces nothing in the reference (it multiplies by the dense matrix, src/generics.jl:83-96, or
 // by a SparseMatrixCSC, ext/RCSparseArraysExt.jl:5-7); this is the K5 "format" row of SURVEY.md §2a.
 // Index parity: the CSR built here must reproduce the non-zero coordinates and values of the
-// matrix handed over bit-exactly (tests/test_gpu_parity.py::test_csr_pattern_bit_exact, and the
-// CPU-side tests/test_abi.py which call rcb_esn_export_csr without a GPU).
+// matrix handed over bit-exactly, and so must the kernel-side layouts derived from it (decoded back
+// and compared in rcb_sell_stats_from_dense; tests/test_abi.py, tests/test_gpu_parity.py).
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -79,14 +79,20 @@ int32_t csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* 
   return RCB_OK;
 }
 
-int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out) {
-  const int32_t n = csr.n;
-  if (n > 65535) return fail(RCB_ERR_UNSUPPORTED, "reservoir size %d exceeds the 16-bit column index of the sliced-ELL format", n);
-  out->n = n;
+static int32_t sell_geometry(const HostCsr& csr, int32_t nthreads, HostSell* out) {
+  if (csr.n > 65535)
+    return fail(RCB_ERR_UNSUPPORTED, "reservoir size %d exceeds the 16-bit column index of the sliced-ELL format", csr.n);
+  out->n = csr.n;
   out->nthreads = nthreads;
   out->nwarps = nthreads / 32;
-  out->R = (n + nthreads - 1) / nthreads;
-  const int32_t npos = out->R * nthreads;
+  out->R = (csr.n + nthreads - 1) / nthreads;
+  return RCB_OK;
+}
+
+// Plain variant: rows sorted by descending length, block (k, w) = positions m*32 .. m*32+31 (m = k*nwarps + w).
+int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out) {
+  RCB_TRY(sell_geometry(csr, nthreads, out));
+  const int32_t n = csr.n, npos = out->R * nthreads, nblk = out->R * out->nwarps;
   std::vector<int32_t> order((size_t)n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
@@ -94,105 +100,309 @@ int32_t sell_from_csr(const HostCsr& csr, int32_t nthreads, HostSell* out) {
   });
   out->perm.assign((size_t)npos, 0xFFFF);
   for (int32_t p = 0; p < n; ++p) out->perm[(size_t)p] = (uint16_t)order[(size_t)p];
-  const int32_t nblk = out->R * out->nwarps;
   out->blk_off.assign((size_t)nblk, 0);
-  out->blk_w2.assign((size_t)nblk, 0);
-  int64_t total_pairs = 0;
-  for (int32_t k = 0; k < out->R; ++k)
-    for (int32_t w = 0; w < out->nwarps; ++w) {
-      int64_t width = 0;
-      for (int32_t l = 0; l < 32; ++l) {
-        int32_t p = k * nthreads + w * 32 + l;
-        if (p < n) {
-          int32_t r = order[(size_t)p];
-          width = std::max<int64_t>(width, csr.rowptr[r + 1] - csr.rowptr[r]);
-        }
-      }
-      int32_t w2 = (int32_t)((width + 1) / 2);
-      out->blk_off[(size_t)(k * out->nwarps + w)] = (int32_t)total_pairs;
-      out->blk_w2[(size_t)(k * out->nwarps + w)] = w2;
-      total_pairs += w2;
+  out->blk_w.assign((size_t)nblk, 0);
+  int64_t total = 0;
+  for (int32_t m = 0; m < nblk; ++m) {
+    int64_t width = 0;
+    for (int32_t l = 0; l < 32; ++l) {
+      const int32_t p = m * 32 + l;
+      if (p < n) width = std::max<int64_t>(width, csr.rowptr[order[(size_t)p] + 1] - csr.rowptr[order[(size_t)p]]);
     }
-  out->vals.assign((size_t)total_pairs * 32, make_float2(0.f, 0.f));
-  out->cols.assign((size_t)total_pairs * 32, 0u);
-  out->padded_nnz = total_pairs * 64;
-  for (int32_t k = 0; k < out->R; ++k)
-    for (int32_t w = 0; w < out->nwarps; ++w) {
-      const int32_t b = k * out->nwarps + w;
-      const int64_t off = out->blk_off[(size_t)b];
-      const int32_t w2 = out->blk_w2[(size_t)b];
-      for (int32_t l = 0; l < 32; ++l) {
-        int32_t p = k * nthreads + w * 32 + l;
-        int32_t r = p < n ? order[(size_t)p] : 0;
-        int64_t beg = p < n ? csr.rowptr[r] : 0, end = p < n ? csr.rowptr[r + 1] : 0;
-        for (int32_t j = 0; j < w2; ++j) {
-          float2 v = make_float2(0.f, 0.f);
-          uint32_t c0 = (uint32_t)r, c1 = (uint32_t)r;
-          int64_t e0 = beg + 2 * j, e1 = e0 + 1;
-          if (e0 < end) { v.x = csr.vals[(size_t)e0]; c0 = (uint32_t)csr.colind[(size_t)e0]; }
-          if (e1 < end) { v.y = csr.vals[(size_t)e1]; c1 = (uint32_t)csr.colind[(size_t)e1]; }
-          out->vals[(size_t)(off + j) * 32 + l] = v;
-          out->cols[(size_t)(off + j) * 32 + l] = c0 | (c1 << 16);
+    out->blk_off[(size_t)m] = (int32_t)total;
+    out->blk_w[(size_t)m] = (int32_t)width;
+    total += width;
+  }
+  out->vals.assign((size_t)total * 32, 0.f);
+  out->cols.assign((size_t)total * 32, 0);
+  out->padded_nnz = total * 32;
+  for (int32_t m = 0; m < nblk; ++m)
+    for (int32_t l = 0; l < 32; ++l) {
+      const int32_t p = m * 32 + l;
+      const int32_t r = p < n ? order[(size_t)p] : 0;
+      const int64_t beg = p < n ? csr.rowptr[r] : 0, end = p < n ? csr.rowptr[r + 1] : 0;
+      for (int32_t j = 0; j < out->blk_w[(size_t)m]; ++j) {
+        const size_t at = (size_t)(out->blk_off[(size_t)m] + j) * 32 + l;
+        const int64_t e = beg + j;
+        out->vals[at] = e < end ? csr.vals[(size_t)e] : 0.f;
+        out->cols[at] = (uint16_t)(e < end ? csr.colind[(size_t)e] : r);
+      }
+    }
+  return RCB_OK;
+}
+
+// ---- bank-conflict-free gather schedule -------------------------------------------------------------
+// The recurrence gathers state[col] from shared memory with one LDS.64 per sequence pair: 16 lanes x
+// 8 B per wavefront, conflict-free iff the 16 column indices of a half-warp are distinct mod 16 (the
+// state arrays have 8- or 24-byte strides, both bijective on the 16 bank pairs).  With random columns a
+// half-warp needs ~3 wavefronts instead of 1.  The pattern is fixed, so the order is ours to choose:
+//   1. rows are grouped into half-warps of 16 so that the column residues (mod 16) of a group are
+//      spread evenly over the 16 residues, and (softly) the rows' own indices are distinct mod 16 so
+//      that the write-back of the new state is conflict-free too;
+//   2. within a group the non-zeros form a bipartite multigraph rows x residues; a proper edge colouring
+//      with Delta = max(degree) colours (Koenig) assigns every non-zero a slot in which no other lane of
+//      the half-warp uses the same residue.  Empty (lane, slot) cells are padded with (0.0f, a column of
+//      a residue unused in that slot).
+// Summation order inside a row changes (a reordering of FP32 adds, ~1e-7 relative; the reference's own
+// BLAS order is not pinned either); the set of (row, col, value) triples is reproduced exactly.
+namespace {
+
+struct GroupPlan {
+  int rows[16];
+  int delta = 0;
+  std::vector<float> val;    // [delta*16] slot-major
+  std::vector<int32_t> col;  // [delta*16]
+};
+
+struct Edge { int u, v; float w; int32_t c; int color; };
+
+void color_group(const HostCsr& csr, GroupPlan& g) {
+  std::vector<Edge> edges;
+  int degL[16] = {0}, degR[16] = {0};
+  for (int u = 0; u < 16; ++u) {
+    const int r = g.rows[u];
+    if (r < 0) continue;
+    for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) {
+      const int32_t c = csr.colind[(size_t)e];
+      edges.push_back({u, (int)(c & 15), csr.vals[(size_t)e], c, -1});
+      degL[u]++; degR[c & 15]++;
+    }
+  }
+  int delta = 0;
+  for (int i = 0; i < 16; ++i) delta = std::max(delta, std::max(degL[i], degR[i]));
+  g.delta = delta;
+  const int dd = std::max(delta, 1);
+  std::vector<int> cl((size_t)16 * dd, -1), cr((size_t)16 * dd, -1);
+  auto CL = [&](int u, int c) -> int& { return cl[(size_t)u * dd + c]; };
+  auto CR = [&](int v, int c) -> int& { return cr[(size_t)v * dd + c]; };
+  for (int ei = 0; ei < (int)edges.size(); ++ei) {
+    Edge& e = edges[(size_t)ei];
+    int a = 0, b = 0;
+    while (CL(e.u, a) != -1) ++a;
+    while (CR(e.v, b) != -1) ++b;
+    if (a != b) {  // free colour a at v by flipping the a/b alternating path that starts at v
+      std::vector<int> path;
+      int node = e.v, side = 1, c1 = a, c2 = b;  // side 1 = residue side
+      for (;;) {
+        const int pe = side ? CR(node, c1) : CL(node, c1);
+        if (pe == -1) break;
+        path.push_back(pe);
+        node = side ? edges[(size_t)pe].u : edges[(size_t)pe].v;
+        side ^= 1;
+        std::swap(c1, c2);
+      }
+      for (int pe : path) { CL(edges[(size_t)pe].u, edges[(size_t)pe].color) = -1; CR(edges[(size_t)pe].v, edges[(size_t)pe].color) = -1; }
+      for (int pe : path) {
+        Edge& x = edges[(size_t)pe];
+        x.color = x.color == a ? b : a;
+        CL(x.u, x.color) = pe; CR(x.v, x.color) = pe;
+      }
+    }
+    e.color = a;
+    CL(e.u, a) = ei; CR(e.v, a) = ei;
+  }
+  g.val.assign((size_t)delta * 16, 0.f);
+  g.col.assign((size_t)delta * 16, -1);
+  for (const Edge& e : edges) {
+    g.val[(size_t)e.color * 16 + e.u] = e.w;
+    g.col[(size_t)e.color * 16 + e.u] = e.c;
+  }
+  for (int j = 0; j < delta; ++j) {  // pad with columns of residues nobody uses in this slot
+    int next = 0;
+    for (int u = 0; u < 16; ++u) {
+      if (g.col[(size_t)j * 16 + u] >= 0) continue;
+      while (CR(next, j) != -1) ++next;
+      g.col[(size_t)j * 16 + u] = next;
+      ++next;
+    }
+  }
+}
+
+}  // namespace
+
+int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* out) {
+  const int32_t n = csr.n;
+  if (n < 64) return sell_from_csr(csr, nthreads, out);  // nothing to balance
+  RCB_TRY(sell_geometry(csr, nthreads, out));
+  const int32_t npos = out->R * nthreads, ngroups = npos / 16, nblk = out->R * out->nwarps;
+  std::vector<int32_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  auto len = [&](int32_t r) { return (int)(csr.rowptr[r + 1] - csr.rowptr[r]); };
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return len(a) > len(b); });
+  std::vector<char> used((size_t)n, 0);
+  std::vector<GroupPlan> plan((size_t)ngroups);
+  size_t head = 0;  // first unassigned position in `order`
+  const int WINDOW = 2048;
+  for (int32_t gi = 0; gi < ngroups; ++gi) {
+    GroupPlan& g = plan[(size_t)gi];
+    std::fill(g.rows, g.rows + 16, -1);
+    int cnt[16] = {0};
+    bool own[16] = {false};
+    while (head < (size_t)n && used[(size_t)order[head]]) ++head;
+    if (head >= (size_t)n) { g.delta = 0; continue; }
+    int nrows = 0;
+    const int seedlen = len(order[head]);
+    auto take = [&](int32_t r) {
+      used[(size_t)r] = 1;
+      g.rows[nrows++] = r;
+      own[r & 15] = true;
+      for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) cnt[csr.colind[(size_t)e] & 15]++;
+    };
+    take(order[head]);
+    while (nrows < 16) {
+      int64_t best = -1;
+      long bestcost = 0;
+      int seen = 0;
+      for (size_t q = head; q < (size_t)n && seen < WINDOW; ++q) {
+        const int32_t r = order[q];
+        if (used[(size_t)r]) continue;
+        ++seen;
+        if (len(r) < seedlen - 1 && best >= 0) break;  // keep lengths within a group close (sorted order)
+        int mx = 0;
+        long sq = 0;
+        int tmp[16];
+        std::copy(cnt, cnt + 16, tmp);
+        for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) tmp[csr.colind[(size_t)e] & 15]++;
+        for (int i = 0; i < 16; ++i) { mx = std::max(mx, tmp[i]); sq += (long)tmp[i] * tmp[i]; }
+        // slots the group would need first, then a distinct own-row residue, then evenness, then length
+        const long cost = (long)std::max(mx, seedlen) * 1000000L + (own[r & 15] ? 50000L : 0L) + sq * 10L + (seedlen - len(r));
+        if (best < 0 || cost < bestcost) { best = (int64_t)q; bestcost = cost; }
+      }
+      if (best < 0) break;
+      take(order[(size_t)best]);
+    }
+    color_group(csr, g);
+  }
+  out->perm.assign((size_t)npos, 0xFFFF);
+  out->blk_off.assign((size_t)nblk, 0);
+  out->blk_w.assign((size_t)nblk, 0);
+  int64_t total = 0;
+  for (int32_t m = 0; m < nblk; ++m) {
+    const int w = std::max(plan[(size_t)2 * m].delta, plan[(size_t)2 * m + 1].delta);
+    out->blk_off[(size_t)m] = (int32_t)total;
+    out->blk_w[(size_t)m] = w;
+    total += w;
+  }
+  out->vals.assign((size_t)total * 32, 0.f);
+  out->cols.assign((size_t)total * 32, 0);
+  out->padded_nnz = total * 32;
+  for (int32_t m = 0; m < nblk; ++m)
+    for (int half = 0; half < 2; ++half) {
+      const GroupPlan& g = plan[(size_t)2 * m + half];
+      for (int u = 0; u < 16; ++u) {
+        const int lane = half * 16 + u;
+        if (g.rows[u] >= 0) out->perm[(size_t)m * 32 + lane] = (uint16_t)g.rows[u];
+        for (int32_t j = 0; j < out->blk_w[(size_t)m]; ++j) {
+          const size_t at = (size_t)(out->blk_off[(size_t)m] + j) * 32 + lane;
+          if (j < g.delta) {
+            out->vals[at] = g.val[(size_t)j * 16 + u];
+            out->cols[at] = (uint16_t)g.col[(size_t)j * 16 + u];
+          } else {
+            out->cols[at] = (uint16_t)u;  // slots beyond this group's own: lane u takes residue u
+          }
         }
       }
     }
   return RCB_OK;
 }
 
+// Decode a HostSell back into canonical CSR (drops the zero padding) — round-trip check of the format.
+int32_t csr_from_sell(const HostSell& s, HostCsr* out) {
+  const int32_t n = s.n;
+  std::vector<std::vector<std::pair<int32_t, float>>> rows((size_t)n);
+  for (int32_t m = 0; m < s.R * s.nwarps; ++m)
+    for (int32_t l = 0; l < 32; ++l) {
+      const uint16_t r = s.perm[(size_t)m * 32 + l];
+      if (r == 0xFFFF) continue;
+      for (int32_t j = 0; j < s.blk_w[(size_t)m]; ++j) {
+        const size_t at = (size_t)(s.blk_off[(size_t)m] + j) * 32 + l;
+        if (s.vals[at] != 0.f) rows[r].push_back({(int32_t)s.cols[at], s.vals[at]});
+      }
+    }
+  out->n = n;
+  out->rowptr.assign((size_t)n + 1, 0);
+  out->colind.clear();
+  out->vals.clear();
+  for (int32_t r = 0; r < n; ++r) {
+    std::sort(rows[(size_t)r].begin(), rows[(size_t)r].end(),
+              [](const std::pair<int32_t, float>& a, const std::pair<int32_t, float>& b) { return a.first < b.first; });
+    for (auto& e : rows[(size_t)r]) { out->colind.push_back(e.first); out->vals.push_back(e.second); }
+    out->rowptr[(size_t)r + 1] = (int64_t)out->colind.size();
+  }
+  return RCB_OK;
+}
+
+// Simulated shared-memory wavefronts of the gather for one pass over W: LDS.64 (16 lanes, 16 bank pairs,
+// column mod 16) and LDS.32 (32 lanes, 32 banks, column mod 32); identical addresses broadcast.
+void sell_conflict_stats(const HostSell& s, int64_t* wf64, int64_t* ideal64, int64_t* wf32, int64_t* ideal32) {
+  *wf64 = *ideal64 = *wf32 = *ideal32 = 0;
+  for (int32_t m = 0; m < s.R * s.nwarps; ++m)
+    for (int32_t j = 0; j < s.blk_w[(size_t)m]; ++j) {
+      int32_t c[32];
+      for (int32_t l = 0; l < 32; ++l) c[l] = s.cols[(size_t)(s.blk_off[(size_t)m] + j) * 32 + l];
+      auto degree = [&](int lo, int hi, int mod) {
+        int worst = 0;
+        for (int b = 0; b < mod; ++b) {
+          int32_t distinct[32];
+          int nd = 0;
+          for (int l = lo; l < hi; ++l)
+            if (c[l] % mod == b && std::find(distinct, distinct + nd, c[l]) == distinct + nd) distinct[nd++] = c[l];
+          worst = std::max(worst, nd);
+        }
+        return worst;
+      };
+      *wf64 += degree(0, 16, 16) + degree(16, 32, 16);
+      *ideal64 += 2;
+      *wf32 += degree(0, 32, 32);
+      *ideal32 += 1;
+    }
+}
+
+// Per-warp byte stream of the fast kernel, see HostFast.
 int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out) {
+  (void)csr;
   out->ok = false;
   out->n = sell.n; out->nthreads = sell.nthreads; out->R = sell.R; out->nwarps = sell.nwarps;
-  if (sell.n > 16383 || sell.R > 16) return RCB_OK;  // byte offsets col*4 must fit 16 bits; 16 width nibbles
-  for (int32_t w2 : sell.blk_w2)
-    if (w2 > 15) return RCB_OK;
+  if (sell.R > 16) return RCB_OK;  // 16 width bytes (two 64-bit words) per warp
+  for (int32_t w : sell.blk_w)
+    if (w > 255) return RCB_OK;
   out->warp_off.assign((size_t)sell.nwarps, 0);
-  out->wwords.assign((size_t)sell.nwarps, 0);
+  out->wwords.assign((size_t)sell.nwarps * 2, 0);
   size_t total = 0;
   for (int32_t w = 0; w < sell.nwarps; ++w) {
     out->warp_off[(size_t)w] = (uint32_t)total;
     for (int32_t k = 0; k < sell.R; ++k) {
-      const int32_t w2 = sell.blk_w2[(size_t)(k * sell.nwarps + w)];
-      out->wwords[(size_t)w] |= (uint64_t)w2 << (4 * k);
-      total += (size_t)(w2 >> 1) * 768 + (size_t)(w2 & 1) * 384;
+      const int32_t wd = sell.blk_w[(size_t)(k * sell.nwarps + w)];
+      out->wwords[(size_t)w * 2 + (k >> 3)] |= (uint64_t)wd << (8 * (k & 7));
+      total += (size_t)(wd >> 2) * 768 + (size_t)((wd >> 1) & 1) * 384 + (size_t)(wd & 1) * 192;
     }
   }
-  if (total > 0xFFFFFFFFull) return RCB_OK;
+  if (total > 0xFFFFFFF0ull) return RCB_OK;
   out->stream.assign(total + 16, 0);
   for (int32_t w = 0; w < sell.nwarps; ++w) {
     unsigned char* p = out->stream.data() + out->warp_off[(size_t)w];
     for (int32_t k = 0; k < sell.R; ++k) {
       const int32_t b = k * sell.nwarps + w;
-      const int32_t w2 = sell.blk_w2[(size_t)b];
+      const int32_t wd = sell.blk_w[(size_t)b];
       const int64_t off = sell.blk_off[(size_t)b];
-      // slot pair j of lane l lives at sell.vals/cols[(off + j)*32 + l]; regroup into quads + tail
-      auto val = [&](int32_t j, int32_t l) { return sell.vals[(size_t)(off + j) * 32 + l]; };
-      auto col = [&](int32_t j, int32_t l) { return sell.cols[(size_t)(off + j) * 32 + l]; };
-      for (int32_t q = 0; q < (w2 >> 1); ++q) {
+      int32_t j = 0;
+      auto emit = [&](int32_t cnt) {  // cnt slots: float[32][cnt] then uint16[32][cnt], lane-major
         float* v = reinterpret_cast<float*>(p);
-        uint16_t* c = reinterpret_cast<uint16_t*>(p + 512);
-        for (int32_t l = 0; l < 32; ++l) {
-          const float2 a = val(2 * q, l), bb = val(2 * q + 1, l);
-          const uint32_t ca = col(2 * q, l), cb = col(2 * q + 1, l);
-          v[4 * l + 0] = a.x; v[4 * l + 1] = a.y; v[4 * l + 2] = bb.x; v[4 * l + 3] = bb.y;
-          c[4 * l + 0] = (uint16_t)((ca & 0xFFFFu) * 4); c[4 * l + 1] = (uint16_t)((ca >> 16) * 4);
-          c[4 * l + 2] = (uint16_t)((cb & 0xFFFFu) * 4); c[4 * l + 3] = (uint16_t)((cb >> 16) * 4);
-        }
-        p += 768;
-      }
-      if (w2 & 1) {
-        float* v = reinterpret_cast<float*>(p);
-        uint16_t* c = reinterpret_cast<uint16_t*>(p + 256);
-        for (int32_t l = 0; l < 32; ++l) {
-          const float2 a = val(w2 - 1, l);
-          const uint32_t ca = col(w2 - 1, l);
-          v[2 * l + 0] = a.x; v[2 * l + 1] = a.y;
-          c[2 * l + 0] = (uint16_t)((ca & 0xFFFFu) * 4); c[2 * l + 1] = (uint16_t)((ca >> 16) * 4);
-        }
-        p += 384;
-      }
+        uint16_t* c = reinterpret_cast<uint16_t*>(p + (size_t)cnt * 128);
+        for (int32_t l = 0; l < 32; ++l)
+          for (int32_t i = 0; i < cnt; ++i) {
+            const size_t at = (size_t)(off + j + i) * 32 + l;
+            v[cnt * l + i] = sell.vals[at];
+            c[cnt * l + i] = sell.cols[at];
+          }
+        p += (size_t)cnt * 192;
+        j += cnt;
+      };
+      for (int32_t q = 0; q < (wd >> 2); ++q) emit(4);
+      if (wd & 2) emit(2);
+      if (wd & 1) emit(1);
     }
   }
-  (void)csr;
   out->ok = true;
   return RCB_OK;
 }

@@ -62,6 +62,7 @@ SIGNATURES = {
     "rcb_ctx_destroy": (_I32, [_P]),
     "rcb_ctx_synchronize": (_I32, [_P]),
     "rcb_ctx_launch_count": (_I32, [_P, C.POINTER(_I64)]),
+    "rcb_ctx_last_kernel": (_I32, [_P, C.c_char_p, _I32]),
     "rcb_ctx_last_kernel_ms": (_I32, [_P, _I32, C.POINTER(C.c_float)]),
     "rcb_esn_create": (_I32, [_P, C.POINTER(EsnDesc), C.POINTER(LayerDesc), C.POINTER(_P)]),
     "rcb_esn_destroy": (_I32, [_P]),
@@ -74,6 +75,7 @@ SIGNATURES = {
     "rcb_esn_export_csr": (_I32, [_P, _I32, _P, _P, _P]),
     "rcb_csr_from_dense": (_I32, [_P, _I64, _I32, C.POINTER(_I64), _P, _P, _P]),
     "rcb_csr_from_csc": (_I32, [_P, _P, _P, _I32, C.POINTER(_I64), _P, _P, _P]),
+    "rcb_sell_stats_from_dense": (_I32, [_P, _I64, _I32, _I32, _I32, _P]),
     "rcb_esn_set_member_params": (_I32, [_P, _I64, _P, _P]),
     "rcb_esn_set_readout": (_I32, [_P, _P, _P, _I64]),
     "rcb_collect": (_I32, [_P, _P, _I64, _I64, _P, _P, _P]),

@@ -198,6 +198,11 @@ class Device:
         check(lib().rcb_ctx_last_kernel_ms(self.handle, which, C.byref(ms)))
         return ms.value
 
+    def last_kernel(self) -> str:
+        buf = C.create_string_buffer(128)
+        check(lib().rcb_ctx_last_kernel(self.handle, buf, 128))
+        return buf.value.decode()
+
     def close(self):
         if self.handle:
             lib().rcb_ctx_destroy(self.handle)
