@@ -20,8 +20,9 @@
 //  * W is a per-warp byte stream (HostFast) walked once per step with 128-bit loads; the slab widths of
 //    a warp sit in one 64-bit register.
 //  * Multiply-adds run as packed FP32 (fma.rn.f32x2 -> FFMA2 with a broadcast scalar operand).
-//  * tanh is evaluated as 1 - 2/(1 + 2^(2x log2 e)) with ex2.approx + rcp.approx and one Newton step on
-//    the reciprocal: absolute error ~1e-7 (the same as tanhf) at a quarter of its instruction count.
+//  * tanh|x| is evaluated as (1 - e)/(1 + e), e = 2^(-2 log2(e) |x|), with ex2.approx + rcp.approx and one
+//    Newton step on the reciprocal, on sequence pairs in packed FP32: absolute error ~1e-7 (the same as
+//    tanhf) in 6.5 instructions per value.
 //    tanh.approx.f32 (2^-11) would break the 1e-5 state tolerance.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -47,14 +48,51 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float y = fminf(fabsf(x) * 2.8853900817779268f, 64.0f);  // 2*log2(e)*|x|, clamped so 1+e stays finite
-  float e, r;
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ float ex2_approx(float y) {
+  float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
-  const float d = 1.0f + e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  r = fmaf(fmaf(-d, r, 1.0f), r, r);  // Newton: r <- r + r (1 - d r)
-  return copysignf(fmaf(-2.0f, r, 1.0f), x);
+  return e;
+}
+__device__ __forceinline__ float rcp_approx(float y) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return r;
+}
+
+// tanh|x| = (1 - e)/(1 + e), e = 2^(-2 log2(e) |x|) in (0, 1]: nothing can overflow, so no clamp is needed.
+// One Newton step on the reciprocal (q = d r - 2, r' = -r q) brings the absolute error to ~1e-7.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = ex2_approx(fabsf(x) * -2.8853900817779268f);
+  const float d = e + 1.0f, n = e - 1.0f;
+  const float r = rcp_approx(d);
+  const float q = fmaf(d, r, -2.0f);
+  return copysignf(n * (r * q), x);
+}
+// the same on a sequence pair with packed FP32 arithmetic: 13 instructions for two values
+__device__ __forceinline__ float2 fast_tanh2(float2 x) {
+  const float2 e = make_float2(ex2_approx(fabsf(x.x) * -2.8853900817779268f), ex2_approx(fabsf(x.y) * -2.8853900817779268f));
+  const float2 d = fadd2(e, make_float2(1.0f, 1.0f));
+  const float2 n = fadd2(e, make_float2(-1.0f, -1.0f));
+  const float2 r = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  const float2 q = ffma2(d, r, make_float2(-2.0f, -2.0f));
+  const float2 t = fmul2(n, fmul2(r, q));
+  return make_float2(copysignf(t.x, x.x), copysignf(t.y, x.y));
 }
 
 __device__ __forceinline__ float4 ldg128(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -107,32 +145,34 @@ __device__ __forceinline__ void gather1(Acc<NB>& A, const unsigned char* cur, ui
   if constexpr (L::HAS1) A.s = fmaf(v, *reinterpret_cast<const float*>(cur + L::single_off(npad, c)), A.s);
 }
 
-// feature f of the fused modifier chain for the NB sequences (same semantics as feature_eval)
+// feature f of the fused modifier chain for the NB sequences (same semantics as feature_eval).
+// Every modifier has the form z = S[ia] * (two ? S[ib] : 1): one code path for all lanes.
 template <int NB>
 __device__ __forceinline__ void feature_lay(const FusedMod& m, const unsigned char* s, uint32_t npad, int n, int f, float* out) {
   using L = Lay<NB>;
   if (m.has_pad && f == m.feat1) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) out[b] = (float)m.pad;
+    for (int b = 0; b < NB; ++b) out[b] = (float)m.pad;  // T(pad.padding), states.jl:79-82
     return;
   }
-  // every modifier is z = a * (second ? b : 1) with a = S[ia], b = S[ib]: branch-free per lane
   int ia = f, ib = f;
   bool two = false;
   const bool even = (f & 1) == 0;
   switch (m.kind) {
-    case RCB_MOD_NLAT1: two = even; break;                                                  // x[i]^2 on 1-based odd i
-    case RCB_MOD_NLAT2: two = even && f >= 2; ia = two ? f - 1 : f; ib = two ? f - 2 : f; break;  // x[i-1]*x[i-2]
+    case RCB_MOD_NLAT1: two = even; break;                                                          // x[i]^2, 1-based odd i
+    case RCB_MOD_NLAT2: two = even && f >= 2; ia = two ? f - 1 : f; ib = two ? f - 2 : f; break;    // x[i-1]*x[i-2]
     case RCB_MOD_NLAT3: two = even && f >= 2 && f < n - 1; ia = two ? f - 1 : f; ib = two ? f + 1 : f; break;
     case RCB_MOD_PARTIAL_SQUARE: two = f < m.thr; break;
     case RCB_MOD_EXTENDED_SQUARE: two = f >= n; ia = ib = two ? f - n : f; break;
     default: break;
   }
-  float a[NB], b[NB];
-  L::load(s, npad, (uint32_t)ia, a);
+  float b[NB];
+  L::load(s, npad, (uint32_t)ia, out);
   L::load(s, npad, (uint32_t)ib, b);
+  if (two) {
 #pragma unroll
-  for (int q = 0; q < NB; ++q) out[q] = two ? a[q] * b[q] : a[q];
+    for (int q = 0; q < NB; ++q) out[q] *= b[q];
+  }
 }
 
 #define TMEM_ST8(addr, o)                                                                                         \
@@ -150,6 +190,8 @@ __device__ __forceinline__ void feature_lay(const FusedMod& m, const unsigned ch
 template <int NB, bool TMEM, int DIN, bool SIMPLE>
 __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, const FastArgs fa) {
   using L = Lay<NB>;
+  constexpr int NP = L::NP;
+  constexpr int NPA = NP > 0 ? NP : 1;
   static_assert(!TMEM || NB <= 7, "the 8th TMEM column of a slab holds the row index");
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,6 +203,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   float* m_s = u_s + 2 * d_in * 8;                                     // [2][8] member scale | leak
   uint32_t* tm_s = reinterpret_cast<uint32_t*>(m_s + 16);
   const long long seq0 = (long long)blockIdx.x * NB;
+  const int nvalid = p.B - seq0 < NB ? (int)(p.B - seq0) : NB;
   const float* u_g = reinterpret_cast<const float*>(p.u);
   const float* h0_g = reinterpret_cast<const float*>(p.h0);
 
@@ -175,10 +218,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   for (int i = tid; i < (int)npad; i += p.nthreads) {
     float v[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const long long seq = seq0 + b;
-      v[b] = (h0_g && seq < p.B && i < p.n) ? h0_g[(size_t)seq * p.h_stride + p.h_off + i] : 0.0f;
-    }
+    for (int b = 0; b < NB; ++b) v[b] = (h0_g && b < nvalid && i < p.n) ? h0_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] : 0.0f;
     L::store(S[0], npad, (uint32_t)i, v);
     if constexpr (!TMEM) L::store(S[1], npad, (uint32_t)i, v);
   }
@@ -190,13 +230,13 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   if (tid < nu) {
     ud = tid / NB;
     ub = tid % NB;
-    useq = seq0 + ub < p.B ? seq0 + ub : p.B - 1;
+    useq = ub < nvalid ? seq0 + ub : p.B - 1;
     u_s[ud * 8 + ub] = u_g[((size_t)useq * p.T + 0) * p.d_in + ud];
   }
   if (tid < NB) {
-    const long long seq = seq0 + tid < p.B ? seq0 + tid : p.B - 1;
+    const long long seq = tid < nvalid ? seq0 + tid : p.B - 1;
     m_s[tid] = p.member_scale ? p.member_scale[seq] : 1.0f;
-    m_s[8 + tid] = p.member_leak ? p.member_leak[seq] : 0.0f;
+    m_s[8 + tid] = p.member_leak ? p.member_leak[seq] : (float)p.leak;
   }
   if constexpr (TMEM) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -222,6 +262,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   const bool use_mscale = !SIMPLE && p.member_scale != nullptr, use_mleak = !SIMPLE && p.member_leak != nullptr;
   float* out_g = reinterpret_cast<float*>(p.states);
   const int F = p.raw ? p.n : p.feat;
+  const size_t seq_stride = (size_t)p.T * F;
   FusedMod mod = p.mod;
   if (p.raw) { mod.kind = 0; mod.has_pad = 0; }
   const float lc_scalar = (float)p.leak;
@@ -246,7 +287,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
       }
       Acc<NB> A;
 #pragma unroll
-      for (int q = 0; q < (NB / 2 > 0 ? NB / 2 : 1); ++q) A.p[q] = make_float2(0.f, 0.f);
+      for (int q = 0; q < NPA; ++q) A.p[q] = make_float2(0.f, 0.f);
       A.s = 0.f;
       for (int q = 0; q < (wd >> 2); ++q) {
         const float4 v = ldg128(wp + lane * 16);
@@ -270,87 +311,131 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
         wp += 192;
         gather1<NB>(A, cur, npad, v, c);
       }
-      float s[NB];
-#pragma unroll
-      for (int q = 0; q < L::NP; ++q) { s[2 * q] = A.p[q].x; s[2 * q + 1] = A.p[q].y; }
-      if constexpr (L::HAS1) s[NB - 1] = A.s;
-      float hold[NB];
+      float2 hp[NPA];
+      float hs = 0.f;
       if constexpr (TMEM) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         r16 = o[7];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) hold[b] = __uint_as_float(o[b]);
+        for (int q = 0; q < NP; ++q) hp[q] = make_float2(__uint_as_float(o[2 * q]), __uint_as_float(o[2 * q + 1]));
+        if constexpr (L::HAS1) hs = __uint_as_float(o[NB - 1]);
       }
       const bool valid = r16 != 0xFFFFu;
       const uint32_t r = valid ? r16 : 0u;
-      if constexpr (!TMEM) L::load(cur, npad, r, hold);
+      if constexpr (!TMEM) {
+        float hv[NB];
+        L::load(cur, npad, r, hv);
+#pragma unroll
+        for (int q = 0; q < NP; ++q) hp[q] = make_float2(hv[2 * q], hv[2 * q + 1]);
+        if constexpr (L::HAS1) hs = hv[NB - 1];
+      }
       if constexpr (!SIMPLE) {
         if (use_mscale) {
 #pragma unroll
-          for (int b = 0; b < NB; ++b) s[b] *= m_s[b];
+          for (int q = 0; q < NP; ++q) A.p[q] = fmul2(A.p[q], *reinterpret_cast<const float2*>(m_s + 2 * q));
+          if constexpr (L::HAS1) A.s *= m_s[NB - 1];
         }
         if (p.bias) {  // bias belongs to the recurrent term: W*h .+ b (esn_cell.jl:179)
           const float bv = __ldg(p.bias + r);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) s[b] += bv;
+          for (int q = 0; q < NP; ++q) A.p[q] = fadd2(A.p[q], make_float2(bv, bv));
+          if constexpr (L::HAS1) A.s += bv;
         }
       }
 #pragma unroll
       for (int d = 0; d < (DIN > 0 ? DIN : 8); ++d) {  // W_in*u (generics.jl:91-96), u broadcast from shared memory
         if (d < d_in) {
           const float w = __ldg(p.Win + (size_t)d * p.npos + pos);
-          const float4 ua = *reinterpret_cast<const float4*>(ucur + d * 8);
-          const float4 ubv = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
-          const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ubv.x, ubv.y, ubv.z, ubv.w};
+          const float2 ww = make_float2(w, w);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) s[b] = fmaf(w, uu[b], s[b]);
+          for (int q = 0; q < NP; ++q) A.p[q] = ffma2(ww, *reinterpret_cast<const float2*>(ucur + d * 8 + 2 * q), A.p[q]);
+          if constexpr (L::HAS1) A.s = fmaf(w, ucur[d * 8 + NB - 1], A.s);
         }
       }
-      float lc = lc_scalar;
-      if constexpr (!SIMPLE) {
-        if (p.leakv) lc = __ldg(p.leakv + r);
-      }
-      float hnew[NB];
+      if (is_tanh) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const float l = use_mleak ? m_s[8 + b] : lc;
-        const float cand = is_tanh ? fast_tanh(s[b]) : apply_act<float>(p.act, s[b]);
-        hnew[b] = fmaf(l, cand, (1.0f - l) * hold[b]);  // (1-a)*h + a*cand, esn_cell.jl:182
+        for (int q = 0; q < NP; ++q) A.p[q] = fast_tanh2(A.p[q]);
+        if constexpr (L::HAS1) A.s = fast_tanh(A.s);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) A.p[q] = make_float2(apply_act<float>(p.act, A.p[q].x), apply_act<float>(p.act, A.p[q].y));
+        if constexpr (L::HAS1) A.s = apply_act<float>(p.act, A.s);
+      }
+      // h' = (1-a)*h + a*cand, esn_cell.jl:182
+      if (use_mleak) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          const float2 l = *reinterpret_cast<const float2*>(m_s + 8 + 2 * q);
+          hp[q] = ffma2(l, A.p[q], fmul2(make_float2(1.0f - l.x, 1.0f - l.y), hp[q]));
+        }
+        if constexpr (L::HAS1) hs = fmaf(m_s[8 + NB - 1], A.s, (1.0f - m_s[8 + NB - 1]) * hs);
+      } else {
+        float lc = lc_scalar;
+        if constexpr (!SIMPLE) {
+          if (p.leakv) lc = __ldg(p.leakv + r);
+        }
+        const float oml = 1.0f - lc;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) hp[q] = ffma2(make_float2(lc, lc), A.p[q], fmul2(make_float2(oml, oml), hp[q]));
+        if constexpr (L::HAS1) hs = fmaf(lc, A.s, oml * hs);
       }
       if constexpr (TMEM) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) o[b] = __float_as_uint(hnew[b]);
+        for (int q = 0; q < NP; ++q) { o[2 * q] = __float_as_uint(hp[q].x); o[2 * q + 1] = __float_as_uint(hp[q].y); }
+        if constexpr (L::HAS1) o[NB - 1] = __float_as_uint(hs);
         o[7] = r16;
         TMEM_ST8(ta + (uint32_t)k * 8u, o);
       } else {
-        if (valid) L::store(nxt, npad, r, hnew);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q) *reinterpret_cast<float2*>(nxt + L::pair_off(npad, r, q)) = hp[q];
+          if constexpr (L::HAS1) *reinterpret_cast<float*>(nxt + L::single_off(npad, r)) = hs;
+        }
       }
     }
     if (tid < nu) u_s[((t + 1) & 1) * d_in * 8 + ud * 8 + ub] = u_next;
     if constexpr (TMEM) {
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       __syncthreads();  // every gather of this step is done: the tile may be overwritten
-      for (int k = 0; k < p.R; ++k) {
-        uint32_t o[8];
-        TMEM_LD8(ta + (uint32_t)k * 8u, o);
+      for (int k = 0; k < p.R; k += 2) {  // two slabs per wait
+        uint32_t o0[8], o1[8];
+        const bool second = k + 1 < p.R;
+        TMEM_LD8(ta + (uint32_t)k * 8u, o0);
+        if (second) TMEM_LD8(ta + (uint32_t)(k + 1) * 8u, o1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (o[7] != 0xFFFFu) {
-          float hn[NB];
+        if (o0[7] != 0xFFFFu) {
 #pragma unroll
-          for (int b = 0; b < NB; ++b) hn[b] = __uint_as_float(o[b]);
-          L::store(nxt, npad, o[7], hn);
+          for (int q = 0; q < NP; ++q)
+            *reinterpret_cast<float2*>(nxt + L::pair_off(npad, o0[7], q)) = make_float2(__uint_as_float(o0[2 * q]), __uint_as_float(o0[2 * q + 1]));
+          if constexpr (L::HAS1) *reinterpret_cast<float*>(nxt + L::single_off(npad, o0[7])) = __uint_as_float(o0[NB - 1]);
+        }
+        if (second && o1[7] != 0xFFFFu) {
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+            *reinterpret_cast<float2*>(nxt + L::pair_off(npad, o1[7], q)) = make_float2(__uint_as_float(o1[2 * q]), __uint_as_float(o1[2 * q + 1]));
+          if constexpr (L::HAS1) *reinterpret_cast<float*>(nxt + L::single_off(npad, o1[7])) = __uint_as_float(o1[NB - 1]);
         }
       }
     }
     __syncthreads();
     if (out_g) {
       // one feature per lane: conflict-free tile reads, 128 B coalesced streaming stores per sequence
-      for (int f = tid; f < F; f += p.nthreads) {
-        float z[NB];
-        feature_lay<NB>(mod, nxt, npad, p.n, f, z);
+      float* po = out_g + ((size_t)seq0 * p.T + t) * F;
+      if (nvalid == NB) {
+        for (int f = tid; f < F; f += p.nthreads) {
+          float z[NB];
+          feature_lay<NB>(mod, nxt, npad, p.n, f, z);
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
-          if (seq0 + b < p.B) __stcs(out_g + ((size_t)(seq0 + b) * p.T + t) * F + f, z[b]);
+          for (int b = 0; b < NB; ++b) __stcs(po + (size_t)b * seq_stride + f, z[b]);
+        }
+      } else {
+        for (int f = tid; f < F; f += p.nthreads) {
+          float z[NB];
+          feature_lay<NB>(mod, nxt, npad, p.n, f, z);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (b < nvalid) __stcs(po + (size_t)b * seq_stride + f, z[b]);
+        }
       }
     }
   }
@@ -362,7 +447,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
       L::load(fin, npad, (uint32_t)i, v);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
-        if (seq0 + b < p.B) hT_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] = v[b];
+        if (b < nvalid) hT_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] = v[b];
     }
   }
   if constexpr (TMEM) {
