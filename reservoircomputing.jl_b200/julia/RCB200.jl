@@ -1,0 +1,231 @@
+# RCB200.jl — reference-side binding of librcb200.so (include/rcb200.h) for SciML/ReservoirComputing.jl
+# v0.12.35.  Source only: Julia is not installed in the build container, so this file is shipped as
+# the binding a maintainer would add (INTEGRATION.md walks through it); the in-tree tests exercise
+# the very same C entry points through ctypes (reservoircomputing.jl_b200/rcb200/_lib.py).
+#
+# The reference has no FFI for this path — its extension points are multiple-dispatch hooks
+# (SURVEY.md §8b).  A reservoir wrapped in `B200Reservoir` selects the methods below:
+#   __collectstates(reservoir, rc, data, ps, st)            src/reservoircomputer.jl:96-133
+#   __predict(reservoir, rc, steps::Integer, ps, st; ...)   src/predict.jl:118-124,74-88
+#   __predict(reservoir, rc, data::AbstractMatrix, ps, st)  src/predict.jl:126-129,163-177
+#   __fit_readout(::B200Ridge, states, targets; ...)        src/train.jl:100-198
+# `ESN`, `DeepESN`, `ReservoirComputer`, `LuxCore.setup`, `train`, `predict`, `collectstates`,
+# `addreadout!` and `resetcarry!` are untouched: `ps`/`st` keep their layout (Appendix A of SURVEY.md),
+# the final carry is copied back into `st.reservoir.carry`, and errors are re-raised as the
+# exception types the reference throws (ArgumentError / DimensionMismatch).
+module RCB200
+
+using ReservoirComputing
+using ReservoirComputing: AbstractReservoirComputer, ReservoirComputer, StatefulLayer, ESNCell,
+                          RidgeRegression, NLAT1, NLAT2, NLAT3, Pad, PartialSquare, ExtendedSquare
+import ReservoirComputing: __collectstates, __predict, __fit_readout
+using SparseArrays: SparseMatrixCSC
+
+const LIB = get(ENV, "RCB200_LIB", joinpath(@__DIR__, "..", "librcb200.so"))
+
+# ---- status -> exception (include/rcb200.h: rcb_status) ------------------------------------------
+const RCB_OK = Int32(0)
+lasterror() = unsafe_string(ccall((:rcb_last_error, LIB), Cstring, ()))
+function check(status::Int32)
+    status == RCB_OK && return nothing
+    msg = lasterror()
+    status == -1 && throw(ArgumentError(msg))
+    status == -2 && throw(DimensionMismatch(msg))
+    status == -4 && throw(ArgumentError(msg))   # solver failure: train.jl:194-196 raises ArgumentError
+    error("librcb200: status $status: $msg")     # CUDA / allocation / unsupported: there is no CPU fallback
+end
+
+# ---- C structs (field order and sizes as in include/rcb200.h) ------------------------------------
+const MAXMOD = 8
+struct LayerDesc
+    res_dims::Int32
+    activation::Int32
+    use_bias::Int32
+    leak_is_vector::Int32
+    leak_scalar::Float64
+    n_modifiers::Int32
+    modifier_kind::NTuple{MAXMOD, Int32}
+    modifier_param::NTuple{MAXMOD, Float64}
+end
+struct ESNDesc
+    n_layers::Int32
+    in_dims::Int32
+    out_dims::Int32
+    readout_activation::Int32
+    readout_use_bias::Int32
+    data_dtype::Int32
+end
+
+activation_id(::typeof(identity)) = Int32(0)
+activation_id(::typeof(tanh)) = Int32(1)
+activation_id(f) = nameof(f) === :tanh_fast ? Int32(2) :
+                   nameof(f) === :sigmoid ? Int32(3) : nameof(f) === :relu ? Int32(4) :
+                   throw(ArgumentError("activation $(f) is outside the B200 hot path"))
+dtype_id(::Type{Float32}) = Int32(0)
+dtype_id(::Type{Float64}) = Int32(1)
+
+modifier_entry(::typeof(NLAT1)) = (Int32(1), 0.0)
+modifier_entry(::typeof(NLAT2)) = (Int32(2), 0.0)
+modifier_entry(::typeof(NLAT3)) = (Int32(3), 0.0)
+modifier_entry(p::Pad) = (Int32(4), Float64(p.padding))
+modifier_entry(p::PartialSquare) = (Int32(5), Float64(p.eta))
+modifier_entry(::typeof(ExtendedSquare)) = (Int32(6), 0.0)
+modifier_entry(w) = hasproperty(w, :func) ? modifier_entry(w.func) :   # WrappedFunction, lux_layers.jl:2-6
+                    throw(ArgumentError("state modifier $(w) is outside the B200 hot path"))
+
+# ---- context + handle ------------------------------------------------------------------------------
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:rcb_ctx_create, LIB), Int32, (Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, C_NULL, out))
+        c = new(out[])
+        finalizer(x -> ccall((:rcb_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), c)
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
+ctx() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context(0)))
+
+"""
+    B200Reservoir(cell)
+
+Marker wrapper selecting the CUDA path: `ESN(...; )` is built as usual and its `reservoir`
+(`StatefulLayer(ESNCell)`) is wrapped — `ReservoirComputer(B200Reservoir(rc.reservoir), rc.states_modifiers, rc.readout)`.
+Parameter and state trees are those of the wrapped layer (LuxCore.initialparameters/initialstates forward).
+"""
+struct B200Reservoir{L} <: ReservoirComputing.AbstractReservoirCollectionLayer
+    layer::L
+end
+ReservoirComputing.LuxCore.initialparameters(rng, r::B200Reservoir) = ReservoirComputing.LuxCore.initialparameters(rng, r.layer)
+ReservoirComputing.LuxCore.initialstates(rng, r::B200Reservoir) = ReservoirComputing.LuxCore.initialstates(rng, r.layer)
+(r::B200Reservoir)(x, ps, st) = r.layer(x, ps, st)   # single steps stay on the reference path
+
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    F::Int
+    N::Int
+end
+
+function Handle(rc::ReservoirComputer, ps, ::Type{T}) where {T}
+    cell = rc.reservoir.layer.cell::ESNCell
+    mods = collect(modifier_entry(m) for m in rc.states_modifiers)
+    length(mods) <= MAXMOD || throw(ArgumentError("at most $MAXMOD state modifiers"))
+    kinds = ntuple(i -> i <= length(mods) ? mods[i][1] : Int32(0), MAXMOD)
+    params = ntuple(i -> i <= length(mods) ? mods[i][2] : 0.0, MAXMOD)
+    α = cell.leak_coefficient
+    ld = LayerDesc(cell.out_dims, activation_id(cell.activation), ReservoirComputing.known(cell.use_bias) ? 1 : 0,
+                   α isa AbstractVector ? 1 : 0, α isa AbstractVector ? 0.0 : Float64(α), length(mods), kinds, params)
+    d = ESNDesc(1, cell.in_dims, rc.readout.out_dims, activation_id(rc.readout.activation),
+                ReservoirComputing.known(rc.readout.use_bias) ? 1 : 0, dtype_id(T))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rcb_esn_create, LIB), Int32, (Ptr{Cvoid}, Ref{ESNDesc}, Ref{LayerDesc}, Ref{Ptr{Cvoid}}),
+                ctx().ptr, Ref(d), Ref(ld), out))
+    h = Handle(out[], 0, cell.out_dims)
+    finalizer(x -> ccall((:rcb_esn_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+    W, Win = ps.reservoir.reservoir_matrix, Matrix{Float32}(ps.reservoir.input_matrix)
+    bias = haskey(ps.reservoir, :bias) ? Vector{Float32}(ps.reservoir.bias) : C_NULL
+    if W isa SparseMatrixCSC                      # return_sparse=true, ext/RCSparseArraysExt.jl:5-7
+        check(ccall((:rcb_esn_set_weights_csc, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Int64, Ptr{Float32}),
+                    h.ptr, 0, W.colptr, W.rowval, Vector{Float32}(W.nzval), Win, size(Win, 1), bias))
+    else                                          # dense Matrix with explicit zeros (rand_sparse default)
+        Wd = Matrix{Float32}(W)
+        check(ccall((:rcb_esn_set_weights_dense, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64, Ptr{Float32}, Int64, Ptr{Float32}),
+                    h.ptr, 0, Wd, size(Wd, 1), Win, size(Win, 1), bias))
+    end
+    α isa AbstractVector && check(ccall((:rcb_esn_set_leak_vector, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}),
+                                        h.ptr, 0, Vector{Float32}(α)))
+    F = Ref{Int32}(0)
+    check(ccall((:rcb_esn_feature_dims, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), h.ptr, F))
+    h.F = F[]
+    return h
+end
+
+# h0: the carry in `st`, or a fresh draw from the replicated rng exactly like the first reference step
+# (esn_cell.jl:169-173, lux_layers.jl:212-216)
+function initial_carry(rc, st, ::Type{T}) where {T}
+    cell = rc.reservoir.layer.cell
+    if st.reservoir.carry === nothing
+        rng = ReservoirComputing.LuxCore.replicate(st.reservoir.cell.rng)
+        return Vector{T}(vec(cell.init_state(rng, cell.out_dims, 1)))
+    end
+    return Vector{T}(vec(first(st.reservoir.carry)))
+end
+store_carry(st, h) = merge(st, (reservoir = merge(st.reservoir, (carry = (reshape(h, :, 1),),)),))
+
+# ---- collectstates: src/reservoircomputer.jl:113-133 --------------------------------------------------
+function __collectstates(res::B200Reservoir, rc::ReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
+    size(data, 2) >= 1 || throw(ArgumentError("collectstates data must have at least one column, got 0."))
+    h = Handle(rc, ps, T)
+    Tn = size(data, 2)
+    states = Matrix{T}(undef, h.F, Tn)                      # similar(data, F, T), :123
+    h0 = initial_carry(rc, st, T)
+    hT = similar(h0)
+    check(ccall((:rcb_collect, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                h.ptr, Matrix{T}(data), Tn, 1, h0, states, hT))
+    return states, store_carry(st, hT)
+end
+
+# ---- ridge: src/train.jl:100-198 ---------------------------------------------------------------------
+"""`B200Ridge(λ)` — a `RidgeRegression` whose `__fit_readout` runs K2 (tcgen05 Gram) + K3 (FP64 Cholesky)."""
+struct B200Ridge{R <: Number}
+    reg::R
+end
+function __fit_readout(obj::B200Ridge, states::AbstractMatrix, targets::AbstractMatrix; kwargs...)
+    size(states, 2) == size(targets, 2) ||
+        throw(DimensionMismatch("states has $(size(states, 2)) samples, targets has $(size(targets, 2))"))
+    F, S = size(states); D = size(targets, 1)
+    Z = states isa Matrix{Float32} || states isa Matrix{Float64} ? states : Matrix{Float64}(states)
+    Y = targets isa Matrix{Float32} || targets isa Matrix{Float64} ? targets : Matrix{Float64}(targets)
+    W = Matrix{Float64}(undef, D, F)
+    check(ccall((:rcb_fit_readout, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Float64, Int32, Ptr{Float64}),
+                ctx().ptr, Z, dtype_id(eltype(Z)), F, S, stride(Z, 2), Y, dtype_id(eltype(Y)), D, size(Y, 2), stride(Y, 2),
+                Float64(obj.reg), 0, W))
+    Tp = promote_type(eltype(states), eltype(targets), typeof(obj.reg))    # train.jl:126-129
+    return Matrix{Tp}(W)
+end
+
+# ---- predict: src/predict.jl:74-88 (autoregressive) and :163-177 (teacher-forced) -----------------------
+function set_readout!(h::Handle, ps)
+    W = Matrix{Float64}(ps.readout.weight)
+    b = haskey(ps.readout, :bias) ? Vector{Float64}(ps.readout.bias) : C_NULL
+    check(ccall((:rcb_esn_set_readout, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), h.ptr, W, b, 1))
+end
+
+function __predict(res::B200Reservoir, rc::ReservoirComputer, steps::Integer, ps, st; initialdata)
+    steps >= 1 || throw(ArgumentError("steps must be ≥ 1, got $steps"))
+    T = eltype(initialdata)
+    h = Handle(rc, ps, T); set_readout!(h, ps)
+    # the reference's loop silently runs in the eltype of the fed-back output (esn_cell.jl:176): Float64
+    # after the default (Float64) ridge fit, Float32 after RidgeRegression(Float32, λ)
+    Tc = promote_type(T, eltype(ps.readout.weight))
+    carry = Vector{Tc}(initial_carry(rc, st, Tc))
+    Y = Matrix{Float64}(undef, rc.readout.out_dims, steps)
+    check(ccall((:rcb_predict_autoregressive, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}, Ptr{Float64}),
+                h.ptr, Vector{T}(initialdata), steps, 1, dtype_id(Tc), carry, Y))
+    return Matrix{Tc}(Y), store_carry(st, carry)
+end
+
+function __predict(res::B200Reservoir, rc::ReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
+    h = Handle(rc, ps, T); set_readout!(h, ps)
+    carry = initial_carry(rc, st, T)
+    Y = Matrix{Float64}(undef, rc.readout.out_dims, size(data, 2))
+    check(ccall((:rcb_predict_teacher, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}),
+                h.ptr, Matrix{T}(data), size(data, 2), 1, carry, Y))
+    return Matrix{promote_type(T, eltype(ps.readout.weight))}(Y), store_carry(st, carry)
+end
+
+"""
+    b200(rc::ReservoirComputer) -> ReservoirComputer
+
+Same model, CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ))`.
+"""
+b200(rc::ReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.states_modifiers, rc.readout)
+
+export B200Reservoir, B200Ridge, b200
+
+end # module
