@@ -1,6 +1,6 @@
 // C-ABI of librcb200.so (declared in include/rcb200.h): contexts, model handles, and the host
 // orchestration of collect / fit_readout / train / predict.  Everything numeric runs in the
-// CUDA kernels of recurrence.cu, dense_kernels.cu, gram_tensor.cu and solve.cu; there is no CPU
+// CUDA kernels of recurrence.cu, recurrence_fast.cu, dense_kernels.cu, gram_tensor.cu and solve.cu; there is no CPU
 // compute path in this library.
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -606,13 +606,34 @@ int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, const voi
 static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt,
                            int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq, int32_t gram_mode,
                            double* GC) {
-  (void)gram_mode;
+  // RCB_GRAM_AUTO: tensor cores once the contraction is large (F^2 S >= 1e12 MACs); the exact FP64 kernel
+  // below that, for FP64 data, and whenever RCB_GRAM_FP64 is asked for.  RCB_GRAM=fp64|tensor overrides AUTO.
+  const double macs = (double)F * (double)F * (double)(T - washout) * (double)nseq;
+  bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 1e12);
+  if (gram_mode == RCB_GRAM_AUTO) {
+    const char* ov = getenv("RCB_GRAM");
+    if (ov && !strcmp(ov, "fp64")) tensor = false;
+    if (ov && !strcmp(ov, "tensor")) tensor = true;
+  }
+  if (zdt != RCB_F32) {
+    if (gram_mode == RCB_GRAM_TENSOR) return fail(RCB_ERR_UNSUPPORTED, "RCB_GRAM_TENSOR needs Float32 states");
+    tensor = false;
+  }
+  ctx->last_gram_tensor = tensor ? 1 : 0;
   timer_begin(ctx, RCB_TIMER_GRAM);
-  GramArgs g;
-  g.A = Z; g.a_dtype = zdt; g.M = F; g.lda = ldz; g.Bm = Z; g.b_dtype = zdt; g.Nc = F; g.ldb = ldz;
-  g.T = T; g.washout = washout; g.nseq = nseq; g.out = GC; g.ldo = F; g.lower_only = true;
-  int32_t st = launch_gram_fp64(ctx, g);
-  if (st == RCB_OK) {
+  int32_t st;
+  bool cross_done = false;
+  if (tensor) {
+    cross_done = d_out <= 8;
+    st = launch_gram_tensor(ctx, (const float*)Z, F, ldz, T, washout, nseq, GC, F, Y, ydt, d_out, ldy,
+                            cross_done ? GC + (size_t)F * F : nullptr);
+  } else {
+    GramArgs g;
+    g.A = Z; g.a_dtype = zdt; g.M = F; g.lda = ldz; g.Bm = Z; g.b_dtype = zdt; g.Nc = F; g.ldb = ldz;
+    g.T = T; g.washout = washout; g.nseq = nseq; g.out = GC; g.ldo = F; g.lower_only = true;
+    st = launch_gram_fp64(ctx, g);
+  }
+  if (st == RCB_OK && !cross_done) {
     GramArgs c;
     c.A = Z; c.a_dtype = zdt; c.M = F; c.lda = ldz; c.Bm = Y; c.b_dtype = ydt; c.Nc = d_out; c.ldb = ldy;
     c.T = T; c.washout = washout; c.nseq = nseq; c.out = GC + (size_t)F * F; c.ldo = F; c.lower_only = false;

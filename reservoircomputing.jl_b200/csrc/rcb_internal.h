@@ -132,13 +132,14 @@ struct rcb_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
-  char last_kernel[96] = "";  // variant name of the most recent recurrence launch
+  char last_kernel[96] = "";
+  int last_gram_tensor = 0;   // 1 when the most recent Gram ran on the tcgen05 path  // variant name of the most recent recurrence launch
   void* timer_pools = nullptr;  // rcb::TimerPool[3]
   // pinned staging + scratch, grown on demand
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
-  void* scratch[12] = {};
-  size_t scratch_bytes[12] = {};
+  void* scratch[16] = {};
+  size_t scratch_bytes[16] = {};
 };
 
 struct rcb_esn {
@@ -161,7 +162,8 @@ namespace rcb {
 
 // scratch slots
 enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5, SCR_TMP2 = 6, SCR_TGT = 7,
-       SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_COUNT = 12 };
+       SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_ZHI = 12, SCR_ZLO = 13, SCR_TCSCR = 14, SCR_TILES = 15,
+       SCR_COUNT = 16 };
 int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out);
 int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out);
 bool is_device_ptr(const void* p);
@@ -212,6 +214,10 @@ struct GramArgs {
   bool lower_only = false;
 };
 int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a);
+// tcgen05 3xTF32 path (gram_tensor.cu): G(F x F, FP64, lower triangle) += Z Z' over the same sample set; Z FP32
+// Y != nullptr && d_out <= 8: the cross term C(F x d_out, ld = ldo) += Z Y' rides along in FP64.
+int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
+                           double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C);
 
 // (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);

@@ -6,6 +6,7 @@ from ._lib import (ArgumentError, CudaError, DimensionMismatch, NumericError, Un
                    GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, lib)
 from .api import (NT, Device, DeepESN, ESN, ESNCell, ExtendedSquare, LinearReadout, NLAT1, NLAT2, NLAT3, Pad,
                   PartialSquare, QRFactorization, QRSolver, RidgeRegression, StandardRidge, addreadout,
-                  apply_modifiers, collectstates, csr_from_matrix, default_device, device_count, export_csr, fit_readout, identity,
+                  apply_modifiers, collectstates, csr_from_matrix, default_device, device_count, export_csr, fit_readout, gram,
+                  ridge_solve, identity,
                   predict, rand32, rand_sparse, randn32, relu, resetcarry, scaled_rand, setup, sigmoid, tanh,
                   tanh_fast, train, zeros32)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "librcb200.so")
+LIB_PATH = os.environ.get("RCB200_LIB") or os.path.join(os.path.dirname(_HERE), "librcb200.so")
 
 RCB_OK, RCB_ERR_ARGUMENT, RCB_ERR_DIMENSION, RCB_ERR_CUDA, RCB_ERR_NUMERIC, RCB_ERR_UNSUPPORTED, RCB_ERR_ALLOC = 0, -1, -2, -3, -4, -5, -6
 RCB_F32, RCB_F64 = 0, 1

@@ -626,6 +626,28 @@ def fit_readout(objective: RidgeRegression, states, targets, solver=None, device
     return W.astype(_promote(objective, Z, Y))
 
 
+def gram(states, targets, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO, into=None):
+    """[G | C] = [Z Z' | Z Y'] as an (F, F + d_out) Float64 array (lower triangle of G), the accumulator that
+    ranks all-reduce before ridge_solve (rcb_gram_accumulate).  `into` adds onto an existing accumulator."""
+    Z, Y = np.asfortranarray(states), np.asfortranarray(targets)
+    dev = device or default_device()
+    F, d_out = Z.shape[0], Y.shape[0]
+    GC = np.zeros((F, F + d_out), dtype=np.float64, order="F") if into is None else into
+    check(lib().rcb_gram_accumulate(dev.handle, ptr(Z), L.dtype_id(Z.dtype), F, Z.shape[1], max(F, 1), ptr(Y),
+                                    L.dtype_id(Y.dtype), d_out, max(d_out, 1), gram_mode, 1 if into is None else 0, ptr(GC)))
+    return GC
+
+
+def ridge_solve(GC, d_out: int, reg: float, device: Optional[Device] = None):
+    """(G + reg I) W' = C from a packed [G | C] (rcb_ridge_solve) -> W (d_out, F) Float64."""
+    dev = device or default_device()
+    GC = np.asfortranarray(GC, dtype=np.float64)
+    F = GC.shape[0]
+    W = np.empty((d_out, F), dtype=np.float64, order="F")
+    check(lib().rcb_ridge_solve(dev.handle, ptr(GC), F, d_out, float(reg), ptr(W)))
+    return W
+
+
 def addreadout(rc, output_matrix, ps, st):
     """addreadout!(rc, W, ps, st): functional update of ps.readout.weight (reservoircomputer.jl:137-144)."""
     return ps.merge(readout=ps.readout.merge(weight=output_matrix)), st
@@ -722,9 +744,13 @@ def resetcarry(rng, rc, st, init_carry=None):
 
 
 def apply_modifiers(mods, x, device: Optional[Device] = None):
-    """Matrix form of the state modifiers (src/states.jl:1-15): x (n, cols) -> (F, cols)."""
+    """State modifiers as plain functions (src/states.jl): a vector (n,) -> (F,) like NLAT2(::AbstractVector), or
+    the matrix form (__apply_tomatrix, :1-15): x (n, cols) -> (F, cols)."""
     mods = _as_mods(mods)
-    X = np.asfortranarray(x)
+    X = np.asarray(x)
+    if X.ndim == 1:
+        return apply_modifiers(mods, X.reshape(-1, 1), device)[:, 0]
+    X = np.asfortranarray(X)
     if X.dtype not in (np.float32, np.float64):
         X = np.asfortranarray(X.astype(np.float64))
     n, cols = X.shape

@@ -411,3 +411,58 @@ def test_c3_shape_properties(R):
 
 def const_init_sparse(M):
     return lambda rng, *dims: M
+
+
+# ---- K2 on tensor cores (tcgen05 3xTF32, csrc/gram_tensor.cu) ------------------------------------------
+@pytest.mark.parametrize("F,S,D", [(300, 5000, 3), (257, 1111, 1), (1024, 4096, 2), (640, 40000, 3)])
+def test_gram_tensor_matches_exact(R, F, S, D):
+    from rcb200 import _lib as L
+
+    rng = np.random.default_rng(F + S)
+    Z = np.asfortranarray((rng.standard_normal((F, S)) * rng.uniform(0.05, 1.0, (F, 1))).astype(np.float32))
+    Y = np.asfortranarray(rng.standard_normal((D, S)).astype(np.float32))
+    g_t = R.gram(Z, Y, gram_mode=L.GRAM_TENSOR)
+    g_e = R.gram(Z, Y, gram_mode=L.GRAM_FP64)
+    Z64 = Z.astype(np.float64)
+    G = np.tril(Z64 @ Z64.T)
+    assert np.allclose(np.tril(g_e[:, :F]), G, rtol=1e-12, atol=1e-9)
+    scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+    # FP32 accumulation inside the tensor core truncates: ~ -3e-8 relative per accumulated MMA, 192 per 512-sample chunk
+    assert np.max(np.abs(np.tril(g_t[:, :F]) - G) / scale) <= 1e-5
+    assert np.linalg.norm(np.tril(g_t[:, :F]) - G) / np.linalg.norm(G) <= 8e-6
+    assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)  # cross term: exact FP64 products
+
+
+def test_ridge_tensor_gram_weights(R):  # the reference's own Float32 case (test_train_ridge.jl:119-141) at rtol 1e-4
+    from rcb200 import _lib as L
+
+    rng = np.random.default_rng(5)
+    F, S, D, lam = 512, 20000, 3, 1e-3
+    Z = np.asfortranarray(rng.standard_normal((F, S)).astype(np.float32))
+    Wt = rng.standard_normal((D, F)).astype(np.float32)
+    Y = np.asfortranarray((Wt @ Z + 0.01 * rng.standard_normal((D, S))).astype(np.float32))
+    W = R.fit_readout(R.RidgeRegression(lam), Z, Y, gram_mode=L.GRAM_TENSOR)
+    Wref = O.train_ridge_qr(Z, Y, lam)
+    assert np.linalg.norm(W - Wref) / np.linalg.norm(Wref) <= WEIGHT_RTOL
+
+
+def test_train_tensor_gram_washout_and_batch(R):
+    """rcb_train with the tensor Gram over several sequences + washout against the exact-Gram run: same sample
+    set (index arithmetic), predictions of the two readouts agree."""
+    from rcb200 import _lib as L
+
+    rng = np.random.default_rng(11)
+    N, B, T, w = 512, 6, 700, 37
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), state_modifiers=(R.NLAT2, R.Pad(1.0)),
+                leak_coefficient=0.7)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(np.stack([series[:, :T] * (1 + 0.01 * b) for b in range(B)], axis=2).astype(np.float32))
+    target = np.asfortranarray(np.stack([series[:, 1:T + 1] * (1 + 0.01 * b) for b in range(B)], axis=2).astype(np.float32))
+    # the tensor Gram carries ~5e-6 relative error (truncating FP32 accumulation): keep lambda above that noise floor
+    (ps_t, _), sw = R.train(esn, data, target, ps, st, objective=R.RidgeRegression(1.0), washout=w, return_states=True,
+                            gram_mode=L.GRAM_TENSOR)
+    ps_e, _ = R.train(esn, data, target, ps, st, objective=R.RidgeRegression(1.0), washout=w, gram_mode=L.GRAM_FP64)
+    Zs = sw.reshape(sw.shape[0], -1, order="F").astype(np.float64)
+    pt, pe = ps_t.readout.weight @ Zs, ps_e.readout.weight @ Zs
+    assert np.linalg.norm(pt - pe) / np.linalg.norm(pe) <= 1e-4
