@@ -136,7 +136,10 @@ static void free_layer(Layer& L) {
   cudaFree(L.sell.perm); cudaFree(L.sell.blk_off); cudaFree(L.sell.blk_w); cudaFree(L.sell.vals); cudaFree(L.sell.cols);
   cudaFree(L.d_Win); cudaFree(L.d_bias); cudaFree(L.d_leak);
   cudaFree(L.fast.stream); cudaFree(L.fast.warp_off); cudaFree(L.fast.wwords);
+  cudaFree(L.fast4.stream); cudaFree(L.fast4.warp_off); cudaFree(L.fast4.wwords); cudaFree(L.d_Win4);
   L.fast = DevFast{};
+  L.fast4 = DevFast{};
+  L.d_Win4 = nullptr;
   L.sell = DevSell{};
   L.d_Win = L.d_bias = L.d_leak = nullptr;
 }
@@ -195,6 +198,20 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
       }
     }
   RCB_TRY(upload(winp, &L.d_Win));
+  if (L.d_in == 3) {
+    HostFast hf4;
+    RCB_TRY(fast_from_csr(L.csr, hs, &hf4, 4));
+    if (hf4.ok) {
+      RCB_TRY(upload(hf4.stream, &L.fast4.stream));
+      RCB_TRY(upload(hf4.warp_off, &L.fast4.warp_off));
+      RCB_TRY(upload(hf4.wwords, &L.fast4.wwords));
+      L.fast4.ok = true;
+      std::vector<float> w4((size_t)npos * 4, 0.f);
+      for (int p = 0; p < npos; ++p)
+        for (int d = 0; d < 3; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
+      RCB_TRY(upload(w4, &L.d_Win4));
+    }
+  }
   if (L.desc.use_bias) {
     std::vector<float> b(bias, bias + L.n);
     RCB_TRY(upload(b, &L.d_bias));

@@ -96,7 +96,8 @@ struct DevFast {
   uint32_t* warp_off = nullptr;
   uint64_t* wwords = nullptr;
 };
-int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out);
+// col_scale: the 16-bit column indices are stored multiplied by it (4 for recurrence_fast7.cu: byte offsets of floats)
+int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out, int32_t col_scale = 1);
 
 struct ModChain {  // fused-epilogue description of a state_modifiers tuple
   int32_t n = 0;
@@ -116,6 +117,8 @@ struct Layer {
   HostCsr csr;
   DevSell sell;
   DevFast fast;
+  DevFast fast4;              // same stream with column*4 (recurrence_fast7.cu)
+  float* d_Win4 = nullptr;    // [npos] float4 (w_in[0..2], 0) by position, when d_in == 3
   float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
   float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
   float* d_bias = nullptr;  // [n] by row

@@ -359,9 +359,10 @@ void sell_conflict_stats(const HostSell& s, int64_t* wf64, int64_t* ideal64, int
 }
 
 // Per-warp byte stream of the fast kernel, see HostFast.
-int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out) {
+int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out, int32_t col_scale) {
   (void)csr;
   out->ok = false;
+  if ((int64_t)sell.n * col_scale > 65536) return RCB_OK;  // scaled column indices must stay 16-bit
   out->n = sell.n; out->nthreads = sell.nthreads; out->R = sell.R; out->nwarps = sell.nwarps;
   if (sell.R > 16) return RCB_OK;  // 16 width bytes (two 64-bit words) per warp
   for (int32_t w : sell.blk_w)
@@ -393,7 +394,7 @@ int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out) {
           for (int32_t i = 0; i < cnt; ++i) {
             const size_t at = (size_t)(off + j + i) * 32 + l;
             v[cnt * l + i] = sell.vals[at];
-            c[cnt * l + i] = sell.cols[at];
+            c[cnt * l + i] = (uint16_t)(sell.cols[at] * col_scale);
           }
         p += (size_t)cnt * 192;
         j += cnt;
