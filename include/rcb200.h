@@ -105,6 +105,8 @@ RCB_API int32_t rcb_device_count(int32_t* count);
 RCB_API int32_t rcb_ctx_create(int32_t device, void* cuda_stream, rcb_ctx** out);
 RCB_API int32_t rcb_ctx_destroy(rcb_ctx* ctx);
 RCB_API int32_t rcb_ctx_synchronize(rcb_ctx* ctx);
+/* number of SMs of the context's GPU (the batched kernels size their sequence tiles from it) */
+RCB_API int32_t rcb_ctx_sm_count(rcb_ctx* ctx, int32_t* sms);
 /* number of kernel launches of this library issued on the context since creation (bench: gpu_launches) */
 RCB_API int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches);
 /* device time [ms] between the first and last kernel of the most recent data-path call, measured

@@ -367,6 +367,12 @@ int32_t rcb_ctx_synchronize(rcb_ctx* ctx) {
   return RCB_OK;
 }
 
+int32_t rcb_ctx_sm_count(rcb_ctx* ctx, int32_t* sms) {
+  if (!ctx || !sms) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *sms = ctx->sm_count;
+  return RCB_OK;
+}
+
 int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches) {
   if (!ctx || !launches) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   *launches = ctx->launches;

@@ -61,6 +61,7 @@ SIGNATURES = {
     "rcb_ctx_create": (_I32, [_I32, _P, C.POINTER(_P)]),
     "rcb_ctx_destroy": (_I32, [_P]),
     "rcb_ctx_synchronize": (_I32, [_P]),
+    "rcb_ctx_sm_count": (_I32, [_P, _P]),
     "rcb_ctx_launch_count": (_I32, [_P, C.POINTER(_I64)]),
     "rcb_ctx_last_kernel": (_I32, [_P, C.c_char_p, _I32]),
     "rcb_ctx_last_kernel_ms": (_I32, [_P, _I32, C.POINTER(C.c_float)]),

@@ -198,6 +198,11 @@ class Device:
         check(lib().rcb_ctx_last_kernel_ms(self.handle, which, C.byref(ms)))
         return ms.value
 
+    def sm_count(self) -> int:
+        n = C.c_int32()
+        check(lib().rcb_ctx_sm_count(self.handle, C.byref(n)))
+        return n.value
+
     def last_kernel(self) -> str:
         buf = C.create_string_buffer(128)
         check(lib().rcb_ctx_last_kernel(self.handle, buf, 128))
@@ -690,6 +695,72 @@ def train(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = N
         sw = states[:, washout:, :]
         return (ps2, st2), (sw[:, :, 0] if vec else sw)
     return ps2, st2
+
+
+# ---- multi-GPU: one process per GPU, partial [G | C] summed by ONE all-reduce -----------------
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous balanced shard [lo, hi) of n_items independent units (sequences / ensemble members)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def time_chunks(T: int, washout: int, rank: int, world: int, overlap: int):
+    """BASELINE config 2: one long sequence, time-chunked after the washout.  Rank r owns the samples
+    [own_lo, own_hi) of [washout, T); it runs the recurrence from start = max(0, own_lo - overlap) with a zero (rank > 0)
+    or the given (rank 0) initial state and discards the first own_lo - start columns as its local washout — the
+    echo-state property re-synchronises the state over the overlap.  Returns (start, own_lo, own_hi)."""
+    lo, hi = shard_range(T - washout, rank, world)
+    own_lo, own_hi = washout + lo, washout + hi
+    start = 0 if rank == 0 else max(0, own_lo - overlap)
+    return start, own_lo, own_hi
+
+
+def _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode):
+    h = _handle(rc, ps, d3.dtype, device)
+    _, T, B = d3.shape
+    h0, cell_sts = _initial_carry(rc, st, d3.dtype, B)
+    GC = np.empty((h.F, h.F + y3.shape[0]), dtype=np.float64, order="F")
+    hT = np.empty((h.sumN, B), dtype=d3.dtype, order="F")
+    check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B, int(washout), gram_mode, ptr(h0), ptr(GC),
+                                  ptr(hT)))
+    return GC, hT, cell_sts
+
+
+def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, washout: int = 0, group=None,
+                  device: Optional[Device] = None, gram_mode=L.GRAM_AUTO, _partial=None, _solve=None):
+    """train() for a pooled readout over sequences sharded across ranks: every rank passes ITS shard (d_in, T, B_r),
+    accumulates its partial [G | C] on its GPU (rcb_train_partial), the partials are summed by one all-reduce over the
+    process group (NCCL over NVLink; gloo in the CPU tests) and every rank solves the same FP64 system
+    (rcb_ridge_solve), so all ranks end with identical readout weights.  The recurrence itself needs no collective.
+    `_partial` / `_solve` are test seams for the CPU-only gloo tests of this host logic."""
+    import torch
+    import torch.distributed as dist
+
+    objective = objective or RidgeRegression(0.0)
+    d3, vec = _as3d(train_data)
+    y3, _ = _as3d(target_data)
+    if y3.dtype not in (np.float32, np.float64):
+        y3 = np.asfortranarray(y3.astype(np.float64))
+    _, T, B = d3.shape
+    if washout < 0:
+        raise ArgumentError(f"washout must be ≥ 0, got {washout}")
+    if washout >= T:
+        raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
+    if y3.shape[1] != T or y3.shape[2] != B:
+        raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
+    partial = _partial or (lambda: _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode))
+    GC, hT, cell_sts = partial() if _partial is None else _partial(rc, ps, st, d3, y3, washout)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.from_numpy(np.ascontiguousarray(GC.T))           # C-order view of the column-major [G | C]
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        GC = np.asfortranarray(t.cpu().numpy().T)
+    d_out = y3.shape[0]
+    W = (_solve or (lambda g, d, r: ridge_solve(g, d, r, device)))(GC, d_out, float(objective.reg))
+    W = np.asarray(W).astype(_promote(objective, d3, y3))
+    return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
 
 
 def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Device] = None):

@@ -466,3 +466,54 @@ def test_train_tensor_gram_washout_and_batch(R):
     Zs = sw.reshape(sw.shape[0], -1, order="F").astype(np.float64)
     pt, pe = ps_t.readout.weight @ Zs, ps_e.readout.weight @ Zs
     assert np.linalg.norm(pt - pe) / np.linalg.norm(pe) <= 1e-4
+
+
+# ---- K1 fast7 (csrc/recurrence_fast7.cu): the 7-sequences-per-CTA kernel the C3 bench line runs ----------
+@pytest.mark.parametrize("N,B,T,mod,leak", [(4096, 1030, 5, "nlat2", 0.5), (8192, 900, 3, "nlat2", 0.5), (4096, 1036, 4, "none", 1.0)])
+def test_fast7_kernel_parity(R, N, B, T, mod, leak):
+    """B > 6 x #SMs selects k1_fast7; checked (i) against the oracle on spot sequences (incl. the ragged last CTA),
+    (ii) bit-for-bit determinism, (iii) against the generic kernel on every sequence."""
+    rng = np.random.default_rng(N + B)
+    mods = R.NLAT2 if mod == "nlat2" else ()
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=True),
+                state_modifiers=mods, leak_coefficient=leak)
+    ps, st = R.setup(rng, esn)
+    lor = O.lorenz_series(T + B)
+    data = np.asfortranarray(np.stack([lor[:, b:b + T] for b in range(B)], axis=2).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    stf = fixed_h0(R, st, esn, [h0])
+    os.environ.pop("RCB_K1_MODE", None)
+    states, st2 = R.collectstates(esn, data, ps, stf)
+    if R.default_device().sm_count() * 6 < B:
+        assert R.default_device().last_kernel().startswith("k1_fast7"), R.default_device().last_kernel()
+    layers = oracle_layers(R, esn, ps)
+    for b in (0, 7 * 73 + 6, B - 1):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
+        assert np.max(np.abs(st2.reservoir.carry[0][:, b] - hs[0])) <= STATE_RTOL * np.max(np.abs(hs[0]))
+    again, _ = R.collectstates(esn, data, ps, stf)
+    assert again.tobytes() == states.tobytes()
+    os.environ["RCB_K1_MODE"] = "v1"
+    try:
+        generic, _ = R.collectstates(esn, data, ps, stf)
+        assert not R.default_device().last_kernel().startswith("k1_fast7")
+    finally:
+        os.environ.pop("RCB_K1_MODE", None)
+    err = np.max(np.abs(states - generic).reshape(N, -1), axis=0) / np.maximum(np.max(np.abs(generic).reshape(N, -1), axis=0), 1e-30)
+    assert float(err.max()) <= STATE_RTOL
+
+
+def test_train_sharded_single_rank_matches_train(R):
+    """train_sharded (rcb_train_partial -> [all-reduce] -> rcb_ridge_solve) == train (rcb_train) on one rank."""
+    rng = np.random.default_rng(23)
+    N, B, T, w = 256, 5, 300, 20
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), state_modifiers=R.NLAT2, leak_coefficient=0.8)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + B + 1)
+    data = np.asfortranarray(np.stack([series[:, b:b + T] for b in range(B)], axis=2).astype(np.float32))
+    target = np.asfortranarray(np.stack([series[:, b + 1:b + T + 1] for b in range(B)], axis=2).astype(np.float32))
+    st = fixed_h0(R, st, esn, [rng.standard_normal((N, B)).astype(np.float32)])
+    ps_a, st_a = R.train(esn, data, target, ps, st, objective=R.RidgeRegression(1e-4), washout=w)
+    ps_b, st_b = R.train_sharded(esn, data, target, ps, st, objective=R.RidgeRegression(1e-4), washout=w)
+    assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) / np.linalg.norm(ps_a.readout.weight) <= 1e-10
+    assert np.array_equal(st_a.reservoir.carry[0], st_b.reservoir.carry[0])
