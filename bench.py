@@ -276,6 +276,9 @@ def run_b200(args, w):
     # end to end through the C-ABI with HOST buffers: pinned inputs H2D every chunk, final carry D2H
     e2e_ms, _, _, _ = timed(u_chunks_host, True, max(1, min(args.steps, 3)), 1)
     e2e_value = units / (e2e_ms * 1e-3)
+    ridge = None
+    if not args.no_ridge:
+        ridge = ridge_leg(torch, R, L, lib, dev, h, w, u_chunks_dev, h0, carry, ring, rank, world, barrier)
     pk = peaks()
     F = h.F
     alg_bytes = 4.0 * F * T * B + 4.0 * d_in * T * B  # state stream out + inputs in, per GPU per pass
@@ -294,6 +297,9 @@ def run_b200(args, w):
                     "d2h_bytes_per_step": int(4 * N * B), "ms_per_step": e2e_ms,
                     "call": "rcb_collect (collectstates) per time chunk, pinned host inputs, final carry read back"},
             "gpu_launches": int(launches), "clocks": clocks}
+    line["roofline"]["traffic"] = ncu_traffic(dev.last_kernel())
+    if ridge is not None:
+        line["ridge"] = ridge
     if rank == 0:
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_sample(w, W, Win)
@@ -305,6 +311,74 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of this same command (profiles/k1_traffic.json; null when the capture is of another kernel variant)."""
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get("bytes_per_launch") if kernel_name.startswith(d.get("kernel_prefix", "?")) else None
+
+
+def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, world, barrier):
+    """BASELINE metric, second half: ridge train time = one full pooled fit over this workload — per time chunk the
+    recurrence (K1) streams states into the ring and the tcgen05 Gram (K2) folds them into the FP64 [G | C]; then one
+    all-reduce of [G | C] across ranks (N > 1) and the FP64 Cholesky solve (K3).  Targets: next input (d_out = d_in)."""
+    N, d_in, B, T, Tc = w["N"], w["d_in"], w["B"], w["T"], w["chunk"]
+    F, D = h.F, d_in
+    nchunks = len(u_chunks)
+    GC = torch.zeros((F + D, F), dtype=torch.float64, device="cuda")      # column-major F x (F + D)
+    Wout = torch.empty((F, D), dtype=torch.float64, device="cuda")        # column-major D x F
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    k1_ms = gram_ms = 0.0
+    barrier()
+    e[0].record()
+    carry.copy_(h0, non_blocking=True)
+    for c in range(nchunks):
+        tc = u_chunks[c].shape[1]
+        L.check(lib.rcb_collect(h.handle, L.ptr(u_chunks[c]), tc, B, L.ptr(carry), L.ptr(ring), L.ptr(carry)))
+        k1_ms += dev.kernel_ms(L.TIMER_RECURRENCE)
+        # targets of the chunk = the inputs themselves (shape d_in x tc x B, same memory order): a stand-in of the right size
+        L.check(lib.rcb_gram_accumulate(dev.handle, L.ptr(ring), 0, F, tc * B, F, L.ptr(u_chunks[c]), 0, D, D, L.GRAM_TENSOR,
+                                        1 if c == 0 else 0, L.ptr(GC)))
+        gram_ms += dev.kernel_ms(L.TIMER_GRAM)
+    e[1].record()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(GC)
+    e[2].record()
+    lam = 1e-4 * T * B * world  # relative ridge 1e-4: above the ~5e-6 relative accuracy of the tensor-core Gram (DESIGN.md K2)
+    L.check(lib.rcb_ridge_solve(dev.handle, L.ptr(GC), F, D, lam, L.ptr(Wout)))
+    e[3].record()
+    barrier()
+    t_acc, t_ar, t_solve = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([t_acc, t_ar, t_solve, k1_ms, gram_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_acc, t_ar, t_solve, k1_ms, gram_ms = [float(x) for x in t]
+    S = float(T) * B
+    tiles = sum(1 for i in range((F + 255) // 256) for j in range((F + 255) // 256) if j * 256 <= i * 256 + 255) * 2
+    issued = 3.0 * 2.0 * tiles * 128 * 256 * S          # three TF32 MMAs per tile per sample
+    bf16 = 1590.0  # fallback of B200_PROFILING.md
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16 = float(json.load(f).get("bf16_tflops", bf16))
+    ok = bool(torch.isfinite(Wout).all())
+    return {"train_s": (t_acc + t_ar + t_solve) * 1e-3, "recurrence_s": k1_ms * 1e-3, "gram_s": gram_ms * 1e-3, "allreduce_s": t_ar * 1e-3,
+            "solve_s": t_solve * 1e-3, "features": F, "samples_per_gpu": S, "lambda": lam, "finite": ok,
+            "gram_algorithmic_tflops": (F * (F + 1) + 2 * F * D) * S / (gram_ms * 1e-3) / 1e12,
+            "gram_issued_tf32_tflops": issued / (gram_ms * 1e-3) / 1e12,
+            "tensor_frac": {"of_nominal_tf32_1100": issued / (gram_ms * 1e-3) / 1e12 / 1100.0,
+                            "of_half_measured_bf16": issued / (gram_ms * 1e-3) / 1e12 / (bf16 / 2.0),
+                            "note": "gram_s includes the HBM-bound TF32 hi/lo split pre-pass; ncu tensor-pipe % in profiles/"},
+            "gram_mode": "tcgen05 3xTF32, FP32 TMEM accumulate per 512 samples, FP64 across"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ridge", action="store_true", help="skip the ridge train-time leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

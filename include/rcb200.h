@@ -100,8 +100,10 @@ typedef struct rcb_esn rcb_esn;
 RCB_API int32_t rcb_version(void);
 RCB_API const char* rcb_last_error(void);
 RCB_API int32_t rcb_device_count(int32_t* count);
-/* One context = one GPU + one stream.  `cuda_stream` NULL -> the library creates its own stream;
- * otherwise a cudaStream_t of the same process (e.g. torch.cuda.current_stream().cuda_stream). */
+/* One context = one GPU + one stream.  `cuda_stream` NULL -> the library creates its own non-blocking stream (it does
+ * NOT synchronise with the legacy default stream: order device buffers you produce on other streams yourself);
+ * otherwise a cudaStream_t of the same process (e.g. torch.cuda.current_stream().cuda_stream; the default streams are
+ * passed as cudaStreamLegacy (0x1) / cudaStreamPerThread (0x2)). */
 RCB_API int32_t rcb_ctx_create(int32_t device, void* cuda_stream, rcb_ctx** out);
 RCB_API int32_t rcb_ctx_destroy(rcb_ctx* ctx);
 RCB_API int32_t rcb_ctx_synchronize(rcb_ctx* ctx);

@@ -735,7 +735,15 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
   void* w_dev = nullptr;
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
   RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
-  RCB_TRY(launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev));
+  int32_t st = launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev);
+  if (st == RCB_ERR_NUMERIC && gram_mode == RCB_GRAM_AUTO && ctx->last_gram_tensor) {
+    // the tensor-core Gram carries ~5e-6 relative error; when lambda sits below that noise floor the system can come out
+    // indefinite.  The states are at hand here: redo the accumulation with exact products in FP64 and solve again.
+    RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
+                                RCB_GRAM_FP64, 1, (double*)gc));
+    st = launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev);
+  }
+  RCB_TRY(st);
   RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;

@@ -438,6 +438,7 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
   RCB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
   // sample sub-chunks sized so that the split states stay within 6 GiB
   long long Ssub = ((long long)6 << 30) / (ldp * 8);
+  if (const char* ov = getenv("RCB_GRAM_SUB_SAMPLES")) Ssub = atoll(ov);  // testing hook: force several sub-chunks
   Ssub = Ssub / KC * KC;
   if (Ssub < KC) Ssub = KC;
   if (Ssub > Stot) Ssub = Stot;

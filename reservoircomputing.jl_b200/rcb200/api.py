@@ -180,8 +180,11 @@ class Device:
     """One GPU + one stream (rcb_ctx).  ``stream`` may be a raw cudaStream_t (e.g. torch's)."""
 
     def __init__(self, device: int = 0, stream: Optional[int] = None):
+        # stream: None -> the library creates its own (non-blocking) stream; a cudaStream_t handle -> that stream.
+        # torch reports its default stream as handle 0, which CUDA spells cudaStreamLegacy (0x1) when passed explicitly.
         h = C.c_void_p()
-        check(lib().rcb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        arg = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        check(lib().rcb_ctx_create(int(device), arg, C.byref(h)))
         self.handle = h
         self.device = int(device)
 

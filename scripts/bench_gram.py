@@ -26,6 +26,12 @@ for name, mode in modes:
     print(f"{name}: F={F} S={S} D={D}  {ms:.3f} ms  algorithmic {alg / ms / 1e9:.1f} TFLOP/s  "
           f"full-square-equivalent {2 * F * F * S / ms / 1e9:.1f} TFLOP/s", flush=True)
     res[name] = GC.clone()
+Cref = (Z.double().T @ Y.double()).T.contiguous()    # (D, F) == rows F..F+D of the packed array
+for name in res:
+    e = (res[name][F:] - Cref).abs()
+    bad = (e > 1e-6).nonzero()
+    print(f"{name}: cross term max abs err vs torch fp64: {float(e.max()):.3e}  bad entries {len(bad)}"
+          + (f" rows(d) {bad[:, 0].unique().tolist()} f range {int(bad[:, 1].min())}..{int(bad[:, 1].max())}" if len(bad) else ""))
 if len(res) == 2:
     a, b = res["tensor"][:F].T.tril(), res["fp64"][:F].T.tril()
     d = torch.sqrt(torch.outer(torch.diag(b), torch.diag(b)))

@@ -433,6 +433,25 @@ def test_gram_tensor_matches_exact(R, F, S, D):
     assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)  # cross term: exact FP64 products
 
 
+def test_gram_tensor_sub_chunks(R):
+    """Several sample sub-chunks per call (what F = 8192 x 256k samples needs): G and the fused cross term."""
+    from rcb200 import _lib as L
+
+    rng = np.random.default_rng(77)
+    F, S, D = 384, 9000, 3
+    Z = np.asfortranarray(rng.standard_normal((F, S)).astype(np.float32))
+    Y = np.asfortranarray(rng.standard_normal((D, S)).astype(np.float32))
+    os.environ["RCB_GRAM_SUB_SAMPLES"] = "2048"
+    try:
+        g_t = R.gram(Z, Y, gram_mode=L.GRAM_TENSOR)
+    finally:
+        os.environ.pop("RCB_GRAM_SUB_SAMPLES", None)
+    Z64 = Z.astype(np.float64)
+    G = np.tril(Z64 @ Z64.T)
+    assert np.max(np.abs(np.tril(g_t[:, :F]) - G)) / np.max(np.diag(G)) <= 1e-5
+    assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)
+
+
 def test_ridge_tensor_gram_weights(R):  # the reference's own Float32 case (test_train_ridge.jl:119-141) at rtol 1e-4
     from rcb200 import _lib as L
 
@@ -515,5 +534,6 @@ def test_train_sharded_single_rank_matches_train(R):
     st = fixed_h0(R, st, esn, [rng.standard_normal((N, B)).astype(np.float32)])
     ps_a, st_a = R.train(esn, data, target, ps, st, objective=R.RidgeRegression(1e-4), washout=w)
     ps_b, st_b = R.train_sharded(esn, data, target, ps, st, objective=R.RidgeRegression(1e-4), washout=w)
-    assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) / np.linalg.norm(ps_a.readout.weight) <= 1e-10
+    # FP64 atomics make the Gram's summation order run-dependent (1e-16), the conditioning amplifies it
+    assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) / np.linalg.norm(ps_a.readout.weight) <= 1e-5
     assert np.array_equal(st_a.reservoir.carry[0], st_b.reservoir.carry[0])
