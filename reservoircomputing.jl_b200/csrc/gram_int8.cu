@@ -1,0 +1,542 @@
+// K2 (tensor-core path): G += Z Z' on the 5th-generation tensor cores with EXACT accumulation.
+//
+// Replaces the O((T+F) F^2) Householder QR of the augmented system (src/train.jl:108-198) by the Gram form the
+// reference's own tests use as cross-check (test/test_train_ridge.jl:18-27).  This file produces the lower triangle of
+// G = Z Z' and, on the way, the cross term C = Z Y' (exact products, FP64).
+//
+// Why not TF32/BF16 splits: the FP32 accumulator of the tensor core truncates (~ -3e-8 relative per accumulated MMA, a
+// bias, not noise).  Over the 1e7 samples of a pooled fit that is ~5e-6 of lambda_max(G) — reservoir features are
+// strongly correlated, lambda_max ~ F * G_ii — and (G + lambda I) comes out indefinite for any reasonable lambda (r01
+// measurement).  So the contraction runs in fixed point instead (the Ozaki scheme):
+//   * a pre-pass finds s_f = 2^e_f > max_t |z_f(t)| per feature and rounds q = rint(z 2^(22-e_f)), |q| < 2^22, then cuts
+//     q into three balanced base-256 digits q = a1 2^16 + a2 2^8 + a3 (a1 in [-64, 64], a2, a3 in [-128, 127]): three
+//     INT8 planes per state (3 B instead of 4 B of FP32; quantisation error <= 2^-23 s_f, unbiased);
+//   * tcgen05.mma.kind::i8 multiplies digit planes into INT32 accumulators in tensor memory — INTEGER accumulation is
+//     exact: acc2 += a1 a1', acc3 += a1 a2' + a2 a1', acc4 += a1 a3' + a3 a1' + a2 a2', acc5 += a2 a3' + a3 a2'.  Only
+//     a3 a3' is dropped: zero-mean digit noise of 3e-10 s_i s_j per sample.  (Dropping order 5 as well left 1e-7 s_i s_j
+//     per sample, which showed as ||E|| ~ lambda on outlier-scaled features — r01 measurement, scripts/dbg_ridge.py.)
+//   * after at most 32768 samples (|acc| < 2^31) the epilogue warps fold
+//         G_ij += 2^(e_i + e_j - 28) (2^16 acc2 + 2^8 acc3 + acc4 + 2^-8 acc5)          in FP64, red.global.add.f64.
+//   Eight INT8 MMAs (K = 32) per 32 samples cost 2/3 of the tensor time of three TF32 MMAs (K = 8) per 8 samples.
+//
+// Mapping: Z is F x S column-major, so both operands are MN-major.  The pre-pass writes the planes pre-tiled in exactly
+// the shared-memory image the MMA wants — [32-sample block][128-feature block][plane][32 rows x 128 B], 16-byte chunks
+// XOR-swizzled with (row & 7) (UMMA SWIZZLE_128B, MN-major, 8-bit) — so a pipeline stage is filled by two contiguous
+// cp.async.bulk copies.  One CTA = one 128 x 256 tile of the lower triangle; CTA pairs (a 2 x 1 cluster, 256 x 256
+// super-tile) fetch half of the shared B tile each and multicast it.  TMEM holds acc3 | acc4 (phase A, 5 MMAs per
+// K-step) or acc2 | acc5 (phase B, 3 MMAs per K-step).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
+// elected thread), warps 2-9 = epilogue.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "rcb_internal.h"
+
+namespace rcb {
+
+namespace {
+
+constexpr int TM = 128, TN = 256, KB = 32, PLANES = 3, STAGES = 5;
+constexpr int BOX = 128 * KB;                          // 4 KB: one plane of 128 features x 32 samples
+constexpr int BLK = PLANES * BOX;                      // 12 KB: the three planes of a feature block
+constexpr int STAGE_BYTES = BLK + 2 * BLK;             // A block + two B blocks = 36 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                           // two per TMEM lane quadrant, half of the tile columns each
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+constexpr int CR = 2, CLUSTER = CR;                    // CTA pair: rows 2I, 2I+1 of 128 share the 256 B columns
+constexpr int MAX_RANGE = 32768;                       // samples per accumulation: 3 * 128 * 128 * 32768 < 2^31
+
+struct GramParams8 {
+  const int2* tiles;          // super-tiles (256 rows x 256 columns) touching the lower triangle
+  const unsigned char* q8;    // digit planes, pre-tiled (see split_int8_kernel)
+  const double* sf;           // per feature 2^(e_f - 14)
+  long long nfb;              // 128-feature blocks per sample block
+  int ntiles, splits;
+  long long S;                // samples in the planes buffer
+  long long per_split;        // samples per K-range, multiple of KB, <= MAX_RANGE
+  double* G;                  // F x F column-major, lower triangle accumulated
+  long long ldo, F;
+  int* err;                   // set to 1 when a barrier wait timed out (the kernel then traps)
+  long long* prof;            // RCB_GRAM_PROF: per CTA [mma waits full, mma waits tmem, producer waits empty, epi waits, total]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug must not hang the GPU
+      if (err) *err = 1;
+      __trap();
+    }
+  }
+}
+// contiguous bulk copy global -> shared memory of every CTA in `mask` (same offset), completing on each one's barrier
+__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor of an 8-bit operand (cute::UMMA::SmemDescriptor bit layout):
+// 128 features = one 128-byte row per sample; 8 samples = one 1024-byte swizzle group (SBO); the next 128 features (LBO).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;      // leading byte offset: next 128 features
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: next 8 samples
+  d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::i8: S32 accumulate, signed 8-bit A and B, both MN-major, M = 128, N = 256 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+                           ((uint32_t)(TM >> 4) << 24);
+
+#define TMEM_LD16(addr, v)                                                                                                        \
+  asm volatile(                                                                                                                   \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),   \
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                              \
+      : "r"(addr)                                                                                                                 \
+      : "memory")
+
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) gram_i8_kernel(const GramParams8 p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  // barriers: full[STAGES] | empty[STAGES] | tfull | tempty | tmem base
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tempty = tfull + 8, tmem_slot = tempty + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CR); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer multicasts into it
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int ri = (int)crank;                                   // my 128-row block inside the 256 x 256 super-tile
+  const long long cid = blockIdx.x / CLUSTER, ncl = gridDim.x / CLUSTER;
+  const uint16_t mask_self = (uint16_t)(1u << ri), mask_all = (uint16_t)((1u << CR) - 1u);
+  const long long nitems = (long long)p.ntiles * p.splits;
+
+  if (warp == 0) {
+    // ===== producer: two contiguous bulk copies per stage =====
+    if (lane == 0) {
+      long long it = 0, wait_acc = 0;
+      const long long tstart = clock64();
+      for (long long item = cid; item < nitems; item += ncl) {
+        const int2 tl = p.tiles[item % p.ntiles];
+        const long long split = item / p.ntiles;
+        const long long s_beg = split * p.per_split;
+        const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
+        const int nst = (int)((s_end - s_beg + KB - 1) / KB);
+        const long long fa = (long long)tl.x * CR + ri, fb = (long long)tl.y * 2 + ri;   // my A block; the B block I fetch
+        for (int phase = 0; phase < 2; ++phase) {
+          const uint32_t bytes = BLK;                      // all three digit planes of a 128-feature block
+          for (int st = 0; st < nst; ++st, ++it) {
+            const int slot = (int)(it % STAGES);
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            const long long w0 = clock64();
+            mbar_wait(empty0 + 8 * slot, ph ^ 1u, p.err);  // both CTAs of the pair have released the slot
+            wait_acc += clock64() - w0;
+            const uint32_t fbar = full0 + 8 * slot;
+            mbar_expect_tx(fbar, 3 * bytes);               // bytes landing in MY shared memory: A + two B blocks
+            const uint32_t sa = base + slot * STAGE_BYTES; // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]
+            const unsigned char* blk = p.q8 + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
+            bulk_load_mc(sa, blk + (size_t)fa * BLK, bytes, fbar, mask_self);
+            bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, bytes, fbar, mask_all);
+          }
+        }
+      }
+      if (p.prof) { p.prof[blockIdx.x * 5 + 2] = wait_acc; p.prof[blockIdx.x * 5 + 4] = clock64() - tstart; }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      long long it = 0, ci = 0, wfull = 0, wtm = 0;
+      for (long long item = cid; item < nitems; item += ncl) {
+        const long long split = item / p.ntiles;
+        const long long s_beg = split * p.per_split;
+        const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
+        const int nst = (int)((s_end - s_beg + KB - 1) / KB);
+        for (int phase = 0; phase < 2; ++phase, ++ci) {
+          const long long w0 = clock64();
+          mbar_wait(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);  // the epilogue has drained the previous accumulators
+          wtm += clock64() - w0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int st = 0; st < nst; ++st, ++it) {
+            const int slot = (int)(it % STAGES);
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            const long long w1 = clock64();
+            mbar_wait(full0 + 8 * slot, ph, p.err);
+            wfull += clock64() - w1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = base + slot * STAGE_BYTES;
+            const uint64_t A1 = umma_desc(sa, BLK), A2 = umma_desc(sa + BOX, BLK), A3 = umma_desc(sa + 2 * BOX, BLK);
+            const uint64_t B1 = umma_desc(sa + BLK, BLK), B2 = umma_desc(sa + BLK + BOX, BLK), B3 = umma_desc(sa + BLK + 2 * BOX, BLK);
+            const uint32_t acc = st > 0 ? 1u : 0u;
+            if (phase == 0) {
+              umma_i8(tmem_base, A1, B2, IDESC, acc);          // acc3 = a1 a2' + a2 a1'
+              umma_i8(tmem_base, A2, B1, IDESC, 1u);
+              umma_i8(tmem_base + TN, A1, B3, IDESC, acc);     // acc4 = a1 a3' + a3 a1' + a2 a2'
+              umma_i8(tmem_base + TN, A3, B1, IDESC, 1u);
+              umma_i8(tmem_base + TN, A2, B2, IDESC, 1u);
+            } else {
+              umma_i8(tmem_base, A1, B1, IDESC, acc);          // acc2 = a1 a1'
+              umma_i8(tmem_base + TN, A2, B3, IDESC, acc);     // acc5 = a2 a3' + a3 a2'
+              umma_i8(tmem_base + TN, A3, B2, IDESC, 1u);
+            }
+            umma_commit_mc(empty0 + 8 * slot, mask_all);       // tells both producers that fill my stage it is free
+          }
+          umma_commit(tfull);                                  // accumulators of this phase complete
+        }
+      }
+      if (p.prof) { p.prof[blockIdx.x * 5 + 0] = wfull; p.prof[blockIdx.x * 5 + 1] = wtm; }
+    }
+  } else {
+    // ===== epilogue: INT32 accumulators -> FP64 G =====
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;          // tile row
+    const int nbeg = ((warp - 2) >> 2) * (TN / (EPI_WARPS / 4));
+    long long ci = 0, wepi = 0;
+    for (long long item = cid; item < nitems; item += ncl) {
+      const int2 tl = p.tiles[item % p.ntiles];
+      const long long gi = ((long long)tl.x * CR + ri) * TM + m;
+      const long long gj0 = (long long)tl.y * TN;
+      const double sfi = gi < p.F ? __ldg(p.sf + gi) : 0.0;
+      for (int phase = 0; phase < 2; ++phase, ++ci) {
+        const long long w0 = clock64();
+        mbar_wait(tfull, (uint32_t)(ci & 1), p.err);
+        wepi += clock64() - w0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+        for (int n0 = nbeg; n0 < nbeg + TN / (EPI_WARPS / 4); n0 += 16) {
+          uint32_t v[16], w[16];
+          TMEM_LD16(trow + (uint32_t)n0, v);
+          TMEM_LD16(trow + (uint32_t)(TN + n0), w);
+          double sfj[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) sfj[q] = gj0 + n0 + q < p.F ? __ldg(p.sf + gj0 + n0 + q) : 0.0;
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const long long gj = gj0 + n0 + q;
+            if (gi < p.F && gj <= gi) {
+              const double a = phase == 0 ? 256.0 * (double)(int)v[q] + (double)(int)w[q]
+                                          : 65536.0 * (double)(int)v[q] + 0.00390625 * (double)(int)w[q];
+              if (a != 0.0) atomicAdd(p.G + (size_t)gj * p.ldo + gi, a * sfi * sfj[q]);
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+    if (p.prof && threadIdx.x == 64) p.prof[blockIdx.x * 5 + 3] = wepi;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- pre-pass 1: per-feature max |z| over the sample set (non-negative floats order like their bit patterns) --------
+// VEC = 4: one thread owns 4 consecutive features (16-byte loads; needs ldz % 4 == 0 and a 16-byte aligned Z).
+constexpr int SLAB = 128;
+template <int VEC>
+__global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ Z, long long ldz, long long F, long long T,
+                                                     long long washout, long long Te, long long s0, long long Sc,
+                                                     int* __restrict__ amax) {
+  const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (f >= F) return;
+  const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB < Sc ? sl0 + SLAB : Sc;
+  float mx[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) mx[v] = 0.f;
+#pragma unroll 8
+  for (long long sl = sl0; sl < sl1; ++sl) {
+    const long long s = s0 + sl;
+    const long long col = (s / Te) * T + washout + (s % Te);
+    if constexpr (VEC == 4) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(Z + (size_t)col * ldz + f));
+      mx[0] = fmaxf(mx[0], fabsf(x.x)); mx[1] = fmaxf(mx[1], fabsf(x.y)); mx[2] = fmaxf(mx[2], fabsf(x.z)); mx[3] = fmaxf(mx[3], fabsf(x.w));
+    } else {
+      mx[0] = fmaxf(mx[0], fabsf(__ldg(Z + (size_t)col * ldz + f)));
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+    if (f + v < F) atomicMax(amax + f + v, __float_as_int(mx[v]));
+}
+
+__device__ __forceinline__ void digits(float x, float qs, int& a1, int& a2, int& a3) {
+  const int q = __float2int_rn(x * qs);
+  a3 = (int)(signed char)(q & 0xFF);
+  const int q1 = (q - a3) >> 8;
+  a2 = (int)(signed char)(q1 & 0xFF);
+  a1 = (q1 - a2) >> 8;
+}
+
+// ---- pre-pass 2: gather the sample set (washout skipped, src/train.jl:36-47), quantise, cut into digit planes laid out
+// as the MMA's shared-memory image, and accumulate the cross term C = Z Y' (d_out <= 8) in FP64 on the way.
+// One thread = VEC consecutive features over a slab of samples: with VEC = 4 a warp reads 512 contiguous bytes per sample
+// and writes one full 128-byte row of each digit plane (32-bit stores, full sectors).
+template <typename TY, int VEC>
+__global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict__ Z, long long ldz, long long F, long long ldp,
+                                                         long long T, long long washout, long long Te, long long s0,
+                                                         long long Sc, const int* __restrict__ amax, unsigned char* __restrict__ q8,
+                                                         double* __restrict__ sf, const TY* __restrict__ Y, long long ldy, int d_out,
+                                                         double* __restrict__ C, long long ldc) {
+  const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB;  // whole sample blocks: rows >= Sc become zeros
+  if (f >= ldp) return;
+  float qs[VEC];
+  bool live[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    live[v] = f + v < F;
+    int e = 0;
+    if (live[v]) {
+      const float mx = __int_as_float(amax[f + v]);
+      if (mx > 0.f && mx < INFINITY) frexpf(mx, &e);   // mx = m 2^e, m in [0.5, 1): 2^e > mx
+      if (e < -100) e = -100;
+    }
+    qs[v] = ldexpf(1.0f, 22 - e);                      // |z| qs < 2^22
+    if (blockIdx.y == 0) sf[f + v] = live[v] ? ldexp(1.0, e - 14) : 0.0;
+  }
+  double acc[VEC][8];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[v][d] = 0.0;
+  const long long nfb = ldp / 128, fbk = f >> 7;
+  const int c = (int)(f & 127);
+#pragma unroll 2
+  for (long long sl = sl0; sl < sl1; ++sl) {
+    int a1[VEC], a2[VEC], a3[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a1[v] = a2[v] = a3[v] = 0;
+    if (sl < Sc) {
+      const long long s = s0 + sl;
+      const long long col = (s / Te) * T + washout + (s % Te);
+      float x[VEC];
+      if constexpr (VEC == 4) {
+        if (live[3]) {
+          const float4 t = __ldcs(reinterpret_cast<const float4*>(Z + (size_t)col * ldz + f));
+          x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) x[v] = live[v] ? __ldcs(Z + (size_t)col * ldz + f + v) : 0.f;
+        }
+      } else {
+        x[0] = live[0] ? __ldcs(Z + (size_t)col * ldz + f) : 0.f;
+      }
+      double y[8];
+      if (C) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) y[d] = d < d_out ? (double)__ldg(Y + (size_t)col * ldy + d) : 0.0;
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (live[v]) {
+          digits(x[v], qs[v], a1[v], a2[v], a3[v]);
+          if (C) {
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+              if (d < d_out) acc[v][d] = fma((double)x[v], y[d], acc[v][d]);
+          }
+        }
+      }
+    }
+    const long long sb = sl / KB;
+    const int r = (int)(sl % KB);
+    unsigned char* box = q8 + ((size_t)(sb * nfb + fbk) * PLANES) * BOX + r * 128 + ((((c >> 4) ^ (r & 7)) << 4) | (c & 15));
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<uint32_t*>(box) = (uint32_t)(a1[0] & 0xFF) | ((uint32_t)(a1[1] & 0xFF) << 8) | ((uint32_t)(a1[2] & 0xFF) << 16) | ((uint32_t)(a1[3] & 0xFF) << 24);
+      *reinterpret_cast<uint32_t*>(box + BOX) = (uint32_t)(a2[0] & 0xFF) | ((uint32_t)(a2[1] & 0xFF) << 8) | ((uint32_t)(a2[2] & 0xFF) << 16) | ((uint32_t)(a2[3] & 0xFF) << 24);
+      *reinterpret_cast<uint32_t*>(box + 2 * BOX) = (uint32_t)(a3[0] & 0xFF) | ((uint32_t)(a3[1] & 0xFF) << 8) | ((uint32_t)(a3[2] & 0xFF) << 16) | ((uint32_t)(a3[3] & 0xFF) << 24);
+    } else {
+      box[0] = (unsigned char)a1[0];
+      box[BOX] = (unsigned char)a2[0];
+      box[2 * BOX] = (unsigned char)a3[0];
+    }
+  }
+  if (C) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      if (live[v]) {
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          if (d < d_out) atomicAdd(C + (size_t)d * ldc + f + v, acc[v][d]);
+      }
+  }
+}
+
+}  // namespace
+
+// G(F x F, ld = ldo, FP64, lower triangle) += Z Z' over {b*T + t : b < nseq, washout <= t < T}; Z is FP32, device.
+// When Y is given (d_out <= 8), C(F x d_out, ld = ldo) += Z Y' is accumulated by the same pre-pass.
+int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
+                           double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C) {
+  if (C && (d_out > 8 || !Y)) return fail(RCB_ERR_UNSUPPORTED, "fused cross term supports d_out <= 8");
+  const long long Te = T - washout, Stot = Te * nseq;
+  if (Stot <= 0) return RCB_OK;
+  const long long ldp = (F + 255) / 256 * 256;   // whole 256 x 256 super-tiles
+  std::vector<int2> tiles;
+  const int nt = (int)(ldp / 256);
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j) tiles.push_back(make_int2(i, j));
+  const int ntiles = (int)tiles.size();
+  void* d_tiles = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_TILES, tiles.size() * sizeof(int2) + 16, &d_tiles));
+  RCB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  int* d_err = reinterpret_cast<int*>((char*)d_tiles + tiles.size() * sizeof(int2));
+  RCB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  // sample sub-chunks: the digit planes (3 B per state) stay within 6 GiB
+  long long Ssub = ((long long)6 << 30) / (ldp * PLANES);
+  if (const char* ov = getenv("RCB_GRAM_SUB_SAMPLES")) Ssub = atoll(ov);  // testing hook: force several sub-chunks
+  Ssub = Ssub / SLAB * SLAB;
+  if (Ssub < SLAB) Ssub = SLAB;
+  if (Ssub > Stot) Ssub = Stot;
+  const long long Ssub_pad = (Ssub + SLAB - 1) / SLAB * SLAB;
+  RCB_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  void *q8 = nullptr, *aux = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_ZHI, (size_t)ldp * Ssub_pad * PLANES, &q8));
+  RCB_TRY(ctx_scratch(ctx, SCR_ZLO, (size_t)ldp * (sizeof(double) + sizeof(int)), &aux));
+  double* sf = reinterpret_cast<double*>(aux);
+  int* amax = reinterpret_cast<int*>(sf + ldp);
+  int ncl_max = 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ctx->sm_count / CLUSTER * CLUSTER)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RCB_CUDA(cudaOccupancyMaxActiveClusters(&ncl_max, gram_i8_kernel, &cfg));
+    if (ncl_max < 1) return fail(RCB_ERR_CUDA, "no %d-CTA cluster of the Gram kernel fits this device", CLUSTER);
+  }
+  static long long* prof_dev = nullptr;
+  const bool prof = getenv("RCB_GRAM_PROF") != nullptr;
+  if (prof && !prof_dev) cudaMalloc(&prof_dev, 148 * 5 * sizeof(long long));
+  for (long long s0 = 0; s0 < Stot; s0 += Ssub) {
+    const long long Sc = Stot - s0 < Ssub ? Stot - s0 : Ssub;
+    RCB_CUDA(cudaMemsetAsync(amax, 0, (size_t)ldp * sizeof(int), ctx->stream));
+    {
+      const bool vec = ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0;
+      const unsigned ny = (unsigned)((Sc + SLAB - 1) / SLAB);
+      if (vec) {
+        colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
+        const dim3 sgrid((unsigned)((ldp + 1023) / 1024), ny);
+        if (C && ydt == RCB_F64)
+          split_int8_kernel<double, 4><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
+                                                                      (const double*)Y, ldy, (int)d_out, C, ldo);
+        else
+          split_int8_kernel<float, 4><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
+                                                                     C ? (const float*)Y : nullptr, ldy, (int)d_out, C, ldo);
+      } else {
+        colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
+        const dim3 sgrid((unsigned)(ldp / 256), ny);
+        if (C && ydt == RCB_F64)
+          split_int8_kernel<double, 1><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
+                                                                      (const double*)Y, ldy, (int)d_out, C, ldo);
+        else
+          split_int8_kernel<float, 1><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
+                                                                     C ? (const float*)Y : nullptr, ldy, (int)d_out, C, ldo);
+      }
+      ctx->launches += 2;
+    }
+    GramParams8 p{};
+    p.tiles = (const int2*)d_tiles; p.ntiles = ntiles; p.q8 = (const unsigned char*)q8; p.sf = sf; p.nfb = ldp / 128;
+    p.S = Sc; p.G = G; p.ldo = ldo; p.F = F; p.err = d_err;
+    if (prof) cudaMemsetAsync(prof_dev, 0, 148 * 5 * sizeof(long long), ctx->stream);
+    p.prof = prof ? prof_dev : nullptr;
+    // K-ranges: at most MAX_RANGE samples (exact INT32 accumulation), and enough of them to fill the last round of clusters
+    long long splits = (Sc + MAX_RANGE - 1) / MAX_RANGE;
+    const long long max_splits = Sc / 2048 > splits ? Sc / 2048 : splits;
+    double best = -1.0;
+    long long best_c = splits;
+    for (long long c = splits; c <= max_splits && c < splits + 64; ++c) {
+      const long long items = (long long)ntiles * c, rounds = (items + ncl_max - 1) / ncl_max;
+      const double eff = (double)items / (double)(rounds * ncl_max);
+      if (eff > best + 1e-9) { best = eff; best_c = c; }
+      if (eff >= 0.97) break;
+    }
+    splits = best_c;
+    p.per_split = ((Sc + splits - 1) / splits + KB - 1) / KB * KB;
+    p.splits = (int)((Sc + p.per_split - 1) / p.per_split);
+    const long long nitems = (long long)ntiles * p.splits;
+    const int grid = (int)(nitems < ncl_max ? nitems : ncl_max) * CLUSTER;
+    const bool tsplit = getenv("RCB_GRAM_TIMING") != nullptr;  // diagnostics: time the MMA kernel alone in the SOLVE timer slot
+    if (tsplit) timer_begin(ctx, RCB_TIMER_SOLVE);
+    gram_i8_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p);
+    if (tsplit) timer_end(ctx, RCB_TIMER_SOLVE);
+    ctx->launches++;
+    RCB_CUDA(cudaGetLastError());
+    if (prof) {
+      static long long hp[148 * 5];
+      RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      RCB_CUDA(cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost));
+      double sum[5] = {0, 0, 0, 0, 0};
+      long long mx = 0;
+      for (int b = 0; b < grid; ++b) { for (int q = 0; q < 5; ++q) sum[q] += (double)hp[b * 5 + q]; if (hp[b * 5 + 4] > mx) mx = hp[b * 5 + 4]; }
+      fprintf(stderr, "[gram prof] grid %d items %lld x %lld samples: avg cycles/CTA: mma waits full %.3g, mma waits tmem %.3g, producer waits "
+              "empty %.3g, epilogue waits %.3g, producer total %.3g (max %lld)\n", grid, nitems, p.per_split, sum[0] / grid, sum[1] / grid,
+              sum[2] / grid, sum[3] / grid, sum[4] / grid, mx);
+    }
+  }
+  return RCB_OK;
+}
+
+}  // namespace rcb
