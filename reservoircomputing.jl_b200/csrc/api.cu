@@ -137,6 +137,9 @@ static void free_layer(Layer& L) {
   cudaFree(L.d_Win); cudaFree(L.d_bias); cudaFree(L.d_leak);
   cudaFree(L.fast.stream); cudaFree(L.fast.warp_off); cudaFree(L.fast.wwords);
   cudaFree(L.fast4.stream); cudaFree(L.fast4.warp_off); cudaFree(L.fast4.wwords); cudaFree(L.d_Win4);
+  cudaFree(L.fast4h.stream); cudaFree(L.fast4h.warp_off); cudaFree(L.fast4h.wwords); cudaFree(L.d_Win4h); cudaFree(L.d_permh);
+  L.fast4h = DevFast{};
+  L.d_Win4h = nullptr; L.d_permh = nullptr;
   L.fast = DevFast{};
   L.fast4 = DevFast{};
   L.d_Win4 = nullptr;
@@ -210,6 +213,28 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
       for (int p = 0; p < npos; ++p)
         for (int d = 0; d < 3; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
       RCB_TRY(upload(w4, &L.d_Win4));
+    }
+    const char* k1mode = getenv("RCB_K1_MODE");
+    if (hf4.ok && L.n == 8192 && esn_nthreads(esn) == 1024 && k1mode && !strcmp(k1mode, "fast7_512")) {  // experimental second schedule: 512 threads x 16 slabs
+      HostSell hs2;
+      HostFast hf2;
+      RCB_TRY(sell_from_csr_balanced(L.csr, 512, &hs2));
+      RCB_TRY(fast_from_csr(L.csr, hs2, &hf2, 4));
+      if (hf2.ok) {
+        const int np2 = hs2.R * hs2.nthreads;
+        std::vector<float> w4((size_t)np2 * 4, 0.f);
+        for (int p = 0; p < np2; ++p) {
+          const uint16_t r = hs2.perm[(size_t)p];
+          if (r != 0xFFFF)
+            for (int d = 0; d < 3; ++d) w4[(size_t)p * 4 + d] = W_in[(size_t)d * ldwin + r];
+        }
+        RCB_TRY(upload(hf2.stream, &L.fast4h.stream));
+        RCB_TRY(upload(hf2.warp_off, &L.fast4h.warp_off));
+        RCB_TRY(upload(hf2.wwords, &L.fast4h.wwords));
+        RCB_TRY(upload(w4, &L.d_Win4h));
+        RCB_TRY(upload(hs2.perm, &L.d_permh));
+        L.fast4h.ok = true;
+      }
     }
   }
   if (L.desc.use_bias) {

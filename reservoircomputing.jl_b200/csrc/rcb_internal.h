@@ -119,6 +119,9 @@ struct Layer {
   DevFast fast;
   DevFast fast4;              // same stream with column*4 (recurrence_fast7.cu)
   float* d_Win4 = nullptr;    // [npos] float4 (w_in[0..2], 0) by position, when d_in == 3
+  DevFast fast4h;             // the same for the 512-thread schedule (N = 8192: 16 slabs per thread)
+  float* d_Win4h = nullptr;
+  uint16_t* d_permh = nullptr;
   float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
   float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
   float* d_bias = nullptr;  // [n] by row

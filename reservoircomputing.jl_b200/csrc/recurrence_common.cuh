@@ -172,6 +172,7 @@ struct RecParams {
 // false when the fast path does not apply (the caller then uses the generic kernel).
 int32_t launch_collect_fast(rcb_ctx* ctx, const RecParams& p, const DevFast& f, bool* launched);
 // recurrence_fast7.cu: the kernel specialised for 7 sequences per CTA, N in {4096, 8192}, 3 inputs, tanh, none/NLAT2
-int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, bool* launched);
+int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, const DevFast& f4h,
+                             const float* Win4h, const uint16_t* permh, bool* launched);
 
 }  // namespace rcb

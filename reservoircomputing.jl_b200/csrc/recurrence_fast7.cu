@@ -28,6 +28,7 @@ struct Fast7Args {
   const uint32_t* warp_off;
   const uint64_t* wwords;
   const float4* Win4;           // [npos] (w_in[0], w_in[1], w_in[2], 0) by position
+  const uint16_t* perm;         // [npos] position -> row of the schedule this stream was built with
   float2 lc2, oml2, m2l2;       // (a, a), (1-a, 1-a), (-2a, -2a): packed operands straight from the constant bank
 };
 
@@ -75,7 +76,9 @@ __device__ __forceinline__ float2 sigm2(float2 x) {
                : "memory")
 
 constexpr int NB = 7;
-constexpr int NT = 1024;
+#ifndef RCB_F7_UREG
+#define RCB_F7_UREG 1   /* 1: the step's inputs live in registers; 0: re-read from shared memory in every slab epilogue */
+#endif
 constexpr uint32_t INVALID = 0xFFFFFFFFu;
 
 // Shared-memory image of the state tile: [N] records of three sequence pairs (24 B per neuron; 3 is invertible
@@ -105,11 +108,13 @@ __device__ __forceinline__ uint32_t ldg32u(const unsigned char* p) { return __ld
 __device__ __forceinline__ float ldg32f(const unsigned char* p) { return __ldg(reinterpret_cast<const float*>(p)); }
 __device__ __forceinline__ uint32_t ldg16u(const unsigned char* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
 
-// NPAD == N (multiple of 1024); MODK: 0 = states as they are, 2 = NLAT2.
-template <int NPAD, int MODK>
+// NPAD == N (multiple of 1024); MODK: 0 = states as they are, 2 = NLAT2; NT threads per CTA (512: 128 registers per
+// thread, 16 row slabs each; 1024: 64 registers, 8 slabs).
+template <int NPAD, int MODK, int NT>
 __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, const Fast7Args fa) {
   using TL = Tile<NPAD>;
   constexpr int R = NPAD / NT;
+  static_assert(R * 8 * (NT / 128) <= 512, "every warp parks its R slabs of 8 TMEM columns; 4 lane quadrants share 512 columns");
   extern __shared__ __align__(16) unsigned char smem[];
   unsigned char* tile = smem;
   float* u_s = reinterpret_cast<float*>(smem + TL::BYTES);  // [2][3][8]
@@ -145,11 +150,11 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tm_s;
-  const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64u;
+  const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * (uint32_t)(8 * R);
   // park (h0 of my rows | 4 * row index) in my TMEM lane: slab k -> columns 8k .. 8k+7
 #pragma unroll 1
   for (int k = 0; k < R; ++k) {
-    const unsigned r16 = __ldg(p.perm + k * NT + tid);
+    const unsigned r16 = __ldg(fa.perm + k * NT + tid);
     const uint32_t r = r16 != 0xFFFFu ? r16 : 0u;
     uint32_t o[8];
 #pragma unroll
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
   const unsigned char* wbase = fa.stream + fa.warp_off[warp];
-  const unsigned long long wword = fa.wwords[2 * warp];  // 8 bits per slab, R <= 8
+  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab, R <= 16
   float* out_g = reinterpret_cast<float*>(p.states);
   const size_t seq_stride = (size_t)p.T * NPAD;        // F == N for both modifiers handled here
   const bool even = (tid & 1) == 0;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
     float2 up[3][3];
     float us[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {  // (t == T reads a stale buffer; the values are not used)
+    for (int d = 0; RCB_F7_UREG && d < 3; ++d) {  // (t == T reads a stale buffer; the values are not used)
       const float4 x0 = *reinterpret_cast<const float4*>(ucur + d * 8), x1 = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
       up[d][0] = make_float2(x0.x, x0.y); up[d][1] = make_float2(x0.z, x0.w); up[d][2] = make_float2(x1.x, x1.y);
       us[d] = x1.z;
@@ -199,18 +204,21 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
         // feature chunk k of z = modifier(tile) -> HBM: one feature per lane (conflict-free tile reads, 128 B coalesced
         // streaming stores per sequence).  NLAT2 (states.jl:277-285, 0-based): even f >= 2 -> x[f-1] * x[f-2]; the parity
         // of f is the parity of tid.  Interleaved with the gathers so that the store queue drains behind them.
+        // Bank-conflict-free mapping: the FIRST load takes column f-2 on even lanes and column f on odd lanes — the 16
+        // columns of a half-warp are then distinct mod 16 (3 c mod 16 is a bijection of the 8-byte slots); the second,
+        // predicated load (even lanes, column f-1) touches 8 distinct odd columns.
         const bool two = MODK == 2 && even && (k > 0 || tid != 0);
-        const uint32_t fa_ = (uint32_t)(tid + NT * k) - (two ? 1u : 0u);
+        const uint32_t fa_ = (uint32_t)(tid + NT * k) - (two ? 2u : 0u);
         const unsigned char* pa = tile + 24u * fa_;
         float2 z0 = *reinterpret_cast<const float2*>(pa), z1 = *reinterpret_cast<const float2*>(pa + 8),
                z2 = *reinterpret_cast<const float2*>(pa + 16);
         float z3 = *reinterpret_cast<const float*>(tile + TL::SINGLE + 4u * fa_);
         if (two) {
-          const unsigned char* pb = pa - 24;
+          const unsigned char* pb = pa + 24;
           z0 = fmul2(z0, *reinterpret_cast<const float2*>(pb));
           z1 = fmul2(z1, *reinterpret_cast<const float2*>(pb + 8));
           z2 = fmul2(z2, *reinterpret_cast<const float2*>(pb + 16));
-          z3 *= *reinterpret_cast<const float*>(tile + TL::SINGLE + 4u * fa_ - 4);
+          z3 *= *reinterpret_cast<const float*>(tile + TL::SINGLE + 4u * fa_ + 4);
         }
         float* pj = po + NT * k;
         if (nvalid == NB) {
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
         }
       }
       if (!do_step) continue;
-      const int wd = (int)((wword >> (8 * k)) & 255ull);
+      const int wd = (int)(((R > 8 && k >= 8 ? wword1 : wword0) >> (8 * (k & 7))) & 255ull);
       const float2 wxy = __ldg(reinterpret_cast<const float2*>(fa.Win4 + k * NT + tid));
       const float wzz = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid) + 2);
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
@@ -254,6 +262,14 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       uint32_t o[8];
       TMEM_LD8(ta + (uint32_t)k * 8u, o);  // my old state of these rows + 4 * row index (waited on below)
       // + W_in * u (src/generics.jl:91-96)
+      if (!RCB_F7_UREG) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float4 x0 = *reinterpret_cast<const float4*>(ucur + d * 8), x1 = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
+          up[d][0] = make_float2(x0.x, x0.y); up[d][1] = make_float2(x0.z, x0.w); up[d][2] = make_float2(x1.x, x1.y);
+          us[d] = x1.z;
+        }
+      }
       {
         const float2 wx = make_float2(wxy.x, wxy.x), wy = make_float2(wxy.y, wxy.y), wz = make_float2(wzz, wzz);
         a0 = ffma2(wx, up[0][0], a0); a1 = ffma2(wx, up[0][1], a1); a2 = ffma2(wx, up[0][2], a2); a3 = fmaf(wxy.x, us[0], a3);
@@ -321,13 +337,13 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-template <int NPAD, int MODK>
+template <int NPAD, int MODK, int NT>
 int32_t launch_one(rcb_ctx* ctx, const RecParams& p, const Fast7Args& fa, int grid) {
-  auto kern = k1_fast7_kernel<NPAD, MODK>;
+  auto kern = k1_fast7_kernel<NPAD, MODK, NT>;
   const size_t smem = Tile<NPAD>::BYTES + 48 * sizeof(float) + 16;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, ctx->stream>>>(p, fa);
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", grid);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s,%dthr> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", NT, grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
@@ -336,11 +352,14 @@ int32_t launch_one(rcb_ctx* ctx, const RecParams& p, const Fast7Args& fa, int gr
 }  // namespace
 
 // Launches the specialised kernel when the call matches its shape; *launched stays false otherwise.
-int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, bool* launched) {
+// f4 / Win4 / perm: the stream built with the 1024-thread schedule; f4h / Win4h / permh: with the 512-thread schedule.
+int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, const DevFast& f4h,
+                             const float* Win4h, const uint16_t* permh, bool* launched) {
   *launched = false;
-  const char* mode = getenv("RCB_K1_MODE");  // testing hook: anything but "fast7" (or unset) skips this kernel
-  if (mode && strcmp(mode, "fast7")) return RCB_OK;
-  if (!f4.ok || !Win4 || p.pre_in || p.d_in != 3 || p.nthreads != NT) return RCB_OK;
+  const char* mode = getenv("RCB_K1_MODE");  // testing hook: fast7 | fast7_512 (or unset) use this kernel, anything else skips it
+  const bool want512 = mode && !strcmp(mode, "fast7_512");  // 512 threads x 128 registers: measured 10 % slower than 1024 x 64
+  if (mode && strcmp(mode, "fast7") && !want512) return RCB_OK;
+  if (!f4.ok || !Win4 || p.pre_in || p.d_in != 3 || p.nthreads != 1024) return RCB_OK;
   if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.bias || p.leakv || p.member_scale || p.member_leak) return RCB_OK;
   if (p.n != p.npad || (p.npad != 8192 && p.npad != 4096)) return RCB_OK;
   if (p.B <= (long long)(NB - 1) * ctx->sm_count) return RCB_OK;  // fewer sequences: smaller tiles fill the machine better
@@ -348,12 +367,15 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
   if ((modk != 0 && modk != RCB_MOD_NLAT2) || (!p.raw && p.mod.has_pad)) return RCB_OK;
   const int grid = (int)((p.B + NB - 1) / NB);
   const float lc = (float)p.leak, oml = 1.0f - lc, m2l = -2.0f * lc;  // (1-a) in the input eltype, esn_cell.jl:186-200
-  Fast7Args fa{f4.stream, f4.warp_off, f4.wwords, reinterpret_cast<const float4*>(Win4), make_float2(lc, lc), make_float2(oml, oml),
+  const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192;
+  Fast7Args fa{half ? f4h.stream : f4.stream, half ? f4h.warp_off : f4.warp_off, half ? f4h.wwords : f4.wwords,
+               reinterpret_cast<const float4*>(half ? Win4h : Win4), half ? permh : p.perm, make_float2(lc, lc), make_float2(oml, oml),
                make_float2(m2l, m2l)};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   int32_t st;
-  if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2>(ctx, p, fa, grid) : launch_one<8192, 0>(ctx, p, fa, grid);
-  else st = modk == 2 ? launch_one<4096, 2>(ctx, p, fa, grid) : launch_one<4096, 0>(ctx, p, fa, grid);
+  if (half) st = modk == 2 ? launch_one<8192, 2, 512>(ctx, p, fa, grid) : launch_one<8192, 0, 512>(ctx, p, fa, grid);
+  else if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024>(ctx, p, fa, grid) : launch_one<8192, 0, 1024>(ctx, p, fa, grid);
+  else st = modk == 2 ? launch_one<4096, 2, 1024>(ctx, p, fa, grid) : launch_one<4096, 0, 1024>(ctx, p, fa, grid);
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (st == RCB_OK) *launched = true;
   return st;

@@ -511,6 +511,18 @@ def test_fast7_kernel_parity(R, N, B, T, mod, leak):
         assert np.max(np.abs(st2.reservoir.carry[0][:, b] - hs[0])) <= STATE_RTOL * np.max(np.abs(hs[0]))
     again, _ = R.collectstates(esn, data, ps, stf)
     assert again.tobytes() == states.tobytes()
+    if N == 8192:  # the experimental 512-thread schedule of the same kernel (weights are re-installed under the env switch)
+        os.environ["RCB_K1_MODE"] = "fast7_512"
+        try:
+            esn2 = R.ESN(3, N, 3, init_reservoir=lambda rng, *d: ps.reservoir.reservoir_matrix,
+                         init_input=lambda rng, *d: ps.reservoir.input_matrix, state_modifiers=mods, leak_coefficient=leak)
+            ps2, st2b = R.setup(np.random.default_rng(0), esn2)
+            half, _ = R.collectstates(esn2, data, ps2, fixed_h0(R, st2b, esn2, [h0]))
+            assert "512thr" in R.default_device().last_kernel()
+        finally:
+            os.environ.pop("RCB_K1_MODE", None)
+        e5 = np.max(np.abs(states - half).reshape(N, -1), axis=0) / np.maximum(np.max(np.abs(states).reshape(N, -1), axis=0), 1e-30)
+        assert float(e5.max()) <= STATE_RTOL
     os.environ["RCB_K1_MODE"] = "v1"
     try:
         generic, _ = R.collectstates(esn, data, ps, stf)
