@@ -226,6 +226,16 @@ RCB_API int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targe
                           int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* GC,
                           void* hT_out);
 
+/* Ensemble / hyper-parameter sweep (BASELINE config 5): sequence b is member b (its own W scale and leak, see
+ * rcb_esn_set_member_params; its own input u[:, :, b] and targets) and gets its OWN readout — one per regularisation
+ * in `lambdas`: the recurrence and the Gram run once per member, the FP64 Cholesky once per (member, lambda).
+ *   W_out  d_out x F x n_lambda x B Float64 (member slowest).  Members are independent: shard them across GPUs with
+ *          no collective.  Same error conventions as rcb_train; a (member, lambda) system that is not
+ *          positive definite -> RCB_ERR_NUMERIC. */
+RCB_API int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                          int64_t washout, int32_t n_lambda, const double* lambdas, int32_t gram_mode, const void* h0,
+                          double* W_out, void* hT_out);
+
 /* ---- K4: predict --------------------------------------------------------------------------------
  * Teacher-forced: replaces __predict(reservoir, rc, data::AbstractMatrix, ps, st)
  * (src/predict.jl:163-177): y_t = readout(modifiers(cell(u_t))).  u: d_in x T x B.

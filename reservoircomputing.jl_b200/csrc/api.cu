@@ -896,6 +896,69 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
   return RCB_OK;
 }
 
+int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                          int64_t washout, int32_t n_lambda, const double* lambdas, int32_t gram_mode, const void* h0,
+                          double* W_out, void* hT_out) {
+  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  if (n_lambda < 1 || !lambdas || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument or n_lambda < 1");
+  for (int32_t i = 0; i < n_lambda; ++i)
+    if (!(lambdas[i] >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambdas[i]);
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
+  const int64_t F = esn->feat, d_out = esn->desc.out_dims, d_in = esn->desc.in_dims, sumN = esn->sumN;
+  const void* u_dev = nullptr;
+  const void* y_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)d_in * T * B * esz, &u_dev));
+  RCB_TRY(stage_in(ctx, SCR_TGT, targets, (size_t)d_out * T * B * ysz, &y_dev));
+  void* h_dev = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_H, (size_t)sumN * B * esz, &h_dev));
+  if (h0) RCB_TRY(to_device(ctx, h_dev, h0, (size_t)sumN * B * esz));
+  else RCB_CUDA(cudaMemsetAsync(h_dev, 0, (size_t)sumN * B * esz, ctx->stream));
+  // members per recurrence chunk: states of the chunk within a quarter of the free memory (<= 16 GiB)
+  size_t free_b = 0, total_b = 0;
+  RCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = std::min<size_t>(free_b / 4, (size_t)16 << 30);
+  const size_t per_member = (size_t)F * T * esz * (esn->layers.size() > 1 ? 3 : 1);
+  int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(budget / per_member)));
+  void* st_dev = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * T * Bc * esz, &st_dev));
+  const size_t gc_elems = (size_t)F * (F + d_out);
+  void *gc = nullptr, *work = nullptr, *w_dev = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_elems * sizeof(double), &gc));
+  RCB_TRY(ctx_scratch(ctx, SCR_W, gc_elems * sizeof(double), &work));
+  const size_t w_elems = (size_t)d_out * F;
+  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_elems * sizeof(double), &w_dev));
+  for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+    const int64_t nb = std::min<int64_t>(Bc, B - b0);
+    const void* uc = (const char*)u_dev + (size_t)b0 * T * d_in * esz;
+    void* hc = (char*)h_dev + (size_t)b0 * sumN * esz;
+    RCB_TRY(collect_device(esn, uc, T, nb, hc, st_dev, hc, b0));
+    for (int64_t b = 0; b < nb; ++b) {
+      const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
+      const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
+      RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
+      RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
+      for (int32_t l = 0; l < n_lambda; ++l) {
+        RCB_CUDA(cudaMemcpyAsync(work, gc, gc_elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        const int32_t st = launch_ridge_solve(ctx, (double*)work, F, d_out, lambdas[l], (double*)w_dev);
+        if (st != RCB_OK) {
+          if (st == RCB_ERR_NUMERIC) {
+            std::string msg = rcb_last_error();
+            return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: %s", (long long)(b0 + b), l, lambdas[l], msg.c_str());
+          }
+          return st;
+        }
+        RCB_TRY(from_device(ctx, W_out + ((size_t)(b0 + b) * n_lambda + l) * w_elems, w_dev, w_elems * sizeof(double)));
+      }
+    }
+  }
+  if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
 static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B, int32_t compute_dtype, bool autoreg,
                               void* h_inout, double* y_out) {
   RCB_TRY(check_ready(esn));

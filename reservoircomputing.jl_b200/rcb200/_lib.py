@@ -84,6 +84,7 @@ SIGNATURES = {
     "rcb_gram_accumulate": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I64, _I32, _I32, _P]),
     "rcb_ridge_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
     "rcb_train": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P, _P, _P, _P]),
+    "rcb_train_members": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),
     "rcb_train_partial": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "rcb_predict_teacher": (_I32, [_P, _P, _I64, _I64, _P, _P]),
     "rcb_predict_autoregressive": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),

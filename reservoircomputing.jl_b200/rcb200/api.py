@@ -766,6 +766,50 @@ def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegres
     return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
 
 
+def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambdas, washout: int = 0,
+                   device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+    """Hyper-parameter / ensemble sweep (BASELINE config 5): member b runs the SAME reservoir with W * w_scale[b] and leak
+    leak[b] on train_data[:, :, b] (pass (d_in, T) data to share it between all members) and gets one readout per
+    regularisation in `lambdas`.  Each member is exactly `train(ESN(... radius*w_scale[b], leak[b]), ...; RidgeRegression(λ))`
+    of the reference (src/train.jl:232-251); the recurrence and the Gram run once per member, the solve once per
+    (member, λ).  Returns W (B, n_lambda, d_out, F) Float64 and the final carries (N, B).  Members are independent: shard
+    them over ranks with shard_range — no collective."""
+    w_scale = np.ascontiguousarray(w_scale, dtype=np.float32)
+    leak = np.ascontiguousarray(leak, dtype=np.float32)
+    lambdas = np.ascontiguousarray(lambdas, dtype=np.float64)
+    B = w_scale.shape[0]
+    if leak.shape[0] != B:
+        raise DimensionMismatch(f"w_scale has {B} members, leak has {leak.shape[0]}")
+    d3, _ = _as3d(train_data)
+    y3, _ = _as3d(target_data)
+    if d3.shape[2] == 1 and B > 1:
+        d3 = np.asfortranarray(np.repeat(d3, B, axis=2))
+    if y3.shape[2] == 1 and B > 1:
+        y3 = np.asfortranarray(np.repeat(y3, B, axis=2))
+    if y3.dtype not in (np.float32, np.float64):
+        y3 = np.asfortranarray(y3.astype(np.float64))
+    _, T, Bd = d3.shape
+    if Bd != B or y3.shape[2] != B:
+        raise DimensionMismatch(f"{B} members but data has {Bd} and targets {y3.shape[2]} sequences")
+    if washout < 0:
+        raise ArgumentError(f"washout must be ≥ 0, got {washout}")
+    if washout >= T:
+        raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
+    if y3.shape[1] != T:
+        raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
+    h = _handle(rc, ps, d3.dtype, device)
+    h0, _ = _initial_carry(rc, st, d3.dtype, B)
+    W = np.empty((y3.shape[0], h.F, lambdas.shape[0], B), dtype=np.float64, order="F")
+    hT = np.empty((h.sumN, B), dtype=d3.dtype, order="F")
+    check(lib().rcb_esn_set_member_params(h.handle, B, ptr(w_scale), ptr(leak)))
+    try:
+        check(lib().rcb_train_members(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B, int(washout), int(lambdas.shape[0]),
+                                      ptr(lambdas), gram_mode, ptr(h0), ptr(W), ptr(hT)))
+    finally:
+        check(lib().rcb_esn_set_member_params(h.handle, 0, None, None))
+    return np.ascontiguousarray(W.transpose(3, 2, 0, 1)), hT
+
+
 def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Device] = None):
     """predict(rc, steps::Integer, ps, st; initialdata) — autoregressive (src/predict.jl:55-60,74-88);
     predict(rc, data::AbstractMatrix, ps, st) — teacher-forced (:90-103,163-177).

@@ -548,3 +548,34 @@ def test_train_sharded_single_rank_matches_train(R):
     # FP64 atomics make the Gram's summation order run-dependent (1e-16), the conditioning amplifies it
     assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) / np.linalg.norm(ps_a.readout.weight) <= 1e-5
     assert np.array_equal(st_a.reservoir.carry[0], st_b.reservoir.carry[0])
+
+
+# ---- C5: ensemble / hyper-parameter sweep (rcb_esn_set_member_params + rcb_train_members) -----------------------
+def test_ensemble_members_match_individual_esns(R):
+    """Member b == the reference's train() on an ESN with reservoir_matrix * w_scale[b] and leak[b], for every lambda."""
+    rng = np.random.default_rng(41)
+    N, T, w = 96, 260, 30
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=1.0, sparsity=6 / N), state_modifiers=R.NLAT2, leak_coefficient=1.0)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(series[:, :T].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:T + 1].astype(np.float32))
+    scales = np.array([0.5, 0.9, 1.2, 0.9, 0.7], np.float32)
+    leaks = np.array([1.0, 0.3, 0.6, 0.8, 0.45], np.float32)
+    lams = np.array([1e-6, 1e-3, 1e-1])
+    B = len(scales)
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    W, hT = R.train_ensemble(esn, data, target, ps, fixed_h0(R, st, esn, [h0]), w_scale=scales, leak=leaks, lambdas=lams, washout=w)
+    assert W.shape == (B, len(lams), 3, N)
+    for b in range(B):
+        layer = O.ESNCellParams(input_matrix=ps.reservoir.input_matrix,
+                                reservoir_matrix=(ps.reservoir.reservoir_matrix * scales[b]).astype(np.float32),
+                                leak=float(leaks[b]), act=O.ACT_TANH, modifiers=((O.MOD_NLAT2, 0.0),))
+        so, hs = O.collectstates([layer], data, [h0[:, b]])
+        assert np.max(np.abs(hT[:, b] - hs[0])) <= 2e-5 * np.max(np.abs(hs[0]))
+        for l, lam in enumerate(lams):
+            Wo = O.train_ridge_qr(so[:, w:], target[:, w:], lam)
+            pred, pred_o = W[b, l] @ so[:, w:].astype(np.float64), Wo @ so[:, w:].astype(np.float64)
+            assert np.linalg.norm(pred - pred_o) / np.linalg.norm(pred_o) <= WEIGHT_RTOL
+            if lam >= 1e-3:
+                assert np.linalg.norm(W[b, l] - Wo) / np.linalg.norm(Wo) <= 2e-3
