@@ -9,4 +9,4 @@ from .api import (NT, Device, DeepESN, ESN, ESNCell, ExtendedSquare, LinearReado
                   apply_modifiers, collectstates, csr_from_matrix, default_device, device_count, export_csr, fit_readout, gram,
                   ridge_solve, identity,
                   predict, rand32, rand_sparse, randn32, relu, resetcarry, scaled_rand, setup, sigmoid, tanh,
-                  tanh_fast, train, train_ensemble, train_sharded, shard_range, time_chunks, zeros32)
+                  tanh_fast, train, train_ensemble, train_sharded, train_time_chunked, chunk_windows, shard_range, time_chunks, zeros32)

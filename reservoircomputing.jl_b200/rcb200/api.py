@@ -766,6 +766,83 @@ def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegres
     return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
 
 
+def chunk_windows(T: int, washout: int, n_chunks: int, overlap: int):
+    """BASELINE config 2: cut the samples [washout, T) of ONE long sequence into n_chunks equal chunks (+ a ragged tail).
+    Chunk c owns [lo, hi) and is computed from a window that starts `overlap` steps earlier from a zero state; those
+    steps are its local washout (the echo-state property re-synchronises the state).  Needs overlap <= washout so that
+    every window has the same length.  Returns (Tc, [(start, lo, hi), ...], tail or None)."""
+    if not 0 <= overlap <= washout:
+        raise ArgumentError(f"time chunking needs 0 ≤ overlap ≤ washout, got overlap={overlap}, washout={washout}")
+    n = T - washout
+    if n_chunks < 1 or n < n_chunks:
+        raise ArgumentError(f"cannot cut {n} samples into {n_chunks} chunks")
+    Tc = n // n_chunks
+    wins = [(washout + c * Tc - overlap, washout + c * Tc, washout + (c + 1) * Tc) for c in range(n_chunks)]
+    rem = n - Tc * n_chunks
+    tail = (T - rem - overlap, T - rem, T) if rem else None
+    return Tc, wins, tail
+
+
+def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, washout: int, n_chunks: int,
+                       overlap: int, group=None, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+    """train() for one long sequence (d_in, T), time-chunked after the washout: the chunks
+    become a BATCH for the batched recurrence kernel, ranks take contiguous slices of the chunk list, and the partial
+    [G | C] are summed by one all-reduce before the replicated FP64 solve.  This is an approximation of the sequential
+    semantics (exact only in the limit of a long overlap); the sequential single-GPU `train` stays the parity reference.
+    The carry stored in the returned st is the state at the end of the last chunk."""
+    import torch
+    import torch.distributed as dist
+
+    objective = objective or RidgeRegression(0.0)
+    X, Y = np.asarray(train_data), np.asarray(target_data)
+    if X.ndim != 2 or Y.ndim != 2:
+        raise DimensionMismatch("train_time_chunked takes one sequence: data (d_in, T), targets (d_out, T)")
+    T = X.shape[1]
+    if Y.shape[1] != T:
+        raise DimensionMismatch(f"states has {T - washout} samples, targets has {Y.shape[1] - washout}")
+    if washout >= T:
+        raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
+    if Y.dtype not in (np.float32, np.float64):
+        Y = Y.astype(np.float64)
+    Tc, wins, tail = chunk_windows(T, washout, n_chunks, overlap)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_range(n_chunks, rank, world)
+    h = _handle(rc, ps, X.dtype, device)
+    F, d_out = h.F, Y.shape[0]
+    GC = np.zeros((F, F + d_out), dtype=np.float64, order="F")
+    hT = None
+
+    def run(windows, length):
+        nonlocal hT
+        B = len(windows)
+        d3 = np.asfortranarray(np.stack([X[:, s:s + length] for s, _, _ in windows], axis=2))
+        y3 = np.asfortranarray(np.stack([Y[:, s:s + length] for s, _, _ in windows], axis=2))
+        h0 = np.zeros((h.sumN, B), dtype=X.dtype, order="F")
+        part = np.empty_like(GC)
+        hh = np.empty((h.sumN, B), dtype=X.dtype, order="F")
+        check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), length, B, int(overlap), gram_mode, ptr(h0),
+                                      ptr(part), ptr(hh)))
+        GC[...] += part
+        hT = hh[:, -1:]
+
+    if hi > lo:
+        run(wins[lo:hi], Tc + overlap)
+    if tail is not None and rank == world - 1:
+        run([tail], tail[2] - tail[0])
+    if world > 1:
+        t = torch.from_numpy(np.ascontiguousarray(GC.T))
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        GC = np.asfortranarray(t.cpu().numpy().T)
+    W = ridge_solve(GC, d_out, float(objective.reg), device).astype(_promote(objective, X, Y))
+    cell_sts = list(_cell_st(rc, st))
+    if hT is None:
+        hT = np.zeros((h.sumN, 1), dtype=X.dtype)
+    return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, np.asfortranarray(hT), True))
+
+
 def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambdas, washout: int = 0,
                    device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
     """Hyper-parameter / ensemble sweep (BASELINE config 5): member b runs the SAME reservoir with W * w_scale[b] and leak

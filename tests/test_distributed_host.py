@@ -98,6 +98,24 @@ def test_shard_range_and_time_chunks():
     assert own[0][0] == wo and own[-1][1] == T and all(own[i][1] == own[i + 1][0] for i in range(7))
 
 
+def test_chunk_windows_cover_the_samples_once():
+    import rcb200 as R
+
+    for T, w, n, ov in [(1_000_000, 1000, 1024, 500), (6000, 300, 7, 250), (100, 10, 9, 10)]:
+        Tc, wins, tail = R.chunk_windows(T, w, n, ov)
+        assert len(wins) == n and all(hi - lo == Tc and lo - s == ov and s >= 0 for s, lo, hi in wins)
+        assert wins[0][1] == w and all(a[2] == b[1] for a, b in zip(wins, wins[1:]))
+        end = wins[-1][2]
+        if tail is not None:
+            assert tail[1] == end and tail[2] == T and tail[1] - tail[0] == ov
+            end = tail[2]
+        assert end == T
+    with pytest.raises(R.ArgumentError):
+        R.chunk_windows(1000, 10, 4, 50)      # overlap > washout: windows would start before t = 0
+    with pytest.raises(R.ArgumentError):
+        R.chunk_windows(20, 10, 11, 5)
+
+
 def test_train_sharded_two_ranks_gloo():
     import torch.multiprocessing as mp
 

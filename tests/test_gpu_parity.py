@@ -579,3 +579,26 @@ def test_ensemble_members_match_individual_esns(R):
             assert np.linalg.norm(pred - pred_o) / np.linalg.norm(pred_o) <= WEIGHT_RTOL
             if lam >= 1e-3:
                 assert np.linalg.norm(W[b, l] - Wo) / np.linalg.norm(Wo) <= 2e-3
+
+
+# ---- C2: one long sequence, time-chunked after the washout (an approximation: echo-state re-synchronisation) ----
+def test_time_chunked_train_approaches_sequential(R):
+    rng = np.random.default_rng(5)
+    N, T, w = 200, 6000, 300
+    esn = R.ESN(1, N, 1, init_reservoir=R.rand_sparse(radius=0.6, sparsity=6 / N), leak_coefficient=1.0)
+    ps, st = R.setup(rng, esn)
+    mg = O.mackey_glass_series(T + 1)
+    data = np.asfortranarray(mg[:, :T].astype(np.float32))
+    target = np.asfortranarray(mg[:, 1:T + 1].astype(np.float32))
+    st0 = fixed_h0(R, st, esn, [np.zeros(N, np.float32)])
+    ps_seq, _ = R.train(esn, data, target, ps, st0, objective=R.RidgeRegression(1e-4), washout=w)
+    ps_chk, st_chk = R.train_time_chunked(esn, data, target, ps, st0, objective=R.RidgeRegression(1e-4), washout=w, n_chunks=7, overlap=250)
+    Ws, Wc = ps_seq.readout.weight, ps_chk.readout.weight
+    states, _ = R.collectstates(esn, data, ps, st0)
+    ys, yc = Ws @ states[:, w:].astype(np.float64), Wc @ states[:, w:].astype(np.float64)
+    assert np.linalg.norm(ys - yc) / np.linalg.norm(ys) <= 1e-4      # radius 0.6: 0.6^250 is far below FP32 resolution
+    assert st_chk.reservoir.carry[0].shape == (N,)
+    Tc, wins, tail = R.chunk_windows(T, w, 7, 250)
+    assert wins[0][1] == w and (tail[2] if tail else wins[-1][2]) == T and all(a[2] == b[1] for a, b in zip(wins, wins[1:]))
+    with pytest.raises(R.ArgumentError):
+        R.chunk_windows(T, 100, 4, 250)
