@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   const size_t seq_stride = (size_t)p.T * NPAD;        // F == N for both modifiers handled here
   const bool even = (tid & 1) == 0;
 
+  float4 vpre = ldg128(wbase + lane * 16);   // first quad of the first slab (a warp whose slab is narrower ignores it)
+  uint2 cpre = ldg64u(wbase + 512 + lane * 8);
   const int T = (int)p.T;
   // Iteration t computes x_{t+1} from the tile (= x_t) and, interleaved, streams out z_t = modifier(x_t), i.e. the
   // collected state of time index t-1 (states[:, t] = modifier(h after consuming u_t), reservoircomputer.jl:127-130).
@@ -237,7 +239,16 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       const float wzz = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid) + 2);
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
       float a3 = 0.f;
-      for (int q = 0; q < (wd >> 2); ++q) {
+      if (wd >= 4) {  // first quad: prefetched into registers during the previous slab's epilogue (hides the L2 round trip)
+        const float4 v = vpre;
+        const uint2 c = cpre;
+        wp += 768;
+        gather7<NPAD>(a0, a1, a2, a3, tile, v.x, c.x & 0xFFFFu);
+        gather7<NPAD>(a0, a1, a2, a3, tile, v.y, c.x >> 16);
+        gather7<NPAD>(a0, a1, a2, a3, tile, v.z, c.y & 0xFFFFu);
+        gather7<NPAD>(a0, a1, a2, a3, tile, v.w, c.y >> 16);
+      }
+      for (int q = 1; q < (wd >> 2); ++q) {
         const float4 v = ldg128(wp + lane * 16);
         const uint2 c = ldg64u(wp + 512 + lane * 8);
         wp += 768;
@@ -258,6 +269,11 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
         const uint32_t c = ldg16u(wp + 128 + lane * 2);
         wp += 192;
         gather7<NPAD>(a0, a1, a2, a3, tile, v, c);
+      }
+      {  // the next slab's stream starts at wp (the first slab of the next step at wbase): fetch its first quad now
+        const unsigned char* wn = k + 1 < R ? wp : wbase;
+        vpre = ldg128(wn + lane * 16);
+        cpre = ldg64u(wn + 512 + lane * 8);
       }
       uint32_t o[8];
       TMEM_LD8(ta + (uint32_t)k * 8u, o);  // my old state of these rows + 4 * row index (waited on below)

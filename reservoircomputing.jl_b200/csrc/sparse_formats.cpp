@@ -379,7 +379,7 @@ int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out, i
     }
   }
   if (total > 0xFFFFFFF0ull) return RCB_OK;
-  out->stream.assign(total + 16, 0);
+  out->stream.assign(total + 1024, 0);  // slack: recurrence_fast7.cu prefetches one quad (768 B) past a narrow slab
   for (int32_t w = 0; w < sell.nwarps; ++w) {
     unsigned char* p = out->stream.data() + out->warp_off[(size_t)w];
     for (int32_t k = 0; k < sell.R; ++k) {
