@@ -333,7 +333,7 @@ __device__ __forceinline__ void digits(float x, float qs, int& a1, int& a2, int&
 // as the MMA's shared-memory image, and accumulate the cross term C = Z Y' (d_out <= 8) in FP64 on the way.
 // One thread = VEC consecutive features over a slab of samples: with VEC = 4 a warp reads 512 contiguous bytes per sample
 // and writes one full 128-byte row of each digit plane (32-bit stores, full sectors).
-template <typename TY, int VEC>
+template <typename TY, int VEC, int DMAX>
 __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict__ Z, long long ldz, long long F, long long ldp,
                                                          long long T, long long washout, long long Te, long long s0,
                                                          long long Sc, const int* __restrict__ amax, unsigned char* __restrict__ q8,
@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
     qs[v] = ldexpf(1.0f, 22 - e);                      // |z| qs < 2^22
     if (blockIdx.y == 0) sf[f + v] = live[v] ? ldexp(1.0, e - 14) : 0.0;
   }
-  double acc[VEC][8];
+  double acc[VEC][DMAX];
 #pragma unroll
   for (int v = 0; v < VEC; ++v)
 #pragma unroll
-    for (int d = 0; d < 8; ++d) acc[v][d] = 0.0;
+    for (int d = 0; d < DMAX; ++d) acc[v][d] = 0.0;
   const long long nfb = ldp / 128, fbk = f >> 7;
   const int c = (int)(f & 127);
-#pragma unroll 2
+#pragma unroll 4
   for (long long sl = sl0; sl < sl1; ++sl) {
     int a1[VEC], a2[VEC], a3[VEC];
 #pragma unroll
@@ -383,10 +383,10 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
       } else {
         x[0] = live[0] ? __ldcs(Z + (size_t)col * ldz + f) : 0.f;
       }
-      double y[8];
+      double y[DMAX];
       if (C) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d) y[d] = d < d_out ? (double)__ldg(Y + (size_t)col * ldy + d) : 0.0;
+        for (int d = 0; d < DMAX; ++d) y[d] = d < d_out ? (double)__ldg(Y + (size_t)col * ldy + d) : 0.0;
       }
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
           digits(x[v], qs[v], a1[v], a2[v], a3[v]);
           if (C) {
 #pragma unroll
-            for (int d = 0; d < 8; ++d)
+            for (int d = 0; d < DMAX; ++d)
               if (d < d_out) acc[v][d] = fma((double)x[v], y[d], acc[v][d]);
           }
         }
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
     for (int v = 0; v < VEC; ++v)
       if (live[v]) {
 #pragma unroll
-        for (int d = 0; d < 8; ++d)
+        for (int d = 0; d < DMAX; ++d)
           if (d < d_out) atomicAdd(C + (size_t)d * ldc + f + v, acc[v][d]);
       }
   }
@@ -476,25 +476,21 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
     {
       const bool vec = ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0;
       const unsigned ny = (unsigned)((Sc + SLAB - 1) / SLAB);
+      const bool y64 = C && ydt == RCB_F64, small = d_out <= 4;
+#define RCB_SPLIT(TY, V, D, G)                                                                                                   \
+  split_int8_kernel<TY, V, D><<<G, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,   \
+                                                          (const TY*)(C ? Y : nullptr), ldy, (int)d_out, C, ldo)
       if (vec) {
         colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
         const dim3 sgrid((unsigned)((ldp + 1023) / 1024), ny);
-        if (C && ydt == RCB_F64)
-          split_int8_kernel<double, 4><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
-                                                                      (const double*)Y, ldy, (int)d_out, C, ldo);
-        else
-          split_int8_kernel<float, 4><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
-                                                                     C ? (const float*)Y : nullptr, ldy, (int)d_out, C, ldo);
+        if (y64) { if (small) RCB_SPLIT(double, 4, 4, sgrid); else RCB_SPLIT(double, 4, 8, sgrid); }
+        else { if (small) RCB_SPLIT(float, 4, 4, sgrid); else RCB_SPLIT(float, 4, 8, sgrid); }
       } else {
         colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
         const dim3 sgrid((unsigned)(ldp / 256), ny);
-        if (C && ydt == RCB_F64)
-          split_int8_kernel<double, 1><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
-                                                                      (const double*)Y, ldy, (int)d_out, C, ldo);
-        else
-          split_int8_kernel<float, 1><<<sgrid, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,
-                                                                     C ? (const float*)Y : nullptr, ldy, (int)d_out, C, ldo);
+        if (y64) RCB_SPLIT(double, 1, 8, sgrid); else RCB_SPLIT(float, 1, 8, sgrid);
       }
+#undef RCB_SPLIT
       ctx->launches += 2;
     }
     GramParams8 p{};
