@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
     if (tid < 3 * NB && t + 1 < T) {  // the other buffer was consumed (into registers) before the barriers of step t-1
       const int ud = tid / NB, ub = tid % NB;
       const long long useq = ub < nvalid ? seq0 + ub : p.B - 1;
-      u_s[((t + 1) & 1) * 24 + ud * 8 + ub] = __ldg(u_g + ((size_t)useq * p.T + (t + 1)) * 3 + ud);
+      // asynchronous 4-byte copy global -> shared: no register, no stall on the load; waited for before this step's barrier
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(u_s + ((t + 1) & 1) * 24 + ud * 8 + ub);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(u_g + ((size_t)useq * p.T + (t + 1)) * 3 + ud) : "memory");
     }
     const unsigned char* wp = wbase;
 #pragma unroll 1
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       TMEM_ST8(ta + (uint32_t)k * 8u, o);
     }
     if (!do_step) break;  // t == T: the last state has been streamed out
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     __syncthreads();  // every gather (and tile read of the output) of this iteration is done: the tile may be overwritten
 #pragma unroll 1
