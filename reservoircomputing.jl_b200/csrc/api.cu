@@ -201,7 +201,7 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
       }
     }
   RCB_TRY(upload(winp, &L.d_Win));
-  if (L.d_in == 3) {
+  if (L.d_in == 3 || L.d_in == 1) {
     HostFast hf4;
     RCB_TRY(fast_from_csr(L.csr, hs, &hf4, 4));
     if (hf4.ok) {
@@ -211,11 +211,11 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
       L.fast4.ok = true;
       std::vector<float> w4((size_t)npos * 4, 0.f);
       for (int p = 0; p < npos; ++p)
-        for (int d = 0; d < 3; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
+        for (int d = 0; d < L.d_in; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
       RCB_TRY(upload(w4, &L.d_Win4));
     }
     const char* k1mode = getenv("RCB_K1_MODE");
-    if (hf4.ok && L.n == 8192 && esn_nthreads(esn) == 1024 && k1mode && !strcmp(k1mode, "fast7_512")) {  // experimental second schedule: 512 threads x 16 slabs
+    if (hf4.ok && L.d_in == 3 && L.n == 8192 && esn_nthreads(esn) == 1024 && k1mode && !strcmp(k1mode, "fast7_512")) {  // experimental second schedule: 512 threads x 16 slabs
       HostSell hs2;
       HostFast hf2;
       RCB_TRY(sell_from_csr_balanced(L.csr, 512, &hs2));

@@ -109,8 +109,8 @@ __device__ __forceinline__ float ldg32f(const unsigned char* p) { return __ldg(r
 __device__ __forceinline__ uint32_t ldg16u(const unsigned char* p) { return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
 
 // NPAD == N (multiple of 1024); MODK: 0 = states as they are, 2 = NLAT2; NT threads per CTA (512: 128 registers per
-// thread, 16 row slabs each; 1024: 64 registers, 8 slabs).
-template <int NPAD, int MODK, int NT>
+// thread, 16 row slabs each; 1024: 64 registers, 8 slabs); DIN = input rows (3: Lorenz-shaped, 1: Mackey-Glass-shaped).
+template <int NPAD, int MODK, int NT, int DIN>
 __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, const Fast7Args fa) {
   using TL = Tile<NPAD>;
   constexpr int R = NPAD / NT;
@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   if (tid < 48) u_s[tid] = 0.0f;
   __syncthreads();
   // inputs: thread tid < 21 owns (input row ud, sequence ub) and keeps the two-deep u_s ring one step ahead
-  if (tid < 3 * NB) {
+  if (tid < DIN * NB) {
     const int ud = tid / NB, ub = tid % NB;
     const long long useq = ub < nvalid ? seq0 + ub : p.B - 1;
-    u_s[ud * 8 + ub] = u_g[((size_t)useq * p.T + 0) * 3 + ud];
+    u_s[ud * 8 + ub] = u_g[((size_t)useq * p.T + 0) * DIN + ud];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -186,20 +186,20 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
     float* po = out_g + ((size_t)seq0 * p.T + (t - 1)) * NPAD + tid;
     // inputs of this step -> registers (broadcast loads, once per step)
     const float* ucur = u_s + (t & 1) * 24;
-    float2 up[3][3];
-    float us[3];
+    float2 up[DIN][3];
+    float us[DIN];
 #pragma unroll
-    for (int d = 0; RCB_F7_UREG && d < 3; ++d) {  // (t == T reads a stale buffer; the values are not used)
+    for (int d = 0; RCB_F7_UREG && d < DIN; ++d) {  // (t == T reads a stale buffer; the values are not used)
       const float4 x0 = *reinterpret_cast<const float4*>(ucur + d * 8), x1 = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
       up[d][0] = make_float2(x0.x, x0.y); up[d][1] = make_float2(x0.z, x0.w); up[d][2] = make_float2(x1.x, x1.y);
       us[d] = x1.z;
     }
-    if (tid < 3 * NB && t + 1 < T) {  // the other buffer was consumed (into registers) before the barriers of step t-1
+    if (tid < DIN * NB && t + 1 < T) {  // the other buffer was consumed (into registers) before the barriers of step t-1
       const int ud = tid / NB, ub = tid % NB;
       const long long useq = ub < nvalid ? seq0 + ub : p.B - 1;
       // asynchronous 4-byte copy global -> shared: no register, no stall on the load; waited for before this step's barrier
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(u_s + ((t + 1) & 1) * 24 + ud * 8 + ub);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(u_g + ((size_t)useq * p.T + (t + 1)) * 3 + ud) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(u_g + ((size_t)useq * p.T + (t + 1)) * DIN + ud) : "memory");
     }
     const unsigned char* wp = wbase;
 #pragma unroll 1
@@ -237,8 +237,14 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       }
       if (!do_step) continue;
       const int wd = (int)(((R > 8 && k >= 8 ? wword1 : wword0) >> (8 * (k & 7))) & 255ull);
-      const float2 wxy = __ldg(reinterpret_cast<const float2*>(fa.Win4 + k * NT + tid));
-      const float wzz = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid) + 2);
+      float2 wxy = make_float2(0.f, 0.f);
+      float wzz = 0.f;
+      if constexpr (DIN == 3) {
+        wxy = __ldg(reinterpret_cast<const float2*>(fa.Win4 + k * NT + tid));
+        wzz = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid) + 2);
+      } else {
+        wxy.x = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid));
+      }
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
       float a3 = 0.f;
       if (wd >= 4) {  // first quad: prefetched into registers during the previous slab's epilogue (hides the L2 round trip)
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       // + W_in * u (src/generics.jl:91-96)
       if (!RCB_F7_UREG) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
+        for (int d = 0; d < DIN; ++d) {
           const float4 x0 = *reinterpret_cast<const float4*>(ucur + d * 8), x1 = *reinterpret_cast<const float4*>(ucur + d * 8 + 4);
           up[d][0] = make_float2(x0.x, x0.y); up[d][1] = make_float2(x0.z, x0.w); up[d][2] = make_float2(x1.x, x1.y);
           us[d] = x1.z;
@@ -291,8 +297,10 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       {
         const float2 wx = make_float2(wxy.x, wxy.x), wy = make_float2(wxy.y, wxy.y), wz = make_float2(wzz, wzz);
         a0 = ffma2(wx, up[0][0], a0); a1 = ffma2(wx, up[0][1], a1); a2 = ffma2(wx, up[0][2], a2); a3 = fmaf(wxy.x, us[0], a3);
-        a0 = ffma2(wy, up[1][0], a0); a1 = ffma2(wy, up[1][1], a1); a2 = ffma2(wy, up[1][2], a2); a3 = fmaf(wxy.y, us[1], a3);
-        a0 = ffma2(wz, up[2][0], a0); a1 = ffma2(wz, up[2][1], a1); a2 = ffma2(wz, up[2][2], a2); a3 = fmaf(wzz, us[2], a3);
+        if constexpr (DIN == 3) {
+          a0 = ffma2(wy, up[1][0], a0); a1 = ffma2(wy, up[1][1], a1); a2 = ffma2(wy, up[1][2], a2); a3 = fmaf(wxy.y, us[1], a3);
+          a0 = ffma2(wz, up[2][0], a0); a1 = ffma2(wz, up[2][1], a1); a2 = ffma2(wz, up[2][2], a2); a3 = fmaf(wzz, us[2], a3);
+        }
       }
       const float2 r0 = sigm2(a0), r1 = sigm2(a1), r2 = sigm2(a2);
       const float r3 = rcp_approx(ex2_approx(a3 * 2.8853900817779268f) + 1.0f);
@@ -356,13 +364,13 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-template <int NPAD, int MODK, int NT>
+template <int NPAD, int MODK, int NT, int DIN>
 int32_t launch_one(rcb_ctx* ctx, const RecParams& p, const Fast7Args& fa, int grid) {
-  auto kern = k1_fast7_kernel<NPAD, MODK, NT>;
+  auto kern = k1_fast7_kernel<NPAD, MODK, NT, DIN>;
   const size_t smem = Tile<NPAD>::BYTES + 48 * sizeof(float) + 16;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, ctx->stream>>>(p, fa);
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s,%dthr> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", NT, grid);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s,%dthr,din=%d> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", NT, DIN, grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
@@ -378,7 +386,7 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
   const char* mode = getenv("RCB_K1_MODE");  // testing hook: fast7 | fast7_512 (or unset) use this kernel, anything else skips it
   const bool want512 = mode && !strcmp(mode, "fast7_512");  // 512 threads x 128 registers: measured 10 % slower than 1024 x 64
   if (mode && strcmp(mode, "fast7") && !want512) return RCB_OK;
-  if (!f4.ok || !Win4 || p.pre_in || p.d_in != 3 || p.nthreads != 1024) return RCB_OK;
+  if (!f4.ok || !Win4 || p.pre_in || (p.d_in != 3 && p.d_in != 1) || p.nthreads != 1024) return RCB_OK;
   if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.bias || p.leakv || p.member_scale || p.member_leak) return RCB_OK;
   if (p.n != p.npad || (p.npad != 8192 && p.npad != 4096)) return RCB_OK;
   if (p.B <= (long long)(NB - 1) * ctx->sm_count) return RCB_OK;  // fewer sequences: smaller tiles fill the machine better
@@ -386,15 +394,20 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
   if ((modk != 0 && modk != RCB_MOD_NLAT2) || (!p.raw && p.mod.has_pad)) return RCB_OK;
   const int grid = (int)((p.B + NB - 1) / NB);
   const float lc = (float)p.leak, oml = 1.0f - lc, m2l = -2.0f * lc;  // (1-a) in the input eltype, esn_cell.jl:186-200
-  const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192;
+  const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192 && p.d_in == 3;
   Fast7Args fa{half ? f4h.stream : f4.stream, half ? f4h.warp_off : f4.warp_off, half ? f4h.wwords : f4.wwords,
                reinterpret_cast<const float4*>(half ? Win4h : Win4), half ? permh : p.perm, make_float2(lc, lc), make_float2(oml, oml),
                make_float2(m2l, m2l)};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   int32_t st;
-  if (half) st = modk == 2 ? launch_one<8192, 2, 512>(ctx, p, fa, grid) : launch_one<8192, 0, 512>(ctx, p, fa, grid);
-  else if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024>(ctx, p, fa, grid) : launch_one<8192, 0, 1024>(ctx, p, fa, grid);
-  else st = modk == 2 ? launch_one<4096, 2, 1024>(ctx, p, fa, grid) : launch_one<4096, 0, 1024>(ctx, p, fa, grid);
+  if (p.d_in == 3) {
+    if (half) st = modk == 2 ? launch_one<8192, 2, 512, 3>(ctx, p, fa, grid) : launch_one<8192, 0, 512, 3>(ctx, p, fa, grid);
+    else if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024, 3>(ctx, p, fa, grid) : launch_one<8192, 0, 1024, 3>(ctx, p, fa, grid);
+    else st = modk == 2 ? launch_one<4096, 2, 1024, 3>(ctx, p, fa, grid) : launch_one<4096, 0, 1024, 3>(ctx, p, fa, grid);
+  } else {  // one input row (Mackey-Glass-shaped, BASELINE config 2 time-chunked)
+    if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024, 1>(ctx, p, fa, grid) : launch_one<8192, 0, 1024, 1>(ctx, p, fa, grid);
+    else st = modk == 2 ? launch_one<4096, 2, 1024, 1>(ctx, p, fa, grid) : launch_one<4096, 0, 1024, 1>(ctx, p, fa, grid);
+  }
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (st == RCB_OK) *launched = true;
   return st;
