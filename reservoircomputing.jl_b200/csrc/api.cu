@@ -185,6 +185,7 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   RCB_TRY(fast_from_csr(L.csr, hs, &hf));
   if (hf.ok) {
     RCB_TRY(upload(hf.stream, &L.fast.stream));
+    L.fast.stream_bytes = hf.stream.size();
     RCB_TRY(upload(hf.warp_off, &L.fast.warp_off));
     RCB_TRY(upload(hf.wwords, &L.fast.wwords));
     L.fast.ok = true;

@@ -92,6 +92,7 @@ struct HostFast {
 };
 struct DevFast {
   bool ok = false;
+  size_t stream_bytes = 0;    // bytes of `stream` (incl. the read-ahead slack)
   unsigned char* stream = nullptr;
   uint32_t* warp_off = nullptr;
   uint64_t* wwords = nullptr;

@@ -37,6 +37,9 @@ struct FastArgs {
   const unsigned char* stream;
   const uint32_t* warp_off;
   const uint64_t* wwords;
+  uint32_t stream_bytes;   // WS kernels: bytes of the W stream staged into shared memory (multiple of 16)
+  uint32_t stage_perm;     // WS kernels: also stage the row permutation (2 B per position)
+  uint32_t stage_win;      // WS kernels: also stage W_in (4 B x d_in per position)
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -95,6 +98,13 @@ __device__ __forceinline__ float2 fast_tanh2(float2 x) {
   return make_float2(copysignf(t.x, x.x), copysignf(t.y, x.y));
 }
 
+// W-stream loads: WS = false -> read-only global path; WS = true -> the stream was staged into shared memory (generic loads)
+template <bool WS> __device__ __forceinline__ float4 ldw128(const unsigned char* p) { if constexpr (WS) return *reinterpret_cast<const float4*>(p); else return __ldg(reinterpret_cast<const float4*>(p)); }
+template <bool WS> __device__ __forceinline__ uint2 ldw64u(const unsigned char* p) { if constexpr (WS) return *reinterpret_cast<const uint2*>(p); else return __ldg(reinterpret_cast<const uint2*>(p)); }
+template <bool WS> __device__ __forceinline__ float2 ldw64f(const unsigned char* p) { if constexpr (WS) return *reinterpret_cast<const float2*>(p); else return __ldg(reinterpret_cast<const float2*>(p)); }
+template <bool WS> __device__ __forceinline__ uint32_t ldw32u(const unsigned char* p) { if constexpr (WS) return *reinterpret_cast<const uint32_t*>(p); else return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+template <bool WS> __device__ __forceinline__ float ldw32f(const unsigned char* p) { if constexpr (WS) return *reinterpret_cast<const float*>(p); else return __ldg(reinterpret_cast<const float*>(p)); }
+template <bool WS> __device__ __forceinline__ uint32_t ldw16u(const unsigned char* p) { if constexpr (WS) return (uint32_t)*reinterpret_cast<const unsigned short*>(p); else return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)); }
 __device__ __forceinline__ float4 ldg128(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint2 ldg64u(const unsigned char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 __device__ __forceinline__ float2 ldg64f(const unsigned char* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
@@ -187,7 +197,10 @@ __device__ __forceinline__ void feature_lay(const FusedMod& m, const unsigned ch
 
 // NB sequences per CTA; TMEM: new state staged in tensor memory (single shared-memory tile);
 // DIN > 0: compile-time input width; SIMPLE: tanh activation, scalar leak, no bias / member parameters.
-template <int NB, bool TMEM, int DIN, bool SIMPLE>
+// WS: the whole W stream (and, when they fit, the row permutation and W_in) is copied into shared memory once and every
+// time step reads it from there — the latency-bound small-batch case (one long sequence, predict) no longer pays an L2
+// round trip per row slab and step.
+template <int NB, bool TMEM, int DIN, bool SIMPLE, bool WS>
 __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, const FastArgs fa) {
   using L = Lay<NB>;
   constexpr int NP = L::NP;
@@ -202,6 +215,26 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   float* u_s = reinterpret_cast<float*>(smem + (TMEM ? 1 : 2) * buf);  // [2][d_in][8]
   float* m_s = u_s + 2 * d_in * 8;                                     // [2][8] member scale | leak
   uint32_t* tm_s = reinterpret_cast<uint32_t*>(m_s + 16);
+  unsigned char* stage = reinterpret_cast<unsigned char*>(tm_s + 4);   // WS: W stream | perm | W_in (16-byte aligned)
+  const uint16_t* perm_p = p.perm;
+  const float* win_p = p.Win;
+  if constexpr (WS) {
+    const uint32_t nthr = (uint32_t)p.nthreads;
+    for (uint32_t i = tid * 16u; i < fa.stream_bytes; i += nthr * 16u)
+      *reinterpret_cast<uint4*>(stage + i) = __ldg(reinterpret_cast<const uint4*>(fa.stream + i));
+    unsigned char* q = stage + fa.stream_bytes;
+    if (fa.stage_perm) {
+      uint16_t* ps_ = reinterpret_cast<uint16_t*>(q);
+      for (int i = tid; i < p.npos; i += (int)nthr) ps_[i] = __ldg(p.perm + i);
+      perm_p = ps_;
+      q += ((size_t)p.npos * 2 + 15) / 16 * 16;
+    }
+    if (fa.stage_win) {
+      float* ws_ = reinterpret_cast<float*>(q);
+      for (int i = tid; i < p.npos * p.d_in; i += (int)nthr) ws_[i] = __ldg(p.Win + i);
+      win_p = ws_;
+    }
+  }
   const long long seq0 = (long long)blockIdx.x * NB;
   const int nvalid = p.B - seq0 < NB ? (int)(p.B - seq0) : NB;
   const float* u_g = reinterpret_cast<const float*>(p.u);
@@ -257,7 +290,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  const unsigned char* wbase = fa.stream + fa.warp_off[warp];
+  const unsigned char* wbase = (WS ? stage : fa.stream) + fa.warp_off[warp];
   const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab
   const bool use_mscale = !SIMPLE && p.member_scale != nullptr, use_mleak = !SIMPLE && p.member_leak != nullptr;
   float* out_g = reinterpret_cast<float*>(p.states);
@@ -283,15 +316,15 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
       if constexpr (TMEM) {
         TMEM_LD8(ta + (uint32_t)k * 8u, o);  // my old state of these rows + the row index (waited on below)
       } else {
-        r16 = __ldg(p.perm + pos);
+        r16 = WS ? (unsigned)perm_p[pos] : (unsigned)__ldg(p.perm + pos);
       }
       Acc<NB> A;
 #pragma unroll
       for (int q = 0; q < NPA; ++q) A.p[q] = make_float2(0.f, 0.f);
       A.s = 0.f;
       for (int q = 0; q < (wd >> 2); ++q) {
-        const float4 v = ldg128(wp + lane * 16);
-        const uint2 c = ldg64u(wp + 512 + lane * 8);
+        const float4 v = ldw128<WS>(wp + lane * 16);
+        const uint2 c = ldw64u<WS>(wp + 512 + lane * 8);
         wp += 768;
         gather1<NB>(A, cur, npad, v.x, c.x & 0xFFFFu);
         gather1<NB>(A, cur, npad, v.y, c.x >> 16);
@@ -299,15 +332,15 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
         gather1<NB>(A, cur, npad, v.w, c.y >> 16);
       }
       if (wd & 2) {
-        const float2 v = ldg64f(wp + lane * 8);
-        const uint32_t c = ldg32u(wp + 256 + lane * 4);
+        const float2 v = ldw64f<WS>(wp + lane * 8);
+        const uint32_t c = ldw32u<WS>(wp + 256 + lane * 4);
         wp += 384;
         gather1<NB>(A, cur, npad, v.x, c & 0xFFFFu);
         gather1<NB>(A, cur, npad, v.y, c >> 16);
       }
       if (wd & 1) {
-        const float v = ldg32f(wp + lane * 4);
-        const uint32_t c = ldg16u(wp + 128 + lane * 2);
+        const float v = ldw32f<WS>(wp + lane * 4);
+        const uint32_t c = ldw16u<WS>(wp + 128 + lane * 2);
         wp += 192;
         gather1<NB>(A, cur, npad, v, c);
       }
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
 #pragma unroll
       for (int d = 0; d < (DIN > 0 ? DIN : 8); ++d) {  // W_in*u (generics.jl:91-96), u broadcast from shared memory
         if (d < d_in) {
-          const float w = __ldg(p.Win + (size_t)d * p.npos + pos);
+          const float w = WS ? win_p[(size_t)d * p.npos + pos] : __ldg(p.Win + (size_t)d * p.npos + pos);
           const float2 ww = make_float2(w, w);
 #pragma unroll
           for (int q = 0; q < NP; ++q) A.p[q] = ffma2(ww, *reinterpret_cast<const float2*>(ucur + d * 8 + 2 * q), A.p[q]);
@@ -461,16 +494,24 @@ size_t fast_smem_bytes(int npad, int nb, int d_in, bool tmem) {
   return (tmem ? 1 : 2) * (size_t)npad * nb * 4 + (size_t)(2 * d_in * 8 + 16) * 4 + 16;
 }
 
-template <int NB, bool TMEM, int DIN, bool SIMPLE>
-static int32_t launch_fast_one(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
-  auto kern = k1_fast_kernel<NB, TMEM, DIN, SIMPLE>;
+template <int NB, bool TMEM, int DIN, bool SIMPLE, bool WS>
+static int32_t launch_fast_ws(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
+  auto kern = k1_fast_kernel<NB, TMEM, DIN, SIMPLE, WS>;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, p.nthreads, smem, ctx->stream>>>(p, fa);
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast<NB=%d,%s,din=%d,%s> grid=%d", NB, TMEM ? "tmem" : "smem2", DIN,
-           SIMPLE ? "simple" : "generic", grid);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast<NB=%d,%s,din=%d,%s%s> grid=%d", NB, TMEM ? "tmem" : "smem2", DIN,
+           SIMPLE ? "simple" : "generic", WS ? ",W-resident" : "", grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
+}
+
+template <int NB, bool TMEM, int DIN, bool SIMPLE>
+static int32_t launch_fast_one(rcb_ctx* ctx, const RecParams& p, const FastArgs& fa, size_t smem, int grid) {
+  if constexpr (NB <= 2 && !TMEM) {
+    if (fa.stream_bytes) return launch_fast_ws<NB, TMEM, DIN, SIMPLE, true>(ctx, p, fa, smem, grid);
+  }
+  return launch_fast_ws<NB, TMEM, DIN, SIMPLE, false>(ctx, p, fa, smem, grid);
 }
 
 template <int NB, bool TMEM>
@@ -518,9 +559,22 @@ int32_t launch_collect_fast(rcb_ctx* ctx, const RecParams& p, const DevFast& f, 
     else if (fits_smem) { nb = c; tmem = false; }
   }
   if (nb == 0) return RCB_OK;
-  const size_t smem = fast_smem_bytes(p.npad, nb, p.d_in, tmem);
+  size_t smem = fast_smem_bytes(p.npad, nb, p.d_in, tmem);
   const int grid = (int)((p.B + nb - 1) / nb);
-  FastArgs fa{f.stream, f.warp_off, f.wwords};
+  FastArgs fa{f.stream, f.warp_off, f.wwords, 0u, 0u, 0u};
+  if (!tmem && nb <= 2 && f.stream_bytes > 0 && !(mode && !strcmp(mode, "nows"))) {
+    // W-resident variant: stage the stream (then the permutation, then W_in) into what is left of shared memory
+    const size_t sb = (f.stream_bytes + 15) / 16 * 16, pb = ((size_t)p.npos * 2 + 15) / 16 * 16, wb = (size_t)p.npos * p.d_in * 4;
+    if (smem + sb <= cap) {
+      fa.stream_bytes = (uint32_t)sb;
+      smem += sb;
+      if (smem + pb <= cap) {
+        fa.stage_perm = 1;
+        smem += pb;
+        if (smem + wb <= cap) { fa.stage_win = 1; smem += wb; }
+      }
+    }
+  }
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   int32_t st = tmem ? launch_fast_stage<true>(ctx, p, fa, nb, smem, grid) : launch_fast_stage<false>(ctx, p, fa, nb, smem, grid);
   timer_end(ctx, RCB_TIMER_RECURRENCE);
