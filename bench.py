@@ -333,6 +333,10 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
     Wout = torch.empty((F, D), dtype=torch.float64, device="cuda")        # column-major D x F
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     k1_ms = gram_ms = 0.0
+    if world > 1:  # warm the NCCL channels for a reduction of this size (GC is still all zeros)
+        import torch.distributed as dist
+
+        dist.all_reduce(GC)
     barrier()
     e[0].record()
     carry.copy_(h0, non_blocking=True)
