@@ -925,34 +925,45 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   int64_t Bc = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(budget / per_member)));
   void* st_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * T * Bc * esz, &st_dev));
-  const size_t gc_elems = (size_t)F * (F + d_out);
+  const size_t gc_elems = (size_t)F * (F + d_out), w_elems = (size_t)d_out * F;
+  // systems per batched factorisation: up to ~1 GiB of [G | C] copies, whole members (all their lambdas) at a time
+  int64_t mg = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / (gc_elems * sizeof(double) * (size_t)n_lambda)));
+  mg = std::min<int64_t>(mg, std::max<int64_t>(1, 4096 / n_lambda));
   void *gc = nullptr, *work = nullptr, *w_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_elems * sizeof(double), &gc));
-  RCB_TRY(ctx_scratch(ctx, SCR_W, gc_elems * sizeof(double), &work));
-  const size_t w_elems = (size_t)d_out * F;
-  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_elems * sizeof(double), &w_dev));
+  RCB_TRY(ctx_scratch(ctx, SCR_W, gc_elems * sizeof(double) * (size_t)(mg * n_lambda), &work));
+  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_elems * sizeof(double) * (size_t)(mg * n_lambda), &w_dev));
+  std::vector<double> lam_rep((size_t)(mg * n_lambda));
+  for (int64_t m = 0; m < mg; ++m)
+    for (int32_t l = 0; l < n_lambda; ++l) lam_rep[(size_t)(m * n_lambda + l)] = lambdas[l];
+  std::vector<int> info((size_t)(mg * n_lambda));
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = std::min<int64_t>(Bc, B - b0);
     const void* uc = (const char*)u_dev + (size_t)b0 * T * d_in * esz;
     void* hc = (char*)h_dev + (size_t)b0 * sumN * esz;
     RCB_TRY(collect_device(esn, uc, T, nb, hc, st_dev, hc, b0));
-    for (int64_t b = 0; b < nb; ++b) {
-      const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
-      const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
-      RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
-      RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
-      for (int32_t l = 0; l < n_lambda; ++l) {
-        RCB_CUDA(cudaMemcpyAsync(work, gc, gc_elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        const int32_t st = launch_ridge_solve(ctx, (double*)work, F, d_out, lambdas[l], (double*)w_dev);
-        if (st != RCB_OK) {
-          if (st == RCB_ERR_NUMERIC) {
-            std::string msg = rcb_last_error();
-            return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: %s", (long long)(b0 + b), l, lambdas[l], msg.c_str());
-          }
-          return st;
-        }
-        RCB_TRY(from_device(ctx, W_out + ((size_t)(b0 + b) * n_lambda + l) * w_elems, w_dev, w_elems * sizeof(double)));
+    for (int64_t g0 = 0; g0 < nb; g0 += mg) {
+      const int64_t ng = std::min<int64_t>(mg, nb - g0);
+      for (int64_t m = 0; m < ng; ++m) {
+        const int64_t b = g0 + m;
+        const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
+        const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
+        RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
+        RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
+        for (int32_t l = 0; l < n_lambda; ++l)
+          RCB_CUDA(cudaMemcpyAsync((double*)work + (size_t)(m * n_lambda + l) * gc_elems, gc, gc_elems * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
       }
+      const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data());
+      if (st == RCB_ERR_NUMERIC) {
+        for (int64_t z = 0; z < ng * n_lambda; ++z)
+          if (info[(size_t)z] != 0)
+            return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: the regularised Gram matrix is not numerically positive definite "
+                        "(non-positive pivot at feature %d)", (long long)(b0 + g0 + z / n_lambda), (int)(z % n_lambda), lambdas[z % n_lambda],
+                        info[(size_t)z]);
+      }
+      RCB_TRY(st);
+      RCB_TRY(from_device(ctx, W_out + (size_t)(b0 + g0) * n_lambda * w_elems, w_dev, w_elems * sizeof(double) * (size_t)(ng * n_lambda)));
     }
   }
   if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));

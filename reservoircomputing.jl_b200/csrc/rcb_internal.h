@@ -228,6 +228,9 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
 
 // (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
+// the same for nsys systems stored back to back, one launch sequence (lambdas: host array or nullptr -> lambda0 for all)
+int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
+                                   int64_t nsys, double* W_out, int* info_out);
 
 // dense input projection P(N x S) = W_in(N x K) * Z(K x S), FP32 (deep layers)
 int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,

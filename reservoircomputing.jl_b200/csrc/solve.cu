@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <string>
+#include <vector>
+
 #include "rcb_internal.h"
 
 namespace rcb {
@@ -14,8 +17,13 @@ namespace rcb {
 constexpr int NBLK = 32;
 
 // Factor the NBLK x NBLK diagonal block at k0 (adds lambda to the diagonal on the way in).
+// Every kernel of the factorisation takes a batch: blockIdx.z selects the system (A += z * stride, its own lambda, its
+// own info flag), so a sweep over regularisations / ensemble members is ONE launch sequence (BASELINE config 5).
 __global__ void __launch_bounds__(NBLK* NBLK) potrf_diag_kernel(double* A, long long lda, long long F, long long k0,
-                                                                  double lambda, int* info) {
+                                                                  double lambda0, const double* lam, long long stride, int* info) {
+  A += (size_t)blockIdx.z * stride;
+  info += blockIdx.z;
+  const double lambda = lam ? lam[blockIdx.z] : lambda0;
   __shared__ double L[NBLK][NBLK + 1];
   const int i = threadIdx.x % NBLK, j = threadIdx.x / NBLK;
   const long long nb = F - k0 < NBLK ? F - k0 : NBLK;
@@ -46,7 +54,8 @@ __global__ void __launch_bounds__(NBLK* NBLK) potrf_diag_kernel(double* A, long 
 }
 
 // Panel: A[i, k0:k0+nb] <- A[i, k0:k0+nb] * L_kk^{-T} for rows below the diagonal block.
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double* A, long long lda, long long F, long long k0) {
+__global__ void __launch_bounds__(128) trsm_panel_kernel(double* A, long long lda, long long F, long long k0, long long stride) {
+  A += (size_t)blockIdx.z * stride;
   __shared__ double L[NBLK][NBLK + 1];
   const long long nb = F - k0 < NBLK ? F - k0 : NBLK;
   for (int e = threadIdx.x; e < NBLK * NBLK; e += blockDim.x) {
@@ -75,7 +84,8 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double* A, long long ld
 }
 
 // Trailing update: A[i, j] -= sum_m P[i, m] P[j, m], i >= j > panel, 64 x 64 tiles, K = NBLK.
-__global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long lda, long long F, long long k0) {
+__global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long lda, long long F, long long k0, long long stride) {
+  A += (size_t)blockIdx.z * stride;
   constexpr int TILE = 64;
   const long long base = k0 + NBLK;
   const long long i0 = base + (long long)blockIdx.y * TILE, j0 = base + (long long)blockIdx.x * TILE;
@@ -113,7 +123,10 @@ __global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long l
 // RHS + o*lda (length F); the solution overwrites it and is also written to W_out[o + d_out*f].
 __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, long long lda, long long F,
                                                                double* RHS, long long ldr, long long d_out,
-                                                               double* W_out) {
+                                                               double* W_out, long long stride) {
+  L += (size_t)blockIdx.z * stride;
+  RHS += (size_t)blockIdx.z * stride;
+  W_out += (size_t)blockIdx.z * d_out * F;
   extern __shared__ double xs[];  // [F]
   __shared__ double blk[NBLK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -171,40 +184,58 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, l
   }
 }
 
-int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out) {
-  int* d_info = nullptr;
+// nsys systems stored back to back (stride F*(F+d_out) doubles, each [G | C], destroyed); lambdas: nsys values on the HOST
+// (nullptr: every system uses lambda0); W_out: nsys x (d_out x F) on the device; info_out (host, nsys ints, may be null)
+// receives 0 or the 1-based feature of the first non-positive pivot.  Returns RCB_ERR_NUMERIC if any system failed.
+int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
+                                   int64_t nsys, double* W_out, int* info_out) {
+  if (nsys < 1) return RCB_OK;
+  if (nsys > 65535) return fail(RCB_ERR_UNSUPPORTED, "at most 65535 systems per batched solve");
   void* tmp = nullptr;
-  RCB_TRY(ctx_scratch(ctx, SCR_INFO, 256, &tmp));
-  d_info = reinterpret_cast<int*>(tmp);
-  RCB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), ctx->stream));
+  RCB_TRY(ctx_scratch(ctx, SCR_INFO, 512 + (size_t)nsys * 16, &tmp));
+  int* d_info = reinterpret_cast<int*>(tmp);
+  double* d_lam = reinterpret_cast<double*>((char*)tmp + 256 + ((size_t)nsys * sizeof(int) + 7) / 8 * 8);
+  RCB_CUDA(cudaMemsetAsync(d_info, 0, (size_t)nsys * sizeof(int), ctx->stream));
+  if (lambdas) RCB_CUDA(cudaMemcpyAsync(d_lam, lambdas, (size_t)nsys * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const double* lam = lambdas ? d_lam : nullptr;
   timer_begin(ctx, RCB_TIMER_SOLVE);
-  const long long lda = F;
+  const long long lda = F, stride = (long long)F * (F + d_out);
+  const unsigned nz = (unsigned)nsys;
   for (long long k0 = 0; k0 < F; k0 += NBLK) {
-    potrf_diag_kernel<<<1, NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0, lambda, d_info);
+    potrf_diag_kernel<<<dim3(1, 1, nz), NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0, lambda0, lam, stride, d_info);
     ctx->launches++;
     const long long rem = F - k0 - NBLK;
     if (rem > 0) {
-      trsm_panel_kernel<<<(unsigned)((rem + 127) / 128), 128, 0, ctx->stream>>>(GC, lda, F, k0);
+      trsm_panel_kernel<<<dim3((unsigned)((rem + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0, stride);
       const unsigned tiles = (unsigned)((rem + 63) / 64);
-      syrk_update_kernel<<<dim3(tiles, tiles), 256, 0, ctx->stream>>>(GC, lda, F, k0);
+      syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, stride);
       ctx->launches += 2;
     }
   }
   const size_t smem = (size_t)F * sizeof(double);
   if (smem > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "feature count %lld too large for the triangular-solve kernel", (long long)F);
   RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cholesky_solve_kernel<<<(unsigned)d_out, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)F * F, lda, d_out, W_out);
+  cholesky_solve_kernel<<<dim3((unsigned)d_out, 1, nz), 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)F * F, lda, d_out, W_out, stride);
   ctx->launches++;
   timer_end(ctx, RCB_TIMER_SOLVE);
   RCB_CUDA(cudaGetLastError());
-  int info = 0;
-  RCB_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<int> info((size_t)nsys, 0);
+  RCB_CUDA(cudaMemcpyAsync(info.data(), d_info, (size_t)nsys * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (info != 0)
-    return fail(RCB_ERR_NUMERIC,
-                "solver Cholesky(Gram) failed to solve the ridge regression system (non-positive pivot at feature %d; "
-                "the regularised Gram matrix is not numerically positive definite)", info);
-  return RCB_OK;
+  int32_t st = RCB_OK;
+  for (int64_t z = 0; z < nsys; ++z) {
+    if (info_out) info_out[z] = info[(size_t)z];
+    if (info[(size_t)z] != 0 && st == RCB_OK)
+      st = fail(RCB_ERR_NUMERIC,
+                "solver Cholesky(Gram) failed to solve the ridge regression system%s (non-positive pivot at feature %d; "
+                "the regularised Gram matrix is not numerically positive definite)",
+                nsys > 1 ? (" #" + std::to_string(z)).c_str() : "", info[(size_t)z]);
+  }
+  return st;
+}
+
+int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out) {
+  return launch_ridge_solve_batched(ctx, GC, F, d_out, lambda, nullptr, 1, W_out, nullptr);
 }
 
 }  // namespace rcb
