@@ -414,14 +414,14 @@ def const_init_sparse(M):
 
 
 # ---- K2 on tensor cores (tcgen05 kind::i8 digit planes, exact INT32 accumulation, csrc/gram_int8.cu) ----------
-@pytest.mark.parametrize("F,S,D", [(300, 5000, 3), (257, 1111, 1), (1024, 4096, 2), (640, 40000, 3)])
+@pytest.mark.parametrize("F,S,D", [(300, 5000, 3), (257, 1111, 1), (1024, 4096, 2), (640, 40000, 3), (384, 3000, 6), (512, 2000, 11)])
 def test_gram_tensor_matches_exact(R, F, S, D):
     from rcb200 import _lib as L
 
     rng = np.random.default_rng(F + S)
     Z = np.asfortranarray((rng.standard_normal((F, S)) * rng.uniform(0.05, 1.0, (F, 1))).astype(np.float32))
-    Y = np.asfortranarray(rng.standard_normal((D, S)).astype(np.float32))
-    g_t = R.gram(Z, Y, gram_mode=L.GRAM_TENSOR)
+    Y = np.asfortranarray(rng.standard_normal((D, S)).astype(np.float64 if D == 6 else np.float32))  # D = 6: Float64 targets
+    g_t = R.gram(Z, Y, gram_mode=L.GRAM_TENSOR)   # D <= 8: cross term fused into the split pre-pass; D = 11: separate kernel
     g_e = R.gram(Z, Y, gram_mode=L.GRAM_FP64)
     Z64 = Z.astype(np.float64)
     G = np.tril(Z64 @ Z64.T)
