@@ -333,10 +333,12 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
     Wout = torch.empty((F, D), dtype=torch.float64, device="cuda")        # column-major D x F
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     k1_ms = gram_ms = 0.0
-    if world > 1:  # warm the NCCL channels for a reduction of this size (GC is still all zeros)
+    packed = None
+    if world > 1:  # warm the NCCL channels for a reduction of this size
         import torch.distributed as dist
 
-        dist.all_reduce(GC)
+        packed = torch.zeros(int(lib.rcb_gc_packed_len(F, D)), dtype=torch.float64, device="cuda")
+        dist.all_reduce(packed)
     barrier()
     e[0].record()
     carry.copy_(h0, non_blocking=True)
@@ -349,10 +351,12 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
                                         1 if c == 0 else 0, L.ptr(GC)))
         gram_ms += dev.kernel_ms(L.TIMER_GRAM)
     e[1].record()
-    if world > 1:
+    if world > 1:  # only the lower triangle of G (+ C) travels: pack -> all-reduce -> unpack
         import torch.distributed as dist
 
-        dist.all_reduce(GC)
+        L.check(lib.rcb_gc_pack(dev.handle, L.ptr(GC), F, D, L.ptr(packed)))
+        dist.all_reduce(packed)
+        L.check(lib.rcb_gc_unpack(dev.handle, L.ptr(packed), F, D, L.ptr(GC)))
     e[2].record()
     lam = 1e-6 * T * B * world  # lambda = 1e-6 (per sample)
     L.check(lib.rcb_ridge_solve(dev.handle, L.ptr(GC), F, D, lam, L.ptr(Wout)))

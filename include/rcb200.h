@@ -208,6 +208,12 @@ RCB_API int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states
 RCB_API int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S,
                             int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out,
                             int64_t ld_targets, int32_t gram_mode, int32_t zero_first, double* GC);
+/* Multi-GPU exchange format of [G | C]: only the lower triangle of G carries data, so ranks all-reduce
+ *   packed = [ column 0 rows 0..F-1 | column 1 rows 1..F-1 | ... | C (F x d_out) ]   (F(F+1)/2 + F d_out doubles)
+ * — half the bytes of the full buffer.  Both buffers may be host or device pointers. */
+RCB_API int64_t rcb_gc_packed_len(int64_t F, int64_t d_out);
+RCB_API int32_t rcb_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double* packed);
+RCB_API int32_t rcb_gc_unpack(rcb_ctx* ctx, const double* packed, int64_t F, int64_t d_out, double* GC);
 /* Solve (G + λ I) W' = C from a packed [G | C]; only the lower triangle of G is read. */
 RCB_API int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
 

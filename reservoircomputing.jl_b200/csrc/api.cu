@@ -730,6 +730,34 @@ int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dty
   return RCB_OK;
 }
 
+int64_t rcb_gc_packed_len(int64_t F, int64_t d_out) { return F * (F + 1) / 2 + F * d_out; }
+
+static int32_t gc_pack_common(rcb_ctx* ctx, const double* src, int64_t F, int64_t d_out, double* dst, bool unpack) {
+  if (!ctx || !src || !dst) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (F < 1 || d_out < 0) return fail(RCB_ERR_ARGUMENT, "bad dimensions");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t full = (size_t)F * (F + d_out) * sizeof(double), pk = (size_t)rcb_gc_packed_len(F, d_out) * sizeof(double);
+  const size_t sb = unpack ? pk : full, db = unpack ? full : pk;
+  const void* s_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_TMP, src, sb, &s_dev));
+  void* d_dev = dst;
+  if (!is_device_ptr(dst)) {
+    RCB_TRY(ctx_scratch(ctx, SCR_TMP2, db, &d_dev));
+    if (unpack) RCB_CUDA(cudaMemcpyAsync(d_dev, dst, db, cudaMemcpyHostToDevice, ctx->stream));  // keep the upper triangle as it is
+  }
+  RCB_TRY(unpack ? launch_gc_pack(ctx, (double*)d_dev, F, d_out, (double*)const_cast<void*>(s_dev), true)
+                 : launch_gc_pack(ctx, (const double*)s_dev, F, d_out, (double*)d_dev, false));
+  if (d_dev != dst) RCB_TRY(from_device(ctx, dst, d_dev, db));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+int32_t rcb_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double* packed) {
+  return gc_pack_common(ctx, GC, F, d_out, packed, false);
+}
+int32_t rcb_gc_unpack(rcb_ctx* ctx, const double* packed, int64_t F, int64_t d_out, double* GC) {
+  return gc_pack_common(ctx, packed, F, d_out, GC, true);
+}
+
 int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double lambda, double* W_out) {
   if (!ctx || !GC || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);

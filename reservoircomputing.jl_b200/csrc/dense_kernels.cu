@@ -171,6 +171,35 @@ int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64
   return RCB_OK;
 }
 
+// ---- lower-triangle packing of [G | C] for the all-reduce between ranks ---------------------------------
+// column j of the triangle starts at j*F - j(j-1)/2; the F x d_out cross block follows the triangle.
+__global__ void __launch_bounds__(256) gc_pack_kernel(const double* __restrict__ GC, long long F, long long d_out,
+                                                      double* __restrict__ packed, int unpack) {
+  const long long j = blockIdx.x;
+  double* P = packed;
+  double* G = const_cast<double*>(GC);
+  if (j < F) {
+    const long long off = j * F - j * (j - 1) / 2 - j;  // + i for row i >= j
+    for (long long i = j + threadIdx.x; i < F; i += blockDim.x) {
+      if (unpack) G[(size_t)j * F + i] = P[off + i];
+      else P[off + i] = G[(size_t)j * F + i];
+    }
+  } else {
+    const long long d = j - F, tri = F * (F + 1) / 2;
+    for (long long i = threadIdx.x; i < F; i += blockDim.x) {
+      if (unpack) G[(size_t)(F + d) * F + i] = P[tri + d * F + i];
+      else P[tri + d * F + i] = G[(size_t)(F + d) * F + i];
+    }
+  }
+}
+
+int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double* packed, bool unpack) {
+  gc_pack_kernel<<<(unsigned)(F + d_out), 256, 0, ctx->stream>>>(GC, F, d_out, packed, unpack ? 1 : 0);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
 // ---- generic modifier chain, one column per CTA iteration ---------------------------------------
 struct ModParams {
   int n_mod;

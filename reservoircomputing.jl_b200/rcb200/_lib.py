@@ -82,6 +82,9 @@ SIGNATURES = {
     "rcb_collect": (_I32, [_P, _P, _I64, _I64, _P, _P, _P]),
     "rcb_fit_readout": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P]),
     "rcb_gram_accumulate": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I64, _I32, _I32, _P]),
+    "rcb_gc_packed_len": (_I64, [_I64, _I64]),
+    "rcb_gc_pack": (_I32, [_P, _P, _I64, _I64, _P]),
+    "rcb_gc_unpack": (_I32, [_P, _P, _I64, _I64, _P]),
     "rcb_ridge_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
     "rcb_train": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P, _P, _P, _P]),
     "rcb_train_members": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),

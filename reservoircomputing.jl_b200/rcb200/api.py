@@ -719,6 +719,39 @@ def time_chunks(T: int, washout: int, rank: int, world: int, overlap: int):
     return start, own_lo, own_hi
 
 
+def _allreduce_gc(GC, d_out, group, device, use_lib=True):
+    """Sum the packed [G | C] over the ranks: only the lower triangle of G (+ C) travels — half the bytes of the buffer
+    (rcb_gc_pack / rcb_gc_unpack; the NumPy packing is the CPU-test stand-in with the same layout)."""
+    import torch
+    import torch.distributed as dist
+
+    F = GC.shape[0]
+    n = F * (F + 1) // 2 + F * d_out
+    if use_lib:
+        dev = device or default_device()
+        packed = np.empty(n, dtype=np.float64)
+        check(lib().rcb_gc_pack(dev.handle, ptr(GC), F, d_out, ptr(packed)))
+    else:
+        packed = np.concatenate([GC[j:, j] for j in range(F)] + [GC[:, F + d] for d in range(d_out)])
+    t = torch.from_numpy(packed)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    packed = t.cpu().numpy()
+    out = np.zeros_like(GC, order="F")
+    if use_lib:
+        check(lib().rcb_gc_unpack(dev.handle, ptr(packed), F, d_out, ptr(out)))
+    else:
+        o = 0
+        for j in range(F):
+            out[j:, j] = packed[o:o + F - j]
+            o += F - j
+        for d in range(d_out):
+            out[:, F + d] = packed[o:o + F]
+            o += F
+    return out
+
+
 def _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode):
     h = _handle(rc, ps, d3.dtype, device)
     _, T, B = d3.shape
@@ -754,13 +787,9 @@ def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegres
         raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
     partial = _partial or (lambda: _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode))
     GC, hT, cell_sts = partial() if _partial is None else _partial(rc, ps, st, d3, y3, washout)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        t = torch.from_numpy(np.ascontiguousarray(GC.T))           # C-order view of the column-major [G | C]
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        GC = np.asfortranarray(t.cpu().numpy().T)
     d_out = y3.shape[0]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        GC = _allreduce_gc(GC, d_out, group, device, use_lib=_partial is None)
     W = (_solve or (lambda g, d, r: ridge_solve(g, d, r, device)))(GC, d_out, float(objective.reg))
     W = np.asarray(W).astype(_promote(objective, d3, y3))
     return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
@@ -831,11 +860,7 @@ def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeR
     if tail is not None and rank == world - 1:
         run([tail], tail[2] - tail[0])
     if world > 1:
-        t = torch.from_numpy(np.ascontiguousarray(GC.T))
-        if dist.get_backend(group) == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        GC = np.asfortranarray(t.cpu().numpy().T)
+        GC = _allreduce_gc(GC, d_out, group, device, use_lib=True)
     W = ridge_solve(GC, d_out, float(objective.reg), device).astype(_promote(objective, X, Y))
     cell_sts = list(_cell_st(rc, st))
     if hT is None:

@@ -603,3 +603,22 @@ def test_time_chunked_train_approaches_sequential(R):
     assert wins[0][1] == w and (tail[2] if tail else wins[-1][2]) == T and all(a[2] == b[1] for a, b in zip(wins, wins[1:]))
     with pytest.raises(R.ArgumentError):
         R.chunk_windows(T, 100, 4, 250)
+
+
+def test_gc_pack_roundtrip(R):
+    from rcb200 import _lib as L
+
+    rng = np.random.default_rng(3)
+    F, D = 37, 3
+    GC = np.asfortranarray(rng.standard_normal((F, F + D)))
+    lib, dev = R.lib(), R.default_device()
+    n = int(lib.rcb_gc_packed_len(F, D))
+    assert n == F * (F + 1) // 2 + F * D
+    packed = np.empty(n)
+    L.check(lib.rcb_gc_pack(dev.handle, L.ptr(GC), F, D, L.ptr(packed)))
+    ref = np.concatenate([GC[j:, j] for j in range(F)] + [GC[:, F + d] for d in range(D)])
+    assert np.array_equal(packed, ref)
+    out = np.zeros_like(GC, order="F")
+    L.check(lib.rcb_gc_unpack(dev.handle, L.ptr(packed), F, D, L.ptr(out)))
+    assert np.array_equal(np.tril(out[:, :F]), np.tril(GC[:, :F])) and np.array_equal(out[:, F:], GC[:, F:])
+    assert np.count_nonzero(np.triu(out[:, :F], 1)) == 0
