@@ -384,6 +384,10 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
             "tensor_frac": {"of_nominal_int8_4500": issued / (gram_ms * 1e-3) / 1e12 / 4500.0,
                             "of_twice_measured_bf16": issued / (gram_ms * 1e-3) / 1e12 / (2.0 * bf16),
                             "note": "gram_s includes the HBM-bound max + digit-split pre-passes; ncu tensor-pipe % in profiles/"},
+            "roofline": {"bound": "tensor", "achieved": issued / (gram_ms * 1e-3) / 1e12, "peak": 2.0 * bf16, "unit": "TOP/s",
+                         "frac": issued / (gram_ms * 1e-3) / 1e12 / (2.0 * bf16),
+                         "peak_source": "2 x measured dense bf16 (INT8 runs at twice the bf16 rate; MEASURED_PEAKS.json)",
+                         "kernel": "gram_i8_kernel (+ colmax / split pre-passes inside the timed span)"},
             "gram_mode": "tcgen05 kind::i8, 3 balanced base-256 digit planes, exact INT32 TMEM accumulation, FP64 across"}
 
 
