@@ -90,7 +90,7 @@ ctx() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context(0)))
     B200Reservoir(cell)
 
 Marker wrapper selecting the CUDA path: `ESN(...; )` is built as usual and its `reservoir`
-(`StatefulLayer(ESNCell)`) is wrapped — `ReservoirComputer(B200Reservoir(rc.reservoir), rc.states_modifiers, rc.readout)`.
+(`StatefulLayer(ESNCell)`) is wrapped — `ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)`.
 Parameter and state trees are those of the wrapped layer (LuxCore.initialparameters/initialstates forward).
 """
 struct B200Reservoir{L} <: ReservoirComputing.AbstractReservoirCollectionLayer
@@ -108,7 +108,7 @@ end
 
 function Handle(rc::ReservoirComputer, ps, ::Type{T}) where {T}
     cell = rc.reservoir.layer.cell::ESNCell
-    mods = collect(modifier_entry(m) for m in rc.states_modifiers)
+    mods = collect(modifier_entry(m) for m in rc.state_modifiers)
     length(mods) <= MAXMOD || throw(ArgumentError("at most $MAXMOD state modifiers"))
     kinds = ntuple(i -> i <= length(mods) ? mods[i][1] : Int32(0), MAXMOD)
     params = ntuple(i -> i <= length(mods) ? mods[i][2] : 0.0, MAXMOD)
@@ -224,7 +224,7 @@ end
 
 Same model, CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ))`.
 """
-b200(rc::ReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.states_modifiers, rc.readout)
+b200(rc::ReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 
 export B200Reservoir, B200Ridge, b200
 
