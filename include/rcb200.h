@@ -140,6 +140,18 @@ RCB_API int32_t rcb_esn_set_weights_dense(rcb_esn* esn, int32_t layer, const flo
 RCB_API int32_t rcb_esn_set_weights_csc(rcb_esn* esn, int32_t layer, const int64_t* colptr, const int64_t* rowval,
                                 const float* nzval, const float* W_in, int64_t ldwin, const float* bias);
 RCB_API int32_t rcb_esn_set_leak_vector(rcb_esn* esn, int32_t layer, const float* leak);
+
+/* Sibling cells of the ESN family — same (inp, (h,)) contract, same collect / train / predict drivers:
+ *   RCB_CELL_ESN     h' = (1-a) h + a phi(W_in u + W h + b)                      src/layers/esn_cell.jl:175-184
+ *   RCB_CELL_ES2N    h' = (1-p) (O h) + p phi(W_in u + W h + b)      p0 = proximity   src/layers/es2n_cell.jl:106-116
+ *   RCB_CELL_RESESN  h' = alpha (O h) + beta phi(W_in u + W h + b)   p0 = alpha, p1 = beta   src/layers/resesn_cell.jl:112-125
+ *   RCB_CELL_EUSN    ESN step (leak = desc.leak_scalar) on W - W' - gamma I   p0 = diffusion gamma   src/layers/eusn_cell.jl:95-106,120-123
+ * O = ps.orthogonal_matrix, a dense N x N Float32 matrix handed over by rcb_esn_set_orthogonal_dense.
+ * rcb_esn_set_cell invalidates weights already installed for the layer (call it first, then rcb_esn_set_weights_*).
+ * rcb_esn_export_csr keeps returning the reservoir_matrix as given (for EuSN: W, not the anti-symmetric operator). */
+typedef enum { RCB_CELL_ESN = 0, RCB_CELL_ES2N = 1, RCB_CELL_RESESN = 2, RCB_CELL_EUSN = 3 } rcb_cell_kind;
+RCB_API int32_t rcb_esn_set_cell(rcb_esn* esn, int32_t layer, int32_t cell_kind, double p0, double p1);
+RCB_API int32_t rcb_esn_set_orthogonal_dense(rcb_esn* esn, int32_t layer, const float* O, int64_t ldo);
 /* Canonical CSR the kernels were built from (0-based, columns ascending) — for the bit-exact
  * sparsity-pattern parity check. */
 RCB_API int32_t rcb_esn_csr_nnz(const rcb_esn* esn, int32_t layer, int64_t* nnz);
@@ -153,6 +165,10 @@ RCB_API int32_t rcb_csr_from_dense(const float* W, int64_t ldw, int32_t n, int64
                                    int32_t* colind, float* vals);
 RCB_API int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n,
                                  int64_t* nnz, int64_t* rowptr, int32_t* colind, float* vals);
+/* Host-only: canonical CSR of the EuSN operator W - W' - diffusion I the kernels apply (eusn_cell.jl:120-123), same
+ * two-call protocol; entries that cancel to exactly 0 are dropped. */
+RCB_API int32_t rcb_eusn_operator_from_dense(const float* W, int64_t ldw, int32_t n, double diffusion, int64_t* nnz,
+                                             int64_t* rowptr, int32_t* colind, float* vals);
 /* Host-only diagnostics of the kernel-side sliced-ELL layout built from a dense matrix (balanced != 0:
  * the bank-conflict-free schedule).  stats[0] = nnz, [1] = padded nnz, [2]/[3] = simulated / ideal
  * shared-memory wavefronts of the LDS.64 gathers of one pass over W, [4]/[5] = same for LDS.32,
@@ -191,7 +207,8 @@ RCB_API int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, c
  *   states  F x S (ld = ld_states), targets d_out x S (ld = ld_targets), dtype each RCB_F32/RCB_F64
  *   W_out   d_out x F Float64 (ld = d_out)
  *   gram_mode: RCB_GRAM_AUTO / RCB_GRAM_FP64 (exact products, FP64 accumulate) /
- *              RCB_GRAM_TENSOR (tcgen05 3xTF32, FP32 accumulate in TMEM, FP64 flush)
+ *              RCB_GRAM_TENSOR (tcgen05 kind::i8 on three base-256 digit planes of the fixed-point states,
+ *              exact INT32 accumulation in TMEM, FP64 fold — DESIGN.md K2)
  * Errors (train.jl:113-134): S_states != S_targets -> RCB_ERR_DIMENSION (caller checks and passes
  * both counts); S < 1 -> RCB_ERR_ARGUMENT; λ < 0 -> RCB_ERR_ARGUMENT; not positive definite ->
  * RCB_ERR_NUMERIC (train.jl:194-196). */

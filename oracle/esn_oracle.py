@@ -167,10 +167,24 @@ class ESNCellParams:
     leak: object = 1.0  # scalar or (N,) vector, esn_cell.jl:131-142
     act: int = ACT_TANH
     modifiers: tuple = ()  # per-layer state modifiers ((kind, param), ...)
+    # sibling cells: "esn" | "es2n" (proximity) | "resesn" (alpha, beta) | "eusn" (diffusion; leak above)
+    cell: str = "esn"
+    orthogonal_matrix: Optional[np.ndarray] = None  # (N, N), ES2N / ResESN
+    proximity: float = 1.0
+    alpha: float = 1.0
+    beta: float = 1.0
+    diffusion: float = 1.0
 
     @property
     def n(self) -> int:
         return self.reservoir_matrix.shape[0]
+
+
+def compute_asym_recurrent(W: np.ndarray, gamma) -> np.ndarray:
+    """src/layers/eusn_cell.jl:120-123 — W .- transpose(W) .- gamma .* I, one fused broadcast:
+    (W_ij - W_ji) in eltype(W), then minus gamma*I_ij in the promoted type."""
+    eye = np.eye(W.shape[0], dtype=W.dtype)
+    return (W - W.T) - gamma * eye
 
 
 def esn_cell_step(p: ESNCellParams, u: np.ndarray, h: np.ndarray) -> np.ndarray:
@@ -180,12 +194,20 @@ def esn_cell_step(p: ESNCellParams, u: np.ndarray, h: np.ndarray) -> np.ndarray:
     """
     T = u.dtype
     win_inp = p.input_matrix @ u  # generics.jl:91-96 (no bias on the input projection)
-    w_state = p.reservoir_matrix @ h  # generics.jl:83-96
+    if p.cell == "eusn":  # eusn_cell.jl:95-106: the same leaky step on the anti-symmetric operator
+        w_state = compute_asym_recurrent(p.reservoir_matrix, T.type(p.diffusion)) @ h
+    else:
+        w_state = p.reservoir_matrix @ h  # generics.jl:83-96
     if p.bias is not None:
         w_state = w_state + (p.bias if w_state.ndim == 1 else p.bias[:, None])
     if win_inp.ndim == 1 and w_state.ndim == 2:  # vector input, N x 1 hidden state (lux_layers.jl:212-216)
         win_inp = win_inp[:, None]
     cand = activation(p.act)(win_inp + w_state)  # :180
+    if p.cell == "es2n":  # es2n_cell.jl:106-116: ((1-p) .* O) * h .+ p .* cand  (.* and * associate left)
+        prox = T.type(p.proximity)
+        return ((T.type(1) - prox) * p.orthogonal_matrix) @ h + prox * cand
+    if p.cell == "resesn":  # resesn_cell.jl:112-125: alpha .* (O * h) .+ beta .* cand
+        return T.type(p.alpha) * (p.orthogonal_matrix @ h) + T.type(p.beta) * cand
     if np.isscalar(p.leak):  # __format_leak :186-188
         lc = T.type(p.leak)
         oml = T.type(1) - lc  # __one_minus_leak :194-196

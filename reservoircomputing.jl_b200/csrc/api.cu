@@ -145,6 +145,8 @@ static void free_layer(Layer& L) {
   L.d_Win4 = nullptr;
   L.sell = DevSell{};
   L.d_Win = L.d_bias = L.d_leak = nullptr;
+  cudaFree(L.d_Ot);
+  L.d_Ot = nullptr;
 }
 
 template <typename V>
@@ -163,6 +165,65 @@ static int esn_nthreads(const rcb_esn* e) {
   return nt > 1024 ? 1024 : nt;
 }
 
+// EuSN (src/layers/eusn_cell.jl:120-123): A = W .- transpose(W) .- gamma .* I, evaluated entry by entry in Float32
+// like the reference's fused broadcast ((W_ij - W_ji) - gamma*I_ij); entries that come out as exact zeros are dropped.
+static int32_t eusn_operator(const HostCsr& W, double gamma, HostCsr* out) {
+  const int32_t n = W.n;
+  std::vector<std::vector<std::pair<int32_t, float>>> rowsT((size_t)n);  // W' by row
+  for (int32_t i = 0; i < n; ++i)
+    for (int64_t k = W.rowptr[(size_t)i]; k < W.rowptr[(size_t)i + 1]; ++k)
+      rowsT[(size_t)W.colind[(size_t)k]].push_back({i, W.vals[(size_t)k]});
+  const float g = (float)gamma;
+  out->n = n;
+  out->rowptr.assign((size_t)n + 1, 0);
+  out->colind.clear();
+  out->vals.clear();
+  for (int32_t i = 0; i < n; ++i) {
+    int64_t ka = W.rowptr[(size_t)i];
+    const int64_t kae = W.rowptr[(size_t)i + 1];
+    size_t kb = 0;
+    const auto& rt = rowsT[(size_t)i];  // ascending by construction
+    bool diag_done = false;
+    auto emit = [&](int32_t j, float wij, float wji) {
+      float v = wij - wji;
+      if (j == i) { v = v - g * 1.0f; diag_done = true; }
+      if (v != 0.f) { out->colind.push_back(j); out->vals.push_back(v); }
+    };
+    auto flush_diag_before = [&](int32_t j) {
+      if (!diag_done && j > i) emit(i, 0.f, 0.f);
+    };
+    while (ka < kae || kb < rt.size()) {
+      const int32_t ja = ka < kae ? W.colind[(size_t)ka] : INT32_MAX;
+      const int32_t jb = kb < rt.size() ? rt[kb].first : INT32_MAX;
+      const int32_t j = ja < jb ? ja : jb;
+      flush_diag_before(j);
+      float wij = 0.f, wji = 0.f;
+      if (ja == j) wij = W.vals[(size_t)ka++];
+      if (jb == j) wji = rt[kb++].second;
+      emit(j, wij, wji);
+    }
+    if (!diag_done) emit(i, 0.f, 0.f);
+    out->rowptr[(size_t)i + 1] = (int64_t)out->colind.size();
+  }
+  return RCB_OK;
+}
+
+// O (host, N x N column-major) -> d_Ot in the position order of the installed schedule
+static int32_t install_orthogonal(rcb_esn* esn, Layer& L) {
+  if (L.h_O.empty() || L.h_perm.empty()) return RCB_OK;
+  RCB_CUDA(cudaSetDevice(esn->ctx->device));
+  cudaFree(L.d_Ot);
+  L.d_Ot = nullptr;
+  const size_t npos = L.h_perm.size(), n = (size_t)L.n;
+  std::vector<float> ot(npos * n, 0.f);
+  for (size_t pos = 0; pos < npos; ++pos) {
+    const uint16_t r = L.h_perm[pos];
+    if (r == 0xFFFF) continue;
+    for (size_t j = 0; j < n; ++j) ot[j * npos + pos] = L.h_O[j * n + r];
+  }
+  return upload(ot, &L.d_Ot);
+}
+
 static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, int64_t ldwin, const float* bias) {
   Layer& L = esn->layers[(size_t)layer];
   if (!W_in) return fail(RCB_ERR_ARGUMENT, "input_matrix pointer is NULL");
@@ -170,10 +231,13 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   if (L.desc.use_bias && !bias) return fail(RCB_ERR_ARGUMENT, "layer %d has use_bias=true but bias is NULL", layer);
   RCB_CUDA(cudaSetDevice(esn->ctx->device));
   free_layer(L);
+  if (L.cell == RCB_CELL_EUSN) RCB_TRY(eusn_operator(L.csr, L.cell_p0, &L.eff));
+  const HostCsr& K = L.cell == RCB_CELL_EUSN ? L.eff : L.csr;  // the operator the kernels apply to h
   HostSell hs;
   const char* plain = getenv("RCB_SELL");  // testing hook: RCB_SELL=plain disables the conflict-free schedule
-  if (plain && !strcmp(plain, "plain")) RCB_TRY(sell_from_csr(L.csr, esn_nthreads(esn), &hs));
-  else RCB_TRY(sell_from_csr_balanced(L.csr, esn_nthreads(esn), &hs));
+  if (plain && !strcmp(plain, "plain")) RCB_TRY(sell_from_csr(K, esn_nthreads(esn), &hs));
+  else RCB_TRY(sell_from_csr_balanced(K, esn_nthreads(esn), &hs));
+  L.h_perm = hs.perm;
   L.sell.n = hs.n; L.sell.nthreads = hs.nthreads; L.sell.R = hs.R; L.sell.nwarps = hs.nwarps;
   L.sell.total_slots = (int64_t)hs.vals.size() / 32;
   RCB_TRY(upload(hs.perm, &L.sell.perm));
@@ -182,7 +246,7 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   RCB_TRY(upload(hs.vals, &L.sell.vals));
   RCB_TRY(upload(hs.cols, &L.sell.cols));
   HostFast hf;
-  RCB_TRY(fast_from_csr(L.csr, hs, &hf));
+  RCB_TRY(fast_from_csr(K, hs, &hf));
   if (hf.ok) {
     RCB_TRY(upload(hf.stream, &L.fast.stream));
     L.fast.stream_bytes = hf.stream.size();
@@ -204,7 +268,7 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   RCB_TRY(upload(winp, &L.d_Win));
   if (L.d_in == 3 || L.d_in == 1) {
     HostFast hf4;
-    RCB_TRY(fast_from_csr(L.csr, hs, &hf4, 4));
+    RCB_TRY(fast_from_csr(K, hs, &hf4, 4));
     if (hf4.ok) {
       RCB_TRY(upload(hf4.stream, &L.fast4.stream));
       RCB_TRY(upload(hf4.warp_off, &L.fast4.warp_off));
@@ -219,8 +283,8 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
     if (hf4.ok && L.d_in == 3 && L.n == 8192 && esn_nthreads(esn) == 1024 && k1mode && !strcmp(k1mode, "fast7_512")) {  // experimental second schedule: 512 threads x 16 slabs
       HostSell hs2;
       HostFast hf2;
-      RCB_TRY(sell_from_csr_balanced(L.csr, 512, &hs2));
-      RCB_TRY(fast_from_csr(L.csr, hs2, &hf2, 4));
+      RCB_TRY(sell_from_csr_balanced(K, 512, &hs2));
+      RCB_TRY(fast_from_csr(K, hs2, &hf2, 4));
       if (hf2.ok) {
         const int np2 = hs2.R * hs2.nthreads;
         std::vector<float> w4((size_t)np2 * 4, 0.f);
@@ -242,6 +306,7 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
     std::vector<float> b(bias, bias + L.n);
     RCB_TRY(upload(b, &L.d_bias));
   }
+  RCB_TRY(install_orthogonal(esn, L));
   L.weights_set = true;
   return RCB_OK;
 }
@@ -259,6 +324,11 @@ static int32_t check_ready(const rcb_esn* esn) {
     if (!esn->layers[l].weights_set) return fail(RCB_ERR_ARGUMENT, "weights of layer %d have not been set", (int)l);
     if (esn->layers[l].desc.leak_is_vector && !esn->layers[l].d_leak)
       return fail(RCB_ERR_ARGUMENT, "layer %d declares a vector leak_coefficient but rcb_esn_set_leak_vector was not called", (int)l);
+    const Layer& L = esn->layers[l];
+    if ((L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN) && !L.d_Ot)
+      return fail(RCB_ERR_ARGUMENT, "layer %d is an ES2N/ResESN cell but rcb_esn_set_orthogonal_dense was not called", (int)l);
+    if (L.cell != RCB_CELL_ESN && esn->member_count)
+      return fail(RCB_ERR_UNSUPPORTED, "ensemble member parameters apply to the plain ESN cell only");
   }
   return RCB_OK;
 }
@@ -516,6 +586,37 @@ int32_t rcb_esn_set_leak_vector(rcb_esn* esn, int32_t layer, const float* leak) 
   return upload(v, &L.d_leak);
 }
 
+int32_t rcb_esn_set_cell(rcb_esn* esn, int32_t layer, int32_t cell_kind, double p0, double p1) {
+  RCB_TRY(check_layer(esn, layer));
+  if (cell_kind < RCB_CELL_ESN || cell_kind > RCB_CELL_EUSN) return fail(RCB_ERR_ARGUMENT, "unknown cell kind %d", cell_kind);
+  Layer& L = esn->layers[(size_t)layer];
+  if (cell_kind != RCB_CELL_ESN && L.desc.leak_is_vector)
+    return fail(RCB_ERR_ARGUMENT, "ES2N / ResESN / EuSN cells take scalar coefficients (es2n_cell.jl:86, resesn_cell.jl:91, eusn_cell.jl:87)");
+  RCB_CUDA(cudaSetDevice(esn->ctx->device));
+  free_layer(L);
+  L.weights_set = false;
+  L.h_perm.clear();
+  L.cell = cell_kind; L.cell_p0 = p0; L.cell_p1 = p1;
+  return RCB_OK;
+}
+
+int32_t rcb_esn_set_orthogonal_dense(rcb_esn* esn, int32_t layer, const float* O, int64_t ldo) {
+  RCB_TRY(check_layer(esn, layer));
+  if (!O) return fail(RCB_ERR_ARGUMENT, "orthogonal_matrix pointer is NULL");
+  Layer& L = esn->layers[(size_t)layer];
+  if (L.cell != RCB_CELL_ES2N && L.cell != RCB_CELL_RESESN)
+    return fail(RCB_ERR_ARGUMENT, "layer %d is not an ES2N / ResESN cell (call rcb_esn_set_cell first)", layer);
+  if (ldo < L.n) return fail(RCB_ERR_DIMENSION, "orthogonal_matrix leading dimension %lld < res_dims=%d", (long long)ldo, L.n);
+  L.h_O.resize((size_t)L.n * L.n);
+  for (int j = 0; j < L.n; ++j)
+    for (int i = 0; i < L.n; ++i) {
+      const float v = O[(size_t)j * ldo + i];
+      if (v != v || v - v != 0.f) return fail(RCB_ERR_NUMERIC, "orthogonal_matrix contains invalid values (NaN/Inf)");
+      L.h_O[(size_t)j * L.n + i] = v;
+    }
+  return install_orthogonal(esn, L);
+}
+
 int32_t rcb_esn_csr_nnz(const rcb_esn* esn, int32_t layer, int64_t* nnz) {
   RCB_TRY(check_layer(esn, layer));
   if (!nnz) return fail(RCB_ERR_ARGUMENT, "nnz is NULL");
@@ -556,6 +657,15 @@ int32_t rcb_csr_from_csc(const int64_t* colptr, const int64_t* rowval, const flo
   HostCsr c;
   RCB_TRY(csr_from_csc(colptr, rowval, nzval, n, &c));
   return csr_out(c, nnz, rowptr, colind, vals);
+}
+
+int32_t rcb_eusn_operator_from_dense(const float* W, int64_t ldw, int32_t n, double diffusion, int64_t* nnz, int64_t* rowptr,
+                                     int32_t* colind, float* vals) {
+  if (!W || !nnz) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  HostCsr c, a;
+  RCB_TRY(csr_from_dense(W, ldw, n, &c));
+  RCB_TRY(eusn_operator(c, diffusion, &a));
+  return csr_out(a, nnz, rowptr, colind, vals);
 }
 
 int32_t rcb_sell_stats_from_dense(const float* W, int64_t ldw, int32_t n, int32_t nthreads, int32_t balanced, int64_t* stats) {

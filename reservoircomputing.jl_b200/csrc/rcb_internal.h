@@ -128,6 +128,13 @@ struct Layer {
   float* d_bias = nullptr;  // [n] by row
   float* d_leak = nullptr;  // [n] by row (vector leak) or nullptr
   bool weights_set = false;
+  // sibling cells (rcb_esn_set_cell): ES2N / ResESN carry a dense orthogonal operator, EuSN an anti-symmetric W
+  int32_t cell = RCB_CELL_ESN;
+  double cell_p0 = 0.0, cell_p1 = 0.0;
+  HostCsr eff;                  // EuSN: W - W' - gamma I, what the kernels are built from (csr stays the user's W)
+  std::vector<float> h_O;       // host copy of O, N x N column-major (kept: the position order comes from W)
+  std::vector<uint16_t> h_perm; // position -> row of the installed schedule
+  float* d_Ot = nullptr;        // [n][npos]: Ot[j*npos + pos] = O[perm[pos], j]
 };
 
 }  // namespace rcb

@@ -74,14 +74,31 @@ __device__ __forceinline__ void row_update(const RecParams& p, const unsigned ch
     }
   }
   T hold[NB], hnew[NB];
-  pack_load<T, NB>(cur, p.npad, r, hold);
-  T lc = (T)p.leak;
-  if (p.leakv) lc = (T)__ldg(p.leakv + r);
+  if (p.Ot) {  // ES2N / ResESN: the skip path is the dense orthogonal operator, not the old state
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const T l = mleak ? mleak[b] : lc;
-    const T cand = apply_act<T>(p.act, win[b] + acc[b]);
-    hnew[b] = (T(1) - l) * hold[b] + l * cand;  // esn_cell.jl:182
+    for (int b = 0; b < NB; ++b) hold[b] = T(0);
+    const float* op = p.Ot + pos;
+#pragma unroll 4
+    for (int j = 0; j < p.n; ++j) {
+      const T o = (T)__ldg(op + (size_t)j * p.npos);
+      T x0[NB];
+      pack_load<T, NB>(cur, p.npad, j, x0);  // same address in every lane: a shared-memory broadcast
+#pragma unroll
+      for (int b = 0; b < NB; ++b) hold[b] = fma(o, x0[b], hold[b]);
+    }
+    const T sa = (T)p.skip_a, cb = (T)p.cand_b;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) hnew[b] = sa * hold[b] + cb * apply_act<T>(p.act, win[b] + acc[b]);
+  } else {
+    pack_load<T, NB>(cur, p.npad, r, hold);
+    T lc = (T)p.leak;
+    if (p.leakv) lc = (T)__ldg(p.leakv + r);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const T l = mleak ? mleak[b] : lc;
+      const T cand = apply_act<T>(p.act, win[b] + acc[b]);
+      hnew[b] = (T(1) - l) * hold[b] + l * cand;  // esn_cell.jl:182
+    }
   }
   if (valid) pack_store<T, NB>(nxt, p.npad, r, hnew);
 }
@@ -228,9 +245,20 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
   p.h_stride = a.h_stride > 0 ? a.h_stride : L.n; p.h_off = a.h_off;
   p.member_scale = a.member_scale; p.member_leak = a.member_leak; p.raw = a.raw_states ? 1 : 0;
   if (a.pre_in) p.d_in = 0;
+  p.Ot = nullptr; p.skip_a = 0.0; p.cand_b = 1.0;
+  if (L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN) {
+    p.Ot = L.d_Ot;
+    // one(T) - T(proximity), es2n_cell.jl:109,113 — evaluated in the data eltype
+    if (L.cell == RCB_CELL_ES2N) {
+      p.skip_a = a.dtype == RCB_F64 ? 1.0 - L.cell_p0 : (double)(1.0f - (float)L.cell_p0);
+      p.cand_b = L.cell_p0;
+    } else {
+      p.skip_a = L.cell_p0; p.cand_b = L.cell_p1;
+    }
+  }
   const size_t esz = a.dtype == RCB_F64 ? 8 : 4;
   const size_t cap = ctx->smem_optin;
-  if (a.dtype == RCB_F32) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
+  if (a.dtype == RCB_F32 && !p.Ot) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
     bool launched = false;
     const int32_t f7 = launch_collect_fast7(ctx, p, L.fast4, L.d_Win4, L.fast4h, L.d_Win4h, L.d_permh, &launched);
     if (f7 != RCB_OK || launched) return f7;
@@ -282,6 +310,7 @@ struct PredLayer {
   const uint16_t* perm; const int32_t* blk_off; const int32_t* blk_w; const float* vals; const uint16_t* cols;
   const float* Win; const float* bias; const float* leakv;
   double leak; int act; FusedMod mod;
+  const float* Ot; double skip_a, cand_b;  // ES2N / ResESN skip operator (see RecParams)
   int h_off;   // element offset of this layer's state double-buffer in smem
   int c_off;   // row offset of this layer in the packed carry array
 };
@@ -363,7 +392,16 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
         T lc = L.leakv ? (T)__ldg(L.leakv + r) : (T)L.leak;
         if (l == 0 && p.member_leak) lc = (T)p.member_leak[seq];
         const T cand = apply_act<T>(L.act, win + acc);
-        const T hn = (T(1) - lc) * cur[r] + lc * cand;
+        T hn;
+        if (L.Ot) {
+          T sk = T(0);
+          const float* op = L.Ot + pos;
+#pragma unroll 4
+          for (int j = 0; j < L.n; ++j) sk = fma((T)__ldg(op + (size_t)j * L.npos), cur[j], sk);
+          hn = (T)L.skip_a * sk + (T)L.cand_b * cand;
+        } else {
+          hn = (T(1) - lc) * cur[r] + lc * cand;
+        }
         if (valid) nxt[r] = hn;
       }
       __syncthreads();
@@ -423,6 +461,13 @@ int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
     q.perm = L.sell.perm; q.blk_off = L.sell.blk_off; q.blk_w = L.sell.blk_w; q.vals = L.sell.vals; q.cols = L.sell.cols;
     q.Win = L.d_Win; q.bias = L.desc.use_bias ? L.d_bias : nullptr; q.leakv = L.desc.leak_is_vector ? L.d_leak : nullptr;
     q.leak = L.desc.leak_scalar; q.act = L.desc.activation; q.mod = make_fused(L);
+    q.Ot = nullptr; q.skip_a = 0.0; q.cand_b = 1.0;
+    if (L.cell == RCB_CELL_ES2N) {
+      q.Ot = L.d_Ot; q.cand_b = L.cell_p0;
+      q.skip_a = a.compute_dtype == RCB_F64 ? 1.0 - L.cell_p0 : (double)(1.0f - (float)L.cell_p0);
+    } else if (L.cell == RCB_CELL_RESESN) {
+      q.Ot = L.d_Ot; q.skip_a = L.cell_p0; q.cand_b = L.cell_p1;
+    }
     q.h_off = h_off; q.c_off = c_off;
     h_off += 2 * q.npad; c_off += L.n;
     zmax = zmax > L.feat ? zmax : L.feat;

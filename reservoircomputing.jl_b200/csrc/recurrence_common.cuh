@@ -166,6 +166,9 @@ struct RecParams {
   const float* member_scale;
   const float* member_leak;
   int raw;  // write the un-modified state (feat == n)
+  // ES2N / ResESN (es2n_cell.jl:106-116, resesn_cell.jl:112-125): h' = skip_a * (O h) + cand_b * phi(...)
+  const float* Ot;  // [n][npos] by position, or nullptr for the leaky ESN / EuSN update
+  double skip_a, cand_b;
 };
 
 // recurrence_fast.cu: picks (sequences per CTA, staging) and launches the tuned kernel; *launched stays

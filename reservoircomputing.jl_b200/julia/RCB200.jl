@@ -16,8 +16,8 @@
 module RCB200
 
 using ReservoirComputing
-using ReservoirComputing: AbstractReservoirComputer, ReservoirComputer, StatefulLayer, ESNCell,
-                          RidgeRegression, NLAT1, NLAT2, NLAT3, Pad, PartialSquare, ExtendedSquare
+using ReservoirComputing: AbstractReservoirComputer, ReservoirComputer, StatefulLayer, ESNCell, ES2NCell, ResESNCell,
+                          EuSNCell, RidgeRegression, NLAT1, NLAT2, NLAT3, Pad, PartialSquare, ExtendedSquare
 import ReservoirComputing: __collectstates, __predict, __fit_readout
 using SparseArrays: SparseMatrixCSC
 
@@ -106,13 +106,20 @@ mutable struct Handle
     N::Int
 end
 
-function Handle(rc::ReservoirComputer, ps, ::Type{T}) where {T}
-    cell = rc.reservoir.layer.cell::ESNCell
+# sibling cells (include/rcb200.h: rcb_cell_kind): (kind, p0, p1, leak)
+cell_variant(c::ESNCell) = (Int32(0), 0.0, 0.0, c.leak_coefficient)
+cell_variant(c::ES2NCell) = (Int32(1), Float64(c.proximity), 0.0, 1.0)               # es2n_cell.jl:106-116
+cell_variant(c::ResESNCell) = (Int32(2), Float64(c.alpha), Float64(c.beta), 1.0)     # resesn_cell.jl:112-125
+cell_variant(c::EuSNCell) = (Int32(3), Float64(c.diffusion), 0.0, c.leak_coefficient) # eusn_cell.jl:95-106
+cell_variant(c) = throw(ArgumentError("cell $(typeof(c)) is outside the B200 hot path"))
+
+function Handle(rc::AbstractReservoirComputer, ps, ::Type{T}) where {T}
+    cell = rc.reservoir.layer.cell
+    kind, p0, p1, α = cell_variant(cell)
     mods = collect(modifier_entry(m) for m in rc.state_modifiers)
     length(mods) <= MAXMOD || throw(ArgumentError("at most $MAXMOD state modifiers"))
     kinds = ntuple(i -> i <= length(mods) ? mods[i][1] : Int32(0), MAXMOD)
     params = ntuple(i -> i <= length(mods) ? mods[i][2] : 0.0, MAXMOD)
-    α = cell.leak_coefficient
     ld = LayerDesc(cell.out_dims, activation_id(cell.activation), ReservoirComputing.known(cell.use_bias) ? 1 : 0,
                    α isa AbstractVector ? 1 : 0, α isa AbstractVector ? 0.0 : Float64(α), length(mods), kinds, params)
     d = ESNDesc(1, cell.in_dims, rc.readout.out_dims, activation_id(rc.readout.activation),
@@ -122,6 +129,7 @@ function Handle(rc::ReservoirComputer, ps, ::Type{T}) where {T}
                 ctx().ptr, Ref(d), Ref(ld), out))
     h = Handle(out[], 0, cell.out_dims)
     finalizer(x -> ccall((:rcb_esn_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
+    kind != 0 && check(ccall((:rcb_esn_set_cell, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Float64, Float64), h.ptr, 0, kind, p0, p1))
     W, Win = ps.reservoir.reservoir_matrix, Matrix{Float32}(ps.reservoir.input_matrix)
     bias = haskey(ps.reservoir, :bias) ? Vector{Float32}(ps.reservoir.bias) : C_NULL
     if W isa SparseMatrixCSC                      # return_sparse=true, ext/RCSparseArraysExt.jl:5-7
@@ -136,6 +144,10 @@ function Handle(rc::ReservoirComputer, ps, ::Type{T}) where {T}
     end
     α isa AbstractVector && check(ccall((:rcb_esn_set_leak_vector, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}),
                                         h.ptr, 0, Vector{Float32}(α)))
+    if kind == 1 || kind == 2                     # ps.reservoir.orthogonal_matrix, es2n_cell.jl:93-104
+        Om = Matrix{Float32}(ps.reservoir.orthogonal_matrix)
+        check(ccall((:rcb_esn_set_orthogonal_dense, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64), h.ptr, 0, Om, size(Om, 1)))
+    end
     F = Ref{Int32}(0)
     check(ccall((:rcb_esn_feature_dims, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), h.ptr, F))
     h.F = F[]
@@ -155,7 +167,7 @@ end
 store_carry(st, h) = merge(st, (reservoir = merge(st.reservoir, (carry = (reshape(h, :, 1),),)),))
 
 # ---- collectstates: src/reservoircomputer.jl:113-133 --------------------------------------------------
-function __collectstates(res::B200Reservoir, rc::ReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
+function __collectstates(res::B200Reservoir, rc::AbstractReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
     size(data, 2) >= 1 || throw(ArgumentError("collectstates data must have at least one column, got 0."))
     h = Handle(rc, ps, T)
     Tn = size(data, 2)
@@ -195,7 +207,7 @@ function set_readout!(h::Handle, ps)
     check(ccall((:rcb_esn_set_readout, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), h.ptr, W, b, 1))
 end
 
-function __predict(res::B200Reservoir, rc::ReservoirComputer, steps::Integer, ps, st; initialdata)
+function __predict(res::B200Reservoir, rc::AbstractReservoirComputer, steps::Integer, ps, st; initialdata)
     steps >= 1 || throw(ArgumentError("steps must be ≥ 1, got $steps"))
     T = eltype(initialdata)
     h = Handle(rc, ps, T); set_readout!(h, ps)
@@ -210,7 +222,7 @@ function __predict(res::B200Reservoir, rc::ReservoirComputer, steps::Integer, ps
     return Matrix{Tc}(Y), store_carry(st, carry)
 end
 
-function __predict(res::B200Reservoir, rc::ReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
+function __predict(res::B200Reservoir, rc::AbstractReservoirComputer, data::AbstractMatrix{T}, ps, st) where {T}
     h = Handle(rc, ps, T); set_readout!(h, ps)
     carry = initial_carry(rc, st, T)
     Y = Matrix{Float64}(undef, rc.readout.out_dims, size(data, 2))
@@ -220,11 +232,13 @@ function __predict(res::B200Reservoir, rc::ReservoirComputer, data::AbstractMatr
 end
 
 """
-    b200(rc::ReservoirComputer) -> ReservoirComputer
+    b200(rc::AbstractReservoirComputer) -> ReservoirComputer
 
-Same model, CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ))`.
+Same model (`ESN`, `ES2N`, `ResESN`, `EuSN` or a hand-built `ReservoirComputer` around one of their cells),
+CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ))`.  `ps` / `st` keep the layout of the
+wrapped model (same field names `reservoir`, `state_modifiers`, `readout`).
 """
-b200(rc::ReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
+b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 
 export B200Reservoir, B200Ridge, b200
 

@@ -72,10 +72,13 @@ SIGNATURES = {
     "rcb_esn_set_weights_dense": (_I32, [_P, _I32, _P, _I64, _P, _I64, _P]),
     "rcb_esn_set_weights_csc": (_I32, [_P, _I32, _P, _P, _P, _P, _I64, _P]),
     "rcb_esn_set_leak_vector": (_I32, [_P, _I32, _P]),
+    "rcb_esn_set_cell": (_I32, [_P, _I32, _I32, _F64, _F64]),
+    "rcb_esn_set_orthogonal_dense": (_I32, [_P, _I32, _P, _I64]),
     "rcb_esn_csr_nnz": (_I32, [_P, _I32, C.POINTER(_I64)]),
     "rcb_esn_export_csr": (_I32, [_P, _I32, _P, _P, _P]),
     "rcb_csr_from_dense": (_I32, [_P, _I64, _I32, C.POINTER(_I64), _P, _P, _P]),
     "rcb_csr_from_csc": (_I32, [_P, _P, _P, _I32, C.POINTER(_I64), _P, _P, _P]),
+    "rcb_eusn_operator_from_dense": (_I32, [_P, _I64, _I32, _F64, C.POINTER(_I64), _P, _P, _P]),
     "rcb_sell_stats_from_dense": (_I32, [_P, _I64, _I32, _I32, _I32, _P]),
     "rcb_esn_set_member_params": (_I32, [_P, _I64, _P, _P]),
     "rcb_esn_set_readout": (_I32, [_P, _P, _P, _I64]),
@@ -93,6 +96,8 @@ SIGNATURES = {
     "rcb_predict_autoregressive": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "rcb_apply_modifiers": (_I32, [_P, _I32, _P, _P, _P, _I32, _I64, _I64, _P]),
 }
+
+CELL_ESN, CELL_ES2N, CELL_RESESN, CELL_EUSN = 0, 1, 2, 3
 
 _lib = None
 

@@ -329,6 +329,79 @@ class ESNCell:
         return NT(cell=NT(rng=copy.deepcopy(rng)), carry=None)
 
 
+def _orthogonal(rng, *dims, gain=1.0):
+    """WeightInitializers.orthogonal (un-vendored; values unpinned upstream): Q of a Gaussian matrix,
+    columns sign-fixed by diag(R)."""
+    n, m = dims
+    q, r = np.linalg.qr(rng.standard_normal((max(n, m), min(n, m))))
+    q = q * np.sign(np.diag(r))
+    q = q if n >= m else q.T
+    return np.asfortranarray((gain * q[:n, :m]).astype(np.float32))
+
+
+orthogonal = _Init(_orthogonal)
+
+
+class _SkipCell(ESNCell):
+    """Cells whose skip path is a dense orthogonal operator: ps gains ``orthogonal_matrix``, drawn after
+    ``reservoir_matrix`` (src/layers/es2n_cell.jl:93-104, src/layers/resesn_cell.jl:100-110)."""
+
+    def __init__(self, in_dims, out_dims, activation=tanh_fast, *, init_orthogonal=orthogonal, **kw):
+        kw.pop("leak_coefficient", None)
+        super().__init__(in_dims, out_dims, activation, **kw)
+        self.init_orthogonal = init_orthogonal
+
+    def initialparameters(self, rng):
+        ps = dict(input_matrix=self.init_input(rng, self.out_dims, self.in_dims),
+                  reservoir_matrix=self.init_reservoir(rng, self.out_dims, self.out_dims),
+                  orthogonal_matrix=self.init_orthogonal(rng, self.out_dims, self.out_dims))
+        if self.use_bias:
+            ps["bias"] = self.init_bias(rng, self.out_dims)
+        return NT(**ps)
+
+
+class ES2NCell(_SkipCell):
+    """src/layers/es2n_cell.jl:66-91: h' = (1-proximity) O h + proximity phi(W_in u + W h + b)."""
+
+    cell_kind = L.CELL_ES2N
+
+    def __init__(self, in_dims, out_dims, activation=tanh_fast, *, proximity=1.0, **kw):
+        super().__init__(in_dims, out_dims, activation, **kw)
+        self.proximity = float(proximity)
+
+    @property
+    def cell_params(self):
+        return (self.proximity, 0.0)
+
+
+class ResESNCell(_SkipCell):
+    """src/layers/resesn_cell.jl:70-98: h' = alpha O h + beta phi(W_in u + W h + b)."""
+
+    cell_kind = L.CELL_RESESN
+
+    def __init__(self, in_dims, out_dims, activation=tanh_fast, *, alpha=1.0, beta=1.0, **kw):
+        super().__init__(in_dims, out_dims, activation, **kw)
+        self.alpha, self.beta = float(alpha), float(beta)
+
+    @property
+    def cell_params(self):
+        return (self.alpha, self.beta)
+
+
+class EuSNCell(ESNCell):
+    """src/layers/eusn_cell.jl:68-93: the leaky ESN step on W - W' - diffusion I (:95-106,120-123)."""
+
+    cell_kind = L.CELL_EUSN
+
+    def __init__(self, in_dims, out_dims, activation=tanh_fast, *, leak_coefficient=1.0, diffusion=1.0, **kw):
+        super().__init__(in_dims, out_dims, activation, leak_coefficient=float(leak_coefficient), **kw)
+        self.diffusion = float(diffusion)
+
+    @property
+    def cell_params(self):
+        return (self.diffusion, 0.0)
+
+
 class LinearReadout:
     """src/layers/basic.jl:129-154."""
 
@@ -361,6 +434,32 @@ class ESN:
     @property
     def layer_modifiers(self):
         return (self.state_modifiers,)
+
+
+class _SingleCellModel(ESN):
+    cell_type = ESNCell
+
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, readout_activation=identity,
+                 state_modifiers=(), **cell_kw):
+        self.reservoir = self.cell_type(in_dims, res_dims, activation, **cell_kw)
+        self.state_modifiers = _as_mods(state_modifiers)
+        self.readout = LinearReadout(res_dims, out_dims, readout_activation)
+        self._cache = {}
+
+
+class ES2N(_SingleCellModel):
+    """src/models/es2n.jl:86-99."""
+    cell_type = ES2NCell
+
+
+class ResESN(_SingleCellModel):
+    """src/models/resesn.jl:89-102."""
+    cell_type = ResESNCell
+
+
+class EuSN(_SingleCellModel):
+    """src/models/eusn.jl:84-97."""
+    cell_type = EuSNCell
 
 
 class DeepESN:
@@ -467,6 +566,9 @@ class _Handle:
         check(lib().rcb_esn_create(dev.handle, C.byref(desc), layers, C.byref(h)))
         self.handle, self.dev, self.keep = h, dev, []
         for i, (c, p) in enumerate(zip(cells, _cell_ps(rc, ps))):
+            kind = getattr(c, "cell_kind", L.CELL_ESN)
+            if kind != L.CELL_ESN:
+                check(lib().rcb_esn_set_cell(h, i, kind, *c.cell_params))
             Win = np.asfortranarray(p.input_matrix, dtype=np.float32)
             bias = np.ascontiguousarray(p.bias, dtype=np.float32) if c.use_bias else None
             W = p.reservoir_matrix
@@ -482,6 +584,9 @@ class _Handle:
             if isinstance(c.leak_coefficient, np.ndarray):
                 lv = np.ascontiguousarray(c.leak_coefficient, dtype=np.float32)
                 check(lib().rcb_esn_set_leak_vector(h, i, ptr(lv)))
+            if kind in (L.CELL_ES2N, L.CELL_RESESN):
+                O = np.asfortranarray(p.orthogonal_matrix, dtype=np.float32)
+                check(lib().rcb_esn_set_orthogonal_dense(h, i, ptr(O), O.shape[0]))
         F, sN = C.c_int32(), C.c_int32()
         check(lib().rcb_esn_feature_dims(h, C.byref(F)))
         check(lib().rcb_esn_carry_dims(h, C.byref(sN)))
@@ -511,7 +616,8 @@ class _Handle:
 def _handle(rc, ps, dtype, dev: Optional[Device] = None) -> _Handle:
     dev = dev or default_device()
     cps = _cell_ps(rc, ps)
-    key = (np.dtype(dtype).str, dev.device) + tuple(id(getattr(p, k)) for p in cps for k in ("input_matrix", "reservoir_matrix"))
+    key = (np.dtype(dtype).str, dev.device) + tuple(id(getattr(p, k)) for p in cps
+                                                   for k in ("input_matrix", "reservoir_matrix", "orthogonal_matrix") if k in p)
     ent = rc._cache.get(key)
     if ent is None:
         ent = (_Handle(rc, ps, dtype, dev), cps)  # keep ps alive so ids are not recycled
@@ -1013,4 +1119,16 @@ def csr_from_matrix(W):
     check(lib().rcb_csr_from_dense(ptr(Wd), n, n, C.byref(nnz), None, None, None))
     rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
     check(lib().rcb_csr_from_dense(ptr(Wd), n, n, C.byref(nnz), ptr(rowptr), ptr(colind), ptr(vals)))
+    return rowptr, colind, vals
+
+
+def eusn_operator_csr(W, diffusion: float):
+    """Host-only (no GPU): canonical CSR of the EuSN operator ``W - W' - diffusion*I`` the kernels are built
+    from (src/layers/eusn_cell.jl:120-123)."""
+    Wd = np.asfortranarray(W.toarray() if hasattr(W, "toarray") else W, dtype=np.float32)
+    n = Wd.shape[0]
+    nnz = C.c_int64()
+    check(lib().rcb_eusn_operator_from_dense(ptr(Wd), n, n, float(diffusion), C.byref(nnz), None, None, None))
+    rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
+    check(lib().rcb_eusn_operator_from_dense(ptr(Wd), n, n, float(diffusion), C.byref(nnz), ptr(rowptr), ptr(colind), ptr(vals)))
     return rowptr, colind, vals

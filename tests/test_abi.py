@@ -135,3 +135,30 @@ def test_setup_structure_and_draw_order(R):
     deep = R.DeepESN(3, [20, 30], 2, state_modifiers=(R.NLAT2,))
     psd, std = R.setup(np.random.default_rng(1), deep)
     assert psd.cells[1].input_matrix.shape == (30, 20) and len(std.cells) == 2
+
+
+# ---- sibling cells: host-side pieces ----------------------------------------------------------------
+@pytest.mark.parametrize("n,k,gamma", [(300, 6, 0.2), (64, 3, 0.0), (128, 128, 1.0)])
+def test_eusn_operator_csr_bit_exact(R, n, k, gamma):  # eusn_cell.jl:120-123, entry by entry in Float32
+    W = O.rand_sparse_like(np.random.default_rng(23), n, radius=0.9, sparsity=k / n)
+    if gamma == 0.0:
+        W[5, 9] = W[9, 5] = 0.25  # a symmetric pair cancels to a structural zero
+    rp, ci, v = R.eusn_operator_csr(W, gamma)
+    A = O.compute_asym_recurrent(W, np.float32(gamma))
+    rp0, ci0, v0 = O.dense_to_csr(A)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+    assert v.tobytes() == v0.astype(np.float32).tobytes()
+
+
+def test_sibling_cell_setup_structure(R):  # es2n_cell.jl:93-104: draw order input, reservoir, orthogonal, bias
+    rc = R.ES2N(3, 20, 2, proximity=0.4, use_bias=True)
+    ps, st = R.setup(np.random.default_rng(4), rc)
+    assert list(ps.reservoir.keys()) == ["input_matrix", "reservoir_matrix", "orthogonal_matrix", "bias"]
+    Om = ps.reservoir.orthogonal_matrix
+    assert Om.shape == (20, 20) and np.allclose(Om.T @ Om, np.eye(20), atol=1e-5)
+    rc = R.ResESN(3, 20, 2, alpha=0.8, beta=0.6)
+    ps, _ = R.setup(np.random.default_rng(4), rc)
+    assert "orthogonal_matrix" in ps.reservoir and "bias" not in ps.reservoir
+    rc = R.EuSN(3, 20, 2, diffusion=0.3, leak_coefficient=0.5)
+    ps, _ = R.setup(np.random.default_rng(4), rc)
+    assert "orthogonal_matrix" not in ps.reservoir and rc.reservoir.cell_params == (0.3, 0.0)

@@ -48,9 +48,17 @@ def oracle_layers(R, rc, ps):
     for c, p, m in zip(rc.cells, cps, rc.layer_modifiers):
         W = p.reservoir_matrix
         W = sp.csr_matrix(W) if (sp.issparse(W) or W.shape[0] > 1500) else np.asarray(W)
+        extra = {}
+        if isinstance(c, R.ES2NCell):
+            extra = dict(cell="es2n", orthogonal_matrix=np.asarray(p.orthogonal_matrix), proximity=c.proximity)
+        elif isinstance(c, R.ResESNCell):
+            extra = dict(cell="resesn", orthogonal_matrix=np.asarray(p.orthogonal_matrix), alpha=c.alpha, beta=c.beta)
+        elif isinstance(c, R.EuSNCell):
+            extra = dict(cell="eusn", diffusion=c.diffusion)
+            W = np.asarray(W.toarray() if sp.issparse(W) else W)
         out.append(O.ESNCellParams(input_matrix=np.asarray(p.input_matrix), reservoir_matrix=W,
                                    bias=np.asarray(p.bias) if c.use_bias else None, leak=c.leak_coefficient,
-                                   act=_act_to_oracle(R, c.activation), modifiers=_mods_to_oracle(m)))
+                                   act=_act_to_oracle(R, c.activation), modifiers=_mods_to_oracle(m), **extra))
     return out
 
 
@@ -622,3 +630,112 @@ def test_gc_pack_roundtrip(R):
     L.check(lib.rcb_gc_unpack(dev.handle, L.ptr(packed), F, D, L.ptr(out)))
     assert np.array_equal(np.tril(out[:, :F]), np.tril(GC[:, :F])) and np.array_equal(out[:, F:], GC[:, F:])
     assert np.count_nonzero(np.triu(out[:, :F], 1)) == 0
+
+
+# ---- sibling cells: ES2N, ResESN, EuSN ------------------------------------------------
+def _sibling_models(R, N, d_in, d_out, use_bias, mods):
+    kw = dict(init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.1), use_bias=use_bias, init_bias=R.randn32, state_modifiers=mods)
+    return {
+        "es2n": R.ES2N(d_in, N, d_out, proximity=0.4, **kw),
+        "resesn": R.ResESN(d_in, N, d_out, alpha=0.8, beta=0.6, **kw),
+        "eusn": R.EuSN(d_in, N, d_out, leak_coefficient=0.6, diffusion=0.2, **kw),
+    }
+
+
+@pytest.mark.parametrize("name", ["es2n", "resesn", "eusn"])
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_sibling_cells_collectstates(R, name, T, use_bias):  # the cells of test/Interface/generic_contracts_tests.jl:47-77
+    N, steps, B = 96, 60, 3
+    rng = np.random.default_rng(5)
+    rc = _sibling_models(R, N, 3, 3, use_bias, (R.NLAT2, R.Pad(1.0)))[name]
+    ps, st = R.setup(rng, rc)
+    data = np.asfortranarray(rng.standard_normal((3, steps, B)).astype(T))
+    h0 = rng.standard_normal((N, B)).astype(T)
+    states, st2 = R.collectstates(rc, data, ps, fixed_h0(R, st, rc, [h0]))
+    assert states.shape == (N + 1, steps, B) and states.dtype == T
+    layers = oracle_layers(R, rc, ps)
+    tol = STATE_RTOL if T == np.float32 else 1e-6  # Float64: gamma and (1-p) cross the ABI as doubles, O / W stay Float32
+    for b in range(B):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= tol
+        assert state_err(st2.reservoir.carry[0][:, b:b + 1], hs[0].reshape(-1, 1)) <= max(tol, STATE_RTOL)
+
+
+def test_sibling_cells_degenerate_to_esn(R):  # the parameter choices of test/collectstates_regression_tests.jl:30-62
+    N, steps = 64, 30
+    rng = np.random.default_rng(11)
+    W = R.rand_sparse(radius=0.9, sparsity=0.1)(rng, N, N)
+    Win = R.scaled_rand(rng, N, 3)
+    Om = R.orthogonal(rng, N, N)
+    kw = dict(init_reservoir=const_init(W), init_input=const_init(Win))
+    data = np.asfortranarray(rng.standard_normal((3, steps)).astype(np.float32))
+    h0 = np.zeros(N, np.float32)
+
+    def run(rc):
+        ps, st = R.setup(np.random.default_rng(0), rc)
+        return R.collectstates(rc, data, ps, fixed_h0(R, st, rc, [h0]))[0]
+
+    esn = run(R.ESN(3, N, 2, leak_coefficient=1.0, **kw))
+    es2n = run(R.ES2N(3, N, 2, proximity=1.0, init_orthogonal=const_init(Om), **kw))   # (1-1) O h + 1 cand
+    res = run(R.ResESN(3, N, 2, alpha=0.0, beta=1.0, init_orthogonal=const_init(Om), **kw))
+    assert state_err(es2n, esn) <= 1e-6 and state_err(res, esn) <= 1e-6
+    Wsym = np.asfortranarray(W + W.T)  # W - W' = 0: EuSN with diffusion 0 is driven by the input alone
+    eusn = run(R.EuSN(3, N, 2, leak_coefficient=1.0, diffusion=0.0, init_reservoir=const_init(Wsym), init_input=const_init(Win)))
+    assert state_err(eusn, np.tanh(Win @ data)) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["es2n", "resesn", "eusn"])
+def test_sibling_cells_train_predict(R, name):
+    N, steps = 80, 300
+    rng = np.random.default_rng(2)
+    rc = _sibling_models(R, N, 3, 3, False, R.NLAT2)[name]
+    ps, st = R.setup(rng, rc)
+    series = O.lorenz_series(steps + 30).astype(np.float32) / 20
+    data, tgt = np.asfortranarray(series[:, :steps]), np.asfortranarray(series[:, 1:steps + 1])
+    h0 = rng.standard_normal(N).astype(np.float32)
+    st = fixed_h0(R, st, rc, [h0])
+    ps2, st2 = R.train(rc, data, tgt, ps, st, objective=R.RidgeRegression(1e-4), washout=20)
+    layers = oracle_layers(R, rc, ps)
+    Wo, hs, _ = O.train(layers, data, tgt, [h0], reg=1e-4, washout=20)
+    assert np.linalg.norm(ps2.readout.weight - Wo) / np.linalg.norm(Wo) <= WEIGHT_RTOL
+    test = np.asfortranarray(series[:, steps:steps + 25])
+    Y, _ = R.predict(rc, test, ps2, st2)                      # teacher-forced
+    Yo, _ = O.predict_teacher(layers, ps2.readout.weight, test, hs)
+    assert state_err(Y, Yo) <= 1e-4
+    Ya, _ = R.predict(rc, 10, ps2, st2, initialdata=test[:, 0])  # autoregressive
+    Yao, _ = O.predict_autoregressive(layers, ps2.readout.weight, 10, test[:, 0], hs)
+    assert state_err(Ya, Yao) <= 1e-3
+
+
+def test_sibling_cell_error_paths(R):
+    import ctypes as C
+    from rcb200 import _lib as L
+
+    dev = R.default_device()
+    desc = L.EsnDesc(1, 2, 2, 0, 0, 0)
+    layers = (L.LayerDesc * 1)()
+    layers[0].res_dims, layers[0].activation, layers[0].leak_scalar = 8, 1, 1.0
+    h = C.c_void_p()
+    L.check(L.lib().rcb_esn_create(dev.handle, C.byref(desc), layers, C.byref(h)))
+    try:
+        with pytest.raises(R.ArgumentError):
+            L.check(L.lib().rcb_esn_set_cell(h, 0, 9, 0.0, 0.0))
+        Om = np.asfortranarray(np.eye(8, dtype=np.float32))
+        with pytest.raises(R.ArgumentError):   # not an ES2N / ResESN layer yet
+            L.check(L.lib().rcb_esn_set_orthogonal_dense(h, 0, L.ptr(Om), 8))
+        L.check(L.lib().rcb_esn_set_cell(h, 0, L.CELL_ES2N, 0.5, 0.0))
+        W = np.asfortranarray(np.eye(8, dtype=np.float32) * 0.5)
+        Win = np.asfortranarray(np.ones((8, 2), np.float32))
+        L.check(L.lib().rcb_esn_set_weights_dense(h, 0, L.ptr(W), 8, L.ptr(Win), 8, None))
+        u = np.zeros((2, 4, 1), np.float32, order="F")
+        out = np.zeros((8, 4, 1), np.float32, order="F")
+        with pytest.raises(R.ArgumentError):   # orthogonal_matrix missing
+            L.check(L.lib().rcb_collect(h, L.ptr(u), 4, 1, None, L.ptr(out), None))
+        with pytest.raises(R.DimensionMismatch):
+            L.check(L.lib().rcb_esn_set_orthogonal_dense(h, 0, L.ptr(Om), 4))
+        L.check(L.lib().rcb_esn_set_orthogonal_dense(h, 0, L.ptr(Om), 8))
+        L.check(L.lib().rcb_collect(h, L.ptr(u), 4, 1, None, L.ptr(out), None))
+        assert np.all(np.isfinite(out))
+    finally:
+        L.lib().rcb_esn_destroy(h)

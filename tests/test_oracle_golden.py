@@ -254,3 +254,48 @@ def test_c_port_matches_numpy_oracle(sparse_form):
         ref, hs = O.collectstates([p], u[:, :, b], [h0[:, b]])
         assert np.allclose(states[:, :, b], ref, rtol=1e-5, atol=1e-6)
         assert np.allclose(hT[:, b], hs[0], rtol=1e-5, atol=1e-6)
+
+
+# ---- sibling cells.  The reference holds no numeric goldens for ES2N / ResESN / EuSN (its tests check
+# shapes, eltypes and dispatch equality, test/collectstates_regression_tests.jl:28-112); the oracle is pinned through
+# the hand-evaluated formulas of src/layers/{es2n,resesn,eusn}_cell.jl and their degenerate ESN limits. ----------------
+def test_eusn_asym_operator_by_hand():  # eusn_cell.jl:120-123
+    W = np.array([[1, 2], [3, 4]], np.float32)
+    A = O.compute_asym_recurrent(W, np.float32(0.5))
+    assert A.dtype == np.float32 and np.array_equal(A, np.array([[-0.5, -1], [1, -0.5]], np.float32))
+    assert O.compute_asym_recurrent(W, np.float64(0.5)).dtype == np.float64  # gamma = T(diffusion) promotes
+
+
+def test_sibling_cells_by_hand():
+    W = np.array([[0, 1], [2, 0]], np.float32)
+    Win = np.eye(2, dtype=np.float32)
+    Om = np.array([[0, 1], [-1, 0]], np.float32)
+    h = np.array([1, 2], np.float32)
+    u = np.array([10, 20], np.float32)
+    cand = u + W @ h  # identity activation: [12, 22]
+    p = O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="es2n", orthogonal_matrix=Om, proximity=0.25)
+    assert np.allclose(O.esn_cell_step(p, u, h), 0.75 * (Om @ h) + 0.25 * cand)      # es2n_cell.jl:113-114
+    p = O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="resesn", orthogonal_matrix=Om, alpha=0.5, beta=2.0)
+    assert np.allclose(O.esn_cell_step(p, u, h), 0.5 * (Om @ h) + 2.0 * cand)         # resesn_cell.jl:121-122
+    p = O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="eusn", leak=0.5, diffusion=1.0)
+    A = np.array([[-1, -1], [1, -1]], np.float32)
+    assert np.allclose(O.esn_cell_step(p, u, h), 0.5 * h + 0.5 * (u + A @ h))         # eusn_cell.jl:100-104
+    # matrix input (batched columns) takes the same path column by column
+    H = np.stack([h, 2 * h], axis=1)
+    U = np.stack([u, u], axis=1)
+    out = O.esn_cell_step(p, U, H)
+    assert np.allclose(out[:, 0], O.esn_cell_step(p, u, h))
+
+
+def test_sibling_cells_degenerate_limits():  # parameter choices of collectstates_regression_tests.jl:30-62
+    rng = np.random.default_rng(0)
+    W = (0.3 * rng.standard_normal((8, 8))).astype(np.float32)
+    Win = (0.5 * rng.standard_normal((8, 3))).astype(np.float32)
+    Om = (0.3 * rng.standard_normal((8, 8))).astype(np.float32)
+    data = rng.standard_normal((3, 20)).astype(np.float32)
+    h0 = [np.zeros(8, np.float32)]
+    esn, _ = O.collectstates([O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, leak=1.0)], data, h0)
+    es2n, _ = O.collectstates([O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="es2n", orthogonal_matrix=Om, proximity=1.0)], data, h0)
+    assert np.array_equal(es2n, esn)
+    res, _ = O.collectstates([O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="resesn", orthogonal_matrix=Om, alpha=0.0, beta=1.0)], data, h0)
+    assert np.array_equal(res, esn)
