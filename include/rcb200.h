@@ -278,6 +278,33 @@ RCB_API int32_t rcb_predict_autoregressive(rcb_esn* esn, const void* u0, int64_t
 RCB_API int32_t rcb_apply_modifiers(rcb_ctx* ctx, int32_t n_modifiers, const int32_t* kinds, const double* params,
                             const void* x, int32_t dtype, int64_t n, int64_t cols, void* out);
 
+/* ---- feature plumbing around the recurrence ----------------------------------------
+ * Extend (src/states.jl:131-145): out[:, c] = vcat(u[:, c], x[:, c]); u d_in x cols, x n x cols, out (d_in+n) x cols. */
+RCB_API int32_t rcb_extend_features(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols,
+                                    int32_t dtype, void* out);
+/* DelayLayer (src/layers/basic.jl:372-433) applied to every column of B sequences in one pass: x is n x T x B,
+ * out ((num_delays+1) n) x T x B with out[:, t, b] = vcat(x[:, t, b], vec(history before step t)).  The buffer shifts
+ * when the layer's call counter `clock` (incremented first) is a multiple of `stride`.  history / history_out:
+ * n x num_delays x B (column j = j-th most recent stored input; NULL in -> zeros, the default init_delay = zeros32;
+ * NULL out -> not returned).  `clock` = st.clock on entry; on exit it is clock + T.
+ * Serves InputDelayESN (delay on the inputs), StateDelayESN and DelayESN (delay on the collected states),
+ * src/models/esn_delay.jl:107-130,276-300,456-490. */
+RCB_API int32_t rcb_delay_features(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int64_t T, int64_t B,
+                                   int32_t num_delays, int32_t stride, const void* history, int64_t clock, void* out,
+                                   void* history_out);
+
+/* LinearReadout applied to a feature matrix (src/layers/basic.jl:171-182): y[:, c] = psi(W z[:, c] + b), W d_out x F Float64,
+ * features F x cols (dtype), y d_out x cols Float64 — the teacher-forced predict of the delay / chain models whose
+ * features are assembled outside K4. */
+RCB_API int32_t rcb_readout_apply(rcb_ctx* ctx, const double* W, const double* bias, int32_t activation, const void* features,
+                                  int32_t dtype, int64_t F, int64_t cols, int64_t d_out, double* y_out);
+
+/* ---- conceptors' correlation: correlation_matrix(states) = (Z Z') / S (src/conceptors.jl:28-33), the
+ * full symmetric F x F matrix in the states' eltype, from the same Gram kernels as the ridge fit (K2).
+ * ridge_map (src/conceptors.jl:639-649) is rcb_fit_readout.  Errors: no states -> RCB_ERR_ARGUMENT (:29). */
+RCB_API int32_t rcb_correlation_matrix(rcb_ctx* ctx, const void* states, int32_t dtype, int64_t F, int64_t S,
+                                       int64_t ld_states, int32_t gram_mode, void* R_out);
+
 #ifdef __cplusplus
 }
 #endif

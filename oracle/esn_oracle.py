@@ -247,6 +247,61 @@ def collectstates(layers: Sequence[ESNCellParams], data: np.ndarray, h0: Sequenc
 
 
 # ----------------------------------------------------------------------------------------------
+# feature plumbing: Extend, DelayLayer, the delay ESNs; conceptors' correlation (8f-4)
+# ----------------------------------------------------------------------------------------------
+def extend(u: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """src/states.jl:138-141 — Extend: vcat(inp, state)."""
+    return np.concatenate([u, x], axis=0)
+
+
+def delay_layer_step(x: np.ndarray, history: np.ndarray, clock: int, stride: int):
+    """One call of DelayLayer, src/layers/basic.jl:426-441: output vcat(inp, vec(history)) with the history as it
+    stood BEFORE the call; then clock += 1 and, when clock % stride == 0, shift the columns and store inp in column 1.
+    ``history``: (n, num_delays), column j = j-th most recent stored input.  Returns (out, history', clock')."""
+    out = np.concatenate([x, history.reshape(-1, order="F")])
+    clock += 1
+    if history.shape[1] > 0 and clock % stride == 0:
+        history = history.copy()
+        history[:, 1:] = history[:, :-1].copy()
+        history[:, 0] = x
+    return out, history, clock
+
+
+def delay_layer_sequence(x: np.ndarray, num_delays: int, stride: int = 1, history=None, clock: int = 0):
+    """DelayLayer over the columns of x (n, T).  history None -> zeros (init_delay = zeros32, basic.jl:395,417-424)."""
+    n, T = x.shape
+    hist = np.zeros((n, num_delays), x.dtype) if history is None else np.array(history, dtype=x.dtype).reshape(n, num_delays)
+    cols = []
+    for t in range(T):
+        o, hist, clock = delay_layer_step(x[:, t], hist, clock, stride)
+        cols.append(o)
+    return np.stack(cols, axis=1), hist, clock
+
+
+def collectstates_delay(layers, data, h0, input_delay=None, state_delay=None, post_mods=()):
+    """InputDelayESN / StateDelayESN / DelayESN, src/models/esn_delay.jl:548-558 (+ the plain __partial_apply for
+    StateDelayESN, whose DelayLayer is simply the first state modifier, :283-296): input delay -> cell -> state delay ->
+    remaining modifiers.  ``input_delay`` / ``state_delay``: (num_delays, stride) or None; ``layers``: one ESNCellParams
+    whose own ``modifiers`` must be empty when a state delay is present."""
+    u = data
+    if input_delay is not None:
+        u, _, _ = delay_layer_sequence(data, *input_delay)
+    z, hs = collectstates(layers, u, h0)
+    if state_delay is not None:
+        z, _, _ = delay_layer_sequence(z, *state_delay)
+        z = apply_modifiers(post_mods, z)
+    return z, hs
+
+
+def correlation_matrix(states: np.ndarray) -> np.ndarray:
+    """src/conceptors.jl:28-33 — (Z Z') / S in float(eltype(states))."""
+    if states.size == 0:
+        raise ArgumentError("states must contain at least one state")
+    Z = states if np.issubdtype(states.dtype, np.floating) else states.astype(np.float64)
+    return (Z @ Z.T) / Z.dtype.type(Z.shape[1])
+
+
+# ----------------------------------------------------------------------------------------------
 # ridge readout fit (src/train.jl)
 # ----------------------------------------------------------------------------------------------
 class ArgumentError(ValueError):

@@ -783,7 +783,7 @@ static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, 
   int32_t st;
   bool cross_done = false;
   if (tensor) {
-    cross_done = d_out <= 8;
+    cross_done = Y && d_out <= 8;
     st = launch_gram_tensor(ctx, (const float*)Z, F, ldz, T, washout, nseq, GC, F, Y, ydt, d_out, ldy,
                             cross_done ? GC + (size_t)F * F : nullptr);
   } else {
@@ -792,7 +792,7 @@ static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, 
     g.T = T; g.washout = washout; g.nseq = nseq; g.out = GC; g.ldo = F; g.lower_only = true;
     st = launch_gram_fp64(ctx, g);
   }
-  if (st == RCB_OK && !cross_done) {
+  if (st == RCB_OK && !cross_done && Y) {
     GramArgs c;
     c.A = Z; c.a_dtype = zdt; c.M = F; c.lda = ldz; c.Bm = Y; c.b_dtype = ydt; c.Nc = d_out; c.ldb = ldy;
     c.T = T; c.washout = washout; c.nseq = nseq; c.out = GC + (size_t)F * F; c.ldo = F; c.lower_only = false;
@@ -1189,6 +1189,95 @@ int32_t rcb_apply_modifiers(rcb_ctx* ctx, int32_t n_modifiers, const int32_t* ki
   if (!is_device_ptr(out)) RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)fout * cols * esz, &o_dev));
   RCB_TRY(launch_modifiers(ctx, c, x_dev, dtype, n, cols, o_dev));
   if (o_dev != out) RCB_TRY(from_device(ctx, out, o_dev, (size_t)fout * cols * esz));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_readout_apply(rcb_ctx* ctx, const double* W, const double* bias, int32_t activation, const void* features,
+                          int32_t dtype, int64_t F, int64_t cols, int64_t d_out, double* y_out) {
+  if (!ctx || !W || !features || !y_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (F < 1 || d_out < 1 || cols < 0) return fail(RCB_ERR_ARGUMENT, "bad dimensions");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const void* z_dev = nullptr;
+  const void* w_dev = nullptr;
+  const void* b_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, features, (size_t)F * cols * esz, &z_dev));
+  RCB_TRY(stage_in(ctx, SCR_W, W, (size_t)F * d_out * sizeof(double), &w_dev));
+  if (bias) RCB_TRY(stage_in(ctx, SCR_INFO, bias, (size_t)d_out * sizeof(double), &b_dev));
+  void* y_dev = y_out;
+  if (!is_device_ptr(y_out)) RCB_TRY(ctx_scratch(ctx, SCR_Y, (size_t)d_out * cols * sizeof(double), &y_dev));
+  RCB_TRY(launch_readout(ctx, (const double*)w_dev, (const double*)b_dev, activation, z_dev, dtype, F, cols, (int)d_out, (double*)y_dev));
+  if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, (size_t)d_out * cols * sizeof(double)));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+// correlation_matrix(states) = (Z Z') / S in float(eltype(states)), src/conceptors.jl:28-33
+int32_t rcb_correlation_matrix(rcb_ctx* ctx, const void* states, int32_t dtype, int64_t F, int64_t S, int64_t ld_states,
+                               int32_t gram_mode, void* R_out) {
+  if (!ctx || !R_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (F < 1 || S < 1 || !states) return fail(RCB_ERR_ARGUMENT, "states must contain at least one state");
+  if (ld_states < F) return fail(RCB_ERR_DIMENSION, "leading dimension smaller than the row count");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const void* Z = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, states, (size_t)ld_states * S * esz, &Z));
+  void* g = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * F * sizeof(double), &g));
+  RCB_CUDA(cudaMemsetAsync(g, 0, (size_t)F * F * sizeof(double), ctx->stream));
+  RCB_TRY(gram_device(ctx, Z, dtype, F, ld_states, nullptr, dtype, 0, 0, S, 0, 1, gram_mode, (double*)g));
+  void* o_dev = R_out;
+  if (!is_device_ptr(R_out)) RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)F * F * esz, &o_dev));
+  RCB_TRY(launch_sym_scale(ctx, (const double*)g, F, 1.0 / (double)S, dtype, o_dev));
+  if (o_dev != R_out) RCB_TRY(from_device(ctx, R_out, o_dev, (size_t)F * F * esz));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_extend_features(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols, int32_t dtype,
+                            void* out) {
+  if (!ctx || !u || !x || !out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (d_in < 1 || n < 1 || cols < 0) return fail(RCB_ERR_ARGUMENT, "bad dimensions");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const void* u_dev = nullptr;
+  const void* x_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)d_in * cols * esz, &u_dev));
+  RCB_TRY(stage_in(ctx, SCR_STATES, x, (size_t)n * cols * esz, &x_dev));
+  void* o_dev = out;
+  if (!is_device_ptr(out)) RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)(d_in + n) * cols * esz, &o_dev));
+  RCB_TRY(launch_extend(ctx, u_dev, d_in, x_dev, n, cols, dtype, o_dev));
+  if (o_dev != out) RCB_TRY(from_device(ctx, out, o_dev, (size_t)(d_in + n) * cols * esz));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_delay_features(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int64_t T, int64_t B, int32_t num_delays,
+                           int32_t stride, const void* history, int64_t clock, void* out, void* history_out) {
+  if (!ctx || !x || !out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (n < 1 || T < 1 || B < 1) return fail(RCB_ERR_ARGUMENT, "bad dimensions");
+  if (num_delays < 0) return fail(RCB_ERR_ARGUMENT, "num_delays must be ≥ 0, got %d", num_delays);
+  if (stride < 1) return fail(RCB_ERR_ARGUMENT, "stride must be ≥ 1, got %d", stride);
+  if (clock < 0) return fail(RCB_ERR_ARGUMENT, "clock must be ≥ 0");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == RCB_F64 ? 8 : 4;
+  const size_t hbytes = (size_t)n * num_delays * B * esz, obytes = (size_t)n * (num_delays + 1) * T * B * esz;
+  const void* x_dev = nullptr;
+  const void* h_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, x, (size_t)n * T * B * esz, &x_dev));
+  if (history && num_delays > 0) RCB_TRY(stage_in(ctx, SCR_H, history, hbytes, &h_dev));
+  void* o_dev = out;
+  if (!is_device_ptr(out)) RCB_TRY(ctx_scratch(ctx, SCR_TMP, obytes, &o_dev));
+  void* ho_dev = nullptr;
+  if (history_out && num_delays > 0) {
+    ho_dev = history_out;
+    if (!is_device_ptr(history_out)) RCB_TRY(ctx_scratch(ctx, SCR_HT, hbytes, &ho_dev));
+  }
+  RCB_TRY(launch_delay(ctx, x_dev, dtype, n, T, B, num_delays, stride, h_dev, clock, o_dev, ho_dev));
+  if (o_dev != out) RCB_TRY(from_device(ctx, out, o_dev, obytes));
+  if (ho_dev && ho_dev != history_out) RCB_TRY(from_device(ctx, history_out, ho_dev, hbytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
 }

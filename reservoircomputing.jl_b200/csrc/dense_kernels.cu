@@ -200,6 +200,134 @@ int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out,
   return RCB_OK;
 }
 
+// ---- feature plumbing ------------------------------------------------------------------
+// R = (lower triangle of G mirrored) * scale, written in the states' eltype: correlation_matrix, src/conceptors.jl:28-33
+template <typename T>
+__global__ void __launch_bounds__(256) sym_scale_kernel(const double* __restrict__ G, long long F, double scale, T* __restrict__ out) {
+  const long long total = F * F;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const long long i = k % F, j = k / F;
+    const long long r = i > j ? i : j, c = i > j ? j : i;
+    out[k] = (T)(G[(size_t)c * F + r] * scale);
+  }
+}
+
+int32_t launch_sym_scale(rcb_ctx* ctx, const double* G, int64_t F, double scale, int32_t dtype, void* out) {
+  const int grid = 4 * ctx->sm_count;
+  if (dtype == RCB_F64) sym_scale_kernel<double><<<grid, 256, 0, ctx->stream>>>(G, F, scale, (double*)out);
+  else sym_scale_kernel<float><<<grid, 256, 0, ctx->stream>>>(G, F, scale, (float*)out);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// Extend (src/states.jl:131-145): out[:, c] = vcat(u[:, c], x[:, c])
+template <typename T>
+__global__ void __launch_bounds__(256) extend_kernel(const T* __restrict__ u, long long d_in, const T* __restrict__ x, long long n,
+                                                     long long cols, T* __restrict__ out) {
+  const long long f = d_in + n;
+  for (long long c = blockIdx.x; c < cols; c += gridDim.x)
+    for (long long i = threadIdx.x; i < f; i += blockDim.x)
+      out[(size_t)c * f + i] = i < d_in ? u[(size_t)c * d_in + i] : x[(size_t)c * n + (i - d_in)];
+}
+
+int32_t launch_extend(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols, int32_t dtype, void* out) {
+  if (cols <= 0) return RCB_OK;
+  const int grid = (int)(cols < 16LL * ctx->sm_count ? cols : 16LL * ctx->sm_count);
+  if (dtype == RCB_F64) extend_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)u, d_in, (const double*)x, n, cols, (double*)out);
+  else extend_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)u, d_in, (const float*)x, n, cols, (float*)out);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// DelayLayer (src/layers/basic.jl:372-433) unrolled over time: at the step with clock value c (1-based count of calls)
+// the output is vcat(x_c, history) with the history BEFORE this step's update; the buffer shifts only when
+// c % stride == 0.  Hence block j (1-based) of step k (local, 1-based; clock c = clock0 + k) is the input of the step
+// with clock stride*(floor((c-1)/stride) - j + 1) when that step lies inside this call, else column j - q of the
+// incoming history (q = stores made before step k within this call).  The same rule evaluated at k = T + 1 gives the
+// outgoing history.
+template <typename T>
+__global__ void __launch_bounds__(256) delay_kernel(const T* __restrict__ x, long long n, long long Tn, long long B, int D, int stride,
+                                                    const T* __restrict__ hist, long long clock0, T* __restrict__ out,
+                                                    T* __restrict__ hist_out) {
+  const long long fo = (long long)(D + 1) * n;
+  const long long steps = Tn + (hist_out ? 1 : 0);
+  for (long long cb = blockIdx.x; cb < steps * B; cb += gridDim.x) {
+    const long long b = cb / steps, k = cb % steps + 1;  // k = Tn + 1: the outgoing history
+    const long long c = clock0 + k;
+    const long long q = (c - 1) / stride - clock0 / stride;
+    const bool fin = k == Tn + 1;
+    T* o = fin ? hist_out + (size_t)b * n * D - n : out + ((size_t)b * Tn + (k - 1)) * fo;  // block j lands at o + j*n
+    const T* xb = x + (size_t)b * Tn * n;
+    if (!fin)
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) o[i] = xb[(size_t)(k - 1) * n + i];
+    for (int j = 1; j <= D; ++j) {
+      const T* src;
+      if (j <= q) {
+        const long long m = (long long)stride * ((c - 1) / stride - j + 1);  // clock of the stored step
+        src = xb + (size_t)(m - clock0 - 1) * n;
+      } else {
+        src = hist ? hist + ((size_t)b * D + (j - q - 1)) * n : nullptr;
+      }
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) o[(size_t)j * n + i] = src ? src[i] : T(0);
+    }
+  }
+}
+
+int32_t launch_delay(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int64_t T, int64_t B, int32_t D, int32_t stride,
+                     const void* hist, int64_t clock0, void* out, void* hist_out) {
+  const long long work = (T + (hist_out ? 1 : 0)) * B;
+  if (work <= 0) return RCB_OK;
+  const int grid = (int)(work < 16LL * ctx->sm_count ? work : 16LL * ctx->sm_count);
+  if (dtype == RCB_F64)
+    delay_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)x, n, T, B, D, stride, (const double*)hist, clock0, (double*)out, (double*)hist_out);
+  else
+    delay_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)x, n, T, B, D, stride, (const float*)hist, clock0, (float*)out, (float*)hist_out);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// LinearReadout over a feature matrix (src/layers/basic.jl:171-182): Y[:, c] = psi(W Z[:, c] + b), Float64 accumulate.
+// One CTA per column, one warp per output row (strided).
+template <typename T>
+__global__ void __launch_bounds__(256) readout_kernel(const double* __restrict__ W, const double* __restrict__ bias, int act,
+                                                      const T* __restrict__ Z, long long F, long long cols, int d_out,
+                                                      double* __restrict__ Y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (long long c = blockIdx.x; c < cols; c += gridDim.x) {
+    const T* z = Z + (size_t)c * F;
+    for (int o = warp; o < d_out; o += nw) {
+      double acc = 0.0;
+      for (long long f = lane; f < F; f += 32) acc = fma(W[(size_t)f * d_out + o], (double)z[f], acc);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+      if (lane == 0) {
+        if (bias) acc += bias[o];
+        switch (act) {
+          case RCB_ACT_TANH: case RCB_ACT_TANH_FAST: acc = tanh(acc); break;
+          case RCB_ACT_SIGMOID: acc = 1.0 / (1.0 + exp(-acc)); break;
+          case RCB_ACT_RELU: acc = acc > 0.0 ? acc : 0.0; break;
+          default: break;
+        }
+        Y[(size_t)c * d_out + o] = acc;
+      }
+    }
+  }
+}
+
+int32_t launch_readout(rcb_ctx* ctx, const double* W, const double* bias, int act, const void* Z, int32_t dtype, int64_t F,
+                       int64_t cols, int d_out, double* Y) {
+  if (cols <= 0) return RCB_OK;
+  const int grid = (int)(cols < 16LL * ctx->sm_count ? cols : 16LL * ctx->sm_count);
+  if (dtype == RCB_F64) readout_kernel<double><<<grid, 256, 0, ctx->stream>>>(W, bias, act, (const double*)Z, F, cols, d_out, Y);
+  else readout_kernel<float><<<grid, 256, 0, ctx->stream>>>(W, bias, act, (const float*)Z, F, cols, d_out, Y);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
 // ---- generic modifier chain, one column per CTA iteration ---------------------------------------
 struct ModParams {
   int n_mod;

@@ -235,6 +235,14 @@ int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out,
 int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
                            double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C);
 
+// feature plumbing (dense_kernels.cu): symmetric fill + scale of a lower-triangle Gram, Extend, DelayLayer over time
+int32_t launch_sym_scale(rcb_ctx* ctx, const double* G, int64_t F, double scale, int32_t dtype, void* out);
+int32_t launch_extend(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols, int32_t dtype, void* out);
+int32_t launch_readout(rcb_ctx* ctx, const double* W, const double* bias, int act, const void* Z, int32_t dtype, int64_t F,
+                       int64_t cols, int d_out, double* Y);
+int32_t launch_delay(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int64_t T, int64_t B, int32_t D, int32_t stride,
+                     const void* hist, int64_t clock0, void* out, void* hist_out);
+
 // (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
 // the same for nsys systems stored back to back, one launch sequence (lambdas: host array or nullptr -> lambda0 for all)

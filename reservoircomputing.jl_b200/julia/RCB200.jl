@@ -231,6 +231,45 @@ function __predict(res::B200Reservoir, rc::AbstractReservoirComputer, data::Abst
     return Matrix{promote_type(T, eltype(ps.readout.weight))}(Y), store_carry(st, carry)
 end
 
+# ---- feature plumbing + conceptor blocks (SURVEY 8f-2 / 8f-4) ------------------------------------------------
+# The delay ESNs (src/models/esn_delay.jl) compose these around rcb_collect exactly like rcb200/api.py:_collect_delay:
+#   input DelayLayer -> rcb_collect (cell) -> state DelayLayer -> remaining modifiers (rcb_apply_modifiers).
+"""
+    delay_features(x, num_delays, stride; history = nothing, clock = 0) -> (out, history′, clock′)
+
+All `size(x, 2)` calls of a `DelayLayer` (src/layers/basic.jl:426-441) in one pass on the GPU.
+"""
+function delay_features(x::Matrix{T}, num_delays::Integer, stride::Integer; history = nothing, clock::Integer = 0) where {T}
+    n, Tn = size(x)
+    out = Matrix{T}(undef, n * (num_delays + 1), Tn)
+    hout = Matrix{T}(undef, n, num_delays)
+    hin = history === nothing ? C_NULL : Matrix{T}(history)
+    check(ccall((:rcb_delay_features, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx().ptr, x, dtype_id(T), n, Tn, 1, num_delays, stride, hin, clock, out, num_delays > 0 ? hout : C_NULL))
+    return out, hout, clock + Tn
+end
+
+"""`extend_features(u, x)` = `vcat(u, x)` column by column — `Extend`, src/states.jl:138-141."""
+function extend_features(u::Matrix{T}, x::Matrix{T}) where {T}
+    size(u, 2) == size(x, 2) || throw(DimensionMismatch("Extend: $(size(u, 2)) input columns, $(size(x, 2)) state columns"))
+    out = Matrix{T}(undef, size(u, 1) + size(x, 1), size(x, 2))
+    check(ccall((:rcb_extend_features, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}),
+                ctx().ptr, u, size(u, 1), x, size(x, 1), size(x, 2), dtype_id(T), out))
+    return out
+end
+
+"""`correlation_matrix_b200(states)` = `(states * states') / size(states, 2)` — src/conceptors.jl:28-33 on the K2 Gram kernels."""
+function correlation_matrix_b200(states::AbstractMatrix{<:Real})
+    isempty(states) && throw(ArgumentError("states must contain at least one state"))
+    T = float(eltype(states)) === Float32 ? Float32 : Float64
+    Z = Matrix{T}(states)
+    R = Matrix{T}(undef, size(Z, 1), size(Z, 1))
+    check(ccall((:rcb_correlation_matrix, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Int32, Ptr{Cvoid}),
+                ctx().ptr, Z, dtype_id(T), size(Z, 1), size(Z, 2), size(Z, 1), 0, R))
+    return R
+end
+
 """
     b200(rc::AbstractReservoirComputer) -> ReservoirComputer
 
@@ -240,6 +279,6 @@ wrapped model (same field names `reservoir`, `state_modifiers`, `readout`).
 """
 b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 
-export B200Reservoir, B200Ridge, b200
+export B200Reservoir, B200Ridge, b200, delay_features, extend_features, correlation_matrix_b200
 
 end # module

@@ -514,6 +514,8 @@ def _is_deep(rc) -> bool:
 
 def setup(rng: np.random.Generator, rc):
     """LuxCore.setup(rng, model) -> (ps, st).  src/reservoircomputer.jl:51-63, esn_deep.jl:156-188."""
+    if isinstance(rc, _DelayModel):
+        return _setup_delay(rng, rc)
     if _is_deep(rc):
         ps_cells = tuple(c.initialparameters(rng) for c in rc.cells)
         ps = NT(cells=ps_cells, state_modifiers=tuple(() for _ in rc.cells), readout=rc.readout.initialparameters(rng))
@@ -667,18 +669,12 @@ def _as3d(data):
 def collectstates(rc, data, ps, st, device: Optional[Device] = None):
     """states (F, T[, B]) with eltype(data), and the new st (final carry stored).
     src/reservoircomputer.jl:96-133, src/models/esn_deep.jl:261-291."""
+    if isinstance(rc, _DelayModel):
+        return _collect_delay(rc, data, ps, st, device)
     d3, vec = _as3d(data)
     if d3.shape[1] < 1:
         raise ArgumentError(f"collectstates data must have at least one column, got {d3.shape[1]}.")
-    dtype = d3.dtype
-    h = _handle(rc, ps, dtype, device)
-    _, T, B = d3.shape
-    h0, cell_sts = _initial_carry(rc, st, dtype, B)
-    states = np.empty((h.F, T, B), dtype=dtype, order="F")
-    hT = np.empty((h.sumN, B), dtype=dtype, order="F")
-    check(lib().rcb_collect(h.handle, ptr(d3), T, B, ptr(h0), ptr(states), ptr(hT)))
-    st2 = _store_carry(rc, st, cell_sts, hT, vec)
-    return (states[:, :, 0] if vec else states), st2
+    return collectstates_core(rc, data, ps, st, device)
 
 
 class RidgeRegression:
@@ -773,6 +769,19 @@ def train(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = N
     -> (ps, st) or ((ps, st), states_wo).  src/train.jl:232-251."""
     objective = objective or RidgeRegression(0.0)
     _check_solver(solver)
+    if isinstance(rc, _DelayModel):  # train.jl:240-250 step by step: the features are assembled outside the fused rcb_train
+        states, st2 = collectstates(rc, train_data, ps, st, device)
+        tgt = np.asarray(target_data)
+        if washout < 0:
+            raise ArgumentError(f"washout must be ≥ 0, got {washout}")
+        if washout >= states.shape[1]:
+            raise ArgumentError(f"washout={washout} is ≥ number of time steps={states.shape[1]}")
+        sw, tw = states[:, washout:], tgt[:, washout:]
+        if sw.ndim == 3:  # pooled over the sequences
+            sw, tw = sw.reshape(sw.shape[0], -1, order="F"), tw.reshape(tw.shape[0], -1, order="F")
+        W = fit_readout(objective, sw, tw, device=device, gram_mode=gram_mode)
+        ps2, st2 = addreadout(rc, W, ps, st2)
+        return ((ps2, st2), states[:, washout:]) if return_states else (ps2, st2)
     d3, vec = _as3d(train_data)
     y3, _ = _as3d(target_data)
     if y3.dtype not in (np.float32, np.float64):
@@ -1023,6 +1032,14 @@ def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Dev
     predict(rc, data::AbstractMatrix, ps, st) — teacher-forced (:90-103,163-177).
     Returns (outputs (d_out, T[, B]), st)."""
     Wro = np.asarray(ps.readout.weight)
+    if isinstance(rc, _DelayModel):
+        if isinstance(steps_or_data, (int, np.integer)):
+            raise L.UnsupportedError("autoregressive predict of the delay ESNs stays on the reference path "
+                                     "(the delay lines are assembled outside the fused predict kernel)")
+        if np.asarray(steps_or_data).shape[1] < 1:
+            raise ArgumentError("predict data must have at least one column, got 0.")
+        z, st2 = collectstates(rc, steps_or_data, ps, st, device)  # y_t = readout(features_t), predict.jl:163-177
+        return readout_apply(rc.readout, ps.readout, z, device), st2
     if isinstance(steps_or_data, (int, np.integer)):
         steps = int(steps_or_data)
         if initialdata is None:
@@ -1132,3 +1149,195 @@ def eusn_operator_csr(W, diffusion: float):
     rowptr, colind, vals = np.empty(n + 1, np.int64), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float32)
     check(lib().rcb_eusn_operator_from_dense(ptr(Wd), n, n, float(diffusion), C.byref(nnz), ptr(rowptr), ptr(colind), ptr(vals)))
     return rowptr, colind, vals
+
+
+# ---- feature plumbing around the recurrence: Extend, DelayLayer, the delay ESNs ------------------------
+def extend_features(u, x, device: Optional[Device] = None):
+    """``vcat(u, x)`` column by column on the GPU — Extend, src/states.jl:131-145.  u (d_in, T[, B]), x (n, T[, B])."""
+    dev = device or default_device()
+    u3, vec = _as3d(u)
+    x3, _ = _as3d(x)
+    if u3.shape[1:] != x3.shape[1:]:
+        raise DimensionMismatch(f"Extend: input has {u3.shape[1:]} columns, state has {x3.shape[1:]}")
+    dt = np.promote_types(u3.dtype, x3.dtype)
+    u3, x3 = np.asfortranarray(u3, dtype=dt), np.asfortranarray(x3, dtype=dt)
+    out = np.empty((u3.shape[0] + x3.shape[0],) + x3.shape[1:], dtype=dt, order="F")
+    check(lib().rcb_extend_features(dev.handle, ptr(u3), u3.shape[0], ptr(x3), x3.shape[0], x3.shape[1] * x3.shape[2],
+                                    L.dtype_id(dt), ptr(out)))
+    return out[:, :, 0] if vec else out
+
+
+class DelayLayer:
+    """DelayLayer(in_dims; num_delays = 2, stride = 1, init_delay = zeros32) — src/layers/basic.jl:372-404."""
+
+    def __init__(self, in_dims, *, num_delays=2, stride=1, init_delay=zeros32):
+        if isinstance(init_delay, tuple):
+            if len(init_delay) != num_delays:
+                raise DimensionMismatch(f"init_delay tuple must have length num_delays={num_delays}, got {len(init_delay)}.")
+        else:
+            init_delay = tuple(init_delay for _ in range(num_delays))
+        self.in_dims, self.num_delays, self.stride, self.init_delay = int(in_dims), int(num_delays), int(stride), init_delay
+
+    def initialparameters(self, rng):
+        return NT()
+
+    def initialstates(self, rng):  # basic.jl:410-415
+        return NT(history=None, clock=0, rng=copy.deepcopy(rng))
+
+    def apply_sequence(self, x, st, device: Optional[Device] = None):
+        """All T calls of the layer at once (rcb_delay_features): x (in_dims, T[, B]) -> ((num_delays+1) in_dims, T[, B]), st'."""
+        dev = device or default_device()
+        x3, vec = _as3d(x)
+        n, T, B = x3.shape
+        if n != self.in_dims:
+            raise DimensionMismatch(f"DelayLayer expected input with {self.in_dims} rows, got {n}.")
+        D = self.num_delays
+        hist = st.history
+        if hist is None and D > 0:  # init_delay_history, basic.jl:417-424: one draw per delay column
+            rng = st.rng
+            cols = [np.asarray(f(rng, n, 1), dtype=x3.dtype).reshape(n) for f in self.init_delay]
+            hist = np.repeat(np.stack(cols, axis=1)[:, :, None], B, axis=2)
+        hist = None if D == 0 else np.asfortranarray(np.asarray(hist, dtype=x3.dtype).reshape(n, D, -1))
+        out = np.empty(((D + 1) * n, T, B), dtype=x3.dtype, order="F")
+        hout = None if D == 0 else np.empty((n, D, B), dtype=x3.dtype, order="F")
+        check(lib().rcb_delay_features(dev.handle, ptr(x3), L.dtype_id(x3.dtype), n, T, B, D, self.stride, ptr(hist),
+                                       int(st.clock), ptr(out), ptr(hout)))
+        new_hist = None if D == 0 else (hout[:, :, 0] if vec else hout)
+        return (out[:, :, 0] if vec else out), st.merge(history=new_hist, clock=int(st.clock) + T)
+
+
+class _DelayModel:
+    """InputDelayESN / StateDelayESN / DelayESN (src/models/esn_delay.jl:107-130,276-300,456-490): an ESNCell with a
+    DelayLayer on its input and / or as the first state modifier.  The recurrence runs through rcb_collect, the delay
+    lines through rcb_delay_features, the remaining modifiers through rcb_apply_modifiers."""
+
+    def __init__(self, in_dims, res_dims, out_dims, activation, n_in, s_in, n_st, s_st, readout_activation, state_modifiers,
+                 cell_kw):
+        self.input_delay = DelayLayer(in_dims, num_delays=n_in, stride=s_in) if n_in is not None else None
+        aug = in_dims * ((n_in or 0) + 1)
+        self.reservoir = ESNCell(aug, res_dims, activation, **cell_kw)
+        self.state_delay = DelayLayer(res_dims, num_delays=n_st, stride=s_st) if n_st is not None else None
+        self.state_modifiers = _as_mods(state_modifiers)  # the modifiers AFTER the state delay
+        fdim = res_dims * ((n_st or 0) + 1)
+        self.readout = LinearReadout(fdim, out_dims, readout_activation)
+        self._cache = {}
+
+    # the recurrence core: the same cell without modifiers (they act after the delay line)
+    @property
+    def cells(self):
+        return (self.reservoir,)
+
+    @property
+    def layer_modifiers(self):
+        return ((),) if self.state_delay is not None else (self.state_modifiers,)
+
+
+class InputDelayESN(_DelayModel):
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, num_delays=2, stride=1, readout_activation=identity,
+                 state_modifiers=(), **kw):
+        super().__init__(in_dims, res_dims, out_dims, activation, num_delays, stride, None, None, readout_activation,
+                         state_modifiers, kw)
+
+
+class StateDelayESN(_DelayModel):
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, num_delays=2, stride=1, readout_activation=identity,
+                 state_modifiers=(), **kw):
+        super().__init__(in_dims, res_dims, out_dims, activation, None, None, num_delays, stride, readout_activation,
+                         state_modifiers, kw)
+
+
+class DelayESN(_DelayModel):
+    def __init__(self, in_dims, res_dims, out_dims, activation=tanh, *, num_input_delays=1, input_stride=1,
+                 num_state_delays=1, state_stride=1, readout_activation=identity, state_modifiers=(), **kw):
+        super().__init__(in_dims, res_dims, out_dims, activation, num_input_delays, input_stride, num_state_delays,
+                         state_stride, readout_activation, state_modifiers, kw)
+
+
+def _setup_delay(rng, rc):  # esn_delay.jl:529-546; StateDelayESN keeps the plain layout with the delay as modifier 1
+    ps = dict(reservoir=rc.reservoir.initialparameters(rng))
+    st = dict(reservoir=rc.reservoir.initialstates(rng))
+    if rc.input_delay is not None:
+        ps = dict(input_delay=NT(), **ps)
+        st = dict(input_delay=rc.input_delay.initialstates(rng), **st)
+    nmods = len(rc.state_modifiers) + (1 if rc.state_delay is not None else 0)
+    ps["state_modifiers"] = tuple(NT() for _ in range(nmods))
+    mst = [NT() for _ in range(nmods)]
+    if rc.state_delay is not None:
+        mst[0] = rc.state_delay.initialstates(rng)
+    st["state_modifiers"] = tuple(mst)
+    ps["readout"] = rc.readout.initialparameters(rng)
+    st["readout"] = NT()
+    return NT(**ps), NT(**st)
+
+
+def _collect_delay(rc, data, ps, st, device):
+    dev = device or default_device()
+    u = np.asarray(data)
+    if u.shape[1] < 1:
+        raise ArgumentError(f"collectstates data must have at least one column, got {u.shape[1]}.")
+    st2 = st
+    if rc.input_delay is not None:
+        u, dst = rc.input_delay.apply_sequence(u, st.input_delay, dev)
+        st2 = st2.merge(input_delay=dst)
+    z, st_core = collectstates_core(rc, u, ps, st2, dev)
+    st2 = st_core
+    if rc.state_delay is not None:
+        z, dst = rc.state_delay.apply_sequence(z, st.state_modifiers[0], dev)
+        st2 = st2.merge(state_modifiers=(dst,) + tuple(st.state_modifiers[1:]))
+        if rc.state_modifiers:
+            z = apply_modifiers(rc.state_modifiers, z, dev)
+    return z, st2
+
+
+def collectstates_core(rc, data, ps, st, device=None):
+    """rcb_collect for the model's cell (+ the modifiers K1 fuses) — shared by the plain and the delay models."""
+    d3, vec = _as3d(data)
+    dtype = d3.dtype
+    h = _handle(rc, ps, dtype, device)
+    _, T, B = d3.shape
+    h0, cell_sts = _initial_carry(rc, st, dtype, B)
+    states = np.empty((h.F, T, B), dtype=dtype, order="F")
+    hT = np.empty((h.sumN, B), dtype=dtype, order="F")
+    check(lib().rcb_collect(h.handle, ptr(d3), T, B, ptr(h0), ptr(states), ptr(hT)))
+    return (states[:, :, 0] if vec else states), _store_carry(rc, st, cell_sts, hT, vec)
+
+
+def readout_apply(ro: LinearReadout, ps_ro, features, device: Optional[Device] = None):
+    """y = psi(W z + b) for every column (src/layers/basic.jl:171-182) on the GPU; Float64 result cast to the promoted eltype."""
+    dev = device or default_device()
+    z3, vec = _as3d(features)
+    F, T, B = z3.shape
+    W = np.asfortranarray(ps_ro.weight, dtype=np.float64)
+    if W.shape[1] != F:
+        raise DimensionMismatch(f"readout weight has {W.shape[1]} columns but the model produces {F} features")
+    b = np.ascontiguousarray(ps_ro.bias, dtype=np.float64) if ro.use_bias else None
+    y = np.empty((W.shape[0], T, B), dtype=np.float64, order="F")
+    check(lib().rcb_readout_apply(dev.handle, ptr(W), ptr(b), _act_id(ro.activation), ptr(z3), L.dtype_id(z3.dtype), F, T * B,
+                                  W.shape[0], ptr(y)))
+    y = y.astype(np.promote_types(z3.dtype, np.asarray(ps_ro.weight).dtype))
+    return y[:, :, 0] if vec else y
+
+
+# ---- conceptors' building blocks (SURVEY 8f-4) ------------------------------------------------------------------------
+def correlation_matrix(states, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+    """correlation_matrix(states) = (Z Z') / S in float(eltype(states)) — src/conceptors.jl:28-33, on the K2 Gram kernels."""
+    Z = np.asarray(states)
+    if Z.size == 0:
+        raise ArgumentError("states must contain at least one state")
+    if Z.dtype not in (np.float32, np.float64):
+        Z = Z.astype(np.float64)
+    Z = np.asfortranarray(Z)
+    dev = device or default_device()
+    F, S = Z.shape
+    R = np.empty((F, F), dtype=Z.dtype, order="F")
+    check(lib().rcb_correlation_matrix(dev.handle, ptr(Z), L.dtype_id(Z.dtype), F, S, F, gram_mode, ptr(R)))
+    return R
+
+
+def ridge_map(features, targets, reg, device: Optional[Device] = None):
+    """ridge_map (src/conceptors.jl:639-649): __fit_readout(RidgeRegression(element_type, reg), features, targets)."""
+    f, t = np.asarray(features), np.asarray(targets)
+    et = np.promote_types(f.dtype, t.dtype)
+    if not np.issubdtype(et, np.floating):
+        et = np.dtype(np.float64)
+    return fit_readout(RidgeRegression(et, reg), f.astype(et), t.astype(et), device=device)

@@ -739,3 +739,110 @@ def test_sibling_cell_error_paths(R):
         assert np.all(np.isfinite(out))
     finally:
         L.lib().rcb_esn_destroy(h)
+
+
+# ---- feature plumbing and conceptor blocks (8f-4) ---------------------------------------
+def test_delay_layer_goldens_gpu(R):  # test/basic_tests.jl:204-246
+    dl = R.DelayLayer(1, num_delays=2, stride=1)
+    st = dl.initialstates(np.random.default_rng(0))
+    x = np.arange(1, 7, dtype=np.float32)[None, :]
+    out, st2 = dl.apply_sequence(x[:, :5], st)
+    assert np.array_equal(out.T, [[1, 0, 0], [2, 1, 0], [3, 2, 1], [4, 3, 2], [5, 4, 3]])
+    assert st2.clock == 5 and np.array_equal(st2.history, [[5, 4]])
+    dl2 = R.DelayLayer(1, num_delays=2, stride=2)
+    out, st2 = dl2.apply_sequence(x[:, :4], dl2.initialstates(np.random.default_rng(0)))
+    assert np.array_equal(out.T, [[1, 0, 0], [2, 0, 0], [3, 2, 0], [4, 2, 0]])
+    with pytest.raises(R.DimensionMismatch):
+        dl.apply_sequence(np.zeros((2, 3), np.float32), st)  # :248-255
+
+
+@pytest.mark.parametrize("D,stride,T1,T2", [(2, 1, 7, 5), (3, 2, 5, 8), (1, 3, 4, 9), (4, 5, 3, 30), (0, 1, 3, 2)])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_delay_layer_matches_oracle_and_resumes(R, D, stride, T1, T2, dt):
+    n, B = 5, 3
+    rng = np.random.default_rng(D * 10 + stride)
+    x = np.asfortranarray(rng.standard_normal((n, T1 + T2, B)).astype(dt))
+    inits = tuple((lambda r, d, b, k=k: np.full((d, b), k + 1.0, np.float32)) for k in range(D))
+    dl = R.DelayLayer(n, num_delays=D, stride=stride, init_delay=inits)
+    st = dl.initialstates(rng)
+    o1, st1 = dl.apply_sequence(x[:, :T1], st)       # two calls: history and clock carry over exactly
+    o2, st2 = dl.apply_sequence(x[:, T1:], st1)
+    out = np.concatenate([o1, o2], axis=1)
+    h0 = np.stack([np.full(n, k + 1.0) for k in range(D)], axis=1) if D else None
+    for b in range(B):
+        ref, hist, clock = O.delay_layer_sequence(x[:, :, b], D, stride, history=h0)
+        assert np.array_equal(out[:, :, b], ref)      # pure data movement: bit-exact
+        if D:
+            assert np.array_equal(st2.history[:, :, b], hist)
+    assert st2.clock == T1 + T2 and out.dtype == dt
+
+
+def test_extend_features_gpu(R):
+    rng = np.random.default_rng(1)
+    u = np.asfortranarray(rng.standard_normal((3, 11, 4)).astype(np.float32))
+    x = np.asfortranarray(rng.standard_normal((17, 11, 4)).astype(np.float32))
+    assert np.array_equal(R.extend_features(u, x), np.concatenate([u, x], axis=0))
+    assert np.array_equal(R.extend_features(u[:, :, 0].astype(np.float64), x[:, :, 0].astype(np.float64)),
+                          O.extend(u[:, :, 0], x[:, :, 0]).astype(np.float64))
+
+
+@pytest.mark.parametrize("kind", ["input", "state", "both"])
+def test_delay_esn_models(R, kind):  # src/models/esn_delay.jl
+    N, T = 60, 80
+    rng = np.random.default_rng(8)
+    kw = dict(init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.1), leak_coefficient=0.7)
+    if kind == "input":
+        rc = R.InputDelayESN(3, N, 3, num_delays=2, stride=2, state_modifiers=R.NLAT2, **kw)
+        idl, sdl, post = (2, 2), None, ()
+    elif kind == "state":
+        rc = R.StateDelayESN(3, N, 3, num_delays=2, stride=1, state_modifiers=(R.NLAT2, R.Pad(1.0)), **kw)
+        idl, sdl, post = None, (2, 1), ((O.MOD_NLAT2, 0.0), (O.MOD_PAD, 1.0))
+    else:
+        rc = R.DelayESN(3, N, 3, num_input_delays=1, input_stride=1, num_state_delays=2, state_stride=3, **kw)
+        idl, sdl, post = (1, 1), (2, 3), ()
+    ps, st = R.setup(rng, rc)
+    assert ps.reservoir.input_matrix.shape == (N, 3 * ((idl[0] if idl else 0) + 1))
+    series = O.lorenz_series(T + 20).astype(np.float32) / 20
+    data, tgt = np.asfortranarray(series[:, :T]), np.asfortranarray(series[:, 1:T + 1])
+    h0 = rng.standard_normal(N).astype(np.float32)
+    st = fixed_h0(R, st, rc, [h0])
+    states, st2 = R.collectstates(rc, data, ps, st)
+    layers = oracle_layers(R, rc, ps)
+    ref, hs = O.collectstates_delay(layers, data, [h0], idl, sdl, post)
+    assert states.shape == ref.shape and state_err(states, ref) <= STATE_RTOL
+    assert ps.readout.weight.shape[1] == N * ((sdl[0] if sdl else 0) + 1)  # esn_delay.jl:292,477 (Pad widens it at train time)
+    # train (collect -> washout -> ridge) and teacher-forced predict continue the delay lines from st
+    ps2, st3 = R.train(rc, data, tgt, ps, st, objective=R.RidgeRegression(1e-4), washout=10)
+    Wo = O.train_ridge_qr(ref[:, 10:], tgt[:, 10:], 1e-4)
+    assert np.linalg.norm(ps2.readout.weight - Wo) / np.linalg.norm(Wo) <= WEIGHT_RTOL
+    test = np.asfortranarray(series[:, T:T + 15])
+    Y, _ = R.predict(rc, test, ps2, st3)
+    full, _ = O.collectstates_delay(layers, np.concatenate([data, test], axis=1), [h0], idl, sdl, post)
+    Yo = O.linear_readout(ps2.readout.weight, full[:, T:].astype(np.float64))
+    assert state_err(Y, Yo) <= 1e-4
+    with pytest.raises(R.UnsupportedError):
+        R.predict(rc, 5, ps2, st3, initialdata=test[:, 0])
+
+
+@pytest.mark.parametrize("F,S,dt", [(20, 200, np.float64), (6, 30, np.float32), (300, 4000, np.float32)])
+def test_correlation_matrix_and_ridge_map(R, F, S, dt):  # test/Models/conceptors_tests.jl:10-13,30-40
+    rng = np.random.default_rng(2024)
+    Z = np.asfortranarray(rng.standard_normal((F, S)).astype(dt))
+    Rm = R.correlation_matrix(Z)
+    ref = O.correlation_matrix(Z.astype(np.float64))
+    assert Rm.dtype == dt and np.array_equal(Rm, Rm.T)
+    assert np.max(np.abs(Rm - ref)) <= (1e-12 if dt == np.float64 else 1e-6)
+    with pytest.raises(R.ArgumentError):
+        R.correlation_matrix(np.zeros((3, 0)))
+    Y = np.asfortranarray(rng.standard_normal((4, S)).astype(dt))
+    M = R.ridge_map(Z, Y, 1e-2)                         # conceptors.jl:639-649
+    Mo = O.train_ridge_qr(Z, Y, 1e-2, reg_dtype=dt)
+    assert M.dtype == dt and np.linalg.norm(M - Mo) / np.linalg.norm(Mo) <= WEIGHT_RTOL
+
+
+def test_correlation_matrix_tensor_path(R):
+    rng = np.random.default_rng(5)
+    Z = np.asfortranarray(rng.standard_normal((512, 20000)).astype(np.float32))
+    Rm = R.correlation_matrix(Z, gram_mode=R.GRAM_TENSOR)
+    ref = (Z.astype(np.float64) @ Z.astype(np.float64).T) / Z.shape[1]
+    assert np.array_equal(Rm, Rm.T) and np.max(np.abs(Rm - ref)) <= 1e-6

@@ -299,3 +299,29 @@ def test_sibling_cells_degenerate_limits():  # parameter choices of collectstate
     assert np.array_equal(es2n, esn)
     res, _ = O.collectstates([O.ESNCellParams(Win, W, act=O.ACT_IDENTITY, cell="resesn", orthogonal_matrix=Om, alpha=0.0, beta=1.0)], data, h0)
     assert np.array_equal(res, esn)
+
+
+# ---- DelayLayer goldens, test/basic_tests.jl:204-246 ----------------------------------------------------------------
+def test_delay_layer_goldens():
+    x = np.arange(1, 7, dtype=np.float32)[None, :]
+    out, hist, clock = O.delay_layer_sequence(x[:, :5], 2, 1)           # :204-222
+    assert np.array_equal(out.T, [[1, 0, 0], [2, 1, 0], [3, 2, 1], [4, 3, 2], [5, 4, 3]])
+    assert clock == 5 and np.array_equal(hist, [[5, 4]])
+    out, hist, clock = O.delay_layer_sequence(x[:, :4], 2, 2)           # :225-246
+    assert np.array_equal(out.T, [[1, 0, 0], [2, 0, 0], [3, 2, 0], [4, 2, 0]])
+    assert np.array_equal(hist, [[4, 2]])
+    # :187-202 — explicit init columns show up unshifted after the first call with stride 2
+    h0 = np.array([[1, 2], [1, 2]], np.float32)
+    o, h1, c1 = O.delay_layer_step(np.array([0.3, 0.7], np.float32), h0, 0, 2)
+    assert c1 == 1 and np.array_equal(h1, h0) and o.shape == (6,)
+    assert np.array_equal(o[2:], [1, 1, 2, 2])  # vec(history) is column-major
+
+
+def test_extend_and_correlation():
+    u = np.array([[1.0, 2.0]]); x = np.array([[3.0, 4.0], [5.0, 6.0]])
+    assert np.array_equal(O.extend(u, x), [[1, 2], [3, 4], [5, 6]])      # src/states.jl:138-141: input first
+    Z = np.array([[1, 2, 3], [0, 1, 0]], np.float32)
+    R = O.correlation_matrix(Z)
+    assert R.dtype == np.float32 and np.allclose(R, np.array([[14, 2], [2, 1]]) / 3)   # src/conceptors.jl:28-33
+    with pytest.raises(O.ArgumentError):
+        O.correlation_matrix(np.zeros((3, 0)))                            # test/Models/conceptors_tests.jl:30
