@@ -299,6 +299,21 @@ RCB_API int32_t rcb_delay_features(rcb_ctx* ctx, const void* x, int32_t dtype, i
 RCB_API int32_t rcb_readout_apply(rcb_ctx* ctx, const double* W, const double* bias, int32_t activation, const void* features,
                                   int32_t dtype, int64_t F, int64_t cols, int64_t d_out, double* y_out);
 
+/* ---- host setup: the spectral radius scale_radius! needs (src/inits/inits_components.jl:126-138) ------
+ * rho = max |eigenvalue| of the N x N reservoir matrix, by an Arnoldi process on the GPU (CSR SpMV + Gram-Schmidt in
+ * Float64) with the small Hessenberg eigenproblem solved on the host — instead of the reference's dense eigvals
+ * (O(N^3): minutes at N = 8192).  tol <= 0 -> 1e-8 (relative residual of the three leading Ritz values);
+ * max_dim <= 0 -> 1500 Krylov vectors; *krylov_dim (may be NULL) returns the dimension used.  Matrices with N <= max_dim
+ * are solved exactly (the Krylov space becomes invariant).  Errors: NaN/Inf -> RCB_ERR_NUMERIC; no convergence within
+ * max_dim -> RCB_ERR_NUMERIC.  The scaling itself (W .*= radius / rho) is an elementwise host operation. */
+RCB_API int32_t rcb_spectral_radius_dense(rcb_ctx* ctx, const float* W, int64_t ldw, int32_t n, double tol, int32_t max_dim,
+                                          double* rho, int32_t* krylov_dim);
+RCB_API int32_t rcb_spectral_radius_csc(rcb_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const float* nzval,
+                                        int32_t n, double tol, int32_t max_dim, double* rho, int32_t* krylov_dim);
+/* Host-only: eigenvalues of an m x m upper Hessenberg matrix (column-major, entries below the sub-diagonal ignored) by
+ * the shifted complex QR iteration the routine above uses. */
+RCB_API int32_t rcb_hessenberg_eigvals(const double* H, int32_t m, double* re, double* im);
+
 /* ---- conceptors' correlation: correlation_matrix(states) = (Z Z') / S (src/conceptors.jl:28-33), the
  * full symmetric F x F matrix in the states' eltype, from the same Gram kernels as the ridge fit (K2).
  * ridge_map (src/conceptors.jl:639-649) is rcb_fit_readout.  Errors: no states -> RCB_ERR_ARGUMENT (:29). */

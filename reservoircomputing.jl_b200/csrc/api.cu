@@ -9,7 +9,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <complex>
 #include <new>
+#include <vector>
 
 #include "rcb_internal.h"
 
@@ -1211,6 +1213,33 @@ int32_t rcb_readout_apply(rcb_ctx* ctx, const double* W, const double* bias, int
   if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, (size_t)d_out * cols * sizeof(double)));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
+}
+
+int32_t rcb_hessenberg_eigvals(const double* H, int32_t m, double* re, double* im) {
+  if (!H || !re || !im || m < 1) return fail(RCB_ERR_ARGUMENT, "bad argument");
+  std::vector<double> h((size_t)m * m);
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) h[(size_t)i * m + j] = H[(size_t)j * m + i];  // column-major in, row-major inside
+  std::vector<std::complex<double>> ev;
+  if (!hessenberg_eigvals(h, m, &ev)) return fail(RCB_ERR_NUMERIC, "Hessenberg QR iteration did not converge");
+  for (int i = 0; i < m; ++i) { re[i] = ev[(size_t)i].real(); im[i] = ev[(size_t)i].imag(); }
+  return RCB_OK;
+}
+
+int32_t rcb_spectral_radius_dense(rcb_ctx* ctx, const float* W, int64_t ldw, int32_t n, double tol, int32_t max_dim,
+                                  double* rho, int32_t* krylov_dim) {
+  if (!ctx || !W || !rho) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  HostCsr c;
+  RCB_TRY(csr_from_dense(W, ldw, n, &c));
+  return spectral_radius_csr(ctx, c, tol, max_dim, rho, krylov_dim);
+}
+
+int32_t rcb_spectral_radius_csc(rcb_ctx* ctx, const int64_t* colptr, const int64_t* rowval, const float* nzval, int32_t n,
+                                double tol, int32_t max_dim, double* rho, int32_t* krylov_dim) {
+  if (!ctx || !colptr || !rowval || !nzval || !rho) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  HostCsr c;
+  RCB_TRY(csr_from_csc(colptr, rowval, nzval, n, &c));
+  return spectral_radius_csr(ctx, c, tol, max_dim, rho, krylov_dim);
 }
 
 // correlation_matrix(states) = (Z Z') / S in float(eltype(states)), src/conceptors.jl:28-33

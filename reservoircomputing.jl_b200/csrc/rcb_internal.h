@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <complex>
 #include <string>
 #include <vector>
 
@@ -242,6 +243,10 @@ int32_t launch_readout(rcb_ctx* ctx, const double* W, const double* bias, int ac
                        int64_t cols, int d_out, double* Y);
 int32_t launch_delay(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int64_t T, int64_t B, int32_t D, int32_t stride,
                      const void* hist, int64_t clock0, void* out, void* hist_out);
+
+// spectral.cu: rho(A) = max |eigenvalue| by Arnoldi on the GPU + Hessenberg QR on the host
+bool hessenberg_eigvals(const std::vector<double>& Hin, int m, std::vector<std::complex<double>>* ev);
+int32_t spectral_radius_csr(rcb_ctx* ctx, const HostCsr& A, double tol, int32_t max_dim, double* rho, int32_t* dim_used);
 
 // (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);

@@ -7,7 +7,7 @@ from ._lib import (ArgumentError, CudaError, DimensionMismatch, NumericError, Un
 from .api import (NT, Device, DelayLayer, InputDelayESN, StateDelayESN, DelayESN, extend_features, readout_apply,
                   correlation_matrix, ridge_map, DeepESN, ESN, ESNCell, ES2N, ES2NCell, ResESN, ResESNCell, EuSN, EuSNCell, orthogonal, ExtendedSquare, LinearReadout, NLAT1, NLAT2, NLAT3, Pad,
                   PartialSquare, QRFactorization, QRSolver, RidgeRegression, StandardRidge, addreadout,
-                  apply_modifiers, collectstates, csr_from_matrix, eusn_operator_csr, default_device, device_count, export_csr, fit_readout, gram,
+                  apply_modifiers, collectstates, csr_from_matrix, eusn_operator_csr, spectral_radius, scale_radius, hessenberg_eigvals, default_device, device_count, export_csr, fit_readout, gram,
                   ridge_solve, identity,
                   predict, rand32, rand_sparse, randn32, relu, resetcarry, scaled_rand, setup, sigmoid, tanh,
                   tanh_fast, train, train_ensemble, train_sharded, train_time_chunked, chunk_windows, shard_range, time_chunks, zeros32)

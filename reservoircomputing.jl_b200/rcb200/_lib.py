@@ -97,6 +97,9 @@ SIGNATURES = {
     "rcb_extend_features": (_I32, [_P, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "rcb_delay_features": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _I32, _I32, _P, _I64, _P, _P]),
     "rcb_readout_apply": (_I32, [_P, _P, _P, _I32, _P, _I32, _I64, _I64, _I64, _P]),
+    "rcb_spectral_radius_dense": (_I32, [_P, _P, _I64, _I32, _F64, _I32, C.POINTER(_F64), C.POINTER(_I32)]),
+    "rcb_spectral_radius_csc": (_I32, [_P, _P, _P, _P, _I32, _F64, _I32, C.POINTER(_F64), C.POINTER(_I32)]),
+    "rcb_hessenberg_eigvals": (_I32, [_P, _I32, _P, _P]),
     "rcb_correlation_matrix": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _I32, _P]),
     "rcb_apply_modifiers": (_I32, [_P, _I32, _P, _P, _P, _I32, _I64, _I64, _P]),
 }

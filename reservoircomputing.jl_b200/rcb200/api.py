@@ -262,12 +262,7 @@ def _spectral_radius(W) -> float:
     if n <= 1500:  # dense eigvals, src/inits/inits_components.jl:127
         Wd = W.toarray() if sp.issparse(W) else np.asarray(W)
         return float(np.max(np.abs(np.linalg.eigvals(Wd.astype(np.float64)))))
-    import scipy.sparse.linalg as spla  # sparse Arnoldi above that: setup only
-
-    v0 = np.random.default_rng(0).standard_normal(n)
-    vals = spla.eigs(sp.csr_matrix(W).astype(np.float64), k=6, which="LM", v0=v0, return_eigenvectors=False,
-                     tol=1e-10, maxiter=20000)
-    return float(np.max(np.abs(vals)))
+    return spectral_radius(W)  # above that: Arnoldi on the GPU (rcb_spectral_radius_*)
 
 
 def _rand_sparse(rng, *dims, radius=1.0, sparsity=0.1, std=1.0, return_sparse=False):
@@ -1341,3 +1336,50 @@ def ridge_map(features, targets, reg, device: Optional[Device] = None):
     if not np.issubdtype(et, np.floating):
         et = np.dtype(np.float64)
     return fit_readout(RidgeRegression(et, reg), f.astype(et), t.astype(et), device=device)
+
+
+# ---- host setup on the GPU ------------------------------------------------------------------------------
+def spectral_radius(W, device: Optional[Device] = None, tol: float = 0.0, max_dim: int = 0, return_dim: bool = False):
+    """max |eigvals(W)| (what scale_radius! needs, src/inits/inits_components.jl:127) by Arnoldi on the GPU instead of a
+    dense eigen-decomposition.  W: dense (N, N) float32 or a scipy sparse matrix (handed over as SparseMatrixCSC)."""
+    import scipy.sparse as sp
+
+    dev = device or default_device()
+    rho, dim = C.c_double(), C.c_int32()
+    if sp.issparse(W):
+        Wc = sp.csc_matrix(W)
+        Wc.sort_indices()
+        colptr, rowval = Wc.indptr.astype(np.int64) + 1, Wc.indices.astype(np.int64) + 1
+        nz = np.ascontiguousarray(Wc.data, dtype=np.float32)
+        check(lib().rcb_spectral_radius_csc(dev.handle, ptr(colptr), ptr(rowval), ptr(nz), Wc.shape[0], float(tol), int(max_dim),
+                                            C.byref(rho), C.byref(dim)))
+    else:
+        Wd = np.asfortranarray(W, dtype=np.float32)
+        check(lib().rcb_spectral_radius_dense(dev.handle, ptr(Wd), Wd.shape[0], Wd.shape[0], float(tol), int(max_dim),
+                                              C.byref(rho), C.byref(dim)))
+    return (rho.value, dim.value) if return_dim else rho.value
+
+
+def scale_radius(W, radius, device: Optional[Device] = None):
+    """scale_radius!(W, radius): W .*= radius / rho(W) in W's eltype (src/inits/inits_components.jl:126-138); returns a
+    new array (dense in, dense out; sparse in, sparse out)."""
+    import scipy.sparse as sp
+
+    rho = np.float32(spectral_radius(W, device))
+    if not rho > 0:  # radius / 0 = Inf in the reference, caught by its Inf check (inits_components.jl:129-136)
+        raise ArgumentError("Sparsity too low for size of the matrix. Increase res_size or increase sparsity.")
+    f = np.float32(radius) / rho
+    out = (W.multiply(f).astype(np.float32).tocsc()) if sp.issparse(W) else np.asfortranarray(np.asarray(W, np.float32) * f)
+    vals = out.data if sp.issparse(out) else out
+    if not np.all(np.isfinite(vals)):
+        raise ArgumentError("Sparsity too low for size of the matrix. Increase res_size or increase sparsity.")
+    return out
+
+
+def hessenberg_eigvals(H):
+    """Host-only: eigenvalues of an upper Hessenberg matrix by the library's shifted complex QR iteration."""
+    Hf = np.asfortranarray(H, dtype=np.float64)
+    m = Hf.shape[0]
+    re, im = np.empty(m), np.empty(m)
+    check(lib().rcb_hessenberg_eigvals(ptr(Hf), m, ptr(re), ptr(im)))
+    return re + 1j * im

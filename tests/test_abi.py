@@ -162,3 +162,25 @@ def test_sibling_cell_setup_structure(R):  # es2n_cell.jl:93-104: draw order inp
     rc = R.EuSN(3, 20, 2, diffusion=0.3, leak_coefficient=0.5)
     ps, _ = R.setup(np.random.default_rng(4), rc)
     assert "orthogonal_matrix" not in ps.reservoir and rc.reservoir.cell_params == (0.3, 0.0)
+
+
+@pytest.mark.parametrize("m,seed", [(1, 0), (2, 1), (5, 2), (40, 3), (200, 4)])
+def test_hessenberg_eigvals_match_lapack(R, m, seed):  # host part of rcb_spectral_radius_* 
+    rng = np.random.default_rng(seed)
+    H = np.triu(rng.standard_normal((m, m)), -1)
+    ev = R.hessenberg_eigvals(H)
+    ref = np.linalg.eigvals(H)
+    key = lambda z: (round(z.real, 8), round(z.imag, 8))
+    a, b = np.array(sorted(ev, key=key)), np.array(sorted(ref, key=key))
+    assert np.max(np.abs(np.sort(np.abs(ev)) - np.sort(np.abs(ref)))) <= 1e-9 * max(1.0, np.max(np.abs(ref)))
+    assert abs(np.sum(ev) - np.trace(H)) <= 1e-9 * m * max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(a - b)) <= 1e-7 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_hessenberg_eigvals_special_cases(R):
+    assert np.allclose(np.sort(R.hessenberg_eigvals(np.diag([3.0, -1.0, 2.0])).real), [-1, 2, 3])
+    J = np.array([[0.0, -1.0], [1.0, 0.0]])               # a conjugate pair on the unit circle
+    ev = R.hessenberg_eigvals(J)
+    assert np.allclose(sorted(ev.imag), [-1, 1]) and np.allclose(ev.real, 0)
+    C3 = np.array([[0.0, 0, 1], [1, 0, 0], [0, 1, 0]])     # cyclic shift: cube roots of unity (all moduli equal)
+    assert np.allclose(np.abs(R.hessenberg_eigvals(C3)), 1.0)

@@ -846,3 +846,38 @@ def test_correlation_matrix_tensor_path(R):
     Rm = R.correlation_matrix(Z, gram_mode=R.GRAM_TENSOR)
     ref = (Z.astype(np.float64) @ Z.astype(np.float64).T) / Z.shape[1]
     assert np.array_equal(Rm, Rm.T) and np.max(np.abs(Rm - ref)) <= 1e-6
+
+
+# ---- host setup on the GPU: spectral radius for scale_radius! ------------------------------------------
+@pytest.mark.parametrize("n,k,sparse", [(1, 1, False), (50, 6, False), (300, 6, False), (1024, 6, True), (1500, 6, True)])
+def test_spectral_radius_matches_dense_eigvals(R, n, k, sparse):  # inits_components.jl:127; test/inits_tests.jl:9-15 tolerance 1e-5
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(n)
+    W = O.rand_sparse_like(rng, n, radius=1.0, sparsity=k / n) * np.float32(1.7) if n > 1 else np.array([[-0.3]], np.float32)
+    ref = float(np.max(np.abs(np.linalg.eigvals(W.astype(np.float64)))))
+    rho, dim = R.spectral_radius(sp.csc_matrix(W) if sparse else W, return_dim=True)
+    assert abs(rho - ref) <= 1e-7 * ref and 1 <= dim <= n
+    Ws = R.scale_radius(sp.csc_matrix(W) if sparse else W, 0.9)
+    Wd = Ws.toarray() if sparse else Ws
+    assert abs(np.max(np.abs(np.linalg.eigvals(Wd.astype(np.float64)))) - 0.9) <= 1e-5
+
+
+def test_spectral_radius_large_and_degenerate(R):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    n = 8192
+    rng = np.random.default_rng(17)
+    rows = np.stack([rng.choice(n, size=6, replace=False) for _ in range(n)], axis=1)
+    W = sp.csc_matrix((rng.standard_normal(6 * n).astype(np.float32), rows.T.ravel(), np.arange(0, 6 * n + 1, 6)), shape=(n, n))
+    rho, dim = R.spectral_radius(W, return_dim=True)
+    ref = np.max(np.abs(spla.eigs(W.astype(np.float64), k=6, which="LM", return_eigenvectors=False, tol=1e-10, maxiter=20000)))
+    assert abs(rho - ref) <= 1e-6 * ref and dim < 1500
+    assert R.spectral_radius(np.zeros((64, 64), np.float32)) == 0.0          # zero matrix
+    with pytest.raises(R.ArgumentError):                                        # scale_radius! of it -> Inf (inits_components.jl:129-136)
+        R.scale_radius(np.zeros((64, 64), np.float32), 1.0)
+    P = np.roll(np.eye(64, dtype=np.float32), 1, axis=0) * np.float32(0.5)      # all 64 eigenvalues on one circle
+    assert abs(R.spectral_radius(P) - 0.5) <= 1e-9
+    with pytest.raises(R.NumericError):
+        R.spectral_radius(np.full((4, 4), np.nan, np.float32))
