@@ -105,66 +105,125 @@ int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a) {
 // The input projection of a deep layer for every time step at once: layer l+1 at step t consumes
 // the modified state of layer l at step t and nothing feeds back (src/models/esn_deep.jl:270-280),
 // so the DeepESN wavefront factors into L recurrence passes with a dense GEMM between them.
-__global__ void __launch_bounds__(256) input_projection_kernel(const float* __restrict__ Wp, long long N, long long K,
-                                                               const float* __restrict__ Z, long long S,
-                                                               float* __restrict__ P) {
-  constexpr int TILE = 64, KC = 16;
-  __shared__ float As[KC][TILE];
-  __shared__ float Bs[KC][TILE + 1];
-  const long long i0 = (long long)blockIdx.x * TILE, j0 = (long long)blockIdx.y * TILE;
+// Register-tiled FP32 GEMM: 128 x 128 output tile per CTA, 8 x 8 per thread, K walked in steps of 16 through a two-stage
+// shared-memory pipeline (next tile's global loads are in flight during the FMAs).  Wp is the position-major W_in
+// ([K][N]: the output row is the contiguous index), Z the K x S feature matrix (column-major).  VEC: N, K multiples of
+// 4 and 16-byte aligned bases -> 128-bit global loads.  Exact FP32 FMA accumulation, like the reference's gemv.
+template <bool VEC>
+__global__ void __launch_bounds__(256, 2) input_projection_kernel(const float* __restrict__ Wp, long long N, long long K,
+                                                                  const float* __restrict__ Z, long long S,
+                                                                  float* __restrict__ P) {
+  constexpr int BM = 128, BN = 128, BK = 16, LDB = BN + 4;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+  const long long i0 = (long long)blockIdx.x * BM, j0 = (long long)blockIdx.y * BN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
-  for (long long k0 = 0; k0 < K; k0 += KC) {
-    {
-      const int li = tid & 63, lk = tid >> 6;
+  float acc[8][8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long k = k0 + lk + 4 * q;
-        As[lk + 4 * q][li] = (k < K && i0 + li < N) ? Wp[(size_t)k * N + i0 + li] : 0.f;
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+  float4 ra[2], rb[2];
+  auto fetch = [&](long long k0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + 256 * q;
+      {  // A: row k0 + idx / 32 of Wp, columns i0 + (idx % 32) * 4 .. +3
+        const long long k = k0 + idx / 32, i = i0 + (idx % 32) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          const float* src = Wp + (size_t)k * N + i;
+          if (VEC && i + 3 < N) v = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (i < N) v.x = __ldg(src);
+            if (i + 1 < N) v.y = __ldg(src + 1);
+            if (i + 2 < N) v.z = __ldg(src + 2);
+            if (i + 3 < N) v.w = __ldg(src + 3);
+          }
+        }
+        ra[q] = v;
       }
-      const int lkk = tid & 15, lj = tid >> 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long j = j0 + lj + 16 * q, k = k0 + lkk;
-        Bs[lkk][lj + 16 * q] = (k < K && j < S) ? Z[(size_t)j * K + k] : 0.f;
+      {  // B: column j0 + idx / 4 of Z, rows k0 + (idx % 4) * 4 .. +3
+        const long long j = j0 + idx / 4, k = k0 + (idx % 4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < S) {
+          const float* src = Z + (size_t)j * K + k;
+          if (VEC && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (k < K) v.x = __ldg(src);
+            if (k + 1 < K) v.y = __ldg(src + 1);
+            if (k + 2 < K) v.z = __ldg(src + 2);
+            if (k + 3 < K) v.w = __ldg(src + 3);
+          }
+        }
+        rb[q] = v;
       }
     }
-    __syncthreads();
+  };
+  auto stash = [&](int buf) {
 #pragma unroll
-    for (int kk = 0; kk < KC; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; b[q] = Bs[kk][ty + 16 * q]; }
-#pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    for (int q = 0; q < 2; ++q) {
+      const int idx = tid + 256 * q;
+      *reinterpret_cast<float4*>(&As[buf][idx / 32][(idx % 32) * 4]) = ra[q];
+      const int j = idx / 4, k = (idx % 4) * 4;
+      Bs[buf][k][j] = rb[q].x; Bs[buf][k + 1][j] = rb[q].y; Bs[buf][k + 2][j] = rb[q].z; Bs[buf][k + 3][j] = rb[q].w;
     }
-    __syncthreads();
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (long long k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + tx * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][ty * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    if (more) {
+      stash(buf ^ 1);  // the other buffer was last read before the barrier that ended the previous iteration
+      __syncthreads();
+      buf ^= 1;
+    }
   }
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+  for (int y = 0; y < 8; ++y) {
+    const long long j = j0 + (y < 4 ? ty * 4 + y : 64 + ty * 4 + (y - 4));
+    if (j >= S) continue;
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const long long i = i0 + tx + 16 * x, j = j0 + ty + 16 * y;
-      if (i < N && j < S) P[(size_t)j * N + i] = acc[x][y];
+    for (int h = 0; h < 2; ++h) {
+      const long long i = i0 + h * 64 + tx * 4;
+      float* dst = P + (size_t)j * N + i;
+      if (VEC && i + 3 < N) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[4 * h][y], acc[4 * h + 1][y], acc[4 * h + 2][y], acc[4 * h + 3][y]);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+          if (i + x < N) dst[x] = acc[4 * h + x][y];
+      }
     }
+  }
 }
 
 int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,
                                 float* P) {
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((S + 63) / 64));
-  if (grid.y > 65535) {
-    // split the sample range so grid.y stays within limits
-    const int64_t step = 65535LL * 64;
-    for (int64_t s0 = 0; s0 < S; s0 += step) {
-      const int64_t sc = S - s0 < step ? S - s0 : step;
-      dim3 g2((unsigned)((N + 63) / 64), (unsigned)((sc + 63) / 64));
-      input_projection_kernel<<<g2, 256, 0, ctx->stream>>>(Win, N, K, Z + (size_t)s0 * K, sc, P + (size_t)s0 * N);
-      ctx->launches++;
-    }
-  } else {
-    input_projection_kernel<<<grid, 256, 0, ctx->stream>>>(Win, N, K, Z, S, P);
+  const bool vec = (N % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Win) | reinterpret_cast<uintptr_t>(Z) |
+                                                      reinterpret_cast<uintptr_t>(P)) % 16 == 0);
+  const int64_t step = 65535LL * 128;  // grid.y limit
+  for (int64_t s0 = 0; s0 < S; s0 += step) {
+    const int64_t sc = S - s0 < step ? S - s0 : step;
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)((sc + 127) / 128));
+    if (vec) input_projection_kernel<true><<<grid, 256, 0, ctx->stream>>>(Win, N, K, Z + (size_t)s0 * K, sc, P + (size_t)s0 * N);
+    else input_projection_kernel<false><<<grid, 256, 0, ctx->stream>>>(Win, N, K, Z + (size_t)s0 * K, sc, P + (size_t)s0 * N);
     ctx->launches++;
   }
   RCB_CUDA(cudaGetLastError());

@@ -881,3 +881,19 @@ def test_spectral_radius_large_and_degenerate(R):
     assert abs(R.spectral_radius(P) - 0.5) <= 1e-9
     with pytest.raises(R.NumericError):
         R.spectral_radius(np.full((4, 4), np.nan, np.float32))
+
+
+@pytest.mark.parametrize("res,T,B", [([30, 51, 40], 70, 2), ([256, 384], 300, 1), ([130, 129, 131], 129, 3)])
+def test_deep_esn_input_projection_shapes(R, res, T, B):
+    """DeepESN layers >= 2 consume a dense GEMM W_in * Z over all time steps (esn_deep.jl:270-280): tile-boundary and
+    unaligned-K shapes of that GEMM against the step-by-step oracle."""
+    rng = np.random.default_rng(sum(res))
+    desn = R.DeepESN(2, res, 2, init_reservoir=R.rand_sparse(radius=0.8, sparsity=0.2), leak_coefficient=0.7, state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, desn)
+    data = np.asfortranarray(rng.standard_normal((2, T, B)).astype(np.float32))
+    hs0 = [rng.standard_normal((n, B)).astype(np.float32) for n in res]
+    states, _ = R.collectstates(desn, data, ps, fixed_h0(R, st, desn, hs0))
+    layers = oracle_layers(R, desn, ps)
+    for b in range(B):
+        ref, _ = O.collectstates(layers, data[:, :, b], [h[:, b] for h in hs0])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
