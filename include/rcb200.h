@@ -173,7 +173,8 @@ RCB_API int32_t rcb_eusn_operator_from_dense(const float* W, int64_t ldw, int32_
  * the bank-conflict-free schedule).  stats[0] = nnz, [1] = padded nnz, [2]/[3] = simulated / ideal
  * shared-memory wavefronts of the LDS.64 gathers of one pass over W, [4]/[5] = same for LDS.32,
  * [6] = 1 when decoding the layout gives back exactly the input triples (bit-exact pattern + values),
- * [7] = rows missing or duplicated in the row permutation (0 = bijection). */
+ * [7] = rows missing or duplicated in the row permutation (0 = bijection), [8]/[9] = simulated / ideal wavefronts of
+ * one 8-byte write-back of the new state by row index.  `stats` holds 10 entries. */
 RCB_API int32_t rcb_sell_stats_from_dense(const float* W, int64_t ldw, int32_t n, int32_t nthreads, int32_t balanced,
                                           int64_t* stats);
 /* Ensemble members (BASELINE config 5): sequence b of a batched call uses W*w_scale[b] and

@@ -690,6 +690,16 @@ int32_t rcb_sell_stats_from_dense(const float* W, int64_t ldw, int32_t n, int32_
     if (r != 0xFFFF) { dup += seen[r]; seen[r] = 1; }
   for (char x : seen) dup += x ? 0 : 1;
   stats[7] = dup;
+  // write-back of the new state by row index: 16 lanes x 8 B per wavefront, conflict-free iff the rows of a half-warp
+  // are distinct mod 16
+  int64_t wb = 0, wbi = 0;
+  for (size_t g = 0; g + 16 <= s.perm.size(); g += 16) {
+    int cnt[16] = {0}, mx = 0;
+    for (int u = 0; u < 16; ++u)
+      if (s.perm[g + u] != 0xFFFF) mx = std::max(mx, ++cnt[s.perm[g + u] & 15]);
+    wb += mx; wbi += mx ? 1 : 0;
+  }
+  stats[8] = wb; stats[9] = wbi;
   return RCB_OK;
 }
 

@@ -349,20 +349,38 @@ int32_t launch_delay(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int6
 }
 
 // LinearReadout over a feature matrix (src/layers/basic.jl:171-182): Y[:, c] = psi(W Z[:, c] + b), Float64 accumulate.
-// One CTA per column, one warp per output row (strided).
+// One CTA per column: every thread walks the features once and feeds up to 4 outputs per pass (W is d_out x F, so the
+// outputs of a feature are contiguous), then a warp shuffle + shared-memory reduction.
 template <typename T>
 __global__ void __launch_bounds__(256) readout_kernel(const double* __restrict__ W, const double* __restrict__ bias, int act,
                                                       const T* __restrict__ Z, long long F, long long cols, int d_out,
                                                       double* __restrict__ Y) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ double red[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long c = blockIdx.x; c < cols; c += gridDim.x) {
     const T* z = Z + (size_t)c * F;
-    for (int o = warp; o < d_out; o += nw) {
-      double acc = 0.0;
-      for (long long f = lane; f < F; f += 32) acc = fma(W[(size_t)f * d_out + o], (double)z[f], acc);
+    for (int o0 = 0; o0 < d_out; o0 += 4) {
+      const int no = d_out - o0 < 4 ? d_out - o0 : 4;
+      double part[4] = {0.0, 0.0, 0.0, 0.0};
+      for (long long f = threadIdx.x; f < F; f += blockDim.x) {
+        const double zf = (double)z[f];
+        const double* wf = W + (size_t)f * d_out + o0;
 #pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-      if (lane == 0) {
+        for (int q = 0; q < 4; ++q)
+          if (q < no) part[q] = fma(__ldg(wf + q), zf, part[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double v = part[q];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0) red[warp][q] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < no) {
+        const int o = o0 + threadIdx.x;
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += red[w][threadIdx.x];
         if (bias) acc += bias[o];
         switch (act) {
           case RCB_ACT_TANH: case RCB_ACT_TANH_FAST: acc = tanh(acc); break;
@@ -372,6 +390,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const double* __restrict__
         }
         Y[(size_t)c * d_out + o] = acc;
       }
+      __syncthreads();
     }
   }
 }

@@ -78,7 +78,7 @@ __device__ __forceinline__ void row_update(const RecParams& p, const unsigned ch
 #pragma unroll
     for (int b = 0; b < NB; ++b) hold[b] = T(0);
     const float* op = p.Ot + pos;
-#pragma unroll 4
+#pragma unroll 16  // O streams from L2: keep enough loads in flight to cover its latency
     for (int j = 0; j < p.n; ++j) {
       const T o = (T)__ldg(op + (size_t)j * p.npos);
       T x0[NB];
@@ -337,10 +337,9 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
   for (int l = 0; l < p.n_layers; ++l) total_h += 2 * p.L[l].npad;
   T* z_s = base + total_h;
   T* in_s = z_s + p.zmax;
-  size_t red_off = (size_t)(total_h + p.zmax + ((p.in_dims + 3) & ~3)) * sizeof(T);
+  size_t red_off = (size_t)(total_h + p.zmax + 2 * ((p.in_dims + 3) & ~3)) * sizeof(T);  // two input buffers
   red_off = (red_off + 7) & ~(size_t)7;  // keep the double array 8-byte aligned
   double* red_s = reinterpret_cast<double*>(smem + red_off);
-  double* y_s = red_s + (size_t)p.nwarps * p.d_out;  // [d_out]
   T* h_g = reinterpret_cast<T*>(p.h);
   for (int l = 0; l < p.n_layers; ++l) {
     const PredLayer& L = p.L[l];
@@ -361,15 +360,21 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
   const T mscale = p.member_scale ? (T)p.member_scale[seq] : T(1);
   __syncthreads();
 
+  // teacher-forced inputs are double-buffered: u_{t+1} is fetched while step t runs (no extra barrier per step)
+  T* in2 = in_s + ((p.in_dims + 3) & ~3);
+  if (!p.autoregressive && tid < p.in_dims) {
+    const size_t idx = ((size_t)seq * p.T) * p.in_dims + tid;
+    in_s[tid] = p.u_is_f64 ? (T) reinterpret_cast<const double*>(p.u)[idx] : (T) reinterpret_cast<const float*>(p.u)[idx];
+  }
+  __syncthreads();
   for (long long t = 0; t < p.T; ++t) {
-    if (!p.autoregressive) {
-      if (tid < p.in_dims) {
-        size_t idx = ((size_t)seq * p.T + t) * p.in_dims + tid;
-        in_s[tid] = p.u_is_f64 ? (T) reinterpret_cast<const double*>(p.u)[idx] : (T) reinterpret_cast<const float*>(p.u)[idx];
-      }
-      __syncthreads();
+    const T* xin = (!p.autoregressive && (t & 1)) ? in2 : in_s;
+    if (!p.autoregressive && tid < p.in_dims && t + 1 < p.T) {
+      const size_t idx = ((size_t)seq * p.T + t + 1) * p.in_dims + tid;
+      T* dst = (t & 1) ? in_s : in2;  // consumed at step t+1; its previous content was last read at step t-1
+      dst[tid] = p.u_is_f64 ? (T) reinterpret_cast<const double*>(p.u)[idx] : (T) reinterpret_cast<const float*>(p.u)[idx];
     }
-    const T* xin = in_s;
+    const T* zlast = nullptr;  // un-modified new state of the last layer (the readout evaluates the modifier on the fly)
     for (int l = 0; l < p.n_layers; ++l) {
       const PredLayer& L = p.L[l];
       const T* cur = base + L.h_off + (t & 1) * L.npad;
@@ -384,10 +389,20 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
         const int off = __ldg(L.blk_off + blk), wd = __ldg(L.blk_w + blk);
         const float* vp = L.vals + (size_t)off * 32 + lane;
         const uint16_t* cp = L.cols + (size_t)off * 32 + lane;
-        for (int j = 0; j < wd; ++j) acc = fma((T)__ldg(vp + (size_t)j * 32), cur[__ldg(cp + (size_t)j * 32)], acc);
+        int j = 0;
+        for (; j + 4 <= wd; j += 4) {  // four W entries in flight per trip: the loads are L2 latency, the chain is not
+          const float v0 = __ldg(vp + (size_t)j * 32), v1 = __ldg(vp + (size_t)(j + 1) * 32), v2 = __ldg(vp + (size_t)(j + 2) * 32),
+                      v3 = __ldg(vp + (size_t)(j + 3) * 32);
+          const int c0 = __ldg(cp + (size_t)j * 32), c1 = __ldg(cp + (size_t)(j + 1) * 32), c2 = __ldg(cp + (size_t)(j + 2) * 32),
+                    c3 = __ldg(cp + (size_t)(j + 3) * 32);
+          const T x0 = cur[c0], x1 = cur[c1], x2 = cur[c2], x3 = cur[c3];
+          acc = fma((T)v0, x0, acc); acc = fma((T)v1, x1, acc); acc = fma((T)v2, x2, acc); acc = fma((T)v3, x3, acc);
+        }
+        for (; j < wd; ++j) acc = fma((T)__ldg(vp + (size_t)j * 32), cur[__ldg(cp + (size_t)j * 32)], acc);
         if (l == 0) acc *= mscale;
         if (L.bias) acc += (T)__ldg(L.bias + r);
         T win = T(0);
+#pragma unroll 4
         for (int d = 0; d < L.d_in; ++d) win = fma((T)__ldg(L.Win + (size_t)d * L.npos + pos), xin[d], win);
         T lc = L.leakv ? (T)__ldg(L.leakv + r) : (T)L.leak;
         if (l == 0 && p.member_leak) lc = (T)p.member_leak[seq];
@@ -396,8 +411,8 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
         if (L.Ot) {
           T sk = T(0);
           const float* op = L.Ot + pos;
-#pragma unroll 4
-          for (int j = 0; j < L.n; ++j) sk = fma((T)__ldg(op + (size_t)j * L.npos), cur[j], sk);
+#pragma unroll 16
+          for (int jj = 0; jj < L.n; ++jj) sk = fma((T)__ldg(op + (size_t)jj * L.npos), cur[jj], sk);
           hn = (T)L.skip_a * sk + (T)L.cand_b * cand;
         } else {
           hn = (T(1) - lc) * cur[r] + lc * cand;
@@ -405,34 +420,52 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
         if (valid) nxt[r] = hn;
       }
       __syncthreads();
-      // modified state of this layer -> z buffer (input of the next layer / of the readout)
-      for (int f = tid; f < L.feat; f += p.nthreads) {
-        T zz[1];
-        feature_eval<T, 1>(L.mod, reinterpret_cast<const unsigned char*>(nxt), L.npad, L.n, f, zz);
-        z_s[f] = zz[0];
+      if (l + 1 < p.n_layers) {
+        // modified state of this layer -> z buffer (input of the next layer)
+        for (int f = tid; f < L.feat; f += p.nthreads) {
+          T zz[1];
+          feature_eval<T, 1>(L.mod, reinterpret_cast<const unsigned char*>(nxt), L.npad, L.n, f, zz);
+          z_s[f] = zz[0];
+        }
+        __syncthreads();
+        xin = z_s;
+      } else {
+        zlast = nxt;
       }
-      __syncthreads();
-      xin = z_s;
     }
-    // readout: y = psi(W_out z + b), accumulated in Float64 (W_out is Float64, basic.jl:171-182)
-    for (int o = 0; o < p.d_out; ++o) {
-      double part = 0.0;
-      for (int f = tid; f < p.feat; f += p.nthreads) part = fma(__ldg(Wout + (size_t)f * p.d_out + o), (double)z_s[f], part);
+    // readout: y = psi(W_out z + b), accumulated in Float64 (W_out is Float64, basic.jl:171-182); z = modifier(new state)
+    // evaluated on the fly, all outputs of a chunk of 4 in one pass over the features
+    const PredLayer& LL = p.L[p.n_layers - 1];
+    for (int o0 = 0; o0 < p.d_out; o0 += 4) {
+      double part[4] = {0.0, 0.0, 0.0, 0.0};
+      const int no = p.d_out - o0 < 4 ? p.d_out - o0 : 4;
+      for (int f = tid; f < p.feat; f += p.nthreads) {
+        T zz[1];
+        feature_eval<T, 1>(LL.mod, reinterpret_cast<const unsigned char*>(zlast), LL.npad, LL.n, f, zz);
+        const double zf = (double)zz[0];
+        const double* wf = Wout + (size_t)f * p.d_out + o0;
 #pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sh);
-      if (lane == 0) red_s[(size_t)warp * p.d_out + o] = part;
+        for (int q = 0; q < 4; ++q)
+          if (q < no) part[q] = fma(__ldg(wf + q), zf, part[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q >= no) break;
+        double v = part[q];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0) red_s[(size_t)warp * p.d_out + o0 + q] = v;
+      }
     }
     __syncthreads();
-    if (tid < p.d_out) {
+    for (int o = tid; o < p.d_out; o += p.nthreads) {
       double ysum = 0.0;
-      for (int w = 0; w < p.nwarps; ++w) ysum += red_s[(size_t)w * p.d_out + tid];
-      if (bout) ysum += bout[tid];
+      for (int w = 0; w < p.nwarps; ++w) ysum += red_s[(size_t)w * p.d_out + o];
+      if (bout) ysum += bout[o];
       ysum = apply_act<double>(p.ro_act, ysum);
-      p.y[((size_t)seq * p.T + t) * p.d_out + tid] = ysum;
-      y_s[tid] = ysum;
+      p.y[((size_t)seq * p.T + t) * p.d_out + o] = ysum;
+      if (p.autoregressive && o < p.in_dims) in_s[o] = (T)ysum;  // y becomes the next input (predict.jl:83)
     }
-    __syncthreads();
-    if (p.autoregressive && tid < p.in_dims) in_s[tid] = (T)y_s[tid];  // y becomes the next input (predict.jl:83)
     __syncthreads();
   }
   if (h_g) {
@@ -480,7 +513,7 @@ int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
   p.member_leak = E.member_count ? E.d_member_leak : nullptr;
   p.u = a.u; p.u_is_f64 = E.desc.data_dtype == RCB_F64; p.T = a.T; p.B = a.B; p.h = a.h; p.y = a.y;
   const size_t esz = a.compute_dtype == RCB_F64 ? 8 : 4;
-  size_t smem = ((size_t)h_off + p.zmax + ((p.in_dims + 3) & ~3)) * esz;
+  size_t smem = ((size_t)h_off + p.zmax + 2 * ((p.in_dims + 3) & ~3)) * esz;
   smem = (smem + 7) & ~(size_t)7;
   smem += ((size_t)p.nwarps * p.d_out + p.d_out) * sizeof(double) + 16;
   if (smem > ctx->smem_optin)

@@ -4,6 +4,8 @@
 // Index parity: the CSR built here must reproduce the non-zero coordinates and values of the
 // matrix handed over bit-exactly, and so must the kernel-side layouts derived from it (decoded back
 // and compared in rcb_sell_stats_from_dense; tests/test_abi.py, tests/test_gpu_parity.py).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -238,6 +240,9 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
   // (1000 per missing entry) far less than an extra slot (1e6) but far more than unevenness (10 per squared count):
   // at N = 8192, 6 non-zeros per column this brings the padding from 21 % down to 4 %.
   const int WINDOW = 4096, SLACK = 4;
+  // a second row of the same residue in a group costs one extra wavefront in each write-back store of the new state
+  long OWNW = 2500L;
+  if (const char* e = getenv("RCB_SCHED_OWN")) OWNW = atol(e);  // testing hook
   for (int32_t gi = 0; gi < ngroups; ++gi) {
     GroupPlan& g = plan[(size_t)gi];
     std::fill(g.rows, g.rows + 16, -1);
@@ -270,7 +275,7 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
         for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) tmp[csr.colind[(size_t)e] & 15]++;
         for (int i = 0; i < 16; ++i) { mx = std::max(mx, tmp[i]); sq += (long)tmp[i] * tmp[i]; }
         // slots the group would need first, then missing entries, then a distinct own-row residue, then evenness
-        const long cost = (long)std::max(mx, seedlen) * 1000000L + (long)(seedlen - len(r)) * 1000L + (own[r & 15] ? 300L : 0L) + sq * 10L;
+        const long cost = (long)std::max(mx, seedlen) * 1000000L + (long)(seedlen - len(r)) * 1000L + (own[r & 15] ? OWNW : 0L) + sq * 10L;
         if (best < 0 || cost < bestcost) { best = (int64_t)q; bestcost = cost; }
       }
       if (best < 0) break;

@@ -872,7 +872,10 @@ def test_spectral_radius_large_and_degenerate(R):
     rows = np.stack([rng.choice(n, size=6, replace=False) for _ in range(n)], axis=1)
     W = sp.csc_matrix((rng.standard_normal(6 * n).astype(np.float32), rows.T.ravel(), np.arange(0, 6 * n + 1, 6)), shape=(n, n))
     rho, dim = R.spectral_radius(W, return_dim=True)
-    ref = np.max(np.abs(spla.eigs(W.astype(np.float64), k=6, which="LM", return_eigenvectors=False, tol=1e-10, maxiter=20000)))
+    # ARPACK with a handful of Ritz values and one start vector can miss the leading pair (it did in 1 of 8 tries at
+    # N = 4096, where dense eigvals confirmed the GPU value): take the best of three starts with a wider wanted set
+    ref = max(np.max(np.abs(spla.eigs(W.astype(np.float64), k=24, which="LM", return_eigenvectors=False, tol=1e-10, maxiter=20000,
+                                      v0=np.random.default_rng(s).standard_normal(n)))) for s in range(3))
     assert abs(rho - ref) <= 1e-6 * ref and dim < 1500
     assert R.spectral_radius(np.zeros((64, 64), np.float32)) == 0.0          # zero matrix
     with pytest.raises(R.ArgumentError):                                        # scale_radius! of it -> Inf (inits_components.jl:129-136)
