@@ -18,7 +18,7 @@ module RCB200
 using ReservoirComputing
 using ReservoirComputing: AbstractReservoirComputer, ReservoirComputer, StatefulLayer, ESNCell, ES2NCell, ResESNCell,
                           EuSNCell, RidgeRegression, NLAT1, NLAT2, NLAT3, Pad, PartialSquare, ExtendedSquare
-import ReservoirComputing: __collectstates, __predict, __fit_readout
+import ReservoirComputing: __collectstates, __predict, __fit_readout, collectstates
 using SparseArrays: SparseMatrixCSC
 
 const LIB = get(ENV, "RCB200_LIB", joinpath(@__DIR__, "..", "librcb200.so"))
@@ -113,46 +113,58 @@ cell_variant(c::ResESNCell) = (Int32(2), Float64(c.alpha), Float64(c.beta), 1.0)
 cell_variant(c::EuSNCell) = (Int32(3), Float64(c.diffusion), 0.0, c.leak_coefficient) # eusn_cell.jl:95-106
 cell_variant(c) = throw(ArgumentError("cell $(typeof(c)) is outside the B200 hot path"))
 
-function Handle(rc::AbstractReservoirComputer, ps, ::Type{T}) where {T}
-    cell = rc.reservoir.layer.cell
+function layer_desc(cell, layer_mods)
     kind, p0, p1, α = cell_variant(cell)
-    mods = collect(modifier_entry(m) for m in rc.state_modifiers)
-    length(mods) <= MAXMOD || throw(ArgumentError("at most $MAXMOD state modifiers"))
+    mods = collect(modifier_entry(m) for m in layer_mods)
+    length(mods) <= MAXMOD || throw(ArgumentError("at most $MAXMOD state modifiers per layer"))
     kinds = ntuple(i -> i <= length(mods) ? mods[i][1] : Int32(0), MAXMOD)
     params = ntuple(i -> i <= length(mods) ? mods[i][2] : 0.0, MAXMOD)
-    ld = LayerDesc(cell.out_dims, activation_id(cell.activation), ReservoirComputing.known(cell.use_bias) ? 1 : 0,
-                   α isa AbstractVector ? 1 : 0, α isa AbstractVector ? 0.0 : Float64(α), length(mods), kinds, params)
-    d = ESNDesc(1, cell.in_dims, rc.readout.out_dims, activation_id(rc.readout.activation),
-                ReservoirComputing.known(rc.readout.use_bias) ? 1 : 0, dtype_id(T))
+    return LayerDesc(cell.out_dims, activation_id(cell.activation), ReservoirComputing.known(cell.use_bias) ? 1 : 0,
+                     α isa AbstractVector ? 1 : 0, α isa AbstractVector ? 0.0 : Float64(α), length(mods), kinds, params)
+end
+
+# One handle for `cells` (ESNCell-family cells, layer order), their per-layer modifier tuples and parameter NamedTuples.
+function build_handle(cells, mods_per_layer, ps_cells, readout, ::Type{T}) where {T}
+    nl = length(cells)
+    lds = [layer_desc(cells[l], mods_per_layer[l]) for l in 1:nl]
+    d = ESNDesc(nl, cells[1].in_dims, readout.out_dims, activation_id(readout.activation),
+                ReservoirComputing.known(readout.use_bias) ? 1 : 0, dtype_id(T))
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:rcb_esn_create, LIB), Int32, (Ptr{Cvoid}, Ref{ESNDesc}, Ref{LayerDesc}, Ref{Ptr{Cvoid}}),
-                ctx().ptr, Ref(d), Ref(ld), out))
-    h = Handle(out[], 0, cell.out_dims)
+    check(ccall((:rcb_esn_create, LIB), Int32, (Ptr{Cvoid}, Ref{ESNDesc}, Ptr{LayerDesc}, Ref{Ptr{Cvoid}}),
+                ctx().ptr, Ref(d), lds, out))
+    h = Handle(out[], 0, sum(c.out_dims for c in cells))
     finalizer(x -> ccall((:rcb_esn_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), h)
-    kind != 0 && check(ccall((:rcb_esn_set_cell, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Float64, Float64), h.ptr, 0, kind, p0, p1))
-    W, Win = ps.reservoir.reservoir_matrix, Matrix{Float32}(ps.reservoir.input_matrix)
-    bias = haskey(ps.reservoir, :bias) ? Vector{Float32}(ps.reservoir.bias) : C_NULL
-    if W isa SparseMatrixCSC                      # return_sparse=true, ext/RCSparseArraysExt.jl:5-7
-        check(ccall((:rcb_esn_set_weights_csc, LIB), Int32,
-                    (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Int64, Ptr{Float32}),
-                    h.ptr, 0, W.colptr, W.rowval, Vector{Float32}(W.nzval), Win, size(Win, 1), bias))
-    else                                          # dense Matrix with explicit zeros (rand_sparse default)
-        Wd = Matrix{Float32}(W)
-        check(ccall((:rcb_esn_set_weights_dense, LIB), Int32,
-                    (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64, Ptr{Float32}, Int64, Ptr{Float32}),
-                    h.ptr, 0, Wd, size(Wd, 1), Win, size(Win, 1), bias))
-    end
-    α isa AbstractVector && check(ccall((:rcb_esn_set_leak_vector, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}),
-                                        h.ptr, 0, Vector{Float32}(α)))
-    if kind == 1 || kind == 2                     # ps.reservoir.orthogonal_matrix, es2n_cell.jl:93-104
-        Om = Matrix{Float32}(ps.reservoir.orthogonal_matrix)
-        check(ccall((:rcb_esn_set_orthogonal_dense, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64), h.ptr, 0, Om, size(Om, 1)))
+    for l in 1:nl
+        cell, p, li = cells[l], ps_cells[l], Int32(l - 1)
+        kind, p0, p1, α = cell_variant(cell)
+        kind != 0 && check(ccall((:rcb_esn_set_cell, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Float64, Float64), h.ptr, li, kind, p0, p1))
+        W, Win = p.reservoir_matrix, Matrix{Float32}(p.input_matrix)
+        bias = haskey(p, :bias) ? Vector{Float32}(p.bias) : C_NULL
+        if W isa SparseMatrixCSC                      # return_sparse=true, ext/RCSparseArraysExt.jl:5-7
+            check(ccall((:rcb_esn_set_weights_csc, LIB), Int32,
+                        (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float32}, Ptr{Float32}, Int64, Ptr{Float32}),
+                        h.ptr, li, W.colptr, W.rowval, Vector{Float32}(W.nzval), Win, size(Win, 1), bias))
+        else                                          # dense Matrix with explicit zeros (rand_sparse default)
+            Wd = Matrix{Float32}(W)
+            check(ccall((:rcb_esn_set_weights_dense, LIB), Int32,
+                        (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64, Ptr{Float32}, Int64, Ptr{Float32}),
+                        h.ptr, li, Wd, size(Wd, 1), Win, size(Win, 1), bias))
+        end
+        α isa AbstractVector && check(ccall((:rcb_esn_set_leak_vector, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}),
+                                            h.ptr, li, Vector{Float32}(α)))
+        if kind == 1 || kind == 2                     # ps.reservoir.orthogonal_matrix, es2n_cell.jl:93-104
+            Om = Matrix{Float32}(p.orthogonal_matrix)
+            check(ccall((:rcb_esn_set_orthogonal_dense, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Int64), h.ptr, li, Om, size(Om, 1)))
+        end
     end
     F = Ref{Int32}(0)
     check(ccall((:rcb_esn_feature_dims, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), h.ptr, F))
     h.F = F[]
     return h
 end
+
+Handle(rc::AbstractReservoirComputer, ps, ::Type{T}) where {T} =
+    build_handle((rc.reservoir.layer.cell,), (rc.state_modifiers,), (ps.reservoir,), rc.readout, T)
 
 # h0: the carry in `st`, or a fresh draw from the replicated rng exactly like the first reference step
 # (esn_cell.jl:169-173, lux_layers.jl:212-216)
@@ -231,6 +243,81 @@ function __predict(res::B200Reservoir, rc::AbstractReservoirComputer, data::Abst
     return Matrix{promote_type(T, eltype(ps.readout.weight))}(Y), store_carry(st, carry)
 end
 
+# ---- DeepESN: src/models/esn_deep.jl:190-291 ------------------------------------------------------------------------
+# DeepESN has its own `collectstates` method and no `:reservoir` field (SURVEY 8b item 6), so the CUDA path is selected
+# by wrapping the whole model; `ps` / `st` keep DeepESN's layout (cells, state_modifiers, readout).
+"""`B200DeepESN(desn)` / `b200(desn)` — a `DeepESN` whose `collectstates` and `predict` run on the GPU."""
+struct B200DeepESN{M <: ReservoirComputing.DeepESN} <:
+       ReservoirComputing.AbstractEchoStateNetwork{(:cells, :state_modifiers, :readout)}
+    cells
+    state_modifiers
+    readout
+    model::M
+end
+B200DeepESN(m::ReservoirComputing.DeepESN) = B200DeepESN(m.cells, m.state_modifiers, m.readout, m)
+ReservoirComputing.LuxCore.initialparameters(rng, d::B200DeepESN) = ReservoirComputing.LuxCore.initialparameters(rng, d.model)
+ReservoirComputing.LuxCore.initialstates(rng, d::B200DeepESN) = ReservoirComputing.LuxCore.initialstates(rng, d.model)
+(d::B200DeepESN)(inp, ps, st) = d.model(inp, ps, st)     # single steps stay on the reference path
+ReservoirComputing.resetcarry!(rng, d::B200DeepESN, st; kwargs...) = ReservoirComputing.resetcarry!(rng, d.model, st; kwargs...)
+ReservoirComputing.addreadout!(d::B200DeepESN, W::AbstractMatrix, ps, st) = ReservoirComputing.addreadout!(d.model, W, ps, st)
+
+deep_handle(d::B200DeepESN, ps, ::Type{T}) where {T} =
+    build_handle(map(c -> c.cell, d.cells), map(m -> m === nothing ? () : m, d.state_modifiers), ps.cells, d.readout, T)
+
+# packed carry (sum of N_l rows): stored carries, or fresh init_state draws like the first reference step of each cell
+function deep_initial_carry(d::B200DeepESN, st, ::Type{T}) where {T}
+    parts = map(zip(d.cells, st.cells)) do (c, s)
+        if s.carry === nothing
+            rng = ReservoirComputing.LuxCore.replicate(s.cell.rng)
+            Vector{T}(vec(c.cell.init_state(rng, c.cell.out_dims, 1)))
+        else
+            Vector{T}(vec(first(s.carry)))
+        end
+    end
+    return reduce(vcat, parts)
+end
+function deep_store_carry(d::B200DeepESN, st, h)
+    off = 0
+    new_cells = map(zip(d.cells, st.cells)) do (c, s)
+        n = c.cell.out_dims
+        part = reshape(h[(off + 1):(off + n)], :, 1)
+        off += n
+        merge(s, (carry = (part,),))
+    end
+    return merge(st, (cells = Tuple(new_cells),))
+end
+
+function collectstates(d::B200DeepESN, data::AbstractMatrix{T}, ps, st::NamedTuple) where {T}
+    size(data, 2) >= 1 || throw(ArgumentError("collectstates data must have at least one column, got 0."))
+    h = deep_handle(d, ps, T)
+    states = Matrix{T}(undef, h.F, size(data, 2))            # eltype(data), esn_deep.jl:288
+    h0 = deep_initial_carry(d, st, T); hT = similar(h0)
+    check(ccall((:rcb_collect, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                h.ptr, Matrix{T}(data), size(data, 2), 1, h0, states, hT))
+    return states, deep_store_carry(d, st, hT)
+end
+
+# predict(rc, ...) passes `nothing` as the reservoir for models without a :reservoir field (src/predict.jl:118-129)
+function __predict(::Nothing, d::B200DeepESN, steps::Integer, ps, st; initialdata)
+    steps >= 1 || throw(ArgumentError("steps must be ≥ 1, got $steps"))
+    T = eltype(initialdata)
+    h = deep_handle(d, ps, T); set_readout!(h, ps)
+    Tc = promote_type(T, eltype(ps.readout.weight))
+    carry = deep_initial_carry(d, st, Tc)
+    Y = Matrix{Float64}(undef, d.readout.out_dims, steps)
+    check(ccall((:rcb_predict_autoregressive, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}, Ptr{Float64}),
+                h.ptr, Vector{T}(initialdata), steps, 1, dtype_id(Tc), carry, Y))
+    return Matrix{Tc}(Y), deep_store_carry(d, st, carry)
+end
+function __predict(::Nothing, d::B200DeepESN, data::AbstractMatrix{T}, ps, st) where {T}
+    h = deep_handle(d, ps, T); set_readout!(h, ps)
+    carry = deep_initial_carry(d, st, T)
+    Y = Matrix{Float64}(undef, d.readout.out_dims, size(data, 2))
+    check(ccall((:rcb_predict_teacher, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Ptr{Float64}),
+                h.ptr, Matrix{T}(data), size(data, 2), 1, carry, Y))
+    return Matrix{promote_type(T, eltype(ps.readout.weight))}(Y), deep_store_carry(d, st, carry)
+end
+
 # ---- feature plumbing + conceptor blocks (SURVEY 8f-2 / 8f-4) ------------------------------------------------
 # The delay ESNs (src/models/esn_delay.jl) compose these around rcb_collect exactly like rcb200/api.py:_collect_delay:
 #   input DelayLayer -> rcb_collect (cell) -> state DelayLayer -> remaining modifiers (rcb_apply_modifiers).
@@ -278,7 +365,8 @@ CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ)
 wrapped model (same field names `reservoir`, `state_modifiers`, `readout`).
 """
 b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
+b200(rc::ReservoirComputing.DeepESN) = B200DeepESN(rc)
 
-export B200Reservoir, B200Ridge, b200, delay_features, extend_features, correlation_matrix_b200
+export B200Reservoir, B200DeepESN, B200Ridge, b200, delay_features, extend_features, correlation_matrix_b200
 
 end # module
