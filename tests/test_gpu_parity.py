@@ -900,3 +900,108 @@ def test_deep_esn_input_projection_shapes(R, res, T, B):
     for b in range(B):
         ref, _ = O.collectstates(layers, data[:, :, b], [h[:, b] for h in hs0])
         assert state_err(states[:, :, b], ref) <= STATE_RTOL
+
+
+# ---- randomized configurations: every kernel variant picks itself from (N, B, dtype, leak kind, bias, activation, chain) ----
+def _fuzz_cases():
+    rng = np.random.default_rng(20240)
+    acts = ["identity", "tanh", "tanh_fast", "sigmoid", "relu"]
+    chains = ["none", "nlat1", "nlat2", "nlat3", "pad", "nlat2_pad", "esq", "psq", "nlat1_nlat3_pad"]
+    cases = []
+    for i in range(36):
+        N = int(rng.choice([1, 2, 3, 7, 31, 32, 33, 64, 100, 257, 300, 513, 1024, 1100]))
+        cases.append(dict(seed=i, N=N, d_in=int(rng.integers(1, 12)), B=int(rng.choice([1, 1, 2, 3, 5, 9, 40])),
+                          T=int(rng.choice([1, 2, 5, 23])), f64=bool(rng.integers(0, 4) == 0), act=str(rng.choice(acts)),
+                          chain=str(rng.choice(chains)), bias=bool(rng.integers(0, 2)), vleak=bool(rng.integers(0, 3) == 0),
+                          sparse=bool(rng.integers(0, 2)), density=float(rng.choice([0.02, 0.1, 0.5, 1.0]))))
+    return cases
+
+
+@pytest.mark.parametrize("c", _fuzz_cases(), ids=lambda c: f"{c['seed']}-N{c['N']}-B{c['B']}-T{c['T']}-{c['act']}-{c['chain']}")
+def test_randomized_configurations(R, c):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(1000 + c["seed"])
+    N, d_in, B, T = c["N"], c["d_in"], c["B"], c["T"]
+    mods = dict(none=(), nlat1=(R.NLAT1,), nlat2=(R.NLAT2,), nlat3=(R.NLAT3,), pad=(R.Pad(-0.5),), nlat2_pad=(R.NLAT2, R.Pad(1.0)),
+                esq=(R.ExtendedSquare,), psq=(R.PartialSquare(0.37),), nlat1_nlat3_pad=(R.NLAT1, R.NLAT3, R.Pad(2.0)))[c["chain"]]
+    act = dict(identity=R.identity, tanh=R.tanh, tanh_fast=R.tanh_fast, sigmoid=R.sigmoid, relu=R.relu)[c["act"]]
+    W = (rng.standard_normal((N, N)) * (rng.random((N, N)) < c["density"])).astype(np.float32)
+    W *= np.float32(0.8 / max(1e-3, np.max(np.abs(np.linalg.eigvals(W.astype(np.float64)))))) if N <= 300 else np.float32(0.5 / np.sqrt(max(1.0, c["density"] * N)))
+    Win = rng.uniform(-0.5, 0.5, (N, d_in)).astype(np.float32)
+    leak = rng.uniform(0.1, 1.0, N).astype(np.float32) if c["vleak"] else float(rng.uniform(0.1, 1.0))
+    Wm = sp.csc_matrix(W) if c["sparse"] else np.asfortranarray(W)
+    esn = R.ESN(d_in, N, 2, act, init_reservoir=lambda r, *d: Wm, init_input=const_init(Win), use_bias=c["bias"],
+                init_bias=R.randn32, leak_coefficient=leak, state_modifiers=mods)
+    ps, st = R.setup(rng, esn)
+    dt = np.float64 if c["f64"] else np.float32
+    data = np.asfortranarray(rng.standard_normal((d_in, T, B)).astype(dt))
+    h0 = rng.standard_normal((N, B)).astype(dt)
+    states, st2 = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [h0]))
+    layers = oracle_layers(R, esn, ps)
+    tol = 1e-11 if c["f64"] else STATE_RTOL
+    for b in range(B):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert states[:, :, b].shape == ref.shape and states.dtype == dt
+        if N >= 8:
+            assert state_err(states[:, :, b], ref) <= tol
+        else:  # a column of 1-3 numbers can pass through zero: its own max-norm is no scale (FMA vs separate rounding); use the trajectory's
+            assert np.max(np.abs(states[:, :, b].astype(np.float64) - ref)) <= tol * max(1.0, np.max(np.abs(ref)))
+        assert state_err(st2.reservoir.carry[0][:, b:b + 1], hs[0].reshape(-1, 1)) <= max(tol, 1e-11) or N < 8
+    rp, ci, v = R.export_csr(esn, ps)                      # pattern + values bit-exact for every hand-off form
+    rp0, ci0, v0 = O.dense_to_csr(W)
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and v.tobytes() == v0.astype(np.float32).tobytes()
+
+
+def _fuzz_train_cases():
+    rng = np.random.default_rng(777)
+    cases = []
+    for i in range(14):
+        cases.append(dict(seed=i, N=int(rng.choice([5, 20, 64, 150, 300])), d=int(rng.integers(1, 4)), B=int(rng.choice([1, 1, 2, 4])),
+                          T=int(rng.choice([60, 150, 400])), washout=int(rng.choice([0, 1, 17])), lam=float(rng.choice([1e-4, 1e-2, 1.0])),
+                          chain=str(rng.choice(["none", "nlat2", "nlat2_pad", "esq"])), ro_act=str(rng.choice(["identity", "tanh"])),
+                          f64=bool(rng.integers(0, 3) == 0)))
+    return cases
+
+
+@pytest.mark.parametrize("c", _fuzz_train_cases(), ids=lambda c: f"{c['seed']}-N{c['N']}-B{c['B']}-T{c['T']}-{c['chain']}-{c['ro_act']}")
+def test_randomized_train_predict(R, c):
+    """train (collect -> washout -> ridge) and both predict modes on random small configurations against the oracle."""
+    rng = np.random.default_rng(5000 + c["seed"])
+    N, d, B, T, w = c["N"], c["d"], c["B"], c["T"], c["washout"]
+    mods = dict(none=(), nlat2=(R.NLAT2,), nlat2_pad=(R.NLAT2, R.Pad(1.0)), esq=(R.ExtendedSquare,))[c["chain"]]
+    ro_act = dict(identity=R.identity, tanh=R.tanh)[c["ro_act"]]
+    esn = R.ESN(d, N, d, init_reservoir=R.rand_sparse(radius=0.8, sparsity=min(1.0, 6 / N)), init_input=R.scaled_rand(scaling=0.5),
+                leak_coefficient=float(rng.uniform(0.3, 1.0)), state_modifiers=mods, readout_activation=ro_act)
+    ps, st = R.setup(rng, esn)
+    dt = np.float64 if c["f64"] else np.float32
+    tt = np.arange(T + 31)[None, :, None]   # sustained O(1) drive: the per-column relative metric needs columns of O(1) norm
+    series = np.sin(tt * rng.uniform(0.05, 0.4, (d, 1, B)) + rng.uniform(0, 6.28, (d, 1, B))) + 0.3 * rng.standard_normal((d, T + 31, B))
+    series = (series / np.max(np.abs(series))).astype(dt)
+    data, tgt = np.asfortranarray(series[:, :T]), np.asfortranarray(0.5 * series[:, 1:T + 1])
+    h0 = rng.standard_normal((N, B)).astype(dt)
+    st = fixed_h0(R, st, esn, [h0])
+    (ps2, st2), states_wo = R.train(esn, data, tgt, ps, st, objective=R.RidgeRegression(c["lam"]), washout=w, return_states=True)
+    layers = oracle_layers(R, esn, ps)
+    Zs, Ys, hT = [], [], []
+    for b in range(B):
+        z, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        stol = 1e-11 if c["f64"] else STATE_RTOL                                                # post-washout states (train.jl:240-243)
+        if N >= 8:
+            assert state_err(states_wo[:, :, b], z[:, w:]) <= stol
+        else:  # a handful of numbers per column: judge against the trajectory's scale (see test_randomized_configurations)
+            assert np.max(np.abs(states_wo[:, :, b].astype(np.float64) - z[:, w:])) <= stol * max(1.0, np.max(np.abs(z)))
+        Zs.append(states_wo[:, :, b]); Ys.append(tgt[:, w:, b]); hT.append(hs[0])
+    # the solver is judged on identical inputs: Householder QR of the augmented system built from the states the GPU
+    # collected (a ridge problem with few samples amplifies the 1e-7 state rounding differences far beyond 1e-4)
+    Wo = O.train_ridge_qr(np.concatenate(Zs, axis=1), np.concatenate(Ys, axis=1), c["lam"])   # pooled over the sequences
+    assert ps2.readout.weight.dtype == np.float64
+    assert np.linalg.norm(ps2.readout.weight - Wo) / np.linalg.norm(Wo) <= WEIGHT_RTOL
+    test = np.asfortranarray(series[:, T:T + 30])
+    Y, _ = R.predict(esn, test, ps2, st2)
+    Ya, _ = R.predict(esn, 12, ps2, st2, initialdata=test[:, 0])
+    for b in range(B):
+        Yo, _ = O.predict_teacher(layers, ps2.readout.weight, test[:, :, b], [hT[b]], ro_act=_act_to_oracle(R, ro_act))
+        assert state_err(Y[:, :, b], Yo) <= 1e-4
+        Yao, _ = O.predict_autoregressive(layers, ps2.readout.weight, 12, test[:, 0, b], [hT[b]], ro_act=_act_to_oracle(R, ro_act))
+        assert state_err(Ya[:, :, b], Yao) <= 1e-3
