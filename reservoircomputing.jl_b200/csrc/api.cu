@@ -268,18 +268,21 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
       }
     }
   RCB_TRY(upload(winp, &L.d_Win));
-  if (L.d_in == 3 || L.d_in == 1) {
-    HostFast hf4;
+  {
+    HostFast hf4;  // the same stream with column * 4 (byte offsets of floats): recurrence_fast7.cu, recurrence_single.cu
     RCB_TRY(fast_from_csr(K, hs, &hf4, 4));
     if (hf4.ok) {
       RCB_TRY(upload(hf4.stream, &L.fast4.stream));
+      L.fast4.stream_bytes = hf4.stream.size();
       RCB_TRY(upload(hf4.warp_off, &L.fast4.warp_off));
       RCB_TRY(upload(hf4.wwords, &L.fast4.wwords));
       L.fast4.ok = true;
-      std::vector<float> w4((size_t)npos * 4, 0.f);
-      for (int p = 0; p < npos; ++p)
-        for (int d = 0; d < L.d_in; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
-      RCB_TRY(upload(w4, &L.d_Win4));
+      if (L.d_in == 3 || L.d_in == 1) {
+        std::vector<float> w4((size_t)npos * 4, 0.f);
+        for (int p = 0; p < npos; ++p)
+          for (int d = 0; d < L.d_in; ++d) w4[(size_t)p * 4 + d] = winp[(size_t)d * npos + p];
+        RCB_TRY(upload(w4, &L.d_Win4));
+      }
     }
     const char* k1mode = getenv("RCB_K1_MODE");
     if (hf4.ok && L.d_in == 3 && L.n == 8192 && esn_nthreads(esn) == 1024 && k1mode && !strcmp(k1mode, "fast7_512")) {  // experimental second schedule: 512 threads x 16 slabs

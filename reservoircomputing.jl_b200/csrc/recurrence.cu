@@ -260,6 +260,8 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
   const size_t cap = ctx->smem_optin;
   if (a.dtype == RCB_F32 && !p.Ot) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
     bool launched = false;
+    const int32_t sg = launch_collect_single(ctx, p, L.fast4, L.d_Win4, &launched);
+    if (sg != RCB_OK || launched) return sg;
     const int32_t f7 = launch_collect_fast7(ctx, p, L.fast4, L.d_Win4, L.fast4h, L.d_Win4h, L.d_permh, &launched);
     if (f7 != RCB_OK || launched) return f7;
     const int32_t fst = launch_collect_fast(ctx, p, L.fast, &launched);

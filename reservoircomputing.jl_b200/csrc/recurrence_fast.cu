@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   const uint32_t npad = (uint32_t)p.npad;
   const size_t buf = (size_t)npad * NB * 4;
   const int d_in = DIN > 0 ? DIN : p.d_in;
-  unsigned char* S[2] = {smem, TMEM ? smem : smem + buf};
+  // both state buffers are addressed as smem + offset (never through a pointer table) so that every access stays an LDS/STS
+  const uint32_t buf1 = TMEM ? 0u : (uint32_t)buf;
   float* u_s = reinterpret_cast<float*>(smem + (TMEM ? 1 : 2) * buf);  // [2][d_in][8]
   float* m_s = u_s + 2 * d_in * 8;                                     // [2][8] member scale | leak
   uint32_t* tm_s = reinterpret_cast<uint32_t*>(m_s + 16);
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     float v[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) v[b] = (h0_g && b < nvalid && i < p.n) ? h0_g[(size_t)(seq0 + b) * p.h_stride + p.h_off + i] : 0.0f;
-    L::store(S[0], npad, (uint32_t)i, v);
-    if constexpr (!TMEM) L::store(S[1], npad, (uint32_t)i, v);
+    L::store(smem, npad, (uint32_t)i, v);
+    if constexpr (!TMEM) L::store(smem + buf1, npad, (uint32_t)i, v);
   }
   for (int i = tid; i < 2 * d_in * 8 + 16; i += p.nthreads) u_s[i] = 0.0f;
   __syncthreads();
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     for (int k = 0; k < p.R; ++k) {
       const unsigned r16 = __ldg(p.perm + k * p.nthreads + tid);
       float hv[NB];
-      L::load(S[0], npad, r16 != 0xFFFFu ? r16 : 0u, hv);
+      L::load(smem, npad, r16 != 0xFFFFu ? r16 : 0u, hv);
       uint32_t o[8];
 #pragma unroll
       for (int b = 0; b < 8; ++b) o[b] = b < NB ? __float_as_uint(hv[b]) : 0u;
@@ -302,8 +303,8 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   const bool is_tanh = SIMPLE || p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST;
 
   for (long long t = 0; t < p.T; ++t) {
-    const unsigned char* cur = S[TMEM ? 0 : (t & 1)];
-    unsigned char* nxt = S[TMEM ? 0 : ((t + 1) & 1)];
+    const unsigned char* cur = smem + ((t & 1) ? buf1 : 0u);
+    unsigned char* nxt = smem + ((t & 1) ? 0u : buf1);
     const float* ucur = u_s + (t & 1) * d_in * 8;
     float u_next = 0.0f;
     if (tid < nu && t + 1 < p.T) u_next = __ldg(u_g + ((size_t)useq * p.T + (t + 1)) * p.d_in + ud);
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   }
   if (p.hT) {
     float* hT_g = reinterpret_cast<float*>(p.hT);
-    const unsigned char* fin = S[TMEM ? 0 : (p.T & 1)];
+    const unsigned char* fin = smem + ((p.T & 1) ? buf1 : 0u);
     for (int i = tid; i < p.n; i += p.nthreads) {
       float v[NB];
       L::load(fin, npad, (uint32_t)i, v);
