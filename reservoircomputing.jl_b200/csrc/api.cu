@@ -104,6 +104,7 @@ struct TimerPool {
 static TimerPool* pools(rcb_ctx* ctx) { return reinterpret_cast<TimerPool*>(ctx->timer_pools); }
 
 void timer_begin(rcb_ctx* ctx, int which) {
+  if (ctx->timers_muted) return;
   TimerPool& p = pools(ctx)[which];
   if (p.used == (int)p.beg.size()) {
     cudaEvent_t a, b;
@@ -115,6 +116,7 @@ void timer_begin(rcb_ctx* ctx, int which) {
   cudaEventRecord(p.beg[p.used], ctx->stream);
 }
 void timer_end(rcb_ctx* ctx, int which) {
+  if (ctx->timers_muted) return;
   TimerPool& p = pools(ctx)[which];
   cudaEventRecord(p.end[p.used], ctx->stream);
   p.used++;
@@ -338,6 +340,77 @@ static int32_t check_ready(const rcb_esn* esn) {
   return RCB_OK;
 }
 
+// DeepESN, one sequence: layer l at step t needs only layer l-1 at step t (esn_deep.jl:270-280), so the layers form a
+// pipeline over time chunks — layer l works on chunk c while layer l-1 is already on chunk c+1, each layer on its own
+// stream (one persistent CTA each, on different SMs), ordered by events.  Wall time ~ (chunks + L - 1) x one chunk of one
+// layer instead of L full passes.  The per-layer carry rows of the packed carry buffer pass the state from chunk to chunk.
+static int32_t collect_device_pipelined(rcb_esn* esn, const void* u_dev, int64_t Tc, const void* h0_dev, void* states,
+                                        void* hT_dev, int64_t chunk) {
+  rcb_ctx* ctx = esn->ctx;
+  const int nl = (int)esn->layers.size();
+  const int64_t nch = (Tc + chunk - 1) / chunk;
+  cudaStream_t main_stream = ctx->stream;
+  for (int l = 0; l < nl; ++l)
+    if (!ctx->aux_streams[l]) RCB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_streams[l], cudaStreamNonBlocking));
+  // buffers: modified states of layers 0..nl-2 for the whole call, one projection chunk per layer >= 1, the carry
+  size_t zbytes = 0, pbytes = 0;
+  std::vector<size_t> zoff((size_t)nl, 0), poff((size_t)nl, 0);
+  for (int l = 0; l < nl; ++l) {
+    const Layer& L = esn->layers[(size_t)l];
+    if (l + 1 < nl) { zoff[(size_t)l] = zbytes; zbytes += ((size_t)L.feat * Tc * sizeof(float) + 255) / 256 * 256; }
+    if (l > 0) { poff[(size_t)l] = pbytes; pbytes += ((size_t)L.sell.R * L.sell.nthreads * chunk * sizeof(float) + 255) / 256 * 256; }
+  }
+  void *zbuf = nullptr, *pbuf = nullptr, *carry = hT_dev;
+  RCB_TRY(ctx_scratch(ctx, SCR_TMP2, zbytes, &zbuf));
+  RCB_TRY(ctx_scratch(ctx, SCR_TMP, pbytes, &pbuf));
+  if (!carry) RCB_TRY(ctx_scratch(ctx, SCR_HT, (size_t)esn->sumN * sizeof(float), &carry));
+  std::vector<cudaEvent_t> done((size_t)nl * nch);
+  for (auto& e : done) RCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaEvent_t fork;
+  RCB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  RCB_CUDA(cudaEventRecord(fork, main_stream));
+  for (int l = 0; l < nl; ++l) RCB_CUDA(cudaStreamWaitEvent(ctx->aux_streams[l], fork, 0));
+  ctx->timers_muted = true;  // from here to the join nothing returns early: the context's stream is swapped per layer
+  int32_t st = RCB_OK;
+  for (int64_t c = 0; c < nch && st == RCB_OK; ++c) {
+    const int64_t t0 = c * chunk, len = std::min(chunk, Tc - t0);
+    int c_off = 0;
+    for (int l = 0; l < nl && st == RCB_OK; ++l) {
+      Layer& L = esn->layers[(size_t)l];
+      cudaStream_t sl = ctx->aux_streams[l];
+      ctx->stream = sl;  // the launchers issue on the context's stream
+      CollectArgs a;
+      a.layer = &L; a.dtype = RCB_F32; a.T = len; a.B = 1;
+      a.h_stride = esn->sumN; a.h_off = c_off;
+      a.h0 = c == 0 ? h0_dev : carry; a.hT = carry;
+      if (l == 0) {
+        a.u = (const float*)u_dev + (size_t)t0 * L.d_in;
+      } else {
+        const Layer& Lp = esn->layers[(size_t)l - 1];
+        const float* zin = (const float*)((const char*)zbuf + zoff[(size_t)l - 1]) + (size_t)t0 * Lp.feat;
+        float* P = (float*)((char*)pbuf + poff[(size_t)l]);
+        cudaStreamWaitEvent(sl, done[(size_t)(l - 1) * nch + c], 0);
+        st = launch_input_projection(ctx, L.d_Win, (int64_t)L.sell.R * L.sell.nthreads, L.d_in, zin, len, P);
+        a.pre_in = P;
+      }
+      a.states = l + 1 < nl ? (void*)((float*)((char*)zbuf + zoff[(size_t)l]) + (size_t)t0 * L.feat)
+                            : (states ? (void*)((float*)states + (size_t)t0 * L.feat) : nullptr);
+      if (st == RCB_OK) st = launch_collect(ctx, a);
+      cudaEventRecord(done[(size_t)l * nch + c], sl);
+      c_off += L.n;
+    }
+  }
+  ctx->stream = main_stream;
+  ctx->timers_muted = false;
+  for (int l = 0; l < nl; ++l) cudaStreamWaitEvent(main_stream, done[(size_t)l * nch + (nch - 1)], 0);
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  for (auto& e : done) cudaEventDestroy(e);
+  cudaEventDestroy(fork);
+  if (st == RCB_OK) snprintf(ctx->last_kernel + strlen(ctx->last_kernel), sizeof(ctx->last_kernel) - strlen(ctx->last_kernel), " [layer pipeline x%lld]", (long long)nch);
+  return st;
+}
+
 // One pass of all layers over `Bc` sequences x `Tc` steps (device pointers).  `states` receives the
 // last layer's modified states (F x Tc x Bc) or is nullptr.  h: packed sumN x Bc carry, in/out.
 static int32_t collect_device(rcb_esn* esn, const void* u_dev, int64_t Tc, int64_t Bc, const void* h0_dev, void* states,
@@ -345,6 +418,13 @@ static int32_t collect_device(rcb_esn* esn, const void* u_dev, int64_t Tc, int64
   rcb_ctx* ctx = esn->ctx;
   const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4;
   const int nl = (int)esn->layers.size();
+  if (nl > 1 && Bc == 1 && esn->desc.data_dtype == RCB_F32 && !esn->member_count) {
+    bool fusable = true;
+    for (const Layer& L : esn->layers) fusable = fusable && chain_is_fusable(L.chain);
+    int64_t chunk = std::max<int64_t>(512, (Tc + 23) / 24);
+    if (const char* e = getenv("RCB_DEEP_CHUNK")) chunk = atoll(e);  // testing hook (0 disables the layer pipeline)
+    if (fusable && chunk > 0 && Tc >= 3 * chunk) return collect_device_pipelined(esn, u_dev, Tc, h0_dev, states, hT_dev, chunk);
+  }
   const void* zin = nullptr;  // modified states of the previous layer
   int c_off = 0;
   for (int l = 0; l < nl; ++l) {
@@ -456,6 +536,8 @@ int32_t rcb_ctx_destroy(rcb_ctx* ctx) {
   delete[] p;
   for (int i = 0; i < SCR_COUNT; ++i) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (cudaStream_t& s : ctx->aux_streams)
+    if (s) { cudaStreamDestroy(s); s = nullptr; }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return RCB_OK;

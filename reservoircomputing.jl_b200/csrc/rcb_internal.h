@@ -150,6 +150,8 @@ struct rcb_ctx {
   char last_kernel[96] = "";
   int last_gram_tensor = 0;   // 1 when the most recent Gram ran on the tcgen05 path  // variant name of the most recent recurrence launch
   void* timer_pools = nullptr;  // rcb::TimerPool[3]
+  bool timers_muted = false;    // set while a pipelined region times itself as a whole
+  cudaStream_t aux_streams[RCB_MAX_LAYERS] = {};  // one per DeepESN layer (layer pipeline over time chunks), created on demand
   // pinned staging + scratch, grown on demand
   void* pinned = nullptr;
   size_t pinned_bytes = 0;

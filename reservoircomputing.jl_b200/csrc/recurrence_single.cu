@@ -13,7 +13,7 @@
 //     written during that step), one feature per lane: conflict-free reads, coalesced streaming stores;
 //   * deep layers read their precomputed input projection one step ahead (registers), so the HBM latency of that
 //     stream is off the chain.
-// Applies to: tanh, scalar leak, no bias, no member parameters, modifier none / NLAT2, d_in in {1, 3} or a precomputed
+// Applies to: tanh, scalar leak, no bias, no member parameters, modifier none / NLAT2 (+ trailing Pad), d_in in {1, 3} or a precomputed
 // projection; everything else keeps using recurrence_fast.cu / recurrence.cu.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -34,6 +34,8 @@ struct SingleArgs {
   uint32_t stream_bytes;        // staged bytes (multiple of 16)
   uint32_t stage_win;           // W_in staged as well
   float lc, oml, m2l;           // a, 1-a, -2a
+  int has_pad;                  // trailing Pad (states.jl:79-82): feature n = pad value
+  float pad;
 };
 
 __device__ __forceinline__ float ex2a(float y) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y)); return e; }
@@ -107,7 +109,9 @@ __global__ void __launch_bounds__(1024, 1) k1_single_kernel(const RecParams p, c
       if constexpr (DIN == 3) { u1 = uc[1]; u2 = uc[2]; }
       if (tid < DIN && t + 1 < T) u_s[((t + 1) & 1) * 4 + tid] = __ldg(u_g + (size_t)(t + 1) * DIN + tid);
     }
-    float* po = out_g + ((size_t)seq * p.T + (t - 1)) * n;
+    const int F = n + a.has_pad;
+    float* po = out_g + ((size_t)seq * p.T + (t - 1)) * F;
+    if (do_out && a.has_pad && tid == 0) __stcs(po + n, a.pad);
     const unsigned char* wp = wbase;
 #pragma unroll
     for (int k = 0; k < MAXR; ++k) {
@@ -205,12 +209,12 @@ int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f
   if (!p.pre_in && !(Win4 && (p.d_in == 1 || p.d_in == 3))) return RCB_OK;
   if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.bias || p.leakv || p.member_scale || p.member_leak || p.Ot) return RCB_OK;
   const int modk = p.raw || p.mod.kind == 0 ? 0 : p.mod.kind;
-  if ((modk != 0 && modk != RCB_MOD_NLAT2) || (!p.raw && p.mod.has_pad)) return RCB_OK;
+  if (modk != 0 && modk != RCB_MOD_NLAT2) return RCB_OK;
   if ((long long)p.npad * 4 > 65535) return RCB_OK;  // 16-bit column*4
   const size_t sb = (f4.stream_bytes + 15) / 16 * 16, pb = ((size_t)p.npos * 2 + 15) / 16 * 16, wb = (size_t)p.npos * 16;
   size_t smem = 2 * (size_t)p.npad * 4 + 32 + sb + pb + 16;
   if (smem > ctx->smem_optin) return RCB_OK;  // the stream does not fit: the other kernels read it through L2
-  SingleArgs a{f4.stream, f4.warp_off, f4.wwords, reinterpret_cast<const float4*>(Win4), (uint32_t)sb, 0u, 0.f, 0.f, 0.f};
+  SingleArgs a{f4.stream, f4.warp_off, f4.wwords, reinterpret_cast<const float4*>(Win4), (uint32_t)sb, 0u, 0.f, 0.f, 0.f, (!p.raw && p.mod.has_pad) ? 1 : 0, (float)p.mod.pad};
   if (din > 0 && smem + wb <= ctx->smem_optin) { a.stage_win = 1; smem += wb; }
   a.lc = (float)p.leak; a.oml = 1.0f - a.lc; a.m2l = -2.0f * a.lc;  // (1-a) in the input eltype, esn_cell.jl:186-200
   timer_begin(ctx, RCB_TIMER_RECURRENCE);

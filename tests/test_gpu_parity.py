@@ -1008,13 +1008,14 @@ def test_randomized_train_predict(R, c):
 
 
 @pytest.mark.parametrize("N,d_in,mod,B,T", [(300, 3, "nlat2", 1, 60), (300, 1, "none", 2, 33), (1024, 3, "nlat2", 1, 40), (2048, 3, "none", 3, 25),
-                                             (4096, 1, "nlat2", 1, 30), (4096, 3, "nlat2", 2, 12), (1100, 3, "nlat2", 1, 20), (65, 1, "nlat2", 5, 50)])
+                                             (4096, 1, "nlat2", 1, 30), (4096, 3, "nlat2", 2, 12), (1100, 3, "nlat2", 1, 20), (65, 1, "nlat2", 5, 50),
+                                             (300, 3, "nlat2_pad", 2, 21), (2048, 1, "pad", 1, 9)])
 def test_single_sequence_kernel_parity(R, N, d_in, mod, B, T):
     """The one-sequence-per-CTA kernel (recurrence_single.cu: BASELINE configs 1, 2 sequential, 4) against the oracle, incl.
     N that is not a multiple of the CTA width, both input widths, the carry, and a second call continuing from it."""
     rng = np.random.default_rng(N + 7 * B)
     esn = R.ESN(d_in, N, d_in, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=N > 1500), leak_coefficient=0.6,
-                state_modifiers=(R.NLAT2,) if mod == "nlat2" else ())
+                state_modifiers=dict(nlat2=(R.NLAT2,), none=(), nlat2_pad=(R.NLAT2, R.Pad(1.0)), pad=(R.Pad(-2.5),))[mod])
     ps, st = R.setup(rng, esn)
     data = np.asfortranarray(rng.standard_normal((d_in, 2 * T, B)).astype(np.float32))
     h0 = rng.standard_normal((N, B)).astype(np.float32)
@@ -1046,3 +1047,36 @@ def test_single_sequence_kernel_in_deep_esn(R):
         assert state_err(states[:, :, b], ref) <= STATE_RTOL
         for l in range(3):
             assert state_err(st2.cells[l].carry[0][:, b:b + 1], hs[l].reshape(-1, 1)) <= STATE_RTOL
+
+
+@pytest.mark.parametrize("chunk", [16, 37])
+def test_deep_esn_layer_pipeline(R, chunk, monkeypatch):
+    """One-sequence DeepESN: the layers run as a pipeline over time chunks on separate streams.  Forced to
+    small chunks here; the result must equal the layer-by-layer pass bit for bit (same kernels, same arithmetic) and
+    match the oracle, including the carries handed from chunk to chunk."""
+    rng = np.random.default_rng(12)
+    res = [128, 192, 96, 160]
+    desn = R.DeepESN(3, res, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.08), leak_coefficient=(1.0, 0.8, 0.6, 0.4),
+                     state_modifiers=(R.NLAT2, R.NLAT2, R.NLAT1, (R.NLAT2, R.Pad(1.0))))
+    ps, st = R.setup(rng, desn)
+    T = 150
+    data = np.asfortranarray(rng.standard_normal((3, T)).astype(np.float32))
+    hs0 = [rng.standard_normal(n).astype(np.float32) for n in res]
+    st0 = fixed_h0(R, st, desn, hs0)
+    monkeypatch.setenv("RCB_DEEP_CHUNK", "0")
+    plain, st_plain = R.collectstates(desn, data, ps, st0)
+    assert "pipeline" not in R.default_device().last_kernel()
+    monkeypatch.setenv("RCB_DEEP_CHUNK", str(chunk))
+    piped, st_piped = R.collectstates(desn, data, ps, st0)
+    assert "layer pipeline" in R.default_device().last_kernel()
+    assert np.array_equal(plain, piped)
+    for l in range(4):
+        assert np.array_equal(st_plain.cells[l].carry[0], st_piped.cells[l].carry[0])
+    ref, hs = O.collectstates(oracle_layers(R, desn, ps), data, hs0)
+    assert state_err(piped, ref) <= STATE_RTOL
+    # train through the pipelined collect
+    tgt = np.asfortranarray(rng.standard_normal((3, T)).astype(np.float32))
+    ps_a, _ = R.train(desn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=10)
+    monkeypatch.setenv("RCB_DEEP_CHUNK", "0")
+    ps_b, _ = R.train(desn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=10)
+    assert np.allclose(ps_a.readout.weight, ps_b.readout.weight, rtol=1e-9, atol=1e-12)
