@@ -1080,3 +1080,43 @@ def test_deep_esn_layer_pipeline(R, chunk, monkeypatch):
     monkeypatch.setenv("RCB_DEEP_CHUNK", "0")
     ps_b, _ = R.train(desn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=10)
     assert np.allclose(ps_a.readout.weight, ps_b.readout.weight, rtol=1e-9, atol=1e-12)
+
+
+def test_plumbing_entry_point_error_paths(R):
+    """Argument errors of the SURVEY 8f entry points map onto the reference's exception types (ArgumentError /
+    DimensionMismatch) through the same status codes as the core path."""
+    import ctypes as C
+    from rcb200 import _lib as L
+
+    dev = R.default_device()
+    lib = L.lib()
+    x = np.zeros((4, 6, 1), np.float32, order="F")
+    out = np.zeros((12, 6, 1), np.float32, order="F")
+    with pytest.raises(R.ArgumentError, match="num_delays"):
+        L.check(lib.rcb_delay_features(dev.handle, L.ptr(x), 0, 4, 6, 1, -1, 1, None, 0, L.ptr(out), None))
+    with pytest.raises(R.ArgumentError, match="stride"):
+        L.check(lib.rcb_delay_features(dev.handle, L.ptr(x), 0, 4, 6, 1, 2, 0, None, 0, L.ptr(out), None))
+    with pytest.raises(R.ArgumentError):
+        L.check(lib.rcb_delay_features(dev.handle, None, 0, 4, 6, 1, 2, 1, None, 0, L.ptr(out), None))
+    with pytest.raises(R.DimensionMismatch):      # DelayLayer row check, basic.jl:427-431
+        R.DelayLayer(3).apply_sequence(np.zeros((4, 5), np.float32), R.DelayLayer(3).initialstates(np.random.default_rng(0)))
+    with pytest.raises(R.DimensionMismatch):      # init_delay tuple length, basic.jl:381-388
+        R.DelayLayer(3, num_delays=2, init_delay=(R.zeros32,))
+    with pytest.raises(R.DimensionMismatch):
+        R.extend_features(np.zeros((2, 5), np.float32), np.zeros((3, 6), np.float32))
+    with pytest.raises(R.ArgumentError, match="at least one state"):   # conceptors.jl:29
+        L.check(lib.rcb_correlation_matrix(dev.handle, L.ptr(x), 0, 4, 0, 4, 0, L.ptr(out)))
+    with pytest.raises(R.DimensionMismatch):
+        L.check(lib.rcb_correlation_matrix(dev.handle, L.ptr(x), 0, 4, 6, 2, 0, L.ptr(out)))
+    rho, dim = C.c_double(), C.c_int32()
+    with pytest.raises(R.ArgumentError):
+        L.check(lib.rcb_spectral_radius_dense(dev.handle, None, 4, 4, 0.0, 0, C.byref(rho), C.byref(dim)))
+    W = np.asfortranarray(np.diag([0.5, -2.0, 1.0, 0.25]).astype(np.float32))
+    L.check(lib.rcb_spectral_radius_dense(dev.handle, L.ptr(W), 4, 4, 0.0, 0, C.byref(rho), C.byref(dim)))
+    assert abs(rho.value - 2.0) < 1e-12 and dim.value <= 4
+    ro = R.LinearReadout(5, 2)
+    with pytest.raises(R.DimensionMismatch):      # readout weight vs feature count
+        R.readout_apply(ro, R.NT(weight=np.zeros((2, 5))), np.zeros((4, 3), np.float32))
+    y = R.readout_apply(R.LinearReadout(4, 2, R.tanh, use_bias=True), R.NT(weight=np.ones((2, 4)), bias=np.array([0.5, -0.5])),
+                        np.full((4, 3), 0.25, np.float32))
+    assert np.allclose(y, np.tanh(np.array([[1.5], [0.5]])) * np.ones((1, 3)))   # psi(W z + b), basic.jl:171-182
