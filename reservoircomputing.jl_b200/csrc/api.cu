@@ -1235,12 +1235,42 @@ static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B,
   const size_t y_bytes = (size_t)esn->desc.out_dims * T * B * sizeof(double);
   if (!is_device_ptr(y_out)) {
     void* p = nullptr;
-    RCB_TRY(ctx_scratch(ctx, SCR_Y, y_bytes, &p));
+    RCB_TRY(ctx_scratch(ctx, SCR_TGT, y_bytes, &p));  // (SCR_Y is an inter-layer buffer of the DeepESN collect)
     y_dev = (double*)p;
   }
-  PredictArgs a;
-  a.esn = esn; a.compute_dtype = compute_dtype; a.autoregressive = autoreg; a.u = u_dev; a.T = T; a.B = B; a.h = h_dev; a.y = y_dev;
-  RCB_TRY(launch_predict(ctx, a));
+  // Teacher-forced prediction has no feedback: y_t = readout(features_t) (predict.jl:163-177), so it is the recurrence kernels
+  // (K1, every tuned variant) followed by the readout over the collected features, in pieces that fit a scratch budget —
+  // 3-4x less per step than the fused loop K4, which stays for the autoregressive mode and per-member readouts.
+  const size_t fbytes = (size_t)esn->feat * dsz;
+  const size_t budget = (size_t)1 << 30;
+  const bool via_collect = !autoreg && esn->readout_members <= 1 && (fbytes * (size_t)T <= budget || B == 1);
+  if (via_collect) {
+    void* carry = h_dev;
+    if (!carry) {
+      RCB_TRY(ctx_scratch(ctx, SCR_HT, h_bytes, &carry));
+      RCB_CUDA(cudaMemsetAsync(carry, 0, h_bytes, ctx->stream));
+    }
+    const bool by_seq = fbytes * (size_t)T <= budget;
+    const int64_t Bc = by_seq ? std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(budget / (fbytes * (size_t)T)))) : 1;
+    const int64_t Tc = by_seq ? T : std::max<int64_t>(1, (int64_t)(budget / fbytes));
+    void* zs = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_STATES, fbytes * (size_t)Tc * (size_t)Bc, &zs));
+    for (int64_t b0 = 0; b0 < B; b0 += Bc) {
+      const int64_t bc = std::min(Bc, B - b0);
+      for (int64_t t0 = 0; t0 < T; t0 += Tc) {
+        const int64_t tc = std::min(Tc, T - t0);
+        const char* uc = (const char*)u_dev + ((size_t)b0 * T + t0) * esn->desc.in_dims * dsz;   // (t0 > 0 only when B == 1)
+        char* hc = (char*)carry + (size_t)b0 * esn->sumN * csz;
+        RCB_TRY(collect_device(esn, uc, tc, bc, hc, zs, hc, b0));
+        RCB_TRY(launch_readout(ctx, esn->d_Wout, esn->d_bout, esn->desc.readout_activation, zs, esn->desc.data_dtype, esn->feat,
+                               tc * bc, (int)esn->desc.out_dims, y_dev + ((size_t)b0 * T + t0) * esn->desc.out_dims));
+      }
+    }
+  } else {
+    PredictArgs a;
+    a.esn = esn; a.compute_dtype = compute_dtype; a.autoregressive = autoreg; a.u = u_dev; a.T = T; a.B = B; a.h = h_dev; a.y = y_dev;
+    RCB_TRY(launch_predict(ctx, a));
+  }
   if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, y_bytes));
   if (h_inout && h_dev != h_inout) RCB_TRY(from_device(ctx, h_inout, h_dev, h_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
