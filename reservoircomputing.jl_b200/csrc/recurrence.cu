@@ -480,6 +480,11 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
 }
 
 int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
+  {
+    bool launched = false;
+    const int32_t fa = launch_predict_auto(ctx, a, &launched);
+    if (fa != RCB_OK || launched) return fa;
+  }
   const rcb_esn& E = *a.esn;
   PredParams p{};
   p.n_layers = (int)E.layers.size();

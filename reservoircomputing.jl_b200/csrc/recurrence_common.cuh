@@ -181,4 +181,7 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
 // recurrence_single.cu: one sequence per CTA (B <= #SMs), instruction-lean; f4: the stream with column*4, Win4 may be null with pre_in
 int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, bool* launched);
 
+// recurrence_single.cu: autoregressive predict of a single-layer ESN, one sequence per CTA, W / W_in resident, y in registers
+int32_t launch_predict_auto(rcb_ctx* ctx, const PredictArgs& pa, bool* launched);
+
 }  // namespace rcb

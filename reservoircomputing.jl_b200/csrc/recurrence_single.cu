@@ -227,4 +227,227 @@ int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f
   return st;
 }
 
+// ================================================================================================================
+// K4 "auto": the autoregressive generative loop (src/predict.jl:74-88) for one ESN layer, one sequence per CTA, with
+// everything of a step on chip: y_t = W_out z_t is fed back as u_{t+1}.  Same staging as k1_single (W stream,
+// permutation, W_in resident); the step is gathers -> tanh -> barrier -> readout partials (modifier evaluated on the
+// fly, Float64 accumulation, W_out through L1) -> barrier -> every warp sums the per-warp partials itself and keeps y
+// in registers: two barriers per step, no global round trip.  T = float or double: the reference runs this loop in
+// Float64 after the default (Float64) ridge fit because the fed-back y promotes the cell (esn_cell.jl:176).
+// ================================================================================================================
+namespace {
+
+struct AutoArgs {
+  const unsigned char* stream;
+  const uint32_t* warp_off;
+  const uint64_t* wwords;
+  const float4* Win4;
+  const uint16_t* perm;
+  uint32_t stream_bytes, stage_win;
+  int n, npad, nthreads, R, npos, d_io, nwarps, has_pad, ro_act, u_is_f64;
+  double leak, pad;
+  const double* Wout;   // d_io x F
+  const double* bout;
+  const void* u0;       // d_io x B (data dtype)
+  void* h;              // n x B (compute dtype), in/out (may be null)
+  double* y;            // d_io x steps x B
+  long long steps;
+};
+
+template <typename T> __device__ __forceinline__ T tanh_step(T x);
+template <> __device__ __forceinline__ double tanh_step<double>(double x) { return tanh(x); }
+template <> __device__ __forceinline__ float tanh_step<float>(float x) {
+  const float r = rcpa(ex2a(x * 2.8853900817779268f) + 1.0f);
+  const float x2 = x * x;
+  const float tp = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
+  return fabsf(x) < 0.15f ? tp : fmaf(-2.0f, r, 1.0f);
+}
+
+template <typename T, int MODK>
+__global__ void __launch_bounds__(1024, 1) k4_auto_kernel(const AutoArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthr = a.nthreads, R = a.R, n = a.n, D = a.d_io;
+  const uint32_t bufB = (uint32_t)sizeof(T) * (uint32_t)a.npad;
+  double* red_s = reinterpret_cast<double*>(smem + 2 * bufB);            // [nwarps][4]
+  unsigned char* stage = smem + 2 * bufB + (size_t)a.nwarps * 32;
+  uint16_t* perm_s = reinterpret_cast<uint16_t*>(stage + a.stream_bytes);
+  const size_t perm_bytes = ((size_t)a.npos * 2 + 15) / 16 * 16;
+  const float4* win_s = reinterpret_cast<const float4*>(stage + a.stream_bytes + perm_bytes);
+  const long long seq = blockIdx.x;
+  T* h_g = reinterpret_cast<T*>(a.h);
+
+  for (uint32_t i = tid * 16u; i < a.stream_bytes; i += (uint32_t)nthr * 16u)
+    *reinterpret_cast<uint4*>(stage + i) = __ldg(reinterpret_cast<const uint4*>(a.stream + i));
+  for (int i = tid; i < a.npos; i += nthr) perm_s[i] = __ldg(a.perm + i);
+  if (a.stage_win)
+    for (int i = tid; i < a.npos; i += nthr) const_cast<float4*>(win_s)[i] = __ldg(a.Win4 + i);
+  for (int i = tid; i < a.npad; i += nthr) {
+    const T v = (h_g && i < n) ? h_g[(size_t)seq * n + i] : T(0);
+    *reinterpret_cast<T*>(smem + sizeof(T) * i) = v;
+    *reinterpret_cast<T*>(smem + bufB + sizeof(T) * i) = v;
+  }
+  T yv[4] = {T(0), T(0), T(0), T(0)};   // the current input: u0, then the fed-back outputs (predict.jl:78-84)
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d < D) yv[d] = a.u_is_f64 ? (T) reinterpret_cast<const double*>(a.u0)[(size_t)seq * D + d]
+                                  : (T) reinterpret_cast<const float*>(a.u0)[(size_t)seq * D + d];
+  __syncthreads();
+  const unsigned char* wbase = stage + a.warp_off[warp];
+  const unsigned long long wword0 = a.wwords[2 * warp], wword1 = a.wwords[2 * warp + 1];
+  uint32_t roff[MAXR];
+#pragma unroll
+  for (int k = 0; k < MAXR; ++k) {
+    const unsigned r16 = k < R ? (unsigned)perm_s[k * nthr + tid] : 0xFFFFu;
+    roff[k] = r16 != 0xFFFFu ? r16 * (uint32_t)sizeof(T) : 0xFFFFFFFFu;
+  }
+  const T lc = (T)a.leak, oml = T(1) - lc;   // one(T) - T(leak), esn_cell.jl:186-200
+  const int F = n + a.has_pad;
+  const double* Wout = a.Wout;
+  constexpr uint32_t CSH = sizeof(T) == 8 ? 1u : 0u;   // the stream carries column * 4: byte offset of a float, half that of a double
+
+  for (long long t = 0; t < a.steps; ++t) {
+    const unsigned char* cur = smem + ((t & 1) ? bufB : 0u);
+    unsigned char* nxt = smem + ((t & 1) ? 0u : bufB);
+    const unsigned char* wp = wbase;
+#pragma unroll
+    for (int k = 0; k < MAXR; ++k) {
+      if (k >= R) break;
+      const int pos = k * nthr + tid;
+      const int wd = (int)(((k < 8 ? wword0 : wword1) >> (8 * (k & 7))) & 255ull);
+      const float4 w = a.stage_win ? win_s[pos] : __ldg(a.Win4 + pos);
+      const uint32_t ro = roff[k];
+      const T hold = *reinterpret_cast<const T*>(cur + (ro != 0xFFFFFFFFu ? ro : 0u));
+      T acc0 = T(0), acc1 = T(0);
+      for (int q = 0; q < (wd >> 2); ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(wp + lane * 16);
+        const uint2 c = *reinterpret_cast<const uint2*>(wp + 512 + lane * 8);
+        wp += 768;
+        acc0 = fma((T)v.x, *reinterpret_cast<const T*>(cur + ((c.x & 0xFFFFu) << CSH)), acc0);
+        acc1 = fma((T)v.y, *reinterpret_cast<const T*>(cur + ((c.x >> 16) << CSH)), acc1);
+        acc0 = fma((T)v.z, *reinterpret_cast<const T*>(cur + ((c.y & 0xFFFFu) << CSH)), acc0);
+        acc1 = fma((T)v.w, *reinterpret_cast<const T*>(cur + ((c.y >> 16) << CSH)), acc1);
+      }
+      if (wd & 2) {
+        const float2 v = *reinterpret_cast<const float2*>(wp + lane * 8);
+        const uint32_t c = *reinterpret_cast<const uint32_t*>(wp + 256 + lane * 4);
+        wp += 384;
+        acc0 = fma((T)v.x, *reinterpret_cast<const T*>(cur + ((c & 0xFFFFu) << CSH)), acc0);
+        acc1 = fma((T)v.y, *reinterpret_cast<const T*>(cur + ((c >> 16) << CSH)), acc1);
+      }
+      if (wd & 1) {
+        const float v = *reinterpret_cast<const float*>(wp + lane * 4);
+        const uint32_t c = (uint32_t)*reinterpret_cast<const unsigned short*>(wp + 128 + lane * 2);
+        wp += 192;
+        acc0 = fma((T)v, *reinterpret_cast<const T*>(cur + (c << CSH)), acc0);
+      }
+      T x = acc0 + acc1;
+      T win = (T)w.x * yv[0];            // W_in * u (generics.jl:91-96), added to the recurrent term (esn_cell.jl:178-180)
+      if (D > 1) win = fma((T)w.y, yv[1], win);
+      if (D > 2) win = fma((T)w.z, yv[2], win);
+      if (D > 3) win = fma((T)w.w, yv[3], win);
+      const T hn = oml * hold + lc * tanh_step<T>(win + x);
+      if (ro != 0xFFFFFFFFu) *reinterpret_cast<T*>(nxt + ro) = hn;
+    }
+    __syncthreads();
+    // readout partials: y = psi(W_out z + b), z = modifier(new state) evaluated on the fly (basic.jl:171-182)
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    const T* zs = reinterpret_cast<const T*>(nxt);
+    for (int f = tid; f < F; f += nthr) {
+      T z;
+      if (f == n) z = (T)a.pad;                                              // Pad, states.jl:79-82
+      else if (MODK == 2 && (f & 1) == 0 && f >= 2) z = zs[f - 1] * zs[f - 2];  // NLAT2, states.jl:277-285
+      else z = zs[f];
+      const double zf = (double)z;
+      const double* wf = Wout + (size_t)f * D;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < D) part[q] = fma(__ldg(wf + q), zf, part[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= D) break;
+      double v = part[q];
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+      if (lane == 0) red_s[warp * 4 + q] = v;
+    }
+    __syncthreads();
+    // every warp reduces the per-warp partials itself (lane o owns output o) and broadcasts: y stays in registers,
+    // no third barrier (a 64-bit shuffle tree over the warps measured slower than this short serial sum)
+    double ysum = 0.0;
+    if (lane < D) {
+      for (int w2 = 0; w2 < a.nwarps; ++w2) ysum += red_s[w2 * 4 + lane];
+      if (a.bout) ysum += __ldg(a.bout + lane);
+      ysum = apply_act<double>(a.ro_act, ysum);
+      if (warp == 0) a.y[((size_t)seq * a.steps + t) * D + lane] = ysum;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < D) yv[d] = (T)__shfl_sync(0xffffffffu, ysum, d);   // y becomes the next input (predict.jl:83)
+  }
+  if (h_g) {
+    const unsigned char* fin = smem + ((a.steps & 1) ? bufB : 0u);
+    for (int i = tid; i < n; i += nthr) h_g[(size_t)seq * n + i] = *reinterpret_cast<const T*>(fin + sizeof(T) * i);
+  }
+}
+
+template <typename T, int MODK>
+int32_t launch_auto_one(rcb_ctx* ctx, const AutoArgs& a, size_t smem, int B) {
+  auto kern = k4_auto_kernel<T, MODK>;
+  RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B, a.nthreads, smem, ctx->stream>>>(a);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k4_auto<%s,%s> grid=%d", sizeof(T) == 8 ? "f64" : "f32", MODK == 2 ? "nlat2" : "raw", B);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+}  // namespace
+
+// Autoregressive predict of a single-layer ESN with everything on chip; *launched stays false outside this shape.
+int32_t launch_predict_auto(rcb_ctx* ctx, const PredictArgs& pa, bool* launched) {
+  *launched = false;
+  const rcb_esn& E = *pa.esn;
+  const char* mode = getenv("RCB_K4_MODE");  // testing hook: "generic" keeps the general fused loop
+  if (mode && !strcmp(mode, "generic")) return RCB_OK;
+  if (!pa.autoregressive || E.layers.size() != 1 || E.readout_members > 1 || E.member_count) return RCB_OK;
+  const Layer& L = E.layers[0];
+  if (!L.fast4.ok || L.fast4.stream_bytes == 0 || !L.d_Win4 || L.sell.R > MAXR) return RCB_OK;
+  if (E.desc.in_dims != E.desc.out_dims || E.desc.in_dims > 3 || E.desc.in_dims == 2) return RCB_OK;  // Win4 holds 1 or 3 input rows
+  if (!(L.desc.activation == RCB_ACT_TANH || L.desc.activation == RCB_ACT_TANH_FAST) || L.desc.use_bias || L.desc.leak_is_vector ||
+      L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN)
+    return RCB_OK;
+  if (!chain_is_fusable(L.chain)) return RCB_OK;
+  int kind = 0, has_pad = 0;
+  double pad = 0.0;
+  {
+    int i = 0;
+    if (L.chain.n > 0 && L.chain.kind[0] != RCB_MOD_PAD) { kind = L.chain.kind[0]; i = 1; }
+    if (i < L.chain.n && L.chain.kind[i] == RCB_MOD_PAD) { has_pad = 1; pad = L.chain.param[i]; }
+  }
+  if (kind != 0 && kind != RCB_MOD_NLAT2) return RCB_OK;
+  const int npad = (L.n + 3) & ~3, npos = L.sell.R * L.sell.nthreads, nwarps = L.sell.nthreads / 32;
+  if ((long long)npad * 4 > 65535) return RCB_OK;
+  const size_t esz = pa.compute_dtype == RCB_F64 ? 8 : 4;
+  const size_t sb = (L.fast4.stream_bytes + 15) / 16 * 16, pb = ((size_t)npos * 2 + 15) / 16 * 16, wb = (size_t)npos * 16;
+  size_t smem = 2 * (size_t)npad * esz + (size_t)nwarps * 32 + sb + pb + 16;
+  if (smem > ctx->smem_optin) return RCB_OK;
+  AutoArgs a{};
+  a.stream = L.fast4.stream; a.warp_off = L.fast4.warp_off; a.wwords = L.fast4.wwords;
+  a.Win4 = reinterpret_cast<const float4*>(L.d_Win4); a.perm = L.sell.perm;
+  a.stream_bytes = (uint32_t)sb; a.stage_win = 0;
+  if (smem + wb <= ctx->smem_optin) { a.stage_win = 1; smem += wb; }
+  a.n = L.n; a.npad = npad; a.nthreads = L.sell.nthreads; a.R = L.sell.R; a.npos = npos; a.d_io = E.desc.in_dims; a.nwarps = nwarps;
+  a.has_pad = has_pad; a.pad = pad; a.ro_act = E.desc.readout_activation; a.u_is_f64 = E.desc.data_dtype == RCB_F64;
+  a.leak = L.desc.leak_scalar; a.Wout = E.d_Wout; a.bout = E.d_bout; a.u0 = pa.u; a.h = pa.h; a.y = pa.y; a.steps = pa.T;
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  int32_t st;
+  if (pa.compute_dtype == RCB_F64) st = kind == 2 ? launch_auto_one<double, 2>(ctx, a, smem, (int)pa.B) : launch_auto_one<double, 0>(ctx, a, smem, (int)pa.B);
+  else st = kind == 2 ? launch_auto_one<float, 2>(ctx, a, smem, (int)pa.B) : launch_auto_one<float, 0>(ctx, a, smem, (int)pa.B);
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  if (st == RCB_OK) *launched = true;
+  return st;
+}
+
 }  // namespace rcb

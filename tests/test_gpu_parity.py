@@ -1120,3 +1120,30 @@ def test_plumbing_entry_point_error_paths(R):
     y = R.readout_apply(R.LinearReadout(4, 2, R.tanh, use_bias=True), R.NT(weight=np.ones((2, 4)), bias=np.array([0.5, -0.5])),
                         np.full((4, 3), 0.25, np.float32))
     assert np.allclose(y, np.tanh(np.array([[1.5], [0.5]])) * np.ones((1, 3)))   # psi(W z + b), basic.jl:171-182
+
+
+@pytest.mark.parametrize("N,d,mods,f64", [(300, 3, "nlat2", True), (300, 3, "nlat2_pad", False), (1024, 1, "none", True), (65, 3, "pad", True)])
+def test_autoregressive_kernel_matches_generic_loop_and_oracle(R, N, d, mods, f64, monkeypatch):
+    """The on-chip autoregressive kernel (k4_auto) against the general fused loop (same library, RCB_K4_MODE=generic)
+    and against the oracle's step-by-step loop (src/predict.jl:74-88), in the reference's Float64 promotion and in Float32."""
+    rng = np.random.default_rng(N + d)
+    chain = dict(nlat2=(R.NLAT2,), nlat2_pad=(R.NLAT2, R.Pad(1.0)), none=(), pad=(R.Pad(0.5),))[mods]
+    esn = R.ESN(d, N, d, init_reservoir=R.rand_sparse(radius=0.9, sparsity=min(1.0, 6 / N)), leak_coefficient=0.7, state_modifiers=chain)
+    ps, st = R.setup(rng, esn)
+    T = 400
+    tt = np.arange(T + 1)[None, :]
+    series = (np.sin(0.07 * tt * (1 + np.arange(d))[:, None]) * 0.6).astype(np.float32)
+    data, tgt = np.asfortranarray(series[:, :T]), np.asfortranarray(series[:, 1:])
+    obj = R.RidgeRegression(1e-3) if f64 else R.RidgeRegression(np.float32, 1e-3)
+    ps2, st2 = R.train(esn, data, tgt, ps, st, objective=obj, washout=50)
+    u0 = tgt[:, -1]
+    Y, st3 = R.predict(esn, 40, ps2, st2, initialdata=u0)
+    assert "k4_auto" in R.default_device().last_kernel() and Y.dtype == (np.float64 if f64 else np.float32)
+    monkeypatch.setenv("RCB_K4_MODE", "generic")
+    Yg, st3g = R.predict(esn, 40, ps2, st2, initialdata=u0)
+    assert "k4_auto" not in R.default_device().last_kernel()
+    assert state_err(Y, Yg) <= (1e-9 if f64 else 1e-4)
+    assert state_err(st3.reservoir.carry[0].reshape(-1, 1), st3g.reservoir.carry[0].reshape(-1, 1)) <= (1e-9 if f64 else 1e-4)
+    layers = oracle_layers(R, esn, ps)
+    Yo, _ = O.predict_autoregressive(layers, ps2.readout.weight, 40, u0, [st2.reservoir.carry[0]])
+    assert state_err(Y, Yo) <= (1e-9 if f64 else 1e-3)
