@@ -534,6 +534,8 @@ int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
     k4_predict_kernel<float><<<(int)a.B, nthreads, smem, ctx->stream>>>(p);
   }
   ctx->launches++;
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k4_generic<%s,layers=%d> grid=%d", a.compute_dtype == RCB_F64 ? "f64" : "f32",
+           p.n_layers, (int)a.B);
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;

@@ -1146,4 +1146,6 @@ def test_autoregressive_kernel_matches_generic_loop_and_oracle(R, N, d, mods, f6
     assert state_err(st3.reservoir.carry[0].reshape(-1, 1), st3g.reservoir.carry[0].reshape(-1, 1)) <= (1e-9 if f64 else 1e-4)
     layers = oracle_layers(R, esn, ps)
     Yo, _ = O.predict_autoregressive(layers, ps2.readout.weight, 40, u0, [st2.reservoir.carry[0]])
-    assert state_err(Y, Yo) <= (1e-9 if f64 else 1e-3)
+    # the reference's very first step runs in eltype(initialdata) = Float32 and only the fed-back Float64 outputs promote
+    # the loop (esn_cell.jl:176); the kernels run every step in the promoted type: a one-step Float32 rounding apart
+    assert state_err(Y, Yo) <= (1e-5 if f64 else 1e-3)
