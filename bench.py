@@ -95,11 +95,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_weights(w, seed=17):
+def make_weights(w, seed=17, reference=False):
     import scipy.sparse as sp
-    from rcb200.api import _rand_sparse, _scaled_rand
 
     rng = np.random.default_rng(seed)
+    if reference:  # the CPU arm stays clear of the product: the oracle's generator (same structure, ARPACK for the radius)
+        from oracle import esn_oracle as O
+
+        W = O.rand_sparse_like(rng, w["N"], radius=w["radius"], sparsity=w["k"] / w["N"], as_csc=True)
+        return sp.csc_matrix(W), O.scaled_rand_like(rng, w["N"], w["d_in"])
+    from rcb200.api import _rand_sparse, _scaled_rand
+
     W = _rand_sparse(rng, w["N"], w["N"], radius=w["radius"], sparsity=w["k"] / w["N"], return_sparse=True)
     Win = _scaled_rand(rng, w["N"], w["d_in"])
     return sp.csc_matrix(W), Win
@@ -136,12 +142,21 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def host_cores():
+    """Cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use
+    every host core, so they size their OpenMP team from the affinity mask instead of the OpenMP default."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(w, W, Win, seconds_target=12.0, threads=0):
     """The oracle's plain-C port (sparse-faithful: CSC SpMV per step, sequences over all host cores) on a
     bounded sample of the workload; returns (neuron-steps/s, cores, sample description)."""
     from oracle import c_oracle
 
-    cores = c_oracle.max_threads() if threads <= 0 else threads
+    cores = host_cores() if threads <= 0 else threads
     Bs = cores * 2
     u = lorenz_batch(Bs, 64, seed=7)
     t0 = time.perf_counter()
@@ -163,12 +178,13 @@ def run_reference(args, w):
     # CPU arm: no process group is needed; under torchrun rank 0 alone runs and prints, the other ranks exit 0
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    W, Win = make_weights(w)
+    W, Win = make_weights(w, reference=True)
     from oracle import c_oracle
 
-    cores = c_oracle.max_threads()
+    cores = host_cores()
     Bs = cores * 2
     u = lorenz_batch(Bs, 64, seed=7)
+    c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, nthreads=cores)  # spin the thread team up before probing
     t0 = time.perf_counter()
     c_oracle.collect(W, Win, u, leak=w["leak"], act=1, mod_kind=2, nthreads=cores)
     probe = time.perf_counter() - t0
