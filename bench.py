@@ -138,6 +138,7 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines must not land on stdout: ONE JSON line there
         dist.init_process_group(backend="nccl" if os.environ.get("RCB_BENCH_BACKEND", "nccl") == "nccl" else "gloo")
     return rank, world, local
 
