@@ -208,7 +208,7 @@ def run_reference(args, w):
                        "SparseMatrixCSC mat-vec (Julia is not installed; see DESIGN.md)"},
             "cpu_baseline": {"value": value, "unit": "neuron-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "neuron-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_b200(args, w):
@@ -321,7 +321,7 @@ def run_b200(args, w):
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_sample(w, W, Win)
             line["cpu_baseline"] = {"value": v, "unit": "neuron-steps/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -368,9 +368,14 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
                                         1 if c == 0 else 0, L.ptr(GC)))
         gram_ms += dev.kernel_ms(L.TIMER_GRAM)
     e[1].record()
+    e_sync = torch.cuda.Event(enable_timing=True)
     if world > 1:  # only the lower triangle of G (+ C) travels: pack -> all-reduce -> unpack
         import torch.distributed as dist
 
+        # ranks reach this point up to a few per cent of the 3 s accumulation apart; a one-element all-reduce absorbs that
+        # skew so that allreduce_s is the exchange itself (the wait is reported as rank_skew_s; train_s contains both)
+        dist.all_reduce(torch.zeros(1, device="cuda"))
+        e_sync.record()
         L.check(lib.rcb_gc_pack(dev.handle, L.ptr(GC), F, D, L.ptr(packed)))
         dist.all_reduce(packed)
         L.check(lib.rcb_gc_unpack(dev.handle, L.ptr(packed), F, D, L.ptr(GC)))
@@ -380,12 +385,16 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
     e[3].record()
     barrier()
     t_acc, t_ar, t_solve = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
+    t_skew = 0.0
     if world > 1:
         import torch.distributed as dist
 
-        t = torch.tensor([t_acc, t_ar, t_solve, k1_ms, gram_ms], device="cuda")
+        t_skew = e[1].elapsed_time(e_sync)
+        t_ar -= t_skew
+        t = torch.tensor([t_acc + t_skew, t_ar, t_solve, k1_ms, gram_ms, t_skew], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_acc, t_ar, t_solve, k1_ms, gram_ms = [float(x) for x in t]
+        # accumulation + wait is the same on every rank (they leave the sync together); t_skew: how long the fastest rank waited
+        t_acc, t_ar, t_solve, k1_ms, gram_ms, t_skew = [float(x) for x in t]
     S = float(T) * B
     tiles = sum(1 for i in range((F + 255) // 256) for j in range((F + 255) // 256) if j * 256 <= i * 256 + 255) * 2
     issued = 6.0 * 2.0 * tiles * 128 * 256 * S          # six INT8 digit-plane MMAs per tile per sample
@@ -395,6 +404,7 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
             bf16 = float(json.load(f).get("bf16_tflops", bf16))
     ok = bool(torch.isfinite(Wout).all())
     return {"train_s": (t_acc + t_ar + t_solve) * 1e-3, "recurrence_s": k1_ms * 1e-3, "gram_s": gram_ms * 1e-3, "allreduce_s": t_ar * 1e-3,
+            "rank_skew_s": t_skew * 1e-3,
             "solve_s": t_solve * 1e-3, "features": F, "samples_per_gpu": S, "lambda": lam, "finite": ok,
             "gram_algorithmic_tflops": (F * (F + 1) + 2 * F * D) * S / (gram_ms * 1e-3) / 1e12,
             "gram_issued_int8_tops": issued / (gram_ms * 1e-3) / 1e12,
@@ -408,7 +418,29 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
             "gram_mode": "tcgen05 kind::i8, 3 balanced base-256 digit planes, exact INT32 TMEM accumulation, FP64 across"}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner on stdout when the
+    first communicator comes up), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to
+    a private duplicate of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
