@@ -1243,7 +1243,8 @@ static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B,
   // 3-4x less per step than the fused loop K4, which stays for the autoregressive mode and per-member readouts.
   const size_t fbytes = (size_t)esn->feat * dsz;
   const size_t budget = (size_t)1 << 30;
-  const bool via_collect = !autoreg && esn->readout_members <= 1 && (fbytes * (size_t)T <= budget || B == 1);
+  const bool via_collect = !autoreg && esn->readout_members <= 1 && (fbytes * (size_t)T <= budget || B == 1) &&
+                           (esn->layers.size() == 1 || esn->desc.data_dtype == RCB_F32);  // (the DeepESN collect is Float32-only)
   if (via_collect) {
     void* carry = h_dev;
     if (!carry) {

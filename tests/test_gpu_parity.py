@@ -1149,3 +1149,24 @@ def test_autoregressive_kernel_matches_generic_loop_and_oracle(R, N, d, mods, f6
     # the reference's very first step runs in eltype(initialdata) = Float32 and only the fed-back Float64 outputs promote
     # the loop (esn_cell.jl:176); the kernels run every step in the promoted type: a one-step Float32 rounding apart
     assert state_err(Y, Yo) <= (1e-5 if f64 else 1e-3)
+
+
+def test_deep_esn_float64_teacher_forced_predict(R):
+    """Float64 data through a DeepESN: collectstates is Float32-only for deep models (documented limit), but predict must
+    keep working in Float64 through the general fused loop."""
+    rng = np.random.default_rng(31)
+    res = [40, 56]
+    desn = R.DeepESN(2, res, 2, init_reservoir=R.rand_sparse(radius=0.8, sparsity=0.2), leak_coefficient=0.8, state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, desn)
+    T = 30
+    data = np.asfortranarray(rng.standard_normal((2, T)))
+    W = rng.standard_normal((2, 56))
+    ps2 = ps.merge(readout=ps.readout.merge(weight=W))
+    hs0 = [rng.standard_normal(n) for n in res]
+    st0 = fixed_h0(R, st, desn, hs0)
+    Y, _ = R.predict(desn, data, ps2, st0)
+    assert Y.dtype == np.float64 and "k4_generic<f64" in R.default_device().last_kernel()
+    Yo, _ = O.predict_teacher(oracle_layers(R, desn, ps2), W, data, hs0)
+    assert state_err(Y, Yo) <= 1e-10
+    with pytest.raises(R.UnsupportedError):
+        R.collectstates(desn, data, ps2, st0)
