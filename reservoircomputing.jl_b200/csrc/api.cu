@@ -151,6 +151,8 @@ static void free_layer(Layer& L) {
   L.d_Win = L.d_bias = L.d_leak = nullptr;
   cudaFree(L.d_Ot);
   L.d_Ot = nullptr;
+  cudaFree(L.d_Orow); cudaFree(L.d_csr_rowptr); cudaFree(L.d_csr_colind); cudaFree(L.d_csr_vals); cudaFree(L.d_Win_cm);
+  L.d_Orow = nullptr; L.d_csr_rowptr = nullptr; L.d_csr_colind = nullptr; L.d_csr_vals = nullptr; L.d_Win_cm = nullptr;
 }
 
 template <typename V>
@@ -225,7 +227,13 @@ static int32_t install_orthogonal(rcb_esn* esn, Layer& L) {
     if (r == 0xFFFF) continue;
     for (size_t j = 0; j < n; ++j) ot[j * npos + pos] = L.h_O[j * n + r];
   }
-  return upload(ot, &L.d_Ot);
+  RCB_TRY(upload(ot, &L.d_Ot));
+  cudaFree(L.d_Orow);
+  L.d_Orow = nullptr;
+  std::vector<float> orow(n * n);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < n; ++j) orow[i * n + j] = L.h_O[j * n + i];
+  return upload(orow, &L.d_Orow);
 }
 
 static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, int64_t ldwin, const float* bias) {
@@ -314,6 +322,17 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
     RCB_TRY(upload(b, &L.d_bias));
   }
   RCB_TRY(install_orthogonal(esn, L));
+  if (L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN) {  // operands of the cooperative kernel (recurrence_coop.cu)
+    std::vector<long long> rp(K.rowptr.begin(), K.rowptr.end());
+    std::vector<int> ci(K.colind.begin(), K.colind.end());
+    RCB_TRY(upload(rp, &L.d_csr_rowptr));
+    RCB_TRY(upload(ci, &L.d_csr_colind));
+    RCB_TRY(upload(K.vals, &L.d_csr_vals));
+    std::vector<float> wcm((size_t)L.n * L.d_in);
+    for (int d = 0; d < L.d_in; ++d)
+      for (int r = 0; r < L.n; ++r) wcm[(size_t)d * L.n + r] = W_in[(size_t)d * ldwin + r];
+    RCB_TRY(upload(wcm, &L.d_Win_cm));
+  }
   L.weights_set = true;
   return RCB_OK;
 }

@@ -136,6 +136,11 @@ struct Layer {
   std::vector<float> h_O;       // host copy of O, N x N column-major (kept: the position order comes from W)
   std::vector<uint16_t> h_perm; // position -> row of the installed schedule
   float* d_Ot = nullptr;        // [n][npos]: Ot[j*npos + pos] = O[perm[pos], j]
+  // cooperative multi-SM kernel of the dense-operator cells (recurrence_coop.cu): O row-major, W as CSR, W_in by row
+  float* d_Orow = nullptr;
+  long long* d_csr_rowptr = nullptr;
+  int* d_csr_colind = nullptr;
+  float* d_csr_vals = nullptr;
 };
 
 }  // namespace rcb

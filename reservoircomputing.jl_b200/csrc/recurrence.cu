@@ -258,6 +258,11 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
   }
   const size_t esz = a.dtype == RCB_F64 ? 8 : 4;
   const size_t cap = ctx->smem_optin;
+  if (a.dtype == RCB_F32 && p.Ot) {
+    bool launched = false;
+    const int32_t cp = launch_collect_coop(ctx, p, L, &launched);
+    if (cp != RCB_OK || launched) return cp;
+  }
   if (a.dtype == RCB_F32 && !p.Ot) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
     bool launched = false;
     const int32_t sg = launch_collect_single(ctx, p, L.fast4, L.d_Win4, &launched);

@@ -1170,3 +1170,35 @@ def test_deep_esn_float64_teacher_forced_predict(R):
     assert state_err(Y, Yo) <= 1e-10
     with pytest.raises(R.UnsupportedError):
         R.collectstates(desn, data, ps2, st0)
+
+
+@pytest.mark.parametrize("name,N,mods", [("es2n", 300, "nlat2_pad"), ("resesn", 1024, "esq"), ("es2n", 130, "nlat1_nlat2"), ("resesn", 64, "none")])
+def test_dense_operator_cells_cooperative_kernel(R, name, N, mods):
+    """ES2N / ResESN, one sequence: the cooperative multi-SM kernel (recurrence_coop.cu: rows of O and W split over a grid,
+    one grid barrier per step) against the oracle and against the single-CTA kernel, incl. carry in / out and a second
+    call, fused and non-fused modifier chains, bias."""
+    import os
+
+    rng = np.random.default_rng(N)
+    chain = dict(nlat2_pad=(R.NLAT2, R.Pad(1.0)), esq=(R.ExtendedSquare,), nlat1_nlat2=(R.NLAT1, R.NLAT2), none=())[mods]
+    kw = dict(init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), use_bias=True, init_bias=R.randn32, state_modifiers=chain)
+    rc = R.ES2N(3, N, 3, proximity=0.3, **kw) if name == "es2n" else R.ResESN(3, N, 3, alpha=0.7, beta=0.5, **kw)
+    ps, st = R.setup(rng, rc)
+    T = 50
+    data = np.asfortranarray(rng.standard_normal((3, 2 * T)).astype(np.float32))
+    h0 = rng.standard_normal(N).astype(np.float32)
+    dev = R.default_device()
+    s1, st1 = R.collectstates(rc, np.asfortranarray(data[:, :T]), ps, fixed_h0(R, st, rc, [h0]))
+    assert "k1_coop" in dev.last_kernel()
+    s2, st2 = R.collectstates(rc, np.asfortranarray(data[:, T:]), ps, st1)
+    states = np.concatenate([s1, s2], axis=1)
+    ref, hs = O.collectstates(oracle_layers(R, rc, ps), data, [h0])
+    assert states.shape == ref.shape and state_err(states, ref) <= STATE_RTOL
+    assert state_err(st2.reservoir.carry[0].reshape(-1, 1), hs[0].reshape(-1, 1)) <= STATE_RTOL
+    os.environ["RCB_K1_MODE"] = "v1"   # the single-CTA path
+    try:
+        sg, _ = R.collectstates(rc, data, ps, fixed_h0(R, st, rc, [h0]))
+        assert "k1_coop" not in dev.last_kernel()
+    finally:
+        del os.environ["RCB_K1_MODE"]
+    assert state_err(states, sg) <= STATE_RTOL
