@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       float2 wxy = make_float2(0.f, 0.f);
       float wzz = 0.f;
       if constexpr (DIN == 3) {
-        wxy = __ldg(reinterpret_cast<const float2*>(fa.Win4 + k * NT + tid));
-        wzz = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid) + 2);
+        const float4 w4 = __ldg(fa.Win4 + k * NT + tid);  // one 128-bit load: every global access costs two extra R2UR here
+        wxy = make_float2(w4.x, w4.y);
+        wzz = w4.z;
       } else {
         wxy.x = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid));
       }
