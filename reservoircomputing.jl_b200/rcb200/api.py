@@ -1029,8 +1029,7 @@ def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Dev
     Wro = np.asarray(ps.readout.weight)
     if isinstance(rc, _DelayModel):
         if isinstance(steps_or_data, (int, np.integer)):
-            raise L.UnsupportedError("autoregressive predict of the delay ESNs stays on the reference path "
-                                     "(the delay lines are assembled outside the fused predict kernel)")
+            return _predict_delay_autoregressive(rc, int(steps_or_data), ps, st, initialdata, device)
         if np.asarray(steps_or_data).shape[1] < 1:
             raise ArgumentError("predict data must have at least one column, got 0.")
         z, st2 = collectstates(rc, steps_or_data, ps, st, device)  # y_t = readout(features_t), predict.jl:163-177
@@ -1383,3 +1382,28 @@ def hessenberg_eigvals(H):
     re, im = np.empty(m), np.empty(m)
     check(lib().rcb_hessenberg_eigvals(ptr(Hf), m, ptr(re), ptr(im)))
     return re + 1j * im
+
+
+def _predict_delay_autoregressive(rc, steps, ps, st, initialdata, device):
+    """y_1 = model(u0), y_{t+1} = model(y_t) (src/predict.jl:74-88) for the delay ESNs: the delay lines sit outside the
+    fused predict kernel, so every step is the same four GPU calls as the teacher-forced path on ONE column (delay on
+    the input, cell, delay on the state + modifiers, readout) with the delay buffers, clocks and the carry threaded
+    through ``st`` — launch-latency bound (a few hundred microseconds per step), but every operation is a library kernel."""
+    if initialdata is None:
+        raise ArgumentError("autoregressive predict needs initialdata")
+    if steps < 1:
+        raise ArgumentError(f"steps must be ≥ 1, got {steps}")
+    cur = np.asarray(initialdata)
+    if cur.ndim != 1:
+        raise ArgumentError("autoregressive predict of the delay ESNs takes one sequence (a vector initialdata)")
+    n_in = cur.shape[0]
+    outs = []
+    for step in range(1, steps + 1):
+        z, st = collectstates(rc, cur[:, None], ps, st, device)
+        y = readout_apply(rc.readout, ps.readout, z, device)[:, 0]
+        if y.shape[0] != n_in:  # predict.jl:62-72
+            raise DimensionMismatch(f"autoregressive predict requires each output to have length {n_in} so it can be used as "
+                                    f"the next input; step {step} produced length {y.shape[0]}")
+        outs.append(y)
+        cur = y
+    return np.stack(outs, axis=1), st

@@ -820,8 +820,28 @@ def test_delay_esn_models(R, kind):  # src/models/esn_delay.jl
     full, _ = O.collectstates_delay(layers, np.concatenate([data, test], axis=1), [h0], idl, sdl, post)
     Yo = O.linear_readout(ps2.readout.weight, full[:, T:].astype(np.float64))
     assert state_err(Y, Yo) <= 1e-4
-    with pytest.raises(R.UnsupportedError):
-        R.predict(rc, 5, ps2, st3, initialdata=test[:, 0])
+    # autoregressive generation: the delay lines, clocks and the carry continue from st3 (history = the training tail)
+    Ya, st4 = R.predict(rc, 12, ps2, st3, initialdata=test[:, 0])
+    assert Ya.shape == (3, 12) and np.all(np.isfinite(Ya))
+    # oracle: replay the training series so that its delay buffers and clocks reach the same content, then generate
+    if idl is not None:
+        _, ih, ic = O.delay_layer_sequence(data, *idl)
+    zall, hs_all = O.collectstates_delay(layers, data, [h0], idl, None, ())
+    if sdl is not None:
+        _, sh, sc = O.delay_layer_sequence(zall, *sdl)
+    cur, hcur, outs = test[:, 0].astype(np.float32), hs_all[0], []
+    for _ in range(12):
+        u = cur
+        if idl is not None:
+            u, ih, ic = O.delay_layer_step(cur.astype(np.float32), ih, ic, idl[1])
+        hcur = O.esn_cell_step(layers[0], u.astype(np.float32), hcur.astype(np.float32))
+        z = O.apply_modifiers(layers[0].modifiers, hcur)
+        if sdl is not None:
+            z, sh, sc = O.delay_layer_step(z, sh, sc, sdl[1])
+            z = O.apply_modifiers(post, z)
+        cur = O.linear_readout(ps2.readout.weight, z.astype(np.float64))
+        outs.append(cur)
+    assert state_err(Ya, np.stack(outs, axis=1)) <= 1e-3
 
 
 @pytest.mark.parametrize("F,S,dt", [(20, 200, np.float64), (6, 30, np.float32), (300, 4000, np.float32)])
