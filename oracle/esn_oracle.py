@@ -293,35 +293,6 @@ def collectstates_delay(layers, data, h0, input_delay=None, state_delay=None, po
     return z, hs
 
 
-def predict_autoregressive_delay(layers, weight, steps, initialdata, h0, input_delay=None, state_delay=None, post_mods=()):
-    """src/predict.jl:74-88 over the delay ESNs' step (src/models/esn_delay.jl:548-558): one column at a time, the delay
-    buffers, clocks and the hidden state carried from step to step."""
-    hs = [np.array(x, copy=True) for x in h0]
-    n_in = len(initialdata)
-    cur = np.asarray(initialdata)
-    ih = ic = sh = sc = None
-    outs = []
-    for step in range(steps):
-        u = cur
-        if input_delay is not None:
-            if ih is None:
-                ih, ic = np.zeros((n_in, input_delay[0]), cur.dtype), 0
-            u, ih, ic = delay_layer_step(cur, ih.astype(cur.dtype), ic, input_delay[1])
-        h = hs[0]
-        if h.dtype != u.dtype:
-            h = h.astype(np.promote_types(h.dtype, u.dtype))
-        hs[0] = esn_cell_step(layers[0], u, h)
-        z = apply_modifiers(layers[0].modifiers, hs[0])
-        if state_delay is not None:
-            if sh is None:
-                sh, sc = np.zeros((z.shape[0], state_delay[0]), z.dtype), 0
-            z, sh, sc = delay_layer_step(z, sh.astype(z.dtype), sc, state_delay[1])
-            z = apply_modifiers(post_mods, z)
-        cur = linear_readout(weight, z)
-        outs.append(cur)
-    return np.stack(outs, axis=1), hs
-
-
 def correlation_matrix(states: np.ndarray) -> np.ndarray:
     """src/conceptors.jl:28-33 — (Z Z') / S in float(eltype(states))."""
     if states.size == 0:
