@@ -358,6 +358,33 @@ function correlation_matrix_b200(states::AbstractMatrix{<:Real})
 end
 
 """
+    spectral_radius_b200(W) -> Float64
+
+`maximum(abs, eigvals(W))` without the dense eigen-decomposition of `scale_radius!` (src/inits/inits_components.jl:126-138):
+Arnoldi on the GPU (`rcb_spectral_radius_dense` / `_csc`).  `scale_radius_b200!(W, radius)` applies the same in-place scaling.
+"""
+function spectral_radius_b200(W::AbstractMatrix{<:Real})
+    rho, dim = Ref{Float64}(0.0), Ref{Int32}(0)
+    if W isa SparseMatrixCSC
+        check(ccall((:rcb_spectral_radius_csc, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float32}, Int32, Float64, Int32, Ref{Float64}, Ref{Int32}),
+                    ctx().ptr, W.colptr, W.rowval, Vector{Float32}(W.nzval), size(W, 1), 0.0, 0, rho, dim))
+    else
+        Wd = Matrix{Float32}(W)
+        check(ccall((:rcb_spectral_radius_dense, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float32}, Int64, Int32, Float64, Int32, Ref{Float64}, Ref{Int32}),
+                    ctx().ptr, Wd, size(Wd, 1), size(Wd, 1), 0.0, 0, rho, dim))
+    end
+    return rho[]
+end
+function scale_radius_b200!(W::AbstractMatrix, radius::AbstractFloat)
+    rho = spectral_radius_b200(W)
+    W .*= eltype(W)(radius) / eltype(W)(rho)
+    any(!isfinite, W) && error("Sparsity too low for size of the matrix. Increase res_size or increase sparsity.")
+    return W
+end
+
+"""
     b200(rc::AbstractReservoirComputer) -> ReservoirComputer
 
 Same model (`ESN`, `ES2N`, `ResESN`, `EuSN` or a hand-built `ReservoirComputer` around one of their cells),
@@ -367,6 +394,6 @@ wrapped model (same field names `reservoir`, `state_modifiers`, `readout`).
 b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 b200(rc::ReservoirComputing.DeepESN) = B200DeepESN(rc)
 
-export B200Reservoir, B200DeepESN, B200Ridge, b200, delay_features, extend_features, correlation_matrix_b200
+export B200Reservoir, B200DeepESN, B200Ridge, b200, spectral_radius_b200, scale_radius_b200!, delay_features, extend_features, correlation_matrix_b200
 
 end # module
