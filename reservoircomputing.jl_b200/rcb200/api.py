@@ -400,9 +400,11 @@ class EuSNCell(ESNCell):
 class LinearReadout:
     """src/layers/basic.jl:129-154."""
 
-    def __init__(self, in_dims, out_dims, activation=identity, *, init_weight=rand32, init_bias=rand32, use_bias=False):
+    def __init__(self, in_dims, out_dims, activation=identity, *, init_weight=rand32, init_bias=rand32, use_bias=False,
+                 include_collect=True):
         self.in_dims, self.out_dims, self.activation = int(in_dims), int(out_dims), activation
         self.init_weight, self.init_bias, self.use_bias = init_weight, init_bias, bool(use_bias)
+        self.include_collect = bool(include_collect)
 
     def initialparameters(self, rng):  # basic.jl:156-164
         ps = dict(weight=self.init_weight(rng, self.out_dims, self.in_dims))
@@ -511,6 +513,8 @@ def setup(rng: np.random.Generator, rc):
     """LuxCore.setup(rng, model) -> (ps, st).  src/reservoircomputer.jl:51-63, esn_deep.jl:156-188."""
     if isinstance(rc, _DelayModel):
         return _setup_delay(rng, rc)
+    if isinstance(rc, ReservoirChain):
+        return _setup_chain(rng, rc)
     if _is_deep(rc):
         ps_cells = tuple(c.initialparameters(rng) for c in rc.cells)
         ps = NT(cells=ps_cells, state_modifiers=tuple(() for _ in rc.cells), readout=rc.readout.initialparameters(rng))
@@ -666,6 +670,8 @@ def collectstates(rc, data, ps, st, device: Optional[Device] = None):
     src/reservoircomputer.jl:96-133, src/models/esn_deep.jl:261-291."""
     if isinstance(rc, _DelayModel):
         return _collect_delay(rc, data, ps, st, device)
+    if isinstance(rc, ReservoirChain):
+        return _collect_chain(rc, data, ps, st, device)
     d3, vec = _as3d(data)
     if d3.shape[1] < 1:
         raise ArgumentError(f"collectstates data must have at least one column, got {d3.shape[1]}.")
@@ -754,7 +760,11 @@ def ridge_solve(GC, d_out: int, reg: float, device: Optional[Device] = None):
 
 
 def addreadout(rc, output_matrix, ps, st):
-    """addreadout!(rc, W, ps, st): functional update of ps.readout.weight (reservoircomputer.jl:137-144)."""
+    """addreadout!(rc, W, ps, st): functional update of ps.readout.weight (reservoircomputer.jl:137-144; the chain
+    variant replaces the weight of its readout layer, train.jl:253-305)."""
+    if isinstance(rc, ReservoirChain):
+        name = rc.names()[-1]
+        return ps.merge(**{name: getattr(ps, name).merge(weight=output_matrix)}), st
     return ps.merge(readout=ps.readout.merge(weight=output_matrix)), st
 
 
@@ -764,7 +774,7 @@ def train(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = N
     -> (ps, st) or ((ps, st), states_wo).  src/train.jl:232-251."""
     objective = objective or RidgeRegression(0.0)
     _check_solver(solver)
-    if isinstance(rc, _DelayModel):  # train.jl:240-250 step by step: the features are assembled outside the fused rcb_train
+    if isinstance(rc, (_DelayModel, ReservoirChain)):  # train.jl:240-250 step by step: the features are assembled outside the fused rcb_train
         states, st2 = collectstates(rc, train_data, ps, st, device)
         tgt = np.asarray(target_data)
         if washout < 0:
@@ -1026,6 +1036,14 @@ def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Dev
     """predict(rc, steps::Integer, ps, st; initialdata) — autoregressive (src/predict.jl:55-60,74-88);
     predict(rc, data::AbstractMatrix, ps, st) — teacher-forced (:90-103,163-177).
     Returns (outputs (d_out, T[, B]), st)."""
+    if isinstance(rc, ReservoirChain):
+        ro_ps = getattr(ps, rc.names()[-1])
+        if isinstance(steps_or_data, (int, np.integer)):
+            return _predict_delay_autoregressive(rc, int(steps_or_data), ps, st, initialdata, device, ro_ps=ro_ps)
+        if np.asarray(steps_or_data).shape[1] < 1:
+            raise ArgumentError("predict data must have at least one column, got 0.")
+        z, st2 = collectstates(rc, steps_or_data, ps, st, device)
+        return readout_apply(rc.readout, ro_ps, z, device), st2
     Wro = np.asarray(ps.readout.weight)
     if isinstance(rc, _DelayModel):
         if isinstance(steps_or_data, (int, np.integer)):
@@ -1384,7 +1402,7 @@ def hessenberg_eigvals(H):
     return re + 1j * im
 
 
-def _predict_delay_autoregressive(rc, steps, ps, st, initialdata, device):
+def _predict_delay_autoregressive(rc, steps, ps, st, initialdata, device, ro_ps=None):
     """y_1 = model(u0), y_{t+1} = model(y_t) (src/predict.jl:74-88) for the delay ESNs: the delay lines sit outside the
     fused predict kernel, so every step is the same four GPU calls as the teacher-forced path on ONE column (delay on
     the input, cell, delay on the state + modifiers, readout) with the delay buffers, clocks and the carry threaded
@@ -1400,10 +1418,134 @@ def _predict_delay_autoregressive(rc, steps, ps, st, initialdata, device):
     outs = []
     for step in range(1, steps + 1):
         z, st = collectstates(rc, cur[:, None], ps, st, device)
-        y = readout_apply(rc.readout, ps.readout, z, device)[:, 0]
+        y = readout_apply(rc.readout, ro_ps if ro_ps is not None else ps.readout, z, device)[:, 0]
         if y.shape[0] != n_in:  # predict.jl:62-72
             raise DimensionMismatch(f"autoregressive predict requires each output to have length {n_in} so it can be used as "
                                     f"the next input; step {step} produced length {y.shape[0]}")
         outs.append(y)
         cur = y
     return np.stack(outs, axis=1), st
+
+
+# ---- ReservoirChain: the one-cell chains of the reference's docs (Extend, Collect, delay lines, modifiers, readout) ----
+class StatefulLayer:
+    """StatefulLayer(cell) — src/layers/lux_layers.jl:27-46."""
+
+    def __init__(self, cell):
+        self.cell = cell
+
+
+class Extend:
+    """Extend(op): vcat(input, op(input)) — src/states.jl:131-145."""
+
+    def __init__(self, op):
+        if not isinstance(op, StatefulLayer):
+            raise L.UnsupportedError("Extend wraps a StatefulLayer(cell) on the B200 path")
+        self.op = op
+
+
+class Collect:
+    """Collect(): a collection point of features — src/layers/basic.jl:246-252."""
+
+
+class _ChainCore:
+    """What the device handle needs to know about the chain's cell: it runs without fused modifiers; the chain applies its
+    own post-processing to the collected raw states."""
+
+    def __init__(self, cell, readout):
+        self.reservoir, self.readout, self._cache = cell, readout, {}
+        self.cells, self.layer_modifiers = (cell,), ((),)
+
+
+class ReservoirChain:
+    """ReservoirChain(layers...) restricted to one recurrent cell (src/layers/lux_layers.jl:125-135):
+    ``[DelayLayer...] , StatefulLayer(cell) | Extend(StatefulLayer(cell)) , [modifier | DelayLayer | Collect ...] , LinearReadout``.
+    A readout built with include_collect=true (the default) contributes an implicit Collect right before it (:156-163);
+    with several collection points the features are vcat-ed in chain order (src/layers/basic.jl:283-308)."""
+
+    def __init__(self, *layers):
+        flat = []
+        for l in layers:
+            if isinstance(l, LinearReadout):
+                if getattr(l, "include_collect", True):
+                    flat.append(Collect())
+                flat.append(l)
+            else:
+                flat.append(l)
+        self.layers = tuple(flat)
+        kinds = [isinstance(l, (StatefulLayer, Extend)) for l in self.layers]
+        if sum(kinds) != 1:
+            raise L.UnsupportedError("the B200 path handles chains with exactly one recurrent cell")
+        self._icell = kinds.index(True)
+        if not isinstance(self.layers[-1], LinearReadout):
+            raise L.UnsupportedError("the chain must end in a LinearReadout")
+        for l in self.layers[:self._icell]:
+            if not isinstance(l, DelayLayer):
+                raise L.UnsupportedError("only DelayLayer may precede the cell on the B200 path")
+        for l in self.layers[self._icell + 1:-1]:
+            if not isinstance(l, (_Modifier, DelayLayer, Collect)):
+                raise L.UnsupportedError(f"layer {l!r} has no B200 implementation")
+        c = self.layers[self._icell]
+        self.extend = isinstance(c, Extend)
+        self.cell = (c.op if self.extend else c).cell
+        self.readout = self.layers[-1]
+        self._core = _ChainCore(self.cell, self.readout)
+
+    def names(self):
+        return [f"layer_{i + 1}" for i in range(len(self.layers))]   # named_tuple_layers, lux_layers.jl
+
+
+def _setup_chain(rng, rc):
+    ps, st = {}, {}
+    for name, l in zip(rc.names(), rc.layers):
+        if isinstance(l, StatefulLayer):
+            ps[name], st[name] = l.cell.initialparameters(rng), l.cell.initialstates(rng)
+        elif isinstance(l, Extend):
+            ps[name], st[name] = NT(op=l.op.cell.initialparameters(rng)), NT(op=l.op.cell.initialstates(rng))
+        elif isinstance(l, DelayLayer):
+            ps[name], st[name] = NT(), l.initialstates(rng)
+        elif isinstance(l, LinearReadout):
+            ps[name], st[name] = l.initialparameters(rng), NT()
+        else:
+            ps[name], st[name] = NT(), NT()
+    return NT(**ps), NT(**st)
+
+
+def _collect_chain(rc, data, ps, st, device):
+    dev = device or default_device()
+    names = rc.names()
+    u = np.asarray(data)
+    if u.shape[1] < 1:
+        raise ArgumentError(f"collectstates data must have at least one column, got {u.shape[1]}.")
+    new_st = {}
+    for i in range(rc._icell):  # delay lines on the input
+        u, new_st[names[i]] = rc.layers[i].apply_sequence(u, getattr(st, names[i]), dev)
+    cname = names[rc._icell]
+    cps, cst = getattr(ps, cname), getattr(st, cname)
+    if rc.extend:
+        cps, cst = cps.op, cst.op
+    raw, core_st = collectstates_core(rc._core, u, NT(reservoir=cps), NT(reservoir=cst), dev)
+    new_st[cname] = NT(op=core_st.reservoir) if rc.extend else core_st.reservoir
+    val = extend_features(u, raw, dev) if rc.extend else raw
+    collected, pending = [], []
+
+    def flush(v):
+        nonlocal pending
+        if pending:
+            v = apply_modifiers(tuple(pending), v, dev)
+            pending = []
+        return v
+
+    for i in range(rc._icell + 1, len(rc.layers) - 1):
+        l = rc.layers[i]
+        if isinstance(l, _Modifier):
+            pending.append(l)
+        elif isinstance(l, DelayLayer):
+            val = flush(val)
+            val, new_st[names[i]] = l.apply_sequence(val, getattr(st, names[i]), dev)
+        else:  # Collect
+            val = flush(val)
+            collected.append(val)
+    val = flush(val)
+    feats = val if not collected else (collected[0] if len(collected) == 1 else np.asfortranarray(np.concatenate(collected, axis=0)))
+    return feats, st.merge(**new_st)

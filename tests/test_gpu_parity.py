@@ -1222,3 +1222,78 @@ def test_dense_operator_cells_cooperative_kernel(R, name, N, mods):
     finally:
         del os.environ["RCB_K1_MODE"]
     assert state_err(states, sg) <= STATE_RTOL
+
+
+# ---- ReservoirChain with one cell: Extend, Collect points, delay lines --------------------------------
+def _chain_cell(R, N, d_in, rng):
+    W = R.rand_sparse(radius=0.9, sparsity=6 / N)(rng, N, N)
+    Win = R.scaled_rand(rng, N, d_in)
+    cell = R.ESNCell(d_in, N, R.tanh, init_reservoir=const_init(W), init_input=const_init(Win), leak_coefficient=0.8)
+    return cell, O.ESNCellParams(input_matrix=Win, reservoir_matrix=W, leak=0.8, act=O.ACT_TANH)
+
+
+def test_reservoir_chain_extend_example(R):  # the docs example of Extend, src/states.jl:113-124
+    rng = np.random.default_rng(3)
+    N, T = 300, 80
+    cell, ocell = _chain_cell(R, N, 3, rng)
+    rc = R.ReservoirChain(R.Extend(R.StatefulLayer(cell)), R.NLAT2, R.LinearReadout(N + 3, 3))
+    ps, st = R.setup(rng, rc)
+    assert list(ps.keys()) == ["layer_1", "layer_2", "layer_3", "layer_4"] and "op" in ps.layer_1   # Collect() inserted before the readout
+    series = O.lorenz_series(T + 20).astype(np.float32) / 20
+    data, tgt = np.asfortranarray(series[:, :T]), np.asfortranarray(series[:, 1:T + 1])
+    h0 = rng.standard_normal(N).astype(np.float32)
+    st = st.merge(layer_1=NT_with_carry(R, st.layer_1, h0, extend=True))
+    states, st2 = R.collectstates(rc, data, ps, st)
+    raw, hs = O.collectstates([ocell], data, [h0])
+    ref = O.nlat2(O.extend(data, raw))                        # the chain order: vcat(input, state), then NLAT2 on all N+3 rows
+    assert states.shape == (N + 3, T) and state_err(states, ref) <= STATE_RTOL
+    ps2, st3 = R.train(rc, data, tgt, ps, st, objective=R.RidgeRegression(1e-4), washout=10)
+    Wo = O.train_ridge_qr(states[:, 10:], tgt[:, 10:], 1e-4)
+    assert ps2.layer_4.weight.shape == (3, N + 3) and np.linalg.norm(ps2.layer_4.weight - Wo) / np.linalg.norm(Wo) <= WEIGHT_RTOL
+    test = np.asfortranarray(series[:, T:T + 15])
+    Y, _ = R.predict(rc, test, ps2, st3)
+    rawt, _ = O.collectstates([ocell], test, hs)
+    assert state_err(Y, O.linear_readout(ps2.layer_4.weight, O.nlat2(O.extend(test, rawt)).astype(np.float64))) <= 1e-4
+    Ya, _ = R.predict(rc, 8, ps2, st3, initialdata=test[:, 0])
+    cur, h, outs = test[:, 0], hs[0], []
+    for _ in range(8):
+        h = O.esn_cell_step(ocell, cur.astype(np.float32), h.astype(np.float32))
+        cur = O.linear_readout(ps2.layer_4.weight, O.nlat2(O.extend(cur.astype(np.float32), h)).astype(np.float64))
+        outs.append(cur)
+    assert state_err(Ya, np.stack(outs, axis=1)) <= 1e-3
+
+
+def NT_with_carry(R, cell_st, h0, extend=False):
+    inner = cell_st.op if extend else cell_st
+    inner = inner.merge(carry=(np.asarray(h0),))
+    return R.NT(op=inner) if extend else inner
+
+
+def test_reservoir_chain_collect_points_and_delay(R):  # multiple Collect layers are vcat-ed in chain order, basic.jl:226-235,283-308
+    rng = np.random.default_rng(9)
+    N, T = 64, 40
+    cell, ocell = _chain_cell(R, N, 2, rng)
+    data = np.asfortranarray(rng.standard_normal((2, T)).astype(np.float32))
+    h0 = rng.standard_normal(N).astype(np.float32)
+    raw, _ = O.collectstates([ocell], data, [h0])
+    # (1) explicit Collect after the cell + the readout's implicit one after NLAT2: features = [raw; NLAT2(raw)]
+    rc = R.ReservoirChain(R.StatefulLayer(cell), R.Collect(), R.NLAT2, R.LinearReadout(2 * N, 2))
+    ps, st = R.setup(rng, rc)
+    st = st.merge(layer_1=NT_with_carry(R, st.layer_1, h0))
+    states, _ = R.collectstates(rc, data, ps, st)
+    assert state_err(states, np.concatenate([raw, O.nlat2(raw)], axis=0)) <= STATE_RTOL
+    # (2) a delay line on the input, one on the state, a modifier after it, explicit Collect only
+    rc = R.ReservoirChain(R.DelayLayer(2, num_delays=1), R.StatefulLayer(R.ESNCell(4, N, R.tanh, leak_coefficient=0.8,
+                          init_reservoir=const_init(ocell.reservoir_matrix), init_input=R.scaled_rand)),
+                          R.DelayLayer(N, num_delays=2, stride=2), R.NLAT1, R.Collect(), R.LinearReadout(3 * N, 2, include_collect=False))
+    ps, st = R.setup(rng, rc)
+    st = st.merge(layer_2=NT_with_carry(R, st.layer_2, h0))
+    states, st2 = R.collectstates(rc, data, ps, st)
+    ocell2 = O.ESNCellParams(input_matrix=np.asarray(ps.layer_2.input_matrix), reservoir_matrix=ocell.reservoir_matrix, leak=0.8, act=O.ACT_TANH)
+    ud, _, _ = O.delay_layer_sequence(data, 1, 1)
+    raw2, _ = O.collectstates([ocell2], ud, [h0])
+    zd, _, _ = O.delay_layer_sequence(raw2, 2, 2)
+    assert states.shape == (3 * N, T) and state_err(states, O.nlat1(zd)) <= STATE_RTOL
+    assert st2.layer_1.clock == T and st2.layer_3.clock == T
+    with pytest.raises(R.UnsupportedError):
+        R.ReservoirChain(R.StatefulLayer(cell), R.StatefulLayer(cell), R.LinearReadout(N, 2))
