@@ -1053,6 +1053,7 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
   size_t budget = free_b / (esn->layers.size() > 1 ? 6 : 2);
   const size_t cap = (size_t)24 << 30;
   if (budget > cap) budget = cap;
+  if (const char* e = getenv("RCB_TRAIN_BUDGET_MB")) budget = (size_t)atoll(e) << 20;  // testing hook: force the chunked paths
   const bool multi = esn->layers.size() > 1;
   int64_t Bc = B, Tc = T;
   const size_t per_seq = (size_t)F * T * esz;
@@ -1064,6 +1065,30 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
       if (Tc < 1) return fail(RCB_ERR_ALLOC, "not enough device memory for one column of states");
       if (multi) return fail(RCB_ERR_UNSUPPORTED, "time-chunked training is implemented for single-layer ESNs");
     }
+  }
+  if (!multi && !states_out && Bc < B && B > 6 * (int64_t)ctx->sm_count && (size_t)F * (size_t)B * esz * 32 <= budget) {
+    // A batch far wider than the machine (the C3 shape) is better cut in TIME: every chunk keeps all B sequences — the
+    // wide-batch recurrence kernel keeps its shape — and the carry links the chunks.  A time window of all sequences is
+    // strided in the caller's d x T x B arrays, so the (small) input and target windows are gathered with 2-D copies.
+    const int64_t Tw = std::max<int64_t>(32, std::min<int64_t>(T, (int64_t)(budget / ((size_t)F * B * esz))));
+    void *st_dev = nullptr, *uw = nullptr, *yw = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * Tw * B * esz, &st_dev));
+    RCB_TRY(ctx_scratch(ctx, SCR_TMP2, (size_t)d_in * Tw * B * esz, &uw));
+    RCB_TRY(ctx_scratch(ctx, SCR_Y, (size_t)d_out * Tw * B * ysz, &yw));
+    for (int64_t t0 = 0; t0 < T; t0 += Tw) {
+      const int64_t nt = std::min<int64_t>(Tw, T - t0);
+      RCB_CUDA(cudaMemcpy2DAsync(uw, (size_t)nt * d_in * esz, (const char*)u_dev + (size_t)t0 * d_in * esz, (size_t)T * d_in * esz,
+                                 (size_t)nt * d_in * esz, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream));
+      RCB_TRY(collect_device(esn, uw, nt, B, h_dev, st_dev, h_dev, 0));
+      const int64_t wo = std::max<int64_t>(0, std::min<int64_t>(nt, washout - t0));
+      if (wo < nt) {
+        RCB_CUDA(cudaMemcpy2DAsync(yw, (size_t)nt * d_out * ysz, (const char*)y_dev + (size_t)t0 * d_out * ysz, (size_t)T * d_out * ysz,
+                                   (size_t)nt * d_out * ysz, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream));
+        RCB_TRY(gram_device(ctx, st_dev, esn->desc.data_dtype, F, F, yw, targets_dtype, d_out, d_out, nt, wo, B, gram_mode, gc_dev));
+      }
+    }
+    if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
+    return RCB_OK;
   }
   void* st_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * Tc * Bc * esz, &st_dev));

@@ -1297,3 +1297,23 @@ def test_reservoir_chain_collect_points_and_delay(R):  # multiple Collect layers
     assert st2.layer_1.clock == T and st2.layer_3.clock == T
     with pytest.raises(R.UnsupportedError):
         R.ReservoirChain(R.StatefulLayer(cell), R.StatefulLayer(cell), R.LinearReadout(N, 2))
+
+
+@pytest.mark.parametrize("budget_mb,B", [(32, 900), (2, 40)])
+def test_train_chunked_paths_match_unchunked(R, budget_mb, B, monkeypatch):
+    """rcb_train cuts work that exceeds its state-buffer budget: in time for batches far wider than the machine (all
+    sequences stay together, the carry links the windows), by sequences otherwise.  Both must reproduce the one-piece fit,
+    including the washout that falls inside the first window and the final carry."""
+    rng = np.random.default_rng(B)
+    N, T, w = 256, 100, 37
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), leak_coefficient=0.6, state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)
+    data = np.asfortranarray(rng.standard_normal((3, T, B)).astype(np.float32))
+    tgt = np.asfortranarray(rng.standard_normal((3, T, B)).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    st0 = fixed_h0(R, st, esn, [h0])
+    ps_a, st_a = R.train(esn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=w)
+    monkeypatch.setenv("RCB_TRAIN_BUDGET_MB", str(budget_mb))
+    ps_b, st_b = R.train(esn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=w)
+    assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) <= 1e-9 * np.linalg.norm(ps_a.readout.weight)
+    assert np.array_equal(st_a.reservoir.carry[0], st_b.reservoir.carry[0])
