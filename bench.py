@@ -397,7 +397,7 @@ def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, worl
         t_acc, t_ar, t_solve, k1_ms, gram_ms, t_skew = [float(x) for x in t]
     S = float(T) * B
     tiles = sum(1 for i in range((F + 255) // 256) for j in range((F + 255) // 256) if j * 256 <= i * 256 + 255) * 2
-    issued = 6.0 * 2.0 * tiles * 128 * 256 * S          # six INT8 digit-plane MMAs per tile per sample
+    issued = 8.0 * 2.0 * tiles * 128 * 256 * S          # eight INT8 digit-plane MMAs (a1a1, a1a2, a2a1, a1a3, a3a1, a2a2, a2a3, a3a2) per tile per sample
     bf16 = 1590.0  # fallback of B200_PROFILING.md
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
