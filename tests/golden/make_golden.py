@@ -53,6 +53,16 @@ def reference_vectors():
             "cite": "test/test_train_ridge.jl:64-91",
             "s": 2.0, "lambda": 0.5, "W_true": [[1.0, -2.0, 0.5], [0.0, 3.0, -1.0]], "rtol": 1e-10,
         },
+        "delay_layer_stride1": {  # DelayLayer(1; num_delays=2, stride=1, init_delay=zeros32) fed 1..5
+            "cite": "test/basic_tests.jl:204-222",
+            "num_delays": 2, "stride": 1, "inputs": [1, 2, 3, 4, 5],
+            "outputs": [[1, 0, 0], [2, 1, 0], [3, 2, 1], [4, 3, 2], [5, 4, 3]],
+        },
+        "delay_layer_stride2": {  # the same layer with stride=2 fed 1..6: the buffer shifts on every second call
+            "cite": "test/basic_tests.jl:225-246",
+            "num_delays": 2, "stride": 2, "inputs": [1, 2, 3, 4],
+            "outputs": [[1, 0, 0], [2, 0, 0], [3, 2, 0], [4, 2, 0]],
+        },
         "autoregressive_identity": {  # identity readout on a 2-dim identity reservoir feeds [1,2] back
             "cite": "test/Interface/array_workflow_tests.jl:145-155",
             "initialdata": [1.0, 2.0], "steps": 3, "output": [[1, 1, 1], [2, 2, 2]], "eltype": "Float64",

@@ -60,6 +60,11 @@ def test_oracle_reproduces_reference_vectors(ref):
     Z = g["s"] * np.eye(tw.shape[1])
     W = O.train_ridge_qr(Z, tw @ Z, g["lambda"])
     assert np.allclose(W, tw * g["s"] ** 2 / (g["s"] ** 2 + g["lambda"]), rtol=g["rtol"])
+    for key in ("delay_layer_stride1", "delay_layer_stride2"):
+        g = ref[key]
+        x = np.array(g["inputs"], np.float32)[None, :]
+        out, _, clock = O.delay_layer_sequence(x, g["num_delays"], g["stride"])
+        assert np.array_equal(out.T, np.array(g["outputs"], np.float32)) and clock == len(g["inputs"]), key
 
 
 def test_oracle_reproduces_esn_small(small):
@@ -104,6 +109,17 @@ def test_cuda_reference_vectors(R, ref):
     Z = np.asfortranarray(g["s"] * np.eye(tw.shape[1]))
     W = R.fit_readout(R.RidgeRegression(g["lambda"]), Z, np.asfortranarray(tw @ Z))
     assert np.allclose(W, tw * g["s"] ** 2 / (g["s"] ** 2 + g["lambda"]), rtol=g["rtol"])
+    for key in ("delay_layer_stride1", "delay_layer_stride2"):
+        g = ref[key]
+        dl = R.DelayLayer(1, num_delays=g["num_delays"], stride=g["stride"])
+        x = np.array(g["inputs"], np.float32)[None, :]
+        out, st = dl.apply_sequence(x, dl.initialstates(np.random.default_rng(0)))
+        assert np.array_equal(out.T, np.array(g["outputs"], np.float32)) and st.clock == len(g["inputs"]), key
+        # call by call, like the reference's loop: same outputs, the buffer and the clock carried in st
+        st = dl.initialstates(np.random.default_rng(0))
+        for i, row in enumerate(g["outputs"]):
+            o, st = dl.apply_sequence(x[:, i:i + 1], st)
+            assert np.array_equal(o[:, 0], np.array(row, np.float32)), (key, i)
 
 
 @pytest.mark.gpu
