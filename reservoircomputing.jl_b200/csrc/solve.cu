@@ -83,39 +83,46 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double* A, long long ld
     if (j < nb) A[(size_t)(k0 + j) * lda + row] = x[j];
 }
 
-// Trailing update: A[i, j] -= sum_m P[i, m] P[j, m], i >= j > panel, 64 x 64 tiles, K = NBLK.
-__global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long lda, long long F, long long k0, long long stride) {
+// Trailing update: A[i, j] -= sum_m P[i, m] P[j, m] over the kw (32 or 64) panel columns starting at kp0, for the
+// lower-triangular region i >= j >= base, j < jlim, in 64 x 64 tiles.  Two 32-wide panels are applied in ONE pass over
+// the trailing matrix (the second panel is factored after a narrow update of its own 32 columns): the matrix is
+// streamed F/64 times instead of F/32 — the factorisation is bound by exactly that traffic when thousands of systems
+// are solved at once (BASELINE config 5).
+__global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long lda, long long F, long long kp0, int kw,
+                                                         long long base, long long jlim, long long stride) {
   A += (size_t)blockIdx.z * stride;
   constexpr int TILE = 64;
-  const long long base = k0 + NBLK;
   const long long i0 = base + (long long)blockIdx.y * TILE, j0 = base + (long long)blockIdx.x * TILE;
-  if (j0 > i0 || i0 >= F) return;
+  if (j0 > i0 || i0 >= F || j0 >= jlim) return;
   __shared__ double Pi[NBLK][TILE];
   __shared__ double Pj[NBLK][TILE];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int e = tid; e < NBLK * TILE; e += 256) {
-    const int ii = e % TILE, m = e / TILE;
-    Pi[m][ii] = i0 + ii < F ? A[(size_t)(k0 + m) * lda + i0 + ii] : 0.0;
-    Pj[m][ii] = j0 + ii < F ? A[(size_t)(k0 + m) * lda + j0 + ii] : 0.0;
-  }
-  __syncthreads();
   double acc[4][4] = {};
+  for (int m0 = 0; m0 < kw; m0 += NBLK) {
+    for (int e = tid; e < NBLK * TILE; e += 256) {
+      const int ii = e % TILE, m = e / TILE;
+      Pi[m][ii] = i0 + ii < F ? A[(size_t)(kp0 + m0 + m) * lda + i0 + ii] : 0.0;
+      Pj[m][ii] = j0 + ii < F ? A[(size_t)(kp0 + m0 + m) * lda + j0 + ii] : 0.0;
+    }
+    __syncthreads();
 #pragma unroll
-  for (int m = 0; m < NBLK; ++m) {
-    double a[4], b[4];
+    for (int m = 0; m < NBLK; ++m) {
+      double a[4], b[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { a[q] = Pi[m][tx + 16 * q]; b[q] = Pj[m][ty + 16 * q]; }
+      for (int q = 0; q < 4; ++q) { a[q] = Pi[m][tx + 16 * q]; b[q] = Pj[m][ty + 16 * q]; }
 #pragma unroll
-    for (int x = 0; x < 4; ++x)
+      for (int x = 0; x < 4; ++x)
 #pragma unroll
-      for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int x = 0; x < 4; ++x)
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const long long i = i0 + tx + 16 * x, j = j0 + ty + 16 * y;
-      if (i < F && j <= i) A[(size_t)j * lda + i] -= acc[x][y];
+      if (i < F && j <= i && j < jlim) A[(size_t)j * lda + i] -= acc[x][y];
     }
 }
 
@@ -201,16 +208,24 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
   timer_begin(ctx, RCB_TIMER_SOLVE);
   const long long lda = F, stride = (long long)F * (F + d_out);
   const unsigned nz = (unsigned)nsys;
-  for (long long k0 = 0; k0 < F; k0 += NBLK) {
+  for (long long k0 = 0; k0 < F; k0 += 2 * NBLK) {
+    // panel pair (k0, k0 + 32): factor the first, bring the second's own 32 columns up to date, factor it, then apply both
+    // to the rest of the trailing matrix in one pass
     potrf_diag_kernel<<<dim3(1, 1, nz), NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0, lambda0, lam, stride, d_info);
     ctx->launches++;
-    const long long rem = F - k0 - NBLK;
-    if (rem > 0) {
-      trsm_panel_kernel<<<dim3((unsigned)((rem + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0, stride);
-      const unsigned tiles = (unsigned)((rem + 63) / 64);
-      syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, stride);
-      ctx->launches += 2;
-    }
+    const long long rem1 = F - k0 - NBLK;
+    if (rem1 <= 0) break;
+    trsm_panel_kernel<<<dim3((unsigned)((rem1 + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0, stride);
+    syrk_update_kernel<<<dim3(1, (unsigned)((rem1 + 63) / 64), nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, NBLK, k0 + NBLK,
+                                                                                        k0 + 2 * NBLK, stride);
+    potrf_diag_kernel<<<dim3(1, 1, nz), NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0 + NBLK, lambda0, lam, stride, d_info);
+    ctx->launches += 3;
+    const long long rem2 = F - k0 - 2 * NBLK;
+    if (rem2 <= 0) break;
+    trsm_panel_kernel<<<dim3((unsigned)((rem2 + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0 + NBLK, stride);
+    const unsigned tiles = (unsigned)((rem2 + 63) / 64);
+    syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, 2 * NBLK, k0 + 2 * NBLK, F, stride);
+    ctx->launches += 2;
   }
   const size_t smem = (size_t)F * sizeof(double);
   if (smem > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "feature count %lld too large for the triangular-solve kernel", (long long)F);
