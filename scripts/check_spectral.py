@@ -1,3 +1,4 @@
+"""Arbitration run for the GPU spectral radius: repeated GPU calls, ARPACK with several start vectors, dense eigvals (N=4096)."""
 import os, sys, time
 import numpy as np
 import scipy.sparse as sp
