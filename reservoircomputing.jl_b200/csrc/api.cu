@@ -881,10 +881,11 @@ int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, const voi
 static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt,
                            int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq, int32_t gram_mode,
                            double* GC) {
-  // RCB_GRAM_AUTO: tensor cores once the contraction is large (F^2 S >= 1e12 MACs); the exact FP64 kernel
+  // RCB_GRAM_AUTO: tensor cores once the contraction is large (F^2 S >= 3e10 MACs: the FP64 kernel runs at ~12 TFLOP/s, the
+  // fixed-point tensor path at ~250 with ~1 ms of pre-pass overhead — they cross near 1e10); the exact FP64 kernel
   // below that, for FP64 data, and whenever RCB_GRAM_FP64 is asked for.  RCB_GRAM=fp64|tensor overrides AUTO.
   const double macs = (double)F * (double)F * (double)(T - washout) * (double)nseq;
-  bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 1e12);
+  bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10);
   if (gram_mode == RCB_GRAM_AUTO) {
     const char* ov = getenv("RCB_GRAM");
     if (ov && !strcmp(ov, "fp64")) tensor = false;
