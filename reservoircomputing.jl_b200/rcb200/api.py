@@ -957,9 +957,14 @@ def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeR
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_range(n_chunks, rank, world)
-    h = _handle(rc, ps, X.dtype, device)
+    dev = device or default_device()
+    h = _handle(rc, ps, X.dtype, dev)
     F, d_out = h.F, Y.shape[0]
-    GC = np.zeros((F, F + d_out), dtype=np.float64, order="F")
+    # [G | C] stays on the GPU from the first partial Gram to the solve (F = 4096: 134 MB that would otherwise cross PCIe
+    # three times); torch only provides the device buffers and the process group
+    tdev = torch.device("cuda", dev.device)
+    GC = torch.zeros((F + d_out, F), dtype=torch.float64, device=tdev)   # memory image of the column-major F x (F + d_out)
+    part = torch.empty_like(GC)
     hT = None
 
     def run(windows, length):
@@ -968,20 +973,28 @@ def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeR
         d3 = np.asfortranarray(np.stack([X[:, s:s + length] for s, _, _ in windows], axis=2))
         y3 = np.asfortranarray(np.stack([Y[:, s:s + length] for s, _, _ in windows], axis=2))
         h0 = np.zeros((h.sumN, B), dtype=X.dtype, order="F")
-        part = np.empty_like(GC)
         hh = np.empty((h.sumN, B), dtype=X.dtype, order="F")
+        torch.cuda.current_stream(tdev).synchronize()
         check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), length, B, int(overlap), gram_mode, ptr(h0),
-                                      ptr(part), ptr(hh)))
-        GC[...] += part
+                                      ptr(part), ptr(hh)))   # returns after its stream has drained
+        GC.add_(part)
         hT = hh[:, -1:]
 
     if hi > lo:
         run(wins[lo:hi], Tc + overlap)
     if tail is not None and rank == world - 1:
         run([tail], tail[2] - tail[0])
-    if world > 1:
-        GC = _allreduce_gc(GC, d_out, group, device, use_lib=True)
-    W = ridge_solve(GC, d_out, float(objective.reg), device).astype(_promote(objective, X, Y))
+    if world > 1:  # only the lower triangle of G (+ C) travels: pack -> all-reduce -> unpack (rcb_gc_pack / rcb_gc_unpack)
+        packed = torch.empty(int(lib().rcb_gc_packed_len(F, d_out)), dtype=torch.float64, device=tdev)
+        torch.cuda.current_stream(tdev).synchronize()
+        check(lib().rcb_gc_pack(dev.handle, ptr(GC), F, d_out, ptr(packed)))
+        dist.all_reduce(packed, group=group)
+        torch.cuda.current_stream(tdev).synchronize()
+        check(lib().rcb_gc_unpack(dev.handle, ptr(packed), F, d_out, ptr(GC)))
+    torch.cuda.current_stream(tdev).synchronize()
+    Wd = np.empty((d_out, F), dtype=np.float64, order="F")
+    check(lib().rcb_ridge_solve(dev.handle, ptr(GC), F, d_out, float(objective.reg), ptr(Wd)))
+    W = Wd.astype(_promote(objective, X, Y))
     cell_sts = list(_cell_st(rc, st))
     if hT is None:
         hT = np.zeros((h.sumN, 1), dtype=X.dtype)
