@@ -905,9 +905,36 @@ def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegres
         raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
     if y3.shape[1] != T or y3.shape[2] != B:
         raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
+    d_out = y3.shape[0]
+    if _partial is None and _solve is None:
+        # the CUDA path: [G | C] never leaves the GPU between the partial Gram, the exchange and the solve
+        dev = device or default_device()
+        tdev = torch.device("cuda", dev.device)
+        h = _handle(rc, ps, d3.dtype, dev)
+        F = h.F
+        h0, cell_sts = _initial_carry(rc, st, d3.dtype, B)
+        GCd = torch.empty((F + d_out, F), dtype=torch.float64, device=tdev)   # memory image of the column-major F x (F + d_out)
+        hT = np.empty((h.sumN, B), dtype=d3.dtype, order="F")
+        torch.cuda.current_stream(tdev).synchronize()
+        check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B, int(washout), gram_mode, ptr(h0),
+                                      ptr(GCd), ptr(hT)))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            packed = torch.empty(int(lib().rcb_gc_packed_len(F, d_out)), dtype=torch.float64, device=tdev)
+            check(lib().rcb_gc_pack(dev.handle, ptr(GCd), F, d_out, ptr(packed)))
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            else:
+                pc = packed.cpu()
+                dist.all_reduce(pc, op=dist.ReduceOp.SUM, group=group)
+                packed.copy_(pc)
+            torch.cuda.current_stream(tdev).synchronize()
+            check(lib().rcb_gc_unpack(dev.handle, ptr(packed), F, d_out, ptr(GCd)))
+        Wd = np.empty((d_out, F), dtype=np.float64, order="F")
+        check(lib().rcb_ridge_solve(dev.handle, ptr(GCd), F, d_out, float(objective.reg), ptr(Wd)))
+        W = Wd.astype(_promote(objective, d3, y3))
+        return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
     partial = _partial or (lambda: _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode))
     GC, hT, cell_sts = partial() if _partial is None else _partial(rc, ps, st, d3, y3, washout)
-    d_out = y3.shape[0]
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         GC = _allreduce_gc(GC, d_out, group, device, use_lib=_partial is None)
     W = (_solve or (lambda g, d, r: ridge_solve(g, d, r, device)))(GC, d_out, float(objective.reg))
