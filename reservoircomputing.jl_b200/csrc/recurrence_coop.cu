@@ -1,5 +1,6 @@
 // K1 "coop": one sequence through a cell with a DENSE N x N operator (ES2N / ResESN: h' = a (O h) + b phi(W_in u + W h + b),
 // src/layers/es2n_cell.jl:106-116, src/layers/resesn_cell.jl:112-125), spread over many SMs.
+// (The slice of O a CTA owns is staged in its shared memory once when it fits: rows_per_cta * N * 4 bytes.)
 // A single CTA has to pull all of O (4 N^2 bytes: 4 MB at N = 1024) through its own L2 port every step — 58 us/step at
 // N = 1024, barely faster than a CPU core.  Here a cooperative grid shares the step: CTA g owns a block of rows, reads only
 // its slice of O (L2-resident, aggregate L2 bandwidth) and of W (CSR), and the new state is exchanged through a small
@@ -19,7 +20,7 @@ namespace rcb {
 namespace {
 
 struct CoopArgs {
-  int n, d_in, feat, act, rows_per_cta;
+  int n, d_in, feat, act, rows_per_cta, o_resident;  // o_resident: this CTA's rows of O are staged in shared memory once
   long long T;
   FusedMod mod;
   const float* Orow;          // n x n row-major
@@ -56,6 +57,9 @@ __global__ void __launch_bounds__(256) k1_coop_kernel(const CoopArgs a) {
   const int n = a.n;
   const int r0 = blockIdx.x * a.rows_per_cta, r1 = min(n, r0 + a.rows_per_cta);
   for (int r = r0 + tid; r < r1; r += blockDim.x) a.hbuf[r] = a.h0 ? a.h0[r] : 0.0f;
+  float* os = hs + ((n + 3) & ~3);  // [rows_per_cta][n]
+  if (a.o_resident)
+    for (int e = tid; e < (r1 - r0) * n; e += blockDim.x) os[e] = __ldg(a.Orow + (size_t)r0 * n + e);
   grid.sync();
   for (long long t = 0; t <= a.T; ++t) {
     const float* hin = a.hbuf + (size_t)(t & 1) * n;
@@ -74,19 +78,19 @@ __global__ void __launch_bounds__(256) k1_coop_kernel(const CoopArgs a) {
     if (t == a.T) break;
     const float* ut = a.u + (size_t)t * a.d_in;
     for (int r = r0 + warp; r < r1; r += nwarps) {
-      const float* orow = a.Orow + (size_t)r * n;
+      const float* orow = a.o_resident ? os + (size_t)(r - r0) * n : a.Orow + (size_t)r * n;
       float skip = 0.f, rec = 0.f;
       if ((n & 3) == 0) {  // 128-bit loads, several in flight: the slice of O streams from L2
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 4
         for (int j = lane * 4; j < n; j += 128) {
-          const float4 o = __ldg(reinterpret_cast<const float4*>(orow + j));
+          const float4 o = *reinterpret_cast<const float4*>(orow + j);
           const float4 h = *reinterpret_cast<const float4*>(hs + j);
           s0 = fmaf(o.x, h.x, s0); s1 = fmaf(o.y, h.y, s1); s2 = fmaf(o.z, h.z, s2); s3 = fmaf(o.w, h.w, s3);
         }
         skip = (s0 + s1) + (s2 + s3);
       } else {
-        for (int j = lane; j < n; j += 32) skip = fmaf(__ldg(orow + j), hs[j], skip);
+        for (int j = lane; j < n; j += 32) skip = fmaf(orow[j], hs[j], skip);
       }
       for (long long e = a.rowptr[r] + lane; e < a.rowptr[r + 1]; e += 32) rec = fmaf(__ldg(a.vals + e), hs[__ldg(a.colind + e)], rec);
 #pragma unroll
@@ -134,21 +138,24 @@ int32_t launch_collect_coop(rcb_ctx* ctx, const RecParams& p, const Layer& L, bo
   void* hb = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_INFO, 2 * (size_t)p.n * sizeof(float), &hb));  // (SCR_RAW may hold the raw states this very call writes)
   a.hbuf = reinterpret_cast<float*>(hb);
-  const size_t smem = (size_t)p.n * sizeof(float);
+  int grid = std::min(ctx->sm_count, std::max(1, p.n / 8));  // one row per warp where the machine is wide enough, one CTA per SM
+  a.rows_per_cta = (p.n + grid - 1) / grid;
+  grid = (p.n + a.rows_per_cta - 1) / a.rows_per_cta;
+  const size_t hs_bytes = (size_t)((p.n + 3) & ~3) * sizeof(float);
+  size_t smem = hs_bytes;
+  const size_t o_bytes = (size_t)a.rows_per_cta * p.n * sizeof(float);
+  a.o_resident = hs_bytes + o_bytes <= ctx->smem_optin ? 1 : 0;   // this CTA's slice of O stays on chip for the whole call
+  if (a.o_resident) smem += o_bytes;
   RCB_CUDA(cudaFuncSetAttribute(k1_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_kernel, 256, smem));
   if (per_sm < 1) return RCB_OK;
-  int grid = std::min(ctx->sm_count * per_sm, std::max(1, p.n / 8));  // one row per warp where the machine is wide enough
-  grid = std::min(grid, ctx->sm_count);
-  a.rows_per_cta = (p.n + grid - 1) / grid;
-  grid = (p.n + a.rows_per_cta - 1) / a.rows_per_cta;
   void* args[] = {(void*)&a};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   cudaError_t e = cudaLaunchCooperativeKernel((void*)k1_coop_kernel, dim3((unsigned)grid), dim3(256), args, smem, ctx->stream);
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (e != cudaSuccess) return fail(RCB_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop<dense skip operator> grid=%d", grid);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop<dense skip operator%s> grid=%d", a.o_resident ? ",O-resident" : "", grid);
   ctx->launches++;
   *launched = true;
   return RCB_OK;
