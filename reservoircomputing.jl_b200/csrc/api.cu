@@ -1392,7 +1392,10 @@ int32_t rcb_hessenberg_eigvals(const double* H, int32_t m, double* re, double* i
   for (int i = 0; i < m; ++i)
     for (int j = 0; j < m; ++j) h[(size_t)i * m + j] = H[(size_t)j * m + i];  // column-major in, row-major inside
   std::vector<std::complex<double>> ev;
-  if (!hessenberg_eigvals(h, m, &ev)) return fail(RCB_ERR_NUMERIC, "Hessenberg QR iteration did not converge");
+  const char* which = getenv("RCB_HESS_QR");  // testing hook: "complex" runs the single-shift fallback directly
+  const bool ok = (which && !strcmp(which, "complex")) ? hessenberg_eigvals(h, m, &ev)
+                                                       : (hessenberg_eigvals_francis(h, m, &ev) || hessenberg_eigvals(h, m, &ev));
+  if (!ok) return fail(RCB_ERR_NUMERIC, "Hessenberg QR iteration did not converge");
   for (int i = 0; i < m; ++i) { re[i] = ev[(size_t)i].real(); im[i] = ev[(size_t)i].imag(); }
   return RCB_OK;
 }

@@ -253,6 +253,7 @@ int32_t launch_delay(rcb_ctx* ctx, const void* x, int32_t dtype, int64_t n, int6
 
 // spectral.cu: rho(A) = max |eigenvalue| by Arnoldi on the GPU + Hessenberg QR on the host
 bool hessenberg_eigvals(const std::vector<double>& Hin, int m, std::vector<std::complex<double>>* ev);
+bool hessenberg_eigvals_francis(const std::vector<double>& Hin, int m, std::vector<std::complex<double>>* ev);
 int32_t spectral_radius_csr(rcb_ctx* ctx, const HostCsr& A, double tol, int32_t max_dim, double* rho, int32_t* dim_used);
 
 // (G + lambda I) W' = C, GC = [G | C] F x (F + d_out) device Float64 (destroyed); W_out d_out x F device.

@@ -184,3 +184,15 @@ def test_hessenberg_eigvals_special_cases(R):
     assert np.allclose(sorted(ev.imag), [-1, 1]) and np.allclose(ev.real, 0)
     C3 = np.array([[0.0, 0, 1], [1, 0, 0], [0, 1, 0]])     # cyclic shift: cube roots of unity (all moduli equal)
     assert np.allclose(np.abs(R.hessenberg_eigvals(C3)), 1.0)
+
+
+def test_hessenberg_eigvals_both_iterations_agree(R, monkeypatch):
+    """The real Francis double-shift iteration (default) and the complex single-shift fallback see the same spectrum."""
+    rng = np.random.default_rng(11)
+    H = np.triu(rng.standard_normal((120, 120)), -1)
+    a = R.hessenberg_eigvals(H)
+    monkeypatch.setenv("RCB_HESS_QR", "complex")
+    b = R.hessenberg_eigvals(H)
+    assert np.max(np.abs(np.sort(np.abs(a)) - np.sort(np.abs(b)))) <= 1e-9 * np.max(np.abs(a))
+    assert abs(a.sum() - b.sum()) <= 1e-9 * 120
+    assert np.sum(a.imag > 0) == np.sum(a.imag < 0)   # complex eigenvalues of a real matrix come in conjugate pairs
