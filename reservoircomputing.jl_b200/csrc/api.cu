@@ -461,12 +461,13 @@ static int32_t collect_device(rcb_esn* esn, const void* u_dev, int64_t Tc, int64
         a.member_leak = esn->d_member_leak + member_off;
       }
     } else {
-      if (esn->desc.data_dtype != RCB_F32)
-        return fail(RCB_ERR_UNSUPPORTED, "DeepESN collectstates is implemented for Float32 data");
       const int npos = L.sell.R * L.sell.nthreads;
       void* P = nullptr;
-      RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)npos * Tc * Bc * sizeof(float), &P));
-      RCB_TRY(launch_input_projection(ctx, L.d_Win, npos, L.d_in, (const float*)zin, Tc * Bc, (float*)P));
+      RCB_TRY(ctx_scratch(ctx, SCR_TMP, (size_t)npos * Tc * Bc * esz, &P));
+      if (esn->desc.data_dtype == RCB_F64)
+        RCB_TRY(launch_input_projection_f64(ctx, L.d_Win, npos, L.d_in, (const double*)zin, Tc * Bc, (double*)P));
+      else
+        RCB_TRY(launch_input_projection(ctx, L.d_Win, npos, L.d_in, (const float*)zin, Tc * Bc, (float*)P));
       a.pre_in = P;
     }
     void* zout = nullptr;
@@ -1289,7 +1290,7 @@ static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B,
   const size_t fbytes = (size_t)esn->feat * dsz;
   const size_t budget = (size_t)1 << 30;
   const bool via_collect = !autoreg && esn->readout_members <= 1 && (fbytes * (size_t)T <= budget || B == 1) &&
-                           (esn->layers.size() == 1 || esn->desc.data_dtype == RCB_F32);  // (the DeepESN collect is Float32-only)
+                           true;
   if (via_collect) {
     void* carry = h_dev;
     if (!carry) {

@@ -214,6 +214,63 @@ __global__ void __launch_bounds__(256, 2) input_projection_kernel(const float* _
   }
 }
 
+// Float64 data (DeepESN with Float64 inputs: W_in stays Float32 as in ps, the product promotes like the reference's gemv):
+// a plain 64 x 64 shared-memory tiled kernel — this path is a correctness path, not a tuned one.
+__global__ void __launch_bounds__(256) input_projection_f64_kernel(const float* __restrict__ Wp, long long N, long long K,
+                                                                   const double* __restrict__ Z, long long S, double* __restrict__ P) {
+  constexpr int TILE = 64, KC = 16;
+  __shared__ double As[KC][TILE];
+  __shared__ double Bs[KC][TILE + 1];
+  const long long i0 = (long long)blockIdx.x * TILE, j0 = (long long)blockIdx.y * TILE;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4] = {};
+  for (long long k0 = 0; k0 < K; k0 += KC) {
+    const int li = tid & 63, lk = tid >> 6;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long k = k0 + lk + 4 * q;
+      As[lk + 4 * q][li] = (k < K && i0 + li < N) ? (double)Wp[(size_t)k * N + i0 + li] : 0.0;
+    }
+    const int lkk = tid & 15, lj = tid >> 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long j = j0 + lj + 16 * q, k = k0 + lkk;
+      Bs[lkk][lj + 16 * q] = (k < K && j < S) ? Z[(size_t)j * K + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { a[q] = As[kk][tx + 16 * q]; b[q] = Bs[kk][ty + 16 * q]; }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const long long i = i0 + tx + 16 * x, j = j0 + ty + 16 * y;
+      if (i < N && j < S) P[(size_t)j * N + i] = acc[x][y];
+    }
+}
+
+int32_t launch_input_projection_f64(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const double* Z, int64_t S, double* P) {
+  const int64_t step = 65535LL * 64;
+  for (int64_t s0 = 0; s0 < S; s0 += step) {
+    const int64_t sc = S - s0 < step ? S - s0 : step;
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((sc + 63) / 64));
+    input_projection_f64_kernel<<<grid, 256, 0, ctx->stream>>>(Win, N, K, Z + (size_t)s0 * K, sc, P + (size_t)s0 * N);
+    ctx->launches++;
+  }
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
 int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,
                                 float* P) {
   const bool vec = (N % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Win) | reinterpret_cast<uintptr_t>(Z) |

@@ -265,5 +265,7 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
 // dense input projection P(N x S) = W_in(N x K) * Z(K x S), FP32 (deep layers)
 int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,
                                 float* P);
+// the same for Float64 features (W_in is Float32 as in ps; Float64 accumulate)
+int32_t launch_input_projection_f64(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const double* Z, int64_t S, double* P);
 
 }  // namespace rcb

@@ -1171,25 +1171,33 @@ def test_autoregressive_kernel_matches_generic_loop_and_oracle(R, N, d, mods, f6
     assert state_err(Y, Yo) <= (1e-5 if f64 else 1e-3)
 
 
-def test_deep_esn_float64_teacher_forced_predict(R):
-    """Float64 data through a DeepESN: collectstates is Float32-only for deep models (documented limit), but predict must
-    keep working in Float64 through the general fused loop."""
+def test_deep_esn_float64_data(R):
+    """Float64 data through a DeepESN: eltype(states) follows the data (esn_deep.jl:288); the inter-layer projection runs
+    in Float64 with the Float32 W_in promoted, like the reference's gemv."""
     rng = np.random.default_rng(31)
-    res = [40, 56]
-    desn = R.DeepESN(2, res, 2, init_reservoir=R.rand_sparse(radius=0.8, sparsity=0.2), leak_coefficient=0.8, state_modifiers=R.NLAT2)
+    res = [40, 56, 33]
+    desn = R.DeepESN(2, res, 2, init_reservoir=R.rand_sparse(radius=0.8, sparsity=0.2), leak_coefficient=0.8,
+                     state_modifiers=(R.NLAT2, R.NLAT1, (R.NLAT3, R.Pad(1.0))))
     ps, st = R.setup(rng, desn)
     T = 30
-    data = np.asfortranarray(rng.standard_normal((2, T)))
-    W = rng.standard_normal((2, 56))
+    data = np.asfortranarray(rng.standard_normal((2, T, 2)))
+    W = rng.standard_normal((2, 34))
     ps2 = ps.merge(readout=ps.readout.merge(weight=W))
-    hs0 = [rng.standard_normal(n) for n in res]
+    hs0 = [rng.standard_normal((n, 2)) for n in res]
     st0 = fixed_h0(R, st, desn, hs0)
+    states, st1 = R.collectstates(desn, data, ps2, st0)
+    assert states.dtype == np.float64 and states.shape == (34, T, 2)
     Y, _ = R.predict(desn, data, ps2, st0)
-    assert Y.dtype == np.float64 and "k4_generic<f64" in R.default_device().last_kernel()
-    Yo, _ = O.predict_teacher(oracle_layers(R, desn, ps2), W, data, hs0)
-    assert state_err(Y, Yo) <= 1e-10
-    with pytest.raises(R.UnsupportedError):
-        R.collectstates(desn, data, ps2, st0)
+    assert Y.dtype == np.float64
+    layers = oracle_layers(R, desn, ps2)
+    for b in range(2):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h[:, b] for h in hs0])
+        assert state_err(states[:, :, b], ref) <= 1e-11
+        for l in range(3):
+            assert state_err(st1.cells[l].carry[0][:, b:b + 1], hs[l].reshape(-1, 1)) <= 1e-11
+        Yo, _ = O.predict_teacher(layers, W, data[:, :, b], [h[:, b] for h in hs0])
+        assert state_err(Y[:, :, b], Yo) <= 1e-10
+
 
 
 @pytest.mark.parametrize("name,N,mods", [("es2n", 300, "nlat2_pad"), ("resesn", 1024, "esq"), ("es2n", 130, "nlat1_nlat2"), ("resesn", 64, "none")])
