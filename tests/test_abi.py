@@ -196,3 +196,33 @@ def test_hessenberg_eigvals_both_iterations_agree(R, monkeypatch):
     assert np.max(np.abs(np.sort(np.abs(a)) - np.sort(np.abs(b)))) <= 1e-9 * np.max(np.abs(a))
     assert abs(a.sum() - b.sum()) <= 1e-9 * 120
     assert np.sum(a.imag > 0) == np.sum(a.imag < 0)   # complex eigenvalues of a real matrix come in conjugate pairs
+
+
+# ---- the kernels' gather schedule is built on the host: its invariants are checkable without a GPU -----------------
+@pytest.mark.parametrize("n,k,nthreads", [(64, 3, 64), (300, 6, 320), (1024, 6, 1024), (2048, 12, 1024), (4096, 6, 1024)])
+def test_gather_schedule_invariants(R, n, k, nthreads):
+    import ctypes as C
+    from rcb200 import _lib as L
+
+    W = O.rand_sparse_like(np.random.default_rng(n + k), n, radius=0.9, sparsity=k / n) if n <= 1500 else None
+    if W is None:  # no spectral scaling needed for a structural test
+        rng = np.random.default_rng(n + k)
+        W = np.zeros((n, n), np.float32)
+        for j in range(n):
+            W[rng.choice(n, size=k, replace=False), j] = rng.standard_normal(k).astype(np.float32)
+    Wf = np.asfortranarray(W, dtype=np.float32)
+    st = (C.c_int64 * 10)()
+    for balanced in (0, 1):
+        L.check(L.lib().rcb_sell_stats_from_dense(L.ptr(Wf), n, n, nthreads, balanced, st))
+        nnz, padded, wf64, ideal64, wf32, ideal32, roundtrip, missing, wb, wbi = list(st)
+        assert nnz == n * k and roundtrip == 1 and missing == 0        # every (row, col, value) triple exactly once, rows a bijection
+        assert padded >= nnz and padded % 32 == 0
+        if balanced:
+            assert wf64 == ideal64                                       # every half-warp LDS.64 gather is bank-conflict free
+            if n >= 300:
+                assert padded <= 1.35 * nnz                              # the price: a bounded amount of padding ...
+            if n >= 4096 and k == 6:
+                assert padded <= 1.10 * nnz                              # ... 4-7 % at the sizes the batched kernel is built for
+            assert wb <= 1.5 * wbi + 8                                   # rows of a half-warp mostly distinct mod 16 (write-back conflicts)
+        else:
+            assert wf64 >= ideal64
