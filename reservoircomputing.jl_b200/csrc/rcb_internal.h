@@ -238,7 +238,7 @@ struct GramArgs {
 int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a);
 // lower triangle of G + cross block <-> contiguous exchange buffer (device pointers)
 int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double* packed, bool unpack);
-// tcgen05 3xTF32 path (gram_tensor.cu): G(F x F, FP64, lower triangle) += Z Z' over the same sample set; Z FP32
+// tcgen05 kind::i8 fixed-point path (gram_int8.cu): G(F x F, FP64, lower triangle) += Z Z' over the same sample set; Z FP32
 // Y != nullptr && d_out <= 8: the cross term C(F x d_out, ld = ldo) += Z Y' rides along in FP64.
 int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
                            double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C);
