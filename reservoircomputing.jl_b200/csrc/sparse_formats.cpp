@@ -233,6 +233,13 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return len(a) > len(b); });
   std::vector<char> used((size_t)n, 0);
   std::vector<GroupPlan> plan((size_t)ngroups);
+  // column-residue histogram of every row (what a candidate would add to the group's counts): 16 bytes per row
+  std::vector<uint8_t> hist((size_t)n * 16, 0);
+  for (int32_t r = 0; r < n; ++r)
+    for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) {
+      uint8_t& h = hist[(size_t)r * 16 + (csr.colind[(size_t)e] & 15)];
+      if (h < 255) ++h;
+    }
   size_t head = 0;  // first unassigned position in `order`
   // Candidate window and length slack of the greedy group builder.  A group of 16 equally long rows needs every column
   // residue hit exactly `len` times to avoid an extra slot (16 padded entries); a few shorter rows in the group give
@@ -270,10 +277,12 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
         if (len(r) < seedlen - SLACK && best >= 0) break;  // keep lengths within a group close (sorted order)
         int mx = 0;
         long sq = 0;
-        int tmp[16];
-        std::copy(cnt, cnt + 16, tmp);
-        for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) tmp[csr.colind[(size_t)e] & 15]++;
-        for (int i = 0; i < 16; ++i) { mx = std::max(mx, tmp[i]); sq += (long)tmp[i] * tmp[i]; }
+        const uint8_t* hr = &hist[(size_t)r * 16];
+        for (int i = 0; i < 16; ++i) {
+          const int t = cnt[i] + hr[i];
+          mx = std::max(mx, t);
+          sq += (long)t * t;
+        }
         // slots the group would need first, then missing entries, then a distinct own-row residue, then evenness
         const long cost = (long)std::max(mx, seedlen) * 1000000L + (long)(seedlen - len(r)) * 1000L + (own[r & 15] ? OWNW : 0L) + sq * 10L;
         if (best < 0 || cost < bestcost) { best = (int64_t)q; bestcost = cost; }
