@@ -216,6 +216,12 @@ RCB_API int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, c
 #define RCB_GRAM_AUTO 0
 #define RCB_GRAM_FP64 1
 #define RCB_GRAM_TENSOR 2
+/* No Gram at all: FP64 Householder QR of the augmented system [Z'; sqrt(λ) I] W' = [Y'; 0] — the reference's own algorithm
+ * (qr(design) \ rhs, src/train.jl:140-147,182) — streamed over sample chunks as a triangular-pentagonal QR (csrc/qr_solve.cu);
+ * error ~ cond(design) instead of cond^2.  The accumulator [R | Q'b] has the footprint of [G | C].
+ * RCB_GRAM_AUTO escalates by itself: λ == 0 (the reference's default objective, train.jl:234) goes straight to QR; a Cholesky
+ * that meets a non-positive pivot is retried on the exact FP64 Gram and then by QR before RCB_ERR_NUMERIC is reported. */
+#define RCB_FIT_QR 3
 RCB_API int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S_states,
                         int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out,
                         int64_t S_targets, int64_t ld_targets, double lambda, int32_t gram_mode,
@@ -234,6 +240,14 @@ RCB_API int32_t rcb_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d
 RCB_API int32_t rcb_gc_unpack(rcb_ctx* ctx, const double* packed, int64_t F, int64_t d_out, double* GC);
 /* Solve (G + λ I) W' = C from a packed [G | C]; only the lower triangle of G is read. */
 RCB_API int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
+
+/* QR-path counterparts (accumulate with rcb_gram_accumulate / rcb_train_partial and gram_mode = RCB_FIT_QR: the buffer then
+ * holds a partial factor [R | Q'b] instead of [G | C]).  Partial factors are not summed but merged:
+ *   rcb_qr_merge   RQ <- QR of [RQ; other]   (one triangular-pentagonal step; ranks all-gather their factors and merge)
+ *   rcb_qr_solve   absorbs the sqrt(λ) I rows into a copy and back-substitutes R W' = Q'b.
+ * A singular R (rank-deficient features at λ = 0) -> RCB_ERR_NUMERIC (train.jl:194-196). */
+RCB_API int32_t rcb_qr_merge(rcb_ctx* ctx, double* RQ, const double* other, int64_t F, int64_t d_out);
+RCB_API int32_t rcb_qr_solve(rcb_ctx* ctx, const double* RQ, int64_t F, int64_t d_out, double lambda, double* W_out);
 
 /* ---- train: collect -> washout -> ridge -> addreadout! ------------------------------------------
  * Replaces train (src/train.jl:232-251) with __apply_washout (:36-47).  Pooled readout over the B

@@ -928,6 +928,33 @@ static int32_t check_ridge_args(int64_t S_states, int64_t S_targets, double lamb
   return RCB_OK;
 }
 
+static int32_t check_fit_mode(int32_t mode) {
+  if (mode < RCB_GRAM_AUTO || mode > RCB_FIT_QR) return fail(RCB_ERR_ARGUMENT, "unknown gram_mode / fit mode %d", mode);
+  return RCB_OK;
+}
+// RCB_GRAM_AUTO takes the QR path for lambda == 0 — the reference's default objective (train.jl:234), where the normal
+// equations square the condition number of a least-squares problem nothing regularises.
+static bool want_qr(int32_t mode, double lambda) { return mode == RCB_FIT_QR || (mode == RCB_GRAM_AUTO && lambda == 0.0); }
+
+// one chunk of samples into the accumulator: [G | C] += (Gram path) or [R | Qb] <- QR([R | Qb; Z' | Y']) (QR path)
+static int32_t accumulate_device(rcb_ctx* ctx, bool qr, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y,
+                                 int32_t ydt, int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq,
+                                 int32_t gram_mode, double* GC) {
+  if (qr) {
+    ctx->last_gram_tensor = 0;
+    return launch_qr_accumulate(ctx, Z, zdt, F, ldz, Y, ydt, d_out, ldy, T, washout, nseq, GC);
+  }
+  return gram_device(ctx, Z, zdt, F, ldz, Y, ydt, d_out, ldy, T, washout, nseq, gram_mode == RCB_FIT_QR ? RCB_GRAM_FP64 : gram_mode, GC);
+}
+// accumulator (destroyed) -> W (d_out x F, device)
+static int32_t solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t d_out, double lambda, double* w_dev) {
+  if (qr) {
+    RCB_TRY(launch_qr_absorb_lambda(ctx, GC, F, d_out, lambda));
+    return launch_qr_solve(ctx, GC, F, d_out, 1, w_dev, nullptr);
+  }
+  return launch_ridge_solve(ctx, GC, F, d_out, lambda, w_dev);
+}
+
 int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S, int64_t ld_states,
                             const void* targets, int32_t targets_dtype, int64_t d_out, int64_t ld_targets, int32_t gram_mode,
                             int32_t zero_first, double* GC) {
@@ -935,6 +962,7 @@ int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dty
   if (F < 1 || d_out < 1) return fail(RCB_ERR_ARGUMENT, "F and d_out must be ≥ 1");
   if (S < 1) return fail(RCB_ERR_ARGUMENT, "ridge regression requires at least one training sample");
   if (ld_states < F || ld_targets < d_out) return fail(RCB_ERR_DIMENSION, "leading dimension smaller than the row count");
+  RCB_TRY(check_fit_mode(gram_mode));
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
   const size_t zsz = states_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
@@ -952,7 +980,8 @@ int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dty
     if (!zero_first) RCB_CUDA(cudaMemcpyAsync(gc_dev, GC, gc_bytes, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (zero_first) RCB_CUDA(cudaMemsetAsync(gc_dev, 0, gc_bytes, ctx->stream));
-  RCB_TRY(gram_device(ctx, Z, states_dtype, F, ld_states, Y, targets_dtype, d_out, ld_targets, S, 0, 1, gram_mode, gc_dev));
+  RCB_TRY(accumulate_device(ctx, gram_mode == RCB_FIT_QR, Z, states_dtype, F, ld_states, Y, targets_dtype, d_out, ld_targets, S, 0, 1,
+                            gram_mode, gc_dev));
   if (gc_host) RCB_TRY(from_device(ctx, GC, gc_dev, gc_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
@@ -996,8 +1025,47 @@ int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out
   RCB_TRY(to_device(ctx, work, GC, gc_bytes));
   void* w_dev = nullptr;
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
-  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
+  RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
   RCB_TRY(launch_ridge_solve(ctx, (double*)work, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+// QR-path counterparts of the [G | C] exchange: a rank's partial factor [R | Qb] (accumulated with gram_mode = RCB_FIT_QR)
+// is merged into another by one more triangular-pentagonal step; lambda enters at solve time.
+int32_t rcb_qr_merge(rcb_ctx* ctx, double* RQ, const double* other, int64_t F, int64_t d_out) {
+  if (!ctx || !RQ || !other) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (F < 1 || d_out < 1) return fail(RCB_ERR_ARGUMENT, "F and d_out must be ≥ 1");
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)F * (F + d_out) * sizeof(double);
+  const void* o_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_TMP, other, bytes, &o_dev));
+  double* r_dev = RQ;
+  if (!is_device_ptr(RQ)) {
+    void* p = nullptr;
+    RCB_TRY(ctx_scratch(ctx, SCR_GC, bytes, &p));
+    r_dev = (double*)p;
+    RCB_CUDA(cudaMemcpyAsync(r_dev, RQ, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RCB_TRY(launch_qr_merge(ctx, r_dev, (const double*)o_dev, F, d_out));
+  if (r_dev != RQ) RCB_TRY(from_device(ctx, RQ, r_dev, bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_qr_solve(rcb_ctx* ctx, const double* RQ, int64_t F, int64_t d_out, double lambda, double* W_out) {
+  if (!ctx || !RQ || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)F * (F + d_out) * sizeof(double);
+  void* work = nullptr;  // absorbing the lambda rows changes the factor: always work on a copy
+  RCB_TRY(ctx_scratch(ctx, SCR_TMP, bytes, &work));
+  RCB_TRY(to_device(ctx, work, RQ, bytes));
+  void* w_dev = nullptr;
+  const size_t w_bytes = (size_t)d_out * F * sizeof(double);
+  RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
+  RCB_TRY(solve_device(ctx, true, (double*)work, F, d_out, lambda, (double*)w_dev));
   RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
@@ -1009,21 +1077,29 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
   if (!ctx || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   RCB_TRY(check_ridge_args(S_states, S_targets, lambda));
   if (!states || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  RCB_TRY(check_fit_mode(gram_mode));
   RCB_CUDA(cudaSetDevice(ctx->device));
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
-  RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
-                              gram_mode, 1, (double*)gc));
   void* w_dev = nullptr;
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
-  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
-  int32_t st = launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev);
-  if (st == RCB_ERR_NUMERIC && gram_mode == RCB_GRAM_AUTO && ctx->last_gram_tensor) {
-    // the tensor-core Gram carries ~5e-6 relative error; when lambda sits below that noise floor the system can come out
-    // indefinite.  The states are at hand here: redo the accumulation with exact products in FP64 and solve again.
+  RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
+  // AUTO: Cholesky on the Gram (tensor cores for large contractions) -> on a failed factorisation the exact FP64 Gram ->
+  // then the Householder QR of the augmented system itself (the reference's algorithm; error ~ cond instead of cond^2).
+  // lambda == 0 goes to QR directly.
+  int32_t modes[3], nm = 0;
+  if (want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
+  else {
+    modes[nm++] = gram_mode;
+    if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
+  }
+  int32_t st = RCB_OK;
+  for (int32_t i = 0; i < nm; ++i) {
+    if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;  // the first attempt already was exact
     RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
-                                RCB_GRAM_FP64, 1, (double*)gc));
-    st = launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev);
+                                modes[i], 1, (double*)gc));
+    st = solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);
   RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
@@ -1036,6 +1112,7 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
 static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
                                 int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* gc_dev,
                                 void* states_out, void* hT_out) {
+  const bool qr = gram_mode == RCB_FIT_QR;
   rcb_ctx* ctx = esn->ctx;
   const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
   const int64_t F = esn->feat, d_out = esn->desc.out_dims, d_in = esn->desc.in_dims, sumN = esn->sumN;
@@ -1086,7 +1163,7 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
       if (wo < nt) {
         RCB_CUDA(cudaMemcpy2DAsync(yw, (size_t)nt * d_out * ysz, (const char*)y_dev + (size_t)t0 * d_out * ysz, (size_t)T * d_out * ysz,
                                    (size_t)nt * d_out * ysz, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream));
-        RCB_TRY(gram_device(ctx, st_dev, esn->desc.data_dtype, F, F, yw, targets_dtype, d_out, d_out, nt, wo, B, gram_mode, gc_dev));
+        RCB_TRY(accumulate_device(ctx, qr, st_dev, esn->desc.data_dtype, F, F, yw, targets_dtype, d_out, d_out, nt, wo, B, gram_mode, gc_dev));
       }
     }
     if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
@@ -1106,7 +1183,7 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
       if (wo < nt) {
         // targets of this chunk: d_out x nt per sequence inside the d_out x T x B array
         const void* yc = (const char*)y_dev + ((size_t)b0 * T + t0) * d_out * ysz;
-        RCB_TRY(gram_device(ctx, st_dev, esn->desc.data_dtype, F, F, yc, targets_dtype, d_out, d_out, nt, wo, nb, gram_mode, gc_dev));
+        RCB_TRY(accumulate_device(ctx, qr, st_dev, esn->desc.data_dtype, F, F, yc, targets_dtype, d_out, d_out, nt, wo, nb, gram_mode, gc_dev));
       }
       if (states_out) {
         for (int64_t b = 0; b < nb; ++b) {
@@ -1137,6 +1214,7 @@ int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int3
                           int64_t washout, int32_t gram_mode, const void* h0, double* GC, void* hT_out) {
   RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
   if (!GC) return fail(RCB_ERR_ARGUMENT, "GC is NULL");
+  RCB_TRY(check_fit_mode(gram_mode));
   rcb_ctx* ctx = esn->ctx;
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
@@ -1163,13 +1241,27 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
   const int64_t F = esn->feat, d_out = esn->desc.out_dims;
+  RCB_TRY(check_fit_mode(gram_mode));
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
-  RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, gram_mode, h0, (double*)gc, states_out, hT_out));
   void* w_dev = nullptr;
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
-  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_bytes, &w_dev));
-  RCB_TRY(launch_ridge_solve(ctx, (double*)gc, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
+  // same escalation as rcb_fit_readout; the states are not kept, so a retry runs the recurrence again (identical carry)
+  int32_t modes[3], nm = 0;
+  if (want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
+  else {
+    modes[nm++] = gram_mode;
+    if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
+  }
+  int32_t st = RCB_OK;
+  for (int32_t i = 0; i < nm; ++i) {
+    if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;
+    RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, modes[i], h0, (double*)gc, states_out, hT_out));
+    st = solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    if (st != RCB_ERR_NUMERIC) break;
+  }
+  RCB_TRY(st);
   RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   // addreadout! (src/reservoircomputer.jl:137-144): install the fitted weight; a bias, if the readout
@@ -1183,6 +1275,7 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
                           double* W_out, void* hT_out) {
   RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
   if (n_lambda < 1 || !lambdas || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument or n_lambda < 1");
+  RCB_TRY(check_fit_mode(gram_mode));
   for (int32_t i = 0; i < n_lambda; ++i)
     if (!(lambdas[i] >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambdas[i]);
   rcb_ctx* ctx = esn->ctx;
@@ -1213,7 +1306,7 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   void *gc = nullptr, *work = nullptr, *w_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_elems * sizeof(double), &gc));
   RCB_TRY(ctx_scratch(ctx, SCR_W, gc_elems * sizeof(double) * (size_t)(mg * n_lambda), &work));
-  RCB_TRY(ctx_scratch(ctx, SCR_Y, w_elems * sizeof(double) * (size_t)(mg * n_lambda), &w_dev));
+  RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_elems * sizeof(double) * (size_t)(mg * n_lambda), &w_dev));  // (SCR_Y is an inter-layer buffer of collect_device)
   std::vector<double> lam_rep((size_t)(mg * n_lambda));
   for (int64_t m = 0; m < mg; ++m)
     for (int32_t l = 0; l < n_lambda; ++l) lam_rep[(size_t)(m * n_lambda + l)] = lambdas[l];
@@ -1225,25 +1318,53 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
     RCB_TRY(collect_device(esn, uc, T, nb, hc, st_dev, hc, b0));
     for (int64_t g0 = 0; g0 < nb; g0 += mg) {
       const int64_t ng = std::min<int64_t>(mg, nb - g0);
+      std::fill(info.begin(), info.end(), 0);
+      if (gram_mode != RCB_FIT_QR) {
+        for (int64_t m = 0; m < ng; ++m) {
+          const int64_t b = g0 + m;
+          const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
+          const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
+          RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
+          RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
+          for (int32_t l = 0; l < n_lambda; ++l)
+            RCB_CUDA(cudaMemcpyAsync((double*)work + (size_t)(m * n_lambda + l) * gc_elems, gc, gc_elems * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data());
+        if (st != RCB_ERR_NUMERIC) RCB_TRY(st);
+        if (st == RCB_ERR_NUMERIC && gram_mode != RCB_GRAM_AUTO) {
+          for (int64_t z = 0; z < ng * n_lambda; ++z)
+            if (info[(size_t)z] != 0)
+              return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: the regularised Gram matrix is not numerically positive definite "
+                          "(non-positive pivot at feature %d)", (long long)(b0 + g0 + z / n_lambda), (int)(z % n_lambda), lambdas[z % n_lambda],
+                          info[(size_t)z]);
+        }
+      }
+      // QR path per member: asked for, lambda == 0 (AUTO), or a failed Cholesky (AUTO).  The factor of the member's samples is
+      // computed once; every lambda absorbs its sqrt(lambda) I rows into a copy (2 F^3 flops instead of 2 S F^2).
       for (int64_t m = 0; m < ng; ++m) {
+        bool need = gram_mode == RCB_FIT_QR;
+        for (int32_t l = 0; l < n_lambda && !need; ++l)
+          need = gram_mode == RCB_GRAM_AUTO && (lambdas[l] == 0.0 || info[(size_t)(m * n_lambda + l)] != 0);
+        if (!need) continue;
         const int64_t b = g0 + m;
         const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
         const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
-        RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
-        RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
-        for (int32_t l = 0; l < n_lambda; ++l)
-          RCB_CUDA(cudaMemcpyAsync((double*)work + (size_t)(m * n_lambda + l) * gc_elems, gc, gc_elems * sizeof(double),
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
+        RCB_TRY(launch_qr_init(ctx, (double*)gc, F, d_out));
+        RCB_TRY(launch_qr_accumulate(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, (double*)gc));
+        for (int32_t l = 0; l < n_lambda; ++l) {
+          const size_t z = (size_t)(m * n_lambda + l);
+          if (!(gram_mode == RCB_FIT_QR || lambdas[l] == 0.0 || info[z] != 0)) continue;
+          double* wk = (double*)work + z * gc_elems;
+          RCB_CUDA(cudaMemcpyAsync(wk, gc, gc_elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+          RCB_TRY(launch_qr_absorb_lambda(ctx, wk, F, d_out, lambdas[l]));
+          const int32_t sq = launch_qr_solve(ctx, wk, F, d_out, 1, (double*)w_dev + z * w_elems, nullptr);
+          if (sq == RCB_ERR_NUMERIC)
+            return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: solver QRFactorization failed to solve the ridge regression system "
+                        "(rank-deficient features)", (long long)(b0 + b), (int)l, lambdas[l]);
+          RCB_TRY(sq);
+        }
       }
-      const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data());
-      if (st == RCB_ERR_NUMERIC) {
-        for (int64_t z = 0; z < ng * n_lambda; ++z)
-          if (info[(size_t)z] != 0)
-            return fail(RCB_ERR_NUMERIC, "member %lld, lambda[%d] = %g: the regularised Gram matrix is not numerically positive definite "
-                        "(non-positive pivot at feature %d)", (long long)(b0 + g0 + z / n_lambda), (int)(z % n_lambda), lambdas[z % n_lambda],
-                        info[(size_t)z]);
-      }
-      RCB_TRY(st);
       RCB_TRY(from_device(ctx, W_out + (size_t)(b0 + g0) * n_lambda * w_elems, w_dev, w_elems * sizeof(double) * (size_t)(ng * n_lambda)));
     }
   }

@@ -160,8 +160,8 @@ struct rcb_ctx {
   // pinned staging + scratch, grown on demand
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
-  void* scratch[16] = {};
-  size_t scratch_bytes[16] = {};
+  void* scratch[24] = {};
+  size_t scratch_bytes[24] = {};
 };
 
 struct rcb_esn {
@@ -185,7 +185,9 @@ namespace rcb {
 // scratch slots
 enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5, SCR_TMP2 = 6, SCR_TGT = 7,
        SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_ZHI = 12, SCR_ZLO = 13, SCR_TCSCR = 14, SCR_TILES = 15,
-       SCR_COUNT = 16 };
+       SCR_WOUT = 16,   // readout weights of the batched ensemble solve (never an inter-layer buffer of collect_device)
+       SCR_QRA = 17, SCR_QRP = 18, SCR_QRW = 19,   // qr_solve.cu: sample chunk [A | B], partial products, W + T
+       SCR_COUNT = 24 };
 int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out);
 int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out);
 bool is_device_ptr(const void* p);
@@ -261,6 +263,15 @@ int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, d
 // the same for nsys systems stored back to back, one launch sequence (lambdas: host array or nullptr -> lambda0 for all)
 int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
                                    int64_t nsys, double* W_out, int* info_out);
+
+// qr_solve.cu — the QR-grade ridge path (Householder QR of [sqrt(lambda) I; Z'], streamed over sample chunks).
+// RQ = [R | Q'b], F x (F + d_out) Float64, the same footprint as [G | C].
+int32_t launch_qr_init(rcb_ctx* ctx, double* RQ, int64_t F, int64_t d_out);
+int32_t launch_qr_merge(rcb_ctx* ctx, double* RQ, const double* other, int64_t F, int64_t d_out);
+int32_t launch_qr_absorb_lambda(rcb_ctx* ctx, double* RQ, int64_t F, int64_t d_out, double lambda);
+int32_t launch_qr_accumulate(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt,
+                             int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq, double* RQ);
+int32_t launch_qr_solve(rcb_ctx* ctx, const double* RQ, int64_t F, int64_t d_out, int64_t nsys, double* W_out, int* info_out);
 
 // dense input projection P(N x S) = W_in(N x K) * Z(K x S), FP32 (deep layers)
 int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const float* Z, int64_t S,

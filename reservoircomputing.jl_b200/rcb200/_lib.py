@@ -14,7 +14,7 @@ RCB_OK, RCB_ERR_ARGUMENT, RCB_ERR_DIMENSION, RCB_ERR_CUDA, RCB_ERR_NUMERIC, RCB_
 RCB_F32, RCB_F64 = 0, 1
 ACT_IDENTITY, ACT_TANH, ACT_TANH_FAST, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 MOD_NLAT1, MOD_NLAT2, MOD_NLAT3, MOD_PAD, MOD_PARTIAL_SQUARE, MOD_EXTENDED_SQUARE = 1, 2, 3, 4, 5, 6
-GRAM_AUTO, GRAM_FP64, GRAM_TENSOR = 0, 1, 2
+GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR = 0, 1, 2, 3
 TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE = 0, 1, 2
 MAX_MODIFIERS, MAX_LAYERS = 8, 8
 
@@ -89,6 +89,8 @@ SIGNATURES = {
     "rcb_gc_pack": (_I32, [_P, _P, _I64, _I64, _P]),
     "rcb_gc_unpack": (_I32, [_P, _P, _I64, _I64, _P]),
     "rcb_ridge_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
+    "rcb_qr_merge": (_I32, [_P, _P, _P, _I64, _I64]),
+    "rcb_qr_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
     "rcb_train": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P, _P, _P, _P]),
     "rcb_train_members": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),
     "rcb_train_partial": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _P, _P]),

@@ -595,7 +595,7 @@ class _Handle:
         self.readout_key = None
 
     def set_readout(self, ps_ro, use_bias):
-        key = (id(ps_ro.weight), id(ps_ro.bias) if use_bias else None)
+        key = (_fingerprint(ps_ro.weight), _fingerprint(ps_ro.bias) if use_bias else None)
         if key == self.readout_key:
             return
         W = np.asfortranarray(ps_ro.weight, dtype=np.float64)
@@ -614,11 +614,38 @@ class _Handle:
             pass
 
 
+def _fingerprint(a):
+    """Identity + a cheap content fingerprint of a parameter array: the device handle is rebuilt when a weight is
+    replaced (``ps.reservoir.merge(bias=new)``) AND when one is edited in place (``W *= 0.9``) — the reference reads ``ps``
+    afresh on every call.  A strided sample of <= 4096 entries plus the end points is hashed: O(1) per call, and an edit
+    that scales or shifts the array always shows (a single-entry edit between the sample points may not — call
+    ``rcb200.invalidate(rc)`` after surgical edits)."""
+    import scipy.sparse as sp
+
+    if a is None:
+        return None
+    if sp.issparse(a):
+        return (id(a), a.shape, a.nnz) + _fingerprint(a.data)[1:] + _fingerprint(a.indices)[1:]
+    a = np.asarray(a)
+    flat = a.reshape(-1, order="K") if a.flags.c_contiguous or a.flags.f_contiguous else a.ravel()
+    step = max(1, flat.size // 4096)
+    sample = np.ascontiguousarray(flat[::step])
+    return (id(a), a.shape, a.dtype.str, hash(sample.tobytes()), float(flat[-1]) if flat.size else 0.0)
+
+
+def invalidate(rc):
+    """Drop the cached device handle of `rc` (weights are uploaded again on the next call)."""
+    rc._cache.clear()
+
+
 def _handle(rc, ps, dtype, dev: Optional[Device] = None) -> _Handle:
     dev = dev or default_device()
     cps = _cell_ps(rc, ps)
-    key = (np.dtype(dtype).str, dev.device) + tuple(id(getattr(p, k)) for p in cps
-                                                   for k in ("input_matrix", "reservoir_matrix", "orthogonal_matrix") if k in p)
+    key = (np.dtype(dtype).str, dev.device) + tuple(
+        _fingerprint(getattr(p, k)) for p in cps for k in ("input_matrix", "reservoir_matrix", "orthogonal_matrix", "bias") if k in p)
+    key += tuple((getattr(c, "cell_kind", L.CELL_ESN), getattr(c, "cell_params", None),
+                  _fingerprint(c.leak_coefficient) if isinstance(c.leak_coefficient, np.ndarray) else c.leak_coefficient,
+                  _act_id(c.activation), c.use_bias) for c in rc.cells)
     ent = rc._cache.get(key)
     if ent is None:
         ent = (_Handle(rc, ps, dtype, dev), cps)  # keep ps alive so ids are not recycled
@@ -695,12 +722,19 @@ class RidgeRegression:
 StandardRidge = RidgeRegression  # src/deprecated.jl:4
 
 
-class QRFactorization:  # solver facades (src/train.jl:85-98); both map onto the FP64 Cholesky kernel
-    pass
+class QRFactorization:
+    """Solver facades (src/train.jl:85-98).  ``solver=None`` is the library's RCB_GRAM_AUTO: Cholesky on the Gram matrix,
+    escalating by itself to the Householder QR of the augmented system (λ == 0, or a failed factorisation).  Passing
+    QRFactorization() / QRSolver() explicitly asks for that QR outright (RCB_FIT_QR, the reference's own algorithm);
+    NormalCholeskyFactorization() pins the normal equations on the exact FP64 Gram."""
 
 
 class QRSolver:
     pass
+
+
+class NormalCholeskyFactorization:
+    """LinearSolve.NormalCholeskyFactorization, one of the algorithms train.jl:187-189 names."""
 
 
 def _promote(objective, *arrays):
@@ -712,9 +746,14 @@ def _promote(objective, *arrays):
     return T
 
 
-def _check_solver(solver):
-    if solver is None or isinstance(solver, (QRFactorization, QRSolver)):
-        return
+def _check_solver(solver, gram_mode=L.GRAM_AUTO):
+    """Validates `solver` (train.jl:158-178) and returns the library's fit mode for it."""
+    if solver is None:
+        return gram_mode
+    if isinstance(solver, (QRFactorization, QRSolver)):
+        return L.FIT_QR
+    if isinstance(solver, NormalCholeskyFactorization):
+        return L.GRAM_FP64
     raise ArgumentError(f"solver {type(solver).__name__} is not supported. Pass QRFactorization(), QRSolver(), "
                         "or a documented LinearSolve.jl algorithm instead.")
 
@@ -722,7 +761,7 @@ def _check_solver(solver):
 def fit_readout(objective: RidgeRegression, states, targets, solver=None, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
     """__fit_readout(::RidgeRegression, states (F, S), targets (d_out, S)) -> W (d_out, F).
     src/train.jl:100-198."""
-    _check_solver(solver)
+    gram_mode = _check_solver(solver, gram_mode)
     Z, Y = np.asarray(states), np.asarray(targets)
     if Z.dtype not in (np.float32, np.float64):
         Z = Z.astype(np.float64)
@@ -759,6 +798,23 @@ def ridge_solve(GC, d_out: int, reg: float, device: Optional[Device] = None):
     return W
 
 
+def qr_merge(RQ, other, d_out: int, device: Optional[Device] = None):
+    """RQ <- QR of [RQ; other] (rcb_qr_merge): merges another rank's partial factor [R | Q'b] into this one, in place."""
+    dev = device or default_device()
+    F = RQ.shape[0] if isinstance(RQ, np.ndarray) else RQ.shape[1]
+    check(lib().rcb_qr_merge(dev.handle, ptr(RQ), ptr(other), F, d_out))
+    return RQ
+
+
+def qr_solve(RQ, d_out: int, reg: float, device: Optional[Device] = None):
+    """W (d_out, F) from a factor [R | Q'b] accumulated with gram_mode = FIT_QR (rcb_qr_solve)."""
+    dev = device or default_device()
+    F = RQ.shape[0] if isinstance(RQ, np.ndarray) else RQ.shape[1]
+    W = np.empty((d_out, F), dtype=np.float64, order="F")
+    check(lib().rcb_qr_solve(dev.handle, ptr(RQ), F, d_out, float(reg), ptr(W)))
+    return W
+
+
 def addreadout(rc, output_matrix, ps, st):
     """addreadout!(rc, W, ps, st): functional update of ps.readout.weight (reservoircomputer.jl:137-144; the chain
     variant replaces the weight of its readout layer, train.jl:253-305)."""
@@ -773,7 +829,7 @@ def train(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = N
     """train(rc, X, Y, ps, st; objective = RidgeRegression(0.0), solver, washout, return_states)
     -> (ps, st) or ((ps, st), states_wo).  src/train.jl:232-251."""
     objective = objective or RidgeRegression(0.0)
-    _check_solver(solver)
+    gram_mode = _check_solver(solver, gram_mode)
     if isinstance(rc, (_DelayModel, ReservoirChain)):  # train.jl:240-250 step by step: the features are assembled outside the fused rcb_train
         states, st2 = collectstates(rc, train_data, ps, st, device)
         tgt = np.asarray(target_data)

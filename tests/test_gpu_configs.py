@@ -1,0 +1,171 @@
+"""The BASELINE configurations parity-checked at their OWN sizes ("untested-config parity holes"):
+K2 tensor Gram at F = 8192, DeepESN 4 x 2048 (C4), the ensemble at N = 1024 (C5), the long single sequence at
+N = 4096 chunked vs sequential (C2).  C1 at the README's lambda = 0 lives in test_gpu_qr.py."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import esn_oracle as O
+from test_gpu_parity import R, fixed_h0, oracle_layers, state_err  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+STATE_RTOL = 1e-5
+WEIGHT_RTOL = 1e-4
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b))
+
+
+# ---- K2 at F = 8192: tensor-core fixed-point Gram against the exact FP64 kernel ----------------------------------------
+def test_k2_tensor_gram_f8192_matches_fp64(R):
+    import torch
+    from rcb200 import _lib as L
+
+    F, S, d_out, r = 8192, 65536, 3, 48
+    dev = R.default_device()
+    tdev = torch.device("cuda", dev.device)
+    g = torch.Generator(device=tdev).manual_seed(8192)
+    # reservoir-like features: bounded, strongly correlated (low-rank drive + a little independent noise); memory image of
+    # the column-major F x S matrix = a contiguous (S, F) tensor
+    Zt = torch.tanh(torch.randn(S, r, device=tdev, generator=g) @ torch.randn(r, F, device=tdev, generator=g) * 0.35
+                    + 0.05 * torch.randn(S, F, device=tdev, generator=g)).contiguous()
+    Yt = (Zt[:, :64] @ torch.randn(64, d_out, device=tdev, generator=g)).contiguous()  # (S, d_out) = col-major d_out x S
+    torch.cuda.synchronize()
+    lib = R.lib()
+    GC = {}
+    for name, mode in (("tensor", R.GRAM_TENSOR), ("fp64", R.GRAM_FP64)):
+        buf = torch.empty((F + d_out, F), dtype=torch.float64, device=tdev)
+        L.check(lib.rcb_gram_accumulate(dev.handle, L.ptr(Zt), L.RCB_F32, F, S, F, L.ptr(Yt), L.RCB_F32, d_out, d_out, mode, 1, L.ptr(buf)))
+        GC[name] = buf
+    Gt, Gf = GC["tensor"][:F].T, GC["fp64"][:F].T   # views: element (i, j) of the column-major G
+    scale = float(Gf.abs().max())
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for _ in range(40):  # 40 random 256 x 256 tiles of the lower triangle
+        j0 = int(rng.integers(0, F // 256)) * 256
+        i0 = int(rng.integers(j0 // 256, F // 256)) * 256
+        a, b = Gt[i0:i0 + 256, j0:j0 + 256], Gf[i0:i0 + 256, j0:j0 + 256]
+        if i0 == j0:
+            a, b = torch.tril(a), torch.tril(b)
+        worst = max(worst, float((a - b).abs().max()) / scale)
+    assert worst <= 1e-7, worst          # measured ~5e-9: the quantisation noise of 22-bit fixed point, unbiased
+    Ct, Cf = GC["tensor"][F:], GC["fp64"][F:]
+    assert float((Ct - Cf).abs().max()) / float(Cf.abs().max()) <= 1e-12   # the cross term is FP64 on both paths
+    # resulting W_out: full-size solve from both accumulators at a regularisation that makes the weights well-posed
+    lam = 1e-2 * float(torch.diagonal(Gf).mean())
+    W = {}
+    for name in GC:
+        w = np.empty((d_out, F), dtype=np.float64, order="F")
+        L.check(lib.rcb_ridge_solve(dev.handle, L.ptr(GC[name]), F, d_out, lam, L.ptr(w)))
+        W[name] = w
+    assert rel(W["tensor"], W["fp64"]) <= WEIGHT_RTOL
+    # ... and against the QR oracle on a sub-sampled problem (256 features, every sample): the sub-matrix of the tensor Gram
+    idx = np.sort(rng.choice(F, 256, replace=False))
+    Zs = Zt[:, torch.as_tensor(idx, device=tdev)].T.cpu().numpy()          # 256 x S
+    Ys = Yt.T.cpu().numpy()
+    lam_s = 1e-2 * float(np.mean(np.sum(Zs.astype(np.float64) ** 2, axis=1)))
+    Wq = O.train_ridge_qr(Zs, Ys, lam_s)
+    Gfull = Gt.cpu().numpy()
+    Gs = np.tril(Gfull[np.ix_(idx, idx)])
+    Gs = Gs + np.tril(Gs, -1).T                                            # lower triangle carries the data
+    Cs = Ct.T.cpu().numpy()[idx]
+    Wt = np.linalg.solve(Gs + lam_s * np.eye(256), Cs).T
+    assert rel(Wt, Wq) <= WEIGHT_RTOL
+
+
+# ---- C4: DeepESN 4 x 2048 with per-layer modifiers -----------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c4(R):
+    rng = np.random.default_rng(2048)
+    mods = (R.NLAT2, R.NLAT2, R.NLAT2, R.Pad(1.0))
+    esn = R.DeepESN(3, [2048] * 4, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / 2048, return_sparse=True),
+                    leak_coefficient=(1.0, 0.8, 0.6, 0.4), state_modifiers=mods)
+    ps, st = R.setup(rng, esn)
+    h0 = [rng.standard_normal(2048).astype(np.float32) for _ in range(4)]
+    st = fixed_h0(R, st, esn, h0)
+    return dict(esn=esn, ps=ps, st=st, h0=h0)
+
+
+@pytest.mark.parametrize("T", [320, 1600])   # 320: layer by layer (SGEMM projections); 1600: the layer pipeline over time chunks
+def test_c4_deep_4x2048_states_and_train(R, c4, T):
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(series[:, :T].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:T + 1].astype(np.float32))
+    esn, ps, st = c4["esn"], c4["ps"], c4["st"]
+    states, st2 = R.collectstates(esn, data, ps, st)
+    assert states.shape == (2049, T) and states.dtype == np.float32
+    if T >= 1536:
+        assert "layer pipeline" in R.default_device().last_kernel()
+    so, hs = O.collectstates(oracle_layers(R, esn, ps), data, c4["h0"])
+    assert state_err(states, so) <= STATE_RTOL
+    for l in range(4):
+        assert np.max(np.abs(st2.cells[l].carry[0] - hs[l])) <= STATE_RTOL * np.max(np.abs(hs[l]))
+    w = 100
+    lam = 1e-6
+    (ps2, _), sw = R.train(esn, data, target, ps, st, objective=R.RidgeRegression(lam), washout=w, return_states=True)
+    assert np.array_equal(sw, states[:, w:])          # train runs the same recurrence
+    Wref = O.train_ridge_qr(sw, target[:, w:], lam)
+    pred, pred_o = ps2.readout.weight @ sw.astype(np.float64), Wref @ sw.astype(np.float64)
+    assert rel(pred, pred_o) <= WEIGHT_RTOL
+    Wq = R.fit_readout(R.RidgeRegression(lam), sw, target[:, w:], solver=R.QRFactorization())
+    assert rel(Wq, Wref) <= WEIGHT_RTOL                # F = 2049 > S: the lambda rows make the system square-rank
+
+
+# ---- C5: ensemble members at N = 1024 -----------------------------------------------------------------------------------
+def test_c5_ensemble_n1024_members(R):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(1024)
+    N, T, w = 1024, 1300, 100
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=1.0, sparsity=6 / N), state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(series[:, :T].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:T + 1].astype(np.float32))
+    scales = np.array([0.5, 0.9, 1.4, 1.1], np.float32)      # radius grid end points (0.5 .. 1.4) and two in between
+    leaks = np.array([0.1, 1.0, 0.55, 0.7], np.float32)       # leak grid end points (0.1 .. 1.0)
+    lams = np.array([1e-8, 1e-4, 1e-1])                       # lambda grid end points and the middle
+    B = len(scales)
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    W, hT = R.train_ensemble(esn, data, target, ps, fixed_h0(R, st, esn, [h0]), w_scale=scales, leak=leaks, lambdas=lams, washout=w)
+    assert W.shape == (B, len(lams), 3, N)
+    W0 = sp.csr_matrix(ps.reservoir.reservoir_matrix)
+    for b in range(B):
+        layer = O.ESNCellParams(input_matrix=ps.reservoir.input_matrix, reservoir_matrix=(W0 * scales[b]).astype(np.float32).tocsr(),
+                                leak=float(leaks[b]), act=O.ACT_TANH, modifiers=((O.MOD_NLAT2, 0.0),))
+        so, hs = O.collectstates([layer], data, [h0[:, b]])
+        assert np.max(np.abs(hT[:, b] - hs[0])) <= 2e-5 * np.max(np.abs(hs[0]))
+        for l, lam in enumerate(lams):
+            Wo = O.train_ridge_qr(so[:, w:], target[:, w:], lam)
+            pred, pred_o = W[b, l] @ so[:, w:].astype(np.float64), Wo @ so[:, w:].astype(np.float64)
+            assert rel(pred, pred_o) <= WEIGHT_RTOL, (b, lam)
+            if lam >= 1e-1:
+                assert rel(W[b, l], Wo) <= 2e-3, (b, lam)
+
+
+# ---- C2: N = 4096, one sequence — time-chunked against sequential on a 20 k prefix ---------------------------------------
+def test_c2_n4096_chunked_vs_sequential(R):
+    rng = np.random.default_rng(4096)
+    N, T, w = 4096, 20000, 1000
+    esn = R.ESN(1, N, 1, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=True), leak_coefficient=1.0)
+    ps, st = R.setup(rng, esn)
+    mg = O.mackey_glass_series(T + 1)
+    data = np.asfortranarray(mg[:, :T].astype(np.float32))
+    target = np.asfortranarray(mg[:, 1:T + 1].astype(np.float32))
+    st0 = fixed_h0(R, st, esn, [np.zeros(N, np.float32)])
+    # sequential semantics vs the oracle on the first 400 steps (the oracle is a dense-gemv-free CSR loop: seconds)
+    states, _ = R.collectstates(esn, data, ps, st0)
+    so, _ = O.collectstates(oracle_layers(R, esn, ps), data[:, :400], [np.zeros(N, np.float32)])
+    assert state_err(states[:, :400], so) <= STATE_RTOL
+    Ws, Wc = {}, {}
+    for lam in (1e-6, 1.0):
+        ps_seq, _ = R.train(esn, data, target, ps, st0, objective=R.RidgeRegression(lam), washout=w)
+        ps_chk, _ = R.train_time_chunked(esn, data, target, ps, st0, objective=R.RidgeRegression(lam), washout=w, n_chunks=76, overlap=500)
+        Ws[lam], Wc[lam] = ps_seq.readout.weight, ps_chk.readout.weight
+        ys, yc = Ws[lam] @ states[:, w:].astype(np.float64), Wc[lam] @ states[:, w:].astype(np.float64)
+        assert rel(yc, ys) <= WEIGHT_RTOL, lam         # radius 0.9: 0.9^500 ~ 1e-23, the chunks re-synchronise exactly in FP32
+    # the weights themselves where the problem is well-posed against FP32 state rounding (cond * 1e-7 << 1e-4)
+    assert rel(Wc[1.0], Ws[1.0]) <= 1e-3
