@@ -118,7 +118,9 @@ RCB_API int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms);
 RCB_API int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len);
 #define RCB_TIMER_RECURRENCE 0 /* K1 / K4 */
 #define RCB_TIMER_GRAM 1       /* K2 */
-#define RCB_TIMER_SOLVE 2      /* K3 */
+#define RCB_TIMER_SOLVE 2      /* K3 (Cholesky / QR) */
+#define RCB_TIMER_EXCHANGE 3   /* pack + NCCL all-reduce (or all-gather + factor merges) + unpack of the multi-GPU train calls */
+#define RCB_TIMER_COUNT 4
 
 /* ---- model handle: replaces ESN / DeepESN + LuxCore.setup parameter hand-off ------------------
  * src/models/esn.jl:93-106, src/models/esn_deep.jl:102-147, src/reservoircomputer.jl:51-63 */
@@ -248,6 +250,44 @@ RCB_API int32_t rcb_ridge_solve(rcb_ctx* ctx, const double* GC, int64_t F, int64
  * A singular R (rank-deficient features at λ = 0) -> RCB_ERR_NUMERIC (train.jl:194-196). */
 RCB_API int32_t rcb_qr_merge(rcb_ctx* ctx, double* RQ, const double* other, int64_t F, int64_t d_out);
 RCB_API int32_t rcb_qr_solve(rcb_ctx* ctx, const double* RQ, int64_t F, int64_t d_out, double lambda, double* W_out);
+
+/* ---- multi-GPU: library-owned NCCL communicator + the sharded train calls -------------------------------
+ * The reference is single-process and single-device; these entry points are what its `train` becomes when the work shards
+ * (src/train.jl:232-251 per shard, then ONE exchange).  NCCL is loaded at run time (dlopen "libnccl.so.2").
+ *   one process per GPU : rank 0 calls rcb_comm_unique_id, the host ships the 128 bytes to every rank by its own means
+ *                         (MPI.jl / Distributed in Julia, torch.distributed in the Python mirror), every rank calls
+ *                         rcb_comm_create(ctx, id, rank, world) — collective.
+ *   one process, n GPUs : rcb_comm_create_local(ctxs, n, comms_out) (ncclCommInitAll); collectives of all n ranks are then
+ *                         issued by the one host thread: rcb_allreduce_gc_local.
+ * The collectives run on the context's stream, ordered behind the kernels that produced their input. */
+typedef struct rcb_comm rcb_comm;
+#define RCB_COMM_ID_BYTES 128
+RCB_API int32_t rcb_comm_unique_id(void* id_out /* RCB_COMM_ID_BYTES */);
+RCB_API int32_t rcb_comm_create(rcb_ctx* ctx, const void* id, int32_t rank, int32_t world, rcb_comm** out);
+RCB_API int32_t rcb_comm_create_local(rcb_ctx* const* ctxs, int32_t n, rcb_comm** comms_out /* n handles */);
+RCB_API int32_t rcb_comm_destroy(rcb_comm* comm);
+RCB_API int32_t rcb_comm_rank(const rcb_comm* comm, int32_t* rank, int32_t* world);
+/* [G | C] <- sum over the ranks, in place (host or device buffer); only the packed lower triangle + C travels. */
+RCB_API int32_t rcb_allreduce_gc(rcb_comm* comm, double* GC, int64_t F, int64_t d_out);
+RCB_API int32_t rcb_allreduce_gc_local(rcb_comm* const* comms, double* const* GCs /* device */, int32_t n, int64_t F, int64_t d_out);
+/* recv (world x bytes) <- every rank's send (bytes), e.g. the per-member readouts of an ensemble shard (C5). */
+RCB_API int32_t rcb_comm_allgather(rcb_comm* comm, const void* send, void* recv, int64_t bytes);
+/* train() with a pooled readout over sequences sharded across ranks (C3): this rank passes ITS B_local sequences; partial
+ * [G | C] per rank, one all-reduce, replicated FP64 solve — every rank returns the same W_out (and installs it).  comm NULL:
+ * one rank.  gram_mode as rcb_train (RCB_FIT_QR / the AUTO escalation exchange factors: all-gather + rcb_qr_merge). */
+RCB_API int32_t rcb_train_sharded(rcb_esn* esn, rcb_comm* comm, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
+                                  int64_t B_local, int64_t washout, double lambda, int32_t gram_mode, const void* h0,
+                                  double* W_out, void* hT_out);
+/* train() of ONE long sequence (C2), time-chunked after the washout: the samples [washout, T) are cut into n_chunks equal
+ * chunks (+ a ragged tail on the last rank); chunk c is computed from a window that starts `overlap` (<= washout) steps
+ * earlier from a zero state — those steps are its local washout (echo-state re-synchronisation: an APPROXIMATION of the
+ * sequential semantics, exact in the limit of a long overlap; rcb_train is the parity reference).  The chunks of a rank
+ * form a batch for the batched recurrence; ranks take contiguous slices of the chunk list; one all-reduce.  EVERY rank
+ * passes the whole series u (d_in x T) and targets (d_out x T).  hT_out (sumN): state at the end of this rank's last chunk. */
+RCB_API int32_t rcb_chunk_windows(int64_t T, int64_t washout, int64_t n_chunks, int64_t overlap, int64_t* Tc, int64_t* tail_len);
+RCB_API int32_t rcb_train_time_chunked(rcb_esn* esn, rcb_comm* comm, const void* u, const void* targets, int32_t targets_dtype,
+                                       int64_t T, int64_t washout, int64_t n_chunks, int64_t overlap, double lambda,
+                                       int32_t gram_mode, double* W_out, void* hT_out);
 
 /* ---- train: collect -> washout -> ridge -> addreadout! ------------------------------------------
  * Replaces train (src/train.jl:232-251) with __apply_washout (:36-47).  Pooled readout over the B

@@ -121,12 +121,12 @@ void timer_end(rcb_ctx* ctx, int which) {
   cudaEventRecord(p.end[p.used], ctx->stream);
   p.used++;
 }
-static void timers_reset(rcb_ctx* ctx) {
-  for (int i = 0; i < 3; ++i) pools(ctx)[i].used = 0;
+void timers_reset(rcb_ctx* ctx) {
+  for (int i = 0; i < RCB_TIMER_COUNT; ++i) pools(ctx)[i].used = 0;
 }
 
 // resolve a host-or-device input into a device pointer (copying host data into a scratch slot)
-static int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, const void** dev) {
+int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, const void** dev) {
   if (!p) { *dev = nullptr; return RCB_OK; }
   if (is_device_ptr(p)) { *dev = p; return RCB_OK; }
   void* d = nullptr;
@@ -541,7 +541,7 @@ int32_t rcb_ctx_create(int32_t device, void* cuda_stream, rcb_ctx** out) {
     RCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
   }
-  ctx->timer_pools = new TimerPool[3];
+  ctx->timer_pools = new TimerPool[RCB_TIMER_COUNT];
   *out = ctx;
   return RCB_OK;
 }
@@ -551,7 +551,7 @@ int32_t rcb_ctx_destroy(rcb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   TimerPool* p = pools(ctx);
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < RCB_TIMER_COUNT; ++i)
     for (size_t k = 0; k < p[i].beg.size(); ++k) { cudaEventDestroy(p[i].beg[k]); cudaEventDestroy(p[i].end[k]); }
   delete[] p;
   for (int i = 0; i < SCR_COUNT; ++i) cudaFree(ctx->scratch[i]);
@@ -590,7 +590,7 @@ int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len) {
 
 int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms) {
   if (!ctx || !ms) return fail(RCB_ERR_ARGUMENT, "NULL argument");
-  if (which < 0 || which > 2) return fail(RCB_ERR_ARGUMENT, "unknown timer %d", which);
+  if (which < 0 || which >= RCB_TIMER_COUNT) return fail(RCB_ERR_ARGUMENT, "unknown timer %d", which);
   RCB_CUDA(cudaSetDevice(ctx->device));
   TimerPool& p = pools(ctx)[which];
   float total = 0.f;
@@ -928,13 +928,13 @@ static int32_t check_ridge_args(int64_t S_states, int64_t S_targets, double lamb
   return RCB_OK;
 }
 
-static int32_t check_fit_mode(int32_t mode) {
+int32_t rcbi_check_fit_mode(int32_t mode) {
   if (mode < RCB_GRAM_AUTO || mode > RCB_FIT_QR) return fail(RCB_ERR_ARGUMENT, "unknown gram_mode / fit mode %d", mode);
   return RCB_OK;
 }
 // RCB_GRAM_AUTO takes the QR path for lambda == 0 — the reference's default objective (train.jl:234), where the normal
 // equations square the condition number of a least-squares problem nothing regularises.
-static bool want_qr(int32_t mode, double lambda) { return mode == RCB_FIT_QR || (mode == RCB_GRAM_AUTO && lambda == 0.0); }
+bool rcbi_want_qr(int32_t mode, double lambda) { return mode == RCB_FIT_QR || (mode == RCB_GRAM_AUTO && lambda == 0.0); }
 
 // one chunk of samples into the accumulator: [G | C] += (Gram path) or [R | Qb] <- QR([R | Qb; Z' | Y']) (QR path)
 static int32_t accumulate_device(rcb_ctx* ctx, bool qr, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y,
@@ -947,7 +947,7 @@ static int32_t accumulate_device(rcb_ctx* ctx, bool qr, const void* Z, int32_t z
   return gram_device(ctx, Z, zdt, F, ldz, Y, ydt, d_out, ldy, T, washout, nseq, gram_mode == RCB_FIT_QR ? RCB_GRAM_FP64 : gram_mode, GC);
 }
 // accumulator (destroyed) -> W (d_out x F, device)
-static int32_t solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t d_out, double lambda, double* w_dev) {
+int32_t rcbi_solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t d_out, double lambda, double* w_dev) {
   if (qr) {
     RCB_TRY(launch_qr_absorb_lambda(ctx, GC, F, d_out, lambda));
     return launch_qr_solve(ctx, GC, F, d_out, 1, w_dev, nullptr);
@@ -962,7 +962,7 @@ int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dty
   if (F < 1 || d_out < 1) return fail(RCB_ERR_ARGUMENT, "F and d_out must be ≥ 1");
   if (S < 1) return fail(RCB_ERR_ARGUMENT, "ridge regression requires at least one training sample");
   if (ld_states < F || ld_targets < d_out) return fail(RCB_ERR_DIMENSION, "leading dimension smaller than the row count");
-  RCB_TRY(check_fit_mode(gram_mode));
+  RCB_TRY(rcbi_check_fit_mode(gram_mode));
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
   const size_t zsz = states_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
@@ -1065,7 +1065,7 @@ int32_t rcb_qr_solve(rcb_ctx* ctx, const double* RQ, int64_t F, int64_t d_out, d
   void* w_dev = nullptr;
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
   RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
-  RCB_TRY(solve_device(ctx, true, (double*)work, F, d_out, lambda, (double*)w_dev));
+  RCB_TRY(rcbi_solve_device(ctx, true, (double*)work, F, d_out, lambda, (double*)w_dev));
   RCB_TRY(from_device(ctx, W_out, w_dev, w_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
@@ -1077,7 +1077,7 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
   if (!ctx || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   RCB_TRY(check_ridge_args(S_states, S_targets, lambda));
   if (!states || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
-  RCB_TRY(check_fit_mode(gram_mode));
+  RCB_TRY(rcbi_check_fit_mode(gram_mode));
   RCB_CUDA(cudaSetDevice(ctx->device));
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
@@ -1088,7 +1088,7 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
   // then the Householder QR of the augmented system itself (the reference's algorithm; error ~ cond instead of cond^2).
   // lambda == 0 goes to QR directly.
   int32_t modes[3], nm = 0;
-  if (want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
+  if (rcbi_want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
   else {
     modes[nm++] = gram_mode;
     if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
@@ -1098,7 +1098,7 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
     if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;  // the first attempt already was exact
     RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
                                 modes[i], 1, (double*)gc));
-    st = solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    st = rcbi_solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
     if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);
@@ -1109,9 +1109,9 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
 
 // shared body of rcb_train / rcb_train_partial: collect in (sequence, time) chunks sized to a
 // device-memory budget, accumulating [G | C] chunk by chunk; states are never kept unless asked for.
-static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
-                                int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* gc_dev,
-                                void* states_out, void* hT_out) {
+int32_t rcbi_train_accumulate(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T,
+                              int64_t B, int64_t washout, int32_t gram_mode, const void* h0, double* gc_dev,
+                              void* states_out, void* hT_out, bool zero_first) {
   const bool qr = gram_mode == RCB_FIT_QR;
   rcb_ctx* ctx = esn->ctx;
   const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
@@ -1125,7 +1125,7 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
   RCB_TRY(ctx_scratch(ctx, SCR_H, (size_t)sumN * B * esz, &h_dev));
   if (h0) RCB_TRY(to_device(ctx, h_dev, h0, (size_t)sumN * B * esz));
   else RCB_CUDA(cudaMemsetAsync(h_dev, 0, (size_t)sumN * B * esz, ctx->stream));
-  RCB_CUDA(cudaMemsetAsync(gc_dev, 0, (size_t)F * (F + d_out) * sizeof(double), ctx->stream));
+  if (zero_first) RCB_CUDA(cudaMemsetAsync(gc_dev, 0, (size_t)F * (F + d_out) * sizeof(double), ctx->stream));
   // chunking: budget for the state buffer (deep nets also hold inter-layer buffers of similar size)
   size_t free_b = 0, total_b = 0;
   RCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1198,7 +1198,7 @@ static int32_t train_accumulate(rcb_esn* esn, const void* u, const void* targets
   return RCB_OK;
 }
 
-static int32_t check_train_args(rcb_esn* esn, const void* u, const void* targets, int64_t T, int64_t B, int64_t washout) {
+int32_t rcbi_check_train_args(rcb_esn* esn, const void* u, const void* targets, int64_t T, int64_t B, int64_t washout) {
   RCB_TRY(check_ready(esn));
   if (!u || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   if (T < 1) return fail(RCB_ERR_ARGUMENT, "collectstates data must have at least one column, got %lld.", (long long)T);
@@ -1212,9 +1212,9 @@ static int32_t check_train_args(rcb_esn* esn, const void* u, const void* targets
 
 int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
                           int64_t washout, int32_t gram_mode, const void* h0, double* GC, void* hT_out) {
-  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  RCB_TRY(rcbi_check_train_args(esn, u, targets, T, B, washout));
   if (!GC) return fail(RCB_ERR_ARGUMENT, "GC is NULL");
-  RCB_TRY(check_fit_mode(gram_mode));
+  RCB_TRY(rcbi_check_fit_mode(gram_mode));
   rcb_ctx* ctx = esn->ctx;
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
@@ -1225,7 +1225,7 @@ int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int3
     RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_bytes, &p));
     gc_dev = (double*)p;
   }
-  RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, gram_mode, h0, gc_dev, nullptr, hT_out));
+  RCB_TRY(rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B, washout, gram_mode, h0, gc_dev, nullptr, hT_out, true));
   if (gc_dev != GC) RCB_TRY(from_device(ctx, GC, gc_dev, gc_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;
@@ -1234,14 +1234,14 @@ int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targets, int3
 int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
                   int64_t washout, double lambda, int32_t gram_mode, const void* h0, double* W_out, void* states_out,
                   void* hT_out) {
-  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  RCB_TRY(rcbi_check_train_args(esn, u, targets, T, B, washout));
   if (!(lambda >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambda);
   if (!W_out) return fail(RCB_ERR_ARGUMENT, "W_out is NULL");
   rcb_ctx* ctx = esn->ctx;
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
   const int64_t F = esn->feat, d_out = esn->desc.out_dims;
-  RCB_TRY(check_fit_mode(gram_mode));
+  RCB_TRY(rcbi_check_fit_mode(gram_mode));
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
   void* w_dev = nullptr;
@@ -1249,7 +1249,7 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
   RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_bytes, &w_dev));
   // same escalation as rcb_fit_readout; the states are not kept, so a retry runs the recurrence again (identical carry)
   int32_t modes[3], nm = 0;
-  if (want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
+  if (rcbi_want_qr(gram_mode, lambda)) modes[nm++] = RCB_FIT_QR;
   else {
     modes[nm++] = gram_mode;
     if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
@@ -1257,8 +1257,8 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
   int32_t st = RCB_OK;
   for (int32_t i = 0; i < nm; ++i) {
     if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;
-    RCB_TRY(train_accumulate(esn, u, targets, targets_dtype, T, B, washout, modes[i], h0, (double*)gc, states_out, hT_out));
-    st = solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    RCB_TRY(rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B, washout, modes[i], h0, (double*)gc, states_out, hT_out, true));
+    st = rcbi_solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
     if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);
@@ -1273,9 +1273,9 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
 int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
                           int64_t washout, int32_t n_lambda, const double* lambdas, int32_t gram_mode, const void* h0,
                           double* W_out, void* hT_out) {
-  RCB_TRY(check_train_args(esn, u, targets, T, B, washout));
+  RCB_TRY(rcbi_check_train_args(esn, u, targets, T, B, washout));
   if (n_lambda < 1 || !lambdas || !W_out) return fail(RCB_ERR_ARGUMENT, "NULL argument or n_lambda < 1");
-  RCB_TRY(check_fit_mode(gram_mode));
+  RCB_TRY(rcbi_check_fit_mode(gram_mode));
   for (int32_t i = 0; i < n_lambda; ++i)
     if (!(lambdas[i] >= 0.0)) return fail(RCB_ERR_ARGUMENT, "RidgeRegression regularization must be ≥ 0, got reg=%g", lambdas[i]);
   rcb_ctx* ctx = esn->ctx;

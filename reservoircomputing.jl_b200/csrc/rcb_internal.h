@@ -154,14 +154,14 @@ struct rcb_ctx {
   int64_t launches = 0;
   char last_kernel[96] = "";
   int last_gram_tensor = 0;   // 1 when the most recent Gram ran on the tcgen05 path  // variant name of the most recent recurrence launch
-  void* timer_pools = nullptr;  // rcb::TimerPool[3]
+  void* timer_pools = nullptr;  // rcb::TimerPool[RCB_TIMER_COUNT]
   bool timers_muted = false;    // set while a pipelined region times itself as a whole
   cudaStream_t aux_streams[RCB_MAX_LAYERS] = {};  // one per DeepESN layer (layer pipeline over time chunks), created on demand
   // pinned staging + scratch, grown on demand
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
-  void* scratch[24] = {};
-  size_t scratch_bytes[24] = {};
+  void* scratch[32] = {};
+  size_t scratch_bytes[32] = {};
 };
 
 struct rcb_esn {
@@ -187,7 +187,9 @@ enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5,
        SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_ZHI = 12, SCR_ZLO = 13, SCR_TCSCR = 14, SCR_TILES = 15,
        SCR_WOUT = 16,   // readout weights of the batched ensemble solve (never an inter-layer buffer of collect_device)
        SCR_QRA = 17, SCR_QRP = 18, SCR_QRW = 19,   // qr_solve.cu: sample chunk [A | B], partial products, W + T
-       SCR_COUNT = 24 };
+       SCR_PACK = 20,                               // comm.cu: packed [G | C] / gathered factors
+       SCR_CHUNK_U = 21, SCR_CHUNK_Y = 22, SCR_CHUNK_UW = 23, SCR_CHUNK_YW = 24,   // comm.cu: staged series + window batches
+       SCR_COUNT = 32 };
 int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out);
 int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out);
 bool is_device_ptr(const void* p);
@@ -195,6 +197,9 @@ bool is_device_ptr(const void* p);
 int32_t to_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int32_t from_device(rcb_ctx* ctx, void* dst, const void* src, size_t bytes);
 void timer_begin(rcb_ctx* ctx, int which);
+void timers_reset(rcb_ctx* ctx);
+// resolve a host-or-device input into a device pointer (host data is copied into scratch slot `slot`)
+int32_t stage_in(rcb_ctx* ctx, int slot, const void* p, size_t bytes, const void** dev);
 void timer_end(rcb_ctx* ctx, int which);
 
 // ---- kernel launchers (device pointers only) -------------------------------------------------
@@ -280,3 +285,16 @@ int32_t launch_input_projection(rcb_ctx* ctx, const float* Win, int64_t N, int64
 int32_t launch_input_projection_f64(rcb_ctx* ctx, const float* Win, int64_t N, int64_t K, const double* Z, int64_t S, double* P);
 
 }  // namespace rcb
+
+// ---- host orchestration shared by api.cu and comm.cu (internal linkage to the library: hidden visibility) -------------
+extern "C" {
+int32_t rcbi_check_fit_mode(int32_t mode);
+bool rcbi_want_qr(int32_t mode, double lambda);
+int32_t rcbi_check_train_args(rcb_esn* esn, const void* u, const void* targets, int64_t T, int64_t B, int64_t washout);
+// collect in chunks and fold them into the accumulator gc_dev ([G | C], or [R | Qb] when gram_mode == RCB_FIT_QR)
+int32_t rcbi_train_accumulate(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
+                              int64_t washout, int32_t gram_mode, const void* h0, double* gc_dev, void* states_out, void* hT_out,
+                              bool zero_first);
+// accumulator (destroyed) -> W (d_out x F, device)
+int32_t rcbi_solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t d_out, double lambda, double* w_dev);
+}

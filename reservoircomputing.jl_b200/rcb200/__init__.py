@@ -3,8 +3,8 @@
 There is no CPU fallback: every call ends in a CUDA kernel of the in-tree library, and importing
 this package without the built library raises on first use."""
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, NumericError, UnsupportedError, LIB_PATH,
-                   GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR, TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, lib)
-from .api import (NT, Device, ReservoirChain, StatefulLayer, Extend, Collect, DelayLayer, InputDelayESN, StateDelayESN, DelayESN, extend_features, readout_apply,
+                   GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR, TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, TIMER_EXCHANGE, lib)
+from .api import (NT, Device, Comm, comm_for, ReservoirChain, StatefulLayer, Extend, Collect, DelayLayer, InputDelayESN, StateDelayESN, DelayESN, extend_features, readout_apply,
                   correlation_matrix, ridge_map, DeepESN, ESN, ESNCell, ES2N, ES2NCell, ResESN, ResESNCell, EuSN, EuSNCell, orthogonal, ExtendedSquare, LinearReadout, NLAT1, NLAT2, NLAT3, Pad,
                   PartialSquare, QRFactorization, QRSolver, NormalCholeskyFactorization, RidgeRegression, StandardRidge, addreadout,
                   apply_modifiers, collectstates, csr_from_matrix, eusn_operator_csr, spectral_radius, scale_radius, hessenberg_eigvals, default_device, device_count, export_csr, fit_readout, gram,

@@ -15,7 +15,8 @@ RCB_F32, RCB_F64 = 0, 1
 ACT_IDENTITY, ACT_TANH, ACT_TANH_FAST, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 MOD_NLAT1, MOD_NLAT2, MOD_NLAT3, MOD_PAD, MOD_PARTIAL_SQUARE, MOD_EXTENDED_SQUARE = 1, 2, 3, 4, 5, 6
 GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR = 0, 1, 2, 3
-TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE = 0, 1, 2
+TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, TIMER_EXCHANGE = 0, 1, 2, 3
+COMM_ID_BYTES = 128
 MAX_MODIFIERS, MAX_LAYERS = 8, 8
 
 
@@ -91,6 +92,17 @@ SIGNATURES = {
     "rcb_ridge_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
     "rcb_qr_merge": (_I32, [_P, _P, _P, _I64, _I64]),
     "rcb_qr_solve": (_I32, [_P, _P, _I64, _I64, _F64, _P]),
+    "rcb_comm_unique_id": (_I32, [_P]),
+    "rcb_comm_create": (_I32, [_P, _P, _I32, _I32, C.POINTER(_P)]),
+    "rcb_comm_create_local": (_I32, [_P, _I32, _P]),
+    "rcb_comm_destroy": (_I32, [_P]),
+    "rcb_comm_rank": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
+    "rcb_allreduce_gc": (_I32, [_P, _P, _I64, _I64]),
+    "rcb_allreduce_gc_local": (_I32, [_P, _P, _I32, _I64, _I64]),
+    "rcb_comm_allgather": (_I32, [_P, _P, _P, _I64]),
+    "rcb_train_sharded": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P, _P, _P]),
+    "rcb_chunk_windows": (_I32, [_I64, _I64, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "rcb_train_time_chunked": (_I32, [_P, _P, _P, _P, _I32, _I64, _I64, _I64, _I64, _F64, _I32, _P, _P]),
     "rcb_train": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _F64, _I32, _P, _P, _P, _P]),
     "rcb_train_members": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),
     "rcb_train_partial": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _P, _P]),

@@ -236,6 +236,63 @@ def device_count() -> int:
     return n.value
 
 
+class Comm:
+    """Library-owned NCCL communicator of one rank (rcb_comm).  The 128-byte NCCL id travels over whatever process group the
+    host already has (torch.distributed here: plumbing only; MPI.jl / Distributed for a Julia host) — every collective on the
+    data path is then issued by the library on the context's stream."""
+
+    def __init__(self, dev: Device, ident, rank: int, world: int):
+        h = C.c_void_p()
+        check(lib().rcb_comm_create(dev.handle, ptr(ident), int(rank), int(world), C.byref(h)))
+        self.handle, self.dev, self.rank, self.world = h, dev, int(rank), int(world)
+
+    def allreduce_gc(self, GC, d_out: int):
+        F = GC.shape[0] if isinstance(GC, np.ndarray) else GC.shape[1]
+        check(lib().rcb_allreduce_gc(self.handle, ptr(GC), F, d_out))
+        return GC
+
+    def allgather(self, send: np.ndarray):
+        send = np.ascontiguousarray(send)
+        recv = np.empty((self.world,) + send.shape, dtype=send.dtype)
+        check(lib().rcb_comm_allgather(self.handle, ptr(send), ptr(recv), send.nbytes))
+        return recv
+
+    def close(self):
+        if self.handle:
+            lib().rcb_comm_destroy(self.handle)
+            self.handle = None
+
+
+_comms = {}
+
+
+def comm_for(dev: Optional[Device] = None, group=None) -> Optional[Comm]:
+    """The rcb_comm that mirrors a torch.distributed process group on this rank's device (None for a single rank).
+    Collective: every rank of the group must call it the first time."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    dev = dev or default_device()
+    key = (dev.device, id(group) if group is not None else None)
+    if key not in _comms:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = np.zeros(L.COMM_ID_BYTES, dtype=np.uint8)
+        if rank == 0:
+            check(lib().rcb_comm_unique_id(ptr(ident)))
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        t = torch.from_numpy(ident)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(dev.device)
+            dist.broadcast(t, src=src, group=group)
+            ident = t.cpu().numpy()
+        else:
+            dist.broadcast(t, src=src, group=group)
+        _comms[key] = Comm(dev, ident, rank, world)
+    return _comms[key]
+
+
 # ---- initializers (host-side producers, SURVEY.md §8a row a25) ------------------------------------
 class _Init:
     """Curried initializer: ``rand_sparse(radius=1.2, sparsity=6/300)`` returns a callable
@@ -627,7 +684,7 @@ def _fingerprint(a):
     if sp.issparse(a):
         return (id(a), a.shape, a.nnz) + _fingerprint(a.data)[1:] + _fingerprint(a.indices)[1:]
     a = np.asarray(a)
-    flat = a.reshape(-1, order="K") if a.flags.c_contiguous or a.flags.f_contiguous else a.ravel()
+    flat = a.ravel(order="K")  # a view for contiguous arrays
     step = max(1, flat.size // 4096)
     sample = np.ascontiguousarray(flat[::step])
     return (id(a), a.shape, a.dtype.str, hash(sample.tobytes()), float(flat[-1]) if flat.size else 0.0)
@@ -939,7 +996,7 @@ def _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode):
     return GC, hT, cell_sts
 
 
-def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, washout: int = 0, group=None,
+def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, solver=None, washout: int = 0, group=None,
                   device: Optional[Device] = None, gram_mode=L.GRAM_AUTO, _partial=None, _solve=None):
     """train() for a pooled readout over sequences sharded across ranks: every rank passes ITS shard (d_in, T, B_r),
     accumulates its partial [G | C] on its GPU (rcb_train_partial), the partials are summed by one all-reduce over the
@@ -963,30 +1020,17 @@ def train_sharded(rc, train_data, target_data, ps, st, *, objective: RidgeRegres
         raise DimensionMismatch(f"states has {T - washout} samples, targets has {y3.shape[1] - washout}")
     d_out = y3.shape[0]
     if _partial is None and _solve is None:
-        # the CUDA path: [G | C] never leaves the GPU between the partial Gram, the exchange and the solve
+        # the CUDA path: partial accumulation, the NCCL exchange and the replicated solve are ONE library call
+        # (rcb_train_sharded); torch.distributed only carried the communicator id (comm_for)
         dev = device or default_device()
-        tdev = torch.device("cuda", dev.device)
         h = _handle(rc, ps, d3.dtype, dev)
         F = h.F
         h0, cell_sts = _initial_carry(rc, st, d3.dtype, B)
-        GCd = torch.empty((F + d_out, F), dtype=torch.float64, device=tdev)   # memory image of the column-major F x (F + d_out)
         hT = np.empty((h.sumN, B), dtype=d3.dtype, order="F")
-        torch.cuda.current_stream(tdev).synchronize()
-        check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B, int(washout), gram_mode, ptr(h0),
-                                      ptr(GCd), ptr(hT)))
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            packed = torch.empty(int(lib().rcb_gc_packed_len(F, d_out)), dtype=torch.float64, device=tdev)
-            check(lib().rcb_gc_pack(dev.handle, ptr(GCd), F, d_out, ptr(packed)))
-            if dist.get_backend(group) == "nccl":
-                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-            else:
-                pc = packed.cpu()
-                dist.all_reduce(pc, op=dist.ReduceOp.SUM, group=group)
-                packed.copy_(pc)
-            torch.cuda.current_stream(tdev).synchronize()
-            check(lib().rcb_gc_unpack(dev.handle, ptr(packed), F, d_out, ptr(GCd)))
+        comm = comm_for(dev, group)
         Wd = np.empty((d_out, F), dtype=np.float64, order="F")
-        check(lib().rcb_ridge_solve(dev.handle, ptr(GCd), F, d_out, float(objective.reg), ptr(Wd)))
+        check(lib().rcb_train_sharded(h.handle, comm.handle if comm else None, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), T, B,
+                                      int(washout), float(objective.reg), _check_solver(solver, gram_mode), ptr(h0), ptr(Wd), ptr(hT)))
         W = Wd.astype(_promote(objective, d3, y3))
         return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, vec))
     partial = _partial or (lambda: _partial_gram_cuda(rc, ps, st, d3, y3, washout, device, gram_mode))
@@ -1015,17 +1059,16 @@ def chunk_windows(T: int, washout: int, n_chunks: int, overlap: int):
     return Tc, wins, tail
 
 
-def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, washout: int, n_chunks: int,
-                       overlap: int, group=None, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
+def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeRegression = None, solver=None, washout: int,
+                       n_chunks: int, overlap: int, group=None, device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
     """train() for one long sequence (d_in, T), time-chunked after the washout: the chunks
     become a BATCH for the batched recurrence kernel, ranks take contiguous slices of the chunk list, and the partial
-    [G | C] are summed by one all-reduce before the replicated FP64 solve.  This is an approximation of the sequential
-    semantics (exact only in the limit of a long overlap); the sequential single-GPU `train` stays the parity reference.
-    The carry stored in the returned st is the state at the end of the last chunk."""
-    import torch
-    import torch.distributed as dist
-
+    [G | C] are summed by one all-reduce before the replicated FP64 solve — all inside rcb_train_time_chunked.  This is an
+    approximation of the sequential semantics (exact only in the limit of a long overlap); the sequential single-GPU
+    `train` stays the parity reference.  The carry stored in the returned st is the state at the end of this rank's last
+    chunk."""
     objective = objective or RidgeRegression(0.0)
+    mode = _check_solver(solver, gram_mode)
     X, Y = np.asarray(train_data), np.asarray(target_data)
     if X.ndim != 2 or Y.ndim != 2:
         raise DimensionMismatch("train_time_chunked takes one sequence: data (d_in, T), targets (d_out, T)")
@@ -1036,52 +1079,19 @@ def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeR
         raise ArgumentError(f"washout={washout} is ≥ number of time steps={T}")
     if Y.dtype not in (np.float32, np.float64):
         Y = Y.astype(np.float64)
-    Tc, wins, tail = chunk_windows(T, washout, n_chunks, overlap)
-    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    lo, hi = shard_range(n_chunks, rank, world)
+    chunk_windows(T, washout, n_chunks, overlap)  # argument checks (the library repeats them)
+    X, Y = np.asfortranarray(X), np.asfortranarray(Y)
     dev = device or default_device()
     h = _handle(rc, ps, X.dtype, dev)
     F, d_out = h.F, Y.shape[0]
-    # [G | C] stays on the GPU from the first partial Gram to the solve (F = 4096: 134 MB that would otherwise cross PCIe
-    # three times); torch only provides the device buffers and the process group
-    tdev = torch.device("cuda", dev.device)
-    GC = torch.zeros((F + d_out, F), dtype=torch.float64, device=tdev)   # memory image of the column-major F x (F + d_out)
-    part = torch.empty_like(GC)
-    hT = None
-
-    def run(windows, length):
-        nonlocal hT
-        B = len(windows)
-        d3 = np.asfortranarray(np.stack([X[:, s:s + length] for s, _, _ in windows], axis=2))
-        y3 = np.asfortranarray(np.stack([Y[:, s:s + length] for s, _, _ in windows], axis=2))
-        h0 = np.zeros((h.sumN, B), dtype=X.dtype, order="F")
-        hh = np.empty((h.sumN, B), dtype=X.dtype, order="F")
-        torch.cuda.current_stream(tdev).synchronize()
-        check(lib().rcb_train_partial(h.handle, ptr(d3), ptr(y3), L.dtype_id(y3.dtype), length, B, int(overlap), gram_mode, ptr(h0),
-                                      ptr(part), ptr(hh)))   # returns after its stream has drained
-        GC.add_(part)
-        hT = hh[:, -1:]
-
-    if hi > lo:
-        run(wins[lo:hi], Tc + overlap)
-    if tail is not None and rank == world - 1:
-        run([tail], tail[2] - tail[0])
-    if world > 1:  # only the lower triangle of G (+ C) travels: pack -> all-reduce -> unpack (rcb_gc_pack / rcb_gc_unpack)
-        packed = torch.empty(int(lib().rcb_gc_packed_len(F, d_out)), dtype=torch.float64, device=tdev)
-        torch.cuda.current_stream(tdev).synchronize()
-        check(lib().rcb_gc_pack(dev.handle, ptr(GC), F, d_out, ptr(packed)))
-        dist.all_reduce(packed, group=group)
-        torch.cuda.current_stream(tdev).synchronize()
-        check(lib().rcb_gc_unpack(dev.handle, ptr(packed), F, d_out, ptr(GC)))
-    torch.cuda.current_stream(tdev).synchronize()
+    comm = comm_for(dev, group)
     Wd = np.empty((d_out, F), dtype=np.float64, order="F")
-    check(lib().rcb_ridge_solve(dev.handle, ptr(GC), F, d_out, float(objective.reg), ptr(Wd)))
+    hT = np.zeros((h.sumN, 1), dtype=X.dtype, order="F")
+    check(lib().rcb_train_time_chunked(h.handle, comm.handle if comm else None, ptr(X), ptr(Y), L.dtype_id(Y.dtype), T, int(washout),
+                                       int(n_chunks), int(overlap), float(objective.reg), mode, ptr(Wd), ptr(hT)))
     W = Wd.astype(_promote(objective, X, Y))
     cell_sts = list(_cell_st(rc, st))
-    if hT is None:
-        hT = np.zeros((h.sumN, 1), dtype=X.dtype)
-    return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, np.asfortranarray(hT), True))
+    return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, True))
 
 
 def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambdas, washout: int = 0,
