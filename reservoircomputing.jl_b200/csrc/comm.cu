@@ -85,6 +85,25 @@ int32_t nccl_api(NcclApi** out) {
       return ::rcb::fail(RCB_ERR_CUDA, "NCCL error %s at %s:%d (%s)", (api)->GetErrorString(_r), __FILE__, __LINE__, #expr); \
   } while (0)
 
+// dst[b][i] = src[b * stride + i], i < len, in 4-byte words: the (overlapping) chunk windows of one series become a batch
+__global__ void window_gather_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long len, long long stride,
+                                     long long nb) {
+  const long long total = len * nb;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const long long b = k / len, i = k - b * len;
+    dst[k] = src[b * stride + i];
+  }
+}
+int32_t launch_window_gather(rcb_ctx* ctx, const void* src, void* dst, size_t len_bytes, size_t stride_bytes, int64_t nb) {
+  const long long len = (long long)(len_bytes / 4), stride = (long long)(stride_bytes / 4);
+  const long long total = len * nb;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 4LL * ctx->sm_count);
+  window_gather_kernel<<<grid ? grid : 1, 256, 0, ctx->stream>>>((const uint32_t*)src, (uint32_t*)dst, len, stride, nb);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
 // sum of the packed lower triangle of [G | C] over the ranks, in place, on the context's stream
 int32_t allreduce_gc_device(rcb_comm* c, double* gc_dev, int64_t F, int64_t d_out) {
   if (c->world == 1) return RCB_OK;
@@ -360,12 +379,10 @@ int32_t rcb_train_time_chunked(rcb_esn* esn, rcb_comm* comm, const void* u, cons
   int32_t st = sharded_fit(esn, comm, lambda, gram_mode, W_out, [&](int32_t mode, double* gc) -> int32_t {
     RCB_CUDA(cudaMemsetAsync(gc, 0, (size_t)esn->feat * (esn->feat + d_out) * sizeof(double), ctx->stream));
     if (nb > 0) {
-      // window c starts `overlap` steps before its own samples; consecutive windows start Tc steps apart: ONE strided copy
+      // window c starts `overlap` steps before its own samples; consecutive windows start Tc steps apart (and overlap): one gather
       const int64_t start = washout + lo * Tc - overlap;
-      RCB_CUDA(cudaMemcpy2DAsync(uw, (size_t)L * d_in * esz, (const char*)u_dev + (size_t)start * d_in * esz, (size_t)Tc * d_in * esz,
-                                 (size_t)L * d_in * esz, (size_t)nb, cudaMemcpyDeviceToDevice, ctx->stream));
-      RCB_CUDA(cudaMemcpy2DAsync(yw, (size_t)L * d_out * ysz, (const char*)y_dev + (size_t)start * d_out * ysz, (size_t)Tc * d_out * ysz,
-                                 (size_t)L * d_out * ysz, (size_t)nb, cudaMemcpyDeviceToDevice, ctx->stream));
+      RCB_TRY(launch_window_gather(ctx, (const char*)u_dev + (size_t)start * d_in * esz, uw, (size_t)L * d_in * esz, (size_t)Tc * d_in * esz, nb));
+      RCB_TRY(launch_window_gather(ctx, (const char*)y_dev + (size_t)start * d_out * ysz, yw, (size_t)L * d_out * ysz, (size_t)Tc * d_out * ysz, nb));
       RCB_TRY(rcbi_train_accumulate(esn, uw, yw, targets_dtype, L, nb, overlap, mode, nullptr, gc, nullptr, hT_dev, false));
       if (!has_tail && nb > 1)  // the carry handed back: the state at the end of this rank's last chunk
         RCB_CUDA(cudaMemcpyAsync(hT_dev, (const char*)hT_dev + (size_t)(nb - 1) * sumN * esz, (size_t)sumN * esz, cudaMemcpyDeviceToDevice, ctx->stream));
