@@ -46,7 +46,9 @@ h0 = rng.standard_normal((N, B)).astype(np.float32)
 lo, hi = R.shard_range(B, rank, world)
 st_r = R.resetcarry(None, esn, st, init_carry=lambda r, n: h0[:, lo:hi])
 st_all = R.resetcarry(None, esn, st, init_carry=lambda r, n: h0)
-for lam, solver, name, tol in ((1e-2, None, "train_sharded (Gram + all-reduce)", 1e-8), (1e-2, R.QRFactorization(), "train_sharded (QR factors merged)", 1e-8),
+# (the exact FP64 Gram on both sides: under AUTO the shard sizes decide between the FP64 and the tensor-core kernel)
+for lam, solver, name, tol in ((1e-2, R.NormalCholeskyFactorization(), "train_sharded (FP64 Gram + all-reduce)", 1e-8),
+                               (1e-2, R.QRFactorization(), "train_sharded (QR factors merged)", 1e-8),
                                (0.0, None, "train_sharded lambda = 0 (AUTO -> QR)", 1e-6)):
     ps_s, st_s = R.train_sharded(esn, np.asfortranarray(data[:, :, lo:hi]), np.asfortranarray(tgt[:, :, lo:hi]), ps, st_r,
                                  objective=R.RidgeRegression(lam), solver=solver, washout=w, device=dev)
