@@ -1300,12 +1300,19 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   void* st_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * T * Bc * esz, &st_dev));
   const size_t gc_elems = (size_t)F * (F + d_out), w_elems = (size_t)d_out * F;
-  // systems per batched factorisation: up to ~1 GiB of [G | C] copies, whole members (all their lambdas) at a time
-  int64_t mg = std::max<int64_t>(1, (int64_t)(((size_t)1 << 30) / (gc_elems * sizeof(double) * (size_t)n_lambda)));
-  mg = std::min<int64_t>(mg, std::max<int64_t>(1, 4096 / n_lambda));
+  const int64_t ldw = solve_padded_ld(F);                        // leading dimension of the systems being factored
+  const size_t slot_elems = (size_t)ldw * (F + d_out);           // >= gc_elems: a slot also serves as QR scratch
+  // systems per batched factorisation: whole members (all their lambdas) at a time, [G | C] copies within a third of the
+  // free memory (<= 48 GiB) — large groups keep every kernel of the factorisation wider than the machine (180 GB of HBM:
+  // config 5's 4096 systems of 8.4 MB are ONE group)
+  const size_t work_budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+  int64_t mg = std::max<int64_t>(1, (int64_t)(work_budget / (slot_elems * sizeof(double) * (size_t)n_lambda)));
+  mg = std::min<int64_t>(mg, std::max<int64_t>(1, 65535 / n_lambda));
+  mg = std::min<int64_t>(mg, Bc);
+  if (const char* e = getenv("RCB_MEMBERS_GROUP")) mg = std::max<int64_t>(1, atoll(e));  // testing hook: force several groups
   void *gc = nullptr, *work = nullptr, *w_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, gc_elems * sizeof(double), &gc));
-  RCB_TRY(ctx_scratch(ctx, SCR_W, gc_elems * sizeof(double) * (size_t)(mg * n_lambda), &work));
+  RCB_TRY(ctx_scratch(ctx, SCR_W, slot_elems * sizeof(double) * (size_t)(mg * n_lambda), &work));
   RCB_TRY(ctx_scratch(ctx, SCR_WOUT, w_elems * sizeof(double) * (size_t)(mg * n_lambda), &w_dev));  // (SCR_Y is an inter-layer buffer of collect_device)
   std::vector<double> lam_rep((size_t)(mg * n_lambda));
   for (int64_t m = 0; m < mg; ++m)
@@ -1320,17 +1327,45 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
       const int64_t ng = std::min<int64_t>(mg, nb - g0);
       std::fill(info.begin(), info.end(), 0);
       if (gram_mode != RCB_FIT_QR) {
-        for (int64_t m = 0; m < ng; ++m) {
-          const int64_t b = g0 + m;
-          const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
-          const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
-          RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
-          RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1, gram_mode, (double*)gc));
-          for (int32_t l = 0; l < n_lambda; ++l)
-            RCB_CUDA(cudaMemcpyAsync((double*)work + (size_t)(m * n_lambda + l) * gc_elems, gc, gc_elems * sizeof(double),
-                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        // [G | C] of member m lands in its first lambda slot, work[m * n_lambda], and is replicated to the others.
+        // Tensor cores take the whole group in ONE launch sequence (member = a dimension of the work list): the F^2 S
+        // threshold of RCB_GRAM_AUTO then counts the group's contraction, not a single member's.
+        const double macs = (double)F * (double)F * (double)(T - washout) * (double)ng;
+        bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10);
+        if (gram_mode == RCB_GRAM_AUTO) {
+          const char* ov = getenv("RCB_GRAM");
+          if (ov && !strcmp(ov, "fp64")) tensor = false;
+          if (ov && !strcmp(ov, "tensor")) tensor = true;
         }
-        const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data());
+        if (esn->desc.data_dtype != RCB_F32 || d_out > 8) {
+          if (gram_mode == RCB_GRAM_TENSOR) return fail(RCB_ERR_UNSUPPORTED, "RCB_GRAM_TENSOR needs Float32 states and d_out <= 8");
+          tensor = false;
+        }
+        const size_t slot_bytes = slot_elems * sizeof(double), member_pitch = slot_bytes * (size_t)n_lambda;
+        RCB_CUDA(cudaMemset2DAsync(work, member_pitch, 0, slot_bytes, (size_t)ng, ctx->stream));
+        if (tensor) {
+          ctx->last_gram_tensor = 1;
+          timer_begin(ctx, RCB_TIMER_GRAM);
+          const int32_t sg = launch_gram_tensor_batched(ctx, (const float*)st_dev + (size_t)g0 * T * F, F, F, T, washout, 1, (double*)work, ldw,
+                                                        (const char*)y_dev + (size_t)(b0 + g0) * T * d_out * ysz, targets_dtype, d_out, d_out,
+                                                        (double*)work + (size_t)ldw * F, ng, T * F, T * d_out, (int64_t)slot_elems * n_lambda);
+          timer_end(ctx, RCB_TIMER_GRAM);
+          RCB_TRY(sg);
+        } else {
+          for (int64_t m = 0; m < ng; ++m) {
+            const int64_t b = g0 + m;
+            const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
+            const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
+            RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
+            RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1,
+                                gram_mode == RCB_GRAM_AUTO ? RCB_GRAM_FP64 : gram_mode, (double*)gc));
+            RCB_CUDA(cudaMemcpy2DAsync((double*)work + (size_t)m * n_lambda * slot_elems, (size_t)ldw * sizeof(double), gc, (size_t)F * sizeof(double),
+                                       (size_t)F * sizeof(double), (size_t)(F + d_out), cudaMemcpyDeviceToDevice, ctx->stream));
+          }
+        }
+        if (n_lambda > 1) RCB_TRY(launch_replicate_blocks(ctx, (double*)work, (int64_t)slot_elems, n_lambda, ng));
+        const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data(),
+                                                      ldw, (int64_t)slot_elems);
         if (st != RCB_ERR_NUMERIC) RCB_TRY(st);
         if (st == RCB_ERR_NUMERIC && gram_mode != RCB_GRAM_AUTO) {
           for (int64_t z = 0; z < ng * n_lambda; ++z)
@@ -1355,7 +1390,7 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
         for (int32_t l = 0; l < n_lambda; ++l) {
           const size_t z = (size_t)(m * n_lambda + l);
           if (!(gram_mode == RCB_FIT_QR || lambdas[l] == 0.0 || info[z] != 0)) continue;
-          double* wk = (double*)work + z * gc_elems;
+          double* wk = (double*)work + z * slot_elems;
           RCB_CUDA(cudaMemcpyAsync(wk, gc, gc_elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
           RCB_TRY(launch_qr_absorb_lambda(ctx, wk, F, d_out, lambdas[l]));
           const int32_t sq = launch_qr_solve(ctx, wk, F, d_out, 1, (double*)w_dev + z * w_elems, nullptr);

@@ -8,6 +8,8 @@
 //   modifiers            — matrix form of src/states.jl (__apply_tomatrix, :1-15).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "rcb_internal.h"
 
 namespace rcb {
@@ -312,6 +314,27 @@ __global__ void __launch_bounds__(256) gc_pack_kernel(const double* __restrict__
 int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out, double* packed, bool unpack) {
   gc_pack_kernel<<<(unsigned)(F + d_out), 256, 0, ctx->stream>>>(GC, F, d_out, packed, unpack ? 1 : 0);
   ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// block m of `copies` consecutive slots (elems doubles each): slots 1 .. copies-1 <- slot 0 (the ensemble sweep's [G | C]
+// shared by the regularisations of a member)
+__global__ void __launch_bounds__(256) replicate_blocks_kernel(double* __restrict__ base, long long elems, int copies) {
+  double* blk = base + (size_t)blockIdx.y * elems * copies;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (long long)gridDim.x * blockDim.x) {
+    const double v = blk[i];
+    for (int c = 1; c < copies; ++c) blk[(size_t)c * elems + i] = v;
+  }
+}
+int32_t launch_replicate_blocks(rcb_ctx* ctx, double* base, int64_t elems, int32_t copies, int64_t nblocks) {
+  if (copies < 2 || nblocks < 1) return RCB_OK;
+  const unsigned gx = (unsigned)std::min<long long>((elems + 255) / 256, 64);
+  for (int64_t b0 = 0; b0 < nblocks; b0 += 65535) {
+    const unsigned gy = (unsigned)std::min<int64_t>(65535, nblocks - b0);
+    replicate_blocks_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(base + (size_t)b0 * elems * copies, elems, copies);
+    ctx->launches++;
+  }
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
 }

@@ -12,19 +12,22 @@
 //     q into three balanced base-256 digits q = a1 2^16 + a2 2^8 + a3 (a1 in [-64, 64], a2, a3 in [-128, 127]): three
 //     INT8 planes per state (3 B instead of 4 B of FP32; quantisation error <= 2^-23 s_f, unbiased);
 //   * tcgen05.mma.kind::i8 multiplies digit planes into INT32 accumulators in tensor memory — INTEGER accumulation is
-//     exact: acc2 += a1 a1', acc3 += a1 a2' + a2 a1', acc4 += a1 a3' + a3 a1' + a2 a2', acc5 += a2 a3' + a3 a2'.  Only
-//     a3 a3' is dropped: zero-mean digit noise of 3e-10 s_i s_j per sample.  (Dropping order 5 as well left 1e-7 s_i s_j
-//     per sample, which showed as ||E|| ~ lambda on outlier-scaled features — r01 measurement, scripts/dbg_ridge.py.)
+//     exact: acc2 += a1 a1', acc3 += a1 a2' + a2 a1', acc4 += a1 a3' + a3 a1' + a2 a2', acc5 += a2 a3' + a3 a2',
+//     acc6 += a3 a3'.  ALL nine digit products are kept: the result is then the exact Gram matrix of the fixed-point
+//     states q 2^(e-22) — positive semi-definite by construction, so (G + lambda I) factors for every lambda > 0 exactly as
+//     it does for the FP64 kernel.  (r01 dropped a3 a3': a PSD term of ~3e-9 G_ii went missing, and the ensemble sweep's
+//     lambda = 1e-8 systems came out indefinite — r02 measurement, config 5.)
 //   * after at most 32768 samples (|acc| < 2^31) the epilogue warps fold
-//         G_ij += 2^(e_i + e_j - 28) (2^16 acc2 + 2^8 acc3 + acc4 + 2^-8 acc5)          in FP64, red.global.add.f64.
-//   Eight INT8 MMAs (K = 32) per 32 samples cost 2/3 of the tensor time of three TF32 MMAs (K = 8) per 8 samples.
+//         G_ij += 2^(e_i + e_j - 28) (2^16 acc2 + 2^8 acc3 + acc4 + 2^-8 acc5 + 2^-16 acc6)     in FP64, red.global.add.f64.
+//   Nine INT8 MMAs (K = 32) per 32 samples cost 3/4 of the tensor time of three TF32 MMAs (K = 8) per 8 samples.
 //
 // Mapping: Z is F x S column-major, so both operands are MN-major.  The pre-pass writes the planes pre-tiled in exactly
 // the shared-memory image the MMA wants — [32-sample block][128-feature block][plane][32 rows x 128 B], 16-byte chunks
 // XOR-swizzled with (row & 7) (UMMA SWIZZLE_128B, MN-major, 8-bit) — so a pipeline stage is filled by two contiguous
 // cp.async.bulk copies.  One CTA = one 128 x 256 tile of the lower triangle; CTA pairs (a 2 x 1 cluster, 256 x 256
 // super-tile) fetch half of the shared B tile each and multicast it.  TMEM holds acc3 | acc4 (phase A, 5 MMAs per
-// K-step) or acc2 | acc5 (phase B, 3 MMAs per K-step).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
+// K-step), acc2 | acc5 (phase B, 3 MMAs per K-step) or acc6 (phase C, 1 MMA per K-step; only the third digit plane is
+// fetched: a third of the bytes of a stage).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
 // elected thread), warps 2-9 = epilogue.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -48,6 +51,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*bar
 constexpr int EPI_WARPS = 8;                           // two per TMEM lane quadrant, half of the tile columns each
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int CR = 2, CLUSTER = CR;                    // CTA pair: rows 2I, 2I+1 of 128 share the 256 B columns
+constexpr int NPHASE = 3;
 constexpr int MAX_RANGE = 32768;                       // samples per accumulation: 3 * 128 * 128 * 32768 < 2^31
 
 struct GramParams8 {
@@ -60,6 +64,9 @@ struct GramParams8 {
   long long per_split;        // samples per K-range, multiple of KB, <= MAX_RANGE
   double* G;                  // F x F column-major, lower triangle accumulated
   long long ldo, F;
+  int nmem;                   // independent problems stacked in the work list (ensemble members): item -> (member, split, tile)
+  long long q8_stride;        // bytes between the members' digit planes
+  long long g_stride;         // doubles between the members' G
   int* err;                   // set to 1 when a barrier wait timed out (the kernel then traps)
   long long* prof;            // RCB_GRAM_PROF: per CTA [mma waits full, mma waits tmem, producer waits empty, epi waits, total]
 };
@@ -164,7 +171,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
   const int ri = (int)crank;                                   // my 128-row block inside the 256 x 256 super-tile
   const long long cid = blockIdx.x / CLUSTER, ncl = gridDim.x / CLUSTER;
   const uint16_t mask_self = (uint16_t)(1u << ri), mask_all = (uint16_t)((1u << CR) - 1u);
-  const long long nitems = (long long)p.ntiles * p.splits;
+  const long long per_mem = (long long)p.ntiles * p.splits;
+  const long long nitems = per_mem * p.nmem;
 
   if (warp == 0) {
     // ===== producer: two contiguous bulk copies per stage =====
@@ -172,14 +180,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
       long long it = 0, wait_acc = 0;
       const long long tstart = clock64();
       for (long long item = cid; item < nitems; item += ncl) {
-        const int2 tl = p.tiles[item % p.ntiles];
-        const long long split = item / p.ntiles;
+        const long long mem = item / per_mem, it_m = item - mem * per_mem;
+        const int2 tl = p.tiles[it_m % p.ntiles];
+        const long long split = it_m / p.ntiles;
         const long long s_beg = split * p.per_split;
         const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
         const int nst = (int)((s_end - s_beg + KB - 1) / KB);
         const long long fa = (long long)tl.x * CR + ri, fb = (long long)tl.y * 2 + ri;   // my A block; the B block I fetch
-        for (int phase = 0; phase < 2; ++phase) {
-          const uint32_t bytes = BLK;                      // all three digit planes of a 128-feature block
+        const unsigned char* q8m = p.q8 + (size_t)mem * p.q8_stride;
+        for (int phase = 0; phase < NPHASE; ++phase) {
+          const uint32_t bytes = phase == 2 ? BOX : BLK;   // all three digit planes of a 128-feature block; phase C: the third only
+          const uint32_t poff = phase == 2 ? 2 * BOX : 0;
           for (int st = 0; st < nst; ++st, ++it) {
             const int slot = (int)(it % STAGES);
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
@@ -189,9 +200,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             const uint32_t fbar = full0 + 8 * slot;
             mbar_expect_tx(fbar, 3 * bytes);               // bytes landing in MY shared memory: A + two B blocks
             const uint32_t sa = base + slot * STAGE_BYTES; // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]
-            const unsigned char* blk = p.q8 + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
-            bulk_load_mc(sa, blk + (size_t)fa * BLK, bytes, fbar, mask_self);
-            bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, bytes, fbar, mask_all);
+            const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
+            bulk_load_mc(sa + poff, blk + (size_t)fa * BLK + poff, bytes, fbar, mask_self);
+            bulk_load_mc(sa + BLK + (uint32_t)ri * BLK + poff, blk + (size_t)fb * BLK + poff, bytes, fbar, mask_all);
           }
         }
       }
@@ -202,11 +213,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
     if (lane == 0) {
       long long it = 0, ci = 0, wfull = 0, wtm = 0;
       for (long long item = cid; item < nitems; item += ncl) {
-        const long long split = item / p.ntiles;
+        const long long split = (item % per_mem) / p.ntiles;
         const long long s_beg = split * p.per_split;
         const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
         const int nst = (int)((s_end - s_beg + KB - 1) / KB);
-        for (int phase = 0; phase < 2; ++phase, ++ci) {
+        for (int phase = 0; phase < NPHASE; ++phase, ++ci) {
           const long long w0 = clock64();
           mbar_wait(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);  // the epilogue has drained the previous accumulators
           wtm += clock64() - w0;
@@ -228,10 +239,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
               umma_i8(tmem_base + TN, A1, B3, IDESC, acc);     // acc4 = a1 a3' + a3 a1' + a2 a2'
               umma_i8(tmem_base + TN, A3, B1, IDESC, 1u);
               umma_i8(tmem_base + TN, A2, B2, IDESC, 1u);
-            } else {
+            } else if (phase == 1) {
               umma_i8(tmem_base, A1, B1, IDESC, acc);          // acc2 = a1 a1'
               umma_i8(tmem_base + TN, A2, B3, IDESC, acc);     // acc5 = a2 a3' + a3 a2'
               umma_i8(tmem_base + TN, A3, B2, IDESC, 1u);
+            } else {
+              umma_i8(tmem_base, A3, B3, IDESC, acc);          // acc6 = a3 a3'
             }
             umma_commit_mc(empty0 + 8 * slot, mask_all);       // tells both producers that fill my stage it is free
           }
@@ -247,11 +260,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
     const int nbeg = ((warp - 2) >> 2) * (TN / (EPI_WARPS / 4));
     long long ci = 0, wepi = 0;
     for (long long item = cid; item < nitems; item += ncl) {
-      const int2 tl = p.tiles[item % p.ntiles];
+      const long long mem = item / per_mem;
+      const int2 tl = p.tiles[(item - mem * per_mem) % p.ntiles];
       const long long gi = ((long long)tl.x * CR + ri) * TM + m;
       const long long gj0 = (long long)tl.y * TN;
-      const double sfi = gi < p.F ? __ldg(p.sf + gi) : 0.0;
-      for (int phase = 0; phase < 2; ++phase, ++ci) {
+      const double* sfm = p.sf + mem * (p.nfb * 128);
+      double* Gm = p.G + (size_t)mem * p.g_stride;
+      const double sfi = gi < p.F ? __ldg(sfm + gi) : 0.0;
+      for (int phase = 0; phase < NPHASE; ++phase, ++ci) {
         const long long w0 = clock64();
         mbar_wait(tfull, (uint32_t)(ci & 1), p.err);
         wepi += clock64() - w0;
@@ -261,18 +277,19 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
         for (int n0 = nbeg; n0 < nbeg + TN / (EPI_WARPS / 4); n0 += 16) {
           uint32_t v[16], w[16];
           TMEM_LD16(trow + (uint32_t)n0, v);
-          TMEM_LD16(trow + (uint32_t)(TN + n0), w);
+          if (phase < 2) TMEM_LD16(trow + (uint32_t)(TN + n0), w);
           double sfj[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) sfj[q] = gj0 + n0 + q < p.F ? __ldg(p.sf + gj0 + n0 + q) : 0.0;
+          for (int q = 0; q < 16; ++q) sfj[q] = gj0 + n0 + q < p.F ? __ldg(sfm + gj0 + n0 + q) : 0.0;
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const long long gj = gj0 + n0 + q;
             if (gi < p.F && gj <= gi) {
               const double a = phase == 0 ? 256.0 * (double)(int)v[q] + (double)(int)w[q]
-                                          : 65536.0 * (double)(int)v[q] + 0.00390625 * (double)(int)w[q];
-              if (a != 0.0) atomicAdd(p.G + (size_t)gj * p.ldo + gi, a * sfi * sfj[q]);
+                               : phase == 1 ? 65536.0 * (double)(int)v[q] + 0.00390625 * (double)(int)w[q]
+                                            : 1.52587890625e-05 * (double)(int)v[q];
+              if (a != 0.0) atomicAdd(Gm + (size_t)gj * p.ldo + gi, a * sfi * sfj[q]);
             }
           }
         }
@@ -298,9 +315,11 @@ constexpr int SLAB = 128;
 template <int VEC>
 __global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ Z, long long ldz, long long F, long long T,
                                                      long long washout, long long Te, long long s0, long long Sc,
-                                                     int* __restrict__ amax) {
+                                                     int* __restrict__ amax, long long z_stride, long long ldp) {
   const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (f >= F) return;
+  Z += (size_t)blockIdx.z * z_stride;       // member
+  amax += (size_t)blockIdx.z * ldp;
   const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB < Sc ? sl0 + SLAB : Sc;
   float mx[VEC];
 #pragma unroll
@@ -338,7 +357,13 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
                                                          long long T, long long washout, long long Te, long long s0,
                                                          long long Sc, const int* __restrict__ amax, unsigned char* __restrict__ q8,
                                                          double* __restrict__ sf, const TY* __restrict__ Y, long long ldy, int d_out,
-                                                         double* __restrict__ C, long long ldc) {
+                                                         double* __restrict__ C, long long ldc, long long z_stride, long long y_stride,
+                                                         long long q8_stride, long long c_stride) {
+  Z += (size_t)blockIdx.z * z_stride;       // member
+  amax += (size_t)blockIdx.z * ldp;
+  sf += (size_t)blockIdx.z * ldp;
+  q8 += (size_t)blockIdx.z * q8_stride;
+  if (C) { Y += (size_t)blockIdx.z * y_stride; C += (size_t)blockIdx.z * c_stride; }
   const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB;  // whole sample blocks: rows >= Sc become zeros
   if (f >= ldp) return;
@@ -428,9 +453,13 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
 
 // G(F x F, ld = ldo, FP64, lower triangle) += Z Z' over {b*T + t : b < nseq, washout <= t < T}; Z is FP32, device.
 // When Y is given (d_out <= 8), C(F x d_out, ld = ldo) += Z Y' is accumulated by the same pre-pass.
-int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
-                           double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C) {
+// nmem > 1: nmem independent problems in one launch sequence (the ensemble sweep, BASELINE config 5) — member z reads
+// Z + z * z_stride (elements) / Y + z * y_stride and accumulates into G + z * g_stride / C + z * g_stride.
+int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
+                                   double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C,
+                                   int64_t nmem, int64_t z_stride, int64_t y_stride, int64_t g_stride) {
   if (C && (d_out > 8 || !Y)) return fail(RCB_ERR_UNSUPPORTED, "fused cross term supports d_out <= 8");
+  if (nmem < 1 || nmem > 65535) return fail(RCB_ERR_UNSUPPORTED, "1 to 65535 members per batched Gram");
   const long long Te = T - washout, Stot = Te * nseq;
   if (Stot <= 0) return RCB_OK;
   const long long ldp = (F + 255) / 256 * 256;   // whole 256 x 256 super-tiles
@@ -445,7 +474,7 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
   int* d_err = reinterpret_cast<int*>((char*)d_tiles + tiles.size() * sizeof(int2));
   RCB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
   // sample sub-chunks: the digit planes (3 B per state) stay within 6 GiB
-  long long Ssub = ((long long)6 << 30) / (ldp * PLANES);
+  long long Ssub = ((long long)6 << 30) / (ldp * PLANES * nmem);
   if (const char* ov = getenv("RCB_GRAM_SUB_SAMPLES")) Ssub = atoll(ov);  // testing hook: force several sub-chunks
   Ssub = Ssub / SLAB * SLAB;
   if (Ssub < SLAB) Ssub = SLAB;
@@ -453,10 +482,11 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
   const long long Ssub_pad = (Ssub + SLAB - 1) / SLAB * SLAB;
   RCB_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   void *q8 = nullptr, *aux = nullptr;
-  RCB_TRY(ctx_scratch(ctx, SCR_ZHI, (size_t)ldp * Ssub_pad * PLANES, &q8));
-  RCB_TRY(ctx_scratch(ctx, SCR_ZLO, (size_t)ldp * (sizeof(double) + sizeof(int)), &aux));
+  const long long q8_stride = ldp * Ssub_pad * PLANES;
+  RCB_TRY(ctx_scratch(ctx, SCR_ZHI, (size_t)q8_stride * nmem, &q8));
+  RCB_TRY(ctx_scratch(ctx, SCR_ZLO, (size_t)ldp * nmem * (sizeof(double) + sizeof(int)), &aux));
   double* sf = reinterpret_cast<double*>(aux);
-  int* amax = reinterpret_cast<int*>(sf + ldp);
+  int* amax = reinterpret_cast<int*>(sf + ldp * nmem);
   int ncl_max = 0;
   {
     cudaLaunchConfig_t cfg = {};
@@ -472,22 +502,23 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
   if (prof && !prof_dev) cudaMalloc(&prof_dev, 148 * 5 * sizeof(long long));
   for (long long s0 = 0; s0 < Stot; s0 += Ssub) {
     const long long Sc = Stot - s0 < Ssub ? Stot - s0 : Ssub;
-    RCB_CUDA(cudaMemsetAsync(amax, 0, (size_t)ldp * sizeof(int), ctx->stream));
+    RCB_CUDA(cudaMemsetAsync(amax, 0, (size_t)ldp * nmem * sizeof(int), ctx->stream));
     {
       const bool vec = ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0;
       const unsigned ny = (unsigned)((Sc + SLAB - 1) / SLAB);
       const bool y64 = C && ydt == RCB_F64, small = d_out <= 4;
 #define RCB_SPLIT(TY, V, D, G)                                                                                                   \
   split_int8_kernel<TY, V, D><<<G, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,   \
-                                                          (const TY*)(C ? Y : nullptr), ldy, (int)d_out, C, ldo)
+                                                          (const TY*)(C ? Y : nullptr), ldy, (int)d_out, C, ldo, z_stride, y_stride,     \
+                                                          q8_stride, g_stride)
       if (vec) {
-        colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
-        const dim3 sgrid((unsigned)((ldp + 1023) / 1024), ny);
+        colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp);
+        const dim3 sgrid((unsigned)((ldp + 1023) / 1024), ny, (unsigned)nmem);
         if (y64) { if (small) RCB_SPLIT(double, 4, 4, sgrid); else RCB_SPLIT(double, 4, 8, sgrid); }
         else { if (small) RCB_SPLIT(float, 4, 4, sgrid); else RCB_SPLIT(float, 4, 8, sgrid); }
       } else {
-        colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax);
-        const dim3 sgrid((unsigned)(ldp / 256), ny);
+        colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp);
+        const dim3 sgrid((unsigned)(ldp / 256), ny, (unsigned)nmem);
         if (y64) RCB_SPLIT(double, 1, 8, sgrid); else RCB_SPLIT(float, 1, 8, sgrid);
       }
 #undef RCB_SPLIT
@@ -496,6 +527,7 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
     GramParams8 p{};
     p.tiles = (const int2*)d_tiles; p.ntiles = ntiles; p.q8 = (const unsigned char*)q8; p.sf = sf; p.nfb = ldp / 128;
     p.S = Sc; p.G = G; p.ldo = ldo; p.F = F; p.err = d_err;
+    p.nmem = (int)nmem; p.q8_stride = q8_stride; p.g_stride = g_stride;
     if (prof) cudaMemsetAsync(prof_dev, 0, 148 * 5 * sizeof(long long), ctx->stream);
     p.prof = prof ? prof_dev : nullptr;
     // K-ranges: at most MAX_RANGE samples (exact INT32 accumulation), and enough of them to fill the last round of clusters
@@ -504,7 +536,7 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
     double best = -1.0;
     long long best_c = splits;
     for (long long c = splits; c <= max_splits && c < splits + 64; ++c) {
-      const long long items = (long long)ntiles * c, rounds = (items + ncl_max - 1) / ncl_max;
+      const long long items = (long long)ntiles * c * nmem, rounds = (items + ncl_max - 1) / ncl_max;
       const double eff = (double)items / (double)(rounds * ncl_max);
       if (eff > best + 1e-9) { best = eff; best_c = c; }
       if (eff >= 0.97) break;
@@ -512,7 +544,7 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
     splits = best_c;
     p.per_split = ((Sc + splits - 1) / splits + KB - 1) / KB * KB;
     p.splits = (int)((Sc + p.per_split - 1) / p.per_split);
-    const long long nitems = (long long)ntiles * p.splits;
+    const long long nitems = (long long)ntiles * p.splits * nmem;
     const int grid = (int)(nitems < ncl_max ? nitems : ncl_max) * CLUSTER;
     const bool tsplit = getenv("RCB_GRAM_TIMING") != nullptr;  // diagnostics: time the MMA kernel alone in the SOLVE timer slot
     if (tsplit) timer_begin(ctx, RCB_TIMER_SOLVE);
@@ -533,6 +565,11 @@ int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz,
     }
   }
   return RCB_OK;
+}
+
+int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
+                           double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C) {
+  return launch_gram_tensor_batched(ctx, Z, F, ldz, T, washout, nseq, G, ldo, Y, ydt, d_out, ldy, C, 1, 0, 0, 0);
 }
 
 }  // namespace rcb

@@ -187,6 +187,7 @@ enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5,
        SCR_RAW = 8, SCR_INFO = 9, SCR_W = 10, SCR_HT = 11, SCR_ZHI = 12, SCR_ZLO = 13, SCR_TCSCR = 14, SCR_TILES = 15,
        SCR_WOUT = 16,   // readout weights of the batched ensemble solve (never an inter-layer buffer of collect_device)
        SCR_QRA = 17, SCR_QRP = 18, SCR_QRW = 19,   // qr_solve.cu: sample chunk [A | B], partial products, W + T
+       SCR_SOLVE = 25,                              // solve.cu: padded copy of one system
        SCR_PACK = 20,                               // comm.cu: packed [G | C] / gathered factors
        SCR_CHUNK_U = 21, SCR_CHUNK_Y = 22, SCR_CHUNK_UW = 23, SCR_CHUNK_YW = 24,   // comm.cu: staged series + window batches
        SCR_COUNT = 32 };
@@ -250,6 +251,11 @@ int32_t launch_gc_pack(rcb_ctx* ctx, const double* GC, int64_t F, int64_t d_out,
 int32_t launch_gram_tensor(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
                            double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C);
 
+int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int64_t ldz, int64_t T, int64_t washout, int64_t nseq,
+                                   double* G, int64_t ldo, const void* Y, int32_t ydt, int64_t d_out, int64_t ldy, double* C,
+                                   int64_t nmem, int64_t z_stride, int64_t y_stride, int64_t g_stride);
+
+int32_t launch_replicate_blocks(rcb_ctx* ctx, double* base, int64_t elems, int32_t copies, int64_t nblocks);
 // feature plumbing (dense_kernels.cu): symmetric fill + scale of a lower-triangle Gram, Extend, DelayLayer over time
 int32_t launch_sym_scale(rcb_ctx* ctx, const double* G, int64_t F, double scale, int32_t dtype, void* out);
 int32_t launch_extend(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols, int32_t dtype, void* out);
@@ -267,7 +273,8 @@ int32_t spectral_radius_csr(rcb_ctx* ctx, const HostCsr& A, double tol, int32_t 
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out);
 // the same for nsys systems stored back to back, one launch sequence (lambdas: host array or nullptr -> lambda0 for all)
 int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
-                                   int64_t nsys, double* W_out, int* info_out);
+                                   int64_t nsys, double* W_out, int* info_out, int64_t lda = 0, int64_t stride = 0);
+int64_t solve_padded_ld(int64_t F);
 
 // qr_solve.cu — the QR-grade ridge path (Householder QR of [sqrt(lambda) I; Z'], streamed over sample chunks).
 // RQ = [R | Q'b], F x (F + d_out) Float64, the same footprint as [G | C].

@@ -6,6 +6,7 @@
 // "solver ... failed to solve the ridge regression system" ArgumentError (train.jl:194-196).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -86,78 +87,140 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double* A, long long ld
 // Trailing update: A[i, j] -= sum_m P[i, m] P[j, m] over the kw (32 or 64) panel columns starting at kp0, for the
 // lower-triangular region i >= j >= base, j < jlim, in 64 x 64 tiles.  Two 32-wide panels are applied in ONE pass over
 // the trailing matrix (the second panel is factored after a narrow update of its own 32 columns): the matrix is
-// streamed F/64 times instead of F/32 — the factorisation is bound by exactly that traffic when thousands of systems
-// are solved at once (BASELINE config 5).
-__global__ void __launch_bounds__(256) syrk_update_kernel(double* A, long long lda, long long F, long long kp0, int kw,
-                                                         long long base, long long jlim, long long stride) {
+// streamed F/64 times instead of F/32.
+// The products run on the FP64 tensor path (mma.sync m8n8k4, DMMA): a warp owns 16 (i) x 32 (j) of the tile as 2 x 4
+// fragments — six 64-bit shared-memory loads feed eight MMAs (2048 FMAs), against eight loads per 512 FMAs of the
+// register-tiled CUDA-core version this replaces (r01: 4.3 TFLOP/s on the batched config-5 solve, shared-memory bound).
+// D[jj][ii] = sum_m Pj[m][jj] Pi[m][ii]: the MMA's row dimension is the tile COLUMN j, so a thread's two accumulators of a
+// fragment are consecutive rows i of one column — 16 contiguous bytes of the column-major matrix.
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One global round trip per tile: every panel element travels global -> shared memory by cp.async (no register staging, all
+// 64 KB of a tile's operands in flight at once), the C tile is loaded into the accumulators at the same time (the MMAs then
+// compute C - Pi Pj' directly: the Pj operand is negated on its way out of shared memory), and the only dependent global
+// access left is the final store.  (r02 ncu of the register-staged version: 62 stall cycles per issued instruction on the
+// loads, tensor pipe 11 % busy, DRAM 6 % — three to eight serial round trips per tile.)
+__device__ __forceinline__ void cp_async_f64(double* smem_dst, const double* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;   // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+constexpr int SYRK_TILE = 64, SYRK_LDP = SYRK_TILE + 4;   // 68: (4 m + col) mod 16 is a bijection of a half-warp's 16 (m, col) pairs
+constexpr int SYRK_KMAX = 2 * NBLK;
+constexpr size_t SYRK_SMEM = 2 * (size_t)SYRK_KMAX * SYRK_LDP * sizeof(double);
+
+__global__ void __launch_bounds__(256, 3) syrk_update_kernel(double* A, long long lda, long long F, long long kp0, int kw,
+                                                            long long base, long long jlim, long long stride) {
   A += (size_t)blockIdx.z * stride;
-  constexpr int TILE = 64;
+  constexpr int TILE = SYRK_TILE, LDP = SYRK_LDP;
   const long long i0 = base + (long long)blockIdx.y * TILE, j0 = base + (long long)blockIdx.x * TILE;
   if (j0 > i0 || i0 >= F || j0 >= jlim) return;
-  __shared__ double Pi[NBLK][TILE];
-  __shared__ double Pj[NBLK][TILE];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[4][4] = {};
-  for (int m0 = 0; m0 < kw; m0 += NBLK) {
-    for (int e = tid; e < NBLK * TILE; e += 256) {
-      const int ii = e % TILE, m = e / TILE;
-      Pi[m][ii] = i0 + ii < F ? A[(size_t)(kp0 + m0 + m) * lda + i0 + ii] : 0.0;
-      Pj[m][ii] = j0 + ii < F ? A[(size_t)(kp0 + m0 + m) * lda + j0 + ii] : 0.0;
+  extern __shared__ double syrk_smem[];
+  double(*Pi)[LDP] = reinterpret_cast<double(*)[LDP]>(syrk_smem);
+  double(*Pj)[LDP] = reinterpret_cast<double(*)[LDP]>(syrk_smem + (size_t)SYRK_KMAX * LDP);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < kw * TILE; e += 256) {
+    const int ii = e % TILE, m = e / TILE;
+    const double* col = A + (size_t)(kp0 + m) * lda;
+    const bool vi = i0 + ii < F, vj = j0 + ii < F;
+    cp_async_f64(&Pi[m][ii], col + (vi ? i0 + ii : 0), vi);
+    cp_async_f64(&Pj[m][ii], col + (vj ? j0 + ii : 0), vj);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int wi = (warp & 3) * 16, wj = (warp >> 2) * 32;   // this warp's corner inside the tile
+  const int fm = lane & 3, fc = lane >> 2;                 // fragment coordinates of this lane
+  double acc[4][2][2];                                      // [j fragment][i fragment][2 consecutive rows], starts as C
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long j = j0 + wj + t * 8 + fc;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long i = i0 + wi + u * 8 + fm * 2 + r;
+        acc[t][u][r] = (i < F && j <= i && j < jlim) ? A[(size_t)j * lda + i] : 0.0;
+      }
     }
-    __syncthreads();
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+#pragma unroll 4
+  for (int k4 = 0; k4 < kw; k4 += 4) {
+    double a[4], b[2];
 #pragma unroll
-    for (int m = 0; m < NBLK; ++m) {
-      double a[4], b[4];
+    for (int t = 0; t < 4; ++t) a[t] = -Pj[k4 + fm][wj + t * 8 + fc];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = Pi[m][tx + 16 * q]; b[q] = Pj[m][ty + 16 * q]; }
+    for (int u = 0; u < 2; ++u) b[u] = Pi[k4 + fm][wi + u * 8 + fc];
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
+    for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
-    }
-    __syncthreads();
+      for (int u = 0; u < 2; ++u) dmma_8x8x4(acc[t][u][0], acc[t][u][1], a[t], b[u]);
   }
 #pragma unroll
-  for (int x = 0; x < 4; ++x)
+  for (int t = 0; t < 4; ++t)
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const long long i = i0 + tx + 16 * x, j = j0 + ty + 16 * y;
-      if (i < F && j <= i && j < jlim) A[(size_t)j * lda + i] -= acc[x][y];
+    for (int u = 0; u < 2; ++u) {
+      const long long j = j0 + wj + t * 8 + fc;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long i = i0 + wi + u * 8 + fm * 2 + r;
+        if (i < F && j <= i && j < jlim) A[(size_t)j * lda + i] = acc[t][u][r];
+      }
     }
 }
 
-// Forward then backward substitution for one right-hand side per CTA.  rhs column o lives at
-// RHS + o*lda (length F); the solution overwrites it and is also written to W_out[o + d_out*f].
+// Forward then backward substitution, one CTA per (system, group of up to RMAX right-hand sides): L is read once for the
+// whole group, and every 32 x 32 diagonal block is staged in shared memory before the serial part (the r01 version chased
+// global loads inside the 32-step dependent chain: 17.8 ms of the 47 ms F = 8192 solve).  rhs column o lives at
+// RHS + o*ldr (length F); the solution overwrites it and is also written to W_out[o + d_out*f].
+template <int RMAX>
 __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, long long lda, long long F,
                                                                double* RHS, long long ldr, long long d_out,
                                                                double* W_out, long long stride) {
   L += (size_t)blockIdx.z * stride;
   RHS += (size_t)blockIdx.z * stride;
   W_out += (size_t)blockIdx.z * d_out * F;
-  extern __shared__ double xs[];  // [F]
-  __shared__ double blk[NBLK];
+  extern __shared__ double xs[];  // [RMAX][F]
+  __shared__ double Ld[NBLK][NBLK + 1];
+  __shared__ double blk[RMAX][NBLK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const long long o = blockIdx.x;
-  double* c = RHS + (size_t)o * ldr;
-  for (long long i = tid; i < F; i += nthreads) xs[i] = c[i];
+  const long long o0 = (long long)blockIdx.x * RMAX;
+  const int nr = (int)(d_out - o0 < RMAX ? d_out - o0 : RMAX);
+  for (int r = 0; r < nr; ++r)
+    for (long long i = tid; i < F; i += nthreads) xs[(size_t)r * F + i] = RHS[(size_t)(o0 + r) * ldr + i];
   __syncthreads();
   // forward: L y = c
   for (long long k0 = 0; k0 < F; k0 += NBLK) {
-    const long long nb = F - k0 < NBLK ? F - k0 : NBLK;
-    if (warp == 0) {
-      double yv = lane < nb ? xs[k0 + lane] : 0.0;
+    const int nb = (int)(F - k0 < NBLK ? F - k0 : NBLK);
+    for (int e = tid; e < NBLK * NBLK; e += nthreads) {
+      const int i = e % NBLK, j = e / NBLK;
+      Ld[i][j] = (i < nb && j < nb && i >= j) ? L[(size_t)(k0 + j) * lda + k0 + i] : 0.0;
+    }
+    __syncthreads();
+    if (warp < nr) {  // warp r solves the diagonal block for right-hand side r
+      double yv = lane < nb ? xs[(size_t)warp * F + k0 + lane] : 0.0;
       for (int j = 0; j < nb; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, yv, j) / L[(size_t)(k0 + j) * lda + k0 + j];
+        const double piv = __shfl_sync(0xffffffffu, yv, j) / Ld[j][j];
         if (lane == j) yv = piv;
-        if (lane > j && lane < nb) yv -= piv * L[(size_t)(k0 + j) * lda + k0 + lane];
+        if (lane > j && lane < nb) yv -= piv * Ld[lane][j];
       }
-      if (lane < nb) { xs[k0 + lane] = yv; blk[lane] = yv; }
+      if (lane < nb) { xs[(size_t)warp * F + k0 + lane] = yv; blk[warp][lane] = yv; }
     }
     __syncthreads();
     for (long long i = k0 + nb + tid; i < F; i += nthreads) {
-      double s = xs[i];
-      for (int m = 0; m < nb; ++m) s -= L[(size_t)(k0 + m) * lda + i] * blk[m];
-      xs[i] = s;
+      double sacc[RMAX];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) sacc[r] = 0.0;
+      for (int m = 0; m < nb; ++m) {
+        const double l = L[(size_t)(k0 + m) * lda + i];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) sacc[r] = fma(l, blk[r][m], sacc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < nr) xs[(size_t)r * F + i] -= sacc[r];
     }
     __syncthreads();
   }
@@ -165,37 +228,55 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, l
   const long long nblocks = (F + NBLK - 1) / NBLK;
   for (long long kb = nblocks - 1; kb >= 0; --kb) {
     const long long k0 = kb * NBLK;
-    const long long nb = F - k0 < NBLK ? F - k0 : NBLK;
+    const int nb = (int)(F - k0 < NBLK ? F - k0 : NBLK);
+    for (int e = tid; e < NBLK * NBLK; e += nthreads) {
+      const int i = e % NBLK, j = e / NBLK;
+      Ld[i][j] = (i < nb && j < nb && i >= j) ? L[(size_t)(k0 + j) * lda + k0 + i] : 0.0;
+    }
     for (int w = warp; w < nb; w += nwarps) {
-      double s = 0.0;
-      for (long long j = k0 + nb + lane; j < F; j += 32) s = fma(L[(size_t)(k0 + w) * lda + j], xs[j], s);
+      double sacc[RMAX];
 #pragma unroll
-      for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-      if (lane == 0) blk[w] = xs[k0 + w] - s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      double xv = lane < nb ? blk[lane] : 0.0;
-      for (int j = (int)nb - 1; j >= 0; --j) {
-        const double piv = __shfl_sync(0xffffffffu, xv, j) / L[(size_t)(k0 + j) * lda + k0 + j];
-        if (lane == j) xv = piv;
-        if (lane < j) xv -= piv * L[(size_t)(k0 + lane) * lda + k0 + j];
+      for (int r = 0; r < RMAX; ++r) sacc[r] = 0.0;
+      for (long long j = k0 + nb + lane; j < F; j += 32) {
+        const double l = L[(size_t)(k0 + w) * lda + j];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r)
+          if (r < nr) sacc[r] = fma(l, xs[(size_t)r * F + j], sacc[r]);
       }
-      if (lane < nb) xs[k0 + lane] = xv;
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        double v = sacc[r];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0 && r < nr) blk[r][w] = xs[(size_t)r * F + k0 + w] - v;
+      }
+    }
+    __syncthreads();
+    if (warp < nr) {
+      double xv = lane < nb ? blk[warp][lane] : 0.0;
+      for (int j = nb - 1; j >= 0; --j) {
+        const double piv = __shfl_sync(0xffffffffu, xv, j) / Ld[j][j];
+        if (lane == j) xv = piv;
+        if (lane < j) xv -= piv * Ld[j][lane];
+      }
+      if (lane < nb) xs[(size_t)warp * F + k0 + lane] = xv;
     }
     __syncthreads();
   }
-  for (long long i = tid; i < F; i += nthreads) {
-    c[i] = xs[i];
-    W_out[o + (size_t)d_out * i] = xs[i];
-  }
+  for (int r = 0; r < nr; ++r)
+    for (long long i = tid; i < F; i += nthreads) {
+      const double v = xs[(size_t)r * F + i];
+      RHS[(size_t)(o0 + r) * ldr + i] = v;
+      W_out[(o0 + r) + (size_t)d_out * i] = v;
+    }
 }
 
 // nsys systems stored back to back (stride F*(F+d_out) doubles, each [G | C], destroyed); lambdas: nsys values on the HOST
 // (nullptr: every system uses lambda0); W_out: nsys x (d_out x F) on the device; info_out (host, nsys ints, may be null)
 // receives 0 or the 1-based feature of the first non-positive pivot.  Returns RCB_ERR_NUMERIC if any system failed.
+// lda_in: leading dimension of every system (0 -> F); stride_in: doubles between systems (0 -> lda * (F + d_out)).
 int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
-                                   int64_t nsys, double* W_out, int* info_out) {
+                                   int64_t nsys, double* W_out, int* info_out, int64_t lda_in, int64_t stride_in) {
   if (nsys < 1) return RCB_OK;
   if (nsys > 65535) return fail(RCB_ERR_UNSUPPORTED, "at most 65535 systems per batched solve");
   void* tmp = nullptr;
@@ -205,8 +286,9 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
   RCB_CUDA(cudaMemsetAsync(d_info, 0, (size_t)nsys * sizeof(int), ctx->stream));
   if (lambdas) RCB_CUDA(cudaMemcpyAsync(d_lam, lambdas, (size_t)nsys * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   const double* lam = lambdas ? d_lam : nullptr;
+  RCB_CUDA(cudaFuncSetAttribute(syrk_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM));
   timer_begin(ctx, RCB_TIMER_SOLVE);
-  const long long lda = F, stride = (long long)F * (F + d_out);
+  const long long lda = lda_in > 0 ? lda_in : F, stride = stride_in > 0 ? stride_in : lda * (F + d_out);
   const unsigned nz = (unsigned)nsys;
   for (long long k0 = 0; k0 < F; k0 += 2 * NBLK) {
     // panel pair (k0, k0 + 32): factor the first, bring the second's own 32 columns up to date, factor it, then apply both
@@ -216,7 +298,7 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
     const long long rem1 = F - k0 - NBLK;
     if (rem1 <= 0) break;
     trsm_panel_kernel<<<dim3((unsigned)((rem1 + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0, stride);
-    syrk_update_kernel<<<dim3(1, (unsigned)((rem1 + 63) / 64), nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, NBLK, k0 + NBLK,
+    syrk_update_kernel<<<dim3(1, (unsigned)((rem1 + 63) / 64), nz), 256, SYRK_SMEM, ctx->stream>>>(GC, lda, F, k0, NBLK, k0 + NBLK,
                                                                                         k0 + 2 * NBLK, stride);
     potrf_diag_kernel<<<dim3(1, 1, nz), NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0 + NBLK, lambda0, lam, stride, d_info);
     ctx->launches += 3;
@@ -224,13 +306,25 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
     if (rem2 <= 0) break;
     trsm_panel_kernel<<<dim3((unsigned)((rem2 + 127) / 128), 1, nz), 128, 0, ctx->stream>>>(GC, lda, F, k0 + NBLK, stride);
     const unsigned tiles = (unsigned)((rem2 + 63) / 64);
-    syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, 0, ctx->stream>>>(GC, lda, F, k0, 2 * NBLK, k0 + 2 * NBLK, F, stride);
+    syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, SYRK_SMEM, ctx->stream>>>(GC, lda, F, k0, 2 * NBLK, k0 + 2 * NBLK, F, stride);
     ctx->launches += 2;
   }
-  const size_t smem = (size_t)F * sizeof(double);
-  if (smem > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "feature count %lld too large for the triangular-solve kernel", (long long)F);
-  RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cholesky_solve_kernel<<<dim3((unsigned)d_out, 1, nz), 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)F * F, lda, d_out, W_out, stride);
+  // right-hand sides per CTA: as many (<= 4) as fit the shared-memory budget next to each other
+  int rmax = 4;
+  while (rmax > 1 && ((size_t)rmax * F * sizeof(double) + 12 * 1024 > ctx->smem_optin || rmax / 2 >= d_out)) rmax /= 2;
+  const size_t smem = (size_t)rmax * F * sizeof(double);
+  if (smem + 12 * 1024 > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "feature count %lld too large for the triangular-solve kernel", (long long)F);
+  const dim3 sgrid((unsigned)((d_out + rmax - 1) / rmax), 1, nz);
+  if (rmax == 4) {
+    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cholesky_solve_kernel<4><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
+  } else if (rmax == 2) {
+    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cholesky_solve_kernel<2><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
+  } else {
+    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cholesky_solve_kernel<1><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
+  }
   ctx->launches++;
   timer_end(ctx, RCB_TIMER_SOLVE);
   RCB_CUDA(cudaGetLastError());
@@ -249,8 +343,23 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
   return st;
 }
 
+// Leading dimension the factorisation works with.  A padded column stride (against DRAM bank camping of power-of-two
+// strides) was measured and does not help: the hook stays for experiments.
+int64_t solve_padded_ld(int64_t F) {
+  long long pad = 0;   // measured on config 5 (r02): 0 -> 444 ms, 4 -> 486 ms, 16 -> 495 ms: no bank effect, padding stays off
+  if (const char* e = getenv("RCB_SOLVE_PAD")) pad = atoll(e);  // testing hook
+  return (F % 32 == 0 && pad > 0) ? F + pad : F;
+}
+
+// One system, [G | C] with leading dimension F: factored in a padded copy (the input is left intact).
 int32_t launch_ridge_solve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda, double* W_out) {
-  return launch_ridge_solve_batched(ctx, GC, F, d_out, lambda, nullptr, 1, W_out, nullptr);
+  const int64_t ld = solve_padded_ld(F);
+  if (ld == F) return launch_ridge_solve_batched(ctx, GC, F, d_out, lambda, nullptr, 1, W_out, nullptr, 0, 0);
+  void* work = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_SOLVE, (size_t)ld * (F + d_out) * sizeof(double), &work));
+  RCB_CUDA(cudaMemcpy2DAsync(work, (size_t)ld * sizeof(double), GC, (size_t)F * sizeof(double), (size_t)F * sizeof(double), (size_t)(F + d_out),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  return launch_ridge_solve_batched(ctx, (double*)work, F, d_out, lambda, nullptr, 1, W_out, nullptr, ld, 0);
 }
 
 }  // namespace rcb
