@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -175,13 +176,15 @@ __global__ void __launch_bounds__(256, 3) syrk_update_kernel(double* A, long lon
 // whole group, and every 32 x 32 diagonal block is staged in shared memory before the serial part (the r01 version chased
 // global loads inside the 32-step dependent chain: 17.8 ms of the 47 ms F = 8192 solve).  rhs column o lives at
 // RHS + o*ldr (length F); the solution overwrites it and is also written to W_out[o + d_out*f].
+// mode: 0 = forward + backward on the whole system (r0 = 0, F = n); 1 = forward only / 2 = backward only on the diagonal
+// block of rows [r0, r0 + F) of a larger system of Ftot rows (the off-diagonal parts are the trsv_update kernels below).
 template <int RMAX>
 __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, long long lda, long long F,
                                                                double* RHS, long long ldr, long long d_out,
-                                                               double* W_out, long long stride) {
-  L += (size_t)blockIdx.z * stride;
-  RHS += (size_t)blockIdx.z * stride;
-  W_out += (size_t)blockIdx.z * d_out * F;
+                                                               double* W_out, long long stride, long long r0, long long Ftot, int mode) {
+  L += (size_t)blockIdx.z * stride + (size_t)r0 * lda + r0;
+  RHS += (size_t)blockIdx.z * stride + r0;
+  W_out += (size_t)blockIdx.z * d_out * Ftot + (size_t)d_out * r0;
   extern __shared__ double xs[];  // [RMAX][F]
   __shared__ double Ld[NBLK][NBLK + 1];
   __shared__ double blk[RMAX][NBLK];
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, l
     for (long long i = tid; i < F; i += nthreads) xs[(size_t)r * F + i] = RHS[(size_t)(o0 + r) * ldr + i];
   __syncthreads();
   // forward: L y = c
-  for (long long k0 = 0; k0 < F; k0 += NBLK) {
+  for (long long k0 = 0; k0 < F && mode != 2; k0 += NBLK) {
     const int nb = (int)(F - k0 < NBLK ? F - k0 : NBLK);
     for (int e = tid; e < NBLK * NBLK; e += nthreads) {
       const int i = e % NBLK, j = e / NBLK;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, l
   }
   // backward: L' x = y, blocks from the bottom; warp w owns column k0+w of the block
   const long long nblocks = (F + NBLK - 1) / NBLK;
-  for (long long kb = nblocks - 1; kb >= 0; --kb) {
+  for (long long kb = nblocks - 1; kb >= 0 && mode != 1; --kb) {
     const long long k0 = kb * NBLK;
     const int nb = (int)(F - k0 < NBLK ? F - k0 : NBLK);
     for (int e = tid; e < NBLK * NBLK; e += nthreads) {
@@ -267,8 +270,59 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(const double* L, l
     for (long long i = tid; i < F; i += nthreads) {
       const double v = xs[(size_t)r * F + i];
       RHS[(size_t)(o0 + r) * ldr + i] = v;
-      W_out[(o0 + r) + (size_t)d_out * i] = v;
+      if (mode != 1) W_out[(o0 + r) + (size_t)d_out * i] = v;
     }
+}
+
+// Off-diagonal parts of the blocked triangular solves of ONE large system, spread over the machine (a single CTA pulling
+// all of L through one SM took 20 of the 37 ms of the F = 8192 solve: 27 GB/s).
+// forward: y[r0 + n :] -= L[r0 + n :, r0 : r0 + n] y[r0 : r0 + n]; grid (row tiles of 128, column chunks of 128), FP64 atomics
+__global__ void __launch_bounds__(128) trsv_update_fwd_kernel(const double* __restrict__ L, long long lda, long long F, long long r0,
+                                                               long long n, double* RHS, long long ldr, int d_out) {
+  __shared__ double xb[8][128];
+  const long long i = r0 + n + (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long c0 = r0 + (long long)blockIdx.y * 128;
+  const int nc = (int)(r0 + n - c0 < 128 ? r0 + n - c0 : 128);
+  for (int o = 0; o < d_out; ++o) xb[o][threadIdx.x] = threadIdx.x < nc ? RHS[(size_t)o * ldr + c0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  if (i >= F) return;
+  double acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0;
+#pragma unroll 4
+  for (int m = 0; m < nc; ++m) {
+    const double l = L[(size_t)(c0 + m) * lda + i];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < d_out) acc[o] = fma(l, xb[o][m], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    if (o < d_out) atomicAdd(RHS + (size_t)o * ldr + i, -acc[o]);
+}
+// backward: x[: r0] -= L[r0 : r0 + n, : r0]' x[r0 : r0 + n]; one warp per column j < r0 (its rows r0.. are contiguous)
+__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __restrict__ L, long long lda, long long r0, long long n,
+                                                               double* RHS, long long ldr, int d_out) {
+  const int lane = threadIdx.x & 31;
+  const long long j = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= r0) return;
+  double acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0;
+  const double* col = L + (size_t)j * lda;
+  for (long long i = r0 + lane; i < r0 + n; i += 32) {
+    const double l = col[i];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < d_out) acc[o] = fma(l, RHS[(size_t)o * ldr + i], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    double v = acc[o];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+    if (lane == 0 && o < d_out) RHS[(size_t)o * ldr + j] -= v;
+  }
 }
 
 // nsys systems stored back to back (stride F*(F+d_out) doubles, each [G | C], destroyed); lambdas: nsys values on the HOST
@@ -309,21 +363,54 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
     syrk_update_kernel<<<dim3(tiles, tiles, nz), 256, SYRK_SMEM, ctx->stream>>>(GC, lda, F, k0, 2 * NBLK, k0 + 2 * NBLK, F, stride);
     ctx->launches += 2;
   }
+  // One large system: blocked triangular solves — diagonal blocks of SOLVE_KB rows by one CTA (per group of right-hand
+  // sides), the off-diagonal matrix-vector products by the whole machine.  Many / small systems: one CTA per system does both sweeps.
+  constexpr long long SOLVE_KB = 1024;
+  const bool blocked = nsys == 1 && F > 2 * SOLVE_KB && d_out <= 8;
+  const long long Fd = blocked ? SOLVE_KB : F;     // rows a diagonal-solve CTA keeps in shared memory
   // right-hand sides per CTA: as many (<= 4) as fit the shared-memory budget next to each other
   int rmax = 4;
-  while (rmax > 1 && ((size_t)rmax * F * sizeof(double) + 12 * 1024 > ctx->smem_optin || rmax / 2 >= d_out)) rmax /= 2;
-  const size_t smem = (size_t)rmax * F * sizeof(double);
+  while (rmax > 1 && ((size_t)rmax * Fd * sizeof(double) + 12 * 1024 > ctx->smem_optin || rmax / 2 >= d_out)) rmax /= 2;
+  const size_t smem = (size_t)rmax * Fd * sizeof(double);
   if (smem + 12 * 1024 > ctx->smem_optin) return fail(RCB_ERR_UNSUPPORTED, "feature count %lld too large for the triangular-solve kernel", (long long)F);
   const dim3 sgrid((unsigned)((d_out + rmax - 1) / rmax), 1, nz);
-  if (rmax == 4) {
-    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cholesky_solve_kernel<4><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
-  } else if (rmax == 2) {
-    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cholesky_solve_kernel<2><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
+  double* RHSp = GC + (size_t)lda * F;
+  auto diag = [&](long long r0, long long n, int mode) -> int32_t {
+    if (rmax == 4) {
+      RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cholesky_solve_kernel<4><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, n, RHSp, lda, d_out, W_out, stride, r0, F, mode);
+    } else if (rmax == 2) {
+      RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cholesky_solve_kernel<2><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, n, RHSp, lda, d_out, W_out, stride, r0, F, mode);
+    } else {
+      RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cholesky_solve_kernel<1><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, n, RHSp, lda, d_out, W_out, stride, r0, F, mode);
+    }
+    ctx->launches++;
+    return RCB_OK;
+  };
+  if (!blocked) {
+    RCB_TRY(diag(0, F, 0));
+    ctx->launches--;  // counted below
   } else {
-    RCB_CUDA(cudaFuncSetAttribute(cholesky_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cholesky_solve_kernel<1><<<sgrid, 1024, smem, ctx->stream>>>(GC, lda, F, GC + (size_t)lda * F, lda, d_out, W_out, stride);
+    for (long long r0 = 0; r0 < F; r0 += SOLVE_KB) {
+      const long long n = std::min<long long>(SOLVE_KB, F - r0);
+      RCB_TRY(diag(r0, n, 1));
+      const long long rest = F - r0 - n;
+      if (rest > 0) {
+        trsv_update_fwd_kernel<<<dim3((unsigned)((rest + 127) / 128), (unsigned)((n + 127) / 128)), 128, 0, ctx->stream>>>(GC, lda, F, r0, n, RHSp, lda, (int)d_out);
+        ctx->launches++;
+      }
+    }
+    for (long long r0 = (F - 1) / SOLVE_KB * SOLVE_KB; r0 >= 0; r0 -= SOLVE_KB) {
+      const long long n = std::min<long long>(SOLVE_KB, F - r0);
+      RCB_TRY(diag(r0, n, 2));
+      if (r0 > 0) {
+        trsv_update_bwd_kernel<<<dim3((unsigned)((r0 + 7) / 8)), 256, 0, ctx->stream>>>(GC, lda, r0, n, RHSp, lda, (int)d_out);
+        ctx->launches++;
+      }
+    }
+    ctx->launches--;
   }
   ctx->launches++;
   timer_end(ctx, RCB_TIMER_SOLVE);

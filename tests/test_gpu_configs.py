@@ -146,6 +146,43 @@ def test_c5_ensemble_n1024_members(R):
                 assert rel(W[b, l], Wo) <= 2e-3, (b, lam)
 
 
+def test_c5_batched_tensor_gram_is_exactly_psd(R, monkeypatch):
+    """The ensemble's Gram matrices on tensor cores (one launch sequence for all members, member = a dimension of the work
+    list): all nine digit products are kept, so the result is the exact Gram of the fixed-point states and the lambda = 1e-8
+    systems factor — no QR escalation, no indefinite (G + lambda I) (r02: dropping a3 a3' broke exactly these)."""
+    rng = np.random.default_rng(7)
+    N, T, w = 512, 2100, 100
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=1.0, sparsity=6 / N), state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(series[:, :T].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:T + 1].astype(np.float32))
+    B = 6
+    scales = np.linspace(0.5, 1.4, B).astype(np.float32)
+    leaks = np.linspace(0.2, 1.0, B).astype(np.float32)
+    lams = np.array([1e-8, 1e-5, 1e-2])
+    st0 = fixed_h0(R, st, esn, [np.zeros((N, B), np.float32)])
+    dev = R.default_device()
+    n0 = dev.launch_count()
+    Wt, _ = R.train_ensemble(esn, data, target, ps, st0, w_scale=scales, leak=leaks, lambdas=lams, washout=w, gram_mode=R.GRAM_TENSOR)
+    launches_tensor = dev.launch_count() - n0
+    Wf, _ = R.train_ensemble(esn, data, target, ps, st0, w_scale=scales, leak=leaks, lambdas=lams, washout=w, gram_mode=R.GRAM_FP64)
+    assert np.all(np.isfinite(Wt))
+    assert launches_tensor < 120          # one Gram launch sequence + one factorisation for all 18 systems (a QR escalation needs hundreds)
+    states, _ = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [np.zeros(N, np.float32)]))
+    for b in range(B):
+        for l, lam in enumerate(lams):
+            # same member, same lambda: predictions of both readouts on a common feature matrix
+            pt, pf = Wt[b, l] @ states[:, w:].astype(np.float64), Wf[b, l] @ states[:, w:].astype(np.float64)
+            assert rel(pt, pf) <= WEIGHT_RTOL, (b, lam)
+            if lam >= 1e-2:
+                assert rel(Wt[b, l], Wf[b, l]) <= 1e-3, (b, lam)
+    # several member groups give the same readouts as one
+    monkeypatch.setenv("RCB_MEMBERS_GROUP", "4")
+    Wg, _ = R.train_ensemble(esn, data, target, ps, st0, w_scale=scales, leak=leaks, lambdas=lams, washout=w, gram_mode=R.GRAM_FP64)
+    assert rel(Wg, Wf) <= 1e-9
+
+
 # ---- C2: N = 4096, one sequence — time-chunked against sequential on a 20 k prefix ---------------------------------------
 def test_c2_n4096_chunked_vs_sequential(R):
     rng = np.random.default_rng(4096)
@@ -169,3 +206,20 @@ def test_c2_n4096_chunked_vs_sequential(R):
         assert rel(yc, ys) <= WEIGHT_RTOL, lam         # radius 0.9: 0.9^500 ~ 1e-23, the chunks re-synchronise exactly in FP32
     # the weights themselves where the problem is well-posed against FP32 state rounding (cond * 1e-7 << 1e-4)
     assert rel(Wc[1.0], Ws[1.0]) <= 1e-3
+
+
+# ---- K3 at size: blocked Cholesky (DMMA trailing update) + blocked multi-CTA triangular solves -----------------------------
+@pytest.mark.parametrize("F,d_out", [(2304, 3), (4096, 1), (4100, 5)])
+def test_k3_large_solve_matches_lapack(R, F, d_out):
+    rng = np.random.default_rng(F)
+    A = rng.standard_normal((F, F + 64))
+    G = A @ A.T
+    C = rng.standard_normal((F, d_out))
+    GC = np.asfortranarray(np.concatenate([G, C], axis=1))
+    lam = 1e-3
+    W = R.ridge_solve(GC, d_out, lam)
+    import scipy.linalg as sla
+
+    Wref = sla.solve(G + lam * np.eye(F), C, assume_a="pos").T
+    assert rel(W, Wref) <= 1e-9
+    assert np.array_equal(GC[:, :F], G)  # the caller's accumulator is left intact
