@@ -169,10 +169,12 @@ def test_c5_batched_tensor_gram_is_exactly_psd(R, monkeypatch):
     Wf, _ = R.train_ensemble(esn, data, target, ps, st0, w_scale=scales, leak=leaks, lambdas=lams, washout=w, gram_mode=R.GRAM_FP64)
     assert np.all(np.isfinite(Wt))
     assert launches_tensor < 120          # one Gram launch sequence + one factorisation for all 18 systems (a QR escalation needs hundreds)
-    states, _ = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [np.zeros(N, np.float32)]))
     for b in range(B):
+        layer = O.ESNCellParams(input_matrix=ps.reservoir.input_matrix, reservoir_matrix=(ps.reservoir.reservoir_matrix * scales[b]).astype(np.float32),
+                                leak=float(leaks[b]), act=O.ACT_TANH, modifiers=((O.MOD_NLAT2, 0.0),))
+        states, _ = O.collectstates([layer], data, [np.zeros(N, np.float32)])
         for l, lam in enumerate(lams):
-            # same member, same lambda: predictions of both readouts on a common feature matrix
+            # same member, same lambda: predictions of both readouts on the member's own features
             pt, pf = Wt[b, l] @ states[:, w:].astype(np.float64), Wf[b, l] @ states[:, w:].astype(np.float64)
             assert rel(pt, pf) <= WEIGHT_RTOL, (b, lam)
             if lam >= 1e-2:
