@@ -320,7 +320,7 @@ def run_b200(args, w):
     e2e_value = units / (e2e_ms * 1e-3)
     ridge = None
     if not args.no_ridge:
-        ridge = ridge_leg(torch, R, L, lib, dev, h, w, u_chunks_dev, h0, carry, ring, rank, world, barrier)
+        ridge = ridge_leg(torch, R, L, lib, dev, h, w, u_host, h0, rank, world, barrier)
     pk = peaks()
     F = h.F
     alg_bytes = 4.0 * F * T * B + 4.0 * d_in * T * B  # state stream out + inputs in, per GPU per pass
@@ -565,81 +565,60 @@ def ncu_traffic(kernel_name):
     return d.get("bytes_per_launch") if kernel_name.startswith(d.get("kernel_prefix", "?")) else None
 
 
-def ridge_leg(torch, R, L, lib, dev, h, w, u_chunks, h0, carry, ring, rank, world, barrier):
-    """BASELINE metric, second half: ridge train time = one full pooled fit over this workload — per time chunk the
-    recurrence (K1) streams states into the ring and the tcgen05 Gram (K2) folds them into the FP64 [G | C]; then one
-    all-reduce of [G | C] across ranks (N > 1) and the FP64 Cholesky solve (K3).  Targets: next input (d_out = d_in)."""
-    N, d_in, B, T, Tc = w["N"], w["d_in"], w["B"], w["T"], w["chunk"]
+def ridge_leg(torch, R, L, lib, dev, h, w, u_host, h0, rank, world, barrier):
+    """BASELINE metric, second half: ridge train time = ONE library call, rcb_train_sharded (what `train` becomes when the
+    sequences shard over GPUs): per time window the recurrence (K1) streams states into HBM and the tcgen05 Gram (K2) folds
+    them into the FP64 [G | C]; then one NCCL all-reduce of the packed [G | C] issued by the library (N > 1) and the FP64
+    Cholesky solve (K3).  Targets: the inputs themselves (d_out = d_in), a stand-in of the right size.  lambda = 1e-6 per
+    sample -> RCB_GRAM_AUTO takes the tensor-core path."""
+    N, d_in, B, T = w["N"], w["d_in"], w["B"], w["T"]
     F, D = h.F, d_in
-    nchunks = len(u_chunks)
-    GC = torch.zeros((F + D, F), dtype=torch.float64, device="cuda")      # column-major F x (F + D)
-    Wout = torch.empty((F, D), dtype=torch.float64, device="cuda")        # column-major D x F
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    k1_ms = gram_ms = 0.0
-    packed = None
-    if world > 1:  # warm the NCCL channels for a reduction of this size
-        import torch.distributed as dist
-
-        packed = torch.zeros(int(lib.rcb_gc_packed_len(F, D)), dtype=torch.float64, device="cuda")
-        dist.all_reduce(packed)
-    barrier()
-    e[0].record()
-    carry.copy_(h0, non_blocking=True)
-    for c in range(nchunks):
-        tc = u_chunks[c].shape[1]
-        L.check(lib.rcb_collect(h.handle, L.ptr(u_chunks[c]), tc, B, L.ptr(carry), L.ptr(ring), L.ptr(carry)))
-        k1_ms += dev.kernel_ms(L.TIMER_RECURRENCE)
-        # targets of the chunk = the inputs themselves (shape d_in x tc x B, same memory order): a stand-in of the right size
-        L.check(lib.rcb_gram_accumulate(dev.handle, L.ptr(ring), 0, F, tc * B, F, L.ptr(u_chunks[c]), 0, D, D, L.GRAM_TENSOR,
-                                        1 if c == 0 else 0, L.ptr(GC)))
-        gram_ms += dev.kernel_ms(L.TIMER_GRAM)
-    e[1].record()
-    e_sync = torch.cuda.Event(enable_timing=True)
-    if world > 1:  # only the lower triangle of G (+ C) travels: pack -> all-reduce -> unpack
-        import torch.distributed as dist
-
-        # ranks reach this point up to a few per cent of the 3 s accumulation apart; a one-element all-reduce absorbs that
-        # skew so that allreduce_s is the exchange itself (the wait is reported as rank_skew_s; train_s contains both)
-        dist.all_reduce(torch.zeros(1, device="cuda"))
-        e_sync.record()
-        L.check(lib.rcb_gc_pack(dev.handle, L.ptr(GC), F, D, L.ptr(packed)))
-        dist.all_reduce(packed)
-        L.check(lib.rcb_gc_unpack(dev.handle, L.ptr(packed), F, D, L.ptr(GC)))
-    e[2].record()
-    lam = 1e-6 * T * B * world  # SURVEY 8d: lambda = 1e-6 (per sample)
-    L.check(lib.rcb_ridge_solve(dev.handle, L.ptr(GC), F, D, lam, L.ptr(Wout)))
-    e[3].record()
-    barrier()
-    t_acc, t_ar, t_solve = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
-    t_skew = 0.0
+    u_dev = torch.from_numpy(np.ascontiguousarray(u_host.transpose(2, 1, 0))).cuda()   # memory order (b, t, d) == column-major (d, t, b)
+    Wout = torch.empty((F, D), dtype=torch.float64, device="cuda")                    # column-major D x F
+    hT = torch.empty_like(h0)
+    washout = 100
+    lam = 1e-6 * (T - washout) * B * world
+    comm = R.comm_for(dev)            # collective on first use: the library's own NCCL communicator
+    if comm is not None:              # warm the NCCL channels for a reduction of this size
+        GCw = torch.zeros((F + D, F), dtype=torch.float64, device="cuda")
+        comm.allreduce_gc(GCw, D)
+        del GCw
+    best = None
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        L.check(lib.rcb_train_sharded(h.handle, comm.handle if comm else None, L.ptr(u_dev), L.ptr(u_dev), L.RCB_F32, T, B, washout, lam,
+                                      L.GRAM_AUTO, L.ptr(h0), L.ptr(Wout), L.ptr(hT)))
+        dt = time.perf_counter() - t0
+        tm = [dev.kernel_ms(i) for i in range(4)]
+        if best is None or dt < best[0]:
+            best = (dt, tm)
+    dt, (k1_ms, gram_ms, solve_ms, exch_ms) = best
     if world > 1:
         import torch.distributed as dist
 
-        t_skew = e[1].elapsed_time(e_sync)
-        t_ar -= t_skew
-        t = torch.tensor([t_acc + t_skew, t_ar, t_solve, k1_ms, gram_ms, t_skew], device="cuda")
+        t = torch.tensor([dt, k1_ms, gram_ms, solve_ms, exch_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # accumulation + wait is the same on every rank (they leave the sync together); t_skew: how long the fastest rank waited
-        t_acc, t_ar, t_solve, k1_ms, gram_ms, t_skew = [float(x) for x in t]
-    S = float(T) * B
+        dt, k1_ms, gram_ms, solve_ms, exch_ms = [float(x) for x in t]
+    S = float(T - washout) * B
     tiles = sum(1 for i in range((F + 255) // 256) for j in range((F + 255) // 256) if j * 256 <= i * 256 + 255) * 2
-    issued = 8.0 * 2.0 * tiles * 128 * 256 * S          # eight INT8 digit-plane MMAs (a1a1, a1a2, a2a1, a1a3, a3a1, a2a2, a2a3, a3a2) per tile per sample
+    nmma = 8.0   # lambda = 1e-6 per sample: the lowest-order digit product (a3 a3') is skipped, eight INT8 MMAs per tile per 32 samples
+    issued = nmma * 2.0 * tiles * 128 * 256 * S
     bf16 = 1590.0  # fallback of B200_PROFILING.md
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            bf16 = float(json.load(f).get("bf16_tflops", bf16))
+            pk = json.load(f)
+        bf16 = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", bf16)))
     ok = bool(torch.isfinite(Wout).all())
-    return {"train_s": (t_acc + t_ar + t_solve) * 1e-3, "recurrence_s": k1_ms * 1e-3, "gram_s": gram_ms * 1e-3, "allreduce_s": t_ar * 1e-3,
-            "rank_skew_s": t_skew * 1e-3,
-            "solve_s": t_solve * 1e-3, "features": F, "samples_per_gpu": S, "lambda": lam, "finite": ok,
+    return {"train_s": dt, "call": "rcb_train_sharded (one call: windows of K1 + K2, NCCL all-reduce inside the library, K3)",
+            "recurrence_s": k1_ms * 1e-3, "gram_s": gram_ms * 1e-3, "allreduce_s": exch_ms * 1e-3,
+            "allreduce_note": "device time of pack + ncclAllReduce + unpack on this rank's stream; includes the wait for the slowest rank",
+            "solve_s": solve_ms * 1e-3, "features": F, "samples_per_gpu": S, "lambda": lam, "finite": ok,
             "gram_algorithmic_tflops": (F * (F + 1) + 2 * F * D) * S / (gram_ms * 1e-3) / 1e12,
             "gram_issued_int8_tops": issued / (gram_ms * 1e-3) / 1e12,
-            "tensor_frac": {"of_nominal_int8_4500": issued / (gram_ms * 1e-3) / 1e12 / 4500.0,
-                            "of_twice_measured_bf16": issued / (gram_ms * 1e-3) / 1e12 / (2.0 * bf16),
-                            "note": "gram_s includes the HBM-bound max + digit-split pre-passes; ncu tensor-pipe % in profiles/"},
             "roofline": {"bound": "tensor", "achieved": issued / (gram_ms * 1e-3) / 1e12, "peak": 2.0 * bf16, "unit": "TOP/s",
                          "frac": issued / (gram_ms * 1e-3) / 1e12 / (2.0 * bf16),
-                         "peak_source": "2 x measured dense bf16 (INT8 runs at twice the bf16 rate; MEASURED_PEAKS.json)",
+                         "peak_source": "2 x measured SUSTAINED dense bf16 (INT8 runs at twice the bf16 rate; the Gram runs seconds under the power cap; MEASURED_PEAKS.json)",
                          "kernel": "gram_i8_kernel (+ colmax / split pre-passes inside the timed span)"},
             "gram_mode": "tcgen05 kind::i8, 3 balanced base-256 digit planes, exact INT32 TMEM accumulation, FP64 across"}
 

@@ -886,7 +886,8 @@ static int32_t gram_device(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, 
   // fixed-point tensor path at ~250 with ~1 ms of pre-pass overhead — they cross near 1e10); the exact FP64 kernel
   // below that, for FP64 data, and whenever RCB_GRAM_FP64 is asked for.  RCB_GRAM=fp64|tensor overrides AUTO.
   const double macs = (double)F * (double)F * (double)(T - washout) * (double)nseq;
-  bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10);
+  bool tensor = gram_mode == RCB_GRAM_TENSOR ||
+                (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10 && ctx->gram_lambda_hint >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE);
   if (gram_mode == RCB_GRAM_AUTO) {
     const char* ov = getenv("RCB_GRAM");
     if (ov && !strcmp(ov, "fp64")) tensor = false;
@@ -1079,6 +1080,7 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
   if (!states || !targets) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   RCB_TRY(rcbi_check_fit_mode(gram_mode));
   RCB_CUDA(cudaSetDevice(ctx->device));
+  LambdaHint hint(ctx, lambda, (double)S_states);
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
   void* w_dev = nullptr;
@@ -1242,6 +1244,7 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
   timers_reset(ctx);
   const int64_t F = esn->feat, d_out = esn->desc.out_dims;
   RCB_TRY(rcbi_check_fit_mode(gram_mode));
+  LambdaHint hint(ctx, lambda, (double)(T - washout) * (double)B);
   void* gc = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
   void* w_dev = nullptr;
@@ -1281,6 +1284,7 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   rcb_ctx* ctx = esn->ctx;
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
+  LambdaHint hint(ctx, *std::min_element(lambdas, lambdas + n_lambda), (double)(T - washout));
   const size_t esz = esn->desc.data_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
   const int64_t F = esn->feat, d_out = esn->desc.out_dims, d_in = esn->desc.in_dims, sumN = esn->sumN;
   const void* u_dev = nullptr;
@@ -1331,7 +1335,8 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
         // Tensor cores take the whole group in ONE launch sequence (member = a dimension of the work list): the F^2 S
         // threshold of RCB_GRAM_AUTO then counts the group's contraction, not a single member's.
         const double macs = (double)F * (double)F * (double)(T - washout) * (double)ng;
-        bool tensor = gram_mode == RCB_GRAM_TENSOR || (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10);
+        bool tensor = gram_mode == RCB_GRAM_TENSOR ||
+                      (gram_mode == RCB_GRAM_AUTO && F >= 256 && macs >= 3e10 && ctx->gram_lambda_hint >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE);
         if (gram_mode == RCB_GRAM_AUTO) {
           const char* ov = getenv("RCB_GRAM");
           if (ov && !strcmp(ov, "fp64")) tensor = false;

@@ -141,9 +141,11 @@ int32_t allmerge_rq_device(rcb_comm* c, double* rq_dev, int64_t F, int64_t d_out
 // partial accumulate (this rank's data) -> exchange -> replicated solve, with the AUTO escalation of rcb_train kept
 // collective-safe: every rank walks the same mode list and sees the same solver status (the reduced system is identical).
 template <typename Accumulate>
-int32_t sharded_fit(rcb_esn* esn, rcb_comm* comm, double lambda, int32_t gram_mode, double* W_out, Accumulate&& accumulate) {
+int32_t sharded_fit(rcb_esn* esn, rcb_comm* comm, double lambda, double samples_total, int32_t gram_mode, double* W_out,
+                    Accumulate&& accumulate) {
   rcb_ctx* ctx = esn->ctx;
   const int64_t F = esn->feat, d_out = esn->desc.out_dims;
+  LambdaHint hint(ctx, lambda, samples_total);
   void *gc = nullptr, *w_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_GC, (size_t)F * (F + d_out) * sizeof(double), &gc));
   const size_t w_bytes = (size_t)d_out * F * sizeof(double);
@@ -331,7 +333,9 @@ int32_t rcb_train_sharded(rcb_esn* esn, rcb_comm* comm, const void* u, const voi
   rcb_ctx* ctx = esn->ctx;
   RCB_CUDA(cudaSetDevice(ctx->device));
   timers_reset(ctx);
-  return sharded_fit(esn, comm, lambda, gram_mode, W_out, [&](int32_t mode, double* gc) {
+  // samples of the pooled fit: every rank holds T - washout per sequence (ragged shards differ by one sequence at most)
+  const double samples = (double)(T - washout) * (double)B_local * (double)(comm ? comm->world : 1);
+  return sharded_fit(esn, comm, lambda, samples, gram_mode, W_out, [&](int32_t mode, double* gc) {
     return rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B_local, washout, mode, h0, gc, nullptr, hT_out, true);
   });
 }
@@ -376,7 +380,7 @@ int32_t rcb_train_time_chunked(rcb_esn* esn, rcb_comm* comm, const void* u, cons
   RCB_TRY(ctx_scratch(ctx, SCR_CHUNK_YW, (size_t)std::max<int64_t>(nb * L, rem + overlap) * d_out * ysz + 16, &yw));
   RCB_TRY(ctx_scratch(ctx, SCR_HT, (size_t)sumN * std::max<int64_t>(nb, 1) * esz, &hT_dev));
   RCB_CUDA(cudaMemsetAsync(hT_dev, 0, (size_t)sumN * esz, ctx->stream));
-  int32_t st = sharded_fit(esn, comm, lambda, gram_mode, W_out, [&](int32_t mode, double* gc) -> int32_t {
+  int32_t st = sharded_fit(esn, comm, lambda, (double)(T - washout), gram_mode, W_out, [&](int32_t mode, double* gc) -> int32_t {
     RCB_CUDA(cudaMemsetAsync(gc, 0, (size_t)esn->feat * (esn->feat + d_out) * sizeof(double), ctx->stream));
     if (nb > 0) {
       // window c starts `overlap` steps before its own samples; consecutive windows start Tc steps apart (and overlap): one gather

@@ -35,6 +35,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "rcb_internal.h"
@@ -52,6 +53,7 @@ constexpr int EPI_WARPS = 8;                           // two per TMEM lane quad
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int CR = 2, CLUSTER = CR;                    // CTA pair: rows 2I, 2I+1 of 128 share the 256 B columns
 constexpr int NPHASE = 3;
+constexpr int CK = 3;                                  // sample blocks per stage in phase C (CK * 3 * BOX <= STAGE_BYTES)
 constexpr int MAX_RANGE = 32768;                       // samples per accumulation: 3 * 128 * 128 * 32768 < 2^31
 
 struct GramParams8 {
@@ -64,6 +66,7 @@ struct GramParams8 {
   long long per_split;        // samples per K-range, multiple of KB, <= MAX_RANGE
   double* G;                  // F x F column-major, lower triangle accumulated
   long long ldo, F;
+  const int* nphase;          // device flag written by phase_select_kernel: 3 = all nine digit products, 2 = a3 a3' skipped
   int nmem;                   // independent problems stacked in the work list (ensemble members): item -> (member, split, tile)
   long long q8_stride;        // bytes between the members' digit planes
   long long g_stride;         // doubles between the members' G
@@ -173,6 +176,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
   const uint16_t mask_self = (uint16_t)(1u << ri), mask_all = (uint16_t)((1u << CR) - 1u);
   const long long per_mem = (long long)p.ntiles * p.splits;
   const long long nitems = per_mem * p.nmem;
+  const int nphase = __ldg(p.nphase);
 
   if (warp == 0) {
     // ===== producer: two contiguous bulk copies per stage =====
@@ -188,21 +192,35 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
         const int nst = (int)((s_end - s_beg + KB - 1) / KB);
         const long long fa = (long long)tl.x * CR + ri, fb = (long long)tl.y * 2 + ri;   // my A block; the B block I fetch
         const unsigned char* q8m = p.q8 + (size_t)mem * p.q8_stride;
-        for (int phase = 0; phase < NPHASE; ++phase) {
-          const uint32_t bytes = phase == 2 ? BOX : BLK;   // all three digit planes of a 128-feature block; phase C: the third only
-          const uint32_t poff = phase == 2 ? 2 * BOX : 0;
-          for (int st = 0; st < nst; ++st, ++it) {
+        for (int phase = 0; phase < nphase; ++phase) {
+          // phases A, B: one 32-sample block per stage, all three digit planes of a 128-feature block (BLK bytes per copy).
+          // phase C needs the third plane only: a stage carries CK consecutive sample blocks [A3 | B3 block 0 | B3 block 1],
+          // so that the stage hand-off is amortised over CK MMAs like in the other phases.
+          const int kper = phase == 2 ? CK : 1;
+          for (int st = 0; st < nst; st += kper, ++it) {
             const int slot = (int)(it % STAGES);
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             const long long w0 = clock64();
             mbar_wait(empty0 + 8 * slot, ph ^ 1u, p.err);  // both CTAs of the pair have released the slot
             wait_acc += clock64() - w0;
             const uint32_t fbar = full0 + 8 * slot;
-            mbar_expect_tx(fbar, 3 * bytes);               // bytes landing in MY shared memory: A + two B blocks
-            const uint32_t sa = base + slot * STAGE_BYTES; // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]
-            const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
-            bulk_load_mc(sa + poff, blk + (size_t)fa * BLK + poff, bytes, fbar, mask_self);
-            bulk_load_mc(sa + BLK + (uint32_t)ri * BLK + poff, blk + (size_t)fb * BLK + poff, bytes, fbar, mask_all);
+            const uint32_t sa = base + slot * STAGE_BYTES;
+            if (phase < 2) {
+              mbar_expect_tx(fbar, 3 * BLK);               // bytes landing in MY shared memory: A + two B blocks
+              // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]
+              const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
+              bulk_load_mc(sa, blk + (size_t)fa * BLK, BLK, fbar, mask_self);
+              bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, BLK, fbar, mask_all);
+            } else {
+              const int nk = nst - st < CK ? nst - st : CK;
+              mbar_expect_tx(fbar, (uint32_t)nk * 3 * BOX);
+              for (int kk = 0; kk < nk; ++kk) {
+                const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st + kk) * p.nfb) * BLK + 2 * BOX;
+                const uint32_t sk = sa + (uint32_t)kk * 3 * BOX;
+                bulk_load_mc(sk, blk + (size_t)fa * BLK, BOX, fbar, mask_self);
+                bulk_load_mc(sk + BOX + (uint32_t)ri * BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_all);
+              }
+            }
           }
         }
       }
@@ -217,12 +235,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
         const long long s_beg = split * p.per_split;
         const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
         const int nst = (int)((s_end - s_beg + KB - 1) / KB);
-        for (int phase = 0; phase < NPHASE; ++phase, ++ci) {
+        for (int phase = 0; phase < nphase; ++phase, ++ci) {
           const long long w0 = clock64();
           mbar_wait(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);  // the epilogue has drained the previous accumulators
           wtm += clock64() - w0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int st = 0; st < nst; ++st, ++it) {
+          const int kper = phase == 2 ? CK : 1;
+          for (int st = 0; st < nst; st += kper, ++it) {
             const int slot = (int)(it % STAGES);
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             const long long w1 = clock64();
@@ -230,21 +249,27 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             wfull += clock64() - w1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = base + slot * STAGE_BYTES;
-            const uint64_t A1 = umma_desc(sa, BLK), A2 = umma_desc(sa + BOX, BLK), A3 = umma_desc(sa + 2 * BOX, BLK);
-            const uint64_t B1 = umma_desc(sa + BLK, BLK), B2 = umma_desc(sa + BLK + BOX, BLK), B3 = umma_desc(sa + BLK + 2 * BOX, BLK);
             const uint32_t acc = st > 0 ? 1u : 0u;
-            if (phase == 0) {
-              umma_i8(tmem_base, A1, B2, IDESC, acc);          // acc3 = a1 a2' + a2 a1'
-              umma_i8(tmem_base, A2, B1, IDESC, 1u);
-              umma_i8(tmem_base + TN, A1, B3, IDESC, acc);     // acc4 = a1 a3' + a3 a1' + a2 a2'
-              umma_i8(tmem_base + TN, A3, B1, IDESC, 1u);
-              umma_i8(tmem_base + TN, A2, B2, IDESC, 1u);
-            } else if (phase == 1) {
-              umma_i8(tmem_base, A1, B1, IDESC, acc);          // acc2 = a1 a1'
-              umma_i8(tmem_base + TN, A2, B3, IDESC, acc);     // acc5 = a2 a3' + a3 a2'
-              umma_i8(tmem_base + TN, A3, B2, IDESC, 1u);
+            if (phase < 2) {
+              const uint64_t A1 = umma_desc(sa, BLK), A2 = umma_desc(sa + BOX, BLK), A3 = umma_desc(sa + 2 * BOX, BLK);
+              const uint64_t B1 = umma_desc(sa + BLK, BLK), B2 = umma_desc(sa + BLK + BOX, BLK), B3 = umma_desc(sa + BLK + 2 * BOX, BLK);
+              if (phase == 0) {
+                umma_i8(tmem_base, A1, B2, IDESC, acc);          // acc3 = a1 a2' + a2 a1'
+                umma_i8(tmem_base, A2, B1, IDESC, 1u);
+                umma_i8(tmem_base + TN, A1, B3, IDESC, acc);     // acc4 = a1 a3' + a3 a1' + a2 a2'
+                umma_i8(tmem_base + TN, A3, B1, IDESC, 1u);
+                umma_i8(tmem_base + TN, A2, B2, IDESC, 1u);
+              } else {
+                umma_i8(tmem_base, A1, B1, IDESC, acc);          // acc2 = a1 a1'
+                umma_i8(tmem_base + TN, A2, B3, IDESC, acc);     // acc5 = a2 a3' + a3 a2'
+                umma_i8(tmem_base + TN, A3, B2, IDESC, 1u);
+              }
             } else {
-              umma_i8(tmem_base, A3, B3, IDESC, acc);          // acc6 = a3 a3'
+              const int nk = nst - st < CK ? nst - st : CK;
+              for (int kk = 0; kk < nk; ++kk) {                  // acc6 = a3 a3' over the CK sample blocks of the stage
+                const uint32_t sk = sa + (uint32_t)kk * 3 * BOX;
+                umma_i8(tmem_base, umma_desc(sk, BOX), umma_desc(sk + BOX, BOX), IDESC, (acc | (uint32_t)kk) ? 1u : 0u);
+              }
             }
             umma_commit_mc(empty0 + 8 * slot, mask_all);       // tells both producers that fill my stage it is free
           }
@@ -267,7 +292,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
       const double* sfm = p.sf + mem * (p.nfb * 128);
       double* Gm = p.G + (size_t)mem * p.g_stride;
       const double sfi = gi < p.F ? __ldg(sfm + gi) : 0.0;
-      for (int phase = 0; phase < NPHASE; ++phase, ++ci) {
+      for (int phase = 0; phase < nphase; ++phase, ++ci) {
         const long long w0 = clock64();
         mbar_wait(tfull, (uint32_t)(ci & 1), p.err);
         wepi += clock64() - w0;
@@ -449,6 +474,27 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
   }
 }
 
+// Phase C (a3 a3') costs a fifth of the kernel (a third sweep over K, L2-fill bound) and only matters when lambda is not far
+// above the term it restores: || sum_s a3 a3' ||_2 <~ 1.2e-8 S s_max^2 (a3 uniform in [-128, 127], Marchenko-Pastur edge),
+// s_max = 2^e_max the largest feature scale.  With lambda >= 1e-6 s_max^2 PER SAMPLE the term is below 2 % of lambda: skipped.
+// lambda unknown (< 0): all nine products.
+__global__ void phase_select_kernel(const int* __restrict__ amax, long long n, double lambda, int* nphase) {
+  __shared__ int smax;
+  if (threadIdx.x == 0) smax = 0;
+  __syncthreads();
+  int mx = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = max(mx, amax[i]);
+  atomicMax(&smax, mx);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float m = __int_as_float(smax);
+    int e = 0;
+    if (m > 0.f && m < INFINITY) frexpf(m, &e);
+    const double s2 = ldexp(1.0, 2 * e);
+    *nphase = (lambda >= 0.0 && lambda >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE * s2) ? 2 : 3;   // lambda is per sample
+  }
+}
+
 }  // namespace
 
 // G(F x F, ld = ldo, FP64, lower triangle) += Z Z' over {b*T + t : b < nseq, washout <= t < T}; Z is FP32, device.
@@ -463,16 +509,25 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   const long long Te = T - washout, Stot = Te * nseq;
   if (Stot <= 0) return RCB_OK;
   const long long ldp = (F + 255) / 256 * 256;   // whole 256 x 256 super-tiles
+  // Work-list order = L2 residency.  The ~74 clusters that run at the same time take consecutive entries; laid out row by
+  // row of the triangle they would share one A panel and stream ~32 different B panels each (r01 ncu: 28x the bytes of the
+  // digit planes read from DRAM, 54 % of the HBM peak next to a tensor pipe at 80 %).  Entries are therefore grouped into
+  // RB x RB blocks of super-tiles: a wave then touches 2 RB panels, every panel slice is fetched from DRAM by the first of
+  // the RB tiles that need it and found in L2 by the others (the clusters of a wave advance through K in step).
   std::vector<int2> tiles;
   const int nt = (int)(ldp / 256);
-  for (int i = 0; i < nt; ++i)
-    for (int j = 0; j <= i; ++j) tiles.push_back(make_int2(i, j));
+  int RB = 6;   // measured at F = 8192 (r02): row-major 74.1 ms, RB 4 / 6 / 8: 75.6 / 73.1 / 78.9 ms — the kernel is not DRAM-bound
+  if (const char* e = getenv("RCB_GRAM_RASTER")) RB = atoi(e) > 0 ? atoi(e) : nt;  // testing hook (a huge value: row-major order)
+  for (int bi = 0; bi < nt; bi += RB)
+    for (int bj = 0; bj <= bi; bj += RB)
+      for (int i = bi; i < std::min(bi + RB, nt); ++i)
+        for (int j = bj; j < std::min(bj + RB, nt) && j <= i; ++j) tiles.push_back(make_int2(i, j));
   const int ntiles = (int)tiles.size();
   void* d_tiles = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_TILES, tiles.size() * sizeof(int2) + 16, &d_tiles));
   RCB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   int* d_err = reinterpret_cast<int*>((char*)d_tiles + tiles.size() * sizeof(int2));
-  RCB_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  RCB_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));
   // sample sub-chunks: the digit planes (3 B per state) stay within 6 GiB
   long long Ssub = ((long long)6 << 30) / (ldp * PLANES * nmem);
   if (const char* ov = getenv("RCB_GRAM_SUB_SAMPLES")) Ssub = atoll(ov);  // testing hook: force several sub-chunks
@@ -487,6 +542,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   RCB_TRY(ctx_scratch(ctx, SCR_ZLO, (size_t)ldp * nmem * (sizeof(double) + sizeof(int)), &aux));
   double* sf = reinterpret_cast<double*>(aux);
   int* amax = reinterpret_cast<int*>(sf + ldp * nmem);
+  int* d_nphase = d_err + 1;
   int ncl_max = 0;
   {
     cudaLaunchConfig_t cfg = {};
@@ -528,6 +584,13 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     p.tiles = (const int2*)d_tiles; p.ntiles = ntiles; p.q8 = (const unsigned char*)q8; p.sf = sf; p.nfb = ldp / 128;
     p.S = Sc; p.G = G; p.ldo = ldo; p.F = F; p.err = d_err;
     p.nmem = (int)nmem; p.q8_stride = q8_stride; p.g_stride = g_stride;
+    {
+      double lam = ctx->gram_lambda_hint;
+      if (const char* e = getenv("RCB_GRAM_PHASES")) lam = atoi(e) == 2 ? 1e300 : -1.0;  // testing hook: force 2 / 3 phases
+      phase_select_kernel<<<1, 1024, 0, ctx->stream>>>(amax, ldp * nmem, lam, d_nphase);
+      ctx->launches++;
+    }
+    p.nphase = d_nphase;
     if (prof) cudaMemsetAsync(prof_dev, 0, 148 * 5 * sizeof(long long), ctx->stream);
     p.prof = prof ? prof_dev : nullptr;
     // K-ranges: at most MAX_RANGE samples (exact INT32 accumulation), and enough of them to fill the last round of clusters
