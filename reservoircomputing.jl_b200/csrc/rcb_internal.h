@@ -81,9 +81,13 @@ struct HostSell;
 //   slab k of warp w (width wd slots) = wd/4 quads, then a pair if wd & 2, then a single if wd & 1
 //     quad:   float4 vals[32] (lane-major, 512 B) | 4 x uint16 cols[32] (256 B)
 //     pair:   float2 vals[32] (256 B)             | 2 x uint16 cols[32] (128 B)
-//     single: float  vals[32] (128 B)             | uint16 cols[32] (64 B)
+//     single: float  vals[32] (128 B)             | uint16 cols[32] (64 B) | 64 B of padding
+// Every piece is a multiple of 128 B, so with a 128-byte-aligned base every 32-lane load of the walk covers whole
+// L1 lines (r02: the 192-byte singles used to leave the rest of a warp's stream 64 B off and the loads of the walk cost
+// 6.6 k data-pipe wavefronts per CTA-step of the C3 kernel against 3.4 k for the bytes they return).
 // The R widths of a warp are packed 4 bits each into one 64-bit word (R <= 16, width <= 15); nothing else
 // is fetched per slab.
+constexpr int RCB_STREAM_SINGLE_BYTES = 256;
 struct HostFast {
   bool ok = false;  // false: pattern does not fit the format (kernel falls back to the generic one)
   int32_t n = 0, nthreads = 0, R = 0, nwarps = 0;

@@ -241,6 +241,10 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
   const float* u_g = reinterpret_cast<const float*>(p.u);
   const float* h0_g = reinterpret_cast<const float*>(p.h0);
 
+  // global loads ahead of tcgen05.alloc: keeps the global-memory descriptor in a uniform register for the whole kernel
+  // (see recurrence_fast7.cu; otherwise two R2UR in front of every LDG / STG of the time loop)
+  const uint32_t woff = fa.warp_off[warp];
+  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab
   uint32_t ta = 0, tmem_base = 0;
   if constexpr (TMEM) {
     if (warp == 0) {
@@ -291,8 +295,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  const unsigned char* wbase = (WS ? stage : fa.stream) + fa.warp_off[warp];
-  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab
+  const unsigned char* wbase = (WS ? stage : fa.stream) + woff;
   const bool use_mscale = !SIMPLE && p.member_scale != nullptr, use_mleak = !SIMPLE && p.member_leak != nullptr;
   float* out_g = reinterpret_cast<float*>(p.states);
   const int F = p.raw ? p.n : p.feat;
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(1024, 1) k1_fast_kernel(const RecParams p, con
       if (wd & 1) {
         const float v = ldw32f<WS>(wp + lane * 4);
         const uint32_t c = ldw16u<WS>(wp + 128 + lane * 2);
-        wp += 192;
+        wp += RCB_STREAM_SINGLE_BYTES;
         gather1<NB>(A, cur, npad, v, c);
       }
       float2 hp[NPA];

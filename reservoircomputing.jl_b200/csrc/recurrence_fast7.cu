@@ -27,7 +27,10 @@ struct Fast7Args {
   const unsigned char* stream;  // HostFast layout with 16-bit column*4
   const uint32_t* warp_off;
   const uint64_t* wwords;
-  const float4* Win4;           // [npos] (w_in[0], w_in[1], w_in[2], 0) by position
+  const float4* Win4;           // [npos] (w_in[0], w_in[1], w_in[2], 0) by position (the 512-thread schedule only)
+  const float* Win;             // [d_in][npos] planes by position: 12 B per row instead of 16 (every global byte costs the LSU
+                                // data pipe twice, request and fill: r02 ncu, 7.1 k of 29 k wavefronts per CTA-step are global)
+  int npos;
   const uint16_t* perm;         // [npos] position -> row of the schedule this stream was built with
   float2 lc2, oml2, m2l2;       // (a, a), (1-a, 1-a), (-2a, -2a): packed operands straight from the constant bank
 };
@@ -125,6 +128,12 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   const float* u_g = reinterpret_cast<const float*>(p.u);
   const float* h0_g = reinterpret_cast<const float*>(p.h0);
 
+  // These global loads stay AHEAD of tcgen05.alloc on purpose: when the kernel's first global access comes after the
+  // allocation (ptxas expands it into a loop with a call to a trap stub), ptxas keeps the global-memory descriptor in a
+  // vector register pair and re-materialises it with two R2UR in front of every LDG / STG of the time loop (84 R2UR in the
+  // SASS, 5.9 k of the 81 k warp-instructions per CTA-step in r01); with a load up here it lives in a uniform register.
+  const unsigned char* wbase = fa.stream + fa.warp_off[warp];
+  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab, R <= 16
   if (warp == 0) {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(tm_s);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "r"(512u) : "memory");
@@ -168,8 +177,6 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
-  const unsigned char* wbase = fa.stream + fa.warp_off[warp];
-  const unsigned long long wword0 = fa.wwords[2 * warp], wword1 = fa.wwords[2 * warp + 1];  // 8 bits per slab, R <= 16
   float* out_g = reinterpret_cast<float*>(p.states);
   const size_t seq_stride = (size_t)p.T * NPAD;        // F == N for both modifiers handled here
   const bool even = (tid & 1) == 0;
@@ -240,11 +247,17 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       float2 wxy = make_float2(0.f, 0.f);
       float wzz = 0.f;
       if constexpr (DIN == 3) {
-        const float4 w4 = __ldg(fa.Win4 + k * NT + tid);  // one 128-bit load: every global access costs two extra R2UR here
-        wxy = make_float2(w4.x, w4.y);
-        wzz = w4.z;
+        if constexpr (NT == 1024) {
+          const float* wq = fa.Win + k * NT + tid;
+          wxy = make_float2(__ldg(wq), __ldg(wq + fa.npos));
+          wzz = __ldg(wq + 2 * fa.npos);
+        } else {
+          const float4 w4 = __ldg(fa.Win4 + k * NT + tid);
+          wxy = make_float2(w4.x, w4.y);
+          wzz = w4.z;
+        }
       } else {
-        wxy.x = __ldg(reinterpret_cast<const float*>(fa.Win4 + k * NT + tid));
+        wxy.x = __ldg(fa.Win + k * NT + tid);
       }
       float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
       float a3 = 0.f;
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       if (wd & 1) {
         const float v = ldg32f(wp + lane * 4);
         const uint32_t c = ldg16u(wp + 128 + lane * 2);
-        wp += 192;
+        wp += RCB_STREAM_SINGLE_BYTES;
         gather7<NPAD>(a0, a1, a2, a3, tile, v, c);
       }
       {  // the next slab's stream starts at wp (the first slab of the next step at wbase): fetch its first quad now
@@ -387,7 +400,7 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
   const char* mode = getenv("RCB_K1_MODE");  // testing hook: fast7 | fast7_512 (or unset) use this kernel, anything else skips it
   const bool want512 = mode && !strcmp(mode, "fast7_512");  // 512 threads x 128 registers: measured 10 % slower than 1024 x 64
   if (mode && strcmp(mode, "fast7") && !want512) return RCB_OK;
-  if (!f4.ok || !Win4 || p.pre_in || (p.d_in != 3 && p.d_in != 1) || p.nthreads != 1024) return RCB_OK;
+  if (!f4.ok || !Win4 || !p.Win || p.pre_in || (p.d_in != 3 && p.d_in != 1) || p.nthreads != 1024) return RCB_OK;
   if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.bias || p.leakv || p.member_scale || p.member_leak) return RCB_OK;
   if (p.n != p.npad || (p.npad != 8192 && p.npad != 4096)) return RCB_OK;
   if (p.B <= (long long)(NB - 1) * ctx->sm_count) return RCB_OK;  // fewer sequences: smaller tiles fill the machine better
@@ -397,8 +410,8 @@ int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4
   const float lc = (float)p.leak, oml = 1.0f - lc, m2l = -2.0f * lc;  // (1-a) in the input eltype, esn_cell.jl:186-200
   const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192 && p.d_in == 3;
   Fast7Args fa{half ? f4h.stream : f4.stream, half ? f4h.warp_off : f4.warp_off, half ? f4h.wwords : f4.wwords,
-               reinterpret_cast<const float4*>(half ? Win4h : Win4), half ? permh : p.perm, make_float2(lc, lc), make_float2(oml, oml),
-               make_float2(m2l, m2l)};
+               reinterpret_cast<const float4*>(half ? Win4h : Win4), p.Win, p.npos, half ? permh : p.perm, make_float2(lc, lc),
+               make_float2(oml, oml), make_float2(m2l, m2l)};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   int32_t st;
   if (p.d_in == 3) {

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(1024, 1) k1_single_kernel(const RecParams p, c
       if (wd & 1) {
         const float v = *reinterpret_cast<const float*>(wp + lane * 4);
         const uint32_t c = (uint32_t)*reinterpret_cast<const unsigned short*>(wp + 128 + lane * 2);
-        wp += 192;
+        wp += RCB_STREAM_SINGLE_BYTES;
         acc0 = fmaf(v, *reinterpret_cast<const float*>(cur + c), acc0);
       }
       float x = acc0 + acc1;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(1024, 1) k4_auto_kernel(const AutoArgs a) {
       if (wd & 1) {
         const float v = *reinterpret_cast<const float*>(wp + lane * 4);
         const uint32_t c = (uint32_t)*reinterpret_cast<const unsigned short*>(wp + 128 + lane * 2);
-        wp += 192;
+        wp += RCB_STREAM_SINGLE_BYTES;
         acc0 = fma((T)v, *reinterpret_cast<const T*>(cur + (c << CSH)), acc0);
       }
       T x = acc0 + acc1;

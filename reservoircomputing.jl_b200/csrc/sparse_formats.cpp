@@ -246,7 +246,9 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
   // the residue balance room at the price of one padded entry each.  The cost below therefore charges a shorter row
   // (1000 per missing entry) far less than an extra slot (1e6) but far more than unevenness (10 per squared count):
   // at N = 8192, 6 non-zeros per column this brings the padding from 21 % down to 4 %.
-  const int WINDOW = 4096, SLACK = 4;
+  int WINDOW = 4096, SLACK = 4;
+  if (const char* e = getenv("RCB_SCHED_WINDOW")) WINDOW = atoi(e);  // testing hooks
+  if (const char* e = getenv("RCB_SCHED_SLACK")) SLACK = atoi(e);
   // a second row of the same residue in a group costs one extra wavefront in each write-back store of the new state
   long OWNW = 2500L;
   if (const char* e = getenv("RCB_SCHED_OWN")) OWNW = atol(e);  // testing hook
@@ -416,7 +418,7 @@ int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out, i
     for (int32_t k = 0; k < sell.R; ++k) {
       const int32_t wd = sell.blk_w[(size_t)(k * sell.nwarps + w)];
       out->wwords[(size_t)w * 2 + (k >> 3)] |= (uint64_t)wd << (8 * (k & 7));
-      total += (size_t)(wd >> 2) * 768 + (size_t)((wd >> 1) & 1) * 384 + (size_t)(wd & 1) * 192;
+      total += (size_t)(wd >> 2) * 768 + (size_t)((wd >> 1) & 1) * 384 + (size_t)(wd & 1) * RCB_STREAM_SINGLE_BYTES;
     }
   }
   if (total > 0xFFFFFFF0ull) return RCB_OK;
@@ -437,7 +439,7 @@ int32_t fast_from_csr(const HostCsr& csr, const HostSell& sell, HostFast* out, i
             v[cnt * l + i] = sell.vals[at];
             c[cnt * l + i] = (uint16_t)(sell.cols[at] * col_scale);
           }
-        p += (size_t)cnt * 192;
+        p += cnt == 1 ? (size_t)RCB_STREAM_SINGLE_BYTES : (size_t)cnt * 192;
         j += cnt;
       };
       for (int32_t q = 0; q < (wd >> 2); ++q) emit(4);
