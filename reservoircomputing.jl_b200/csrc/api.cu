@@ -1357,16 +1357,22 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
           timer_end(ctx, RCB_TIMER_GRAM);
           RCB_TRY(sg);
         } else {
-          for (int64_t m = 0; m < ng; ++m) {
-            const int64_t b = g0 + m;
-            const void* Zb = (const char*)st_dev + (size_t)b * T * F * esz;
-            const void* Yb = (const char*)y_dev + (size_t)(b0 + b) * T * d_out * ysz;
-            RCB_CUDA(cudaMemsetAsync(gc, 0, gc_elems * sizeof(double), ctx->stream));
-            RCB_TRY(gram_device(ctx, Zb, esn->desc.data_dtype, F, F, Yb, targets_dtype, d_out, d_out, T, washout, 1,
-                                gram_mode == RCB_GRAM_AUTO ? RCB_GRAM_FP64 : gram_mode, (double*)gc));
-            RCB_CUDA(cudaMemcpy2DAsync((double*)work + (size_t)m * n_lambda * slot_elems, (size_t)ldw * sizeof(double), gc, (size_t)F * sizeof(double),
-                                       (size_t)F * sizeof(double), (size_t)(F + d_out), cudaMemcpyDeviceToDevice, ctx->stream));
-          }
+          // exact FP64 Gram of every member of the group in two batched launches (G on the FP64 tensor path, the thin cross
+          // term C = Z Y' in the CUDA-core kernel), straight into each member's first lambda slot
+          ctx->last_gram_tensor = 0;
+          GramArgs g;
+          g.A = (const char*)st_dev + (size_t)g0 * T * F * esz; g.a_dtype = esn->desc.data_dtype; g.M = F; g.lda = F;
+          g.Bm = g.A; g.b_dtype = g.a_dtype; g.Nc = F; g.ldb = F;
+          g.T = T; g.washout = washout; g.nseq = 1; g.out = (double*)work; g.ldo = ldw; g.lower_only = true;
+          g.nbatch = ng; g.a_bstride = T * F; g.b_bstride = T * F; g.o_bstride = (int64_t)slot_elems * n_lambda;
+          GramArgs c = g;
+          c.Bm = (const char*)y_dev + (size_t)(b0 + g0) * T * d_out * ysz; c.b_dtype = targets_dtype; c.Nc = d_out; c.ldb = d_out;
+          c.b_bstride = T * d_out; c.out = (double*)work + (size_t)ldw * F; c.lower_only = false;
+          timer_begin(ctx, RCB_TIMER_GRAM);
+          int32_t sg = launch_gram_fp64(ctx, g);
+          if (sg == RCB_OK) sg = launch_gram_fp64(ctx, c);
+          timer_end(ctx, RCB_TIMER_GRAM);
+          RCB_TRY(sg);
         }
         if (n_lambda > 1) RCB_TRY(launch_replicate_blocks(ctx, (double*)work, (int64_t)slot_elems, n_lambda, ng));
         const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data(),

@@ -9,6 +9,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
 
 #include "rcb_internal.h"
 
@@ -21,6 +24,7 @@ struct GramParams {
   long long T, washout, Te, Stot, chunk;
   double* out; long long ldo;
   int lower_only;
+  long long nbatch, a_bstride, b_bstride, o_bstride, splits;   // batch b = blockIdx.z / splits: operands / output advance by these element counts
 };
 
 template <typename TA, typename TB>
@@ -31,14 +35,16 @@ __global__ void __launch_bounds__(256) gram_fp64_kernel(const GramParams g) {
   __shared__ double As[KC][TILE];
   __shared__ double Bs[KC][TILE];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const TA* A = reinterpret_cast<const TA*>(g.A);
-  const TB* B = reinterpret_cast<const TB*>(g.B);
+  const long long bz = (long long)blockIdx.z / g.splits, sz = (long long)blockIdx.z % g.splits;
+  const TA* A = reinterpret_cast<const TA*>(g.A) + (size_t)bz * g.a_bstride;
+  const TB* B = reinterpret_cast<const TB*>(g.B) + (size_t)bz * g.b_bstride;
+  double* out = g.out + (size_t)bz * g.o_bstride;
   double acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  const long long s_beg = (long long)blockIdx.z * g.chunk;
+  const long long s_beg = sz * g.chunk;
   const long long s_end = s_beg + g.chunk < g.Stot ? s_beg + g.chunk : g.Stot;
   const int li = tid & 63, ls = tid >> 6;  // 64 rows x 4 samples per pass
   for (long long s0 = s_beg; s0 < s_end; s0 += KC) {
@@ -73,8 +79,185 @@ __global__ void __launch_bounds__(256) gram_fp64_kernel(const GramParams g) {
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const long long i = i0 + ty + 16 * x, j = j0 + tx + 16 * y;
-      if (i < g.M && j < g.Nc && !(g.lower_only && j > i)) atomicAdd(g.out + (size_t)j * g.ldo + i, acc[x][y]);
+      if (i < g.M && j < g.Nc && !(g.lower_only && j > i)) atomicAdd(out + (size_t)j * g.ldo + i, acc[x][y]);
     }
+}
+
+// The symmetric part G += Z Z' on the FP64 tensor path (mma.sync m8n8k4, DMMA) — the exact Gram of RCB_GRAM_FP64 and of
+// AUTO below the tensor-core thresholds (config 5 with a lambda grid that reaches 1e-8: r02 139 ms in the CUDA-core kernel
+// above, 9 TFLOP/s, shared-memory bound at 8 operand loads per 16 DFMA).  Same fragment mapping as the Cholesky's trailing
+// update (solve.cu): a warp owns 16 (i) x 32 (j) of a 64 x 64 tile, six 32-bit operand loads + conversions feed eight MMAs
+// (2048 FMAs).  Operands stay in their own element type in shared memory (cp.async, 16 bytes at a time, three stages of 32
+// samples in flight) and are widened on their way into the fragments, so Float32 states cost half the staging traffic.
+// Only the lower-triangle tiles are launched (linear tile index); batch / sample-split decode as above.
+__device__ __forceinline__ void gram_dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <typename T> struct DmmaCfg;
+template <> struct DmmaCfg<float> { static constexpr int LDP = 72, VEC = 4; };    // 72 mod 32 = 8: (8 k + column) is a bijection of a warp's 32 (k, column) pairs
+template <> struct DmmaCfg<double> { static constexpr int LDP = 68, VEC = 2; };   // (4 k + column) mod 16 a bijection of a half-warp's pairs
+constexpr int GD_TILE = 64, GD_KS = 32, GD_STAGES = 3;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams g) {
+  constexpr int TILE = GD_TILE, KS = GD_KS, LDP = DmmaCfg<T>::LDP, VEC = DmmaCfg<T>::VEC, CH = TILE / VEC;
+  extern __shared__ __align__(16) unsigned char gd_smem[];
+  T(*Pi)[KS][LDP] = reinterpret_cast<T(*)[KS][LDP]>(gd_smem);
+  T(*Pj)[KS][LDP] = reinterpret_cast<T(*)[KS][LDP]>(gd_smem + (size_t)GD_STAGES * KS * LDP * sizeof(T));
+  // lower-triangle tile (ti >= tj) from the linear index
+  const long long t = blockIdx.x;
+  long long ti = (long long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (ti * (ti + 1) / 2 > t) --ti;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  const long long tj = t - ti * (ti + 1) / 2;
+  const long long i0 = ti * TILE, j0 = tj * TILE;
+  const long long bz = (long long)blockIdx.z / g.splits, sz = (long long)blockIdx.z % g.splits;
+  const T* A = reinterpret_cast<const T*>(g.A) + (size_t)bz * g.a_bstride;
+  double* out = g.out + (size_t)bz * g.o_bstride;
+  const long long s_beg = sz * g.chunk;
+  const long long s_end = s_beg + g.chunk < g.Stot ? s_beg + g.chunk : g.Stot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nst = (int)((s_end - s_beg + KS - 1) / KS);
+  auto issue = [&](int st) {   // stage st of this CTA's sample range -> ring slot st % STAGES
+    if (st < nst) {
+      const int slot = st % GD_STAGES;
+      const long long s0 = s_beg + (long long)st * KS;
+      for (int e = tid; e < KS * CH; e += 256) {
+        const int ss = e / CH, c = (e % CH) * VEC;
+        const long long s = s0 + ss;
+        const bool vs = s < s_end;
+        const long long col = vs ? (s / g.Te) * g.T + g.washout + (s % g.Te) : 0;
+        const T* src = A + (size_t)col * g.lda;
+        const long long ri = g.M - (i0 + c), rj = g.M - (j0 + c);   // valid elements left in the row
+        const int bi = vs && ri > 0 ? (int)(ri < VEC ? ri : VEC) * (int)sizeof(T) : 0;
+        const int bj = vs && rj > 0 ? (int)(rj < VEC ? rj : VEC) * (int)sizeof(T) : 0;
+        const uint32_t di = (uint32_t)__cvta_generic_to_shared(&Pi[slot][ss][c]), dj = (uint32_t)__cvta_generic_to_shared(&Pj[slot][ss][c]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(di), "l"(src + (bi ? i0 + c : 0)), "r"(bi) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dj), "l"(src + (bj ? j0 + c : 0)), "r"(bj) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int wi = (warp & 3) * 16, wj = (warp >> 2) * 32;
+  const int fm = lane & 3, fc = lane >> 2;
+  double acc[4][2][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) acc[a][u][0] = acc[a][u][1] = 0.0;
+  issue(0);
+  issue(1);
+  for (int st = 0; st < nst; ++st) {
+    issue(st + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncthreads();
+    const int slot = st % GD_STAGES;
+#pragma unroll
+    for (int k4 = 0; k4 < KS; k4 += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = (double)Pj[slot][k4 + fm][wj + q * 8 + fc];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) b[u] = (double)Pi[slot][k4 + fm][wi + u * 8 + fc];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) gram_dmma_8x8x4(acc[q][u][0], acc[q][u][1], a[q], b[u]);
+    }
+    __syncthreads();   // the slot is refilled by the issue() of the next iteration
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long j = j0 + wj + q * 8 + fc;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const long long i = i0 + wi + u * 8 + fm * 2 + r;
+        if (i < g.M && j <= i) atomicAdd(out + (size_t)j * g.ldo + i, acc[q][u][r]);
+      }
+    }
+}
+
+// Thin cross term C(F x d_out) += Z Y' for d_out <= 8: one thread per feature (coalesced along the contiguous feature axis),
+// the targets of a sample block broadcast from shared memory, FP64 accumulators in registers — one pass over Z at memory
+// speed (r02: the 64 x 64-tiled kernel above spent 12.5 ms on config 5's 256 cross terms of 3 columns, 97 % of its MACs on
+// padding; this one is bound by reading Z once).
+template <typename TZ, typename TY>
+__global__ void __launch_bounds__(128) cross_thin_kernel(const GramParams g) {
+  constexpr int SB = 64;   // samples per shared-memory block of targets
+  __shared__ double ys[SB][8];
+  const long long bz = (long long)blockIdx.z / g.splits, sz = (long long)blockIdx.z % g.splits;
+  const TZ* A = reinterpret_cast<const TZ*>(g.A) + (size_t)bz * g.a_bstride;
+  const TY* B = reinterpret_cast<const TY*>(g.B) + (size_t)bz * g.b_bstride;
+  double* out = g.out + (size_t)bz * g.o_bstride;
+  const long long f = (long long)blockIdx.x * 128 + threadIdx.x;
+  const int d_out = (int)g.Nc;
+  const long long s_beg = sz * g.chunk, s_end = s_beg + g.chunk < g.Stot ? s_beg + g.chunk : g.Stot;
+  double acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.0;
+  for (long long s0 = s_beg; s0 < s_end; s0 += SB) {
+    const int ns = (int)(s_end - s0 < SB ? s_end - s0 : SB);
+    __syncthreads();
+    for (int e = threadIdx.x; e < SB * 8; e += 128) {
+      const int ss = e >> 3, o = e & 7;
+      double v = 0.0;
+      if (ss < ns && o < d_out) {
+        const long long s = s0 + ss, col = (s / g.Te) * g.T + g.washout + (s % g.Te);
+        v = (double)B[(size_t)col * g.ldb + o];
+      }
+      ys[ss][o] = v;
+    }
+    __syncthreads();
+    if (f < g.M) {
+      const long long c0 = (s0 / g.Te) * g.T + g.washout + (s0 % g.Te);
+      const bool contiguous = (s0 % g.Te) + ns <= g.Te;   // the block does not straddle a sequence boundary
+#pragma unroll 4
+      for (int ss = 0; ss < ns; ++ss) {
+        long long col = c0 + ss;
+        if (!contiguous) { const long long s = s0 + ss; col = (s / g.Te) * g.T + g.washout + (s % g.Te); }
+        const double z = (double)A[(size_t)col * g.lda + f];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fma(z, ys[ss][o], acc[o]);
+      }
+    }
+  }
+  if (f < g.M)
+    for (int o = 0; o < d_out; ++o) atomicAdd(out + (size_t)o * g.ldo + f, acc[o]);
+}
+
+template <typename TZ, typename TY>
+static int32_t launch_cross_thin(rcb_ctx* ctx, GramParams g) {
+  const long long fb = (g.M + 127) / 128;
+  long long splits = (8LL * ctx->sm_count + fb * g.nbatch - 1) / (fb * g.nbatch);
+  splits = std::max<long long>(1, std::min<long long>(splits, (g.Stot + 255) / 256));
+  if (g.nbatch * splits > 65535) splits = std::max<long long>(1, 65535 / g.nbatch);
+  g.chunk = ((g.Stot + splits - 1) / splits + 63) / 64 * 64;
+  g.splits = (g.Stot + g.chunk - 1) / g.chunk;
+  cross_thin_kernel<TZ, TY><<<dim3((unsigned)fb, 1, (unsigned)(g.nbatch * g.splits)), 128, 0, ctx->stream>>>(g);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+template <typename T>
+static int32_t launch_gram_dmma(rcb_ctx* ctx, GramParams g) {
+  const long long tm = (g.M + GD_TILE - 1) / GD_TILE, tiles = tm * (tm + 1) / 2;
+  long long splits = (4LL * ctx->sm_count + tiles * g.nbatch - 1) / (tiles * g.nbatch);
+  const long long max_splits = (g.Stot + 511) / 512;
+  splits = std::max<long long>(1, std::min(splits, max_splits));
+  if (g.nbatch * splits > 65535) splits = std::max<long long>(1, 65535 / g.nbatch);
+  g.chunk = ((g.Stot + splits - 1) / splits + GD_KS - 1) / GD_KS * GD_KS;
+  splits = (g.Stot + g.chunk - 1) / g.chunk;
+  g.splits = splits;
+  const size_t smem = 2 * (size_t)GD_STAGES * GD_KS * DmmaCfg<T>::LDP * sizeof(T);
+  RCB_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_dmma_kernel<T><<<dim3((unsigned)tiles, 1, (unsigned)(g.nbatch * splits)), 256, smem, ctx->stream>>>(g);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
 }
 
 int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a) {
@@ -82,18 +265,33 @@ int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a) {
   g.A = a.A; g.M = a.M; g.lda = a.lda; g.B = a.Bm; g.Nc = a.Nc; g.ldb = a.ldb;
   g.T = a.T; g.washout = a.washout; g.Te = a.T - a.washout; g.Stot = g.Te * a.nseq;
   g.out = a.out; g.ldo = a.ldo; g.lower_only = a.lower_only ? 1 : 0;
+  g.nbatch = std::max<int64_t>(1, a.nbatch); g.a_bstride = a.a_bstride; g.b_bstride = a.b_bstride; g.o_bstride = a.o_bstride;
+  g.splits = 1;
   if (g.Stot <= 0) return RCB_OK;
+  if (g.nbatch > 65535) return fail(RCB_ERR_UNSUPPORTED, "at most 65535 Gram matrices per batched launch");
+  const bool a64 = a.a_dtype == RCB_F64, b64 = a.b_dtype == RCB_F64;
+  const size_t esz = a64 ? 8 : 4;
+  // symmetric rank-S update of one matrix with itself, rows 16-byte aligned: the tensor-path kernel
+  if (a.A == a.Bm && a.lower_only && a.a_dtype == a.b_dtype && a.M == a.Nc && a.lda == a.ldb && a.a_bstride == a.b_bstride && a.M >= 32 &&
+      ((size_t)a.lda * esz) % 16 == 0 && ((size_t)a.a_bstride * esz) % 16 == 0 && ((uintptr_t)a.A) % 16 == 0 && !getenv("RCB_GRAM_NO_DMMA"))
+    return a64 ? launch_gram_dmma<double>(ctx, g) : launch_gram_dmma<float>(ctx, g);
+  if (!a.lower_only && a.Nc <= 8 && a.M >= 64) {   // thin cross term: one pass over A at memory speed
+    if (!a64 && !b64) return launch_cross_thin<float, float>(ctx, g);
+    if (!a64 && b64) return launch_cross_thin<float, double>(ctx, g);
+    if (a64 && !b64) return launch_cross_thin<double, float>(ctx, g);
+    return launch_cross_thin<double, double>(ctx, g);
+  }
   const long long tm = (a.M + 63) / 64, tn = (a.Nc + 63) / 64;
-  const long long tiles = a.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  const long long tiles = (a.lower_only ? tm * (tm + 1) / 2 : tm * tn) * g.nbatch;
   long long splits = (4LL * ctx->sm_count + tiles - 1) / tiles;
   const long long max_splits = (g.Stot + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
+  if (g.nbatch * splits > 65535) splits = std::max<long long>(1, 65535 / g.nbatch);
   g.chunk = ((g.Stot + splits - 1) / splits + 15) / 16 * 16;
   splits = (g.Stot + g.chunk - 1) / g.chunk;
-  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
-  const bool a64 = a.a_dtype == RCB_F64, b64 = a.b_dtype == RCB_F64;
+  g.splits = splits;
+  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)(splits * g.nbatch));
   if (!a64 && !b64) gram_fp64_kernel<float, float><<<grid, 256, 0, ctx->stream>>>(g);
   else if (!a64 && b64) gram_fp64_kernel<float, double><<<grid, 256, 0, ctx->stream>>>(g);
   else if (a64 && !b64) gram_fp64_kernel<double, float><<<grid, 256, 0, ctx->stream>>>(g);

@@ -250,6 +250,7 @@ struct GramArgs {
   int64_t T = 0, washout = 0, nseq = 1;
   double* out = nullptr; int64_t ldo = 0;
   bool lower_only = false;
+  int64_t nbatch = 1, a_bstride = 0, b_bstride = 0, o_bstride = 0;   // batched: nbatch problems, element strides of A / B / out
 };
 int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a);
 // lower triangle of G + cross block <-> contiguous exchange buffer (device pointers)

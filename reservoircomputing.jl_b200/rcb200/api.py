@@ -1135,7 +1135,7 @@ def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambda
                                       ptr(lambdas), gram_mode, ptr(h0), ptr(W), ptr(hT)))
     finally:
         check(lib().rcb_esn_set_member_params(h.handle, 0, None, None))
-    return np.ascontiguousarray(W.transpose(3, 2, 0, 1)), hT
+    return W.transpose(3, 2, 0, 1), hT   # a view of the (d_out, F, n_lambda, B) result: W[b, l] is the (d_out, F) readout, column-major
 
 
 def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Device] = None):
