@@ -8,8 +8,9 @@
 #   __collectstates(reservoir, rc, data, ps, st)            src/reservoircomputer.jl:96-133
 #   __predict(reservoir, rc, steps::Integer, ps, st; ...)   src/predict.jl:118-124,74-88
 #   __predict(reservoir, rc, data::AbstractMatrix, ps, st)  src/predict.jl:126-129,163-177
-#   __fit_readout(::B200Ridge, states, targets; ...)        src/train.jl:100-198
-# `ESN`, `DeepESN`, `ReservoirComputer`, `LuxCore.setup`, `train`, `predict`, `collectstates`,
+#   __train_ridge(::B200Cholesky / ::B200QR, ::RidgeRegression, states, targets)   src/train.jl:140-198
+#   train(rc::ReservoirComputer{<:B200Reservoir}, X, Y, ps, st; ...)               src/train.jl:232-251 (fused: rcb_train)
+# `ESN`, `DeepESN`, `ReservoirComputer`, `LuxCore.setup`, `predict`, `collectstates`, `RidgeRegression`,
 # `addreadout!` and `resetcarry!` are untouched: `ps`/`st` keep their layout (Appendix A of SURVEY.md),
 # the final carry is copied back into `st.reservoir.carry`, and errors are re-raised as the
 # exception types the reference throws (ArgumentError / DimensionMismatch).
@@ -18,7 +19,9 @@ module RCB200
 using ReservoirComputing
 using ReservoirComputing: AbstractReservoirComputer, ReservoirComputer, StatefulLayer, ESNCell, ES2NCell, ResESNCell,
                           EuSNCell, RidgeRegression, NLAT1, NLAT2, NLAT3, Pad, PartialSquare, ExtendedSquare
-import ReservoirComputing: __collectstates, __predict, __fit_readout, collectstates
+using ReservoirComputing: AbstractReservoirComputingSolver
+using ReservoirComputing.LuxCore: AbstractLuxWrapperLayer
+import ReservoirComputing: __collectstates, __predict, __fit_readout, __train_ridge, collectstates, train
 using SparseArrays: SparseMatrixCSC
 
 const LIB = get(ENV, "RCB200_LIB", joinpath(@__DIR__, "..", "librcb200.so"))
@@ -93,12 +96,10 @@ Marker wrapper selecting the CUDA path: `ESN(...; )` is built as usual and its `
 (`StatefulLayer(ESNCell)`) is wrapped — `ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)`.
 Parameter and state trees are those of the wrapped layer (LuxCore.initialparameters/initialstates forward).
 """
-struct B200Reservoir{L} <: ReservoirComputing.AbstractReservoirCollectionLayer
+struct B200Reservoir{L} <: AbstractLuxWrapperLayer{:layer}   # like StatefulLayer (lux_layers.jl:27): ps / st are those of `layer`
     layer::L
 end
-ReservoirComputing.LuxCore.initialparameters(rng, r::B200Reservoir) = ReservoirComputing.LuxCore.initialparameters(rng, r.layer)
-ReservoirComputing.LuxCore.initialstates(rng, r::B200Reservoir) = ReservoirComputing.LuxCore.initialstates(rng, r.layer)
-(r::B200Reservoir)(x, ps, st) = r.layer(x, ps, st)   # single steps stay on the reference path
+(r::B200Reservoir)(x, ps, st) = r.layer(x, ps, st)   # single steps stay on the reference path (reservoircomputer.jl:90-94)
 
 mutable struct Handle
     ptr::Ptr{Cvoid}
@@ -193,23 +194,194 @@ function __collectstates(res::B200Reservoir, rc::AbstractReservoirComputer, data
 end
 
 # ---- ridge: src/train.jl:100-198 ---------------------------------------------------------------------
-"""`B200Ridge(λ)` — a `RidgeRegression` whose `__fit_readout` runs K2 (tcgen05 Gram) + K3 (FP64 Cholesky)."""
-struct B200Ridge{R <: Number}
-    reg::R
+# The objective stays the reference's `RidgeRegression(λ)`; the GPU path is selected the way the reference selects any
+# other algorithm — through `solver` (train.jl:100-106, 149-198):
+#     train(rc, X, Y, ps, st; objective = RidgeRegression(1e-6), solver = B200Cholesky())
+#   B200Cholesky(gram = :auto | :fp64 | :tensor)  Gram form (K2) + FP64 Cholesky (K3); `:auto` escalates by itself: λ == 0
+#                                                 -> QR, a failed pivot -> exact FP64 Gram -> QR (include/rcb200.h)
+#   B200QR()                                      FP64 Householder QR of [Z'; √λ I] on the GPU — the reference's own algorithm
+const GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR = Int32(0), Int32(1), Int32(2), Int32(3)
+struct B200Cholesky <: AbstractReservoirComputingSolver
+    gram::Symbol
 end
-function __fit_readout(obj::B200Ridge, states::AbstractMatrix, targets::AbstractMatrix; kwargs...)
+B200Cholesky(; gram::Symbol = :auto) = B200Cholesky(gram)
+struct B200QR <: AbstractReservoirComputingSolver end
+gram_mode(s::B200Cholesky) = s.gram === :auto ? GRAM_AUTO : s.gram === :fp64 ? GRAM_FP64 : s.gram === :tensor ? GRAM_TENSOR :
+                             throw(ArgumentError("B200Cholesky: gram must be :auto, :fp64 or :tensor, got :$(s.gram)"))
+gram_mode(::B200QR) = FIT_QR
+const B200Solver = Union{B200Cholesky, B200QR}
+
+dense32or64(x::Matrix{Float32}) = x
+dense32or64(x::Matrix{Float64}) = x
+dense32or64(x::AbstractMatrix{Float32}) = Matrix{Float32}(x)
+dense32or64(x::AbstractMatrix) = Matrix{Float64}(x)
+
+function __train_ridge(solver::B200Solver, objective::RidgeRegression, states::AbstractMatrix, targets::AbstractMatrix; kwargs...)
     size(states, 2) == size(targets, 2) ||
         throw(DimensionMismatch("states has $(size(states, 2)) samples, targets has $(size(targets, 2))"))
     F, S = size(states); D = size(targets, 1)
-    Z = states isa Matrix{Float32} || states isa Matrix{Float64} ? states : Matrix{Float64}(states)
-    Y = targets isa Matrix{Float32} || targets isa Matrix{Float64} ? targets : Matrix{Float64}(targets)
+    Z, Y = dense32or64(states), dense32or64(targets)
     W = Matrix{Float64}(undef, D, F)
     check(ccall((:rcb_fit_readout, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Float64, Int32, Ptr{Float64}),
                 ctx().ptr, Z, dtype_id(eltype(Z)), F, S, stride(Z, 2), Y, dtype_id(eltype(Y)), D, size(Y, 2), stride(Y, 2),
-                Float64(obj.reg), 0, W))
-    Tp = promote_type(eltype(states), eltype(targets), typeof(obj.reg))    # train.jl:126-129
+                Float64(objective.reg), gram_mode(solver), W))
+    Tp = promote_type(eltype(states), eltype(targets), typeof(objective.reg))    # train.jl:126-129
     return Matrix{Tp}(W)
+end
+
+"""`B200Ridge(λ)` — shorthand objective: `RidgeRegression(λ)` solved with `B200Cholesky()`."""
+struct B200Ridge{R <: Number}
+    reg::R
+end
+__fit_readout(obj::B200Ridge, states::AbstractMatrix, targets::AbstractMatrix; solver = nothing, kwargs...) =
+    __train_ridge(solver isa B200Solver ? solver : B200Cholesky(), RidgeRegression(obj.reg), states, targets; kwargs...)
+
+# ---- train: src/train.jl:232-251, fused ---------------------------------------------------------------------------
+# The generic `train` materialises the F x T state matrix on the host between `collectstates` and `__fit_readout`.  For a
+# CUDA-backed reservoir with a GPU solver the whole chain collect -> washout -> Gram -> solve -> addreadout! is ONE call
+# (rcb_train): the states never leave the device (the library cuts long inputs into windows that fit HBM) unless
+# `return_states = true` asks for them.  Every other (objective, solver) combination falls through to the generic method.
+function train(rc::ReservoirComputer{<:B200Reservoir}, train_data::AbstractMatrix{T}, target_data::AbstractMatrix, ps, st;
+               objective = RidgeRegression(0.0), solver = nothing, washout::Integer = 0, return_states::Bool = false,
+               kwargs...) where {T <: Union{Float32, Float64}}
+    if objective isa B200Ridge
+        objective, solver = RidgeRegression(objective.reg), solver isa B200Solver ? solver : B200Cholesky()
+    end
+    if !(objective isa RidgeRegression && solver isa B200Solver)
+        return invoke(train, Tuple{Any, Any, Any, Any, Any}, rc, train_data, target_data, ps, st;
+                      objective, solver, washout, return_states, kwargs...)
+    end
+    Tn = size(train_data, 2)
+    Tn >= 1 || throw(ArgumentError("collectstates data must have at least one column, got 0."))
+    washout >= 0 || throw(ArgumentError("washout must be ≥ 0, got $washout"))                       # train.jl:37
+    washout < Tn || throw(ArgumentError("washout=$washout is ≥ number of time steps=$Tn"))          # train.jl:39-43
+    size(target_data, 2) == Tn ||
+        throw(DimensionMismatch("states has $(Tn - washout) samples, targets has $(size(target_data, 2) - washout)"))
+    h = Handle(rc, ps, T)
+    X, Y = Matrix{T}(train_data), dense32or64(target_data)
+    D = size(Y, 1)
+    W = Matrix{Float64}(undef, D, h.F)
+    states = return_states ? Matrix{T}(undef, h.F, Tn) : nothing
+    h0 = initial_carry(rc, st, T); hT = similar(h0)
+    check(ccall((:rcb_train, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Float64, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Ptr{Cvoid}),
+                h.ptr, X, Y, dtype_id(eltype(Y)), Tn, 1, washout, Float64(objective.reg), gram_mode(solver), h0, W,
+                states === nothing ? C_NULL : states, hT))
+    Tp = promote_type(T, eltype(target_data), typeof(objective.reg))                                 # train.jl:126-129
+    ps2, st2 = ReservoirComputing.addreadout!(rc, Matrix{Tp}(W), ps, store_carry(st, hT))
+    return return_states ? ((ps2, st2), states[:, (washout + 1):end]) : (ps2, st2)
+end
+
+# ---- streaming / sharded fit (SURVEY 8e): the pieces a multi-process Julia host (MPI.jl, Distributed) composes ----------
+"""
+    gram_accumulate!(GC, states, targets; gram = :auto, zero_first = false) -> GC
+
+`[G | C] += [Z Z' | Z Y']` (F x (F + d_out) Float64, lower triangle of G) — one chunk of a streamed ridge fit.
+`ridge_solve(GC, d_out, λ)` finishes it; ranks sum their `GC` in between (`allreduce_gc!`).
+"""
+function gram_accumulate!(GC::Matrix{Float64}, states::AbstractMatrix, targets::AbstractMatrix; gram::Symbol = :auto, zero_first::Bool = false)
+    Z, Y = dense32or64(states), dense32or64(targets)
+    F, S = size(Z); D = size(Y, 1)
+    size(GC) == (F, F + D) || throw(DimensionMismatch("GC must be $F x $(F + D), got $(size(GC))"))
+    check(ccall((:rcb_gram_accumulate, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Ptr{Cvoid}, Int32, Int64, Int64, Int32, Int32, Ptr{Float64}),
+                ctx().ptr, Z, dtype_id(eltype(Z)), F, S, stride(Z, 2), Y, dtype_id(eltype(Y)), D, stride(Y, 2),
+                gram_mode(B200Cholesky(gram)), zero_first ? 1 : 0, GC))
+    return GC
+end
+function ridge_solve(GC::Matrix{Float64}, d_out::Integer, λ::Real)
+    F = size(GC, 1)
+    W = Matrix{Float64}(undef, d_out, F)
+    check(ccall((:rcb_ridge_solve, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Ptr{Float64}), ctx().ptr, GC, F, d_out, Float64(λ), W))
+    return W
+end
+
+"""
+    Comm(rank, world, id) / comm_unique_id()
+
+Library-owned NCCL communicator, one process per GPU: rank 0 draws `id = comm_unique_id()` (128 bytes), ships it to every
+rank by the host's own means (`MPI.Bcast!`, a `RemoteChannel`, a file), then every rank constructs `Comm(rank, world, id)`.
+"""
+mutable struct Comm
+    ptr::Ptr{Cvoid}
+    function Comm(rank::Integer, world::Integer, id::Vector{UInt8})
+        length(id) == 128 || throw(ArgumentError("the communicator id has 128 bytes, got $(length(id))"))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:rcb_comm_create, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Ref{Ptr{Cvoid}}), ctx().ptr, id, rank, world, out))
+        c = new(out[])
+        finalizer(x -> ccall((:rcb_comm_destroy, LIB), Int32, (Ptr{Cvoid},), x.ptr), c)
+    end
+end
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:rcb_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    return id
+end
+allreduce_gc!(comm::Comm, GC::Matrix{Float64}, d_out::Integer) =
+    (check(ccall((:rcb_allreduce_gc, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64), comm.ptr, GC, size(GC, 1), d_out)); GC)
+
+"""
+    train_sharded(rc, comm, data, targets, ps, st; objective, solver = B200Cholesky(), washout = 0)
+
+`train` with ONE pooled readout over sequences sharded across ranks (BASELINE config 3): this rank passes its own
+`d_in x T x B_local` inputs and `d_out x T x B_local` targets; the partial `[G | C]` are summed by one NCCL all-reduce inside
+the library and every rank gets the same readout.  `comm = nothing`: a single rank.
+"""
+function train_sharded(rc::ReservoirComputer{<:B200Reservoir}, comm::Union{Comm, Nothing}, data::Array{T, 3}, targets::Array{<:Union{Float32, Float64}, 3},
+                       ps, st; objective::RidgeRegression = RidgeRegression(0.0), solver::B200Solver = B200Cholesky(), washout::Integer = 0) where {T <: Union{Float32, Float64}}
+    _, Tn, B = size(data)
+    (size(targets, 2), size(targets, 3)) == (Tn, B) || throw(DimensionMismatch("targets must be d_out x $Tn x $B, got $(size(targets))"))
+    h = Handle(rc, ps, T)
+    W = Matrix{Float64}(undef, size(targets, 1), h.F)
+    h0 = repeat(initial_carry(rc, st, T), 1, B); hT = similar(h0)
+    check(ccall((:rcb_train_sharded, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Float64, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                h.ptr, comm === nothing ? C_NULL : comm.ptr, data, targets, dtype_id(eltype(targets)), Tn, B, washout,
+                Float64(objective.reg), gram_mode(solver), h0, W, hT))
+    ps2, _ = ReservoirComputing.addreadout!(rc, W, ps, st)
+    return ps2, hT
+end
+
+"""
+    train_time_chunked(rc, comm, data, targets, ps, st; objective, solver, washout, n_chunks, overlap)
+
+`train` of ONE long series (BASELINE config 2) cut into `n_chunks` windows after the washout; every window re-synchronises
+over `overlap` steps from a zero state (echo-state property — an approximation; plain `train` is the sequential reference).
+"""
+function train_time_chunked(rc::ReservoirComputer{<:B200Reservoir}, comm::Union{Comm, Nothing}, data::Matrix{T}, targets::Matrix{<:Union{Float32, Float64}},
+                            ps, st; objective::RidgeRegression = RidgeRegression(0.0), solver::B200Solver = B200Cholesky(), washout::Integer,
+                            n_chunks::Integer, overlap::Integer = washout) where {T <: Union{Float32, Float64}}
+    h = Handle(rc, ps, T)
+    W = Matrix{Float64}(undef, size(targets, 1), h.F)
+    hT = Vector{T}(undef, h.N)
+    check(ccall((:rcb_train_time_chunked, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Int64, Float64, Int32, Ptr{Float64}, Ptr{Cvoid}),
+                h.ptr, comm === nothing ? C_NULL : comm.ptr, data, targets, dtype_id(eltype(targets)), size(data, 2), washout, n_chunks,
+                overlap, Float64(objective.reg), gram_mode(solver), W, hT))
+    ps2, _ = ReservoirComputing.addreadout!(rc, W, ps, st)
+    return ps2, store_carry(st, hT)
+end
+
+"""
+    train_ensemble(rc, data, targets, ps, st; w_scale, leak, lambdas, washout = 0, solver = B200Cholesky()) -> W, hT
+
+Hyper-parameter sweep (BASELINE config 5): member `b` runs the same reservoir with `W * w_scale[b]` and leak `leak[b]` and gets
+one readout per `λ ∈ lambdas`; `W` is `d_out x F x length(lambdas) x B`.  Members are independent: shard them over ranks.
+"""
+function train_ensemble(rc::ReservoirComputer{<:B200Reservoir}, data::Array{T, 3}, targets::Array{<:Union{Float32, Float64}, 3}, ps, st;
+                        w_scale::Vector{Float32}, leak::Vector{Float32}, lambdas::Vector{Float64}, washout::Integer = 0,
+                        solver::B200Solver = B200Cholesky()) where {T <: Union{Float32, Float64}}
+    _, Tn, B = size(data)
+    length(w_scale) == B == length(leak) || throw(DimensionMismatch("w_scale / leak need one entry per member ($B)"))
+    h = Handle(rc, ps, T)
+    W = Array{Float64, 4}(undef, size(targets, 1), h.F, length(lambdas), B)
+    h0 = repeat(initial_carry(rc, st, T), 1, B); hT = similar(h0)
+    check(ccall((:rcb_esn_set_member_params, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float32}, Ptr{Float32}), h.ptr, B, w_scale, leak))
+    check(ccall((:rcb_train_members, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Int64, Int64, Int32, Ptr{Float64}, Int32, Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                h.ptr, data, targets, dtype_id(eltype(targets)), Tn, B, washout, length(lambdas), lambdas, gram_mode(solver), h0, W, hT))
+    return W, hT
 end
 
 # ---- predict: src/predict.jl:74-88 (autoregressive) and :163-177 (teacher-forced) -----------------------
@@ -388,12 +560,14 @@ end
     b200(rc::AbstractReservoirComputer) -> ReservoirComputer
 
 Same model (`ESN`, `ES2N`, `ResESN`, `EuSN` or a hand-built `ReservoirComputer` around one of their cells),
-CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = B200Ridge(λ))`.  `ps` / `st` keep the layout of the
-wrapped model (same field names `reservoir`, `state_modifiers`, `readout`).
+CUDA-backed reservoir: `train(b200(esn), X, Y, ps, st; objective = RidgeRegression(λ), solver = B200Cholesky())` runs
+collect -> washout -> Gram -> solve as one library call.  `ps` / `st` keep the layout of the wrapped model (same field
+names `reservoir`, `state_modifiers`, `readout`).
 """
 b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 b200(rc::ReservoirComputing.DeepESN) = B200DeepESN(rc)
 
-export B200Reservoir, B200DeepESN, B200Ridge, b200, spectral_radius_b200, scale_radius_b200!, delay_features, extend_features, correlation_matrix_b200
+export B200Reservoir, B200DeepESN, B200Ridge, B200Cholesky, B200QR, b200, gram_accumulate!, ridge_solve, Comm, comm_unique_id, allreduce_gc!,
+       train_sharded, train_time_chunked, train_ensemble, spectral_radius_b200, scale_radius_b200!, delay_features, extend_features, correlation_matrix_b200
 
 end # module
