@@ -116,11 +116,15 @@ RCB_API int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches);
 RCB_API int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms);
 /* name of the kernel variant the most recent recurrence call launched, e.g. "k1_fast<NB=7,tmem,din=3,simple>" */
 RCB_API int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len);
+/* Diagnostics of the most recent RCB_GRAM_AUTO ridge fit on this context: how many iterative-refinement passes it ran on the
+ * exact normal equations and |delta W| / |W| of the last correction (0 / 0.0: none — QR path, explicit gram_mode, d_out > 8). */
+RCB_API int32_t rcb_ctx_last_refine(rcb_ctx* ctx, int32_t* steps, double* rel);
 #define RCB_TIMER_RECURRENCE 0 /* K1 / K4 */
 #define RCB_TIMER_GRAM 1       /* K2 */
 #define RCB_TIMER_SOLVE 2      /* K3 (Cholesky / QR) */
 #define RCB_TIMER_EXCHANGE 3   /* pack + NCCL all-reduce (or all-gather + factor merges) + unpack of the multi-GPU train calls */
-#define RCB_TIMER_COUNT 4
+#define RCB_TIMER_REFINE 4     /* exact-residual kernels of the iterative refinement (its recurrence re-runs and re-solves count under 0 and 2) */
+#define RCB_TIMER_COUNT 5
 
 /* ---- model handle: replaces ESN / DeepESN + LuxCore.setup parameter hand-off ------------------
  * src/models/esn.jl:93-106, src/models/esn_deep.jl:102-147, src/reservoircomputer.jl:51-63 */
@@ -222,7 +226,14 @@ RCB_API int32_t rcb_collect(rcb_esn* esn, const void* u, int64_t T, int64_t B, c
  * (qr(design) \ rhs, src/train.jl:140-147,182) — streamed over sample chunks as a triangular-pentagonal QR (csrc/qr_solve.cu);
  * error ~ cond(design) instead of cond^2.  The accumulator [R | Q'b] has the footprint of [G | C].
  * RCB_GRAM_AUTO escalates by itself: λ == 0 (the reference's default objective, train.jl:234) goes straight to QR; a Cholesky
- * that meets a non-positive pivot is retried on the exact FP64 Gram and then by QR before RCB_ERR_NUMERIC is reported. */
+ * that meets a non-positive pivot is retried on the exact FP64 Gram and then by QR before RCB_ERR_NUMERIC is reported.
+ * RCB_GRAM_AUTO also REFINES every Cholesky-on-Gram solution on the exact normal equations (corrected semi-normal
+ * equations): R = Z (Y - W Z)' - λ W' with exact products and FP64 accumulation (one more pass over the samples; the fused
+ * train calls re-run the recurrence), W += (L L')^-1 R, until the estimated error of W is below 1e-5 of its norm — so the
+ * weights of the AUTO path agree with the reference's Float64 QR to the 1e-4 tolerance whichever Gram kernel ran (the
+ * tensor-core Gram alone is the Gram of states rounded to 22 bits: its raw solution is off by ~2^-23 / (λ per sample)).
+ * A refinement that does not contract escalates like a failed pivot.  Explicit RCB_GRAM_FP64 / RCB_GRAM_TENSOR return the raw
+ * Cholesky solution. */
 #define RCB_FIT_QR 3
 RCB_API int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S_states,
                         int64_t ld_states, const void* targets, int32_t targets_dtype, int64_t d_out,

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <complex>
 #include <new>
 #include <vector>
@@ -588,6 +589,13 @@ int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len) {
   return RCB_OK;
 }
 
+int32_t rcb_ctx_last_refine(rcb_ctx* ctx, int32_t* steps, double* rel) {
+  if (!ctx) return fail(RCB_ERR_ARGUMENT, "ctx is NULL");
+  if (steps) *steps = ctx->refine_steps;
+  if (rel) *rel = ctx->refine_last;
+  return RCB_OK;
+}
+
 int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms) {
   if (!ctx || !ms) return fail(RCB_ERR_ARGUMENT, "NULL argument");
   if (which < 0 || which >= RCB_TIMER_COUNT) return fail(RCB_ERR_ARGUMENT, "unknown timer %d", which);
@@ -941,6 +949,12 @@ bool rcbi_want_qr(int32_t mode, double lambda) { return mode == RCB_FIT_QR || (m
 static int32_t accumulate_device(rcb_ctx* ctx, bool qr, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y,
                                  int32_t ydt, int64_t d_out, int64_t ldy, int64_t T, int64_t washout, int64_t nseq,
                                  int32_t gram_mode, double* GC) {
+  if (gram_mode == RCBI_RESIDUAL) {   // refinement pass: exact residual of ctx->refine_W into the rhs slot of the factored buffer
+    timer_begin(ctx, RCB_TIMER_REFINE);
+    const int32_t st = launch_ridge_residual(ctx, Z, zdt, F, ldz, Y, ydt, d_out, ldy, T, washout, nseq, ctx->refine_W, GC + (size_t)F * F, F);
+    timer_end(ctx, RCB_TIMER_REFINE);
+    return st;
+  }
   if (qr) {
     ctx->last_gram_tensor = 0;
     return launch_qr_accumulate(ctx, Z, zdt, F, ldz, Y, ydt, d_out, ldy, T, washout, nseq, GC);
@@ -954,6 +968,50 @@ int32_t rcbi_solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t 
     return launch_qr_solve(ctx, GC, F, d_out, 1, w_dev, nullptr);
   }
   return launch_ridge_solve(ctx, GC, F, d_out, lambda, w_dev);
+}
+
+// Iterative refinement of a Cholesky-on-Gram solution (the "corrected semi-normal equations" of SURVEY 7.3-2).  `gc` holds
+// the factor L of (G~ + lambda I) — G~ the accumulated Gram: exact FP64 products, or the tensor path's Gram of the 22-bit
+// fixed-point states — and w_dev the solution W0 of the perturbed system.  Every step evaluates the residual of the EXACT
+// normal equations,  R = Z (Y - W Z)' - lambda W'  (one more pass over the samples: `pass` re-runs the accumulation in
+// RCBI_RESIDUAL mode, `reduce` sums the rhs slot over the ranks of a sharded fit), and corrects W by L'^-1 L^-1 R.  The
+// iteration contracts with rho ~ |G~ - G| / lambda (~ the relative error of W0) and stops once the estimated error of W,
+// rho |delta| / |W|, is below 1e-5 — an order inside the 1e-4 weight tolerance — or stalls (rho >= 0.5: not a usable
+// preconditioner; the caller escalates).  Returns RCB_OK, or RCB_ERR_NUMERIC when it stalls.
+int32_t rcbi_refine(rcb_ctx* ctx, int64_t F, int64_t d_out, double lambda, double* gc, double* w_dev,
+                    const std::function<int32_t(double*)>& pass, const std::function<int32_t(double*, int64_t)>& reduce, int world) {
+  ctx->refine_steps = 0;
+  ctx->refine_last = 0.0;
+  if (d_out > 8 || solve_padded_ld(F) != F) return RCB_OK;
+  int max_steps = 4;
+  if (const char* e = getenv("RCB_REFINE")) max_steps = atoi(e);   // testing hook: 0 switches the refinement off
+  void* scr = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_DELTA, (size_t)d_out * F * sizeof(double) + 64, &scr));
+  double* delta = (double*)scr;
+  double* norms = delta + (size_t)d_out * F;
+  double prev = -1.0;
+  for (int k = 0; k < max_steps; ++k) {
+    RCB_TRY(launch_refine_init(ctx, w_dev, F, d_out, lambda / (double)world, gc + (size_t)F * F, F));   // summed over `world` ranks by reduce
+    ctx->refine_W = w_dev;
+    const int32_t sp = pass(gc);
+    ctx->refine_W = nullptr;
+    RCB_TRY(sp);
+    if (reduce) RCB_TRY(reduce(gc + (size_t)F * F, F * d_out));
+    RCB_TRY(launch_cholesky_resolve(ctx, gc, F, d_out, delta));
+    RCB_TRY(launch_refine_update(ctx, w_dev, delta, F * d_out, norms));
+    double h[2];
+    RCB_CUDA(cudaMemcpyAsync(h, norms, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!(h[0] == h[0]) || !(h[1] == h[1])) return fail(RCB_ERR_NUMERIC, "iterative refinement produced non-finite weights");
+    const double rel = h[1] > 0.0 ? sqrt(h[0] / h[1]) : 0.0;
+    ctx->refine_steps = k + 1;
+    ctx->refine_last = rel;
+    const double rho = prev > 0.0 ? rel / prev : rel;   // first step: the error of W0 is itself ~ rho
+    if (k > 0 && rho >= 0.5) return fail(RCB_ERR_NUMERIC, "iterative refinement stalled (contraction %.2g): the Gram factor is not a usable preconditioner at this lambda", rho);
+    if (rho * rel <= 1e-5) break;
+    prev = rel;
+  }
+  return RCB_OK;
 }
 
 int32_t rcb_gram_accumulate(rcb_ctx* ctx, const void* states, int32_t states_dtype, int64_t F, int64_t S, int64_t ld_states,
@@ -1095,12 +1153,24 @@ int32_t rcb_fit_readout(rcb_ctx* ctx, const void* states, int32_t states_dtype, 
     modes[nm++] = gram_mode;
     if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
   }
+  timers_reset(ctx);
+  const size_t zsz = states_dtype == RCB_F64 ? 8 : 4, ysz = targets_dtype == RCB_F64 ? 8 : 4;
+  const void* Z = nullptr;
+  const void* Y = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_STATES, states, (size_t)ld_states * S_states * zsz, &Z));
+  RCB_TRY(stage_in(ctx, SCR_TGT, targets, (size_t)ld_targets * S_states * ysz, &Y));
+  auto accumulate = [&](int32_t mode, double* acc) {
+    return accumulate_device(ctx, mode == RCB_FIT_QR, Z, states_dtype, F, ld_states, Y, targets_dtype, d_out, ld_targets, S_states, 0, 1, mode, acc);
+  };
   int32_t st = RCB_OK;
   for (int32_t i = 0; i < nm; ++i) {
     if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;  // the first attempt already was exact
-    RCB_TRY(rcb_gram_accumulate(ctx, states, states_dtype, F, S_states, ld_states, targets, targets_dtype, d_out, ld_targets,
-                                modes[i], 1, (double*)gc));
+    RCB_CUDA(cudaMemsetAsync(gc, 0, (size_t)F * (F + d_out) * sizeof(double), ctx->stream));
+    RCB_TRY(accumulate(modes[i], (double*)gc));
     st = rcbi_solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    // AUTO: the Cholesky-on-Gram solution is refined on the exact normal equations (QR-grade weights); a stall escalates
+    if (st == RCB_OK && gram_mode == RCB_GRAM_AUTO && modes[i] != RCB_FIT_QR)
+      st = rcbi_refine(ctx, F, d_out, lambda, (double*)gc, (double*)w_dev, [&](double* acc) { return accumulate(RCBI_RESIDUAL, acc); }, nullptr, 1);
     if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);
@@ -1262,6 +1332,10 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
     if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;
     RCB_TRY(rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B, washout, modes[i], h0, (double*)gc, states_out, hT_out, true));
     st = rcbi_solve_device(ctx, modes[i] == RCB_FIT_QR, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    if (st == RCB_OK && gram_mode == RCB_GRAM_AUTO && modes[i] != RCB_FIT_QR)   // refinement passes re-run the recurrence (same carry)
+      st = rcbi_refine(ctx, F, d_out, lambda, (double*)gc, (double*)w_dev, [&](double* acc) {
+        return rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B, washout, RCBI_RESIDUAL, h0, acc, nullptr, nullptr, false);
+      }, nullptr, 1);
     if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <new>
+#include <functional>
 #include <vector>
 
 #include "rcb_internal.h"
@@ -162,6 +163,22 @@ int32_t sharded_fit(rcb_esn* esn, rcb_comm* comm, double lambda, double samples_
     RCB_TRY(accumulate(modes[i], (double*)gc));
     if (comm) RCB_TRY(qr ? allmerge_rq_device(comm, (double*)gc, F, d_out) : allreduce_gc_device(comm, (double*)gc, F, d_out));
     st = rcbi_solve_device(ctx, qr, (double*)gc, F, d_out, lambda, (double*)w_dev);
+    // AUTO: refine on the exact normal equations; the residual of every rank's samples is summed like [G | C] was (every
+    // rank sees the same norms, so the iteration stays collective-safe)
+    if (st == RCB_OK && gram_mode == RCB_GRAM_AUTO && !qr) {
+      std::function<int32_t(double*, int64_t)> reduce;
+      if (comm && comm->world > 1)
+        reduce = [&](double* slot, int64_t n) -> int32_t {
+          NcclApi* api = nullptr;
+          RCB_TRY(nccl_api(&api));
+          timer_begin(ctx, RCB_TIMER_EXCHANGE);
+          RCB_NCCL(api, api->AllReduce(slot, slot, (size_t)n, ncclFloat64, ncclSum, comm->comm, ctx->stream));
+          timer_end(ctx, RCB_TIMER_EXCHANGE);
+          return RCB_OK;
+        };
+      st = rcbi_refine(ctx, F, d_out, lambda, (double*)gc, (double*)w_dev, [&](double* acc) { return accumulate(RCBI_RESIDUAL, acc); }, reduce,
+                       comm ? comm->world : 1);
+    }
     if (st != RCB_ERR_NUMERIC) break;
   }
   RCB_TRY(st);
@@ -336,7 +353,8 @@ int32_t rcb_train_sharded(rcb_esn* esn, rcb_comm* comm, const void* u, const voi
   // samples of the pooled fit: every rank holds T - washout per sequence (ragged shards differ by one sequence at most)
   const double samples = (double)(T - washout) * (double)B_local * (double)(comm ? comm->world : 1);
   return sharded_fit(esn, comm, lambda, samples, gram_mode, W_out, [&](int32_t mode, double* gc) {
-    return rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B_local, washout, mode, h0, gc, nullptr, hT_out, true);
+    const bool res = mode == RCBI_RESIDUAL;   // refinement pass: the factored buffer is kept, the carry has been handed back already
+    return rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B_local, washout, mode, h0, gc, nullptr, res ? nullptr : hT_out, !res);
   });
 }
 
@@ -381,7 +399,7 @@ int32_t rcb_train_time_chunked(rcb_esn* esn, rcb_comm* comm, const void* u, cons
   RCB_TRY(ctx_scratch(ctx, SCR_HT, (size_t)sumN * std::max<int64_t>(nb, 1) * esz, &hT_dev));
   RCB_CUDA(cudaMemsetAsync(hT_dev, 0, (size_t)sumN * esz, ctx->stream));
   int32_t st = sharded_fit(esn, comm, lambda, (double)(T - washout), gram_mode, W_out, [&](int32_t mode, double* gc) -> int32_t {
-    RCB_CUDA(cudaMemsetAsync(gc, 0, (size_t)esn->feat * (esn->feat + d_out) * sizeof(double), ctx->stream));
+    if (mode != RCBI_RESIDUAL) RCB_CUDA(cudaMemsetAsync(gc, 0, (size_t)esn->feat * (esn->feat + d_out) * sizeof(double), ctx->stream));
     if (nb > 0) {
       // window c starts `overlap` steps before its own samples; consecutive windows start Tc steps apart (and overlap): one gather
       const int64_t start = washout + lo * Tc - overlap;

@@ -184,59 +184,168 @@ __global__ void __launch_bounds__(256, 2) gram_dmma_kernel(const GramParams g) {
 // the targets of a sample block broadcast from shared memory, FP64 accumulators in registers — one pass over Z at memory
 // speed (r02: the 64 x 64-tiled kernel above spent 12.5 ms on config 5's 256 cross terms of 3 columns, 97 % of its MACs on
 // padding; this one is bound by reading Z once).
-template <typename TZ, typename TY>
+template <typename TZ, typename TY, int DO>
 __global__ void __launch_bounds__(128) cross_thin_kernel(const GramParams g) {
-  constexpr int SB = 64;   // samples per shared-memory block of targets
-  __shared__ double ys[SB][8];
+  constexpr int SB = 64, UN = 16;   // samples per shared-memory block of targets; feature loads in flight per thread
+  __shared__ double ys[SB][DO];
   const long long bz = (long long)blockIdx.z / g.splits, sz = (long long)blockIdx.z % g.splits;
   const TZ* A = reinterpret_cast<const TZ*>(g.A) + (size_t)bz * g.a_bstride;
   const TY* B = reinterpret_cast<const TY*>(g.B) + (size_t)bz * g.b_bstride;
   double* out = g.out + (size_t)bz * g.o_bstride;
   const long long f = (long long)blockIdx.x * 128 + threadIdx.x;
+  const bool fv = f < g.M;
   const int d_out = (int)g.Nc;
   const long long s_beg = sz * g.chunk, s_end = s_beg + g.chunk < g.Stot ? s_beg + g.chunk : g.Stot;
-  double acc[8];
+  double acc[DO];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) acc[o] = 0.0;
+  for (int o = 0; o < DO; ++o) acc[o] = 0.0;
+  // sample -> column of the F x (T * nseq) array, advanced incrementally (no 64-bit division in the loops)
+  long long seq = s_beg / g.Te, tin = s_beg % g.Te;
   for (long long s0 = s_beg; s0 < s_end; s0 += SB) {
     const int ns = (int)(s_end - s0 < SB ? s_end - s0 : SB);
     __syncthreads();
-    for (int e = threadIdx.x; e < SB * 8; e += 128) {
-      const int ss = e >> 3, o = e & 7;
+    for (int e = threadIdx.x; e < SB * DO; e += 128) {
+      const int ss = e / DO, o = e % DO;
       double v = 0.0;
       if (ss < ns && o < d_out) {
-        const long long s = s0 + ss, col = (s / g.Te) * g.T + g.washout + (s % g.Te);
-        v = (double)B[(size_t)col * g.ldb + o];
+        long long sq = seq, tt = tin + ss;
+        while (tt >= g.Te) { tt -= g.Te; ++sq; }
+        v = (double)B[(size_t)(sq * g.T + g.washout + tt) * g.ldb + o];
       }
       ys[ss][o] = v;
     }
     __syncthreads();
-    if (f < g.M) {
-      const long long c0 = (s0 / g.Te) * g.T + g.washout + (s0 % g.Te);
-      const bool contiguous = (s0 % g.Te) + ns <= g.Te;   // the block does not straddle a sequence boundary
-#pragma unroll 4
-      for (int ss = 0; ss < ns; ++ss) {
-        long long col = c0 + ss;
-        if (!contiguous) { const long long s = s0 + ss; col = (s / g.Te) * g.T + g.washout + (s % g.Te); }
-        const double z = (double)A[(size_t)col * g.lda + f];
+    for (int s1 = 0; s1 < ns; s1 += UN) {
+      TZ z[UN];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = fma(z, ys[ss][o], acc[o]);
+      for (int q = 0; q < UN; ++q) {   // UN independent loads in flight before the first FMA
+        long long sq = seq, tt = tin + s1 + q;
+        while (tt >= g.Te) { tt -= g.Te; ++sq; }
+        z[q] = (fv && s1 + q < ns) ? A[(size_t)(sq * g.T + g.washout + tt) * g.lda + f] : TZ(0);
+      }
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const double zd = (double)z[q];
+#pragma unroll
+        for (int o = 0; o < DO; ++o) acc[o] = fma(zd, ys[(s1 + q) & (SB - 1)][o], acc[o]);
       }
     }
+    tin += ns;
+    while (tin >= g.Te) { tin -= g.Te; ++seq; }
   }
-  if (f < g.M)
-    for (int o = 0; o < d_out; ++o) atomicAdd(out + (size_t)o * g.ldo + f, acc[o]);
+  if (fv) {
+#pragma unroll
+    for (int o = 0; o < DO; ++o)
+      if (o < d_out) atomicAdd(out + (size_t)o * g.ldo + f, acc[o]);
+  }
 }
 
 template <typename TZ, typename TY>
 static int32_t launch_cross_thin(rcb_ctx* ctx, GramParams g) {
   const long long fb = (g.M + 127) / 128;
-  long long splits = (8LL * ctx->sm_count + fb * g.nbatch - 1) / (fb * g.nbatch);
+  long long splits = (16LL * ctx->sm_count + fb * g.nbatch - 1) / (fb * g.nbatch);
   splits = std::max<long long>(1, std::min<long long>(splits, (g.Stot + 255) / 256));
   if (g.nbatch * splits > 65535) splits = std::max<long long>(1, 65535 / g.nbatch);
   g.chunk = ((g.Stot + splits - 1) / splits + 63) / 64 * 64;
   g.splits = (g.Stot + g.chunk - 1) / g.chunk;
-  cross_thin_kernel<TZ, TY><<<dim3((unsigned)fb, 1, (unsigned)(g.nbatch * g.splits)), 128, 0, ctx->stream>>>(g);
+  const dim3 grid((unsigned)fb, 1, (unsigned)(g.nbatch * g.splits));
+  if (g.Nc <= 4) cross_thin_kernel<TZ, TY, 4><<<grid, 128, 0, ctx->stream>>>(g);
+  else cross_thin_kernel<TZ, TY, 8><<<grid, 128, 0, ctx->stream>>>(g);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+// ---- iterative refinement: residual targets E[:, col] = y_col - W z_col for the samples of the set ---------------------------
+// SB samples per CTA iteration share every load of W (d_out x F, FP64, L2-resident); the features of a sample are read
+// once, coalesced along the contiguous feature axis; FP64 accumulation, warp-shuffle + shared-memory reduction.
+template <typename TZ, typename TY, int DO>
+__global__ void __launch_bounds__(256) residual_e_kernel(const double* __restrict__ W, const TZ* __restrict__ Z, long long ldz,
+                                                         const TY* __restrict__ Y, long long ldy, long long F, long long T,
+                                                         long long washout, long long Te, long long Stot, int d_out,
+                                                         double* __restrict__ E) {
+  // one warp = SB samples at a time, lanes along the contiguous feature axis, UN feature strides per pass: SB * UN
+  // independent 128-byte loads in flight per warp, every load of W (L1-resident) shared by the SB samples
+  constexpr int SB = 4, UN = 4;
+  const int lane = threadIdx.x & 31;
+  const long long wg = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 8;
+  for (long long s0 = wg * SB; s0 < Stot; s0 += nw * SB) {
+    long long col[SB];
+    {
+      long long sq = s0 / Te, tt = s0 % Te;
+#pragma unroll
+      for (int q = 0; q < SB; ++q) {
+        col[q] = sq * T + washout + tt;
+        if (s0 + q + 1 < Stot && ++tt == Te) { tt = 0; ++sq; }
+      }
+    }
+    double acc[SB][DO];
+#pragma unroll
+    for (int q = 0; q < SB; ++q)
+#pragma unroll
+      for (int o = 0; o < DO; ++o) acc[q][o] = 0.0;
+    for (long long f0 = lane; f0 < F; f0 += 32 * UN) {
+      TZ z[UN][SB];
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int q = 0; q < SB; ++q) z[u][q] = f0 + 32 * u < F ? Z[(size_t)col[q] * ldz + f0 + 32 * u] : TZ(0);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        double w[DO];
+#pragma unroll
+        for (int o = 0; o < DO; ++o) w[o] = (o < d_out && f0 + 32 * u < F) ? __ldg(W + (size_t)(f0 + 32 * u) * d_out + o) : 0.0;
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+          const double zd = (double)z[u][q];
+#pragma unroll
+          for (int o = 0; o < DO; ++o) acc[q][o] = fma(w[o], zd, acc[q][o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < SB; ++q)
+#pragma unroll
+      for (int o = 0; o < DO; ++o) {
+        double v = acc[q][o];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0 && o < d_out && s0 + q < Stot) E[(size_t)col[q] * d_out + o] = (double)Y[(size_t)col[q] * ldy + o] - v;
+      }
+  }
+}
+
+__global__ void refine_init_kernel(const double* __restrict__ W, long long F, int d_out, double lambda, double* __restrict__ R, long long ldr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F * d_out) return;
+  const long long f = i % F, o = i / F;
+  R[(size_t)o * ldr + f] = -lambda * W[(size_t)f * d_out + o];
+}
+
+__global__ void __launch_bounds__(256) refine_update_kernel(double* __restrict__ W, const double* __restrict__ delta, long long n, double* norms) {
+  double d2 = 0.0, w2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = delta[i], w = W[i] + d;
+    W[i] = w;
+    d2 = fma(d, d, d2); w2 = fma(w, w, w2);
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) { d2 += __shfl_xor_sync(0xffffffffu, d2, sh); w2 += __shfl_xor_sync(0xffffffffu, w2, sh); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(norms, d2); atomicAdd(norms + 1, w2); }
+}
+
+int32_t launch_refine_init(rcb_ctx* ctx, const double* W, int64_t F, int64_t d_out, double lambda, double* R, int64_t ldr) {
+  const long long n = F * d_out;
+  refine_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(W, F, (int)d_out, lambda, R, ldr);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
+}
+
+int32_t launch_refine_update(rcb_ctx* ctx, double* W, const double* delta, int64_t n, double* norms) {
+  RCB_CUDA(cudaMemsetAsync(norms, 0, 2 * sizeof(double), ctx->stream));
+  const int grid = (int)std::min<long long>((n + 255) / 256, 4LL * ctx->sm_count);
+  refine_update_kernel<<<grid, 256, 0, ctx->stream>>>(W, delta, n, norms);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
@@ -299,6 +408,33 @@ int32_t launch_gram_fp64(rcb_ctx* ctx, const GramArgs& a) {
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
+}
+
+int32_t launch_ridge_residual(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt, int64_t d_out,
+                              int64_t ldy, int64_t T, int64_t washout, int64_t nseq, const double* W, double* R, int64_t ldr) {
+  if (d_out > 8) return fail(RCB_ERR_UNSUPPORTED, "iterative refinement supports d_out <= 8");
+  const long long Te = T - washout, Stot = Te * nseq;
+  if (Stot <= 0) return RCB_OK;
+  void* e = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_RESID, (size_t)d_out * T * nseq * sizeof(double), &e));
+  const int grid = (int)std::min<long long>((Stot + 31) / 32, 16LL * ctx->sm_count);   // 8 warps x 4 samples per CTA pass
+  const bool z64 = zdt == RCB_F64, y64 = ydt == RCB_F64;
+#define RCB_RES(TZ, TY)                                                                                                                   \
+  do {                                                                                                                                    \
+    if (d_out <= 4) residual_e_kernel<TZ, TY, 4><<<grid, 256, 0, ctx->stream>>>(W, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e); \
+    else residual_e_kernel<TZ, TY, 8><<<grid, 256, 0, ctx->stream>>>(W, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e);            \
+  } while (0)
+  if (!z64 && !y64) RCB_RES(float, float);
+  else if (!z64 && y64) RCB_RES(float, double);
+  else if (z64 && !y64) RCB_RES(double, float);
+  else RCB_RES(double, double);
+#undef RCB_RES
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  GramArgs c;   // R += Z E' with the thin cross-term kernel
+  c.A = Z; c.a_dtype = zdt; c.M = F; c.lda = ldz; c.Bm = e; c.b_dtype = RCB_F64; c.Nc = d_out; c.ldb = d_out;
+  c.T = T; c.washout = washout; c.nseq = nseq; c.out = R; c.ldo = ldr; c.lower_only = false;
+  return launch_gram_fp64(ctx, c);
 }
 
 // ---- P(npos x S) = Wp(npos x K) * Z(K x S), all column-major FP32 ------------------------------

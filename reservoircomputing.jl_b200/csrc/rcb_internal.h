@@ -5,6 +5,7 @@
 
 #include <complex>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/rcb200.h"
@@ -161,6 +162,9 @@ struct rcb_ctx {
                                    // solved with (< 0: unknown).  RCB_GRAM_AUTO takes the tensor-core Gram — 22-bit fixed-point
                                    // states — only when it is >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE; gram_int8.cu skips its
                                    // lowest-order digit product under the same condition
+  const double* refine_W = nullptr;   // readout (d_out x F, device) the RCBI_RESIDUAL accumulation pass evaluates
+  int refine_steps = 0;               // refinement passes of the most recent fit (diagnostics)
+  double refine_last = 0.0;           // |delta| / |W| of its last correction
   int last_gram_tensor = 0;   // 1 when the most recent Gram ran on the tcgen05 path  // variant name of the most recent recurrence launch
   void* timer_pools = nullptr;  // rcb::TimerPool[RCB_TIMER_COUNT]
   bool timers_muted = false;    // set while a pipelined region times itself as a whole
@@ -198,6 +202,7 @@ enum { SCR_U = 0, SCR_STATES = 1, SCR_H = 2, SCR_Y = 3, SCR_GC = 4, SCR_TMP = 5,
        SCR_SOLVE = 25,                              // solve.cu: padded copy of one system
        SCR_PACK = 20,                               // comm.cu: packed [G | C] / gathered factors
        SCR_CHUNK_U = 21, SCR_CHUNK_Y = 22, SCR_CHUNK_UW = 23, SCR_CHUNK_YW = 24,   // comm.cu: staged series + window batches
+       SCR_RESID = 26, SCR_DELTA = 27,              // iterative refinement: residual targets E, correction + norms
        SCR_COUNT = 32 };
 int32_t ctx_scratch(rcb_ctx* ctx, int slot, size_t bytes, void** out);
 int32_t ctx_pinned(rcb_ctx* ctx, size_t bytes, void** out);
@@ -265,6 +270,18 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
                                    int64_t nmem, int64_t z_stride, int64_t y_stride, int64_t g_stride);
 
 int32_t launch_replicate_blocks(rcb_ctx* ctx, double* base, int64_t elems, int32_t copies, int64_t nblocks);
+// Iterative refinement of a ridge solution on the EXACT normal equations (corrected semi-normal equations):
+//   R(F x d_out, ld = ldr) += sum over the sample set of z_s (y_s - W z_s)'   — exact products, FP64 accumulation; one pass over Z
+int32_t launch_ridge_residual(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t F, int64_t ldz, const void* Y, int32_t ydt, int64_t d_out,
+                              int64_t ldy, int64_t T, int64_t washout, int64_t nseq, const double* W, double* R, int64_t ldr);
+int32_t launch_refine_init(rcb_ctx* ctx, const double* W, int64_t F, int64_t d_out, double lambda, double* R, int64_t ldr);   // R = -lambda W'
+// W += delta (n elements); norms[0] = |delta|^2, norms[1] = |W + delta|^2 (device, zeroed by the call)
+int32_t launch_refine_update(rcb_ctx* ctx, double* W, const double* delta, int64_t n, double* norms);
+// internal accumulation mode of accumulate_device / rcbi_train_accumulate: the "accumulator" is the factored [L | rhs] buffer
+// of a finished solve and the pass adds the exact residual of ctx->refine_W into its rhs slot
+constexpr int32_t RCBI_RESIDUAL = 100;
+// solve.cu: triangular solves only, on a buffer launch_ridge_solve has already factored in place (rhs slot = new right-hand sides)
+int32_t launch_cholesky_resolve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double* W_out);
 // feature plumbing (dense_kernels.cu): symmetric fill + scale of a lower-triangle Gram, Extend, DelayLayer over time
 int32_t launch_sym_scale(rcb_ctx* ctx, const double* G, int64_t F, double scale, int32_t dtype, void* out);
 int32_t launch_extend(rcb_ctx* ctx, const void* u, int64_t d_in, const void* x, int64_t n, int64_t cols, int32_t dtype, void* out);
@@ -327,4 +344,8 @@ int32_t rcbi_train_accumulate(rcb_esn* esn, const void* u, const void* targets, 
                               bool zero_first);
 // accumulator (destroyed) -> W (d_out x F, device)
 int32_t rcbi_solve_device(rcb_ctx* ctx, bool qr, double* GC, int64_t F, int64_t d_out, double lambda, double* w_dev);
+// iterative refinement of a Cholesky-on-Gram solution on the exact normal equations (api.cu); `pass` adds this rank's exact
+// residual into the rhs slot of the factored buffer, `reduce` (may be empty) sums that slot over `world` ranks
+int32_t rcbi_refine(rcb_ctx* ctx, int64_t F, int64_t d_out, double lambda, double* gc, double* w_dev,
+                    const std::function<int32_t(double*)>& pass, const std::function<int32_t(double*, int64_t)>& reduce, int world);
 }

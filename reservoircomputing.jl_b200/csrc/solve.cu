@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __re
 // (nullptr: every system uses lambda0); W_out: nsys x (d_out x F) on the device; info_out (host, nsys ints, may be null)
 // receives 0 or the 1-based feature of the first non-positive pivot.  Returns RCB_ERR_NUMERIC if any system failed.
 // lda_in: leading dimension of every system (0 -> F); stride_in: doubles between systems (0 -> lda * (F + d_out)).
-int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
-                                   int64_t nsys, double* W_out, int* info_out, int64_t lda_in, int64_t stride_in) {
+static int32_t ridge_solve_impl(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
+                                int64_t nsys, double* W_out, int* info_out, int64_t lda_in, int64_t stride_in, bool factored) {
   if (nsys < 1) return RCB_OK;
   if (nsys > 65535) return fail(RCB_ERR_UNSUPPORTED, "at most 65535 systems per batched solve");
   void* tmp = nullptr;
@@ -344,7 +344,7 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
   timer_begin(ctx, RCB_TIMER_SOLVE);
   const long long lda = lda_in > 0 ? lda_in : F, stride = stride_in > 0 ? stride_in : lda * (F + d_out);
   const unsigned nz = (unsigned)nsys;
-  for (long long k0 = 0; k0 < F; k0 += 2 * NBLK) {
+  for (long long k0 = 0; k0 < F && !factored; k0 += 2 * NBLK) {
     // panel pair (k0, k0 + 32): factor the first, bring the second's own 32 columns up to date, factor it, then apply both
     // to the rest of the trailing matrix in one pass
     potrf_diag_kernel<<<dim3(1, 1, nz), NBLK * NBLK, 0, ctx->stream>>>(GC, lda, F, k0, lambda0, lam, stride, d_info);
@@ -428,6 +428,16 @@ int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t 
                 nsys > 1 ? (" #" + std::to_string(z)).c_str() : "", info[(size_t)z]);
   }
   return st;
+}
+
+int32_t launch_ridge_solve_batched(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double lambda0, const double* lambdas,
+                                   int64_t nsys, double* W_out, int* info_out, int64_t lda_in, int64_t stride_in) {
+  return ridge_solve_impl(ctx, GC, F, d_out, lambda0, lambdas, nsys, W_out, info_out, lda_in, stride_in, false);
+}
+// The two triangular sweeps alone, on a buffer that launch_ridge_solve has factored in place: L in the lower triangle, the rhs
+// slot (columns F .. F + d_out) filled with new right-hand sides — the correction step of the iterative refinement.
+int32_t launch_cholesky_resolve(rcb_ctx* ctx, double* GC, int64_t F, int64_t d_out, double* W_out) {
+  return ridge_solve_impl(ctx, GC, F, d_out, 0.0, nullptr, 1, W_out, nullptr, 0, 0, true);
 }
 
 // Leading dimension the factorisation works with.  A padded column stride (against DRAM bank camping of power-of-two

@@ -15,7 +15,7 @@ RCB_F32, RCB_F64 = 0, 1
 ACT_IDENTITY, ACT_TANH, ACT_TANH_FAST, ACT_SIGMOID, ACT_RELU = 0, 1, 2, 3, 4
 MOD_NLAT1, MOD_NLAT2, MOD_NLAT3, MOD_PAD, MOD_PARTIAL_SQUARE, MOD_EXTENDED_SQUARE = 1, 2, 3, 4, 5, 6
 GRAM_AUTO, GRAM_FP64, GRAM_TENSOR, FIT_QR = 0, 1, 2, 3
-TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, TIMER_EXCHANGE = 0, 1, 2, 3
+TIMER_RECURRENCE, TIMER_GRAM, TIMER_SOLVE, TIMER_EXCHANGE, TIMER_REFINE = 0, 1, 2, 3, 4
 COMM_ID_BYTES = 128
 MAX_MODIFIERS, MAX_LAYERS = 8, 8
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "rcb_ctx_launch_count": (_I32, [_P, C.POINTER(_I64)]),
     "rcb_ctx_last_kernel": (_I32, [_P, C.c_char_p, _I32]),
     "rcb_ctx_last_kernel_ms": (_I32, [_P, _I32, C.POINTER(C.c_float)]),
+    "rcb_ctx_last_refine": (_I32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "rcb_esn_create": (_I32, [_P, C.POINTER(EsnDesc), C.POINTER(LayerDesc), C.POINTER(_P)]),
     "rcb_esn_destroy": (_I32, [_P]),
     "rcb_esn_feature_dims": (_I32, [_P, C.POINTER(_I32)]),

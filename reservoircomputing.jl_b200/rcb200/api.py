@@ -206,6 +206,12 @@ class Device:
         check(lib().rcb_ctx_sm_count(self.handle, C.byref(n)))
         return n.value
 
+    def last_refine(self):
+        """(refinement passes, |delta W| / |W| of the last one) of the most recent AUTO ridge fit on this context."""
+        n, r = C.c_int32(0), C.c_double(0.0)
+        check(lib().rcb_ctx_last_refine(self.handle, C.byref(n), C.byref(r)))
+        return int(n.value), float(r.value)
+
     def last_kernel(self) -> str:
         buf = C.create_string_buffer(128)
         check(lib().rcb_ctx_last_kernel(self.handle, buf, 128))

@@ -178,3 +178,66 @@ def test_train_members_qr_fallback(R):
                 Wref = O.train_ridge_qr(so[:, 50:], Y[:, 50:], lam)
                 pred, pred_o = W[b, li] @ so[:, 50:].astype(np.float64), Wref @ so[:, 50:].astype(np.float64)
                 assert np.linalg.norm(pred - pred_o) / np.linalg.norm(pred_o) <= 1e-4, (mode, b, lam)
+
+
+# ---- iterative refinement of the Cholesky-on-Gram solution (corrected semi-normal equations) ----------------
+@pytest.fixture(scope="module")
+def esn_states(R):
+    """Real reservoir features: N = 512 NLAT2 states of a Lorenz-driven ESN (strongly correlated, cond(G) ~ 1e12)."""
+    rng = np.random.default_rng(512)
+    N, T, w = 512, 2100, 100
+    esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=1.0, sparsity=6 / N), state_modifiers=R.NLAT2)
+    ps, st = R.setup(rng, esn)
+    series = O.lorenz_series(T + 1)
+    data = np.asfortranarray(series[:, :T].astype(np.float32))
+    target = np.asfortranarray(series[:, 1:T + 1].astype(np.float32))
+    states, _ = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, [np.zeros(N, np.float32)]))
+    return dict(esn=esn, ps=ps, st=st, data=data, target=target, Z=np.asfortranarray(states[:, w:]), Y=np.asfortranarray(target[:, w:]), w=w)
+
+
+@pytest.mark.parametrize("lam", [1e-2, 1e-4, 1e-6])
+def test_auto_refines_tensor_gram_to_qr_grade_weights(R, esn_states, lam, monkeypatch):
+    """The tensor-core Gram is the Gram of states rounded to 22-bit fixed point: its raw Cholesky solution is off by
+    ~2^-23 / (lambda per sample) (8.8e-3 at lambda = 1e-2, S = 2000).  AUTO corrects it with exact residuals: the WEIGHTS then
+    meet the 1e-4 tolerance against the oracle's Float64 QR on the same states."""
+    Z, Y = esn_states["Z"], esn_states["Y"]
+    Wref = O.train_ridge_qr(Z, Y, lam)
+    monkeypatch.setenv("RCB_GRAM", "tensor")          # force AUTO onto the tensor path at this (small) size
+    W = R.fit_readout(R.RidgeRegression(lam), Z, Y)
+    steps, last = R.default_device().last_refine()
+    assert steps >= 1 and last <= 1e-3
+    assert rel(W, Wref) <= WEIGHT_RTOL, (lam, steps, last)
+    monkeypatch.setenv("RCB_REFINE", "0")             # the raw solution, for the record: outside the tolerance
+    W0 = R.fit_readout(R.RidgeRegression(lam), Z, Y)
+    assert R.default_device().last_refine()[0] == 0
+    assert rel(W0, Wref) > rel(W, Wref)
+    if lam <= 1e-2:
+        assert rel(W0, Wref) > WEIGHT_RTOL
+
+
+@pytest.mark.parametrize("lam", [1e-6, 1e-8])
+def test_auto_refines_fp64_cholesky_at_small_lambda(R, esn_states, lam, monkeypatch):
+    """Cholesky on the exact Gram loses cond(G + lambda I) * eps; one or two corrections on the exact normal equations
+    bring the weights to QR grade (error ~ cond(design) * eps)."""
+    Z, Y = esn_states["Z"], esn_states["Y"]
+    Wref = O.train_ridge_qr(Z, Y, lam)
+    monkeypatch.setenv("RCB_GRAM", "fp64")
+    W = R.fit_readout(R.RidgeRegression(lam), Z, Y)
+    assert R.default_device().last_refine()[0] >= 1
+    assert rel(W, Wref) <= WEIGHT_RTOL, lam
+
+
+def test_train_refines_end_to_end(R, esn_states, monkeypatch):
+    """train() (fused: collect -> Gram -> solve -> refinement passes that re-run the recurrence) against the oracle's QR on
+    the oracle-equal states; windows forced so that the residual pass walks several chunks."""
+    e = esn_states
+    lam = 1e-3
+    st0 = fixed_h0(R, e["st"], e["esn"], [np.zeros(512, np.float32)])
+    Wref = O.train_ridge_qr(e["Z"], e["Y"], lam)
+    monkeypatch.setenv("RCB_GRAM", "tensor")
+    for budget in (None, "3"):                        # 3 MB: the time-chunked accumulation path (1.5k-step windows)
+        if budget:
+            monkeypatch.setenv("RCB_TRAIN_BUDGET_MB", budget)
+        ps2, _ = R.train(e["esn"], e["data"], e["target"], e["ps"], st0, objective=R.RidgeRegression(lam), washout=e["w"])
+        assert R.default_device().last_refine()[0] >= 1
+        assert rel(ps2.readout.weight, Wref) <= WEIGHT_RTOL, budget
