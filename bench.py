@@ -417,6 +417,35 @@ def other_configs(R, dev, cpu=True):
         out["C4"] = {"train_s": tt, "device": dev_ms(), "kernel": dev.last_kernel()}
     except Exception as e:  # noqa: BLE001
         out["C4"] = {"error": repr(e)[:200]}
+    try:  # a shape OUTSIDE the specialised kernel: N = 2048, 1024 sequences, cell bias, per-neuron leak, NLAT2
+        import torch
+        from rcb200 import _lib as L
+        from rcb200.api import _Handle
+
+        N, B, T = 2048, 1024, 1000
+        rng = np.random.default_rng(7)
+        esn = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), use_bias=True,
+                    leak_coefficient=rng.uniform(0.3, 1.0, N).astype(np.float32), state_modifiers=R.NLAT2)
+        ps, st = R.setup(rng, esn)
+        hh = _Handle(esn, ps, np.float32, dev)
+        u = torch.from_numpy(np.ascontiguousarray(lorenz_batch(B, T, seed=9).transpose(2, 1, 0))).cuda()
+        h0 = torch.zeros((B, N), dtype=torch.float32, device="cuda")
+        ring = torch.empty((B, T, hh.F), dtype=torch.float32, device="cuda")
+        ms = []
+        for _ in range(4):
+            L.check(R.lib().rcb_collect(hh.handle, L.ptr(u), T, B, L.ptr(h0), L.ptr(ring), L.ptr(h0)))
+            torch.cuda.synchronize()
+            ms.append(dev.kernel_ms(0))
+        k1 = float(np.median(ms[1:]))
+        alg = 4.0 * hh.F * T * B + 4.0 * 3 * T * B
+        pk = peaks()
+        out["k1_generic_shape"] = {"workload": "N=2048, 1024 sequences x 1000 steps, cell bias, per-neuron leak, NLAT2 (8.4 GB of states per pass >> L2)",
+                                   "kernel": dev.last_kernel(), "k1_ms": k1, "value": float(N) * T * B / (k1 * 1e-3), "unit": "neuron-steps/s",
+                                   "roofline": {"bound": "hbm", "achieved": alg / (k1 * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                "frac": alg / (k1 * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+        del ring, u, h0
+    except Exception as e:  # noqa: BLE001
+        out["k1_generic_shape"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -325,6 +325,15 @@ RCB_API int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targe
                           int64_t washout, int32_t n_lambda, const double* lambdas, int32_t gram_mode, const void* h0,
                           double* W_out, void* hT_out);
 
+/* ---- single model step --------------------------------------------------------------------------
+ * Replaces one call of the model, (rc)(inp, ps, st) (src/reservoircomputer.jl:90-94): __partial_apply — the cell step
+ * cell((inp, (h,)), ps, st) (src/layers/esn_cell.jl:175-184) and the state modifiers — followed by the readout.
+ *   u d_in x B (one column per sequence), h_inout sumN x B carry (NULL: zero start), features_out F x B (data dtype, may be
+ *   NULL), y_out out_dims x B Float64 (may be NULL: __partial_apply only; non-NULL needs an installed readout).
+ * One launch of the recurrence kernel with T = 1 plus the readout kernel: launch-latency bound (~10 us); loops belong in
+ * rcb_collect / rcb_predict_*. */
+RCB_API int32_t rcb_step(rcb_esn* esn, const void* u, int64_t B, void* h_inout, void* features_out, double* y_out);
+
 /* ---- K4: predict --------------------------------------------------------------------------------
  * Teacher-forced: replaces __predict(reservoir, rc, data::AbstractMatrix, ps, st)
  * (src/predict.jl:163-177): y_t = readout(modifiers(cell(u_t))).  u: d_in x T x B.

@@ -1241,6 +1241,12 @@ int32_t rcbi_train_accumulate(rcb_esn* esn, const void* u, const void* targets, 
     if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
     return RCB_OK;
   }
+  if (gram_mode == RCBI_RESIDUAL && ctx->cache_states_enable && ctx->cache_states && ctx->cache_u == u && ctx->cache_T == T && ctx->cache_B == B) {
+    // the whole state array of this very call is still in scratch (one chunk): the residual pass reads it instead of
+    // running the recurrence again
+    return accumulate_device(ctx, false, ctx->cache_states, esn->desc.data_dtype, F, F, y_dev, targets_dtype, d_out, d_out, T, washout, B, gram_mode, gc_dev);
+  }
+  ctx->cache_states = nullptr;
   void* st_dev = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_STATES, (size_t)F * Tc * Bc * esz, &st_dev));
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
@@ -1266,6 +1272,7 @@ int32_t rcbi_train_accumulate(rcb_esn* esn, const void* u, const void* targets, 
       }
     }
   }
+  if (ctx->cache_states_enable && Bc == B && Tc == T) { ctx->cache_states = st_dev; ctx->cache_u = u; ctx->cache_T = T; ctx->cache_B = B; }
   if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
   return RCB_OK;
 }
@@ -1328,6 +1335,11 @@ int32_t rcb_train(rcb_esn* esn, const void* u, const void* targets, int32_t targ
     if (gram_mode == RCB_GRAM_AUTO) { modes[nm++] = RCB_GRAM_FP64; modes[nm++] = RCB_FIT_QR; }
   }
   int32_t st = RCB_OK;
+  struct CacheScope {   // states of a single-chunk accumulation stay valid for the refinement passes of this call only
+    rcb_ctx* c;
+    explicit CacheScope(rcb_ctx* x) : c(x) { c->cache_states_enable = true; c->cache_states = nullptr; }
+    ~CacheScope() { c->cache_states_enable = false; c->cache_states = nullptr; }
+  } cache_scope(ctx);
   for (int32_t i = 0; i < nm; ++i) {
     if (i > 0 && modes[i] == RCB_GRAM_FP64 && !ctx->last_gram_tensor) continue;
     RCB_TRY(rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B, washout, modes[i], h0, (double*)gc, states_out, hT_out, true));
@@ -1560,6 +1572,47 @@ static int32_t predict_common(rcb_esn* esn, const void* u, int64_t T, int64_t B,
     RCB_TRY(launch_predict(ctx, a));
   }
   if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, y_bytes));
+  if (h_inout && h_dev != h_inout) RCB_TRY(from_device(ctx, h_inout, h_dev, h_bytes));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RCB_OK;
+}
+
+int32_t rcb_step(rcb_esn* esn, const void* u, int64_t B, void* h_inout, void* features_out, double* y_out) {
+  RCB_TRY(check_ready(esn));
+  if (!u) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  if (B < 1) return fail(RCB_ERR_ARGUMENT, "batch must have at least one sequence, got %lld.", (long long)B);
+  if (y_out && !esn->d_Wout) return fail(RCB_ERR_ARGUMENT, "the readout has not been trained or set (addreadout!)");
+  if (y_out && esn->readout_members > 1) return fail(RCB_ERR_UNSUPPORTED, "rcb_step applies one shared readout");
+  rcb_ctx* ctx = esn->ctx;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  timers_reset(ctx);
+  const size_t dsz = esn->desc.data_dtype == RCB_F64 ? 8 : 4;
+  const void* u_dev = nullptr;
+  RCB_TRY(stage_in(ctx, SCR_U, u, (size_t)esn->desc.in_dims * B * dsz, &u_dev));
+  const size_t h_bytes = (size_t)esn->sumN * B * dsz, f_bytes = (size_t)esn->feat * B * dsz;
+  void* h_dev = nullptr;
+  if (h_inout && is_device_ptr(h_inout)) h_dev = h_inout;
+  else {
+    RCB_TRY(ctx_scratch(ctx, SCR_H, h_bytes, &h_dev));
+    if (h_inout) RCB_CUDA(cudaMemcpyAsync(h_dev, h_inout, h_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else RCB_CUDA(cudaMemsetAsync(h_dev, 0, h_bytes, ctx->stream));
+  }
+  void* z_dev = features_out && is_device_ptr(features_out) ? features_out : nullptr;
+  if (!z_dev) RCB_TRY(ctx_scratch(ctx, SCR_STATES, f_bytes, &z_dev));
+  RCB_TRY(collect_device(esn, u_dev, 1, B, h_dev, z_dev, h_dev, 0));
+  if (y_out) {
+    double* y_dev = y_out;
+    const size_t y_bytes = (size_t)esn->desc.out_dims * B * sizeof(double);
+    if (!is_device_ptr(y_out)) {
+      void* p = nullptr;
+      RCB_TRY(ctx_scratch(ctx, SCR_TGT, y_bytes, &p));
+      y_dev = (double*)p;
+    }
+    RCB_TRY(launch_readout(ctx, esn->d_Wout, esn->d_bout, esn->desc.readout_activation, z_dev, esn->desc.data_dtype, esn->feat, B,
+                           (int)esn->desc.out_dims, y_dev));
+    if (y_dev != y_out) RCB_TRY(from_device(ctx, y_out, y_dev, y_bytes));
+  }
+  if (features_out && z_dev != features_out) RCB_TRY(from_device(ctx, features_out, z_dev, f_bytes));
   if (h_inout && h_dev != h_inout) RCB_TRY(from_device(ctx, h_inout, h_dev, h_bytes));
   RCB_CUDA(cudaStreamSynchronize(ctx->stream));
   return RCB_OK;

@@ -352,6 +352,11 @@ int32_t rcb_train_sharded(rcb_esn* esn, rcb_comm* comm, const void* u, const voi
   timers_reset(ctx);
   // samples of the pooled fit: every rank holds T - washout per sequence (ragged shards differ by one sequence at most)
   const double samples = (double)(T - washout) * (double)B_local * (double)(comm ? comm->world : 1);
+  struct CacheScope {   // (as in rcb_train: a single-chunk accumulation keeps its states for the refinement passes)
+    rcb_ctx* c;
+    explicit CacheScope(rcb_ctx* x) : c(x) { c->cache_states_enable = true; c->cache_states = nullptr; }
+    ~CacheScope() { c->cache_states_enable = false; c->cache_states = nullptr; }
+  } cache_scope(ctx);
   return sharded_fit(esn, comm, lambda, samples, gram_mode, W_out, [&](int32_t mode, double* gc) {
     const bool res = mode == RCBI_RESIDUAL;   // refinement pass: the factored buffer is kept, the carry has been handed back already
     return rcbi_train_accumulate(esn, u, targets, targets_dtype, T, B_local, washout, mode, h0, gc, nullptr, res ? nullptr : hT_out, !res);

@@ -346,23 +346,26 @@ __global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ Z
   Z += (size_t)blockIdx.z * z_stride;       // member
   amax += (size_t)blockIdx.z * ldp;
   const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB < Sc ? sl0 + SLAB : Sc;
-  float mx[VEC];
+  // maxima as bit patterns of |z| (non-negative floats order like integers) — NaN and Inf rank above every finite value
+  // instead of being dropped by fmaxf, so a diverged reservoir is seen by phase_select_kernel
+  int mx[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) mx[v] = 0.f;
+  for (int v = 0; v < VEC; ++v) mx[v] = 0;
 #pragma unroll 8
   for (long long sl = sl0; sl < sl1; ++sl) {
     const long long s = s0 + sl;
     const long long col = (s / Te) * T + washout + (s % Te);
     if constexpr (VEC == 4) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(Z + (size_t)col * ldz + f));
-      mx[0] = fmaxf(mx[0], fabsf(x.x)); mx[1] = fmaxf(mx[1], fabsf(x.y)); mx[2] = fmaxf(mx[2], fabsf(x.z)); mx[3] = fmaxf(mx[3], fabsf(x.w));
+      mx[0] = max(mx[0], __float_as_int(fabsf(x.x))); mx[1] = max(mx[1], __float_as_int(fabsf(x.y)));
+      mx[2] = max(mx[2], __float_as_int(fabsf(x.z))); mx[3] = max(mx[3], __float_as_int(fabsf(x.w)));
     } else {
-      mx[0] = fmaxf(mx[0], fabsf(__ldg(Z + (size_t)col * ldz + f)));
+      mx[0] = max(mx[0], __float_as_int(fabsf(__ldg(Z + (size_t)col * ldz + f))));
     }
   }
 #pragma unroll
   for (int v = 0; v < VEC; ++v)
-    if (f + v < F) atomicMax(amax + f + v, __float_as_int(mx[v]));
+    if (f + v < F) atomicMax(amax + f + v, mx[v]);
 }
 
 __device__ __forceinline__ void digits(float x, float qs, int& a1, int& a2, int& a3) {
@@ -478,7 +481,10 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
 // above the term it restores: || sum_s a3 a3' ||_2 <~ 1.2e-8 S s_max^2 (a3 uniform in [-128, 127], Marchenko-Pastur edge),
 // s_max = 2^e_max the largest feature scale.  With lambda >= 1e-6 s_max^2 PER SAMPLE the term is below 2 % of lambda: skipped.
 // lambda unknown (< 0): all nine products.
-__global__ void phase_select_kernel(const int* __restrict__ amax, long long n, double lambda, int* nphase) {
+// Non-finite states (a diverged reservoir: identity / relu activation with a radius above 1) cannot be quantised: no MMA
+// phase runs (nphase = 0) and the accumulators are poisoned with NaN, so the solve fails with RCB_ERR_NUMERIC exactly as it
+// does after the exact FP64 kernel, which propagates the NaN by itself.
+__global__ void phase_select_kernel(const int* __restrict__ amax, long long n, double lambda, int* nphase, double* G, long long g_stride, int nmem) {
   __shared__ int smax;
   if (threadIdx.x == 0) smax = 0;
   __syncthreads();
@@ -487,6 +493,11 @@ __global__ void phase_select_kernel(const int* __restrict__ amax, long long n, d
   atomicMax(&smax, mx);
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (smax >= 0x7F800000) {
+      *nphase = 0;
+      for (int m = 0; m < nmem; ++m) G[(size_t)m * g_stride] = __longlong_as_double(0x7FF8000000000000LL);
+      return;
+    }
     const float m = __int_as_float(smax);
     int e = 0;
     if (m > 0.f && m < INFINITY) frexpf(m, &e);
@@ -587,7 +598,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     {
       double lam = ctx->gram_lambda_hint;
       if (const char* e = getenv("RCB_GRAM_PHASES")) lam = atoi(e) == 2 ? 1e300 : -1.0;  // testing hook: force 2 / 3 phases
-      phase_select_kernel<<<1, 1024, 0, ctx->stream>>>(amax, ldp * nmem, lam, d_nphase);
+      phase_select_kernel<<<1, 1024, 0, ctx->stream>>>(amax, ldp * nmem, lam, d_nphase, G, g_stride, (int)nmem);
       ctx->launches++;
     }
     p.nphase = d_nphase;

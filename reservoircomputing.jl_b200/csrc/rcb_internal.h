@@ -162,6 +162,9 @@ struct rcb_ctx {
                                    // solved with (< 0: unknown).  RCB_GRAM_AUTO takes the tensor-core Gram — 22-bit fixed-point
                                    // states — only when it is >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE; gram_int8.cu skips its
                                    // lowest-order digit product under the same condition
+  // states kept from a single-chunk accumulation so that the refinement passes of the same call need not re-run the
+  // recurrence: enabled by callers whose passes repeat ONE rcbi_train_accumulate call on the same inputs
+  bool cache_states_enable = false; const void* cache_u = nullptr; const void* cache_states = nullptr; int64_t cache_T = 0, cache_B = 0;
   const double* refine_W = nullptr;   // readout (d_out x F, device) the RCBI_RESIDUAL accumulation pass evaluates
   int refine_steps = 0;               // refinement passes of the most recent fit (diagnostics)
   double refine_last = 0.0;           // |delta| / |W| of its last correction

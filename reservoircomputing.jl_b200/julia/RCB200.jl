@@ -193,6 +193,22 @@ function __collectstates(res::B200Reservoir, rc::AbstractReservoirComputer, data
     return states, store_carry(st, hT)
 end
 
+# ---- single model call: src/reservoircomputer.jl:81-94 -------------------------------------------------------------
+# `(rc)(inp, ps, st)` keeps running on the reference path (B200Reservoir forwards the cell call: one step is launch-latency
+# bound).  `step_b200` is the same call on the GPU — cell step + modifiers + readout in one rcb_step — for hosts that keep
+# everything else there; `partial = true` stops before the readout (`__partial_apply`).
+function step_b200(rc::ReservoirComputer{<:B200Reservoir}, inp::AbstractVector{T}, ps, st; partial::Bool = false) where {T <: Union{Float32, Float64}}
+    h = Handle(rc, ps, T)
+    partial || set_readout!(h, ps)
+    carry = initial_carry(rc, st, T)
+    feats = Vector{T}(undef, h.F)
+    y = partial ? nothing : Vector{Float64}(undef, rc.readout.out_dims)
+    check(ccall((:rcb_step, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}),
+                h.ptr, Vector{T}(inp), 1, carry, feats, partial ? C_NULL : y))
+    out = partial ? feats : Vector{promote_type(T, eltype(ps.readout.weight))}(y)
+    return out, store_carry(st, carry)
+end
+
 # ---- ridge: src/train.jl:100-198 ---------------------------------------------------------------------
 # The objective stays the reference's `RidgeRegression(λ)`; the GPU path is selected the way the reference selects any
 # other algorithm — through `solver` (train.jl:100-106, 149-198):
@@ -567,7 +583,7 @@ names `reservoir`, `state_modifiers`, `readout`).
 b200(rc::AbstractReservoirComputer) = ReservoirComputer(B200Reservoir(rc.reservoir), rc.state_modifiers, rc.readout)
 b200(rc::ReservoirComputing.DeepESN) = B200DeepESN(rc)
 
-export B200Reservoir, B200DeepESN, B200Ridge, B200Cholesky, B200QR, b200, gram_accumulate!, ridge_solve, Comm, comm_unique_id, allreduce_gc!,
+export B200Reservoir, B200DeepESN, B200Ridge, B200Cholesky, B200QR, b200, step_b200, gram_accumulate!, ridge_solve, Comm, comm_unique_id, allreduce_gc!,
        train_sharded, train_time_chunked, train_ensemble, spectral_radius_b200, scale_radius_b200!, delay_features, extend_features, correlation_matrix_b200
 
 end # module

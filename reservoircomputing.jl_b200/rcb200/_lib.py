@@ -108,6 +108,7 @@ SIGNATURES = {
     "rcb_train_members": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),
     "rcb_train_partial": (_I32, [_P, _P, _P, _I32, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "rcb_predict_teacher": (_I32, [_P, _P, _I64, _I64, _P, _P]),
+    "rcb_step": (_I32, [_P, _P, _I64, _P, _P, _P]),
     "rcb_predict_autoregressive": (_I32, [_P, _P, _I64, _I64, _I32, _P, _P]),
     "rcb_extend_features": (_I32, [_P, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "rcb_delay_features": (_I32, [_P, _P, _I32, _I64, _I64, _I64, _I32, _I32, _P, _I64, _P, _P]),

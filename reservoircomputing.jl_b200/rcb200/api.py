@@ -1201,6 +1201,37 @@ def predict(rc, steps_or_data, ps, st, *, initialdata=None, device: Optional[Dev
     return (Y[:, :, 0] if vec else Y), st2
 
 
+def apply(rc, inp, ps, st, device: Optional[Device] = None, partial: bool = False):
+    """One call of the model, ``(rc)(inp, ps, st)`` (src/reservoircomputer.jl:90-94): cell step + state modifiers
+    (``__partial_apply``, :81-88) + readout, on the GPU (rcb_step).  ``inp`` is a vector (d_in,) or one column per sequence
+    (d_in, B).  Returns (y, st') — or (features, st') with ``partial=True`` — with the carry threaded through ``st`` exactly as
+    a loop of such calls does in the reference (that loop is ``collectstates`` / ``predict``)."""
+    x = np.asarray(inp)
+    vec = x.ndim == 1
+    x = np.asfortranarray(x.reshape(x.shape[0], -1))
+    dtype = x.dtype if x.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    x = x.astype(dtype)
+    B = x.shape[1]
+    h = _handle(rc, ps, dtype, device)
+    h0, cell_sts = _initial_carry(rc, st, dtype, B)
+    feats = np.empty((h.F, B), dtype=dtype, order="F")
+    y = None
+    if not partial:
+        h.set_readout(ps.readout, rc.readout.use_bias)
+        y = np.empty((rc.readout.out_dims, B), dtype=np.float64, order="F")
+    check(lib().rcb_step(h.handle, ptr(x), B, ptr(h0), ptr(feats), ptr(y)))
+    st2 = _store_carry(rc, st, cell_sts, h0, vec)
+    if partial:
+        return (feats[:, 0] if vec else feats), st2
+    y = y.astype(np.promote_types(np.asarray(ps.readout.weight).dtype, dtype))
+    return (y[:, 0] if vec else y), st2
+
+
+def partial_apply(rc, inp, ps, st, device: Optional[Device] = None):
+    """``__partial_apply(rc, inp, ps, st)``: cell step + state modifiers, no readout (src/reservoircomputer.jl:81-88)."""
+    return apply(rc, inp, ps, st, device, partial=True)
+
+
 def resetcarry(rng, rc, st, init_carry=None):
     """resetcarry!(rng, rc, st; init_carry) — src/reservoircomputer.jl:207-232, esn_deep.jl:219-259."""
     new = []

@@ -236,3 +236,21 @@ def test_k3_large_solve_matches_lapack(R, F, d_out):
     Wref = sla.solve(G + lam * np.eye(F), C, assume_a="pos").T
     assert rel(W, Wref) <= 1e-9
     assert np.array_equal(GC[:, :F], G)  # the caller's accumulator is left intact
+
+
+def test_tensor_gram_reports_non_finite_states(R):
+    """A diverged reservoir (NaN / Inf features) must not turn into a finite but wrong readout on the tensor path: the
+    pre-pass ranks non-finite values above every finite maximum, no MMA phase runs, the accumulator is poisoned and the
+    solve fails like it does after the exact FP64 kernel (which propagates the NaN by itself)."""
+    rng = np.random.default_rng(3)
+    F, S = 256, 4096
+    Z = np.asfortranarray(np.tanh(rng.standard_normal((F, S))).astype(np.float32))
+    Y = np.asfortranarray(rng.standard_normal((2, S)).astype(np.float32))
+    for bad in (np.nan, np.inf):
+        Zb = Z.copy(order="F")
+        Zb[17, 1234] = bad
+        for mode in (R.GRAM_TENSOR, R.GRAM_FP64):
+            with pytest.raises(R.NumericError):
+                R.fit_readout(R.RidgeRegression(1e-3), Zb, Y, gram_mode=mode)
+    W = R.fit_readout(R.RidgeRegression(1e-3), Z, Y, gram_mode=R.GRAM_TENSOR)   # the clean data still fit
+    assert np.all(np.isfinite(W))

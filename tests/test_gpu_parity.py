@@ -1325,3 +1325,37 @@ def test_train_chunked_paths_match_unchunked(R, budget_mb, B, monkeypatch):
     ps_b, st_b = R.train(esn, data, tgt, ps, st0, objective=R.RidgeRegression(1e-2), washout=w)
     assert np.linalg.norm(ps_a.readout.weight - ps_b.readout.weight) <= 1e-9 * np.linalg.norm(ps_a.readout.weight)
     assert np.array_equal(st_a.reservoir.carry[0], st_b.reservoir.carry[0])
+
+
+# ---- single model call (rc)(inp, ps, st): src/reservoircomputer.jl:81-94 -------------------------------------------------
+@pytest.mark.parametrize("batch", [None, 5])
+def test_single_step_call_matches_a_loop_of_reference_steps(R, batch):
+    """`apply` = cell step + modifiers + readout on the GPU (rcb_step); a Python loop of such calls threads the carry through
+    `st` exactly like the reference's collectstates / teacher-forced predict loops do (reservoircomputer.jl:113-133)."""
+    rng = np.random.default_rng(90)
+    N, T = 120, 12
+    esn = R.ESN(3, N, 2, init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.1), leak_coefficient=0.7, use_bias=True,
+                state_modifiers=(R.NLAT2, R.Pad(1.0)))
+    ps, st = R.setup(rng, esn)
+    Wro = rng.standard_normal((2, N + 1))
+    ps, st = R.addreadout(esn, Wro, ps, st)
+    B = batch or 1
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    st = fixed_h0(R, st, esn, [h0 if batch else h0[:, 0]])
+    data = rng.standard_normal((3, T, B)).astype(np.float32)
+    layers = oracle_layers(R, esn, ps)
+    ys, zs = [], []
+    s = st
+    for t in range(T):
+        x = data[:, t, :] if batch else data[:, t, 0]
+        z, _ = R.partial_apply(esn, x, ps, s)            # does not advance `s` here: the next call re-runs the same step
+        y, s = R.apply(esn, x, ps, s)
+        ys.append(y); zs.append(z)
+    for b in range(B):
+        so, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        zb = np.stack([z[:, b] if batch else z for z in zs], axis=1)
+        yb = np.stack([y[:, b] if batch else y for y in ys], axis=1)
+        assert state_err(zb, so) <= 1e-5
+        assert np.max(np.abs(yb - Wro @ so.astype(np.float64))) <= 1e-5 * np.max(np.abs(yb))
+        carry = s.reservoir.carry[0]
+        assert np.max(np.abs((carry[:, b] if batch else carry) - hs[0])) <= 1e-5 * np.max(np.abs(hs[0]))
