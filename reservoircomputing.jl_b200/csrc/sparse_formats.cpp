@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cmath>
 #include <numeric>
 
@@ -314,6 +315,19 @@ int32_t sell_from_csr_balanced(const HostCsr& csr, int32_t nthreads, HostSell* o
       load[(size_t)best] += bw[(size_t)idx[(size_t)q]];
       cnt[(size_t)best]++;
     }
+  }
+  if (getenv("RCB_SCHED_DEBUG")) {   // where the padding comes from (entries)
+    long imb = 0, shortr = 0, pairing = 0;
+    for (int32_t gi = 0; gi < ngroups; ++gi) {
+      int mxl = 0, sum = 0, cntr = 0;
+      for (int u = 0; u < 16; ++u)
+        if (plan[(size_t)gi].rows[u] >= 0) { const int l = len(plan[(size_t)gi].rows[u]); mxl = std::max(mxl, l); sum += l; ++cntr; }
+      imb += (long)(plan[(size_t)gi].delta - mxl) * 16;
+      shortr += (long)mxl * 16 - sum;
+    }
+    for (int32_t m = 0; m < nblk; ++m) pairing += 16L * std::abs(plan[(size_t)2 * m].delta - plan[(size_t)2 * m + 1].delta);
+    fprintf(stderr, "[sched] nnz %lld: residue imbalance %ld, rows shorter than the group's longest %ld, unequal group pairs %ld\n",
+            (long long)csr.rowptr.back(), imb, shortr, pairing);
   }
   out->perm.assign((size_t)npos, 0xFFFF);
   out->blk_off.assign((size_t)nblk, 0);
