@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librcb200.so")
-SOURCES = ["api.cu", "comm.cu", "qr_solve.cu", "recurrence.cu", "recurrence_fast.cu", "recurrence_fast7.cu", "recurrence_single.cu", "recurrence_coop.cu", "dense_kernels.cu", "gram_int8.cu", "solve.cu", "spectral.cu", "sparse_formats.cpp"]
+SOURCES = ["api.cu", "comm.cu", "qr_solve.cu", "recurrence.cu", "recurrence_fast.cu", "recurrence_fast7.cu", "recurrence_single.cu", "recurrence_coop.cu", "recurrence_cluster.cu", "dense_kernels.cu", "gram_int8.cu", "solve.cu", "spectral.cu", "sparse_formats.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-cudart", "static"]

@@ -154,6 +154,9 @@ static void free_layer(Layer& L) {
   L.d_Ot = nullptr;
   cudaFree(L.d_Orow); cudaFree(L.d_csr_rowptr); cudaFree(L.d_csr_colind); cudaFree(L.d_csr_vals); cudaFree(L.d_Win_cm);
   L.d_Orow = nullptr; L.d_csr_rowptr = nullptr; L.d_csr_colind = nullptr; L.d_csr_vals = nullptr; L.d_Win_cm = nullptr;
+  cudaFree(L.cl.vals); cudaFree(L.cl.cols); cudaFree(L.cl.off); cudaFree(L.cl.width); cudaFree(L.d_rowpos);
+  L.cl = DevClusterEll{};
+  L.d_rowpos = nullptr;
 }
 
 template <typename V>
@@ -333,6 +336,29 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
     for (int d = 0; d < L.d_in; ++d)
       for (int r = 0; r < L.n; ++r) wcm[(size_t)d * L.n + r] = W_in[(size_t)d * ldwin + r];
     RCB_TRY(upload(wcm, &L.d_Win_cm));
+  }
+  {  // operands of the cluster kernel (recurrence_cluster.cu): per-CTA ELL slices by row, W_in by row, row -> position map
+    HostClusterEll he;
+    RCB_TRY(cluster_ell_from_csr(K, &he));
+    if (he.ok && L.cell != RCB_CELL_ES2N && L.cell != RCB_CELL_RESESN) {
+      RCB_TRY(upload(he.vals, &L.cl.vals));
+      RCB_TRY(upload(he.cols, &L.cl.cols));
+      RCB_TRY(upload(he.off, &L.cl.off));
+      RCB_TRY(upload(he.width, &L.cl.width));
+      L.cl.cs = he.cs; L.cl.rpc = he.rpc; L.cl.ntc = he.ntc;
+      L.cl.max_width = *std::max_element(he.width.begin(), he.width.end());
+      std::vector<int> rowpos((size_t)L.n, 0);
+      for (int p = 0; p < npos; ++p)
+        if (hs.perm[(size_t)p] != 0xFFFF) rowpos[hs.perm[(size_t)p]] = p;
+      RCB_TRY(upload(rowpos, &L.d_rowpos));
+      if (L.d_in <= 8 && !L.d_Win_cm) {
+        std::vector<float> wcm((size_t)L.n * L.d_in);
+        for (int d = 0; d < L.d_in; ++d)
+          for (int r = 0; r < L.n; ++r) wcm[(size_t)d * L.n + r] = W_in[(size_t)d * ldwin + r];
+        RCB_TRY(upload(wcm, &L.d_Win_cm));
+      }
+      L.cl.ok = he.vals.size() > 0 || L.n > 0;
+    }
   }
   L.weights_set = true;
   return RCB_OK;

@@ -96,6 +96,23 @@ struct HostFast {
   std::vector<uint32_t> warp_off;   // [nwarps] byte offset of the warp's stream
   std::vector<uint64_t> wwords;     // [nwarps] packed widths
 };
+// recurrence_cluster.cu: rows of W split over the 8 CTAs of a cluster, thread = row, ELL slice per CTA ([width][ntc], lane-major)
+struct HostClusterEll {
+  bool ok = false;
+  int cs = 8, rpc = 0, ntc = 0;   // cluster size, rows / threads per CTA
+  std::vector<int> off, width;
+  std::vector<float> vals;
+  std::vector<uint16_t> cols;
+};
+struct DevClusterEll {
+  bool ok = false;
+  int cs = 8, rpc = 0, ntc = 0, max_width = 0;
+  float* vals = nullptr;
+  uint16_t* cols = nullptr;
+  int* off = nullptr;
+  int* width = nullptr;
+};
+int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out);
 struct DevFast {
   bool ok = false;
   size_t stream_bytes = 0;    // bytes of `stream` (incl. the read-ahead slack)
@@ -129,6 +146,8 @@ struct Layer {
   DevFast fast4h;             // the same for the 512-thread schedule (N = 8192: 16 slabs per thread)
   float* d_Win4h = nullptr;
   uint16_t* d_permh = nullptr;
+  DevClusterEll cl;           // recurrence_cluster.cu
+  int* d_rowpos = nullptr;    // [n] row -> position of the installed schedule (inverse of sell.perm)
   float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
   float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
   float* d_bias = nullptr;  // [n] by row

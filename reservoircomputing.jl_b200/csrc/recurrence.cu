@@ -265,6 +265,8 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
   }
   if (a.dtype == RCB_F32 && !p.Ot) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
     bool launched = false;
+    const int32_t cl = launch_collect_cluster(ctx, p, L, &launched);
+    if (cl != RCB_OK || launched) return cl;
     const int32_t sg = launch_collect_single(ctx, p, L.fast4, L.d_Win4, &launched);
     if (sg != RCB_OK || launched) return sg;
     const int32_t f7 = launch_collect_fast7(ctx, p, L.fast4, L.d_Win4, L.fast4h, L.d_Win4h, L.d_permh, &launched);

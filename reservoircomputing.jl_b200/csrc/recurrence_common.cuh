@@ -184,6 +184,9 @@ int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f
 // recurrence_single.cu: autoregressive predict of a single-layer ESN, one sequence per CTA, W / W_in resident, y in registers
 int32_t launch_predict_auto(rcb_ctx* ctx, const PredictArgs& pa, bool* launched);
 
+// recurrence_cluster.cu: few sequences, each spread over a cluster of 8 SMs (state exchanged through distributed shared memory)
+int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched);
+
 // recurrence_coop.cu: ES2N / ResESN, one sequence, a cooperative grid with one barrier per step
 int32_t launch_collect_coop(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched);
 

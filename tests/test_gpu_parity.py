@@ -1041,7 +1041,7 @@ def test_single_sequence_kernel_parity(R, N, d_in, mod, B, T):
     h0 = rng.standard_normal((N, B)).astype(np.float32)
     dev = R.default_device()
     s1, st1 = R.collectstates(esn, np.asfortranarray(data[:, :T]), ps, fixed_h0(R, st, esn, [h0]))
-    assert "k1_single" in dev.last_kernel()
+    assert ("k1_cluster" if N >= 4096 else "k1_single") in dev.last_kernel()    # from N = 4096 on a sequence is spread over a cluster of 8 SMs
     s2, st2 = R.collectstates(esn, np.asfortranarray(data[:, T:]), ps, st1)      # continues from the stored carry
     states = np.concatenate([s1, s2], axis=1)
     layers = oracle_layers(R, esn, ps)
@@ -1359,3 +1359,51 @@ def test_single_step_call_matches_a_loop_of_reference_steps(R, batch):
         assert np.max(np.abs(yb - Wro @ so.astype(np.float64))) <= 1e-5 * np.max(np.abs(yb))
         carry = s.reservoir.carry[0]
         assert np.max(np.abs((carry[:, b] if batch else carry) - hs[0])) <= 1e-5 * np.max(np.abs(hs[0]))
+
+
+# ---- K1 cluster: one sequence spread over a thread-block cluster, state exchanged through distributed shared memory ------
+@pytest.mark.parametrize("N,d_in,mod,B,T,csize", [(64, 3, "nlat2", 1, 40, 2), (300, 1, "none", 3, 33, 4), (1100, 3, "nlat2_pad", 2, 25, 8), (2048, 3, "nlat3", 1, 20, 4),
+                                                   (4096, 1, "extsq", 2, 15, 8), (8192, 3, "nlat2", 1, 12, 8), (517, 2, "psq", 4, 30, 2)])
+def test_cluster_kernel_parity(R, monkeypatch, N, d_in, mod, B, T, csize):
+    """recurrence_cluster.cu forced at every size (by default it takes N >= 4096): rows not a multiple of the cluster / warp
+    size, every fused modifier, cell bias and per-neuron leak, several sequences (one cluster each), the carry and a second
+    call that continues from it."""
+    monkeypatch.setenv("RCB_K1_MODE", "cluster")
+    monkeypatch.setenv("RCB_CLUSTER_SIZE", str(csize))
+    rng = np.random.default_rng(N + 11 * B)
+    mods = dict(nlat2=(R.NLAT2,), none=(), nlat2_pad=(R.NLAT2, R.Pad(1.0)), nlat3=(R.NLAT3,), extsq=(R.ExtendedSquare,), psq=(R.PartialSquare(0.4),))[mod]
+    esn = R.ESN(d_in, N, d_in, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=N > 1500), use_bias=True,
+                init_bias=lambda r, *d: (0.1 * r.standard_normal(d)).astype(np.float32),
+                leak_coefficient=rng.uniform(0.3, 1.0, N).astype(np.float32) if N % 2 else 0.6, state_modifiers=mods)
+    ps, st = R.setup(rng, esn)
+    data = np.asfortranarray(rng.standard_normal((d_in, 2 * T, B)).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    dev = R.default_device()
+    s1, st1 = R.collectstates(esn, np.asfortranarray(data[:, :T]), ps, fixed_h0(R, st, esn, [h0]))
+    assert "k1_cluster" in dev.last_kernel()
+    s2, st2 = R.collectstates(esn, np.asfortranarray(data[:, T:]), ps, st1)
+    states = np.concatenate([s1, s2], axis=1)
+    layers = oracle_layers(R, esn, ps)
+    for b in range(B):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
+        assert np.max(np.abs(st2.reservoir.carry[0][:, b] - hs[0])) <= STATE_RTOL * np.max(np.abs(hs[0]))
+
+
+def test_cluster_kernel_deep_layers(R, monkeypatch):
+    """DeepESN through the cluster kernel: layers >= 2 read their precomputed input projection (stored in the position order
+    of the layer's schedule) through the row -> position map."""
+    monkeypatch.setenv("RCB_K1_MODE", "cluster")
+    rng = np.random.default_rng(77)
+    sizes = [160, 96, 224]
+    esn = R.DeepESN(3, sizes, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=0.08), leak_coefficient=(1.0, 0.7, 0.5),
+                    state_modifiers=(R.NLAT2, R.NLAT1, R.Pad(1.0)))
+    ps, st = R.setup(rng, esn)
+    T = 60
+    data = np.asfortranarray(rng.standard_normal((3, T)).astype(np.float32))
+    h0 = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    states, st2 = R.collectstates(esn, data, ps, fixed_h0(R, st, esn, h0))
+    ref, hs = O.collectstates(oracle_layers(R, esn, ps), data, h0)
+    assert state_err(states, ref) <= STATE_RTOL
+    for l in range(3):
+        assert np.max(np.abs(st2.cells[l].carry[0] - hs[l])) <= STATE_RTOL * np.max(np.abs(hs[l]))
