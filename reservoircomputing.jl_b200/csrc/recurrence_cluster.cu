@@ -56,9 +56,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// asynchronous store into (any) CTA of the cluster; completes 4 transaction bytes on the mbarrier `bar` of the same CTA
-__device__ __forceinline__ void st_async(uint32_t addr, float v, uint32_t bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(bar)
+// asynchronous 16-byte store into (any) CTA of the cluster; completes 16 transaction bytes on the mbarrier `bar` of the same
+// CTA.  Four rows per store (gathered with shuffles): every store is one update of the receiver's transaction count, and those
+// updates are what a step waits for (r02: one 4-byte store per row cost ~1.4 us per step at every N)
+__device__ __forceinline__ void st_async4(uint32_t addr, float v0, float v1, float v2, float v3, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(__float_as_uint(v0)), "r"(__float_as_uint(v1)), "r"(__float_as_uint(v2)), "r"(__float_as_uint(v3)), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -128,8 +131,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
     xb[i] = v;
     xb[a.npad + i] = v;
   }
-  const int row = (int)crank * a.rpc + tid;
-  const bool mine = tid < a.rpc && row < n;
+  const int row = (int)crank * a.rpc + tid;   // rpc == ntc == blockDim.x: rows beyond n are ghosts that send zeros
+  const bool mine = row < n;
   // per-row constants in registers
   float win[MAXDIN];
 #pragma unroll
@@ -150,11 +153,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
   const uint32_t bar0 = smem_addr(bars);
   uint32_t peer[CS], peer_bar[CS];
   {
-    const uint32_t mine_addr = smem_addr(xb + (mine ? row : 0));
+    const uint32_t mine_addr = smem_addr(xb + row);
 #pragma unroll
     for (int c = 0; c < CS; ++c) { peer[c] = map_to_cta(mine_addr, (uint32_t)c); peer_bar[c] = map_to_cta(bar0, (uint32_t)c); }
   }
-  const uint32_t step_bytes = (uint32_t)n * 4u;   // every valid row of the cluster sends 4 bytes into every CTA per step
+  const uint32_t step_bytes = (uint32_t)a.npad * 4u;   // every row slot of the cluster (npad = CS * ntc) lands in every CTA once per step
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -194,14 +197,18 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
       for (int d = 0; d < MAXDIN; ++d)
         if (d < a.d_in) un[d] = __ldg(u_g + (size_t)(t + 1) * a.d_in + d);
     }
+    float hn = 0.0f;
     if (mine) {
       float acc0 = 0.f, acc1 = 0.f;
-      int j = 0;
-      for (; j + 1 < width; j += 2) {   // (padded entries: value 0, column 0)
-        acc0 = fmaf(ev[(size_t)j * a.ntc + tid], cur[ec[(size_t)j * a.ntc + tid]], acc0);
-        acc1 = fmaf(ev[(size_t)(j + 1) * a.ntc + tid], cur[ec[(size_t)(j + 1) * a.ntc + tid]], acc1);
+      for (int j = 0; j < width; j += 4) {   // width is a multiple of 4 (padded entries: value 0, column 0); 4 independent chains
+        const uint16_t* cj = ec + (size_t)j * a.ntc + tid;
+        const float* vj = ev + (size_t)j * a.ntc + tid;
+        const int c0 = cj[0], c1 = cj[a.ntc], c2 = cj[2 * a.ntc], c3 = cj[3 * a.ntc];
+        const float v0 = vj[0], v1 = vj[a.ntc], v2 = vj[2 * a.ntc], v3 = vj[3 * a.ntc];
+        const float x0 = cur[c0], x1 = cur[c1], x2 = cur[c2], x3 = cur[c3];
+        acc0 = fmaf(v0, x0, acc0); acc1 = fmaf(v1, x1, acc1);
+        acc0 = fmaf(v2, x2, acc0); acc1 = fmaf(v3, x3, acc1);
       }
-      if (j < width) acc0 = fmaf(ev[(size_t)j * a.ntc + tid], cur[ec[(size_t)j * a.ntc + tid]], acc0);
       float x = acc0 + acc1 + bias;     // the bias belongs to the recurrent term (esn_cell.jl:179)
       if (a.pre_in) {
         x += pre;
@@ -213,11 +220,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
         x += wi;                        // W_in u + (W h + b), generics.jl:91-96
       }
       const float phi = is_tanh ? fast_tanh(x) : apply_act<float>(a.act, x);
-      const float hn = fmaf(lc, phi, oml * hold);   // esn_cell.jl:182
+      hn = fmaf(lc, phi, oml * hold);   // esn_cell.jl:182
       hold = hn;
-      const uint32_t nxt_off = (uint32_t)(((t + 1) & 1) * a.npad) * 4u, nxt_bar = 8u * (uint32_t)((t + 1) & 1);
+    }
+    {
+      const float v1 = __shfl_down_sync(0xffffffffu, hn, 1), v2 = __shfl_down_sync(0xffffffffu, hn, 2), v3 = __shfl_down_sync(0xffffffffu, hn, 3);
+      if ((tid & 3) == 0) {
+        const uint32_t nxt_off = (uint32_t)(((t + 1) & 1) * a.npad) * 4u, nxt_bar = 8u * (uint32_t)((t + 1) & 1);
 #pragma unroll
-      for (int c = 0; c < CS; ++c) st_async(peer[c] + nxt_off, hn, peer_bar[c] + nxt_bar);
+        for (int c = 0; c < CS; ++c) st_async4(peer[c] + nxt_off, hn, v1, v2, v3, peer_bar[c] + nxt_bar);
+      }
     }
   }
   if (a.hT && mine) a.hT[(size_t)seq * a.h_stride + a.h_off + row] = hold;
@@ -237,7 +249,7 @@ int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out) {
   if (const char* e = getenv("RCB_CLUSTER_SIZE")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) CS = v; }  // testing hook
   while (CS < CSMAX && (n + CS - 1) / CS > 1024) CS *= 2;
   out->cs = CS;
-  const int rpc = (n + CS - 1) / CS, ntc = (rpc + 31) / 32 * 32;
+  const int ntc = ((n + CS - 1) / CS + 31) / 32 * 32, rpc = ntc;   // whole warps of rows per CTA: every warp sends full 16-byte groups
   if (ntc > 1024) return RCB_OK;
   out->rpc = rpc; out->ntc = ntc;
   out->off.assign(CS, 0);
@@ -246,6 +258,7 @@ int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out) {
   for (int c = 0; c < CS; ++c) {
     int w = 0;
     for (int r = c * rpc; r < std::min(n, (c + 1) * rpc); ++r) w = std::max(w, (int)(csr.rowptr[r + 1] - csr.rowptr[r]));
+    w = (w + 3) / 4 * 4;   // the kernel walks four entries at a time
     out->off[(size_t)c] = (int)total;
     out->width[(size_t)c] = w;
     total += (size_t)w * ntc;
@@ -281,7 +294,7 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
                                                       // 1.1 / 1.8 / 3.4 / 8.1 of one CTA — the exchange has a ~1.4 us floor, so only large N gains
   if (p.pre_in && !L.d_rowpos) return RCB_OK;
   ClusterArgs a{};
-  a.n = p.n; a.npad = (p.n + 3) & ~3; a.d_in = p.pre_in ? 0 : p.d_in; a.feat = p.raw ? p.n : p.feat; a.act = p.act;
+  a.n = p.n; a.npad = e.cs * e.ntc; a.d_in = p.pre_in ? 0 : p.d_in; a.feat = p.raw ? p.n : p.feat; a.act = p.act;
   a.rpc = e.rpc; a.ntc = e.ntc; a.npos = p.npos; a.T = p.T;
   a.mod = p.mod;
   if (p.raw) { a.mod.kind = 0; a.mod.has_pad = 0; }
