@@ -245,7 +245,7 @@ int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out) {
   out->ok = false;
   if (n > 65535) return RCB_OK;
   // cluster size: 8 SMs from N = 4096 on; smaller reservoirs exchange less and a smaller cluster has the cheaper barrier
-  int CS = n >= 4096 ? 8 : n >= 2048 ? 4 : 2;
+  int CS = 8;   // measured (r02, us per step at N = 1024 / 2048 / 4096 with 2 | 4 | 8 SMs): 1.39 1.13 1.13 / 2.52 1.64 1.43 / - 2.48 1.85
   if (const char* e = getenv("RCB_CLUSTER_SIZE")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) CS = v; }  // testing hook
   while (CS < CSMAX && (n + CS - 1) / CS > 1024) CS *= 2;
   out->cs = CS;
@@ -290,8 +290,8 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
   if (!e.ok || p.Ot || p.member_scale || p.member_leak || (p.d_in > MAXDIN && !p.pre_in)) return RCB_OK;
   const int CS = e.cs;
   if (p.B * CS > ctx->sm_count) return RCB_OK;        // more sequences than clusters: one CTA per sequence fills the machine
-  if (!forced && p.n < 4096) return RCB_OK;           // measured (r02): 1.4 / 1.6 / 1.8 / 2.9 us per step at N = 1024 / 2048 / 4096 / 8192 against
-                                                      // 1.1 / 1.8 / 3.4 / 8.1 of one CTA — the exchange has a ~1.4 us floor, so only large N gains
+  if (!forced && p.n < 2048) return RCB_OK;           // measured (r02): 1.13 / 1.43 / 1.85 / 2.9 us per step at N = 1024 / 2048 / 4096 / 8192 against
+                                                      // 1.22 / 1.83 / 3.6 / 8.1 of one CTA — the exchange has a ~1.1 us floor, so only large N gains
   if (p.pre_in && !L.d_rowpos) return RCB_OK;
   ClusterArgs a{};
   a.n = p.n; a.npad = e.cs * e.ntc; a.d_in = p.pre_in ? 0 : p.d_in; a.feat = p.raw ? p.n : p.feat; a.act = p.act;
