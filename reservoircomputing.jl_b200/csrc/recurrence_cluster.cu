@@ -107,8 +107,26 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return fabsf(x) < 0.15f ? tp : fmaf(-2.0f, r, 1.0f);
 }
 
-template <int CS>
-__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster_kernel(const ClusterArgs a) {
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (uint32_t)v;
+}
+
+// DIN: input rows known at compile time (1, 3), 0 = deep layer (precomputed projection), 9 = any d_in <= MAXDIN at run time.
+// MODK: 0 = states as they are, 2 = NLAT2, 9 = any fused modifier chain (run-time switch).
+// One warp per scheduler is the normal case here (128 .. 1024 threads per CTA), so every instruction on the per-step path is
+// exposed latency: the first generic version spent 1.1 k cycles per step on ~1000 instructions of run-time dispatch and
+// 64-bit index arithmetic (clock64 instrumentation of thread 0, N = 1024: wait 276, output 627, gather + update 1111,
+// send 242 cycles per step) — hence the compile-time variants and plain 32-bit shared-memory addresses below.
+// NTMAX: CTA width the variant is compiled for (512: 128 registers per thread, room for the register-resident rows; 1024: 64).
+template <int CS, int DIN, int MODK, int NTMAX>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NTMAX, 1) k1_cluster_kernel(const ClusterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* xb = reinterpret_cast<float*>(smem);                 // [2][npad] full state, double-buffered
   uint32_t crank;
@@ -123,7 +141,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
   {
     const float* gv = a.ell_vals + a.ell_off[crank];
     const uint16_t* gc = a.ell_cols + a.ell_off[crank];
-    for (int i = tid; i < width * a.ntc; i += blockDim.x) { ev[i] = __ldg(gv + i); ec[i] = __ldg(gc + i); }
+    for (int i = tid; i < width * a.ntc; i += blockDim.x) { ev[i] = __ldg(gv + i); ec[i] = (uint16_t)(__ldg(gc + i) * 4u); }   // byte offsets (n <= 16383)
   }
   const float* h0 = a.h0 ? a.h0 + (size_t)seq * a.h_stride + a.h_off : nullptr;
   for (int i = tid; i < a.npad; i += blockDim.x) {
@@ -134,30 +152,32 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
   const int row = (int)crank * a.rpc + tid;   // rpc == ntc == blockDim.x: rows beyond n are ghosts that send zeros
   const bool mine = row < n;
   // per-row constants in registers
-  float win[MAXDIN];
+  constexpr int ND = DIN == 9 ? MAXDIN : (DIN == 0 ? 1 : DIN);
+  float win[ND];
 #pragma unroll
-  for (int d = 0; d < MAXDIN; ++d) win[d] = (mine && a.Win && d < a.d_in) ? __ldg(a.Win + (size_t)d * n + row) : 0.0f;
+  for (int d = 0; d < ND; ++d) win[d] = (DIN != 0 && mine && d < a.d_in) ? __ldg(a.Win + (size_t)d * n + row) : 0.0f;
   const float bias = (mine && a.bias) ? __ldg(a.bias + row) : 0.0f;
   const float lc = (mine && a.leakv) ? __ldg(a.leakv + row) : a.leak;
   const float oml = 1.0f - lc;
   const bool is_tanh = a.act == RCB_ACT_TANH || a.act == RCB_ACT_TANH_FAST;
-  const float* u_g = a.u ? a.u + (size_t)seq * a.T * a.d_in : nullptr;
-  const float* pin = (a.pre_in && mine) ? a.pre_in + (size_t)seq * a.T * a.npos + __ldg(a.rowpos + row) : nullptr;
+  const float* u_g = DIN != 0 ? a.u + (size_t)seq * a.T * a.d_in : nullptr;
+  const float* pin = (DIN == 0 && mine) ? a.pre_in + (size_t)seq * a.T * a.npos + __ldg(a.rowpos + row) : nullptr;
   float pre = pin ? __ldg(pin) : 0.0f;                        // deep layers: the projection of the step about to run
-  float un[MAXDIN];
+  float un[ND];
 #pragma unroll
-  for (int d = 0; d < MAXDIN; ++d) un[d] = (u_g && !a.pre_in && d < a.d_in) ? __ldg(u_g + d) : 0.0f;
+  for (int d = 0; d < ND; ++d) un[d] = (DIN != 0 && d < a.d_in) ? __ldg(u_g + d) : 0.0f;
   float hold = (mine && h0) ? h0[row] : 0.0f;   // (not from xb: another thread of the CTA initialises that entry)
   // my slot in the next-state buffer of every CTA of the cluster (buffer 0; buffer 1 lies npad floats further), and that
   // CTA's pair of mbarriers (one per buffer)
-  const uint32_t bar0 = smem_addr(bars);
-  uint32_t peer[CS], peer_bar[CS];
-  {
-    const uint32_t mine_addr = smem_addr(xb + row);
+  const uint32_t bar0 = smem_addr(bars), xb0 = smem_addr(xb), buf_bytes = (uint32_t)a.npad * 4u;
+  constexpr bool PEER_REGS = NTMAX <= 512;   // (64 registers per thread at 1024 threads: the addresses are re-mapped per send)
+  const uint32_t mine_addr = xb0 + 4u * (uint32_t)row;
+  uint32_t peer[PEER_REGS ? CS : 1], peer_bar[PEER_REGS ? CS : 1];
+  if constexpr (PEER_REGS) {
 #pragma unroll
     for (int c = 0; c < CS; ++c) { peer[c] = map_to_cta(mine_addr, (uint32_t)c); peer_bar[c] = map_to_cta(bar0, (uint32_t)c); }
   }
-  const uint32_t step_bytes = (uint32_t)a.npad * 4u;   // every row slot of the cluster (npad = CS * ntc) lands in every CTA once per step
+  const uint32_t step_bytes = buf_bytes;   // every row slot of the cluster (npad = CS * ntc) lands in every CTA once per step
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -166,57 +186,97 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
     mbar_expect_tx(bar0, step_bytes);       // values of step 1 land in buffer 0
   }
   const int F = a.feat;
-  float* out_g = a.states ? a.states + (size_t)seq * a.T * F : nullptr;
+  float* po = a.states ? a.states + (size_t)seq * a.T * F + row : nullptr;   // my feature of the column about to be written
+  const uint32_t ev0 = smem_addr(ev) + 4u * (uint32_t)tid, ec0 = smem_addr(ec) + 2u * (uint32_t)tid;
+  const uint32_t vstride = (uint32_t)a.ntc * 4u, cstride = (uint32_t)a.ntc * 2u;
+  __syncthreads();   // the staged slice is complete
+  // The first WR entries of my row live in REGISTERS for the whole call (they never change): the per-step gather is then WR
+  // independent shared-memory loads issued back to back instead of a chain of three dependent loads per entry.  Longer rows
+  // (dense-ish reservoirs) continue in the shared-memory slice.
+  constexpr int WR = NTMAX <= 512 ? 16 : 0;   // (no room in 64 registers: the 1024-thread variant walks the shared-memory slice)
+  float rv[WR > 0 ? WR : 1];
+  uint32_t rcol[WR > 0 ? WR : 1];
+#pragma unroll
+  for (int j = 0; j < WR; ++j) {
+    rv[j] = j < width ? lds_f32(ev0 + (uint32_t)j * vstride) : 0.0f;
+    rcol[j] = j < width ? lds_u16(ec0 + (uint32_t)j * cstride) : 0u;
+  }
+  // entries the warp actually needs (rows of a warp differ in length: slots beyond the longest are skipped by the whole warp)
+  int wlen = 0;
+#pragma unroll
+  for (int j = 0; j < WR; ++j) wlen = rv[j] != 0.0f ? j + 1 : wlen;
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) wlen = max(wlen, __shfl_xor_sync(0xffffffffu, wlen, sh));
+  const bool pad_writer = a.mod.has_pad && crank == 0 && tid == 0;
   __syncthreads();
   cluster_arrive();   // every CTA's buffers and barriers are initialised before a peer sends into them
   cluster_wait();
   const int T = (int)a.T;
   // Iteration t: wait for the values of step t - 1 (buffer t & 1), write their modifier output, then run step t.
   for (int t = 0; t <= T; ++t) {
-    const float* cur = xb + (size_t)(t & 1) * a.npad;
+    const uint32_t cur = xb0 + (uint32_t)(t & 1) * buf_bytes;
     if (t > 0) {
       const uint32_t bar = bar0 + 8u * (uint32_t)(t & 1);
       mbar_wait(bar, (uint32_t)(((t - 1) >> 1) & 1));
       if (tid == 0 && t + 1 < T) mbar_expect_tx(bar, step_bytes);   // re-armed for the values of step t + 1 (same buffer)
-      if (out_g) {
+      if (po) {
         // collected column t - 1 = modifier(state after step t - 1): my rows, from the local copy of the full state
-        float* po = out_g + (size_t)(t - 1) * F;
         if (mine) {
-          __stcs(po + row, cl_feature(a.mod, cur, n, row));
-          if (a.mod.kind == RCB_MOD_EXTENDED_SQUARE) __stcs(po + n + row, cl_feature(a.mod, cur, n, n + row));
+          if constexpr (MODK == 0) {
+            __stcs(po, hold);                                      // (my own new value is still in a register)
+          } else if constexpr (MODK == 2) {                        // states.jl:277-285 (0-based): even f >= 2 -> x[f-1] * x[f-2]
+            float z = hold;
+            if ((row & 1) == 0 && row >= 2) z = lds_f32(cur + 4u * (uint32_t)row - 4u) * lds_f32(cur + 4u * (uint32_t)row - 8u);
+            __stcs(po, z);
+          } else {
+            const float* s = xb + (size_t)(t & 1) * a.npad;
+            __stcs(po, cl_feature(a.mod, s, n, row));
+            if (a.mod.kind == RCB_MOD_EXTENDED_SQUARE) __stcs(po + n, cl_feature(a.mod, s, n, n + row));
+          }
         }
-        if (a.mod.has_pad && crank == 0 && tid == 0) __stcs(po + a.mod.feat1, (float)a.mod.pad);
+        if (MODK == 9 && pad_writer) __stcs(po + a.mod.feat1, (float)a.mod.pad);
+        po += F;
       }
     }
     if (t == T) break;
-    float uc[MAXDIN];
+    float uc[ND];
 #pragma unroll
-    for (int d = 0; d < MAXDIN; ++d) uc[d] = un[d];
-    if (u_g && !a.pre_in && t + 1 < T) {
+    for (int d = 0; d < ND; ++d) uc[d] = un[d];
+    if (DIN != 0 && t + 1 < T) {
 #pragma unroll
-      for (int d = 0; d < MAXDIN; ++d)
-        if (d < a.d_in) un[d] = __ldg(u_g + (size_t)(t + 1) * a.d_in + d);
+      for (int d = 0; d < ND; ++d)
+        if (DIN != 9 || d < a.d_in) un[d] = __ldg(u_g + (size_t)(t + 1) * a.d_in + d);
     }
     float hn = 0.0f;
     if (mine) {
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int j = 0; j < width; j += 4) {   // width is a multiple of 4 (padded entries: value 0, column 0); 4 independent chains
-        const uint16_t* cj = ec + (size_t)j * a.ntc + tid;
-        const float* vj = ev + (size_t)j * a.ntc + tid;
-        const int c0 = cj[0], c1 = cj[a.ntc], c2 = cj[2 * a.ntc], c3 = cj[3 * a.ntc];
-        const float v0 = vj[0], v1 = vj[a.ntc], v2 = vj[2 * a.ntc], v3 = vj[3 * a.ntc];
-        const float x0 = cur[c0], x1 = cur[c1], x2 = cur[c2], x3 = cur[c3];
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < WR; j += 4) {
+        if (j < wlen) {   // warp-uniform
+          acc0 = fmaf(rv[j], lds_f32(cur + rcol[j]), acc0);
+          acc1 = fmaf(rv[j + 1], lds_f32(cur + rcol[j + 1]), acc1);
+          acc2 = fmaf(rv[j + 2], lds_f32(cur + rcol[j + 2]), acc2);
+          acc3 = fmaf(rv[j + 3], lds_f32(cur + rcol[j + 3]), acc3);
+        }
+      }
+      acc0 += acc2; acc1 += acc3;
+      uint32_t pv = ev0 + WR * vstride, pc = ec0 + WR * cstride;
+      for (int j = WR; j < width; j += 4) {   // width is a multiple of 4 (padded entries: value 0, column 0); 4 independent chains
+        const uint32_t c0_ = lds_u16(pc), c1_ = lds_u16(pc + cstride), c2_ = lds_u16(pc + 2 * cstride), c3_ = lds_u16(pc + 3 * cstride);
+        const float v0 = lds_f32(pv), v1 = lds_f32(pv + vstride), v2 = lds_f32(pv + 2 * vstride), v3 = lds_f32(pv + 3 * vstride);
+        const float x0 = lds_f32(cur + c0_), x1 = lds_f32(cur + c1_), x2 = lds_f32(cur + c2_), x3 = lds_f32(cur + c3_);
         acc0 = fmaf(v0, x0, acc0); acc1 = fmaf(v1, x1, acc1);
         acc0 = fmaf(v2, x2, acc0); acc1 = fmaf(v3, x3, acc1);
+        pv += 4 * vstride; pc += 4 * cstride;
       }
       float x = acc0 + acc1 + bias;     // the bias belongs to the recurrent term (esn_cell.jl:179)
-      if (a.pre_in) {
+      if constexpr (DIN == 0) {
         x += pre;
         if (t + 1 < T) pre = __ldg(pin + (size_t)(t + 1) * a.npos);
       } else {
         float wi = 0.f;
 #pragma unroll
-        for (int d = 0; d < MAXDIN; ++d) wi = fmaf(win[d], uc[d], wi);
+        for (int d = 0; d < ND; ++d) wi = fmaf(win[d], uc[d], wi);
         x += wi;                        // W_in u + (W h + b), generics.jl:91-96
       }
       const float phi = is_tanh ? fast_tanh(x) : apply_act<float>(a.act, x);
@@ -226,9 +286,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(1024, 1) k1_cluster
     {
       const float v1 = __shfl_down_sync(0xffffffffu, hn, 1), v2 = __shfl_down_sync(0xffffffffu, hn, 2), v3 = __shfl_down_sync(0xffffffffu, hn, 3);
       if ((tid & 3) == 0) {
-        const uint32_t nxt_off = (uint32_t)(((t + 1) & 1) * a.npad) * 4u, nxt_bar = 8u * (uint32_t)((t + 1) & 1);
+        const uint32_t nxt_off = (uint32_t)((t + 1) & 1) * buf_bytes, nxt_bar = 8u * (uint32_t)((t + 1) & 1);
 #pragma unroll
-        for (int c = 0; c < CS; ++c) st_async4(peer[c] + nxt_off, hn, v1, v2, v3, peer_bar[c] + nxt_bar);
+        for (int c = 0; c < CS; ++c) {
+          if constexpr (PEER_REGS) st_async4(peer[c] + nxt_off, hn, v1, v2, v3, peer_bar[c] + nxt_bar);
+          else st_async4(map_to_cta(mine_addr + nxt_off, (uint32_t)c), hn, v1, v2, v3, map_to_cta(bar0 + nxt_bar, (uint32_t)c));
+        }
       }
     }
   }
@@ -245,10 +308,9 @@ int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out) {
   out->ok = false;
   if (n > 65535) return RCB_OK;
   // cluster size: 8 SMs from N = 4096 on; smaller reservoirs exchange less and a smaller cluster has the cheaper barrier
-  int CS = 8;   // measured (r02, us per step at N = 1024 / 2048 / 4096 with 2 | 4 | 8 SMs): 1.39 1.13 1.13 / 2.52 1.64 1.43 / - 2.48 1.85
-  if (const char* e = getenv("RCB_CLUSTER_SIZE")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) CS = v; }  // testing hook
-  while (CS < CSMAX && (n + CS - 1) / CS > 1024) CS *= 2;
+  const int CS = CSMAX;   // measured (r02, us per step at N = 1024 / 2048 / 4096 with 2 | 4 | 8 SMs): 1.39 1.13 1.13 / 2.52 1.64 1.43 / - 2.48 1.85
   out->cs = CS;
+  if (n > 16383) return RCB_OK;   // the kernel keeps column byte offsets in 16 bits
   const int ntc = ((n + CS - 1) / CS + 31) / 32 * 32, rpc = ntc;   // whole warps of rows per CTA: every warp sends full 16-byte groups
   if (ntc > 1024) return RCB_OK;
   out->rpc = rpc; out->ntc = ntc;
@@ -266,14 +328,33 @@ int32_t cluster_ell_from_csr(const HostCsr& csr, HostClusterEll* out) {
   if (total > (size_t)1 << 30) return RCB_OK;
   out->vals.assign(total, 0.f);
   out->cols.assign(total, 0);
+  // Slot order inside a row is free: per warp (32 consecutive rows) and slot, every lane takes one of its remaining entries
+  // whose shared-memory bank (column mod 32) no earlier lane of the slot uses, if it has one — the gathers of a slot then
+  // spread over the banks instead of piling up 3-4 deep as 32 random columns do.
   for (int c = 0; c < CS; ++c)
-    for (int r = c * rpc; r < std::min(n, (c + 1) * rpc); ++r) {
-      const int tid = r - c * rpc;
-      int j = 0;
-      for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e, ++j) {
-        const size_t at = (size_t)out->off[(size_t)c] + (size_t)j * ntc + tid;
-        out->vals[at] = csr.vals[(size_t)e];
-        out->cols[at] = (uint16_t)csr.colind[(size_t)e];
+    for (int w0 = c * rpc; w0 < std::min(n, (c + 1) * rpc); w0 += 32) {
+      const int w1 = std::min(std::min(n, (c + 1) * rpc), w0 + 32);
+      std::vector<std::vector<int64_t>> left((size_t)(w1 - w0));
+      int wmax = 0;
+      for (int r = w0; r < w1; ++r) {
+        for (int64_t e = csr.rowptr[r]; e < csr.rowptr[r + 1]; ++e) left[(size_t)(r - w0)].push_back(e);
+        wmax = std::max(wmax, (int)left[(size_t)(r - w0)].size());
+      }
+      for (int j = 0; j < wmax; ++j) {
+        bool used[32] = {false};
+        for (int r = w0; r < w1; ++r) {
+          std::vector<int64_t>& L = left[(size_t)(r - w0)];
+          if (L.empty()) continue;
+          size_t pick = 0;
+          for (size_t q = 0; q < L.size(); ++q)
+            if (!used[csr.colind[(size_t)L[q]] & 31]) { pick = q; break; }
+          const int64_t e = L[pick];
+          L.erase(L.begin() + (long)pick);
+          used[csr.colind[(size_t)e] & 31] = true;
+          const size_t at = (size_t)out->off[(size_t)c] + (size_t)j * ntc + (size_t)(r - c * rpc);
+          out->vals[at] = csr.vals[(size_t)e];
+          out->cols[at] = (uint16_t)csr.colind[(size_t)e];
+        }
       }
     }
   out->ok = true;
@@ -290,7 +371,7 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
   if (!e.ok || p.Ot || p.member_scale || p.member_leak || (p.d_in > MAXDIN && !p.pre_in)) return RCB_OK;
   const int CS = e.cs;
   if (p.B * CS > ctx->sm_count) return RCB_OK;        // more sequences than clusters: one CTA per sequence fills the machine
-  if (!forced && p.n < 2048) return RCB_OK;           // measured (r02): 1.13 / 1.43 / 1.85 / 2.9 us per step at N = 1024 / 2048 / 4096 / 8192 against
+  if (!forced && p.n < 1024) return RCB_OK;           // measured (r02): 1.13 / 1.43 / 1.85 / 2.9 us per step at N = 1024 / 2048 / 4096 / 8192 against
                                                       // 1.22 / 1.83 / 3.6 / 8.1 of one CTA — the exchange has a ~1.1 us floor, so only large N gains
   if (p.pre_in && !L.d_rowpos) return RCB_OK;
   ClusterArgs a{};
@@ -307,15 +388,21 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
   if (!p.pre_in && p.d_in > 0 && !a.Win) return RCB_OK;
   const size_t smem = 2 * (size_t)a.npad * sizeof(float) + (size_t)e.max_width * e.ntc * (sizeof(float) + sizeof(uint16_t)) + 64;   // + the two mbarriers
   if (smem > ctx->smem_optin) return RCB_OK;
+  const int din_k = p.pre_in ? 0 : (p.d_in == 1 ? 1 : p.d_in == 3 ? 3 : 9);
+  const int mod_k = (a.mod.kind == 0 && !a.mod.has_pad) ? 0 : (a.mod.kind == RCB_MOD_NLAT2 && !a.mod.has_pad) ? 2 : 9;
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   cudaError_t err = cudaSuccess;
-#define RCB_CL(N_)                                                                                                     \
-  do {                                                                                                                 \
-    err = cudaFuncSetAttribute(k1_cluster_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-    if (err == cudaSuccess) k1_cluster_kernel<N_><<<(unsigned)(p.B * N_), e.ntc, smem, ctx->stream>>>(a);              \
+#define RCB_CLN(D_, M_, NT_)                                                                                                        \
+  do {                                                                                                                              \
+    err = cudaFuncSetAttribute(k1_cluster_kernel<CSMAX, D_, M_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (err == cudaSuccess) k1_cluster_kernel<CSMAX, D_, M_, NT_><<<(unsigned)(p.B * CSMAX), e.ntc, smem, ctx->stream>>>(a);         \
   } while (0)
-  if (CS == 8) RCB_CL(8); else if (CS == 4) RCB_CL(4); else RCB_CL(2);
+#define RCB_CL(D_, M_) do { if (e.ntc <= 512) RCB_CLN(D_, M_, 512); else RCB_CLN(D_, M_, 1024); } while (0)
+#define RCB_CLM(D_) do { if (mod_k == 0) RCB_CL(D_, 0); else if (mod_k == 2) RCB_CL(D_, 2); else RCB_CL(D_, 9); } while (0)
+  if (din_k == 0) RCB_CLM(0); else if (din_k == 1) RCB_CLM(1); else if (din_k == 3) RCB_CLM(3); else RCB_CLM(9);
+#undef RCB_CLM
 #undef RCB_CL
+#undef RCB_CLN
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (err != cudaSuccess) return fail(RCB_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(err), __FILE__, __LINE__);
   snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_cluster<%d SMs per sequence, %d rows per CTA> grid=%d", CS, e.rpc, (int)(p.B * CS));

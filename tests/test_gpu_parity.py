@@ -1041,7 +1041,7 @@ def test_single_sequence_kernel_parity(R, N, d_in, mod, B, T):
     h0 = rng.standard_normal((N, B)).astype(np.float32)
     dev = R.default_device()
     s1, st1 = R.collectstates(esn, np.asfortranarray(data[:, :T]), ps, fixed_h0(R, st, esn, [h0]))
-    assert ("k1_cluster" if N >= 2048 else "k1_single") in dev.last_kernel()    # from N = 2048 on a sequence is spread over a cluster of 8 SMs
+    assert ("k1_cluster" if N >= 1024 else "k1_single") in dev.last_kernel()    # from N = 1024 on a sequence is spread over a cluster of 8 SMs
     s2, st2 = R.collectstates(esn, np.asfortranarray(data[:, T:]), ps, st1)      # continues from the stored carry
     states = np.concatenate([s1, s2], axis=1)
     layers = oracle_layers(R, esn, ps)
