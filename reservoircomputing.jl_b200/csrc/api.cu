@@ -154,6 +154,8 @@ static void free_layer(Layer& L) {
   L.d_Ot = nullptr;
   cudaFree(L.d_Orow); cudaFree(L.d_csr_rowptr); cudaFree(L.d_csr_colind); cudaFree(L.d_csr_vals); cudaFree(L.d_Win_cm);
   L.d_Orow = nullptr; L.d_csr_rowptr = nullptr; L.d_csr_colind = nullptr; L.d_csr_vals = nullptr; L.d_Win_cm = nullptr;
+  cudaFree(L.d_bias_pos); cudaFree(L.d_leak_pos);
+  L.d_bias_pos = L.d_leak_pos = nullptr;
   cudaFree(L.cl.vals); cudaFree(L.cl.cols); cudaFree(L.cl.off); cudaFree(L.cl.width); cudaFree(L.d_rowpos);
   L.cl = DevClusterEll{};
   L.d_rowpos = nullptr;
@@ -324,6 +326,16 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
   if (L.desc.use_bias) {
     std::vector<float> b(bias, bias + L.n);
     RCB_TRY(upload(b, &L.d_bias));
+    std::vector<float> bp((size_t)npos, 0.f);   // the same by position (recurrence_fast7.cu)
+    for (int p = 0; p < npos; ++p)
+      if (hs.perm[(size_t)p] != 0xFFFF) bp[(size_t)p] = bias[hs.perm[(size_t)p]];
+    RCB_TRY(upload(bp, &L.d_bias_pos));
+  }
+  if (!L.h_leak.empty()) {   // a vector leak installed before the weights
+    std::vector<float> lp((size_t)npos, 1.f);
+    for (int p = 0; p < npos; ++p)
+      if (hs.perm[(size_t)p] != 0xFFFF) lp[(size_t)p] = L.h_leak[hs.perm[(size_t)p]];
+    RCB_TRY(upload(lp, &L.d_leak_pos));
   }
   RCB_TRY(install_orthogonal(esn, L));
   if (L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN) {  // operands of the cooperative kernel (recurrence_coop.cu)
@@ -724,6 +736,15 @@ int32_t rcb_esn_set_leak_vector(rcb_esn* esn, int32_t layer, const float* leak) 
   cudaFree(L.d_leak);
   L.d_leak = nullptr;
   std::vector<float> v(leak, leak + L.n);
+  L.h_leak = v;
+  cudaFree(L.d_leak_pos);
+  L.d_leak_pos = nullptr;
+  if (!L.h_perm.empty()) {   // the schedule is installed: the position-ordered copy for recurrence_fast7.cu
+    std::vector<float> lp(L.h_perm.size(), 1.f);
+    for (size_t p = 0; p < L.h_perm.size(); ++p)
+      if (L.h_perm[p] != 0xFFFF) lp[p] = leak[L.h_perm[p]];
+    RCB_TRY(upload(lp, &L.d_leak_pos));
+  }
   return upload(v, &L.d_leak);
 }
 

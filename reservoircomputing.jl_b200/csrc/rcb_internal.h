@@ -150,6 +150,8 @@ struct Layer {
   int* d_rowpos = nullptr;    // [n] row -> position of the installed schedule (inverse of sell.perm)
   float* d_Win = nullptr;   // [d_in][n] position-permuted when small (row = d, col = position)
   float* d_Win_cm = nullptr;  // N x d_in column-major as given (dense input projection GEMM)
+  float* d_bias_pos = nullptr;  // [npos] cell bias / per-neuron leak in the position order of the schedule (recurrence_fast7.cu)
+  float* d_leak_pos = nullptr;
   float* d_bias = nullptr;  // [n] by row
   float* d_leak = nullptr;  // [n] by row (vector leak) or nullptr
   bool weights_set = false;
@@ -159,6 +161,7 @@ struct Layer {
   HostCsr eff;                  // EuSN: W - W' - gamma I, what the kernels are built from (csr stays the user's W)
   std::vector<float> h_O;       // host copy of O, N x N column-major (kept: the position order comes from W)
   std::vector<uint16_t> h_perm; // position -> row of the installed schedule
+  std::vector<float> h_leak;    // host copy of a vector leak (the position-ordered device copy is rebuilt when the schedule changes)
   float* d_Ot = nullptr;        // [n][npos]: Ot[j*npos + pos] = O[perm[pos], j]
   // cooperative multi-SM kernel of the dense-operator cells (recurrence_coop.cu): O row-major, W as CSR, W_in by row
   float* d_Orow = nullptr;

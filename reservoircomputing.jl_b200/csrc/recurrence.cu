@@ -269,7 +269,7 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
     if (cl != RCB_OK || launched) return cl;
     const int32_t sg = launch_collect_single(ctx, p, L.fast4, L.d_Win4, &launched);
     if (sg != RCB_OK || launched) return sg;
-    const int32_t f7 = launch_collect_fast7(ctx, p, L.fast4, L.d_Win4, L.fast4h, L.d_Win4h, L.d_permh, &launched);
+    const int32_t f7 = launch_collect_fast7(ctx, p, L.fast4, L.d_Win4, L.fast4h, L.d_Win4h, L.d_permh, L.d_bias_pos, L.d_leak_pos, &launched);
     if (f7 != RCB_OK || launched) return f7;
     const int32_t fst = launch_collect_fast(ctx, p, L.fast, &launched);
     if (fst != RCB_OK || launched) return fst;

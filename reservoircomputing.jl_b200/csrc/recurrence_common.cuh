@@ -176,7 +176,7 @@ struct RecParams {
 int32_t launch_collect_fast(rcb_ctx* ctx, const RecParams& p, const DevFast& f, bool* launched);
 // recurrence_fast7.cu: the kernel specialised for 7 sequences per CTA, N in {4096, 8192}, 3 inputs, tanh, none/NLAT2
 int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, const DevFast& f4h,
-                             const float* Win4h, const uint16_t* permh, bool* launched);
+                             const float* Win4h, const uint16_t* permh, const float* bias_pos, const float* leak_pos, bool* launched);
 
 // recurrence_single.cu: one sequence per CTA (B <= #SMs), instruction-lean; f4: the stream with column*4, Win4 may be null with pre_in
 int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, bool* launched);

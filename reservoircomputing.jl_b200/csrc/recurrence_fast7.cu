@@ -31,6 +31,8 @@ struct Fast7Args {
   const float* Win;             // [d_in][npos] planes by position: 12 B per row instead of 16 (every global byte costs the LSU
                                 // data pipe twice, request and fill: r02 ncu, 7.1 k of 29 k wavefronts per CTA-step are global)
   int npos;
+  const float* bias_pos;        // GEN variants: cell bias by position (or nullptr) ...
+  const float* leak_pos;        // ... and per-neuron leak by position (or nullptr: the scalar below)
   const uint16_t* perm;         // [npos] position -> row of the schedule this stream was built with
   float2 lc2, oml2, m2l2;       // (a, a), (1-a, 1-a), (-2a, -2a): packed operands straight from the constant bank
 };
@@ -113,7 +115,9 @@ __device__ __forceinline__ uint32_t ldg16u(const unsigned char* p) { return (uin
 
 // NPAD == N (multiple of 1024); MODK: 0 = states as they are, 2 = NLAT2; NT threads per CTA (512: 128 registers per
 // thread, 16 row slabs each; 1024: 64 registers, 8 slabs); DIN = input rows (3: Lorenz-shaped, 1: Mackey-Glass-shaped).
-template <int NPAD, int MODK, int NT, int DIN>
+// GEN: cell bias and / or per-neuron leak (one extra coalesced load each per row slab; the scalar-leak, bias-free C3 shape keeps
+// its own instantiation).
+template <int NPAD, int MODK, int NT, int DIN, bool GEN = false>
 __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, const Fast7Args fa) {
   using TL = Tile<NPAD>;
   constexpr int R = NPAD / NT;
@@ -316,6 +320,18 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
           a0 = ffma2(wz, up[2][0], a0); a1 = ffma2(wz, up[2][1], a1); a2 = ffma2(wz, up[2][2], a2); a3 = fmaf(wzz, us[2], a3);
         }
       }
+      float2 lc2 = fa.lc2, oml2 = fa.oml2, m2l2 = fa.m2l2;
+      if constexpr (GEN) {
+        if (fa.bias_pos) {   // the bias belongs to the recurrent term (esn_cell.jl:179)
+          const float b = __ldg(fa.bias_pos + k * NT + tid);
+          const float2 bb = make_float2(b, b);
+          a0 = fadd2(a0, bb); a1 = fadd2(a1, bb); a2 = fadd2(a2, bb); a3 += b;
+        }
+        if (fa.leak_pos) {
+          const float l = __ldg(fa.leak_pos + k * NT + tid), om = 1.0f - l, m2 = -2.0f * l;
+          lc2 = make_float2(l, l); oml2 = make_float2(om, om); m2l2 = make_float2(m2, m2);
+        }
+      }
       const float2 r0 = sigm2(a0), r1 = sigm2(a1), r2 = sigm2(a2);
       const float r3 = rcp_approx(ex2_approx(a3 * 2.8853900817779268f) + 1.0f);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -323,10 +339,10 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
       const float2 h0 = make_float2(__uint_as_float(o[0]), __uint_as_float(o[1]));
       const float2 h1 = make_float2(__uint_as_float(o[2]), __uint_as_float(o[3]));
       const float2 h2 = make_float2(__uint_as_float(o[4]), __uint_as_float(o[5]));
-      const float2 n0 = ffma2(fa.m2l2, r0, ffma2(fa.oml2, h0, fa.lc2));
-      const float2 n1 = ffma2(fa.m2l2, r1, ffma2(fa.oml2, h1, fa.lc2));
-      const float2 n2 = ffma2(fa.m2l2, r2, ffma2(fa.oml2, h2, fa.lc2));
-      const float n3 = fmaf(fa.m2l2.x, r3, fmaf(fa.oml2.x, __uint_as_float(o[6]), fa.lc2.x));
+      const float2 n0 = ffma2(m2l2, r0, ffma2(oml2, h0, lc2));
+      const float2 n1 = ffma2(m2l2, r1, ffma2(oml2, h1, lc2));
+      const float2 n2 = ffma2(m2l2, r2, ffma2(oml2, h2, lc2));
+      const float n3 = fmaf(m2l2.x, r3, fmaf(oml2.x, __uint_as_float(o[6]), lc2.x));
       o[0] = __float_as_uint(n0.x); o[1] = __float_as_uint(n0.y); o[2] = __float_as_uint(n1.x); o[3] = __float_as_uint(n1.y);
       o[4] = __float_as_uint(n2.x); o[5] = __float_as_uint(n2.y); o[6] = __float_as_uint(n3);
       TMEM_ST8(ta + (uint32_t)k * 8u, o);
@@ -378,13 +394,14 @@ __global__ void __launch_bounds__(NT, 1) k1_fast7_kernel(const RecParams p, cons
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-template <int NPAD, int MODK, int NT, int DIN>
+template <int NPAD, int MODK, int NT, int DIN, bool GEN = false>
 int32_t launch_one(rcb_ctx* ctx, const RecParams& p, const Fast7Args& fa, int grid) {
-  auto kern = k1_fast7_kernel<NPAD, MODK, NT, DIN>;
+  auto kern = k1_fast7_kernel<NPAD, MODK, NT, DIN, GEN>;
   const size_t smem = Tile<NPAD>::BYTES + 48 * sizeof(float) + 16;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NT, smem, ctx->stream>>>(p, fa);
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s,%dthr,din=%d> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", NT, DIN, grid);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_fast7<N=%d,%s,%dthr,din=%d%s> grid=%d", NPAD, MODK == 2 ? "nlat2" : "raw", NT, DIN,
+           GEN ? ",bias/leak-vector" : "", grid);
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   return RCB_OK;
@@ -395,33 +412,44 @@ int32_t launch_one(rcb_ctx* ctx, const RecParams& p, const Fast7Args& fa, int gr
 // Launches the specialised kernel when the call matches its shape; *launched stays false otherwise.
 // f4 / Win4 / perm: the stream built with the 1024-thread schedule; f4h / Win4h / permh: with the 512-thread schedule.
 int32_t launch_collect_fast7(rcb_ctx* ctx, const RecParams& p, const DevFast& f4, const float* Win4, const DevFast& f4h,
-                             const float* Win4h, const uint16_t* permh, bool* launched) {
+                             const float* Win4h, const uint16_t* permh, const float* bias_pos, const float* leak_pos, bool* launched) {
   *launched = false;
   const char* mode = getenv("RCB_K1_MODE");  // testing hook: fast7 | fast7_512 (or unset) use this kernel, anything else skips it
   const bool want512 = mode && !strcmp(mode, "fast7_512");  // 512 threads x 128 registers: measured 10 % slower than 1024 x 64
   if (mode && strcmp(mode, "fast7") && !want512) return RCB_OK;
   if (!f4.ok || !Win4 || !p.Win || p.pre_in || (p.d_in != 3 && p.d_in != 1) || p.nthreads != 1024) return RCB_OK;
-  if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.bias || p.leakv || p.member_scale || p.member_leak) return RCB_OK;
-  if (p.n != p.npad || (p.npad != 8192 && p.npad != 4096)) return RCB_OK;
+  if (!(p.act == RCB_ACT_TANH || p.act == RCB_ACT_TANH_FAST) || p.member_scale || p.member_leak) return RCB_OK;
+  if ((p.bias && !bias_pos) || (p.leakv && !leak_pos)) return RCB_OK;
+  const bool gen = p.bias || p.leakv;
+  if (p.n != p.npad || (p.npad != 8192 && p.npad != 4096 && p.npad != 2048)) return RCB_OK;
   if (p.B <= (long long)(NB - 1) * ctx->sm_count) return RCB_OK;  // fewer sequences: smaller tiles fill the machine better
   const int modk = p.raw || p.mod.kind == 0 ? 0 : p.mod.kind;
   if ((modk != 0 && modk != RCB_MOD_NLAT2) || (!p.raw && p.mod.has_pad)) return RCB_OK;
   const int grid = (int)((p.B + NB - 1) / NB);
   const float lc = (float)p.leak, oml = 1.0f - lc, m2l = -2.0f * lc;  // (1-a) in the input eltype, esn_cell.jl:186-200
-  const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192 && p.d_in == 3;
+  const bool half = f4h.ok && Win4h && permh && want512 && p.npad == 8192 && p.d_in == 3 && !gen;
   Fast7Args fa{half ? f4h.stream : f4.stream, half ? f4h.warp_off : f4.warp_off, half ? f4h.wwords : f4.wwords,
-               reinterpret_cast<const float4*>(half ? Win4h : Win4), p.Win, p.npos, half ? permh : p.perm, make_float2(lc, lc),
+               reinterpret_cast<const float4*>(half ? Win4h : Win4), p.Win, p.npos, p.bias ? bias_pos : nullptr, p.leakv ? leak_pos : nullptr,
+               half ? permh : p.perm, make_float2(lc, lc),
                make_float2(oml, oml), make_float2(m2l, m2l)};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
   int32_t st;
+#define RCB_F7(N_, D_)                                                                                                            \
+  do {                                                                                                                            \
+    if (gen) st = modk == 2 ? launch_one<N_, 2, 1024, D_, true>(ctx, p, fa, grid) : launch_one<N_, 0, 1024, D_, true>(ctx, p, fa, grid);   \
+    else st = modk == 2 ? launch_one<N_, 2, 1024, D_>(ctx, p, fa, grid) : launch_one<N_, 0, 1024, D_>(ctx, p, fa, grid);                   \
+  } while (0)
   if (p.d_in == 3) {
     if (half) st = modk == 2 ? launch_one<8192, 2, 512, 3>(ctx, p, fa, grid) : launch_one<8192, 0, 512, 3>(ctx, p, fa, grid);
-    else if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024, 3>(ctx, p, fa, grid) : launch_one<8192, 0, 1024, 3>(ctx, p, fa, grid);
-    else st = modk == 2 ? launch_one<4096, 2, 1024, 3>(ctx, p, fa, grid) : launch_one<4096, 0, 1024, 3>(ctx, p, fa, grid);
+    else if (p.npad == 8192) RCB_F7(8192, 3);
+    else if (p.npad == 4096) RCB_F7(4096, 3);
+    else RCB_F7(2048, 3);
   } else {  // one input row (Mackey-Glass-shaped, BASELINE config 2 time-chunked)
-    if (p.npad == 8192) st = modk == 2 ? launch_one<8192, 2, 1024, 1>(ctx, p, fa, grid) : launch_one<8192, 0, 1024, 1>(ctx, p, fa, grid);
-    else st = modk == 2 ? launch_one<4096, 2, 1024, 1>(ctx, p, fa, grid) : launch_one<4096, 0, 1024, 1>(ctx, p, fa, grid);
+    if (p.npad == 8192) RCB_F7(8192, 1);
+    else if (p.npad == 4096) RCB_F7(4096, 1);
+    else RCB_F7(2048, 1);
   }
+#undef RCB_F7
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (st == RCB_OK) *launched = true;
   return st;

@@ -542,6 +542,40 @@ def test_fast7_kernel_parity(R, N, B, T, mod, leak, d_in):
     assert float(err.max()) <= STATE_RTOL
 
 
+@pytest.mark.parametrize("N,B,T,mod,bias,leakv,d_in", [(2048, 1030, 6, "nlat2", True, True, 3), (4096, 900, 4, "none", True, False, 1),
+                                                        (2048, 1000, 5, "nlat2", False, False, 3), (8192, 890, 3, "nlat2", False, True, 3)])
+def test_fast7_kernel_bias_leak_vector_and_n2048(R, N, B, T, mod, bias, leakv, d_in):
+    """The 7-sequences-per-CTA kernel beyond the benchmark shape (r02): N = 2048, a cell bias, a per-neuron leak — against the
+    oracle on spot sequences and against the generic kernel on every sequence."""
+    rng = np.random.default_rng(N + B + 1)
+    mods = R.NLAT2 if mod == "nlat2" else ()
+    kw = dict(init_bias=lambda r, *d: (0.2 * r.standard_normal(d)).astype(np.float32)) if bias else {}
+    esn = R.ESN(d_in, N, d_in, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N, return_sparse=True), state_modifiers=mods,
+                use_bias=bias, leak_coefficient=rng.uniform(0.2, 1.0, N).astype(np.float32) if leakv else 0.6, **kw)
+    ps, st = R.setup(rng, esn)
+    lor = O.lorenz_series(T + B)[:d_in]
+    data = np.asfortranarray(np.stack([lor[:, b:b + T] for b in range(B)], axis=2).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    stf = fixed_h0(R, st, esn, [h0])
+    os.environ.pop("RCB_K1_MODE", None)
+    states, st2 = R.collectstates(esn, data, ps, stf)
+    if R.default_device().sm_count() * 6 < B:
+        name = R.default_device().last_kernel()
+        assert name.startswith("k1_fast7") and (("bias/leak-vector" in name) == (bias or leakv)), name
+    layers = oracle_layers(R, esn, ps)
+    for b in (0, 7 * 61 + 3, B - 1):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert state_err(states[:, :, b], ref) <= STATE_RTOL
+        assert np.max(np.abs(st2.reservoir.carry[0][:, b] - hs[0])) <= STATE_RTOL * np.max(np.abs(hs[0]))
+    os.environ["RCB_K1_MODE"] = "v1"
+    try:
+        generic, _ = R.collectstates(esn, data, ps, stf)
+    finally:
+        os.environ.pop("RCB_K1_MODE", None)
+    err = np.max(np.abs(states - generic).reshape(N, -1), axis=0) / np.maximum(np.max(np.abs(generic).reshape(N, -1), axis=0), 1e-30)
+    assert float(err.max()) <= STATE_RTOL
+
+
 def test_train_sharded_single_rank_matches_train(R):
     """train_sharded (rcb_train_partial -> [all-reduce] -> rcb_ridge_solve) == train (rcb_train) on one rank."""
     rng = np.random.default_rng(23)
