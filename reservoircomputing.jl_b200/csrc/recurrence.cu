@@ -489,6 +489,8 @@ __global__ void __launch_bounds__(1024, 1) k4_predict_kernel(const PredParams p)
 int32_t launch_predict(rcb_ctx* ctx, const PredictArgs& a) {
   {
     bool launched = false;
+    const int32_t fc = launch_predict_auto_cluster(ctx, a, &launched);
+    if (fc != RCB_OK || launched) return fc;
     const int32_t fa = launch_predict_auto(ctx, a, &launched);
     if (fa != RCB_OK || launched) return fa;
   }

@@ -300,6 +300,195 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(NTMAX, 1) k1_cluste
   cluster_wait();
 }
 
+// ================================================================================================================
+// K4 on a cluster: the autoregressive predict loop (src/predict.jl:74-88) of a single-layer ESN, one sequence per cluster.
+//   out = initialdata;  repeat:  x <- cell(out, x);  out <- psi(W_out modifier(x) + b);  output[:, i] = out
+// The state update and exchange are those of k1_cluster above (rows over the 8 CTAs, st.async + mbarrier), in the COMPUTE
+// dtype T — Float64 after the default (Float64) ridge fit, because the fed-back output promotes the cell (esn_cell.jl:176).
+// The readout needs every feature: each CTA evaluates it REDUNDANTLY from its local copy of the full new state (F x d_out
+// multiply-adds over its threads + one block reduction), so the fed-back output is available in every CTA without a second
+// exchange.  One CTA (k4_auto, recurrence_single.cu) needs 3.5 / 11 / 20 us per step at N = 1024 / 4096 / 8192.
+struct AutoClusterArgs {
+  int n, npad, d_io, ntc, rpc, has_pad, ro_act, u_is_f64, nwarps;
+  long long steps;
+  double leak, pad;
+  const float* ell_vals;
+  const uint16_t* ell_cols;
+  const int* ell_off;
+  const int* ell_width;
+  const float* Win;       // n x d_io column-major (by row)
+  const double* Wout;     // d_io x F
+  const double* bout;
+  const void* u0;         // d_io x B (data dtype)
+  void* h;                // n x B (compute dtype), in/out (may be null)
+  double* y;              // d_io x steps x B
+};
+
+template <typename T> __device__ __forceinline__ T cl_tanh(T x);
+template <> __device__ __forceinline__ double cl_tanh<double>(double x) { return tanh(x); }
+template <> __device__ __forceinline__ float cl_tanh<float>(float x) { return fast_tanh(x); }
+
+template <typename T> __device__ __forceinline__ T lds_t(uint32_t addr);
+template <> __device__ __forceinline__ float lds_t<float>(uint32_t addr) { return lds_f32(addr); }
+template <> __device__ __forceinline__ double lds_t<double>(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// four consecutive rows of type T into one CTA of the cluster: 16 bytes (float) or two 16-byte stores (double)
+__device__ __forceinline__ void send4(uint32_t addr, float a, float b, float c, float d, uint32_t bar) { st_async4(addr, a, b, c, d, bar); }
+__device__ __forceinline__ void send4(uint32_t addr, double a, double b, double c, double d, uint32_t bar) {
+  const unsigned long long ua = __double_as_longlong(a), ub = __double_as_longlong(b), uc = __double_as_longlong(c), ud = __double_as_longlong(d);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(addr), "l"(ua), "l"(ub), "r"(bar) : "memory");
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(addr + 16u), "l"(uc), "l"(ud), "r"(bar) : "memory");
+}
+
+template <typename T, int MODK>
+__global__ void __cluster_dims__(CSMAX, 1, 1) __launch_bounds__(512, 1) k4_cluster_kernel(const AutoClusterArgs a) {
+  constexpr int CS = CSMAX, ES = (int)sizeof(T);
+  extern __shared__ __align__(16) unsigned char smem[];
+  T* xb = reinterpret_cast<T*>(smem);                          // [2][npad] full state in the compute dtype
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n, D = a.d_io;
+  const long long seq = blockIdx.x / CS;
+  const int width = a.ell_width[crank];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)a.npad * ES);
+  double* red_s = reinterpret_cast<double*>(bars + 2);          // [nwarps][4]
+  float* ev = reinterpret_cast<float*>(red_s + (size_t)a.nwarps * 4);
+  uint16_t* ec = reinterpret_cast<uint16_t*>(ev + (size_t)width * a.ntc);
+  {
+    const float* gv = a.ell_vals + a.ell_off[crank];
+    const uint16_t* gc = a.ell_cols + a.ell_off[crank];
+    for (int i = tid; i < width * a.ntc; i += blockDim.x) { ev[i] = __ldg(gv + i); ec[i] = __ldg(gc + i); }
+  }
+  T* h_g = reinterpret_cast<T*>(a.h);
+  for (int i = tid; i < a.npad; i += blockDim.x) {
+    const T v = (h_g && i < n) ? h_g[(size_t)seq * n + i] : T(0);
+    xb[i] = v;
+    xb[a.npad + i] = v;
+  }
+  const int row = (int)crank * a.rpc + tid;
+  const bool mine = row < n;
+  float win[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) win[d] = (mine && d < D) ? __ldg(a.Win + (size_t)d * n + row) : 0.0f;
+  const T lc = (T)a.leak, oml = T(1) - lc;
+  T hold = (mine && h_g) ? h_g[(size_t)seq * n + row] : T(0);
+  T yv[4] = {T(0), T(0), T(0), T(0)};   // the current input: initialdata, then the fed-back outputs (predict.jl:78-84)
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d < D) yv[d] = a.u_is_f64 ? (T) reinterpret_cast<const double*>(a.u0)[(size_t)seq * D + d] : (T) reinterpret_cast<const float*>(a.u0)[(size_t)seq * D + d];
+  const uint32_t bar0 = smem_addr(bars), xb0 = smem_addr(xb), buf_bytes = (uint32_t)a.npad * ES;
+  const uint32_t mine_addr = xb0 + (uint32_t)ES * (uint32_t)row;
+  uint32_t peer[CS], peer_bar[CS];
+#pragma unroll
+  for (int c = 0; c < CS; ++c) { peer[c] = map_to_cta(mine_addr, (uint32_t)c); peer_bar[c] = map_to_cta(bar0, (uint32_t)c); }
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar0 + 8, buf_bytes);
+    mbar_expect_tx(bar0, buf_bytes);
+  }
+  __syncthreads();
+  // my row's first WR entries in registers, as in k1_cluster
+  constexpr int WR = 16;
+  const uint32_t ev0 = smem_addr(ev) + 4u * (uint32_t)tid, ec0 = smem_addr(ec) + 2u * (uint32_t)tid;
+  const uint32_t vstride = (uint32_t)a.ntc * 4u, cstride = (uint32_t)a.ntc * 2u;
+  float rv[WR];
+  uint32_t rcol[WR];
+#pragma unroll
+  for (int j = 0; j < WR; ++j) {
+    rv[j] = j < width ? lds_f32(ev0 + (uint32_t)j * vstride) : 0.0f;
+    rcol[j] = j < width ? lds_u16(ec0 + (uint32_t)j * cstride) * (uint32_t)ES : 0u;
+  }
+  int wlen = 0;
+#pragma unroll
+  for (int j = 0; j < WR; ++j) wlen = rv[j] != 0.0f ? j + 1 : wlen;
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) wlen = max(wlen, __shfl_xor_sync(0xffffffffu, wlen, sh));
+  const int F = n + a.has_pad;
+  cluster_arrive();
+  cluster_wait();
+  const int steps = (int)a.steps;
+  for (int t = 0; t < steps; ++t) {
+    const uint32_t cur = xb0 + (uint32_t)(t & 1) * buf_bytes;
+    // ---- state update of my row with the current input (esn_cell.jl:175-184) and exchange ----
+    T hn = T(0);
+    if (mine) {
+      T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+#pragma unroll
+      for (int j = 0; j < WR; j += 4) {
+        if (j < wlen) {
+          acc0 = fma((T)rv[j], lds_t<T>(cur + rcol[j]), acc0);
+          acc1 = fma((T)rv[j + 1], lds_t<T>(cur + rcol[j + 1]), acc1);
+          acc2 = fma((T)rv[j + 2], lds_t<T>(cur + rcol[j + 2]), acc2);
+          acc3 = fma((T)rv[j + 3], lds_t<T>(cur + rcol[j + 3]), acc3);
+        }
+      }
+      for (int j = WR; j < width; ++j)
+        acc0 = fma((T)lds_f32(ev0 + (uint32_t)j * vstride), lds_t<T>(cur + lds_u16(ec0 + (uint32_t)j * cstride) * (uint32_t)ES), acc0);
+      T x = (acc0 + acc2) + (acc1 + acc3);
+      T wi = (T)win[0] * yv[0];             // W_in * u (generics.jl:91-96)
+      if (D > 1) wi = fma((T)win[1], yv[1], wi);
+      if (D > 2) wi = fma((T)win[2], yv[2], wi);
+      if (D > 3) wi = fma((T)win[3], yv[3], wi);
+      hn = oml * hold + lc * cl_tanh<T>(wi + x);
+      hold = hn;
+    }
+    {
+      const T v1 = __shfl_down_sync(0xffffffffu, hn, 1), v2 = __shfl_down_sync(0xffffffffu, hn, 2), v3 = __shfl_down_sync(0xffffffffu, hn, 3);
+      if ((tid & 3) == 0) {
+        const uint32_t nxt_off = (uint32_t)((t + 1) & 1) * buf_bytes, nxt_bar = 8u * (uint32_t)((t + 1) & 1);
+#pragma unroll
+        for (int c = 0; c < CS; ++c) send4(peer[c] + nxt_off, hn, v1, v2, v3, peer_bar[c] + nxt_bar);
+      }
+    }
+    // ---- wait for the whole new state, then the readout (every CTA computes all of it) ----
+    const uint32_t bar = bar0 + 8u * (uint32_t)((t + 1) & 1);
+    mbar_wait(bar, (uint32_t)((t >> 1) & 1));
+    if (tid == 0 && t + 2 < steps) mbar_expect_tx(bar, buf_bytes);   // values of step t + 2 land in the same buffer
+    const uint32_t zs = xb0 + (uint32_t)((t + 1) & 1) * buf_bytes;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int f = tid; f < F; f += blockDim.x) {
+      T z;
+      if (f == n) z = (T)a.pad;                                                                     // Pad, states.jl:79-82
+      else if (MODK == 2 && (f & 1) == 0 && f >= 2) z = lds_t<T>(zs + (uint32_t)ES * (uint32_t)(f - 1)) * lds_t<T>(zs + (uint32_t)ES * (uint32_t)(f - 2));   // NLAT2
+      else z = lds_t<T>(zs + (uint32_t)ES * (uint32_t)f);
+      const double zf = (double)z;
+      const double* wf = a.Wout + (size_t)f * D;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < D) part[q] = fma(__ldg(wf + q), zf, part[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= D) break;
+      double v = part[q];
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+      if (lane == 0) red_s[warp * 4 + q] = v;
+    }
+    __syncthreads();
+    double ysum = 0.0;
+    if (lane < D) {
+      for (int w2 = 0; w2 < a.nwarps; ++w2) ysum += red_s[w2 * 4 + lane];
+      if (a.bout) ysum += __ldg(a.bout + lane);
+      ysum = apply_act<double>(a.ro_act, ysum);
+      if (crank == 0 && warp == 0) a.y[((size_t)seq * a.steps + t) * D + lane] = ysum;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+      if (d < D) yv[d] = (T)__shfl_sync(0xffffffffu, ysum, d);   // y becomes the next input (predict.jl:83)
+    __syncthreads();   // red_s is rewritten by the next step's readout
+  }
+  if (h_g && mine) h_g[(size_t)seq * n + row] = hold;
+  cluster_arrive();
+  cluster_wait();
+}
+
 }  // namespace
 
 // Builds the per-CTA ELL slices of the cluster kernel from the layer's CSR (host, once per weight upload).
@@ -406,6 +595,61 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (err != cudaSuccess) return fail(RCB_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(err), __FILE__, __LINE__);
   snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_cluster<%d SMs per sequence, %d rows per CTA> grid=%d", CS, e.rpc, (int)(p.B * CS));
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  *launched = true;
+  return RCB_OK;
+}
+
+// Autoregressive predict of a single-layer ESN on a cluster per sequence; *launched stays false outside this shape.
+int32_t launch_predict_auto_cluster(rcb_ctx* ctx, const PredictArgs& pa, bool* launched) {
+  *launched = false;
+  const rcb_esn& E = *pa.esn;
+  const char* mode = getenv("RCB_K4_MODE");  // testing hook: "cluster" forces this kernel (any N), anything else skips it
+  const bool forced = mode && !strcmp(mode, "cluster");
+  if (mode && !forced) return RCB_OK;
+  if (!pa.autoregressive || E.layers.size() != 1 || E.readout_members > 1 || E.member_count) return RCB_OK;
+  const Layer& L = E.layers[0];
+  const DevClusterEll& e = L.cl;
+  if (!e.ok || e.ntc > 512 || !L.d_Win_cm || pa.B * CSMAX > ctx->sm_count) return RCB_OK;
+  if (!forced && L.n < 1024) return RCB_OK;
+  if (E.desc.in_dims != E.desc.out_dims || E.desc.in_dims > 4) return RCB_OK;
+  if (!(L.desc.activation == RCB_ACT_TANH || L.desc.activation == RCB_ACT_TANH_FAST) || L.desc.use_bias || L.desc.leak_is_vector ||
+      L.cell == RCB_CELL_ES2N || L.cell == RCB_CELL_RESESN)
+    return RCB_OK;
+  if (!chain_is_fusable(L.chain)) return RCB_OK;
+  int kind = 0, has_pad = 0;
+  double pad = 0.0;
+  {
+    int i = 0;
+    if (L.chain.n > 0 && L.chain.kind[0] != RCB_MOD_PAD) { kind = L.chain.kind[0]; i = 1; }
+    if (i < L.chain.n && L.chain.kind[i] == RCB_MOD_PAD) { has_pad = 1; pad = L.chain.param[i]; }
+  }
+  if (kind != 0 && kind != RCB_MOD_NLAT2) return RCB_OK;
+  const size_t esz = pa.compute_dtype == RCB_F64 ? 8 : 4;
+  const int npad = e.cs * e.ntc, nwarps = e.ntc / 32;
+  if ((size_t)npad * esz > 65535) return RCB_OK;   // column byte offsets in 16 + log2(esz) bits of a 32-bit register: fine; guard the ELL's 16-bit columns
+  const size_t smem = 2 * (size_t)npad * esz + 16 + (size_t)nwarps * 32 + (size_t)e.max_width * e.ntc * (sizeof(float) + sizeof(uint16_t)) + 64;
+  if (smem > ctx->smem_optin) return RCB_OK;
+  AutoClusterArgs a{};
+  a.n = L.n; a.npad = npad; a.d_io = E.desc.in_dims; a.ntc = e.ntc; a.rpc = e.rpc; a.has_pad = has_pad; a.ro_act = E.desc.readout_activation;
+  a.u_is_f64 = E.desc.data_dtype == RCB_F64; a.nwarps = nwarps; a.steps = pa.T; a.leak = L.desc.leak_scalar; a.pad = pad;
+  a.ell_vals = e.vals; a.ell_cols = e.cols; a.ell_off = e.off; a.ell_width = e.width;
+  a.Win = L.d_Win_cm; a.Wout = E.d_Wout; a.bout = E.d_bout; a.u0 = pa.u; a.h = pa.h; a.y = pa.y;
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  cudaError_t err = cudaSuccess;
+#define RCB_K4C(T_, M_)                                                                                                   \
+  do {                                                                                                                    \
+    err = cudaFuncSetAttribute(k4_cluster_kernel<T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (err == cudaSuccess) k4_cluster_kernel<T_, M_><<<(unsigned)(pa.B * CSMAX), e.ntc, smem, ctx->stream>>>(a);          \
+  } while (0)
+  if (pa.compute_dtype == RCB_F64) { if (kind == 2) RCB_K4C(double, 2); else RCB_K4C(double, 0); }
+  else { if (kind == 2) RCB_K4C(float, 2); else RCB_K4C(float, 0); }
+#undef RCB_K4C
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  if (err != cudaSuccess) return fail(RCB_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(err), __FILE__, __LINE__);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k4_cluster<%s,%s,%d SMs per sequence> grid=%d", esz == 8 ? "f64" : "f32", kind == 2 ? "nlat2" : "raw",
+           CSMAX, (int)(pa.B * CSMAX));
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   *launched = true;

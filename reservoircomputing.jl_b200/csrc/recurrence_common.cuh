@@ -183,6 +183,8 @@ int32_t launch_collect_single(rcb_ctx* ctx, const RecParams& p, const DevFast& f
 
 // recurrence_single.cu: autoregressive predict of a single-layer ESN, one sequence per CTA, W / W_in resident, y in registers
 int32_t launch_predict_auto(rcb_ctx* ctx, const PredictArgs& pa, bool* launched);
+// recurrence_cluster.cu: the same loop with the sequence spread over a cluster of 8 SMs (N >= 1024)
+int32_t launch_predict_auto_cluster(rcb_ctx* ctx, const PredictArgs& pa, bool* launched);
 
 // recurrence_cluster.cu: few sequences, each spread over a cluster of 8 SMs (state exchanged through distributed shared memory)
 int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched);

@@ -1192,10 +1192,10 @@ def test_autoregressive_kernel_matches_generic_loop_and_oracle(R, N, d, mods, f6
     ps2, st2 = R.train(esn, data, tgt, ps, st, objective=obj, washout=50)
     u0 = tgt[:, -1]
     Y, st3 = R.predict(esn, 40, ps2, st2, initialdata=u0)
-    assert "k4_auto" in R.default_device().last_kernel() and Y.dtype == (np.float64 if f64 else np.float32)
+    assert ("k4_cluster" if N >= 1024 else "k4_auto") in R.default_device().last_kernel() and Y.dtype == (np.float64 if f64 else np.float32)
     monkeypatch.setenv("RCB_K4_MODE", "generic")
     Yg, st3g = R.predict(esn, 40, ps2, st2, initialdata=u0)
-    assert "k4_auto" not in R.default_device().last_kernel()
+    assert "k4_auto" not in R.default_device().last_kernel() and "k4_cluster" not in R.default_device().last_kernel()
     assert state_err(Y, Yg) <= (1e-9 if f64 else 1e-4)
     assert state_err(st3.reservoir.carry[0].reshape(-1, 1), st3g.reservoir.carry[0].reshape(-1, 1)) <= (1e-9 if f64 else 1e-4)
     layers = oracle_layers(R, esn, ps)
@@ -1441,3 +1441,33 @@ def test_cluster_kernel_deep_layers(R, monkeypatch):
     assert state_err(states, ref) <= STATE_RTOL
     for l in range(3):
         assert np.max(np.abs(st2.cells[l].carry[0] - hs[l])) <= STATE_RTOL * np.max(np.abs(hs[l]))
+
+
+@pytest.mark.parametrize("N,d,mods,f64", [(64, 3, "nlat2", True), (300, 3, "nlat2_pad", False), (517, 2, "none", True), (1100, 1, "pad", True),
+                                           (2048, 3, "nlat2", True), (4096, 3, "nlat2", False)])
+def test_autoregressive_cluster_kernel(R, N, d, mods, f64, monkeypatch):
+    """k4_cluster (recurrence_cluster.cu): the autoregressive loop with the sequence spread over 8 SMs — forced at every size —
+    against the one-CTA / general loops of the same library and against the oracle's step-by-step loop (src/predict.jl:74-88)."""
+    rng = np.random.default_rng(N + d + 5)
+    chain = dict(nlat2=(R.NLAT2,), nlat2_pad=(R.NLAT2, R.Pad(1.0)), none=(), pad=(R.Pad(0.5),))[mods]
+    esn = R.ESN(d, N, d, init_reservoir=R.rand_sparse(radius=0.9, sparsity=min(1.0, 6 / N), return_sparse=N > 1500), leak_coefficient=0.7,
+                state_modifiers=chain)
+    ps, st = R.setup(rng, esn)
+    T = 300
+    tt = np.arange(T + 1)[None, :]
+    series = (np.sin(0.07 * tt * (1 + np.arange(d))[:, None]) * 0.6).astype(np.float32)
+    data, tgt = np.asfortranarray(series[:, :T]), np.asfortranarray(series[:, 1:])
+    obj = R.RidgeRegression(1e-3) if f64 else R.RidgeRegression(np.float32, 1e-3)
+    ps2, st2 = R.train(esn, data, tgt, ps, st, objective=obj, washout=50)
+    u0 = tgt[:, -1]
+    monkeypatch.setenv("RCB_K4_MODE", "cluster")
+    Y, st3 = R.predict(esn, 30, ps2, st2, initialdata=u0)
+    assert "k4_cluster" in R.default_device().last_kernel() and Y.dtype == (np.float64 if f64 else np.float32)
+    monkeypatch.setenv("RCB_K4_MODE", "generic")
+    Yg, st3g = R.predict(esn, 30, ps2, st2, initialdata=u0)
+    assert "k4_cluster" not in R.default_device().last_kernel()
+    assert state_err(Y, Yg) <= (1e-9 if f64 else 1e-4)
+    assert state_err(st3.reservoir.carry[0].reshape(-1, 1), st3g.reservoir.carry[0].reshape(-1, 1)) <= (1e-9 if f64 else 1e-4)
+    if N <= 1100:
+        Yo, _ = O.predict_autoregressive(oracle_layers(R, esn, ps), ps2.readout.weight, 30, u0, [st2.reservoir.carry[0]])
+        assert state_err(Y, Yo) <= (1e-5 if f64 else 1e-3)
