@@ -218,10 +218,17 @@ __global__ void __launch_bounds__(128) cross_thin_kernel(const GramParams g) {
     for (int s1 = 0; s1 < ns; s1 += UN) {
       TZ z[UN];
 #pragma unroll
-      for (int q = 0; q < UN; ++q) {   // UN independent loads in flight before the first FMA
-        long long sq = seq, tt = tin + s1 + q;
-        while (tt >= g.Te) { tt -= g.Te; ++sq; }
-        z[q] = (fv && s1 + q < ns) ? A[(size_t)(sq * g.T + g.washout + tt) * g.lda + f] : TZ(0);
+      if (tin + s1 + UN <= g.Te && s1 + UN <= ns) {   // the usual case: UN whole columns inside one sequence
+        const TZ* a0 = A + (size_t)(seq * g.T + g.washout + tin + s1) * g.lda + f;
+#pragma unroll
+        for (int q = 0; q < UN; ++q) z[q] = fv ? __ldcs(a0 + (size_t)q * g.lda) : TZ(0);   // UN independent loads in flight before the first FMA
+      } else {
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+          long long sq = seq, tt = tin + s1 + q;
+          while (tt >= g.Te) { tt -= g.Te; ++sq; }
+          z[q] = (fv && s1 + q < ns) ? __ldcs(A + (size_t)(sq * g.T + g.washout + tt) * g.lda + f) : TZ(0);
+        }
       }
 #pragma unroll
       for (int q = 0; q < UN; ++q) {
@@ -243,7 +250,8 @@ __global__ void __launch_bounds__(128) cross_thin_kernel(const GramParams g) {
 template <typename TZ, typename TY>
 static int32_t launch_cross_thin(rcb_ctx* ctx, GramParams g) {
   const long long fb = (g.M + 127) / 128;
-  long long splits = (16LL * ctx->sm_count + fb * g.nbatch - 1) / (fb * g.nbatch);
+  // about eight waves of CTAs (7 resident per SM): the last, partly filled wave of a 2.3-wave grid cost a fifth of the launch
+  long long splits = (56LL * ctx->sm_count + fb * g.nbatch - 1) / (fb * g.nbatch);
   splits = std::max<long long>(1, std::min<long long>(splits, (g.Stot + 255) / 256));
   if (g.nbatch * splits > 65535) splits = std::max<long long>(1, 65535 / g.nbatch);
   g.chunk = ((g.Stot + splits - 1) / splits + 63) / 64 * 64;
@@ -260,7 +268,7 @@ static int32_t launch_cross_thin(rcb_ctx* ctx, GramParams g) {
 // SB samples per CTA iteration share every load of W (d_out x F, FP64, L2-resident); the features of a sample are read
 // once, coalesced along the contiguous feature axis; FP64 accumulation, warp-shuffle + shared-memory reduction.
 template <typename TZ, typename TY, int DO>
-__global__ void __launch_bounds__(256) residual_e_kernel(const double* __restrict__ W, const TZ* __restrict__ Z, long long ldz,
+__global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __restrict__ W, const TZ* __restrict__ Z, long long ldz,
                                                          const TY* __restrict__ Y, long long ldy, long long F, long long T,
                                                          long long washout, long long Te, long long Stot, int d_out,
                                                          double* __restrict__ E) {
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(256) residual_e_kernel(const double* __restric
 #pragma unroll
       for (int u = 0; u < UN; ++u)
 #pragma unroll
-        for (int q = 0; q < SB; ++q) z[u][q] = f0 + 32 * u < F ? Z[(size_t)col[q] * ldz + f0 + 32 * u] : TZ(0);
+        for (int q = 0; q < SB; ++q) z[u][q] = f0 + 32 * u < F ? __ldcs(Z + (size_t)col[q] * ldz + f0 + 32 * u) : TZ(0);   // streaming: W stays in L1
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         double w[DO];

@@ -25,9 +25,10 @@
 // the shared-memory image the MMA wants — [32-sample block][128-feature block][plane][32 rows x 128 B], 16-byte chunks
 // XOR-swizzled with (row & 7) (UMMA SWIZZLE_128B, MN-major, 8-bit) — so a pipeline stage is filled by two contiguous
 // cp.async.bulk copies.  One CTA = one 128 x 256 tile of the lower triangle; CTA pairs (a 2 x 1 cluster, 256 x 256
-// super-tile) fetch half of the shared B tile each and multicast it.  TMEM holds acc3 | acc4 (phase A, 5 MMAs per
-// K-step), acc2 | acc5 (phase B, 3 MMAs per K-step) or acc6 (phase C, 1 MMA per K-step; only the third digit plane is
-// fetched: a third of the bytes of a stage).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
+// super-tile) fetch half of the shared B tile each and multicast it.  TMEM holds acc4 | acc5 (phase A, 5 MMAs per
+// K-step, all three planes), acc2 | acc3 (phase B, 3 MMAs per K-step on the first two planes: two thirds of the bytes of
+// a stage — with all three planes this phase was bound by the L2 -> SM fetch, 36 KB per 411 tensor cycles) or acc6
+// (phase C, 1 MMA per K-step; only the third digit plane is fetched: a third of the bytes of a stage).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
 // elected thread), warps 2-9 = epilogue.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -44,16 +45,22 @@ namespace rcb {
 
 namespace {
 
-constexpr int TM = 128, TN = 256, KB = 32, PLANES = 3, STAGES = 5;
+constexpr int TM = 128, TN = 256, KB = 32, PLANES = 3;
 constexpr int BOX = 128 * KB;                          // 4 KB: one plane of 128 features x 32 samples
 constexpr int BLK = PLANES * BOX;                      // 12 KB: the three planes of a feature block
-constexpr int STAGE_BYTES = BLK + 2 * BLK;             // A block + two B blocks = 36 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+// PAIR = false: every CTA issues its own M = 128 MMAs (cta_group::1) and holds A + both B blocks (36 KB per stage).
+// PAIR = true: the CTA pair issues ONE M = 256 MMA (cta_group::2, leader CTA only); a CTA holds its A block and ITS half of
+// B (24 KB per stage), the tensor cores of the pair exchange the B halves — a third less shared-memory traffic per MMA.
+template <bool PAIR> struct K2Cfg {
+  static constexpr int STAGE_BYTES = PAIR ? 2 * BLK : 3 * BLK;
+  static constexpr int STAGES = PAIR ? 8 : 5;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+};
 constexpr int EPI_WARPS = 8;                           // two per TMEM lane quadrant, half of the tile columns each
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr int CR = 2, CLUSTER = CR;                    // CTA pair: rows 2I, 2I+1 of 128 share the 256 B columns
 constexpr int NPHASE = 3;
-constexpr int CK = 3;                                  // sample blocks per stage in phase C (CK * 3 * BOX <= STAGE_BYTES)
+constexpr int CK = 3;                                  // sample blocks per stage in phase C (CK * (3 or 2) * BOX <= STAGE_BYTES)
 constexpr int MAX_RANGE = 32768;                       // samples per accumulation: 3 * 128 * 128 * 32768 < 2^31
 
 struct GramParams8 {
@@ -71,6 +78,8 @@ struct GramParams8 {
   long long q8_stride;        // bytes between the members' digit planes
   long long g_stride;         // doubles between the members' G
   int* err;                   // set to 1 when a barrier wait timed out (the kernel then traps)
+  int relay;                  // pair: lanes of the peer's warp 1 that take turns relaying "stage landed" to the leader
+  int relaxed;                // testing hook: relay with a relaxed arrive
   long long* prof;            // RCB_GRAM_PROF: per CTA [mma waits full, mma waits tmem, producer waits empty, epi waits, total]
 };
 
@@ -109,6 +118,36 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+__device__ __forceinline__ void umma_commit2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {
+      if (err) *err = 1;
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -127,15 +166,25 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
   return d;
 }
+template <bool PAIR>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // kind::i8: S32 accumulate, signed 8-bit A and B, both MN-major, M = 128, N = 256 (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
                            ((uint32_t)(TM >> 4) << 24);
+// the pair's instruction: M = 256 (128 rows per CTA), N = 256 (128 columns of B from each CTA)
+constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+                            ((uint32_t)((2 * TM) >> 4) << 24);
 
 #define TMEM_LD16(addr, v)                                                                                                        \
   asm volatile(                                                                                                                   \
@@ -145,23 +194,32 @@ constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u
       : "r"(addr)                                                                                                                 \
       : "memory")
 
+template <bool PAIR>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) gram_i8_kernel(const GramParams8 p) {
+  constexpr int STAGES = K2Cfg<PAIR>::STAGES, STAGE_BYTES = K2Cfg<PAIR>::STAGE_BYTES;
+  constexpr int NBLK = PAIR ? 2 : 3;   // 128-feature blocks per stage: A + (my half of B | both B blocks)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
-  // barriers: full[STAGES] | empty[STAGES] | tfull | tempty | tmem base
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tempty = tfull + 8, tmem_slot = tempty + 8;
+  // barriers: full[STAGES] | empty[STAGES] | pfull[STAGES] (pair: the peer's stage has landed) | tfull | tempty | tmem base
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, pfull0 = bars + 16 * STAGES, tfull = bars + 24 * STAGES, tempty = tfull + 8,
+                 tmem_slot = tempty + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CR); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PAIR ? 1 : CR); mbar_init(pfull0 + 8 * s, 1); }
     mbar_init(tfull, 1);
-    mbar_init(tempty, EPI_WARPS);
+    mbar_init(tempty, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // pair: the leader waits for the epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // pair: the same warp of both CTAs allocates (and frees) collectively
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -206,19 +264,23 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             const uint32_t fbar = full0 + 8 * slot;
             const uint32_t sa = base + slot * STAGE_BYTES;
             if (phase < 2) {
-              mbar_expect_tx(fbar, 3 * BLK);               // bytes landing in MY shared memory: A + two B blocks
-              // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]
+              // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]      (pair: A | my B block)
+              // phase B multiplies the first two digit planes only: two thirds of the bytes, same offsets
+              const uint32_t nb = phase == 0 ? BLK : 2 * BOX;
+              mbar_expect_tx(fbar, NBLK * nb);             // bytes landing in MY shared memory
               const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
-              bulk_load_mc(sa, blk + (size_t)fa * BLK, BLK, fbar, mask_self);
-              bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, BLK, fbar, mask_all);
+              bulk_load_mc(sa, blk + (size_t)fa * BLK, nb, fbar, mask_self);
+              if (PAIR) bulk_load_mc(sa + BLK, blk + (size_t)fb * BLK, nb, fbar, mask_self);
+              else bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, nb, fbar, mask_all);
             } else {
               const int nk = nst - st < CK ? nst - st : CK;
-              mbar_expect_tx(fbar, (uint32_t)nk * 3 * BOX);
+              mbar_expect_tx(fbar, (uint32_t)nk * NBLK * BOX);
               for (int kk = 0; kk < nk; ++kk) {
                 const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st + kk) * p.nfb) * BLK + 2 * BOX;
-                const uint32_t sk = sa + (uint32_t)kk * 3 * BOX;
+                const uint32_t sk = sa + (uint32_t)kk * NBLK * BOX;
                 bulk_load_mc(sk, blk + (size_t)fa * BLK, BOX, fbar, mask_self);
-                bulk_load_mc(sk + BOX + (uint32_t)ri * BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_all);
+                if (PAIR) bulk_load_mc(sk + BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_self);
+                else bulk_load_mc(sk + BOX + (uint32_t)ri * BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_all);
               }
             }
           }
@@ -227,9 +289,29 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
       if (p.prof) { p.prof[blockIdx.x * 5 + 2] = wait_acc; p.prof[blockIdx.x * 5 + 4] = clock64() - tstart; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      long long it = 0, ci = 0, wfull = 0, wtm = 0;
+    // ===== MMA issuer (pair: the leader CTA issues for both; the peer's warp 1 relays "my stage has landed") =====
+    if (PAIR && ri != 0) {
+      if (lane < p.relay) {   // several lanes take turns: the round trip of one remote arrive must not pace the stages
+        long long it = 0;
+        for (long long item = cid; item < nitems; item += ncl) {
+          const long long split = (item % per_mem) / p.ntiles;
+          const long long s_beg = split * p.per_split;
+          const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
+          const int nst = (int)((s_end - s_beg + KB - 1) / KB);
+          for (int phase = 0; phase < nphase; ++phase) {
+            const int kper = phase == 2 ? CK : 1;
+            for (int st = 0; st < nst; st += kper, ++it) {
+              if ((int)(it % p.relay) != lane) continue;
+              const int slot = (int)(it % STAGES);
+              mbar_wait(full0 + 8 * slot, (uint32_t)((it / STAGES) & 1), p.err);
+              if (p.relaxed) mbar_arrive_remote_relaxed(pfull0 + 8 * slot, 0u);
+              else mbar_arrive_remote(pfull0 + 8 * slot, 0u);
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
+      long long it = 0, ci = 0, wfull = 0, wtm = 0, wpeer = 0;
       for (long long item = cid; item < nitems; item += ncl) {
         const long long split = (item % per_mem) / p.ntiles;
         const long long s_beg = split * p.per_split;
@@ -237,7 +319,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
         const int nst = (int)((s_end - s_beg + KB - 1) / KB);
         for (int phase = 0; phase < nphase; ++phase, ++ci) {
           const long long w0 = clock64();
-          mbar_wait(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);  // the epilogue has drained the previous accumulators
+          if (PAIR) mbar_wait_cluster(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);  // the epilogue warps (pair: of both CTAs) have drained
+          else mbar_wait(tempty, (uint32_t)(ci & 1) ^ 1u, p.err);                // the previous accumulators
           wtm += clock64() - w0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int kper = phase == 2 ? CK : 1;
@@ -247,36 +330,45 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             const long long w1 = clock64();
             mbar_wait(full0 + 8 * slot, ph, p.err);
             wfull += clock64() - w1;
+            if (PAIR) {
+              const long long w2 = clock64();
+              mbar_wait_cluster(pfull0 + 8 * slot, ph, p.err);
+              wpeer += clock64() - w2;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = base + slot * STAGE_BYTES;
             const uint32_t acc = st > 0 ? 1u : 0u;
+            constexpr uint32_t ID = PAIR ? IDESC2 : IDESC;
             if (phase < 2) {
               const uint64_t A1 = umma_desc(sa, BLK), A2 = umma_desc(sa + BOX, BLK), A3 = umma_desc(sa + 2 * BOX, BLK);
               const uint64_t B1 = umma_desc(sa + BLK, BLK), B2 = umma_desc(sa + BLK + BOX, BLK), B3 = umma_desc(sa + BLK + 2 * BOX, BLK);
               if (phase == 0) {
-                umma_i8(tmem_base, A1, B2, IDESC, acc);          // acc3 = a1 a2' + a2 a1'
-                umma_i8(tmem_base, A2, B1, IDESC, 1u);
-                umma_i8(tmem_base + TN, A1, B3, IDESC, acc);     // acc4 = a1 a3' + a3 a1' + a2 a2'
-                umma_i8(tmem_base + TN, A3, B1, IDESC, 1u);
-                umma_i8(tmem_base + TN, A2, B2, IDESC, 1u);
+                umma_i8<PAIR>(tmem_base, A1, B3, ID, acc);          // acc4 = a1 a3' + a3 a1' + a2 a2'
+                umma_i8<PAIR>(tmem_base, A3, B1, ID, 1u);
+                umma_i8<PAIR>(tmem_base, A2, B2, ID, 1u);
+                umma_i8<PAIR>(tmem_base + TN, A2, B3, ID, acc);     // acc5 = a2 a3' + a3 a2'
+                umma_i8<PAIR>(tmem_base + TN, A3, B2, ID, 1u);
               } else {
-                umma_i8(tmem_base, A1, B1, IDESC, acc);          // acc2 = a1 a1'
-                umma_i8(tmem_base + TN, A2, B3, IDESC, acc);     // acc5 = a2 a3' + a3 a2'
-                umma_i8(tmem_base + TN, A3, B2, IDESC, 1u);
+                umma_i8<PAIR>(tmem_base, A1, B1, ID, acc);          // acc2 = a1 a1'
+                umma_i8<PAIR>(tmem_base + TN, A1, B2, ID, acc);     // acc3 = a1 a2' + a2 a1'
+                umma_i8<PAIR>(tmem_base + TN, A2, B1, ID, 1u);
               }
             } else {
               const int nk = nst - st < CK ? nst - st : CK;
               for (int kk = 0; kk < nk; ++kk) {                  // acc6 = a3 a3' over the CK sample blocks of the stage
-                const uint32_t sk = sa + (uint32_t)kk * 3 * BOX;
-                umma_i8(tmem_base, umma_desc(sk, BOX), umma_desc(sk + BOX, BOX), IDESC, (acc | (uint32_t)kk) ? 1u : 0u);
+                const uint32_t sk = sa + (uint32_t)kk * NBLK * BOX;
+                umma_i8<PAIR>(tmem_base, umma_desc(sk, BOX), umma_desc(sk + BOX, BOX), ID, (acc | (uint32_t)kk) ? 1u : 0u);
               }
             }
-            umma_commit_mc(empty0 + 8 * slot, mask_all);       // tells both producers that fill my stage it is free
+            // the stage is free: tell the producer(s) that fill it (pair: one commit frees the slot in both CTAs)
+            if (PAIR) umma_commit2_mc(empty0 + 8 * slot, mask_all);
+            else umma_commit_mc(empty0 + 8 * slot, mask_all);
           }
-          umma_commit(tfull);                                  // accumulators of this phase complete
+          if (PAIR) umma_commit2_mc(tfull, mask_all);          // accumulators of this phase complete (in both CTAs)
+          else umma_commit(tfull);
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 5 + 0] = wfull; p.prof[blockIdx.x * 5 + 1] = wtm; }
+      if (p.prof) { p.prof[blockIdx.x * 5 + 0] = wfull; p.prof[blockIdx.x * 5 + 1] = wtm; if (PAIR) p.prof[(blockIdx.x + 1) * 5 + 0] = wpeer; }
     }
   } else {
     // ===== epilogue: INT32 accumulators -> FP64 G =====
@@ -311,8 +403,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
           for (int q = 0; q < 16; ++q) {
             const long long gj = gj0 + n0 + q;
             if (gi < p.F && gj <= gi) {
-              const double a = phase == 0 ? 256.0 * (double)(int)v[q] + (double)(int)w[q]
-                               : phase == 1 ? 65536.0 * (double)(int)v[q] + 0.00390625 * (double)(int)w[q]
+              const double a = phase == 0 ? (double)(int)v[q] + 0.00390625 * (double)(int)w[q]
+                               : phase == 1 ? 65536.0 * (double)(int)v[q] + 256.0 * (double)(int)w[q]
                                             : 1.52587890625e-05 * (double)(int)v[q];
               if (a != 0.0) atomicAdd(Gm + (size_t)gj * p.ldo + gi, a * sfi * sfj[q]);
             }
@@ -320,7 +412,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(tempty, 0u);   // the leader's barrier counts the epilogue warps of both CTAs
+          else mbar_arrive(tempty);
+        }
       }
     }
     if (p.prof && threadIdx.x == 64) p.prof[blockIdx.x * 5 + 3] = wepi;
@@ -330,7 +425,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
   cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -340,21 +436,25 @@ constexpr int SLAB = 128;
 template <int VEC>
 __global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ Z, long long ldz, long long F, long long T,
                                                      long long washout, long long Te, long long s0, long long Sc,
-                                                     int* __restrict__ amax, long long z_stride, long long ldp) {
+                                                     int* __restrict__ amax, long long z_stride, long long ldp, int spc) {
   const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (f >= F) return;
   Z += (size_t)blockIdx.z * z_stride;       // member
   amax += (size_t)blockIdx.z * ldp;
-  const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB < Sc ? sl0 + SLAB : Sc;
+  // spc slabs per CTA: one atomic per feature and CTA
+  const long long sl0 = (long long)blockIdx.y * spc * SLAB, sl1 = sl0 + (long long)spc * SLAB < Sc ? sl0 + (long long)spc * SLAB : Sc;
   // maxima as bit patterns of |z| (non-negative floats order like integers) — NaN and Inf rank above every finite value
   // instead of being dropped by fmaxf, so a diverged reservoir is seen by phase_select_kernel
   int mx[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) mx[v] = 0;
+  // sample -> column of the F x (T * nseq) array, advanced incrementally (a 64-bit division per sample and thread cost more
+  // than everything else in these pre-passes)
+  long long sq = (s0 + sl0) / Te, tt = (s0 + sl0) % Te;
 #pragma unroll 8
   for (long long sl = sl0; sl < sl1; ++sl) {
-    const long long s = s0 + sl;
-    const long long col = (s / Te) * T + washout + (s % Te);
+    const long long col = sq * T + washout + tt;
+    if (++tt == Te) { tt = 0; ++sq; }
     if constexpr (VEC == 4) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(Z + (size_t)col * ldz + f));
       mx[0] = max(mx[0], __float_as_int(fabsf(x.x))); mx[1] = max(mx[1], __float_as_int(fabsf(x.y)));
@@ -368,12 +468,11 @@ __global__ void __launch_bounds__(256) colmax_kernel(const float* __restrict__ Z
     if (f + v < F) atomicMax(amax + f + v, mx[v]);
 }
 
-__device__ __forceinline__ void digits(float x, float qs, int& a1, int& a2, int& a3) {
-  const int q = __float2int_rn(x * qs);
-  a3 = (int)(signed char)(q & 0xFF);
-  const int q1 = (q - a3) >> 8;
-  a2 = (int)(signed char)(q1 & 0xFF);
-  a1 = (q1 - a2) >> 8;
+// Balanced base-256 digits of q = rint(x qs), |q| < 2^22: q = a1 2^16 + a2 2^8 + a3 with a2, a3 in [-128, 127].  Adding 128
+// to every digit position turns them into plain unsigned bytes (no borrows), and byte ^ 0x80 is the two's-complement digit:
+// the result holds a3 | a2 | a1 in bytes 0 | 1 | 2.
+__device__ __forceinline__ uint32_t digits3(float x, float qs) {
+  return ((uint32_t)__float2int_rn(x * qs) + 0x00808080u) ^ 0x00808080u;
 }
 
 // ---- pre-pass 2: gather the sample set (washout skipped, src/train.jl:36-47), quantise, cut into digit planes laid out
@@ -386,14 +485,13 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
                                                          long long Sc, const int* __restrict__ amax, unsigned char* __restrict__ q8,
                                                          double* __restrict__ sf, const TY* __restrict__ Y, long long ldy, int d_out,
                                                          double* __restrict__ C, long long ldc, long long z_stride, long long y_stride,
-                                                         long long q8_stride, long long c_stride) {
+                                                         long long q8_stride, long long c_stride, int spc) {
   Z += (size_t)blockIdx.z * z_stride;       // member
   amax += (size_t)blockIdx.z * ldp;
   sf += (size_t)blockIdx.z * ldp;
   q8 += (size_t)blockIdx.z * q8_stride;
   if (C) { Y += (size_t)blockIdx.z * y_stride; C += (size_t)blockIdx.z * c_stride; }
   const long long f = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  const long long sl0 = (long long)blockIdx.y * SLAB, sl1 = sl0 + SLAB;  // whole sample blocks: rows >= Sc become zeros
   if (f >= ldp) return;
   float qs[VEC];
   bool live[VEC];
@@ -416,14 +514,54 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
     for (int d = 0; d < DMAX; ++d) acc[v][d] = 0.0;
   const long long nfb = ldp / 128, fbk = f >> 7;
   const int c = (int)(f & 127);
+  // spc slabs per CTA (r02: with one slab the FP64 atomics of the cross term, one per feature, output and 128 samples — 5e7
+  // per 8.6 GB window on 24 576 addresses — paced the kernel, not its 15 GB of traffic)
+  const long long nslab = (Sc + SLAB - 1) / SLAB;
+  for (long long slab = (long long)blockIdx.y * spc; slab < ((long long)blockIdx.y + 1) * spc && slab < nslab; ++slab) {
+  const long long sl0 = slab * SLAB, sl1 = sl0 + SLAB;  // whole sample blocks: rows >= Sc become zeros
+  long long sq = (s0 + sl0) / Te, tt = (s0 + sl0) % Te;
+  if (VEC == 4 && live[VEC - 1] && sl1 <= Sc) {
+    // the usual case — every feature of the vector and every sample of the slab exist: no predication, plain pointer steps
+    // (r02: the general loop below issued 214 warp instructions per sample, 5.4 ms per 8.6 GB window; FSEL / ISETP / branches)
+    for (int sbi = 0; sbi < SLAB / KB; ++sbi) {
+      unsigned char* blk = q8 + ((size_t)((sl0 / KB + sbi) * nfb + fbk) * PLANES) * BOX + (c & 15);
+#pragma unroll 4
+      for (int r = 0; r < KB; ++r) {
+        const long long col = sq * T + washout + tt;
+        if (++tt == Te) { tt = 0; ++sq; }
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(Z + (size_t)col * ldz + f));
+        const float x[4] = {t.x, t.y, t.z, t.w};
+        uint32_t dg[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dg[v] = digits3(x[v], qs[v]);
+        if (C) {
+          double y[DMAX];
+#pragma unroll
+          for (int d = 0; d < DMAX; ++d) y[d] = (DMAX <= 4 || d < d_out) ? (double)__ldg(Y + (size_t)col * ldy + d) : 0.0;
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const double xd = (double)x[v];
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) acc[v][d] = fma(xd, y[d], acc[v][d]);
+          }
+        }
+        unsigned char* box = blk + r * 128 + (((c >> 4) ^ (r & 7)) << 4);
+        const uint32_t lo01 = __byte_perm(dg[0], dg[1], 0x5140), lo23 = __byte_perm(dg[2], dg[3], 0x5140);
+        const uint32_t hi01 = __byte_perm(dg[0], dg[1], 0x0062), hi23 = __byte_perm(dg[2], dg[3], 0x0062);
+        *reinterpret_cast<uint32_t*>(box) = __byte_perm(hi01, hi23, 0x5410);
+        *reinterpret_cast<uint32_t*>(box + BOX) = __byte_perm(lo01, lo23, 0x7632);
+        *reinterpret_cast<uint32_t*>(box + 2 * BOX) = __byte_perm(lo01, lo23, 0x5410);
+      }
+    }
+  } else
 #pragma unroll 4
   for (long long sl = sl0; sl < sl1; ++sl) {
-    int a1[VEC], a2[VEC], a3[VEC];
+    uint32_t dg[VEC];   // a3 | a2 | a1 of every feature
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) a1[v] = a2[v] = a3[v] = 0;
+    for (int v = 0; v < VEC; ++v) dg[v] = 0u;
     if (sl < Sc) {
-      const long long s = s0 + sl;
-      const long long col = (s / Te) * T + washout + (s % Te);
+      const long long col = sq * T + washout + tt;
+      if (++tt == Te) { tt = 0; ++sq; }
       float x[VEC];
       if constexpr (VEC == 4) {
         if (live[3]) {
@@ -444,7 +582,7 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         if (live[v]) {
-          digits(x[v], qs[v], a1[v], a2[v], a3[v]);
+          dg[v] = digits3(x[v], qs[v]);
           if (C) {
 #pragma unroll
             for (int d = 0; d < DMAX; ++d)
@@ -457,14 +595,18 @@ __global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict
     const int r = (int)(sl % KB);
     unsigned char* box = q8 + ((size_t)(sb * nfb + fbk) * PLANES) * BOX + r * 128 + ((((c >> 4) ^ (r & 7)) << 4) | (c & 15));
     if constexpr (VEC == 4) {
-      *reinterpret_cast<uint32_t*>(box) = (uint32_t)(a1[0] & 0xFF) | ((uint32_t)(a1[1] & 0xFF) << 8) | ((uint32_t)(a1[2] & 0xFF) << 16) | ((uint32_t)(a1[3] & 0xFF) << 24);
-      *reinterpret_cast<uint32_t*>(box + BOX) = (uint32_t)(a2[0] & 0xFF) | ((uint32_t)(a2[1] & 0xFF) << 8) | ((uint32_t)(a2[2] & 0xFF) << 16) | ((uint32_t)(a2[3] & 0xFF) << 24);
-      *reinterpret_cast<uint32_t*>(box + 2 * BOX) = (uint32_t)(a3[0] & 0xFF) | ((uint32_t)(a3[1] & 0xFF) << 8) | ((uint32_t)(a3[2] & 0xFF) << 16) | ((uint32_t)(a3[3] & 0xFF) << 24);
+      // 4 x 3 byte transpose with byte permutes: plane word = digit p of features 0..3
+      const uint32_t lo01 = __byte_perm(dg[0], dg[1], 0x5140), lo23 = __byte_perm(dg[2], dg[3], 0x5140);   // f0.a3 f1.a3 f0.a2 f1.a2
+      const uint32_t hi01 = __byte_perm(dg[0], dg[1], 0x0062), hi23 = __byte_perm(dg[2], dg[3], 0x0062);   // f0.a1 f1.a1 . .
+      *reinterpret_cast<uint32_t*>(box) = __byte_perm(hi01, hi23, 0x5410);
+      *reinterpret_cast<uint32_t*>(box + BOX) = __byte_perm(lo01, lo23, 0x7632);
+      *reinterpret_cast<uint32_t*>(box + 2 * BOX) = __byte_perm(lo01, lo23, 0x5410);
     } else {
-      box[0] = (unsigned char)a1[0];
-      box[BOX] = (unsigned char)a2[0];
-      box[2 * BOX] = (unsigned char)a3[0];
+      box[0] = (unsigned char)(dg[0] >> 16);
+      box[BOX] = (unsigned char)(dg[0] >> 8);
+      box[2 * BOX] = (unsigned char)dg[0];
     }
+  }
   }
   if (C) {
 #pragma unroll
@@ -546,7 +688,13 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   if (Ssub < SLAB) Ssub = SLAB;
   if (Ssub > Stot) Ssub = Stot;
   const long long Ssub_pad = (Ssub + SLAB - 1) / SLAB * SLAB;
-  RCB_CUDA(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  // RCB_GRAM_PAIR=1: one M = 256 MMA per CTA pair (cta_group::2) instead of one M = 128 MMA per CTA with a multicast B tile.
+  // Measured r02 (F = 8192, S = 262144, eight products): 66.0 ms vs 53.6 ms — the leader has to learn through a relayed
+  // barrier that the peer's stage has landed, and the multicast form already receives only what it needs; kept as a tested option.
+  const bool pair = getenv("RCB_GRAM_PAIR") && atoi(getenv("RCB_GRAM_PAIR")) == 1;
+  const int SMEM_BYTES = pair ? K2Cfg<true>::SMEM_BYTES : K2Cfg<false>::SMEM_BYTES;
+  void (*kern)(const GramParams8) = pair ? gram_i8_kernel<true> : gram_i8_kernel<false>;
+  RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   void *q8 = nullptr, *aux = nullptr;
   const long long q8_stride = ldp * Ssub_pad * PLANES;
   RCB_TRY(ctx_scratch(ctx, SCR_ZHI, (size_t)q8_stride * nmem, &q8));
@@ -561,7 +709,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    RCB_CUDA(cudaOccupancyMaxActiveClusters(&ncl_max, gram_i8_kernel, &cfg));
+    RCB_CUDA(cudaOccupancyMaxActiveClusters(&ncl_max, kern, &cfg));
     if (ncl_max < 1) return fail(RCB_ERR_CUDA, "no %d-CTA cluster of the Gram kernel fits this device", CLUSTER);
   }
   static long long* prof_dev = nullptr;
@@ -572,19 +720,31 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     RCB_CUDA(cudaMemsetAsync(amax, 0, (size_t)ldp * nmem * sizeof(int), ctx->stream));
     {
       const bool vec = ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0;
-      const unsigned ny = (unsigned)((Sc + SLAB - 1) / SLAB);
-      const bool y64 = C && ydt == RCB_F64, small = d_out <= 4;
+      const long long nslab = (Sc + SLAB - 1) / SLAB, fxb = (ldp + 1023) / 1024;
+      // slabs per CTA: as many as still leave about eight waves of CTAs (three resident per SM)
+      const int spc = (int)std::max<long long>(1, std::min<long long>(8, nslab * fxb * nmem / (24LL * ctx->sm_count)));
+      const unsigned ny = (unsigned)((nslab + spc - 1) / spc);
+      const bool y64 = C && ydt == RCB_F64;
 #define RCB_SPLIT(TY, V, D, G)                                                                                                   \
   split_int8_kernel<TY, V, D><<<G, 256, 0, ctx->stream>>>(Z, ldz, F, ldp, T, washout, Te, s0, Sc, amax, (unsigned char*)q8, sf,   \
                                                           (const TY*)(C ? Y : nullptr), ldy, (int)d_out, C, ldo, z_stride, y_stride,     \
-                                                          q8_stride, g_stride)
+                                                          q8_stride, g_stride, spc)
       if (vec) {
-        colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp);
+        colmax_kernel<4><<<dim3((unsigned)((F + 1023) / 1024), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp, spc);
         const dim3 sgrid((unsigned)((ldp + 1023) / 1024), ny, (unsigned)nmem);
-        if (y64) { if (small) RCB_SPLIT(double, 4, 4, sgrid); else RCB_SPLIT(double, 4, 8, sgrid); }
-        else { if (small) RCB_SPLIT(float, 4, 4, sgrid); else RCB_SPLIT(float, 4, 8, sgrid); }
+        // d_out <= 4: the accumulator count is the template argument itself (no padded FP64 multiply-adds)
+#define RCB_SPLIT_D(TY)                                                                          \
+  switch (C ? (int)d_out : 1) {                                                                  \
+    case 1: RCB_SPLIT(TY, 4, 1, sgrid); break;                                                   \
+    case 2: RCB_SPLIT(TY, 4, 2, sgrid); break;                                                   \
+    case 3: RCB_SPLIT(TY, 4, 3, sgrid); break;                                                   \
+    case 4: RCB_SPLIT(TY, 4, 4, sgrid); break;                                                   \
+    default: RCB_SPLIT(TY, 4, 8, sgrid);                                                         \
+  }
+        if (y64) { RCB_SPLIT_D(double); } else { RCB_SPLIT_D(float); }
+#undef RCB_SPLIT_D
       } else {
-        colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp);
+        colmax_kernel<1><<<dim3((unsigned)((F + 255) / 256), ny, (unsigned)nmem), 256, 0, ctx->stream>>>(Z, ldz, F, T, washout, Te, s0, Sc, amax, z_stride, ldp, spc);
         const dim3 sgrid((unsigned)(ldp / 256), ny, (unsigned)nmem);
         if (y64) RCB_SPLIT(double, 1, 8, sgrid); else RCB_SPLIT(float, 1, 8, sgrid);
       }
@@ -595,6 +755,8 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     p.tiles = (const int2*)d_tiles; p.ntiles = ntiles; p.q8 = (const unsigned char*)q8; p.sf = sf; p.nfb = ldp / 128;
     p.S = Sc; p.G = G; p.ldo = ldo; p.F = F; p.err = d_err;
     p.nmem = (int)nmem; p.q8_stride = q8_stride; p.g_stride = g_stride;
+    p.relay = getenv("RCB_GRAM_RELAY") ? std::max(1, std::min(K2Cfg<true>::STAGES, atoi(getenv("RCB_GRAM_RELAY")))) : 4;
+    p.relaxed = getenv("RCB_GRAM_RELAXED") ? 1 : 0;
     {
       double lam = ctx->gram_lambda_hint;
       if (const char* e = getenv("RCB_GRAM_PHASES")) lam = atoi(e) == 2 ? 1e300 : -1.0;  // testing hook: force 2 / 3 phases
@@ -622,7 +784,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     const int grid = (int)(nitems < ncl_max ? nitems : ncl_max) * CLUSTER;
     const bool tsplit = getenv("RCB_GRAM_TIMING") != nullptr;  // diagnostics: time the MMA kernel alone in the SOLVE timer slot
     if (tsplit) timer_begin(ctx, RCB_TIMER_SOLVE);
-    gram_i8_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p);
+    kern<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p);
     if (tsplit) timer_end(ctx, RCB_TIMER_SOLVE);
     ctx->launches++;
     RCB_CUDA(cudaGetLastError());
@@ -633,6 +795,11 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
       double sum[5] = {0, 0, 0, 0, 0};
       long long mx = 0;
       for (int b = 0; b < grid; ++b) { for (int q = 0; q < 5; ++q) sum[q] += (double)hp[b * 5 + q]; if (hp[b * 5 + 4] > mx) mx = hp[b * 5 + 4]; }
+      if (pair) {
+        double own = 0, peer = 0;
+        for (int b = 0; b < grid; b += 2) { own += (double)hp[b * 5]; peer += (double)hp[(b + 1) * 5]; }
+        fprintf(stderr, "[gram prof] pair: leader waits own stage %.3g, peer's stage %.3g cycles per pair\n", own / (grid / 2), peer / (grid / 2));
+      }
       fprintf(stderr, "[gram prof] grid %d items %lld x %lld samples: avg cycles/CTA: mma waits full %.3g, mma waits tmem %.3g, producer waits "
               "empty %.3g, epilogue waits %.3g, producer total %.3g (max %lld)\n", grid, nitems, p.per_split, sum[0] / grid, sum[1] / grid,
               sum[2] / grid, sum[3] / grid, sum[4] / grid, mx);
