@@ -265,10 +265,18 @@ static int32_t launch_cross_thin(rcb_ctx* ctx, GramParams g) {
 }
 
 // ---- iterative refinement: residual targets E[:, col] = y_col - W z_col for the samples of the set ---------------------------
-// SB samples per CTA iteration share every load of W (d_out x F, FP64, L2-resident); the features of a sample are read
-// once, coalesced along the contiguous feature axis; FP64 accumulation, warp-shuffle + shared-memory reduction.
+// SB samples per warp iteration share every load of W; the features of a sample are read once, coalesced along the contiguous
+// feature axis; FP64 accumulation, warp-shuffle reduction.  W is read from a TRANSPOSED copy WT[o][f] (feature-contiguous,
+// L1-resident): in the caller's d_out x F column-major order the 8-byte loads of a warp are 24 bytes apart (d_out = 3) and each
+// touches six or seven 128-byte lines.  (r02: 3.3 ms per 8.6 GB window = 2.6 TB/s either way — the kernel is bound by the
+// 48 KB of loads 24 resident warps keep in flight per SM, not by L1; a shared-memory ring fed by bulk copies is the next step.)
+// DO = d_out for d_out <= 4 (no padded multiply-adds); DO = 8 guards o < d_out.
+__global__ void transpose_w_kernel(const double* __restrict__ W, long long F, int d_out, double* __restrict__ WT) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < F * d_out) WT[(i % d_out) * F + i / d_out] = W[i];
+}
 template <typename TZ, typename TY, int DO>
-__global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __restrict__ W, const TZ* __restrict__ Z, long long ldz,
+__global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __restrict__ WT, const TZ* __restrict__ Z, long long ldz,
                                                          const TY* __restrict__ Y, long long ldy, long long F, long long T,
                                                          long long washout, long long Te, long long Stot, int d_out,
                                                          double* __restrict__ E) {
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __rest
       for (int u = 0; u < UN; ++u) {
         double w[DO];
 #pragma unroll
-        for (int o = 0; o < DO; ++o) w[o] = (o < d_out && f0 + 32 * u < F) ? __ldg(W + (size_t)(f0 + 32 * u) * d_out + o) : 0.0;
+        for (int o = 0; o < DO; ++o) w[o] = ((DO <= 4 || o < d_out) && f0 + 32 * u < F) ? __ldg(WT + (size_t)o * F + f0 + 32 * u) : 0.0;
 #pragma unroll
         for (int q = 0; q < SB; ++q) {
           const double zd = (double)z[u][q];
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __rest
         double v = acc[q][o];
 #pragma unroll
         for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
-        if (lane == 0 && o < d_out && s0 + q < Stot) E[(size_t)col[q] * d_out + o] = (double)Y[(size_t)col[q] * ldy + o] - v;
+        if (lane == 0 && (DO <= 4 || o < d_out) && s0 + q < Stot) E[(size_t)col[q] * d_out + o] = (double)Y[(size_t)col[q] * ldy + o] - v;
       }
   }
 }
@@ -424,19 +432,29 @@ int32_t launch_ridge_residual(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t 
   const long long Te = T - washout, Stot = Te * nseq;
   if (Stot <= 0) return RCB_OK;
   void* e = nullptr;
-  RCB_TRY(ctx_scratch(ctx, SCR_RESID, (size_t)d_out * T * nseq * sizeof(double), &e));
+  RCB_TRY(ctx_scratch(ctx, SCR_RESID, ((size_t)d_out * T * nseq + (size_t)d_out * F) * sizeof(double), &e));   // E | WT
+  double* wt = (double*)e + (size_t)d_out * T * nseq;
+  transpose_w_kernel<<<(unsigned)((F * d_out + 255) / 256), 256, 0, ctx->stream>>>(W, F, (int)d_out, wt);
+  ctx->launches++;
   const int grid = (int)std::min<long long>((Stot + 31) / 32, 16LL * ctx->sm_count);   // 8 warps x 4 samples per CTA pass
   const bool z64 = zdt == RCB_F64, y64 = ydt == RCB_F64;
-#define RCB_RES(TZ, TY)                                                                                                                   \
-  do {                                                                                                                                    \
-    if (d_out <= 4) residual_e_kernel<TZ, TY, 4><<<grid, 256, 0, ctx->stream>>>(W, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e); \
-    else residual_e_kernel<TZ, TY, 8><<<grid, 256, 0, ctx->stream>>>(W, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e);            \
+#define RCB_RES_D(TZ, TY, D) residual_e_kernel<TZ, TY, D><<<grid, 256, 0, ctx->stream>>>(wt, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e)
+#define RCB_RES(TZ, TY)                     \
+  do {                                      \
+    switch ((int)d_out) {                   \
+      case 1: RCB_RES_D(TZ, TY, 1); break;  \
+      case 2: RCB_RES_D(TZ, TY, 2); break;  \
+      case 3: RCB_RES_D(TZ, TY, 3); break;  \
+      case 4: RCB_RES_D(TZ, TY, 4); break;  \
+      default: RCB_RES_D(TZ, TY, 8);        \
+    }                                       \
   } while (0)
   if (!z64 && !y64) RCB_RES(float, float);
   else if (!z64 && y64) RCB_RES(float, double);
   else if (z64 && !y64) RCB_RES(double, float);
   else RCB_RES(double, double);
 #undef RCB_RES
+#undef RCB_RES_D
   ctx->launches++;
   RCB_CUDA(cudaGetLastError());
   GramArgs c;   // R += Z E' with the thin cross-term kernel

@@ -441,6 +441,28 @@ def test_gram_tensor_matches_exact(R, F, S, D):
     assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)  # cross term: exact FP64 products
 
 
+@pytest.mark.parametrize("env", [{"RCB_GRAM_PAIR": "1"}, {"RCB_GRAM_PAIR": "1", "RCB_GRAM_PHASES": "2"}, {"RCB_GRAM_PHASES": "2"},
+                                 {"RCB_GRAM_PAIR": "1", "RCB_GRAM_RELAY": "1"}])
+def test_gram_tensor_pair_variant_and_phase_groups(R, monkeypatch, env):
+    """The cta_group::2 form of the kernel (one M = 256 MMA per CTA pair, the peer's stages announced through a relayed
+    barrier) and the eight-product mode (phases A and B only) against the exact Gram: same digit products, same result."""
+    from rcb200 import _lib as L
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(5)
+    F, S, D = 700, 70000, 3        # several super-tiles incl. a partial one; more than one 32768-sample accumulation range
+    Z = np.asfortranarray((rng.standard_normal((F, S)) * rng.uniform(0.05, 1.0, (F, 1))).astype(np.float32))
+    Y = np.asfortranarray(rng.standard_normal((D, S)).astype(np.float32))
+    g_t = R.gram(Z, Y, gram_mode=L.GRAM_TENSOR)
+    Z64 = Z.astype(np.float64)
+    G = np.tril(Z64 @ Z64.T)
+    scale = np.sqrt(np.outer(np.diag(G), np.diag(G)))
+    assert np.max(np.abs(np.tril(g_t[:, :F]) - G) / scale) <= 1e-6
+    assert np.linalg.norm(np.tril(g_t[:, :F]) - G) / np.linalg.norm(G) <= 2e-7
+    assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)
+
+
 def test_gram_tensor_sub_chunks(R):
     """Several sample sub-chunks per call (what F = 8192 x 256k samples needs): G and the fused cross term."""
     from rcb200 import _lib as L
