@@ -78,6 +78,7 @@ struct GramParams8 {
   long long q8_stride;        // bytes between the members' digit planes
   long long g_stride;         // doubles between the members' G
   int* err;                   // set to 1 when a barrier wait timed out (the kernel then traps)
+  unsigned* sync;             // round counter: the producers of all CTAs start a round of work items together (L2 locality)
   int relay;                  // pair: lanes of the peer's warp 1 that take turns relaying "stage landed" to the leader
   int relaxed;                // testing hook: relay with a relaxed arrive
   long long* prof;            // RCB_GRAM_PROF: per CTA [mma waits full, mma waits tmem, producer waits empty, epi waits, total]
@@ -239,9 +240,21 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
   if (warp == 0) {
     // ===== producer: two contiguous bulk copies per stage =====
     if (lane == 0) {
-      long long it = 0, wait_acc = 0;
+      long long it = 0, wait_acc = 0, round = 0;
       const long long tstart = clock64();
-      for (long long item = cid; item < nitems; item += ncl) {
+      for (long long item = cid; item < nitems; item += ncl, ++round) {
+        if (p.sync && round > 0) {
+          // the clusters of a round stream the same few feature panels: keep them within the L2 window of each other by
+          // starting every round together (all CTAs are resident: the grid is at most one wave)
+          const unsigned target = (unsigned)(gridDim.x * round);
+          const long long t0 = clock64();
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync) : "memory");
+            if (seen < target) __nanosleep(100);
+            if (clock64() - t0 > 4000000000LL) { if (p.err) *p.err = 1; __trap(); }
+          } while (seen < target);
+        }
         const long long mem = item / per_mem, it_m = item - mem * per_mem;
         const int2 tl = p.tiles[it_m % p.ntiles];
         const long long split = it_m / p.ntiles;
@@ -285,6 +298,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             }
           }
         }
+        if (p.sync) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.sync) : "memory");
       }
       if (p.prof) { p.prof[blockIdx.x * 5 + 2] = wait_acc; p.prof[blockIdx.x * 5 + 4] = clock64() - tstart; }
     }
@@ -680,7 +694,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   RCB_TRY(ctx_scratch(ctx, SCR_TILES, tiles.size() * sizeof(int2) + 16, &d_tiles));
   RCB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
   int* d_err = reinterpret_cast<int*>((char*)d_tiles + tiles.size() * sizeof(int2));
-  RCB_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));
+  RCB_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int), ctx->stream));   // [err | nphase | round counter | -]
   // sample sub-chunks: the digit planes (3 B per state) stay within 6 GiB
   long long Ssub = ((long long)6 << 30) / (ldp * PLANES * nmem);
   if (const char* ov = getenv("RCB_GRAM_SUB_SAMPLES")) Ssub = atoll(ov);  // testing hook: force several sub-chunks
@@ -755,6 +769,8 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     p.tiles = (const int2*)d_tiles; p.ntiles = ntiles; p.q8 = (const unsigned char*)q8; p.sf = sf; p.nfb = ldp / 128;
     p.S = Sc; p.G = G; p.ldo = ldo; p.F = F; p.err = d_err;
     p.nmem = (int)nmem; p.q8_stride = q8_stride; p.g_stride = g_stride;
+    p.sync = (getenv("RCB_GRAM_SYNC") && atoi(getenv("RCB_GRAM_SYNC")) == 1) ? reinterpret_cast<unsigned*>(d_err + 2) : nullptr;
+    if (p.sync) RCB_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned), ctx->stream));
     p.relay = getenv("RCB_GRAM_RELAY") ? std::max(1, std::min(K2Cfg<true>::STAGES, atoi(getenv("RCB_GRAM_RELAY")))) : 4;
     p.relaxed = getenv("RCB_GRAM_RELAXED") ? 1 : 0;
     {
