@@ -112,7 +112,9 @@ RCB_API int32_t rcb_ctx_sm_count(rcb_ctx* ctx, int32_t* sms);
 /* number of kernel launches of this library issued on the context since creation (bench: gpu_launches) */
 RCB_API int32_t rcb_ctx_launch_count(rcb_ctx* ctx, int64_t* launches);
 /* device time [ms] between the first and last kernel of the most recent data-path call, measured
- * with CUDA events on the context's stream (bench: roofline.achieved) */
+ * with CUDA events on the context's stream (bench: roofline.achieved).  The same spans are NVTX ranges on the calling host
+ * thread ("rcb200:K1/K4 recurrence", "rcb200:K2 gram", "rcb200:K3 solve", "rcb200:exchange (NCCL)", "rcb200:refinement
+ * residual"): a profiler timeline shows which part of a train / predict call the kernels under it belong to. */
 RCB_API int32_t rcb_ctx_last_kernel_ms(rcb_ctx* ctx, int32_t which, float* ms);
 /* name of the kernel variant the most recent recurrence call launched, e.g. "k1_fast<NB=7,tmem,din=3,simple>" */
 RCB_API int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len);

@@ -3,6 +3,7 @@
 // CUDA kernels of recurrence.cu, recurrence_fast.cu, dense_kernels.cu, gram_tensor.cu and solve.cu; there is no CPU
 // compute path in this library.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; the ranges cost nothing unless a profiler injects its library
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -104,7 +105,11 @@ struct TimerPool {
 };
 static TimerPool* pools(rcb_ctx* ctx) { return reinterpret_cast<TimerPool*>(ctx->timer_pools); }
 
+// Every timed span is also an NVTX range on the calling host thread (tracing), named after the kernel family.
+static const char* const kRangeNames[RCB_TIMER_COUNT] = {"rcb200:K1/K4 recurrence", "rcb200:K2 gram", "rcb200:K3 solve",
+                                                         "rcb200:exchange (NCCL)", "rcb200:refinement residual"};
 void timer_begin(rcb_ctx* ctx, int which) {
+  nvtxRangePushA(kRangeNames[which]);
   if (ctx->timers_muted) return;
   TimerPool& p = pools(ctx)[which];
   if (p.used == (int)p.beg.size()) {
@@ -117,6 +122,7 @@ void timer_begin(rcb_ctx* ctx, int which) {
   cudaEventRecord(p.beg[p.used], ctx->stream);
 }
 void timer_end(rcb_ctx* ctx, int which) {
+  nvtxRangePop();
   if (ctx->timers_muted) return;
   TimerPool& p = pools(ctx)[which];
   cudaEventRecord(p.end[p.used], ctx->stream);
