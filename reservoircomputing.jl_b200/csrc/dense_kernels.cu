@@ -331,6 +331,126 @@ __global__ void __launch_bounds__(256, 3) residual_e_kernel(const double* __rest
   }
 }
 
+// The same residual with the states staged through shared memory by bulk copies (r02): the register version above keeps
+// only the 48 KB of loads its resident warps hold in flight per SM (2.6 TB/s); here thread 0 streams tiles of 32 samples x
+// FC features (+ the matching chunk of WT, shared by the eight warps) into a two-stage ring — up to 150 KB in flight per SM —
+// and the warps read them back conflict-free (lane = two neighbouring features of a 64-feature half block: 8-byte reads of the
+// states, 16-byte reads of WT).  Needs 16-byte aligned sample columns (ldz, F multiples of 4 elements for Float32).
+namespace {
+__device__ __forceinline__ uint32_t rr_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rr_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void rr_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+}  // namespace
+
+template <typename TZ, typename TY, int DO>
+__global__ void __launch_bounds__(288, 1) residual_ring_kernel(const double* __restrict__ WT, const TZ* __restrict__ Z, long long ldz,
+                                                               const TY* __restrict__ Y, long long ldy, long long F, long long T,
+                                                               long long washout, long long Te, long long Stot, int d_out,
+                                                               double* __restrict__ E) {
+  constexpr int SPC = 32, SB = 4, NST = 4;              // samples per CTA tile, per warp; ring stages
+  constexpr int ROWB = 1024;                            // bytes of a sample's slice in a stage
+  constexpr int FC = ROWB / (int)sizeof(TZ);            // features per chunk
+  constexpr int ZT = SPC * ROWB, WTB = DO * FC * 8;     // bytes of the state tile / of the WT chunk of a stage
+  constexpr int STAGE = ZT + WTB;
+  extern __shared__ __align__(128) unsigned char rr_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * NST];   // full[NST] | empty[NST]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = rr_smem(rr_raw), full0 = rr_smem(&bars[0]), empty0 = rr_smem(&bars[NST]);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * i), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * i), "r"(8) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long ngroups = (Stot + SPC - 1) / SPC;
+  const int nchunk = (int)((F + FC - 1) / FC);
+  if (warp == 8) {
+    // ===== producer warp: lane q streams sample q's slice, lanes < DO the chunk of WT =====
+    long long it = 0;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      const long long s = g * SPC + lane;
+      const bool live = s < Stot;
+      const int ns = (int)(Stot - g * SPC < SPC ? Stot - g * SPC : SPC);
+      const TZ* zrow = live ? Z + (size_t)((s / Te) * T + washout + s % Te) * ldz : Z;
+      for (int ch = 0; ch < nchunk; ++ch, ++it) {
+        const int slot = (int)(it % NST);
+        rr_wait(empty0 + 8 * slot, (uint32_t)(((it / NST) & 1) ^ 1));
+        const long long f0 = (long long)ch * FC;
+        const int nf = (int)(F - f0 < FC ? F - f0 : FC);
+        const uint32_t fb = full0 + 8 * slot, sa = base + (uint32_t)slot * STAGE;
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)(ns * nf * (int)sizeof(TZ) + DO * nf * 8)) : "memory");
+        __syncwarp();
+        if (live) rr_bulk(sa + (uint32_t)lane * ROWB, zrow + f0, (uint32_t)(nf * (int)sizeof(TZ)), fb);
+        if (lane < DO) rr_bulk(sa + ZT + (uint32_t)lane * FC * 8, WT + (size_t)(lane < d_out ? lane : 0) * F + f0, (uint32_t)(nf * 8), fb);
+      }
+    }
+    return;
+  }
+  long long it = 0;
+  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const long long s0 = g * SPC + warp * SB;
+    double acc[SB][DO];
+#pragma unroll
+    for (int q = 0; q < SB; ++q)
+#pragma unroll
+      for (int o = 0; o < DO; ++o) acc[q][o] = 0.0;
+    for (int ch = 0; ch < nchunk; ++ch, ++it) {
+      const int slot = (int)(it % NST);
+      rr_wait(full0 + 8 * slot, (uint32_t)((it / NST) & 1));
+      const unsigned char* st = rr_raw + (size_t)slot * STAGE;
+      const long long f0 = (long long)ch * FC;
+      const int nf = (int)(F - f0 < FC ? F - f0 : FC);
+      if (s0 < Stot) {
+        for (int fl = 2 * lane; fl < nf; fl += 64) {     // nf is a multiple of 4 (alignment), so fl + 1 < nf as well
+          double w[DO][2];
+#pragma unroll
+          for (int o = 0; o < DO; ++o) {
+            const double2 t = *reinterpret_cast<const double2*>(st + ZT + ((size_t)o * FC + fl) * 8);
+            w[o][0] = t.x; w[o][1] = t.y;
+          }
+#pragma unroll
+          for (int q = 0; q < SB; ++q) {
+            if (s0 + q < Stot) {                         // (rows past the end of the sample set were not copied)
+              const TZ* zr = reinterpret_cast<const TZ*>(st + (size_t)(warp * SB + q) * ROWB) + fl;
+              const double z0 = (double)zr[0], z1 = (double)zr[1];
+#pragma unroll
+              for (int o = 0; o < DO; ++o) acc[q][o] = fma(w[o][1], z1, fma(w[o][0], z0, acc[q][o]));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < SB; ++q) {
+      const long long s = s0 + q;
+      const long long c = s < Stot ? (s / Te) * T + washout + s % Te : 0;
+#pragma unroll
+      for (int o = 0; o < DO; ++o) {
+        double v = acc[q][o];
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0 && (DO <= 4 || o < d_out) && s < Stot) E[(size_t)c * d_out + o] = (double)Y[(size_t)c * ldy + o] - v;
+      }
+    }
+  }
+}
+
 __global__ void refine_init_kernel(const double* __restrict__ W, long long F, int d_out, double lambda, double* __restrict__ R, long long ldr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F * d_out) return;
@@ -432,13 +552,28 @@ int32_t launch_ridge_residual(rcb_ctx* ctx, const void* Z, int32_t zdt, int64_t 
   const long long Te = T - washout, Stot = Te * nseq;
   if (Stot <= 0) return RCB_OK;
   void* e = nullptr;
-  RCB_TRY(ctx_scratch(ctx, SCR_RESID, ((size_t)d_out * T * nseq + (size_t)d_out * F) * sizeof(double), &e));   // E | WT
-  double* wt = (double*)e + (size_t)d_out * T * nseq;
+  const size_t e_len = ((size_t)d_out * T * nseq + 1) / 2 * 2;   // WT starts 16-byte aligned (bulk copies)
+  RCB_TRY(ctx_scratch(ctx, SCR_RESID, (e_len + (size_t)d_out * F) * sizeof(double), &e));   // E | WT
+  double* wt = (double*)e + e_len;
   transpose_w_kernel<<<(unsigned)((F * d_out + 255) / 256), 256, 0, ctx->stream>>>(W, F, (int)d_out, wt);
   ctx->launches++;
   const int grid = (int)std::min<long long>((Stot + 31) / 32, 16LL * ctx->sm_count);   // 8 warps x 4 samples per CTA pass
   const bool z64 = zdt == RCB_F64, y64 = ydt == RCB_F64;
-#define RCB_RES_D(TZ, TY, D) residual_e_kernel<TZ, TY, D><<<grid, 256, 0, ctx->stream>>>(wt, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e)
+  // the shared-memory ring needs 16-byte aligned sample slices (bulk copies); RCB_RESID_RING=0: the register version (A/B hook)
+  const size_t zesz = z64 ? 8 : 4;
+  const bool ring = ((uintptr_t)Z % 16 == 0) && ((size_t)ldz * zesz) % 16 == 0 && ((size_t)F * zesz) % 16 == 0 && F >= 256 && (F * 8) % 16 == 0 &&
+                    !(getenv("RCB_RESID_RING") && atoi(getenv("RCB_RESID_RING")) == 0);
+  const int rgrid = (int)std::min<long long>((Stot + 31) / 32, (long long)ctx->sm_count);
+#define RCB_RES_D(TZ, TY, D)                                                                                                              \
+  do {                                                                                                                                    \
+    if (ring) {                                                                                                                           \
+      constexpr int smem = 4 * (32 * 1024 + D * (1024 / (int)sizeof(TZ)) * 8);                                                            \
+      cudaFuncSetAttribute(residual_ring_kernel<TZ, TY, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                           \
+      residual_ring_kernel<TZ, TY, D><<<rgrid, 288, smem, ctx->stream>>>(wt, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e); \
+    } else {                                                                                                                              \
+      residual_e_kernel<TZ, TY, D><<<grid, 256, 0, ctx->stream>>>(wt, (const TZ*)Z, ldz, (const TY*)Y, ldy, F, T, washout, Te, Stot, (int)d_out, (double*)e); \
+    }                                                                                                                                     \
+  } while (0)
 #define RCB_RES(TZ, TY)                     \
   do {                                      \
     switch ((int)d_out) {                   \

@@ -241,3 +241,23 @@ def test_train_refines_end_to_end(R, esn_states, monkeypatch):
         ps2, _ = R.train(e["esn"], e["data"], e["target"], e["ps"], st0, objective=R.RidgeRegression(lam), washout=e["w"])
         assert R.default_device().last_refine()[0] >= 1
         assert rel(ps2.readout.weight, Wref) <= WEIGHT_RTOL, budget
+
+
+@pytest.mark.parametrize("F,S,d_out,dt", [(300, 1999, 3, np.float32), (256, 700, 1, np.float32), (1028, 4100, 5, np.float32),
+                                          (384, 1500, 2, np.float64), (512, 33, 8, np.float32), (302, 900, 3, np.float32)])
+def test_refinement_residual_ring_matches_register_kernel(R, F, S, d_out, dt, monkeypatch):
+    """The exact residual E = Y - W Z has two kernels: sample tiles staged through a shared-memory ring by bulk copies (16-byte
+    aligned slices: F * sizeof % 16 == 0) and the register version (everything else, here F = 302).  Same products, FP64
+    accumulation: the refined weights agree to rounding, and both meet the QR oracle."""
+    rng = np.random.default_rng(F + S)
+    Z = np.asfortranarray(np.tanh(rng.standard_normal((F, 24)) @ rng.standard_normal((24, S)) * 0.4 + 0.05 * rng.standard_normal((F, S))).astype(dt))
+    Y = np.asfortranarray((rng.standard_normal((d_out, F)) @ Z / np.sqrt(F)).astype(dt))
+    lam = 1e-5 * S
+    monkeypatch.setenv("RCB_GRAM", "fp64")
+    out = {}
+    for ring in ("1", "0"):
+        monkeypatch.setenv("RCB_RESID_RING", ring)
+        out[ring] = R.fit_readout(R.RidgeRegression(lam), Z, Y)
+        assert R.default_device().last_refine()[0] >= 1
+    assert rel(out["1"], out["0"]) <= 1e-9
+    assert rel(out["1"], O.train_ridge_qr(Z, Y, lam)) <= WEIGHT_RTOL
