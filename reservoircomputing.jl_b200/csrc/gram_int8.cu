@@ -497,7 +497,7 @@ __device__ __forceinline__ uint32_t digits3(float x, float qs) {
 // One thread = VEC consecutive features over a slab of samples: with VEC = 4 a warp reads 512 contiguous bytes per sample
 // and writes one full 128-byte row of each digit plane (32-bit stores, full sectors).
 template <typename TY, int VEC, int DMAX>
-__global__ void __launch_bounds__(256) split_int8_kernel(const float* __restrict__ Z, long long ldz, long long F, long long ldp,
+__global__ void __launch_bounds__(256, 4) split_int8_kernel(const float* __restrict__ Z, long long ldz, long long F, long long ldp,
                                                          long long T, long long washout, long long Te, long long s0,
                                                          long long Sc, const int* __restrict__ amax, unsigned char* __restrict__ q8,
                                                          double* __restrict__ sf, const TY* __restrict__ Y, long long ldy, int d_out,
