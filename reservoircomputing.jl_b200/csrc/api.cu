@@ -348,6 +348,11 @@ static int32_t install_weights(rcb_esn* esn, int32_t layer, const float* W_in, i
     std::vector<long long> rp(K.rowptr.begin(), K.rowptr.end());
     std::vector<int> ci(K.colind.begin(), K.colind.end());
     RCB_TRY(upload(rp, &L.d_csr_rowptr));
+    L.h_csr_rowptr = rp;
+    L.csr_sorted = true;
+    for (int r = 0; r < L.n && L.csr_sorted; ++r)
+      for (long long e = rp[(size_t)r] + 1; e < rp[(size_t)r + 1]; ++e)
+        if (ci[(size_t)e] <= ci[(size_t)e - 1]) { L.csr_sorted = false; break; }
     RCB_TRY(upload(ci, &L.d_csr_colind));
     RCB_TRY(upload(K.vals, &L.d_csr_vals));
     std::vector<float> wcm((size_t)L.n * L.d_in);

@@ -166,6 +166,8 @@ struct Layer {
   // cooperative multi-SM kernel of the dense-operator cells (recurrence_coop.cu): O row-major, W as CSR, W_in by row
   float* d_Orow = nullptr;
   long long* d_csr_rowptr = nullptr;
+  std::vector<long long> h_csr_rowptr;   // host copy (recurrence_coop.cu sizes its per-CTA slices from it)
+  bool csr_sorted = false;               // columns ascending inside every row
   int* d_csr_colind = nullptr;
   float* d_csr_vals = nullptr;
 };

@@ -262,6 +262,8 @@ int32_t launch_collect(rcb_ctx* ctx, const CollectArgs& a) {
     bool launched = false;
     const int32_t cp = launch_collect_coop(ctx, p, L, &launched);
     if (cp != RCB_OK || launched) return cp;
+    const int32_t cb = launch_collect_coop_batched(ctx, p, L, &launched);
+    if (cb != RCB_OK || launched) return cb;
   }
   if (a.dtype == RCB_F32 && !p.Ot) {  // the tuned path (recurrence_fast.cu); falls through when it does not apply
     bool launched = false;

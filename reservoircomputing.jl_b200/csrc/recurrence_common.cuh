@@ -191,5 +191,7 @@ int32_t launch_collect_cluster(rcb_ctx* ctx, const RecParams& p, const Layer& L,
 
 // recurrence_coop.cu: ES2N / ResESN, one sequence, a cooperative grid with one barrier per step
 int32_t launch_collect_coop(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched);
+// recurrence_coop.cu: the same cells in batches: rows x sequences over a cooperative grid, the slices of O resident
+int32_t launch_collect_coop_batched(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched);
 
 }  // namespace rcb

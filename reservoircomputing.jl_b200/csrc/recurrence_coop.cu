@@ -113,6 +113,236 @@ __global__ void __launch_bounds__(256) k1_coop_kernel(const CoopArgs a) {
   }
 }
 
+
+// ---- the same cells in BATCHES (r02) -----------------------------------------------------------------------------------
+// B sequences through a dense-operator cell: with one CTA per sequence (tile) every CTA pulls all of O through its own L2
+// port every step (58 us/step at N = 1024 whatever B).  Here a cooperative grid is a 2-D decomposition rows x sequences:
+// CTA (rb, kb) keeps ITS rows of O resident in shared memory for the whole call and owns a block of sequences; per step it
+// streams the state of its sequences (H[j][b], sequences contiguous: [n][Bpad] global exchange buffer, double-buffered)
+// through a cp.async ring in slabs of JC columns and accumulates acc[row] += O[row][j] h[j][b] with one thread per
+// (sequence, row group) — the slice of O is read as warp-wide broadcasts, the states conflict-free along the sequences.
+// The sparse term, the input projection and the activation are the epilogue of the same thread; one grid.sync() per step.
+struct CoopBArgs {
+  int n, d_in, feat, act, rpc, spc, R, K, rt, ecap;   // rows / sequences per CTA, grid shape, rows per thread, sparse entries per CTA
+  int G, spct, jc;                                    // row groups (the other 8 / G warps split the sequences), lanes per pass, slab columns
+  long long T, B, Bpad, h_stride, h_off;
+  FusedMod mod;
+  const float* Orow;
+  const long long* rowptr;
+  const int* colind;
+  const float* vals;
+  const float* Win;
+  const float* bias;
+  float skip_a, cand_b;
+  const float* u;             // [B][T][d_in]
+  const float* h0;            // [B][h_stride] or nullptr
+  float* hbuf;                // [2][n][Bpad]
+  float* states;              // [B][T][feat] or nullptr
+  float* hT;
+  long long* prof;            // RCB_COOPB_PROF: cycles of CTA 0 in [output, slab loop, epilogue, grid barrier]
+};
+
+__device__ __forceinline__ float coopb_feature(const FusedMod& m, const float* s, long long ld, int n, int f) {
+  if (m.has_pad && f == m.feat1) return (float)m.pad;
+#define S_(i) __ldcg(s + (size_t)(i) * ld)
+  switch (m.kind) {
+    case RCB_MOD_NLAT1: { const float v = S_(f); return (f & 1) == 0 ? v * v : v; }
+    case RCB_MOD_NLAT2: return ((f & 1) == 0 && f >= 2) ? S_(f - 1) * S_(f - 2) : S_(f);
+    case RCB_MOD_NLAT3: return ((f & 1) == 0 && f >= 2 && f < n - 1) ? S_(f - 1) * S_(f + 1) : S_(f);
+    case RCB_MOD_PARTIAL_SQUARE: { const float v = S_(f); return f < m.thr ? v * v : v; }
+    case RCB_MOD_EXTENDED_SQUARE: { const float v = S_(f < n ? f : f - n); return f < n ? v : v * v; }
+    default: return S_(f);
+  }
+#undef S_
+}
+
+constexpr int CB_JCMAX = 64, CB_NSTG = 4, CB_MAXRT = 8, CB_MAXDIN = 8;
+
+// One slab (CB_JC columns) of the dense term for a thread's RT rows x NS sequences: the slice of O as warp-wide 16-byte
+// broadcasts, the states conflict-free along the sequences.  Slabs and rows are zero-padded, so there is no bounds logic here
+// (r02: the first version with run-time row counts and column checks issued 146 instructions per four columns).
+template <int RT, int NS>
+__device__ __forceinline__ void coopb_slab(const float* __restrict__ hs, const float* __restrict__ orow, int np4, int spct, int nq,
+                                           float (&acc)[CB_MAXRT][NS]) {
+#pragma unroll 4
+  for (int jq = 0; jq < nq; ++jq) {
+    float h[4][NS];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < NS; ++q) h[i][q] = hs[(jq * 4 + i) * spct + 32 * q];
+#pragma unroll
+    for (int rr = 0; rr < RT; ++rr) {
+      const float4 o = *reinterpret_cast<const float4*>(orow + (size_t)rr * np4 + jq * 4);
+#pragma unroll
+      for (int q = 0; q < NS; ++q) acc[rr][q] = fmaf(o.w, h[3][q], fmaf(o.z, h[2][q], fmaf(o.y, h[1][q], fmaf(o.x, h[0][q], acc[rr][q]))));
+    }
+  }
+}
+
+// NS: sequences per thread (lanes tb, tb + 32, ...).  The 8 warps are G row groups (<= 8 rows per thread) x 8 / G sequence
+// groups: a CTA pass covers spct = (8 / G) * 32 * NS sequences, and every state value is read by G warps only.
+template <int NS>
+__global__ void __launch_bounds__(256) k1_coop_batched_kernel(const CoopBArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float cb_smem[];
+  const int SPCT = a.spct, CB_JC = a.jc;
+  const int tid = threadIdx.x, n = a.n, np4 = (n + 3) & ~3;
+  const int rb = blockIdx.x % a.R, kb = blockIdx.x / a.R;
+  const int r0 = rb * a.rpc, r1 = min(n, r0 + a.rpc), nrows = r1 - r0;
+  const long long b0 = (long long)kb * a.spc, b1 = b0 + a.spc < a.B ? b0 + a.spc : a.B;
+  const int rows_alloc = a.G * a.rt, npc = ((n + CB_JC - 1) / CB_JC) * CB_JC;   // whole row groups, whole slabs: zero padding
+  float* os = cb_smem;                                  // [rows_alloc][npc]: my rows of O, resident
+  float* hc = os + (size_t)rows_alloc * npc;            // [CB_NSTG][CB_JC][SPCT]: slabs of the states of the current sequence lanes
+  float* wb = hc + (size_t)CB_NSTG * CB_JC * SPCT;      // [rpc][d_in + 1]: my rows of W_in and the bias
+  int* rp = reinterpret_cast<int*>(wb + (size_t)a.rpc * (a.d_in + 1));   // [rpc + 1]: my rows of the sparse operator (local offsets)
+  int* ecol = rp + a.rpc + 1;                           // [ecap] columns (ascending inside a row)
+  float* eval_ = reinterpret_cast<float*>(ecol + a.ecap);   // [ecap] values
+  for (int e = tid; e < rows_alloc * npc; e += blockDim.x) {
+    const int r = e / npc, j = e - r * npc;
+    os[e] = (r < nrows && j < n) ? __ldg(a.Orow + (size_t)(r0 + r) * n + j) : 0.0f;
+  }
+  for (int e = tid; e < CB_NSTG * CB_JC * SPCT; e += blockDim.x) hc[e] = 0.0f;   // columns past n / lanes past the block stay finite
+  const long long e0g = a.rowptr[r0];
+  for (int r = tid; r <= a.rpc; r += blockDim.x) rp[r] = (int)(a.rowptr[min(r0 + r, r1)] - e0g);
+  for (int e = tid; e < (int)(a.rowptr[r1] - e0g); e += blockDim.x) { ecol[e] = __ldg(a.colind + e0g + e); eval_[e] = __ldg(a.vals + e0g + e); }
+  for (int e = tid; e < nrows * (a.d_in + 1); e += blockDim.x) {
+    const int r = e / (a.d_in + 1), d = e - r * (a.d_in + 1);
+    wb[e] = d < a.d_in ? __ldg(a.Win + (size_t)d * n + r0 + r) : (a.bias ? __ldg(a.bias + r0 + r) : 0.0f);
+  }
+  for (long long e = tid; e < (long long)nrows * (b1 - b0); e += blockDim.x) {
+    const int r = r0 + (int)(e / (b1 - b0));
+    const long long b = b0 + e % (b1 - b0);
+    a.hbuf[(size_t)r * a.Bpad + b] = a.h0 ? a.h0[(size_t)b * a.h_stride + a.h_off + r] : 0.0f;
+  }
+  const int g = (tid >> 5) % a.G, sg = (tid >> 5) / a.G;   // my row group and sequence group (one warp = one of each)
+  const int tb = sg * 32 * NS + (tid & 31);             // my first sequence lane of a pass
+  const int lr0 = g * a.rt;                             // first local row of my group
+  const int nslab = (n + CB_JC - 1) / CB_JC;
+  long long pc[4] = {0, 0, 0, 0}, pt = 0;
+  grid.sync();
+  for (long long t = 0; t <= a.T; ++t) {
+    const float* hin = a.hbuf + (size_t)(t & 1) * n * a.Bpad;
+    float* hout = a.hbuf + (size_t)((t + 1) & 1) * n * a.Bpad;
+    for (long long sb0 = b0; sb0 < b1 || sb0 == b0; sb0 += SPCT) {
+      const int nsb = (int)(b1 - sb0 < SPCT ? b1 - sb0 : SPCT);
+      const int q4 = (nsb + 3) >> 2;                    // 16-byte pieces per column of the slab
+      auto issue = [&](int slab) {
+        if (t < a.T && slab < nslab) {
+          float* dst = hc + (size_t)(slab % CB_NSTG) * CB_JC * SPCT;
+          const int j0 = slab * CB_JC, nj = min(CB_JC, n - j0);
+          for (int e = tid; e < nj * q4; e += blockDim.x) {
+            const int j = e / q4, q = e - j * q4;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (size_t)j * SPCT + 4 * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(hin + (size_t)(j0 + j) * a.Bpad + sb0 + 4 * q) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+#pragma unroll
+      for (int s = 0; s < CB_NSTG - 1; ++s) issue(s);
+      pt = clock64();
+      if (sb0 == b0 && t > 0 && a.states) {
+        // collected column t-1 of my sequences, my rows (features fastest: contiguous runs per sequence) — while the first slabs fly
+        const long long cnt = (long long)nrows * (b1 - b0);
+        for (long long e = tid; e < cnt; e += blockDim.x) {
+          const int f = r0 + (int)(e % nrows);
+          const long long b = b0 + e / nrows;
+          float* out = a.states + ((size_t)b * a.T + (t - 1)) * a.feat;
+          out[f] = coopb_feature(a.mod, hin + b, a.Bpad, n, f);
+          if (a.mod.kind == RCB_MOD_EXTENDED_SQUARE) out[n + f] = coopb_feature(a.mod, hin + b, a.Bpad, n, n + f);
+        }
+        if (a.mod.has_pad && rb == 0)
+          for (long long b = b0 + tid; b < b1; b += blockDim.x) a.states[((size_t)b * a.T + (t - 1)) * a.feat + a.mod.feat1] = (float)a.mod.pad;
+      }
+      if (t == a.T) break;
+      pc[0] += clock64() - pt; pt = clock64();
+      float acc[CB_MAXRT][NS], rec[CB_MAXRT][NS], uv[CB_MAXDIN][NS];
+      int cur[CB_MAXRT], end[CB_MAXRT];
+#pragma unroll
+      for (int rr = 0; rr < CB_MAXRT; ++rr) {
+        const bool live = rr < a.rt && lr0 + rr < nrows;
+        cur[rr] = live ? rp[lr0 + rr] : 0;
+        end[rr] = live ? rp[lr0 + rr + 1] : 0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) { acc[rr][q] = 0.0f; rec[rr][q] = 0.0f; }
+      }
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const long long b = sb0 + tb + 32 * q < b1 ? sb0 + tb + 32 * q : b1 - 1;
+#pragma unroll
+        for (int d = 0; d < CB_MAXDIN; ++d) uv[d][q] = d < a.d_in ? __ldg(a.u + ((size_t)b * a.T + t) * a.d_in + d) : 0.0f;
+      }
+      for (int slab = 0; slab < nslab; ++slab) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(CB_NSTG - 2) : "memory");
+        __syncthreads();                                 // slab landed for everyone; the buffer refilled below is no longer read
+        issue(slab + CB_NSTG - 1);
+        const float* hs = hc + (size_t)(slab % CB_NSTG) * CB_JC * SPCT + tb;
+        const int j0 = slab * CB_JC, nj = min(CB_JC, n - j0);
+        const float* orow = os + (size_t)lr0 * npc + j0;
+        switch (a.rt) {
+          case 1: coopb_slab<1, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 2: coopb_slab<2, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 3: coopb_slab<3, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 4: coopb_slab<4, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 5: coopb_slab<5, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 6: coopb_slab<6, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 7: coopb_slab<7, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          default: coopb_slab<8, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+        }
+        // the sparse term from the same slab: the entries of my rows whose column lies in [j0, j0 + nj) (ascending columns)
+#pragma unroll
+        for (int rr = 0; rr < CB_MAXRT; ++rr) {
+          while (cur[rr] < end[rr]) {
+            const int c = ecol[cur[rr]];
+            if (c >= j0 + nj) break;
+            const float v = eval_[cur[rr]];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) rec[rr][q] = fmaf(v, hs[(size_t)(c - j0) * SPCT + 32 * q], rec[rr][q]);
+            ++cur[rr];
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      pc[1] += clock64() - pt; pt = clock64();
+#pragma unroll
+      for (int q = 0; q < NS; ++q) {
+        const long long b = sb0 + tb + 32 * q;
+        if (b < b1) {
+#pragma unroll
+          for (int rr = 0; rr < CB_MAXRT; ++rr) {
+            if (rr < a.rt && lr0 + rr < nrows) {
+              const float* w = wb + (size_t)(lr0 + rr) * (a.d_in + 1);
+              float win = 0.f;
+#pragma unroll
+              for (int d = 0; d < CB_MAXDIN; ++d)
+                if (d < a.d_in) win = fmaf(w[d], uv[d][q], win);
+              const float x = win + (rec[rr][q] + w[a.d_in]);   // the bias belongs to the recurrent term (es2n_cell.jl:111)
+              __stcg(hout + (size_t)(r0 + lr0 + rr) * a.Bpad + b, a.skip_a * acc[rr][q] + a.cand_b * apply_act<float>(a.act, x));
+            }
+          }
+        }
+      }
+      __syncthreads();                                   // the ring is reused by the next pass over sequences
+      pc[2] += clock64() - pt;
+    }
+    if (t == a.T) break;
+    pt = clock64();
+    grid.sync();
+    pc[3] += clock64() - pt;
+  }
+  if (a.prof && blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 4; ++i) a.prof[i] = pc[i];
+  if (a.hT) {
+    const float* fin = a.hbuf + (size_t)(a.T & 1) * n * a.Bpad;
+    for (long long e = tid; e < (long long)nrows * (b1 - b0); e += blockDim.x) {
+      const int r = r0 + (int)(e % nrows);
+      const long long b = b0 + e / nrows;
+      a.hT[(size_t)b * a.h_stride + a.h_off + r] = __ldcg(fin + (size_t)r * a.Bpad + b);
+    }
+  }
+}
+
 }  // namespace
 
 // ES2N / ResESN, one Float32 sequence, direct inputs: cooperative multi-SM kernel; *launched stays false otherwise.
@@ -158,6 +388,98 @@ int32_t launch_collect_coop(rcb_ctx* ctx, const RecParams& p, const Layer& L, bo
   snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop<dense skip operator%s> grid=%d", a.o_resident ? ",O-resident" : "", grid);
   ctx->launches++;
   *launched = true;
+  return RCB_OK;
+}
+
+// ES2N / ResESN, a batch of Float32 sequences, direct inputs: the 2-D cooperative kernel; *launched stays false otherwise.
+int32_t launch_collect_coop_batched(rcb_ctx* ctx, const RecParams& p, const Layer& L, bool* launched) {
+  *launched = false;
+  const char* mode = getenv("RCB_K1_MODE");  // testing hook: anything but "coop" (or unset) skips this kernel
+  if (mode && strcmp(mode, "coop")) return RCB_OK;
+  if (!p.Ot || !L.d_Orow || !L.d_csr_rowptr || !L.d_Win_cm || p.B < 2 || p.pre_in || p.member_scale || p.member_leak || p.leakv) return RCB_OK;
+  if (p.n < 128 || p.d_in > CB_MAXDIN || !L.csr_sorted || (int)L.h_csr_rowptr.size() != p.n + 1) return RCB_OK;
+  // Where it pays (r02, profiles/r02_dense_operator_batched.txt): N = 1024, 148 sequences 47 vs 58 us/step for one CTA per
+  // sequence tile; it loses at N = 512 x 32 (26 vs 17), N = 1024 x 1024 (164 vs 142) and N = 2048 x 296 (355 vs 249) — the slab
+  // loop runs at 30 % issue efficiency with two warps per scheduler.  Until that is fixed the kernel is taken by default only
+  // around the measured win; RCB_K1_MODE=coop forces it (tests).
+  if (!mode && !(p.n >= 768 && p.n <= 1536 && p.B >= 64 && p.B <= 2LL * ctx->sm_count)) return RCB_OK;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  if (!coop) return RCB_OK;
+  CoopBArgs a{};
+  a.n = p.n; a.d_in = p.d_in; a.feat = p.raw ? p.n : p.feat; a.act = p.act; a.T = p.T; a.B = p.B;
+  a.Bpad = (p.B + 3) & ~3LL;
+  a.mod = p.mod;
+  if (p.raw) { a.mod.kind = 0; a.mod.has_pad = 0; }
+  a.Orow = L.d_Orow; a.rowptr = L.d_csr_rowptr; a.colind = L.d_csr_colind; a.vals = L.d_csr_vals; a.Win = L.d_Win_cm; a.bias = p.bias;
+  a.skip_a = (float)p.skip_a; a.cand_b = (float)p.cand_b;
+  a.u = reinterpret_cast<const float*>(p.u);
+  a.h0 = reinterpret_cast<const float*>(p.h0); a.h_stride = p.h_stride; a.h_off = p.h_off;
+  a.states = reinterpret_cast<float*>(p.states);
+  a.hT = reinterpret_cast<float*>(p.hT);
+  // grid shape: as many row blocks as keep a CTA's slice of O (+ the ring of state slabs + its rows of W, W_in) inside shared
+  // memory, the sequences over the remaining factor of the SM count.  Inside a CTA: G row groups (rows per thread <= 8) x 8 / G
+  // sequence groups of 32 * NS lanes; the ring holds CB_NSTG slabs of jc columns x spct <= 128 lanes (<= 64 KB).
+  const size_t ring_max = (size_t)CB_NSTG * 32 * 128 * sizeof(float);
+  if (ctx->smem_optin < ring_max + 8192 + (size_t)(p.n + CB_JCMAX) * sizeof(float) * 16) return RCB_OK;
+  const size_t budget = ctx->smem_optin - ring_max - 8192;
+  const size_t npc = (size_t)((p.n + CB_JCMAX - 1) / CB_JCMAX) * CB_JCMAX;           // (a multiple of either slab width)
+  const int rpc_max = (int)std::min<size_t>(budget / (npc * sizeof(float)) / 16 * 16, 8 * CB_MAXRT);   // whole row groups of any G
+  if (rpc_max < 16) return RCB_OK;                                                   // N > ~2.4 k rows of 16 do not fit: generic kernel
+  int R = (p.n + rpc_max - 1) / rpc_max;
+  if (R > ctx->sm_count) return RCB_OK;
+  int K = (int)std::min<long long>(std::max(1, ctx->sm_count / R), (p.B + 3) / 4);
+  R = std::min(ctx->sm_count / K, p.n);                                              // spend the SMs K leaves over on shorter row blocks
+  a.rpc = (p.n + R - 1) / R; R = (p.n + a.rpc - 1) / a.rpc;
+  a.spc = (int)(((p.B + K - 1) / K + 3) & ~3LL); K = (int)((p.B + a.spc - 1) / a.spc);
+  a.G = a.rpc > 32 ? 8 : a.rpc > 16 ? 4 : 2;
+  a.rt = (a.rpc + a.G - 1) / a.G;
+  const int sgc = 8 / a.G;                                                           // sequence groups
+  const int lanes = (a.spc + 32 * sgc - 1) / (32 * sgc);                             // sequences per thread to cover the block in one pass
+  const int ns = std::min(lanes <= 1 ? 1 : lanes <= 2 ? 2 : 4, 4 / sgc);             // spct <= 128
+  a.spct = sgc * 32 * ns;
+  a.jc = a.spct <= 64 ? 64 : 32;
+  int ecap = 0;
+  for (int rb = 0; rb < R; ++rb) {
+    const int r0 = rb * a.rpc, r1 = std::min(p.n, r0 + a.rpc);
+    ecap = std::max(ecap, (int)(L.h_csr_rowptr[(size_t)r1] - L.h_csr_rowptr[(size_t)r0]));
+  }
+  a.ecap = ecap;
+  const size_t npc_k = (size_t)((p.n + a.jc - 1) / a.jc) * a.jc;
+  const size_t smem = ((size_t)a.G * a.rt * npc_k + (size_t)CB_NSTG * a.jc * a.spct + (size_t)a.rpc * (p.d_in + 1) + a.rpc + 1 + 2 * (size_t)ecap) * sizeof(float);
+  a.R = R; a.K = K;
+  if (a.rt > CB_MAXRT || smem > ctx->smem_optin) return RCB_OK;
+  void* kern = ns == 1 ? (void*)k1_coop_batched_kernel<1> : ns == 2 ? (void*)k1_coop_batched_kernel<2> : (void*)k1_coop_batched_kernel<4>;
+  RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  if (ns == 1) RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<1>, 256, smem));
+  else if (ns == 2) RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<2>, 256, smem));
+  else RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<4>, 256, smem));
+  if (per_sm < 1 || R * K > per_sm * ctx->sm_count) return RCB_OK;
+  void* hb = nullptr;
+  RCB_TRY(ctx_scratch(ctx, SCR_INFO, 2 * (size_t)p.n * a.Bpad * sizeof(float), &hb));
+  a.hbuf = reinterpret_cast<float*>(hb);
+  RCB_CUDA(cudaMemsetAsync(hb, 0, 2 * (size_t)p.n * a.Bpad * sizeof(float), ctx->stream));   // (the padding lanes are read by the 16-byte copies)
+  static long long* prof_dev = nullptr;
+  const bool prof = getenv("RCB_COOPB_PROF") != nullptr;
+  if (prof && !prof_dev) cudaMalloc(&prof_dev, 4 * sizeof(long long));
+  a.prof = prof ? prof_dev : nullptr;
+  void* args[] = {(void*)&a};
+  timer_begin(ctx, RCB_TIMER_RECURRENCE);
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)(R * K)), dim3(256), args, smem, ctx->stream);
+  timer_end(ctx, RCB_TIMER_RECURRENCE);
+  if (e != cudaSuccess) return fail(RCB_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop_batched<dense skip operator,O-resident,%dx%d per thread,%d row groups> grid=%dx%d rows/CTA=%d seq/CTA=%d", a.rt, ns,
+           a.G, R, K, a.rpc, a.spc);
+  ctx->launches++;
+  *launched = true;
+  if (prof) {
+    long long hp[4];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(hp, prof_dev, sizeof(hp), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[coop batched prof] cycles per step of CTA 0: output %.0f, slab loop %.0f, epilogue %.0f, grid barrier %.0f\n", (double)hp[0] / p.T,
+            (double)hp[1] / p.T, (double)hp[2] / p.T, (double)hp[3] / p.T);
+  }
   return RCB_OK;
 }
 

@@ -1288,6 +1288,45 @@ def test_dense_operator_cells_cooperative_kernel(R, name, N, mods):
     assert state_err(states, sg) <= STATE_RTOL
 
 
+@pytest.mark.parametrize("name,N,B,mods", [("es2n", 300, 5, "nlat2_pad"), ("resesn", 1024, 37, "esq"), ("es2n", 130, 70, "nlat1_nlat2"),
+                                           ("resesn", 520, 150, "none"), ("es2n", 257, 2, "nlat2_pad")])
+def test_dense_operator_cells_batched_cooperative_kernel(R, name, N, B, mods):
+    """ES2N / ResESN in batches: the 2-D cooperative kernel (rows x sequences, each CTA's slice of O resident in shared memory,
+    the states exchanged through a global double buffer with one grid barrier per step) against the oracle and against the
+    one-CTA-per-sequence-tile kernel, incl. carry in / out over two calls, modifier chains, bias."""
+    import os
+
+    rng = np.random.default_rng(N + B)
+    chain = dict(nlat2_pad=(R.NLAT2, R.Pad(1.0)), esq=(R.ExtendedSquare,), nlat1_nlat2=(R.NLAT1, R.NLAT2), none=())[mods]
+    kw = dict(init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N), use_bias=True, init_bias=R.randn32, state_modifiers=chain)
+    rc = R.ES2N(3, N, 3, proximity=0.3, **kw) if name == "es2n" else R.ResESN(3, N, 3, alpha=0.7, beta=0.5, **kw)
+    ps, st = R.setup(rng, rc)
+    T = 40
+    data = np.asfortranarray(rng.standard_normal((3, 2 * T, B)).astype(np.float32))
+    h0 = rng.standard_normal((N, B)).astype(np.float32)
+    dev = R.default_device()
+    os.environ["RCB_K1_MODE"] = "coop"   # (by default the kernel is only taken in the shape range where it was measured to win)
+    try:
+        s1, st1 = R.collectstates(rc, np.asfortranarray(data[:, :T]), ps, fixed_h0(R, st, rc, [h0]))
+        assert "k1_coop_batched" in dev.last_kernel()
+        s2, st2 = R.collectstates(rc, np.asfortranarray(data[:, T:]), ps, st1)
+    finally:
+        del os.environ["RCB_K1_MODE"]
+    states = np.concatenate([s1, s2], axis=1)
+    layers = oracle_layers(R, rc, ps)
+    for b in sorted({0, 1, B // 2, B - 1}):
+        ref, hs = O.collectstates(layers, data[:, :, b], [h0[:, b]])
+        assert states[:, :, b].shape == ref.shape and state_err(states[:, :, b], ref) <= STATE_RTOL, b
+        assert state_err(st2.reservoir.carry[0][:, b:b + 1], hs[0].reshape(-1, 1)) <= STATE_RTOL
+    os.environ["RCB_K1_MODE"] = "v1"   # one CTA per tile of sequences
+    try:
+        sg, _ = R.collectstates(rc, data, ps, fixed_h0(R, st, rc, [h0]))
+        assert "k1_coop" not in dev.last_kernel()
+    finally:
+        del os.environ["RCB_K1_MODE"]
+    assert state_err(states, sg) <= STATE_RTOL
+
+
 # ---- ReservoirChain with one cell: Extend, Collect points, delay lines (SURVEY 8f-2) --------------------------------
 def _chain_cell(R, N, d_in, rng):
     W = R.rand_sparse(radius=0.9, sparsity=6 / N)(rng, N, N)
