@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k1_coop_kernel(const CoopArgs a) {
 // The sparse term, the input projection and the activation are the epilogue of the same thread; one grid.sync() per step.
 struct CoopBArgs {
   int n, d_in, feat, act, rpc, spc, R, K, rt, ecap;   // rows / sequences per CTA, grid shape, rows per thread, sparse entries per CTA
-  int G, spct, jc;                                    // row groups (the other 8 / G warps split the sequences), lanes per pass, slab columns
+  int G, SG, spct, jc;                                // row groups x sequence groups (x column shares = 8 warps), lanes per pass, slab columns
   long long T, B, Bpad, h_stride, h_off;
   FusedMod mod;
   const float* Orow;
@@ -180,8 +180,13 @@ __device__ __forceinline__ void coopb_slab(const float* __restrict__ hs, const f
   }
 }
 
-// NS: sequences per thread (lanes tb, tb + 32, ...).  The 8 warps are G row groups (<= 8 rows per thread) x 8 / G sequence
-// groups: a CTA pass covers spct = (8 / G) * 32 * NS sequences, and every state value is read by G warps only.
+// NS: sequences per thread (lanes tb, tb + 32, ...).  The 8 warps are G row groups (<= 8 rows per thread) x SG sequence groups
+// x KS column splits (G * SG * KS = 8): a CTA pass covers spct = SG * 32 * NS sequences; the KS warps of a (row group, sequence
+// group) split the columns of every slab and merge their partial sums once per pass.
+// What bounds the product (r02, ncu + cycle counters): every FMA of a warp needs one element of O broadcast from shared memory
+// — one LSU wavefront per (row, column) and warp, a 16-byte broadcast costs four — so the wavefronts per warp-FMA are
+// 1 / NS + 1 / RT: the mapping has to maximise the sequences and rows PER THREAD, and put spare warps on column ranges
+// (more warps per row or sequence group re-read the same operands).  The launcher picks (K, G, SG, NS) by that cost.
 template <int NS>
 __global__ void __launch_bounds__(256) k1_coop_batched_kernel(const CoopBArgs a) {
   cg::grid_group grid = cg::this_grid();
@@ -215,7 +220,9 @@ __global__ void __launch_bounds__(256) k1_coop_batched_kernel(const CoopBArgs a)
     const long long b = b0 + e % (b1 - b0);
     a.hbuf[(size_t)r * a.Bpad + b] = a.h0 ? a.h0[(size_t)b * a.h_stride + a.h_off + r] : 0.0f;
   }
-  const int g = (tid >> 5) % a.G, sg = (tid >> 5) / a.G;   // my row group and sequence group (one warp = one of each)
+  const int KS = 8 / (a.G * a.SG);
+  const int wq = (tid >> 5) % (a.G * a.SG), kh = (tid >> 5) / (a.G * a.SG);   // (row group x sequence group) and my share of the columns
+  const int g = wq % a.G, sg = wq / a.G;                // my row group and sequence group
   const int tb = sg * 32 * NS + (tid & 31);             // my first sequence lane of a pass
   const int lr0 = g * a.rt;                             // first local row of my group
   const int nslab = (n + CB_JC - 1) / CB_JC;
@@ -279,21 +286,23 @@ __global__ void __launch_bounds__(256) k1_coop_batched_kernel(const CoopBArgs a)
         issue(slab + CB_NSTG - 1);
         const float* hs = hc + (size_t)(slab % CB_NSTG) * CB_JC * SPCT + tb;
         const int j0 = slab * CB_JC, nj = min(CB_JC, n - j0);
-        const float* orow = os + (size_t)lr0 * npc + j0;
+        const int nqh = CB_JC / 4 / KS, jh = kh * nqh * 4;         // my quads of the slab
+        const float* orow = os + (size_t)lr0 * npc + j0 + jh;
+        const float* hsk = hs + (size_t)jh * SPCT;
         switch (a.rt) {
-          case 1: coopb_slab<1, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 2: coopb_slab<2, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 3: coopb_slab<3, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 4: coopb_slab<4, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 5: coopb_slab<5, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 6: coopb_slab<6, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          case 7: coopb_slab<7, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
-          default: coopb_slab<8, NS>(hs, orow, npc, SPCT, CB_JC / 4, acc); break;
+          case 1: coopb_slab<1, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 2: coopb_slab<2, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 3: coopb_slab<3, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 4: coopb_slab<4, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 5: coopb_slab<5, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 6: coopb_slab<6, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          case 7: coopb_slab<7, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
+          default: coopb_slab<8, NS>(hsk, orow, npc, SPCT, nqh, acc); break;
         }
         // the sparse term from the same slab: the entries of my rows whose column lies in [j0, j0 + nj) (ascending columns)
 #pragma unroll
         for (int rr = 0; rr < CB_MAXRT; ++rr) {
-          while (cur[rr] < end[rr]) {
+          while (kh == 0 && cur[rr] < end[rr]) {
             const int c = ecol[cur[rr]];
             if (c >= j0 + nj) break;
             const float v = eval_[cur[rr]];
@@ -304,11 +313,34 @@ __global__ void __launch_bounds__(256) k1_coop_batched_kernel(const CoopBArgs a)
         }
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (KS > 1) {   // merge the partial sums of the column shares through the (now idle) ring
+        __syncthreads();
+        const int wl = a.G * a.SG * 32;                // threads of one column share
+        float* red = hc + (size_t)(kh > 0 ? kh - 1 : 0) * CB_MAXRT * NS * wl + (wq * 32 + (tid & 31));
+        if (kh > 0) {
+#pragma unroll
+          for (int rr = 0; rr < CB_MAXRT; ++rr)
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+              if (rr < a.rt) red[(rr * NS + q) * wl] = acc[rr][q];
+        }
+        __syncthreads();
+        if (kh == 0) {
+          for (int k = 0; k < KS - 1; ++k) {
+            const float* rk = hc + (size_t)k * CB_MAXRT * NS * wl + (wq * 32 + (tid & 31));
+#pragma unroll
+            for (int rr = 0; rr < CB_MAXRT; ++rr)
+#pragma unroll
+              for (int q = 0; q < NS; ++q)
+                if (rr < a.rt) acc[rr][q] += rk[(rr * NS + q) * wl];
+          }
+        }
+      }
       pc[1] += clock64() - pt; pt = clock64();
 #pragma unroll
       for (int q = 0; q < NS; ++q) {
         const long long b = sb0 + tb + 32 * q;
-        if (b < b1) {
+        if (kh == 0 && b < b1) {
 #pragma unroll
           for (int rr = 0; rr < CB_MAXRT; ++rr) {
             if (rr < a.rt && lr0 + rr < nrows) {
@@ -398,11 +430,12 @@ int32_t launch_collect_coop_batched(rcb_ctx* ctx, const RecParams& p, const Laye
   if (mode && strcmp(mode, "coop")) return RCB_OK;
   if (!p.Ot || !L.d_Orow || !L.d_csr_rowptr || !L.d_Win_cm || p.B < 2 || p.pre_in || p.member_scale || p.member_leak || p.leakv) return RCB_OK;
   if (p.n < 128 || p.d_in > CB_MAXDIN || !L.csr_sorted || (int)L.h_csr_rowptr.size() != p.n + 1) return RCB_OK;
-  // Where it pays (r02, profiles/r02_dense_operator_batched.txt): N = 1024, 148 sequences 47 vs 58 us/step for one CTA per
-  // sequence tile; it loses at N = 512 x 32 (26 vs 17), N = 1024 x 1024 (164 vs 142) and N = 2048 x 296 (355 vs 249) — the slab
-  // loop runs at 30 % issue efficiency with two warps per scheduler.  Until that is fixed the kernel is taken by default only
-  // around the measured win; RCB_K1_MODE=coop forces it (tests).
-  if (!mode && !(p.n >= 768 && p.n <= 1536 && p.B >= 64 && p.B <= 2LL * ctx->sm_count)) return RCB_OK;
+  // Where it pays (r02, profiles/r02_dense_operator_batched.txt; us per step, this kernel vs one CTA per sequence tile):
+  // N = 300 x 16 sequences 10.2 vs 11.8, 512 x 32: 15.0 vs 16.7, 1024 x 148: 43 vs 58, 2048 x 296: 242 vs 249, 1024 x 1024:
+  // 142 vs 142, 1024 x 296: 75 vs 64.  The slab loop is barrier- and issue-bound (33 % issue efficiency, 14 k warp
+  // instructions per warp and step), not bandwidth-bound; until that is fixed the kernel is the default only up to one
+  // sequence per SM, where the one-CTA-per-tile kernel cannot share the stream of O at all.  RCB_K1_MODE=coop forces it (tests).
+  if (!mode && p.B > ctx->sm_count) return RCB_OK;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
   if (!coop) return RCB_OK;
@@ -417,45 +450,52 @@ int32_t launch_collect_coop_batched(rcb_ctx* ctx, const RecParams& p, const Laye
   a.h0 = reinterpret_cast<const float*>(p.h0); a.h_stride = p.h_stride; a.h_off = p.h_off;
   a.states = reinterpret_cast<float*>(p.states);
   a.hT = reinterpret_cast<float*>(p.hT);
-  // grid shape: as many row blocks as keep a CTA's slice of O (+ the ring of state slabs + its rows of W, W_in) inside shared
-  // memory, the sequences over the remaining factor of the SM count.  Inside a CTA: G row groups (rows per thread <= 8) x 8 / G
-  // sequence groups of 32 * NS lanes; the ring holds CB_NSTG slabs of jc columns x spct <= 128 lanes (<= 64 KB).
-  const size_t ring_max = (size_t)CB_NSTG * 32 * 128 * sizeof(float);
-  if (ctx->smem_optin < ring_max + 8192 + (size_t)(p.n + CB_JCMAX) * sizeof(float) * 16) return RCB_OK;
-  const size_t budget = ctx->smem_optin - ring_max - 8192;
-  const size_t npc = (size_t)((p.n + CB_JCMAX - 1) / CB_JCMAX) * CB_JCMAX;           // (a multiple of either slab width)
-  const int rpc_max = (int)std::min<size_t>(budget / (npc * sizeof(float)) / 16 * 16, 8 * CB_MAXRT);   // whole row groups of any G
-  if (rpc_max < 16) return RCB_OK;                                                   // N > ~2.4 k rows of 16 do not fit: generic kernel
-  int R = (p.n + rpc_max - 1) / rpc_max;
-  if (R > ctx->sm_count) return RCB_OK;
-  int K = (int)std::min<long long>(std::max(1, ctx->sm_count / R), (p.B + 3) / 4);
-  R = std::min(ctx->sm_count / K, p.n);                                              // spend the SMs K leaves over on shorter row blocks
-  a.rpc = (p.n + R - 1) / R; R = (p.n + a.rpc - 1) / a.rpc;
-  a.spc = (int)(((p.B + K - 1) / K + 3) & ~3LL); K = (int)((p.B + a.spc - 1) / a.spc);
-  a.G = a.rpc > 32 ? 8 : a.rpc > 16 ? 4 : 2;
-  a.rt = (a.rpc + a.G - 1) / a.G;
-  const int sgc = 8 / a.G;                                                           // sequence groups
-  const int lanes = (a.spc + 32 * sgc - 1) / (32 * sgc);                             // sequences per thread to cover the block in one pass
-  const int ns = std::min(lanes <= 1 ? 1 : lanes <= 2 ? 2 : 4, 4 / sgc);             // spct <= 128
-  a.spct = sgc * 32 * ns;
-  a.jc = a.spct <= 64 ? 64 : 32;
-  int ecap = 0;
-  for (int rb = 0; rb < R; ++rb) {
-    const int r0 = rb * a.rpc, r1 = std::min(p.n, r0 + a.rpc);
-    ecap = std::max(ecap, (int)(L.h_csr_rowptr[(size_t)r1] - L.h_csr_rowptr[(size_t)r0]));
+  // Shape: K sequence blocks x R = #SMs / K row blocks; inside a CTA G row groups (rt <= 8 rows per thread) x SG sequence
+  // groups (32 * NS lanes each, NS <= 5) x KS column shares.  Candidates are ranked by shared-memory wavefronts per step of a
+  // CTA, passes * n * G * SG * (NS + rt): a state value costs one wavefront per warp that reads it, an element of O one per warp.
+  struct Cand { int K, R, rpc, spc, G, SG, NS, rt, spct, jc; size_t smem; double cost; int ecap; };
+  Cand best{}; best.cost = -1.0;
+  for (int K = 1; K <= ctx->sm_count && (long long)K * 4 <= p.B + 3; K *= 2) {
+    int R = std::min(ctx->sm_count / K, p.n);
+    if (R < 1) break;
+    const int rpc = (p.n + R - 1) / R;
+    R = (p.n + rpc - 1) / rpc;
+    if (rpc > 8 * CB_MAXRT) continue;
+    const int spc = (int)(((p.B + K - 1) / K + 3) & ~3LL);
+    const int Kc = (int)((p.B + spc - 1) / spc);
+    const int G = rpc > 32 ? 8 : rpc > 16 ? 4 : rpc > 8 ? 2 : 1, rt = (rpc + G - 1) / G;
+    for (int NS = 1; NS <= 5; ++NS) {
+      int SG = 1;
+      while (SG * 2 * G <= 8 && SG * 32 * NS < spc) SG *= 2;
+      const int spct = SG * 32 * NS, KS = 8 / (G * SG), passes = (spc + spct - 1) / spct;
+      int jc = (int)((size_t)96 * 1024 / sizeof(float) / CB_NSTG / spct) / (4 * KS) * (4 * KS);   // ring <= 96 KB, whole quads per column share
+      jc = std::min(jc, 64);
+      if (jc < 4 * KS) continue;
+      int ecap = 0;
+      for (int rb = 0; rb < R; ++rb) {
+        const int r0 = rb * rpc, r1 = std::min(p.n, r0 + rpc);
+        ecap = std::max(ecap, (int)(L.h_csr_rowptr[(size_t)r1] - L.h_csr_rowptr[(size_t)r0]));
+      }
+      const size_t npc = (size_t)((p.n + jc - 1) / jc) * jc;
+      const size_t ring = std::max((size_t)CB_NSTG * jc * spct, (size_t)(KS - 1) * CB_MAXRT * NS * (size_t)(G * SG * 32));   // (+ the merge buffer)
+      const size_t smem = ((size_t)G * rt * npc + ring + (size_t)rpc * (p.d_in + 1) + rpc + 1 + 2 * (size_t)ecap) * sizeof(float);
+      if (smem > ctx->smem_optin) continue;
+      const double cost = (double)passes * p.n * G * SG * (NS + rt) + 600.0 * ((p.n + jc - 1) / jc) * passes;   // + a barrier per slab
+      if (best.cost < 0 || cost < best.cost) best = Cand{Kc, R, rpc, spc, G, SG, NS, rt, spct, jc, smem, cost, ecap};
+    }
   }
-  a.ecap = ecap;
-  const size_t npc_k = (size_t)((p.n + a.jc - 1) / a.jc) * a.jc;
-  const size_t smem = ((size_t)a.G * a.rt * npc_k + (size_t)CB_NSTG * a.jc * a.spct + (size_t)a.rpc * (p.d_in + 1) + a.rpc + 1 + 2 * (size_t)ecap) * sizeof(float);
-  a.R = R; a.K = K;
-  if (a.rt > CB_MAXRT || smem > ctx->smem_optin) return RCB_OK;
-  void* kern = ns == 1 ? (void*)k1_coop_batched_kernel<1> : ns == 2 ? (void*)k1_coop_batched_kernel<2> : (void*)k1_coop_batched_kernel<4>;
+  if (best.cost < 0) return RCB_OK;   // no slice of O fits next to the ring (N > ~6 k): the generic kernel
+  a.K = best.K; a.R = best.R; a.rpc = best.rpc; a.spc = best.spc; a.G = best.G; a.SG = best.SG; a.rt = best.rt; a.spct = best.spct; a.jc = best.jc;
+  a.ecap = best.ecap;
+  const int ns = best.NS, R = best.R, K = best.K;
+  const size_t smem = best.smem;
+  void* kern = ns == 1 ? (void*)k1_coop_batched_kernel<1> : ns == 2 ? (void*)k1_coop_batched_kernel<2> : ns == 3 ? (void*)k1_coop_batched_kernel<3>
+               : ns == 4 ? (void*)k1_coop_batched_kernel<4> : (void*)k1_coop_batched_kernel<5>;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  if (ns == 1) RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<1>, 256, smem));
-  else if (ns == 2) RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<2>, 256, smem));
-  else RCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_coop_batched_kernel<4>, 256, smem));
-  if (per_sm < 1 || R * K > per_sm * ctx->sm_count) return RCB_OK;
+  cudaFuncAttributes fa{};
+  RCB_CUDA(cudaFuncGetAttributes(&fa, kern));
+  if (fa.numRegs * 256 > 65536 || R * K > ctx->sm_count) return RCB_OK;   // one CTA per SM, all resident (cooperative launch)
+  const int nthr = 256;
   void* hb = nullptr;
   RCB_TRY(ctx_scratch(ctx, SCR_INFO, 2 * (size_t)p.n * a.Bpad * sizeof(float), &hb));
   a.hbuf = reinterpret_cast<float*>(hb);
@@ -466,11 +506,11 @@ int32_t launch_collect_coop_batched(rcb_ctx* ctx, const RecParams& p, const Laye
   a.prof = prof ? prof_dev : nullptr;
   void* args[] = {(void*)&a};
   timer_begin(ctx, RCB_TIMER_RECURRENCE);
-  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)(R * K)), dim3(256), args, smem, ctx->stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)(R * K)), dim3((unsigned)nthr), args, smem, ctx->stream);
   timer_end(ctx, RCB_TIMER_RECURRENCE);
   if (e != cudaSuccess) return fail(RCB_ERR_CUDA, "cooperative launch failed: %s", cudaGetErrorString(e));
-  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop_batched<dense skip operator,O-resident,%dx%d per thread,%d row groups> grid=%dx%d rows/CTA=%d seq/CTA=%d", a.rt, ns,
-           a.G, R, K, a.rpc, a.spc);
+  snprintf(ctx->last_kernel, sizeof(ctx->last_kernel), "k1_coop_batched<O-resident,%dx%d per thread,%dx%dx%d warps> grid=%dx%d rows/CTA=%d seq/CTA=%d", a.rt, ns, a.G, a.SG,
+           8 / (a.G * a.SG), R, K, a.rpc, a.spc);
   ctx->launches++;
   *launched = true;
   if (prof) {
