@@ -24,17 +24,21 @@
 // Mapping: Z is F x S column-major, so both operands are MN-major.  The pre-pass writes the planes pre-tiled in exactly
 // the shared-memory image the MMA wants — [32-sample block][128-feature block][plane][32 rows x 128 B], 16-byte chunks
 // XOR-swizzled with (row & 7) (UMMA SWIZZLE_128B, MN-major, 8-bit) — so a pipeline stage is filled by two contiguous
-// cp.async.bulk copies.  One CTA = one 128 x 256 tile of the lower triangle; CTA pairs (a 2 x 1 cluster, 256 x 256
-// super-tile) fetch half of the shared B tile each and multicast it.  TMEM holds acc4 | acc5 (phase A, 5 MMAs per
+// copies.  One CTA = one 128 x 256 tile of the lower triangle; a CTA pair (2 x 1 cluster) owns a 256 x 256 super-tile and
+// issues ONE M = 256 MMA per product (cta_group::2, leader CTA): each CTA holds its A block and its half of the B tile,
+// loaded by tensor-map copies that complete on the leader's barrier.  (RCB_GRAM_PAIR=0: one M = 128 MMA per CTA, each CTA
+// fetches half of B with a plain bulk copy and multicasts it.)  TMEM holds acc4 | acc5 (phase A, 5 MMAs per
 // K-step, all three planes), acc2 | acc3 (phase B, 3 MMAs per K-step on the first two planes: two thirds of the bytes of
 // a stage — with all three planes this phase was bound by the L2 -> SM fetch, 36 KB per 411 tensor cycles) or acc6
 // (phase C, 1 MMA per K-step; only the third digit plane is fetched: a third of the bytes of a stage).  warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
 // elected thread), warps 2-9 = epilogue.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -48,9 +52,9 @@ namespace {
 constexpr int TM = 128, TN = 256, KB = 32, PLANES = 3;
 constexpr int BOX = 128 * KB;                          // 4 KB: one plane of 128 features x 32 samples
 constexpr int BLK = PLANES * BOX;                      // 12 KB: the three planes of a feature block
-// PAIR = false: every CTA issues its own M = 128 MMAs (cta_group::1) and holds A + both B blocks (36 KB per stage).
-// PAIR = true: the CTA pair issues ONE M = 256 MMA (cta_group::2, leader CTA only); a CTA holds its A block and ITS half of
-// B (24 KB per stage), the tensor cores of the pair exchange the B halves — a third less shared-memory traffic per MMA.
+// PAIR = true (default): the CTA pair issues ONE M = 256 MMA (cta_group::2, leader CTA only); a CTA holds its A block and ITS
+// half of B (24 KB per stage, 8 stages), the tensor cores of the pair exchange the B halves — a third less shared-memory
+// traffic per MMA.  PAIR = false: every CTA issues its own M = 128 MMAs (cta_group::1) and holds A + both B blocks (36 KB).
 template <bool PAIR> struct K2Cfg {
   static constexpr int STAGE_BYTES = PAIR ? 2 * BLK : 3 * BLK;
   static constexpr int STAGES = PAIR ? 8 : 5;
@@ -79,8 +83,6 @@ struct GramParams8 {
   long long g_stride;         // doubles between the members' G
   int* err;                   // set to 1 when a barrier wait timed out (the kernel then traps)
   unsigned* sync;             // round counter: the producers of all CTAs start a round of work items together (L2 locality)
-  int relay;                  // pair: lanes of the peer's warp 1 that take turns relaying "stage landed" to the leader
-  int relaxed;                // testing hook: relay with a relaxed arrive
   long long* prof;            // RCB_GRAM_PROF: per CTA [mma waits full, mma waits tmem, producer waits empty, epi waits, total]
 };
 
@@ -129,11 +131,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t bar, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(rank));
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
-}
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err) {
   uint32_t done = 0;
   const long long t0 = clock64();
@@ -148,6 +145,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
       __trap();
     }
   }
+}
+// pair form: a tile of the planes buffer (2-D tensor map over 256-byte rows) into MY shared memory, completing its bytes on
+// the LEADER's barrier — only tensor copies can signal a barrier of the peer CTA (.cta_group::2)
+__device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* tm, int32_t row, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(0), "r"(row)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -196,19 +200,21 @@ constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1
       : "memory")
 
 template <bool PAIR>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) gram_i8_kernel(const GramParams8 p) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1)
+    gram_i8_kernel(const GramParams8 p, const __grid_constant__ CUtensorMap tm3, const __grid_constant__ CUtensorMap tm2,
+                   const __grid_constant__ CUtensorMap tm1) {   // tensor maps with boxes of three / two / one digit plane (pair form only)
   constexpr int STAGES = K2Cfg<PAIR>::STAGES, STAGE_BYTES = K2Cfg<PAIR>::STAGE_BYTES;
   constexpr int NBLK = PAIR ? 2 : 3;   // 128-feature blocks per stage: A + (my half of B | both B blocks)
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
-  // barriers: full[STAGES] | empty[STAGES] | pfull[STAGES] (pair: the peer's stage has landed) | tfull | tempty | tmem base
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, pfull0 = bars + 16 * STAGES, tfull = bars + 24 * STAGES, tempty = tfull + 8,
+  // barriers: full[STAGES] | empty[STAGES] | tfull | tempty | tmem base
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tempty = tfull + 8,
                  tmem_slot = tempty + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PAIR ? 1 : CR); mbar_init(pfull0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, PAIR ? 1 : CR); }
     mbar_init(tfull, 1);
     mbar_init(tempty, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // pair: the leader waits for the epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -236,6 +242,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
   const long long per_mem = (long long)p.ntiles * p.splits;
   const long long nitems = per_mem * p.nmem;
   const int nphase = __ldg(p.nphase);
+  uint32_t lead_full0 = full0;   // the leader's full barriers (pair form: the peer's tiles complete there as well)
+  if (PAIR) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lead_full0) : "r"(full0), "r"(0u));
 
   if (warp == 0) {
     // ===== producer: two contiguous bulk copies per stage =====
@@ -283,20 +291,34 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
               // A [p1 p2 p3] | B block 0 [p1 p2 p3] | B block 1 [p1 p2 p3]      (pair: A | my B block)
               // phase B multiplies the first two digit planes only: two thirds of the bytes, same offsets
               const uint32_t nb = phase == 0 ? BLK : 2 * BOX;
-              mbar_expect_tx(fbar, NBLK * nb);             // bytes landing in MY shared memory
-              const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
-              bulk_load_mc(sa, blk + (size_t)fa * BLK, nb, fbar, mask_self);
-              if (PAIR) bulk_load_mc(sa + BLK, blk + (size_t)fb * BLK, nb, fbar, mask_self);
-              else bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, nb, fbar, mask_all);
+              if (PAIR) {
+                // both CTAs' tiles complete on the LEADER's barrier, which the leader arms with the bytes of the pair
+                if (ri == 0) mbar_expect_tx(fbar, 2 * NBLK * nb);
+                const long long row0 = (long long)(mem * p.q8_stride / 256) + ((long long)(s_beg / KB + st) * p.nfb) * (BLK / 256);
+                const CUtensorMap* tm = phase == 0 ? &tm3 : &tm2;
+                tma_load_pair(sa, tm, (int32_t)(row0 + fa * (BLK / 256)), lead_full0 + 8 * slot);
+                tma_load_pair(sa + BLK, tm, (int32_t)(row0 + fb * (BLK / 256)), lead_full0 + 8 * slot);
+              } else {
+                mbar_expect_tx(fbar, NBLK * nb);           // bytes landing in MY shared memory
+                const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st) * p.nfb) * BLK;
+                bulk_load_mc(sa, blk + (size_t)fa * BLK, nb, fbar, mask_self);
+                bulk_load_mc(sa + BLK + (uint32_t)ri * BLK, blk + (size_t)fb * BLK, nb, fbar, mask_all);
+              }
             } else {
               const int nk = nst - st < CK ? nst - st : CK;
-              mbar_expect_tx(fbar, (uint32_t)nk * NBLK * BOX);
+              if (PAIR) { if (ri == 0) mbar_expect_tx(fbar, 2u * (uint32_t)nk * NBLK * BOX); }
+              else mbar_expect_tx(fbar, (uint32_t)nk * NBLK * BOX);
               for (int kk = 0; kk < nk; ++kk) {
-                const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st + kk) * p.nfb) * BLK + 2 * BOX;
                 const uint32_t sk = sa + (uint32_t)kk * NBLK * BOX;
-                bulk_load_mc(sk, blk + (size_t)fa * BLK, BOX, fbar, mask_self);
-                if (PAIR) bulk_load_mc(sk + BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_self);
-                else bulk_load_mc(sk + BOX + (uint32_t)ri * BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_all);
+                if (PAIR) {
+                  const long long row0 = (long long)(mem * p.q8_stride / 256) + ((long long)(s_beg / KB + st + kk) * p.nfb) * (BLK / 256) + 2 * BOX / 256;
+                  tma_load_pair(sk, &tm1, (int32_t)(row0 + fa * (BLK / 256)), lead_full0 + 8 * slot);
+                  tma_load_pair(sk + BOX, &tm1, (int32_t)(row0 + fb * (BLK / 256)), lead_full0 + 8 * slot);
+                } else {
+                  const unsigned char* blk = q8m + ((size_t)(s_beg / KB + st + kk) * p.nfb) * BLK + 2 * BOX;
+                  bulk_load_mc(sk, blk + (size_t)fa * BLK, BOX, fbar, mask_self);
+                  bulk_load_mc(sk + BOX + (uint32_t)ri * BOX, blk + (size_t)fb * BLK, BOX, fbar, mask_all);
+                }
               }
             }
           }
@@ -306,29 +328,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
       if (p.prof) { p.prof[blockIdx.x * 5 + 2] = wait_acc; p.prof[blockIdx.x * 5 + 4] = clock64() - tstart; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (pair: the leader CTA issues for both; the peer's warp 1 relays "my stage has landed") =====
+    // ===== MMA issuer (pair: the leader CTA issues for both) =====
     if (PAIR && ri != 0) {
-      if (lane < p.relay) {   // several lanes take turns: the round trip of one remote arrive must not pace the stages
-        long long it = 0;
-        for (long long item = cid; item < nitems; item += ncl) {
-          const long long split = (item % per_mem) / p.ntiles;
-          const long long s_beg = split * p.per_split;
-          const long long s_end = s_beg + p.per_split < p.S ? s_beg + p.per_split : p.S;
-          const int nst = (int)((s_end - s_beg + KB - 1) / KB);
-          for (int phase = 0; phase < nphase; ++phase) {
-            const int kper = phase == 2 ? CK : 1;
-            for (int st = 0; st < nst; st += kper, ++it) {
-              if ((int)(it % p.relay) != lane) continue;
-              const int slot = (int)(it % STAGES);
-              mbar_wait(full0 + 8 * slot, (uint32_t)((it / STAGES) & 1), p.err);
-              if (p.relaxed) mbar_arrive_remote_relaxed(pfull0 + 8 * slot, 0u);
-              else mbar_arrive_remote(pfull0 + 8 * slot, 0u);
-            }
-          }
-        }
-      }
+      // (the peer's tiles complete on the leader's barriers: nothing to do here)
     } else if (lane == 0) {
-      long long it = 0, ci = 0, wfull = 0, wtm = 0, wpeer = 0;
+      long long it = 0, ci = 0, wfull = 0, wtm = 0;
       for (long long item = cid; item < nitems; item += ncl) {
         const long long split = (item % per_mem) / p.ntiles;
         const long long s_beg = split * p.per_split;
@@ -345,13 +349,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
             const int slot = (int)(it % STAGES);
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             const long long w1 = clock64();
-            mbar_wait(full0 + 8 * slot, ph, p.err);
+            if (PAIR) mbar_wait_cluster(full0 + 8 * slot, ph, p.err);   // (bytes written by the peer's copies as well)
+            else mbar_wait(full0 + 8 * slot, ph, p.err);
             wfull += clock64() - w1;
-            if (PAIR) {
-              const long long w2 = clock64();
-              mbar_wait_cluster(pfull0 + 8 * slot, ph, p.err);
-              wpeer += clock64() - w2;
-            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = base + slot * STAGE_BYTES;
             const uint32_t acc = st > 0 ? 1u : 0u;
@@ -385,7 +385,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NTHREADS, 1) g
           else umma_commit(tfull);
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 5 + 0] = wfull; p.prof[blockIdx.x * 5 + 1] = wtm; if (PAIR) p.prof[(blockIdx.x + 1) * 5 + 0] = wpeer; }
+      if (p.prof) { p.prof[blockIdx.x * 5 + 0] = wfull; p.prof[blockIdx.x * 5 + 1] = wtm; }
     }
   } else {
     // ===== epilogue: INT32 accumulators -> FP64 G =====
@@ -705,12 +705,15 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   if (Ssub < SLAB) Ssub = SLAB;
   if (Ssub > Stot) Ssub = Stot;
   const long long Ssub_pad = (Ssub + SLAB - 1) / SLAB * SLAB;
-  // RCB_GRAM_PAIR=1: one M = 256 MMA per CTA pair (cta_group::2) instead of one M = 128 MMA per CTA with a multicast B tile.
-  // Measured r02 (F = 8192, S = 262144, eight products): 66.0 ms vs 53.6 ms — the leader has to learn through a relayed
-  // barrier that the peer's stage has landed, and the multicast form already receives only what it needs; kept as a tested option.
-  const bool pair = getenv("RCB_GRAM_PAIR") && atoi(getenv("RCB_GRAM_PAIR")) == 1;
+  // One M = 256 MMA per CTA pair (cta_group::2, each CTA holds its A block and ITS half of B: a third less shared-memory traffic
+  // per MMA) unless RCB_GRAM_PAIR=0 asks for one M = 128 MMA per CTA with a multicast B tile.  Measured r02 (F = 8192,
+  // S = 262144, kernel alone): 8 products 50.5 vs 53.9 ms, 9 products 60.5 vs 65.0 ms.  The two-MMA form is bound by shared-memory
+  // bandwidth (36 KB written + 60 KB read per 685 tensor cycles in phase A); the pair form needs its tiles to complete on the
+  // LEADER's barrier, which only tensor-map copies can do (.cta_group::2) — a first version with plain bulk copies and a
+  // relayed barrier lost 20 %.
+  const bool pair = !(getenv("RCB_GRAM_PAIR") && atoi(getenv("RCB_GRAM_PAIR")) == 0);
   const int SMEM_BYTES = pair ? K2Cfg<true>::SMEM_BYTES : K2Cfg<false>::SMEM_BYTES;
-  void (*kern)(const GramParams8) = pair ? gram_i8_kernel<true> : gram_i8_kernel<false>;
+  void (*kern)(const GramParams8, const CUtensorMap, const CUtensorMap, const CUtensorMap) = pair ? gram_i8_kernel<true> : gram_i8_kernel<false>;
   RCB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   void *q8 = nullptr, *aux = nullptr;
   const long long q8_stride = ldp * Ssub_pad * PLANES;
@@ -732,6 +735,26 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
   static long long* prof_dev = nullptr;
   const bool prof = getenv("RCB_GRAM_PROF") != nullptr;
   if (prof && !prof_dev) cudaMalloc(&prof_dev, 148 * 5 * sizeof(long long));
+  // pair form: the planes buffer as a 2-D tensor of 256-byte rows; boxes of 48 / 32 / 16 rows = three / two / one digit plane
+  CUtensorMap tmaps[3];
+  memset(tmaps, 0, sizeof(tmaps));
+  if (pair) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RCB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(RCB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[2] = {256, (cuuint64_t)((size_t)q8_stride * nmem / 256)};
+    const cuuint64_t gstr[1] = {256};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 3; ++i) {
+      const cuuint32_t box[2] = {256, (cuuint32_t)((3 - i) * BOX / 256)};
+      const CUresult r = ((EncodeFn)fn)(&tmaps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, q8, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(RCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+  }
   for (long long s0 = 0; s0 < Stot; s0 += Ssub) {
     const long long Sc = Stot - s0 < Ssub ? Stot - s0 : Ssub;
     RCB_CUDA(cudaMemsetAsync(amax, 0, (size_t)ldp * nmem * sizeof(int), ctx->stream));
@@ -774,8 +797,6 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     p.nmem = (int)nmem; p.q8_stride = q8_stride; p.g_stride = g_stride;
     p.sync = (getenv("RCB_GRAM_SYNC") && atoi(getenv("RCB_GRAM_SYNC")) == 0) ? nullptr : reinterpret_cast<unsigned*>(d_err + 2);   // RCB_GRAM_SYNC=0: A/B hook
     if (p.sync) RCB_CUDA(cudaMemsetAsync(p.sync, 0, sizeof(unsigned), ctx->stream));
-    p.relay = getenv("RCB_GRAM_RELAY") ? std::max(1, std::min(K2Cfg<true>::STAGES, atoi(getenv("RCB_GRAM_RELAY")))) : 4;
-    p.relaxed = getenv("RCB_GRAM_RELAXED") ? 1 : 0;
     {
       double lam = ctx->gram_lambda_hint;
       if (const char* e = getenv("RCB_GRAM_PHASES")) lam = atoi(e) == 2 ? 1e300 : -1.0;  // testing hook: force 2 / 3 phases
@@ -803,7 +824,7 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
     const int grid = (int)(nitems < ncl_max ? nitems : ncl_max) * CLUSTER;
     const bool tsplit = getenv("RCB_GRAM_TIMING") != nullptr;  // diagnostics: time the MMA kernel alone in the SOLVE timer slot
     if (tsplit) timer_begin(ctx, RCB_TIMER_SOLVE);
-    kern<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p);
+    kern<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(p, tmaps[0], tmaps[1], tmaps[2]);
     if (tsplit) timer_end(ctx, RCB_TIMER_SOLVE);
     ctx->launches++;
     RCB_CUDA(cudaGetLastError());
@@ -814,11 +835,6 @@ int32_t launch_gram_tensor_batched(rcb_ctx* ctx, const float* Z, int64_t F, int6
       double sum[5] = {0, 0, 0, 0, 0};
       long long mx = 0;
       for (int b = 0; b < grid; ++b) { for (int q = 0; q < 5; ++q) sum[q] += (double)hp[b * 5 + q]; if (hp[b * 5 + 4] > mx) mx = hp[b * 5 + 4]; }
-      if (pair) {
-        double own = 0, peer = 0;
-        for (int b = 0; b < grid; b += 2) { own += (double)hp[b * 5]; peer += (double)hp[(b + 1) * 5]; }
-        fprintf(stderr, "[gram prof] pair: leader waits own stage %.3g, peer's stage %.3g cycles per pair\n", own / (grid / 2), peer / (grid / 2));
-      }
       fprintf(stderr, "[gram prof] grid %d items %lld x %lld samples: avg cycles/CTA: mma waits full %.3g, mma waits tmem %.3g, producer waits "
               "empty %.3g, epilogue waits %.3g, producer total %.3g (max %lld)\n", grid, nitems, p.per_split, sum[0] / grid, sum[1] / grid,
               sum[2] / grid, sum[3] / grid, sum[4] / grid, mx);

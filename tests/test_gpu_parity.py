@@ -441,11 +441,12 @@ def test_gram_tensor_matches_exact(R, F, S, D):
     assert np.allclose(g_t[:, F:], Z64 @ Y.astype(np.float64).T, rtol=1e-12, atol=1e-9)  # cross term: exact FP64 products
 
 
-@pytest.mark.parametrize("env", [{"RCB_GRAM_PAIR": "1"}, {"RCB_GRAM_PAIR": "1", "RCB_GRAM_PHASES": "2"}, {"RCB_GRAM_PHASES": "2"},
-                                 {"RCB_GRAM_PAIR": "1", "RCB_GRAM_RELAY": "1"}])
+@pytest.mark.parametrize("env", [{"RCB_GRAM_PAIR": "1"}, {"RCB_GRAM_PAIR": "1", "RCB_GRAM_PHASES": "2"}, {"RCB_GRAM_PAIR": "0", "RCB_GRAM_PHASES": "2"},
+                                 {"RCB_GRAM_PAIR": "0"}, {"RCB_GRAM_PAIR": "1", "RCB_GRAM_SYNC": "0"}])
 def test_gram_tensor_pair_variant_and_phase_groups(R, monkeypatch, env):
-    """The cta_group::2 form of the kernel (one M = 256 MMA per CTA pair, the peer's stages announced through a relayed
-    barrier) and the eight-product mode (phases A and B only) against the exact Gram: same digit products, same result."""
+    """Both forms of the kernel — one M = 256 MMA per CTA pair (cta_group::2, tensor-map copies completing on the leader's
+    barrier; the default) and one M = 128 MMA per CTA with a multicast B tile — in the nine- and the eight-product mode,
+    against the exact Gram: same digit products, same result."""
     from rcb200 import _lib as L
 
     for k, v in env.items():
