@@ -1466,11 +1466,24 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   for (int64_t m = 0; m < mg; ++m)
     for (int32_t l = 0; l < n_lambda; ++l) lam_rep[(size_t)(m * n_lambda + l)] = lambdas[l];
   std::vector<int> info((size_t)(mg * n_lambda));
+  // RCB_MEMBERS_PROF: host wall clock (with a stream synchronisation) at the stations of the sweep
+  const bool mprof = getenv("RCB_MEMBERS_PROF") != nullptr;
+  auto mark = [&](const char* what) {
+    if (!mprof) return;
+    static double t_prev = 0.0;
+    cudaStreamSynchronize(ctx->stream);
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (what) fprintf(stderr, "[members prof] %-22s %8.2f ms\n", what, (now - t_prev) * 1e3);
+    t_prev = now;
+  };
+  mark(nullptr);
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
     const int64_t nb = std::min<int64_t>(Bc, B - b0);
     const void* uc = (const char*)u_dev + (size_t)b0 * T * d_in * esz;
     void* hc = (char*)h_dev + (size_t)b0 * sumN * esz;
     RCB_TRY(collect_device(esn, uc, T, nb, hc, st_dev, hc, b0));
+    mark("recurrence");
     for (int64_t g0 = 0; g0 < nb; g0 += mg) {
       const int64_t ng = std::min<int64_t>(mg, nb - g0);
       std::fill(info.begin(), info.end(), 0);
@@ -1518,10 +1531,13 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
           timer_end(ctx, RCB_TIMER_GRAM);
           RCB_TRY(sg);
         }
+        mark("gram");
         if (n_lambda > 1) RCB_TRY(launch_replicate_blocks(ctx, (double*)work, (int64_t)slot_elems, n_lambda, ng));
+        mark("replicate");
         const int32_t st = launch_ridge_solve_batched(ctx, (double*)work, F, d_out, 0.0, lam_rep.data(), ng * n_lambda, (double*)w_dev, info.data(),
                                                       ldw, (int64_t)slot_elems);
         if (st != RCB_ERR_NUMERIC) RCB_TRY(st);
+        mark("solve");
         if (st == RCB_ERR_NUMERIC && gram_mode != RCB_GRAM_AUTO) {
           for (int64_t z = 0; z < ng * n_lambda; ++z)
             if (info[(size_t)z] != 0)
@@ -1556,6 +1572,7 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
         }
       }
       RCB_TRY(from_device(ctx, W_out + (size_t)(b0 + g0) * n_lambda * w_elems, w_dev, w_elems * sizeof(double) * (size_t)(ng * n_lambda)));
+      mark("weights to host");
     }
   }
   if (hT_out) RCB_TRY(from_device(ctx, hT_out, h_dev, (size_t)sumN * B * esz));
