@@ -1116,12 +1116,18 @@ def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambda
         raise DimensionMismatch(f"w_scale has {B} members, leak has {leak.shape[0]}")
     d3, _ = _as3d(train_data)
     y3, _ = _as3d(target_data)
-    if d3.shape[2] == 1 and B > 1:
-        d3 = np.asfortranarray(np.repeat(d3, B, axis=2))
-    if y3.shape[2] == 1 and B > 1:
-        y3 = np.asfortranarray(np.repeat(y3, B, axis=2))
     if y3.dtype not in (np.float32, np.float64):
         y3 = np.asfortranarray(y3.astype(np.float64))
+
+    def tile_members(a3):   # shared series: one (d, T) block per member, written once in the library's layout
+        out = np.empty((a3.shape[0], a3.shape[1], B), dtype=a3.dtype, order="F")
+        out[...] = a3
+        return out
+
+    if d3.shape[2] == 1 and B > 1:
+        d3 = tile_members(d3)
+    if y3.shape[2] == 1 and B > 1:
+        y3 = tile_members(y3)
     _, T, Bd = d3.shape
     if Bd != B or y3.shape[2] != B:
         raise DimensionMismatch(f"{B} members but data has {Bd} and targets {y3.shape[2]} sequences")
