@@ -1485,12 +1485,16 @@ int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int3
   struct Joiner { std::thread t; ~Joiner() { if (t.joinable()) t.join(); } } prefault;
   {
     const size_t w_total = w_elems * sizeof(double) * (size_t)B * (size_t)n_lambda;
-    if (w_total >= ((size_t)8 << 20) && !is_device_ptr(W_out))
-      prefault.t = std::thread([W_out, w_total] {
-        volatile char* p = reinterpret_cast<volatile char*>(W_out);
-        for (size_t o = 0; o < w_total; o += 4096) p[o] = 0;
-        p[w_total - 1] = 0;
-      });
+    if (w_total >= ((size_t)8 << 20) && !is_device_ptr(W_out)) {
+      try {
+        prefault.t = std::thread([W_out, w_total] {
+          volatile char* p = reinterpret_cast<volatile char*>(W_out);
+          for (size_t o = 0; o < w_total; o += 4096) p[o] = 0;
+          p[w_total - 1] = 0;
+        });
+      } catch (...) {   // no thread to spare: the copy takes the page faults itself
+      }
+    }
   }
   mark("staging + scratch");
   for (int64_t b0 = 0; b0 < B; b0 += Bc) {
