@@ -121,6 +121,10 @@ RCB_API int32_t rcb_ctx_last_kernel(rcb_ctx* ctx, char* buf, int32_t len);
 /* Diagnostics of the most recent RCB_GRAM_AUTO ridge fit on this context: how many iterative-refinement passes it ran on the
  * exact normal equations and |delta W| / |W| of the last correction (0 / 0.0: none — QR path, explicit gram_mode, d_out > 8). */
 RCB_API int32_t rcb_ctx_last_refine(rcb_ctx* ctx, int32_t* steps, double* rel);
+/* Failure detection (the reference has none on this path: a diverged reservoir silently produces NaN weights): *flag = 1 if the
+ * carry of any recurrence of the most recent data-path call on this context held a NaN or an Inf after its last step — identity /
+ * relu activation with a spectral radius above 1, non-finite inputs.  Synchronises the context's stream. */
+RCB_API int32_t rcb_ctx_last_nonfinite(rcb_ctx* ctx, int32_t* flag);
 #define RCB_TIMER_RECURRENCE 0 /* K1 / K4 */
 #define RCB_TIMER_GRAM 1       /* K2 */
 #define RCB_TIMER_SOLVE 2      /* K3 (Cholesky / QR) */

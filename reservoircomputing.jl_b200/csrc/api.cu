@@ -131,6 +131,33 @@ void timer_end(rcb_ctx* ctx, int which) {
 }
 void timers_reset(rcb_ctx* ctx) {
   for (int i = 0; i < RCB_TIMER_COUNT; ++i) pools(ctx)[i].used = 0;
+  if (ctx->d_nonfinite) cudaMemsetAsync(ctx->d_nonfinite, 0, sizeof(int), ctx->stream);   // per data-path call
+}
+
+// SURVEY §5 (failure detection): a diverged reservoir (identity / relu activation with a radius above 1, NaN inputs) is visible
+// in the carry — a non-finite state stays non-finite through (1 - a) h + a phi(...) — so one pass over the sumN x B carry after
+// every recurrence is the whole check (33 MB at the C3 shape: microseconds).
+template <typename T>
+__global__ void nonfinite_kernel(const T* __restrict__ x, long long n, int* flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T v = x[i];
+    bad = bad || !(fabs((double)v) <= 1.7976931348623157e308);   // false for NaN and +-Inf
+  }
+  if (bad) *flag = 1;
+}
+static int32_t note_nonfinite(rcb_ctx* ctx, const void* carry, int64_t n, int32_t dtype) {
+  if (!carry || n <= 0) return RCB_OK;
+  if (!ctx->d_nonfinite) {
+    RCB_CUDA(cudaMalloc(&ctx->d_nonfinite, sizeof(int)));
+    RCB_CUDA(cudaMemsetAsync(ctx->d_nonfinite, 0, sizeof(int), ctx->stream));
+  }
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 4LL * ctx->sm_count);
+  if (dtype == RCB_F64) nonfinite_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)carry, n, ctx->d_nonfinite);
+  else nonfinite_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)carry, n, ctx->d_nonfinite);
+  ctx->launches++;
+  RCB_CUDA(cudaGetLastError());
+  return RCB_OK;
 }
 
 // resolve a host-or-device input into a device pointer (copying host data into a scratch slot)
@@ -478,6 +505,7 @@ static int32_t collect_device_pipelined(rcb_esn* esn, const void* u_dev, int64_t
   for (auto& e : done) cudaEventDestroy(e);
   cudaEventDestroy(fork);
   if (st == RCB_OK) snprintf(ctx->last_kernel + strlen(ctx->last_kernel), sizeof(ctx->last_kernel) - strlen(ctx->last_kernel), " [layer pipeline x%lld]", (long long)nch);
+  if (st == RCB_OK) st = note_nonfinite(ctx, carry, esn->sumN, RCB_F32);
   return st;
 }
 
@@ -541,7 +569,7 @@ static int32_t collect_device(rcb_esn* esn, const void* u_dev, int64_t Tc, int64
     zin = zout;
     c_off += L.n;
   }
-  return RCB_OK;
+  return note_nonfinite(ctx, hT_dev, esn->sumN * Bc, esn->desc.data_dtype);
 }
 
 }  // namespace rcb
@@ -607,6 +635,7 @@ int32_t rcb_ctx_destroy(rcb_ctx* ctx) {
   delete[] p;
   for (int i = 0; i < SCR_COUNT; ++i) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->d_nonfinite) cudaFree(ctx->d_nonfinite);
   for (cudaStream_t& s : ctx->aux_streams)
     if (s) { cudaStreamDestroy(s); s = nullptr; }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -643,6 +672,18 @@ int32_t rcb_ctx_last_refine(rcb_ctx* ctx, int32_t* steps, double* rel) {
   if (!ctx) return fail(RCB_ERR_ARGUMENT, "ctx is NULL");
   if (steps) *steps = ctx->refine_steps;
   if (rel) *rel = ctx->refine_last;
+  return RCB_OK;
+}
+
+int32_t rcb_ctx_last_nonfinite(rcb_ctx* ctx, int32_t* flag) {
+  if (!ctx || !flag) return fail(RCB_ERR_ARGUMENT, "NULL argument");
+  *flag = 0;
+  if (!ctx->d_nonfinite) return RCB_OK;
+  RCB_CUDA(cudaSetDevice(ctx->device));
+  int h = 0;
+  RCB_CUDA(cudaMemcpyAsync(&h, ctx->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *flag = h ? 1 : 0;
   return RCB_OK;
 }
 

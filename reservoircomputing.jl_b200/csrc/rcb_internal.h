@@ -182,6 +182,7 @@ struct rcb_ctx {
   size_t smem_optin = 0;
   int64_t launches = 0;
   char last_kernel[96] = "";
+  int* d_nonfinite = nullptr;     // device flag: the carry of a recurrence of the current call held a NaN / Inf (rcb_ctx_last_nonfinite)
   double gram_lambda_hint = -1.0;  // regularisation PER SAMPLE (lambda / number of samples) the accumulator being built will be
                                    // solved with (< 0: unknown).  RCB_GRAM_AUTO takes the tensor-core Gram — 22-bit fixed-point
                                    // states — only when it is >= RCB_TENSOR_MIN_LAMBDA_PER_SAMPLE; gram_int8.cu skips its

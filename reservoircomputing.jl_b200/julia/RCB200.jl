@@ -90,6 +90,18 @@ const DEFAULT_CTX = Ref{Union{Nothing, Context}}(nothing)
 ctx() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Context(0)))
 
 """
+    diverged(c::Context = ctx()) -> Bool
+
+`true` if the carry of a recurrence of the most recent call held a NaN / Inf (`rcb_ctx_last_nonfinite`): a diverged
+reservoir, which the reference path only shows as NaN weights later on.
+"""
+function diverged(c::Context = ctx())
+    f = Ref{Int32}(0)
+    check(ccall((:rcb_ctx_last_nonfinite, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), c.ptr, f))
+    return f[] != 0
+end
+
+"""
     B200Reservoir(cell)
 
 Marker wrapper selecting the CUDA path: `ESN(...; )` is built as usual and its `reservoir`

@@ -67,6 +67,7 @@ SIGNATURES = {
     "rcb_ctx_last_kernel": (_I32, [_P, C.c_char_p, _I32]),
     "rcb_ctx_last_kernel_ms": (_I32, [_P, _I32, C.POINTER(C.c_float)]),
     "rcb_ctx_last_refine": (_I32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
+    "rcb_ctx_last_nonfinite": (_I32, [_P, C.POINTER(C.c_int32)]),
     "rcb_esn_create": (_I32, [_P, C.POINTER(EsnDesc), C.POINTER(LayerDesc), C.POINTER(_P)]),
     "rcb_esn_destroy": (_I32, [_P]),
     "rcb_esn_feature_dims": (_I32, [_P, C.POINTER(_I32)]),

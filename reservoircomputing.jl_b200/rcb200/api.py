@@ -212,6 +212,12 @@ class Device:
         check(lib().rcb_ctx_last_refine(self.handle, C.byref(n), C.byref(r)))
         return int(n.value), float(r.value)
 
+    def last_nonfinite(self) -> bool:
+        """True if the carry of a recurrence of the most recent call held a NaN / Inf (a diverged reservoir)."""
+        f = C.c_int32(0)
+        check(lib().rcb_ctx_last_nonfinite(self.handle, C.byref(f)))
+        return bool(f.value)
+
     def last_kernel(self) -> str:
         buf = C.create_string_buffer(128)
         check(lib().rcb_ctx_last_kernel(self.handle, buf, 128))

@@ -254,3 +254,28 @@ def test_tensor_gram_reports_non_finite_states(R):
                 R.fit_readout(R.RidgeRegression(1e-3), Zb, Y, gram_mode=mode)
     W = R.fit_readout(R.RidgeRegression(1e-3), Z, Y, gram_mode=R.GRAM_TENSOR)   # the clean data still fit
     assert np.all(np.isfinite(W))
+
+
+def test_nonfinite_carry_flag(R):
+    """SURVEY 5 (failure detection): a reservoir that diverges (identity activation, spectral radius 1.6) leaves Inf / NaN in the
+    carry; the context reports it after collectstates and after a fused train, and reports nothing for a healthy reservoir."""
+    rng = np.random.default_rng(3)
+    N, T = 256, 700
+    data = np.asfortranarray(rng.standard_normal((3, T)).astype(np.float32))
+    target = np.asfortranarray(rng.standard_normal((3, T)).astype(np.float32))
+    dev = R.default_device()
+    good = R.ESN(3, N, 3, init_reservoir=R.rand_sparse(radius=0.9, sparsity=6 / N))
+    ps, st = R.setup(rng, good)
+    R.collectstates(good, data, ps, st)
+    assert not dev.last_nonfinite()
+    bad = R.ESN(3, N, 3, R.identity, init_reservoir=R.rand_sparse(radius=1.6, sparsity=6 / N), leak_coefficient=1.0)
+    psb, stb = R.setup(rng, bad)
+    states, _ = R.collectstates(bad, data, psb, stb)
+    assert not np.all(np.isfinite(states[:, -1]))
+    assert dev.last_nonfinite()
+    with pytest.raises(R.NumericError):
+        R.train(bad, data, target, psb, stb, objective=R.RidgeRegression(1e-3))
+    assert dev.last_nonfinite()
+    R.collectstates(good, data, ps, st)           # the flag belongs to the most recent call
+    assert not dev.last_nonfinite()
+
