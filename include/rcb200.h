@@ -326,7 +326,9 @@ RCB_API int32_t rcb_train_partial(rcb_esn* esn, const void* u, const void* targe
  * in `lambdas`: the recurrence and the Gram run once per member, the FP64 Cholesky once per (member, lambda).
  *   W_out  d_out x F x n_lambda x B Float64 (member slowest).  Members are independent: shard them across GPUs with
  *          no collective.  Same error conventions as rcb_train; a (member, lambda) system that is not
- *          positive definite -> RCB_ERR_NUMERIC. */
+ *          positive definite -> RCB_ERR_NUMERIC.  A large host W_out is touched (zero-filled page by page) by a helper thread
+ *          while the GPU works, so that the final copy does not pay the page faults of a fresh allocation: its contents
+ *          are undefined until the call returns RCB_OK. */
 RCB_API int32_t rcb_train_members(rcb_esn* esn, const void* u, const void* targets, int32_t targets_dtype, int64_t T, int64_t B,
                           int64_t washout, int32_t n_lambda, const double* lambdas, int32_t gram_mode, const void* h0,
                           double* W_out, void* hT_out);
