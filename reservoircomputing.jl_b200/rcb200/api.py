@@ -1106,6 +1106,14 @@ def train_time_chunked(rc, train_data, target_data, ps, st, *, objective: RidgeR
     return addreadout(rc, W, ps, _store_carry(rc, st, cell_sts, hT, True))
 
 
+def _tile_members(a3, B):
+    """A shared (d, T, 1) series as one (d, T) block per member in the library's column-major layout — one broadcast write
+    (np.repeat + asfortranarray took 23 ms per 15 MB array in config 5, this takes 1 ms)."""
+    out = np.empty((a3.shape[0], a3.shape[1], B), dtype=a3.dtype, order="F")
+    out[...] = a3
+    return out
+
+
 def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambdas, washout: int = 0,
                    device: Optional[Device] = None, gram_mode=L.GRAM_AUTO):
     """Hyper-parameter / ensemble sweep (BASELINE config 5): member b runs the SAME reservoir with W * w_scale[b] and leak
@@ -1124,16 +1132,10 @@ def train_ensemble(rc, train_data, target_data, ps, st, *, w_scale, leak, lambda
     y3, _ = _as3d(target_data)
     if y3.dtype not in (np.float32, np.float64):
         y3 = np.asfortranarray(y3.astype(np.float64))
-
-    def tile_members(a3):   # shared series: one (d, T) block per member, written once in the library's layout
-        out = np.empty((a3.shape[0], a3.shape[1], B), dtype=a3.dtype, order="F")
-        out[...] = a3
-        return out
-
     if d3.shape[2] == 1 and B > 1:
-        d3 = tile_members(d3)
+        d3 = _tile_members(d3, B)
     if y3.shape[2] == 1 and B > 1:
-        y3 = tile_members(y3)
+        y3 = _tile_members(y3, B)
     _, T, Bd = d3.shape
     if Bd != B or y3.shape[2] != B:
         raise DimensionMismatch(f"{B} members but data has {Bd} and targets {y3.shape[2]} sequences")

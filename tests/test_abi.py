@@ -226,3 +226,15 @@ def test_gather_schedule_invariants(R, n, k, nthreads):
             assert wb <= 1.5 * wbi + 8                                   # rows of a half-warp mostly distinct mod 16 (write-back conflicts)
         else:
             assert wf64 >= ideal64
+
+
+def test_tile_members_layout():
+    """Host logic of the ensemble sweep: a shared series becomes one column-major (d, T) block per member."""
+    from rcb200.api import _tile_members
+
+    a = np.asfortranarray(np.arange(3 * 7, dtype=np.float32).reshape(3, 7, 1))
+    out = _tile_members(a, 5)
+    assert out.shape == (3, 7, 5) and out.flags.f_contiguous and out.dtype == np.float32
+    assert np.array_equal(out, np.repeat(a, 5, axis=2))
+    assert np.array_equal(np.frombuffer(out.tobytes(order="A"), np.float32)[:21], a.ravel(order="F"))
+
